@@ -16,11 +16,14 @@
  */
 #define _GNU_SOURCE
 #include <setjmp.h>
+#include <signal.h>
+#include <sys/time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
 #include <unistd.h>
+#include <fcntl.h>
 
 #include "pip.h"
 
@@ -29,22 +32,52 @@ struct ref_cell { int flags; long long param1, param2; };
 extern struct ref_cell *sol_space_dp;
 extern int verbose_dp, deepest_cut_dp;
 
-static jmp_buf pipref_env;
-static int pipref_armed = 0;
+static sigjmp_buf pipref_env;
+static volatile int pipref_armed = 0;
+static int pipref_timeout_ms = 0;
+#define setjmp(e) sigsetjmp(e, 1)
 
 void pipref_exit_hook(int code)
 {
-  if (pipref_armed) longjmp(pipref_env, 1000 + code);
+  if (pipref_armed) siglongjmp(pipref_env, 1000 + code);
   _exit(code);
+}
+
+/* arithmetic faults of the reference (division by zero after a silent wrap) and run-away
+ * problems become statuses too: 2000 = SIGFPE, 2001 = SIGSEGV, 3000 = time limit */
+static void on_signal(int sig)
+{
+  if (!pipref_armed) _exit(128 + sig);
+  siglongjmp(pipref_env, sig == SIGFPE ? 2000 : sig == SIGSEGV ? 2001 : 3000);
+}
+void pipref_set_timeout_ms(int ms) { pipref_timeout_ms = ms; }
+static void guard_on(void)
+{
+  struct itimerval it;
+  static int installed = 0;
+  if (!installed) { signal(SIGFPE, on_signal); signal(SIGSEGV, on_signal); signal(SIGALRM, on_signal); installed = 1; }
+  if (pipref_timeout_ms <= 0) return;
+  memset(&it, 0, sizeof it);
+  it.it_value.tv_sec = pipref_timeout_ms / 1000;
+  it.it_value.tv_usec = (pipref_timeout_ms % 1000) * 1000;
+  setitimer(ITIMER_REAL, &it, NULL);
+}
+static void guard_off(void)
+{
+  struct itimerval it;
+  if (pipref_timeout_ms <= 0) return;
+  memset(&it, 0, sizeof it);
+  setitimer(ITIMER_REAL, &it, NULL);
 }
 
 static int saved_stderr = -1, saved_stdout = -1;
 static void quiet_begin(void)
 {
   fflush(stdout); fflush(stderr);
+  static int devnull = -1;
+  if (devnull < 0) devnull = open("/dev/null", O_WRONLY);
   saved_stderr = dup(2); saved_stdout = dup(1);
-  FILE *n = fopen("/dev/null", "w");
-  if (n) { dup2(fileno(n), 2); dup2(fileno(n), 1); fclose(n); }
+  if (devnull >= 0) { dup2(devnull, 2); dup2(devnull, 1); }
 }
 static void quiet_end(void)
 {
@@ -80,10 +113,12 @@ int pipref_traiter(int nvar, int nparm, int ni, int nc, int bigparm, int nq,
   rc = setjmp(pipref_env);
   if (rc) {
     pipref_armed = 0;
+    guard_off();
     quiet_end();
     after_fatal();
     return rc;
   }
+  guard_on();
   hq = tab_hwm_dp();
   ineq = tab_alloc_dp(ni, ncol, nvar);              /* as tab_get_dp, source/tab.c:231-242 */
   for (i = 0; i < ni; i++) {
@@ -119,6 +154,7 @@ int pipref_traiter(int nvar, int nparm, int ni, int nc, int bigparm, int nq,
   }
   tab_reset_dp(hq);
   pipref_armed = 0;
+  guard_off();
   quiet_end();
   return non_vide ? 0 : 1;
 }
@@ -179,10 +215,11 @@ int pipref_solve_ser(int dom_rows, int dom_cols, const long long *dom,
   quiet_begin();
   rc = setjmp(pipref_env);
   if (rc) {
-    pipref_armed = 0; quiet_end(); after_fatal();
+    pipref_armed = 0; guard_off(); quiet_end(); after_fatal();
     if (ser_n) *ser_n = 0;
     return rc;                       /* matrices leak on the fatal path: test harness only */
   }
+  guard_on();
   D = mk_matrix(dom_rows, dom_cols, dom);
   if (has_ctx) C = mk_matrix(ctx_rows, ctx_cols, ctx);
   o = pip_options_init_dp();
@@ -190,6 +227,7 @@ int pipref_solve_ser(int dom_rows, int dom_cols, const long long *dom,
   o->Maximize = opts[4]; o->Urs_parms = opts[5]; o->Urs_unknowns = opts[6]; o->Compute_dual = opts[7];
   q = pip_solve_dp(D, C, bg, o);
   pipref_armed = 0;
+  guard_off();
   quiet_end();
   if (ser) { ser_out = ser; ser_cap = cap; ser_len = 0; ser_quast(q); if (ser_n) *ser_n = ser_len; }
   if (text && text_cap > 0) {
@@ -247,6 +285,7 @@ double pipref_bench_dense(long first, long count,
   o->Nq = opts[0]; o->Verbose = -1; o->Simplify = opts[2]; o->Deepest_cut = opts[3];
   o->Maximize = opts[4]; o->Urs_parms = opts[5]; o->Urs_unknowns = opts[6]; o->Compute_dual = opts[7];
   quiet_begin();
+  guard_on();
   for (i = first; i < first + count; i++) {
     PipQuast_dp *q = NULL; int rc;
     size_t dsz = (size_t)dom_rows * dom_cols, csz = (size_t)ctx_rows * ctx_cols;
