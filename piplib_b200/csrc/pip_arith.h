@@ -1,0 +1,106 @@
+/* Exact integer helpers of the solver core (wrapping int64, the reference's _dp width).
+ *
+ * Semantics follow include/piplib/piplib.h:128-169 and source/integrer.c:41-89 of the reference:
+ *   gcd      = llabs(euclid(a, b)), gcd(0,0) = 0
+ *   mod      = C remainder, +|b| when negative  (piplib_llmod_xx)
+ *   floor_q  = (a - mod(a,b)) / b               (piplib_int_floor_div_q)
+ *   div      = C truncating division (used where the division is exact)
+ *   bitlen   = bit length of |x|, 0 -> 1        (piplib_lllog2_xx)
+ * The implementations are GPU-shaped: 32-bit fast paths (there is no integer divider on the SM;
+ * a 64-bit '/' is a ~100-instruction subroutine) and exact division by a modular inverse.
+ */
+#ifndef PIP_ARITH_H
+#define PIP_ARITH_H
+
+#include "pip_types.h"
+#include "simt.h"
+
+PIP_HD pip_u64 pip_uabs(pip_i64 v) { return v < 0 ? 0ull - (pip_u64)v : (pip_u64)v; }
+
+PIP_HD pip_u64 pip_gcd_u64(pip_u64 a, pip_u64 b)
+{
+  while (b) {
+    if (((a | b) >> 32) == 0) {            /* both fit 32 bits: stay on the 32-bit path */
+      unsigned x = (unsigned)a, y = (unsigned)b;
+      while (y) { unsigned r = x % y; x = y; y = r; }
+      return x;
+    }
+    pip_u64 r = a % b; a = b; b = r;
+  }
+  return a;
+}
+PIP_HD pip_i64 pip_gcd(pip_i64 a, pip_i64 b) { return (pip_i64)pip_gcd_u64(pip_uabs(a), pip_uabs(b)); }
+
+/* C truncating division, b != 0 */
+PIP_HD pip_i64 pip_div(pip_i64 a, pip_i64 b)
+{
+  if (a == (pip_i64)(int)a && b == (pip_i64)(int)b && (int)a != (-2147483647 - 1))
+    return (pip_i64)((int)a / (int)b);
+  return a / b;
+}
+/* C remainder, b != 0 */
+PIP_HD pip_i64 pip_rem(pip_i64 a, pip_i64 b)
+{
+  if (a == (pip_i64)(int)a && b == (pip_i64)(int)b && (int)a != (-2147483647 - 1))
+    return (pip_i64)((int)a % (int)b);
+  return a % b;
+}
+PIP_HD pip_i64 pip_mod(pip_i64 a, pip_i64 b)
+{
+  pip_i64 m = pip_rem(a, b);
+  if (m < 0) m += (b < 0 ? -b : b);
+  return m;
+}
+PIP_HD pip_i64 pip_floor_q(pip_i64 a, pip_i64 b) { return pip_div(a - pip_mod(a, b), b); }
+
+PIP_HD int pip_bitlen(pip_i64 x)
+{
+  pip_u64 u = pip_uabs(x);
+  int n = 0;
+  while (u >> 32) { u >>= 32; n += 32; }
+  unsigned w = (unsigned)u;
+  while (w) { w >>= 1; n++; }
+  return n ? n : 1;
+}
+
+/* multiplicative inverse of an odd d modulo 2^64 (Newton: each step doubles the valid bits) */
+PIP_HD pip_u64 pip_inv_odd(pip_u64 d)
+{
+  pip_u64 x = (3ull * d) ^ 2ull;     /* 5 bits */
+  x *= 2ull - d * x;                 /* 10 */
+  x *= 2ull - d * x;                 /* 20 */
+  x *= 2ull - d * x;                 /* 40 */
+  x *= 2ull - d * x;                 /* 80 */
+  return x;
+}
+
+/* exact division z / g for g > 0 dividing z: shift out the power of two, multiply by the
+ * inverse of the odd part.  Bit-identical to C '/' whenever the division is exact. */
+struct PipExactDiv {
+  pip_u64 inv;
+  int shift;
+};
+PIP_HD PipExactDiv pip_exact_prepare(pip_i64 g)
+{
+  PipExactDiv e;
+  pip_u64 u = (pip_u64)g;
+  int s = 0;
+  while ((u & 1ull) == 0ull) { u >>= 1; s++; }   /* g != 0 */
+  e.shift = s;
+  e.inv = pip_inv_odd(u);
+  return e;
+}
+PIP_HD pip_i64 pip_exact_apply(pip_i64 z, const PipExactDiv &e)
+{
+  return (pip_i64)((pip_u64)(z >> e.shift) * e.inv);
+}
+
+/* does the exact product a*b fit in int64? (informative overflow flag only) */
+PIP_DEV bool pip_mul_wraps(pip_i64 a, pip_i64 b)
+{
+  pip_i64 lo = (pip_i64)((pip_u64)a * (pip_u64)b);
+  pip_i64 hi = pip_mulhi(a, b);
+  return hi != (lo >> 63);
+}
+
+#endif

@@ -1,0 +1,883 @@
+/* Warp-per-problem parametric dual simplex + Gomory cuts (the PipLib solver core), sm_100a.
+ *
+ * One warp owns one problem.  The problem's whole working set -- tableau, context, the tableau
+ * of the current compatibility sub-solve, cut scratch -- lives in a per-warp arena (shared
+ * memory for size class S, global memory for class G).  Lanes map to row *positions*: each
+ * lane updates its own row during a pivot (the running-gcd early-out of the reference stays a
+ * per-lane scalar loop), and every order-dependent scan (first negative row, lexicographic
+ * column choice, sign classification) is one ballot + find-first-set per 32 positions, so the
+ * reference's position order is preserved bit for bit.
+ *
+ * The reference's recursion (source/traiter.c:628-791: traiter -> compa_test -> traiter and
+ * traiter -> traiter at a split) is flattened into one state machine:
+ *   - a compatibility sub-solve is a "call" that switches the current tableau descriptor to
+ *     the sub tableau and returns to one of three sites (context check, +test, -test);
+ *   - a split pushes the ELSE continuation (tableau + context snapshot) on a per-warp frame
+ *     stack in global memory and carries on with the THEN branch in place; a finished branch
+ *     pops the stack.  The solution cells come out in the reference's pre-order.
+ *
+ * Tableau model: position k has a packed word fl[k] = flag | link << 8,
+ * link = owned column for a Unit position, storage slot otherwise; den[k] is the row's common
+ * denominator.  Exactly ni slots are live at any time ([0, ni)); a pivot hands the pivot row's
+ * slot to the Unit position that owned the pivot column (source/traiter.c:503-516).
+ *
+ * Every function cites the reference lines it restates; none of it is derived from the
+ * reference's code structure (no malloc'd Tableau, no pointer-swapped rows, no recursion).
+ */
+#ifndef PIP_SOLVER_H
+#define PIP_SOLVER_H
+
+#include "pip_arith.h"
+#include "pip_types.h"
+#include "simt.h"
+
+#define PIP_FLAG(x) ((x) & 0xff)
+#define PIP_LINK(x) ((x) >> 8)
+#define PIP_MKFL(f, l) ((f) | ((l) << 8))
+
+struct PipTab {          /* warp-uniform, lives in registers */
+  int den, fl, data, det;   /* word offsets into the arena */
+  int stride, pcap, rcap;   /* words per slot, position capacity, slot capacity */
+  int nvar, nparm, ni;
+  int ldet;
+};
+
+struct PipStats {
+  unsigned pivots, cuts, subsolves, splits, max_rows, max_cols;
+  unsigned long long elem_updates;
+};
+
+/* capacity slack per level: {new parameters, main cut rows, extra context rows, sub cut rows} */
+PIP_DEV void pip_slack(int level, int &dp, int &dr, int &dx, int &ds)
+{
+  if (level >= 3) {
+    const int k = level - 3 > 5 ? 5 : level - 3;      /* classes G3..G8 grow geometrically */
+    dp = 6 << k; dr = 64 << (2 * k); dx = 24 << (2 * k); ds = 24 << (2 * k);
+  }
+  else if (level == 2) { dp = 3; dr = 12; dx = 10; ds = 10; }
+  else if (level == 1) { dp = 2; dr = 6; dx = 6; ds = 6; }
+  else { dp = 1; dr = 2; dx = 3; ds = 3; }
+}
+
+struct PipLayout {
+  PipTab m, s;
+  int ctx, cstride, crcap;
+  int cut, tmp;
+  int total;
+};
+
+/* Carve the arena for one problem.  Returns false when even this slack level does not fit. */
+PIP_DEV bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level, int words, PipLayout &L)
+{
+  int dp, dr, dx, ds;
+  pip_slack(level, dp, dr, dx, ds);
+  const bool integer = (flags & PIP_F_INT) != 0;
+  const bool ctxful = nparm > 0 || nc > 0;
+  if (!(integer && nparm > 0)) dp = 0;
+  if (!integer) dr = 0;
+  if (!ctxful) { dx = 0; ds = 0; }
+  int C = (nvar + 1 + nparm + dp) | 1;
+  int R = ni + dr, Pm = nvar + R;
+  int XC = (nparm + dp + 1) | 1;
+  int XR = ctxful ? nc + dx + 2 * dp : 0;
+  int SR = ctxful ? XR + 1 + ds : 0;
+  int SP = ctxful ? nparm + dp + SR : 0;
+  int o = 0;
+  L.m.det = o; o += 4;
+  L.s.det = o; o += 4;
+  L.cut = o; o += (C + 3) & ~1;
+  L.m.den = o; o += Pm;
+  L.m.fl = o; o += (Pm + 1) / 2;
+  L.tmp = o; o += ((Pm > SP ? Pm : SP) + 1) / 2;
+  L.m.data = o; o += R * C;
+  L.ctx = o; o += XR * XC;
+  L.s.den = o; o += SP;
+  L.s.fl = o; o += (SP + 1) / 2;
+  L.s.data = o; o += SR * XC;
+  L.total = o;
+  L.m.stride = C; L.m.pcap = Pm; L.m.rcap = R;
+  L.m.nvar = nvar; L.m.nparm = nparm; L.m.ni = ni; L.m.ldet = 1;
+  L.s.stride = XC; L.s.pcap = SP; L.s.rcap = SR;
+  L.s.nvar = nparm; L.s.nparm = 0; L.s.ni = 0; L.s.ldet = 1;
+  L.cstride = XC; L.crcap = XR;
+  return o <= words;
+}
+
+/* ---- small accessors ------------------------------------------------------------------- */
+PIP_DEV int *pip_fl(pip_i64 *B, const PipTab &T) { return (int *)(B + T.fl); }
+PIP_DEV pip_i64 *pip_den(pip_i64 *B, const PipTab &T) { return B + T.den; }
+PIP_DEV pip_i64 *pip_row(pip_i64 *B, const PipTab &T, int slot) { return B + T.data + slot * T.stride; }
+
+/* chercher_xx, source/traiter.c:39-44: first position in [from, n) whose flag meets the mask */
+PIP_DEV int pip_first_flag(pip_i64 *B, const PipTab &T, int mask, int from, int n)
+{
+  const int *fl = pip_fl(B, T);
+  const int lane = W::lane();
+  for (int base = from & ~31; base < n; base += 32) {
+    int k = base + lane;
+    bool p = (k >= from && k < n) && ((fl[k] & mask) != 0);
+    unsigned m = W::ballot(p);
+    if (m) return base + pip_ffs(m) - 1;
+  }
+  return n;
+}
+
+/* tab_simplify_xx, source/tab.c:396-427 on `rows` rows of `width` words (lane = row) */
+PIP_DEV bool pip_simplify_rows(pip_i64 *base, int rows, int stride, int width, int cst)
+{
+  bool fault = false;
+  for (int r = W::lane(); r < rows; r += 32) {
+    pip_i64 *row = base + r * stride;
+    pip_i64 g = 0;
+    for (int j = 0; j < width; j++) {
+      if (j == cst) continue;
+      g = pip_gcd(g, row[j]);
+      if (g == 1) break;
+    }
+    if (g == 0 || g == 1) continue;
+    for (int j = 0; j < width; j++)
+      row[j] = (j == cst) ? pip_floor_q(row[j], g) : pip_div(row[j], g);
+  }
+  return fault;
+}
+
+/* tab_sort_rows_xx, source/traiter.c:556-623.  size = max_j |(int)(double(T[i][j])/double(d))|
+ * stored as float; an out-of-range (int) conversion is INT_MIN on the reference's x86-64 and
+ * never raises the maximum.  Selection sort by first minimum strictly below smax. */
+PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
+{
+  const int lane = W::lane();
+  const int nl = T.nvar + T.ni;
+  int *fl = pip_fl(B, T);
+  pip_i64 *den = pip_den(B, T);
+  float *sz = (float *)(B + tmpoff);
+  unsigned smax_u = 0;
+  for (int k = T.nvar + lane; k < nl; k += 32) {
+    int f = fl[k];
+    if (f & PIP_UNIT) continue;
+    const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+    pip_i64 d = den[k];
+    unsigned s = 0;
+    if (d == 1) {
+      for (int j = 0; j < T.nvar; j++) {
+        pip_u64 u = pip_uabs(row[j]);
+        if (u < 2147483648ull && (unsigned)u > s) s = (unsigned)u;
+      }
+    } else {
+      double dd = pip_ll2d(d);
+      for (int j = 0; j < T.nvar; j++) {
+        double t = pip_ll2d(row[j]) / dd;
+        double a = t < 0 ? -t : t;
+        if (a < 2147483648.0) { unsigned v = (unsigned)(int)a; if (v > s) s = v; }
+      }
+    }
+    sz[k] = (float)(double)s;
+    if (s > smax_u) smax_u = s;
+  }
+  smax_u = W::redmax(smax_u);
+  const double smax = (double)smax_u;
+  W::sync();
+  for (int i = T.nvar; i < nl; i++) {
+    if (fl[i] & PIP_UNIT) continue;            /* uniform read */
+    unsigned best = 0xffffffffu;
+    int bestk = i;
+    for (int base = i & ~31; base < nl; base += 32) {
+      int k = base + lane;
+      unsigned key = 0xffffffffu;
+      if (k >= i && k < nl && !(fl[k] & PIP_UNIT)) {
+        float s = sz[k];
+        if ((double)s < smax) key = pip_f2u(s);
+      }
+      unsigned m = W::redmin(key);
+      if (m < best) {
+        best = m;
+        bestk = base + pip_ffs(W::ballot(key == m)) - 1;
+      }
+    }
+    if (best != 0xffffffffu && bestk != i) {
+      W::sync();
+      if (lane == 0) {
+        int f = fl[i]; fl[i] = fl[bestk]; fl[bestk] = f;
+        pip_i64 d = den[i]; den[i] = den[bestk]; den[bestk] = d;
+        float s = sz[i]; sz[i] = sz[bestk]; sz[bestk] = s;
+      }
+      W::sync();
+    }
+  }
+  W::sync();
+}
+
+/* exam_coef_xx, source/traiter.c:101-159.  Returns the first row proved negative or nl. */
+PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
+{
+  const int lane = W::lane();
+  const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
+  int *fl = pip_fl(B, T);
+  if (bigparm >= 0) {
+    for (int base = 0; base < nl; base += 32) {
+      int k = base + lane;
+      int f = k < nl ? fl[k] : 0;
+      bool unk = PIP_FLAG(f) == PIP_UNKNOWN;
+      pip_i64 v = unk ? pip_row(B, T, PIP_LINK(f))[bigparm] : 0;
+      unsigned mneg = W::ballot(unk && v < 0);
+      int first = mneg ? pip_ffs(mneg) - 1 : 32;
+      if (unk && v > 0 && lane < first) fl[k] = PIP_MKFL(PIP_PLUS, PIP_LINK(f));
+      if (mneg) {
+        if (lane == first) fl[k] = PIP_MKFL(PIP_MINUS, PIP_LINK(f));
+        W::sync();
+        return base + first;
+      }
+    }
+    W::sync();
+  }
+  for (int base = 0; base < nl; base += 32) {
+    int k = base + lane;
+    int f = k < nl ? fl[k] : 0;
+    bool unk = PIP_FLAG(f) == PIP_UNKNOWN;
+    int ff = PIP_ZERO;
+    if (unk) {
+      const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+      for (int j = T.nvar + 1; j < ncol; j++) {
+        pip_i64 v = row[j];
+        int fff = v < 0 ? PIP_MINUS : v > 0 ? PIP_PLUS : PIP_ZERO;
+        if (fff != PIP_ZERO && fff != ff) {
+          if (ff == PIP_ZERO) ff = fff;
+          else { ff = PIP_UNKNOWN; break; }
+        }
+      }
+      pip_i64 c = row[T.nvar];
+      int fff = c < 0 ? PIP_MINUS : c > 0 ? PIP_PLUS : PIP_ZERO;
+      if (ff == PIP_PLUS) { if (fff == PIP_MINUS) ff = PIP_UNKNOWN; }
+      else if (ff == PIP_ZERO) ff = fff;
+      else if (ff == PIP_MINUS) { if (fff != PIP_MINUS) ff = PIP_UNKNOWN; }
+    }
+    unsigned mneg = W::ballot(unk && ff == PIP_MINUS);
+    int first = mneg ? pip_ffs(mneg) - 1 : 32;
+    if (unk && lane <= first) fl[k] = PIP_MKFL(ff, PIP_LINK(f));
+    if (mneg) { W::sync(); return base + first; }
+  }
+  W::sync();
+  return nl;
+}
+
+/* valeur_xx, source/traiter.c:246-252 */
+PIP_DEV pip_i64 pip_entry(pip_i64 *B, const PipTab &T, int f, pip_i64 d, int j)
+{
+  if (f & PIP_UNIT) return PIP_LINK(f) == j ? d : 0;
+  return pip_row(B, T, PIP_LINK(f))[j];
+}
+
+/* choisir_piv_xx, source/traiter.c:297-341: lexicographic pivot column.  For each candidate
+ * column the difference x_k = pivot*val(k,j) - val(k,pivj)*foo is evaluated for 32 positions at
+ * a time; the first non-zero x in position order decides. */
+PIP_DEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, pip_i64 &pivot_out)
+{
+  const int lane = W::lane();
+  const int nl = T.nvar + T.ni;
+  const int *fl = pip_fl(B, T);
+  const pip_i64 *den = pip_den(B, T);
+  const pip_i64 *prow = pip_row(B, T, PIP_LINK(fl[pivi]));
+  int pivj = -1;
+  pip_i64 pivot = 0;
+  for (int cb = 0; cb < T.nvar; cb += 32) {
+    int jc = cb + lane;
+    unsigned cand = W::ballot(jc < T.nvar && prow[jc] > 0);
+    while (cand) {
+      int j = cb + pip_ffs(cand) - 1;
+      cand &= cand - 1;
+      pip_i64 foo = prow[j];
+      if (pivj < 0) { pivj = j; pivot = foo; continue; }
+      bool neg = false;
+      for (int base = 0; base < nl; base += 32) {
+        int k = base + lane;
+        pip_i64 x = 0;
+        if (k < nl) {
+          int f = fl[k];
+          pip_i64 a, b;
+          if (f & PIP_UNIT) {
+            int u = PIP_LINK(f);
+            pip_i64 d = den[k];
+            a = (u == j) ? d : 0;
+            b = (u == pivj) ? d : 0;
+          } else {
+            const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+            a = row[j]; b = row[pivj];
+          }
+          x = (pip_i64)((pip_u64)pivot * (pip_u64)a - (pip_u64)b * (pip_u64)foo);
+        }
+        unsigned nz = W::ballot(x != 0);
+        if (nz) {
+          unsigned ng = W::ballot(x < 0);
+          neg = (ng >> (pip_ffs(nz) - 1)) & 1u;
+          break;
+        }
+      }
+      if (neg) { pivj = j; pivot = foo; }
+    }
+  }
+  pivot_out = pivot;
+  return pivj;
+}
+
+/* pivoter_xx, source/traiter.c:345-548.
+ * returns 0 done, -1 no positive coefficient (infeasible), or a PIP_ST_* fatal status */
+PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
+{
+  const int lane = W::lane();
+  const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
+  int *fl = pip_fl(B, T);
+  pip_i64 *den = pip_den(B, T);
+  pip_i64 pivot;
+  const int pivj = pip_choose_column(B, T, pivi, pivot);
+  if (pivj < 0) return -1;
+
+  const int pslot = PIP_LINK(fl[pivi]);
+  pip_i64 *prow = pip_row(B, T, pslot);
+  const pip_i64 dpiv = den[pivi];
+  /* determinant bookkeeping = the overflow verdict, source/traiter.c:394-447 (uniform) */
+  {
+    pip_i64 d = pip_gcd(pivot, dpiv);
+    if (d == 0) return PIP_ST_FAULT;
+    pip_i64 ppivot = pip_div(pivot, d), dppiv = pip_div(dpiv, d);
+    pip_i64 *det = B + T.det;
+    pip_i64 dv[PIP_MAX_DET];
+    for (int i = 0; i < PIP_MAX_DET; i++) dv[i] = i < T.ldet ? det[i] : 0;
+    for (int i = 0; i < PIP_MAX_DET; i++) {
+      if (i >= T.ldet) break;
+      pip_i64 g = pip_gcd(dv[i], dppiv);
+      if (g == 0) return PIP_ST_FAULT;
+      dv[i] = pip_div(dv[i], g);
+      dppiv = pip_div(dppiv, g);
+    }
+    if (dppiv != 1) return PIP_ST_FATAL + 1;            /* "Integer overflow" */
+    int i = 0;
+    const int bp = pip_bitlen(ppivot);
+    for (; i < T.ldet; i++)
+      if (pip_bitlen(dv[i]) + bp < 64) { dv[i] = (pip_i64)((pip_u64)dv[i] * (pip_u64)ppivot); break; }
+    if (i >= T.ldet) {
+      T.ldet++;
+      if (T.ldet >= PIP_MAX_DET) return PIP_ST_FATAL + 1; /* "Integer overflow : 4" */
+      dv[i] = ppivot;
+    }
+    W::sync();
+    if (lane == 0) for (int k = 0; k < PIP_MAX_DET; k++) if (k < T.ldet) det[k] = dv[k];
+  }
+  st.pivots++;
+  if ((unsigned)nl > st.max_rows) st.max_rows = nl;
+  if ((unsigned)ncol > st.max_cols) st.max_cols = ncol;
+  st.elem_updates += (unsigned long long)(T.ni - 1) * ncol;
+
+  /* rank-1 update of every stored row but the pivot row, source/traiter.c:467-502 */
+  bool fault = false;
+  for (int k = lane; k < nl; k += 32) {
+    if (k == pivi) continue;
+    int f = fl[k];
+    if (f & PIP_UNIT) continue;
+    pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+    pip_i64 foo = row[pivj];
+    const pip_i64 dk = den[k];
+    if (foo == 0 && dk == 1) continue;        /* the update is the identity and g stays 1 */
+    pip_i64 lpiv = pivot;
+    if (foo == 0) lpiv = 1;                    /* gcd(pivot,0) = pivot */
+    else {
+      pip_i64 d = pip_gcd(pivot, foo);
+      if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
+    }
+    pip_i64 g = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
+    const pip_i64 newden = g;
+    for (int j = 0; j < ncol; j++) {
+      pip_i64 z;
+      if (j == pivj) z = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
+      else z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
+      row[j] = z;
+      if (g != 1) g = pip_gcd(g, z);
+    }
+    if (g != 1) {
+      if (g == 0) { fault = true; continue; }
+      PipExactDiv e = pip_exact_prepare(g);
+      for (int j = 0; j < ncol; j++) row[j] = pip_exact_apply(row[j], e);
+      den[k] = pip_exact_apply(newden, e);
+    } else den[k] = newden;
+  }
+  if (W::any(fault)) return PIP_ST_FAULT;
+  W::sync();
+  /* the Unit position owning pivj takes the pivot row's slot, source/traiter.c:503-516 */
+  int ku = nl;
+  for (int base = 0; base < nl; base += 32) {
+    int k = base + lane;
+    int f = k < nl ? fl[k] : 0;
+    unsigned m = W::ballot((f & PIP_UNIT) && PIP_LINK(f) == pivj && k < nl);
+    if (m) { ku = base + pip_ffs(m) - 1; break; }
+  }
+  if (ku >= nl) return PIP_ST_FAULT;
+  for (int j = lane; j < ncol; j += 32) prow[j] = (j == pivj) ? dpiv : -prow[j];
+  W::sync();
+  if (lane == 0) {
+    fl[ku] = PIP_MKFL(PIP_PLUS, pslot); den[ku] = pivot;
+    fl[pivi] = PIP_MKFL(PIP_UNIT | PIP_ZERO, pivj); den[pivi] = 1;
+  }
+  W::sync();
+  /* re-flag from the sign of the pivot-column entry, source/traiter.c:518-529 */
+  for (int k = lane; k < nl; k += 32) {
+    int f = fl[k];
+    if (f & PIP_UNIT) continue;
+    int ff = PIP_FLAG(f);
+    pip_i64 v = pip_row(B, T, PIP_LINK(f))[pivj];
+    int fff = v < 0 ? PIP_MINUS : v == 0 ? PIP_ZERO : PIP_PLUS;
+    if (fff != PIP_ZERO && fff != ff) {
+      if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
+      else ff = PIP_UNKNOWN;
+      fl[k] = PIP_MKFL(ff, PIP_LINK(f));
+    }
+  }
+  W::sync();
+  return 0;
+}
+
+PIP_DEV void pip_put(PipCell *out, int idx, int kind, pip_i64 p1, pip_i64 p2)
+{
+  out[idx].kind = kind; out[idx].pad = 0; out[idx].p1 = p1; out[idx].p2 = p2;
+}
+
+/* solution_xx, source/traiter.c:255-271: 1 + nvar*(2+nparm) cells, lane-parallel */
+PIP_DEV void pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int at)
+{
+  const int per = T.nparm + 2, total = 1 + T.nvar * per;
+  const int *fl = pip_fl(B, T);
+  const pip_i64 *den = pip_den(B, T);
+  for (int c = W::lane(); c < total; c += 32) {
+    if (c == 0) { pip_put(out, at, PIP_C_LIST, T.nvar, 0); continue; }
+    int i = (c - 1) / per, r = (c - 1) % per;
+    if (r == 0) { pip_put(out, at + c, PIP_C_FORM, T.nparm + 1, 0); continue; }
+    int j = (r == per - 1) ? T.nvar : T.nvar + r;
+    int f = fl[i];
+    pip_i64 d = den[i];
+    pip_put(out, at + c, PIP_C_VAL, pip_entry(B, T, f, d, j), d);
+  }
+}
+
+/* has_cut_xx, source/integrer.c:230-254 (serial, one lane) */
+PIP_DEV bool pip_has_cut(const pip_i64 *ctx, int cstride, int nr, int nparm, int p, const pip_i64 *cut)
+{
+  for (int row = 0; row < nr; row++) {
+    const pip_i64 *r = ctx + row * cstride;
+    if (r[p] != cut[1 + nparm]) continue;
+    if (r[nparm] != cut[0]) continue;
+    int col;
+    for (col = p + 1; col < nparm; col++) if (r[col] != 0) break;
+    if (col < nparm) continue;
+    for (col = 0; col < p; col++) if (r[col] != cut[1 + col]) break;
+    if (col < p) continue;
+    return true;
+  }
+  return false;
+}
+
+/* find_parm_xx, source/integrer.c:258-291 (serial, one lane; cut = const, params, denominator) */
+PIP_DEV int pip_find_parm(const pip_i64 *ctx, int cstride, int nr, int nparm, pip_i64 *cut)
+{
+  if (cut[1 + nparm - 1] != 0) return -1;
+  cut[0] = cut[0] + cut[1 + nparm] - 1;
+  for (int p = nparm - 1; p >= 0; p--) {
+    if (cut[1 + p] != 0) break;
+    if (!pip_has_cut(ctx, cstride, nr, nparm, p, cut)) continue;
+    cut[0] = cut[0] + 1 - cut[1 + nparm];
+    for (int c = 0; c < nparm + 2; c++) cut[c] = -cut[c];
+    bool found = pip_has_cut(ctx, cstride, nr, nparm, p, cut);
+    for (int c = 0; c < nparm + 2; c++) cut[c] = -cut[c];
+    if (found) return p;
+    cut[0] = cut[0] + cut[1 + nparm] - 1;
+  }
+  cut[0] = cut[0] + 1 - cut[1 + nparm];
+  return -1;
+}
+
+/* The solver for one problem.  `B` is the warp's working arena (`words` words), `out` the
+ * warp's cell window (at least sol_size cells free), `stk` the warp's frame stack. */
+PIP_DEV void pip_solve_one(const PipProblem &P, const pip_i64 *in, pip_i64 *B, int words, int slack_level,
+                           PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
+                           int sol_size, int maxcol, int maxparm,
+                           int &status_out, int &ncell_out, PipStats &st)
+{
+  const int lane = W::lane();
+  const bool integer = (P.flags & PIP_F_INT) != 0;
+  PipLayout L;
+  int level_try = slack_level;
+  while (!pip_layout(P.nvar, P.nparm, P.ni, P.nc, P.flags, level_try, words, L)) {
+    if (--level_try < 0) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
+  }
+  if (P.flags & (PIP_F_DUAL | PIP_F_DEEPEST)) { status_out = PIP_ST_UNSUPPORTED; ncell_out = 0; return; }
+
+  PipTab T = L.m, M = L.m;       /* current tableau, saved main tableau while in a sub-solve */
+  int level = 0;                  /* 0 = main problem, 1 = compatibility / context sub-solve */
+  int nc = P.nc;
+  int ncell = 0, status = PIP_ST_OK;
+  int ret_site = 0, ci = 0, cplus = 0, critic = 0, pivi = 0, depth = 0;
+  bool feasible = false;
+  pip_i64 top = 0;
+  pip_i64 *ctx = B + L.ctx;
+  pip_i64 *cut = B + L.cut;
+  const int cstride = L.cstride;
+
+  /* ---- load: source/tab.c:222-248 (tab_get) + tab_simplify when an integer solution is wanted */
+  {
+    const int ncol = P.nvar + P.nparm + 1;
+    int *fl = pip_fl(B, T);
+    pip_i64 *den = pip_den(B, T);
+    for (int k = lane; k < P.nvar + P.ni; k += 32) {
+      if (k < P.nvar) { fl[k] = PIP_MKFL(PIP_UNIT, k); den[k] = 1; }
+      else { fl[k] = PIP_MKFL(PIP_UNKNOWN, k - P.nvar); den[k] = 1; }
+    }
+    for (int e = lane; e < P.ni * ncol; e += 32) {
+      int r = e / ncol, j = e - r * ncol;
+      pip_row(B, T, r)[j] = in[e];
+    }
+    const pip_i64 *cin = in + (pip_i64)P.ni * ncol;
+    for (int e = lane; e < P.nc * (P.nparm + 1); e += 32) {
+      int r = e / (P.nparm + 1), j = e - r * (P.nparm + 1);
+      ctx[r * cstride + j] = cin[e];
+    }
+    if (lane == 0) { B[L.m.det] = 1; B[L.s.det] = 1; }
+    W::sync();
+    if (integer) {
+      pip_simplify_rows(B + T.data, P.ni, T.stride, ncol, P.nvar);
+      pip_simplify_rows(ctx, P.nc, cstride, P.nparm + 1, P.nparm);
+      W::sync();
+    }
+  }
+
+  /* context emptiness check, source/piplib.c:818-826 / source/maind.c:199-204 */
+  if (nc > 0) { ret_site = 0; goto BUILD_SUB; }
+  goto ENTRY;
+
+BUILD_SUB:
+  /* expanser_xx(context, nparm, nc, nparm+1, nparm, extra, 0) (source/traiter.c:191-199,
+   * 211-218): nparm Unit positions, the nc context rows, and for ret_site 1/2 the tested row */
+  {
+    M = T;
+    PipTab S = L.s;
+    const int np = M.nparm;
+    const int extra = ret_site == 0 ? 0 : 1;
+    S.nvar = np; S.nparm = 0; S.ni = nc + extra; S.ldet = 1;
+    if (np + nc + extra > S.pcap || nc + extra > S.rcap || np + 1 > S.stride) { status = PIP_ST_CAPACITY; goto DONE; }
+    int *sfl = pip_fl(B, S);
+    pip_i64 *sden = pip_den(B, S);
+    for (int k = lane; k < np + nc + extra; k += 32) {
+      sfl[k] = k < np ? PIP_MKFL(PIP_UNIT, k) : PIP_MKFL(PIP_UNKNOWN, k - np);
+      sden[k] = 1;
+    }
+    for (int e = lane; e < nc * (np + 1); e += 32) {
+      int r = e / (np + 1), j = e - r * (np + 1);
+      pip_row(B, S, r)[j] = ctx[r * cstride + j];
+    }
+    if (extra) {
+      const int f = pip_fl(B, M)[ci];
+      const pip_i64 *row = pip_row(B, M, PIP_LINK(f));
+      pip_i64 *nr = pip_row(B, S, nc);
+      for (int j = lane; j <= np; j += 32) {
+        pip_i64 v = (j < np) ? row[M.nvar + 1 + j] : row[M.nvar];
+        if (ret_site == 1) { if (j == np && !critic) v -= 1; }
+        else { v = -v; if (j == np) v -= 1; }
+        nr[j] = v;
+      }
+    }
+    if (lane == 0) B[S.det] = 1;
+    T = S;
+    level = 1;
+    W::sync();
+  }
+
+ENTRY:
+  /* traiter_xx entry, source/traiter.c:643-656 (the private context copy is implicit) */
+  if (level) st.subsolves++;
+  pip_sort_rows(B, T, L.tmp);
+
+LOOP:
+  {
+    const int nl = T.nvar + T.ni;
+    pivi = pip_first_flag(B, T, PIP_MINUS, 0, nl);
+    if (pivi < nl) goto PIVOT;
+    pivi = pip_exam_coef(B, T, level ? -1 : P.bigparm);
+    if (pivi < nl) goto PIVOT;
+    if (T.nparm == 0) goto NONNEG;
+    /* compa_test_xx, source/traiter.c:162-243 */
+    if (T.nparm >= maxparm) { status = PIP_ST_FATAL + 1; goto DONE; }
+    ci = 0;
+  }
+
+COMPA_NEXT:
+  {
+    const int nl = T.nvar + T.ni;
+    ci = pip_first_flag(B, T, PIP_CRITIC | PIP_UNKNOWN, ci, nl);
+    if (ci >= nl) goto AFTER_COMPA;
+    const pip_i64 *row = pip_row(B, T, PIP_LINK(pip_fl(B, T)[ci]));
+    bool pos = false;
+    for (int j = lane; j < T.nvar; j += 32) pos = pos || row[j] > 0;
+    critic = W::any(pos) ? 0 : 1;
+    ret_site = 1;
+    goto BUILD_SUB;
+  }
+
+SUB_DONE:
+  {
+    /* the sub-solve's transient cells count against SOL_SIZE (source/sol.c:96-100) */
+    const int need = feasible ? 1 + 2 * T.nvar : 1;
+    if (ncell + need >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+    T = M;
+    level = 0;
+    if (ret_site == 0) {
+      if (!feasible) { status = PIP_ST_VOID; goto DONE; }
+      goto ENTRY;
+    }
+    if (ret_site == 1) { cplus = feasible; ret_site = 2; goto BUILD_SUB; }
+    {
+      int *fl = pip_fl(B, T);
+      const int f = fl[ci];
+      int nf;
+      const bool cminus = feasible;
+      if (cplus && cminus) nf = critic ? PIP_CRITIC : PIP_UNKNOWN;
+      else if (cminus) nf = PIP_MINUS;
+      else nf = cplus ? PIP_PLUS : PIP_ZERO;
+      W::sync();
+      if (lane == 0) fl[ci] = PIP_MKFL(nf, PIP_LINK(f));
+      W::sync();
+      if (nf == PIP_MINUS) goto AFTER_COMPA;
+      ci++;
+      goto COMPA_NEXT;
+    }
+  }
+
+AFTER_COMPA:
+  {
+    const int nl = T.nvar + T.ni;
+    pivi = pip_first_flag(B, T, PIP_MINUS, 0, nl);
+    if (pivi < nl) goto PIVOT;
+    pivi = pip_first_flag(B, T, PIP_CRITIC, 0, nl);
+    if (pivi >= nl) pivi = pip_first_flag(B, T, PIP_UNKNOWN, 0, nl);
+    if (pivi >= nl) goto NONNEG;
+  }
+  /* split, source/traiter.c:695-759 */
+  {
+    const int np = T.nparm, ncol = T.nvar + np + 1, nl = T.nvar + T.ni;
+    if (nc >= L.crcap) { status = PIP_ST_CAPACITY; goto DONE; }
+    if (np >= maxparm) { status = PIP_ST_FATAL + 2; goto DONE; }
+    if (ncell + np + 3 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+    int *fl = pip_fl(B, T);
+    const pip_i64 *row = pip_row(B, T, PIP_LINK(fl[pivi]));
+    pip_i64 g = 0;
+    for (int j = 0; j < np; j++) g = pip_gcd(g, row[T.nvar + 1 + j]);
+    if (!integer) g = pip_gcd(g, row[T.nvar]);
+    if (g == 0) { status = PIP_ST_FAULT; goto DONE; }
+    pip_i64 *crow = ctx + nc * cstride;
+    for (int j = lane; j <= np; j += 32) {
+      pip_i64 v;
+      if (j < np) v = pip_div(row[T.nvar + 1 + j], g);
+      else v = integer ? pip_floor_q(row[T.nvar], g) : pip_div(row[T.nvar], g);
+      crow[j] = v;
+      pip_put(out, ncell + 2 + j, PIP_C_VAL, v, 1);
+    }
+    if (lane == 0) {
+      pip_put(out, ncell, PIP_C_IF, 0, 0);
+      pip_put(out, ncell + 1, PIP_C_FORM, np + 1, 0);
+    }
+    ncell += np + 3;
+    W::sync();
+    /* push the ELSE continuation */
+    {
+      const pip_i64 fsize = 12 + nl + (nl + 1) / 2 + (pip_i64)T.ni * ncol + (pip_i64)(nc + 1) * (np + 1) + 1;
+      if (top + fsize > stk_cap) { status = PIP_ST_CAPACITY; goto DONE; }
+      pip_i64 *F = stk + top;
+      if (lane == 0) {
+        F[0] = T.nvar; F[1] = np; F[2] = T.ni; F[3] = nc; F[4] = pivi; F[5] = T.ldet;
+        for (int k = 0; k < PIP_MAX_DET; k++) F[8 + k] = B[T.det + k];
+        F[fsize - 1] = fsize;
+      }
+      pip_i64 *q = F + 12;
+      const pip_i64 *den = pip_den(B, T);
+      for (int k = lane; k < nl; k += 32) q[k] = den[k];
+      q += nl;
+      int *qi = (int *)q;
+      for (int k = lane; k < nl; k += 32) qi[k] = fl[k];
+      q += (nl + 1) / 2;
+      for (int e = lane; e < T.ni * ncol; e += 32) {
+        int r = e / ncol, j = e - r * ncol;
+        q[e] = pip_row(B, T, r)[j];
+      }
+      q += (pip_i64)T.ni * ncol;
+      for (int e = lane; e < (nc + 1) * (np + 1); e += 32) {
+        int r = e / (np + 1), j = e - r * (np + 1);
+        q[e] = ctx[r * cstride + j];
+      }
+      top += fsize;
+    }
+    W::sync();
+    if (lane == 0) fl[pivi] = PIP_MKFL(PIP_PLUS, PIP_LINK(fl[pivi]));
+    W::sync();
+    nc++;
+    depth++;
+    st.splits++;
+    goto ENTRY;
+  }
+
+NONNEG:
+  if (level == 0 && !integer) {
+    const int total = 1 + T.nvar * (T.nparm + 2);
+    if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+    pip_emit_solution(B, T, out, ncell);
+    ncell += total;
+    goto LEAF;
+  }
+  /* integrer_xx, source/integrer.c:305-534 */
+  {
+    const int nvar = T.nvar, np = T.nparm, ncol = nvar + np + 1, nl = nvar + T.ni;
+    if (ncol >= maxcol) { status = PIP_ST_FATAL + 3; goto DONE; }
+    int *fl = pip_fl(B, T);
+    pip_i64 *den = pip_den(B, T);
+    int verdict = 0;     /* 0 integral, -1 none, >0 cut row */
+    for (int i = 0; i < nvar; i++) {
+      const pip_i64 D = den[i];
+      const int f = fl[i];
+      if (D == 1) continue;
+      if (f & PIP_UNIT) continue;
+      if (D == 0) { status = PIP_ST_FAULT; goto DONE; }
+      const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+      bool okv = false, okc = false, okp = false;
+      W::sync();
+      for (int j = lane; j < ncol; j += 32) {
+        pip_i64 v = row[j], x;
+        if (j < nvar) { x = pip_mod(v, D); okv = okv || x > 0; }
+        else if (j == nvar) { x = -pip_mod(-v, D); okc = okc || x != 0; }
+        else if (!level && j == P.bigparm) x = 0;
+        else { x = -pip_mod(-v, D); okp = okp || x != 0; }
+        cut[j] = x;
+      }
+      if (lane == 0) cut[ncol] = D;
+      const bool ok_var = W::any(okv), ok_const = W::any(okc), ok_parm = W::any(okp);
+      W::sync();
+      if (!ok_parm && !ok_const) continue;                  /* case (a) */
+      if (!ok_parm && !ok_var) { verdict = -1; break; }     /* case (b) */
+      if (T.ni >= T.rcap || nl >= T.pcap) { status = PIP_ST_CAPACITY; goto DONE; }
+      int parm = -1;
+      if (ok_parm) {                                         /* case (e), source/integrer.c:493-520 */
+        if (lane == 0) parm = pip_find_parm(ctx, cstride, nc, np, cut + nvar);
+        W::sync();
+        parm = W::shfl(parm, 0);
+        if (parm == -1) {
+          /* add_parm_xx, source/integrer.c:156-227 */
+          if (nc + 2 > L.crcap || np + 2 > cstride || ncol + 1 > T.stride) { status = PIP_ST_CAPACITY; goto DONE; }
+          if (ncell + np + 5 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+          const pip_i64 *c = cut + nvar;
+          if (lane == 0) {
+            pip_put(out, ncell, PIP_C_NEW, np, 0);
+            pip_put(out, ncell + 1, PIP_C_DIV, 0, 0);
+            pip_put(out, ncell + 2, PIP_C_FORM, np + 1, 0);
+            for (int j = 0; j < np; j++) pip_put(out, ncell + 3 + j, PIP_C_VAL, -c[1 + j], 1);
+            pip_put(out, ncell + 3 + np, PIP_C_VAL, -c[0], 1);
+            pip_put(out, ncell + 4 + np, PIP_C_VAL, c[1 + np], 1);
+            for (int k = 0; k < nc; k++) { pip_i64 *r = ctx + k * cstride; r[np + 1] = r[np]; r[np] = 0; }
+            pip_i64 *r0 = ctx + nc * cstride, *r1 = r0 + cstride;
+            for (int j = 0; j < np; j++) { r0[j] = -c[1 + j]; r1[j] = c[1 + j]; }
+            r0[np] = -c[1 + np]; r1[np] = c[1 + np];
+            r0[np + 1] = -c[0]; r1[np + 1] = c[0] - 1 + c[1 + np];
+          }
+          /* the new parameter's tableau column starts at zero in every stored row */
+          for (int r = lane; r < T.ni; r += 32) pip_row(B, T, r)[ncol] = 0;
+          ncell += np + 5;
+          parm = np;
+          T.nparm = np + 1;
+          nc += 2;
+          W::sync();
+        }
+        if (!ok_var) { status = PIP_ST_FATAL + 134; goto DONE; }   /* assert(ok_var) */
+      }
+      {
+        pip_i64 *nr = pip_row(B, T, T.ni);
+        for (int j = lane; j < ncol; j += 32) nr[j] = cut[j];
+        W::sync();
+        if (lane == 0) {
+          if (ok_parm) {
+            if (parm == np) nr[ncol] = cut[ncol];           /* fresh column: 0 + D */
+            else nr[nvar + 1 + parm] += cut[ncol];
+          }
+          fl[nl] = PIP_MKFL(PIP_MINUS, T.ni);
+          den[nl] = D;
+        }
+        T.ni++;
+        st.cuts++;
+        verdict = nl;
+        W::sync();
+      }
+      break;
+    }
+    if (verdict > 0) { pivi = verdict; goto PIVOT; }
+    if (level) { feasible = (verdict == 0); goto SUB_DONE; }
+    if (verdict == 0) {
+      const int total = 1 + T.nvar * (T.nparm + 2);
+      if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+      pip_emit_solution(B, T, out, ncell);
+      ncell += total;
+    } else {
+      if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+      if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
+      ncell += 1;
+    }
+    goto LEAF;
+  }
+
+PIVOT:
+  {
+    int rc = pip_pivot(B, T, pivi, st);
+    if (rc == 0) goto LOOP;
+    if (rc > 0) { status = rc; goto DONE; }
+    if (level) { feasible = false; goto SUB_DONE; }
+    if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+    if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
+    ncell += 1;
+  }
+
+LEAF:
+  /* a branch of the main problem is finished: resume the innermost pending ELSE branch
+   * (source/traiter.c:747-758) or stop */
+  if (depth == 0) goto DONE;
+  {
+    W::sync();
+    const pip_i64 fsize = stk[top - 1];
+    const pip_i64 *F = stk + (top - fsize);
+    T.nvar = (int)F[0]; T.nparm = (int)F[1]; T.ni = (int)F[2]; nc = (int)F[3]; pivi = (int)F[4]; T.ldet = (int)F[5];
+    const int np = T.nparm, ncol = T.nvar + np + 1, nl = T.nvar + T.ni;
+    int *fl = pip_fl(B, T);
+    pip_i64 *den = pip_den(B, T);
+    if (lane == 0) for (int k = 0; k < PIP_MAX_DET; k++) B[T.det + k] = F[8 + k];
+    const pip_i64 *q = F + 12;
+    for (int k = lane; k < nl; k += 32) den[k] = q[k];
+    q += nl;
+    const int *qi = (const int *)q;
+    for (int k = lane; k < nl; k += 32) fl[k] = qi[k];
+    q += (nl + 1) / 2;
+    for (int e = lane; e < T.ni * ncol; e += 32) {
+      int r = e / ncol, j = e - r * ncol;
+      pip_row(B, T, r)[j] = q[e];
+    }
+    q += (pip_i64)T.ni * ncol;
+    for (int e = lane; e < (nc + 1) * (np + 1); e += 32) {
+      int r = e / (np + 1), j = e - r * (np + 1);
+      pip_i64 v = q[e];
+      if (r == nc) v = (j < np) ? -v : -(v + 1);          /* the negated condition */
+      ctx[r * cstride + j] = v;
+    }
+    top -= fsize;
+    depth--;
+    W::sync();
+    if (lane == 0) fl[pivi] = PIP_MKFL(PIP_MINUS, PIP_LINK(fl[pivi]));
+    W::sync();
+    nc++;
+    goto PIVOT;
+  }
+
+DONE:
+  W::sync();
+  status_out = status;
+  ncell_out = (status == PIP_ST_OK) ? ncell : 0;
+}
+
+#endif

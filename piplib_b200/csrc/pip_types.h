@@ -1,0 +1,88 @@
+/* Shared host/device plain-data types of the batched PipLib solver core.
+ *
+ * Vocabulary follows the reference (paths relative to the reference tree):
+ *   tableau row flags    source/tab.h:58-63
+ *   solution cell kinds  source/sol.c:42-50, cell = {flags, param1, param2} source/sol.c:37-40
+ *   hard limits          source/type.h:39,49,50 and source/tab.h:70
+ */
+#ifndef PIP_TYPES_H
+#define PIP_TYPES_H
+
+#include <stdint.h>
+
+typedef long long pip_i64;
+typedef unsigned long long pip_u64;
+
+/* row flags */
+enum { PIP_UNIT = 1, PIP_PLUS = 2, PIP_MINUS = 4, PIP_ZERO = 8, PIP_CRITIC = 16, PIP_UNKNOWN = 32 };
+/* cell kinds */
+enum { PIP_C_FREE = 0, PIP_C_NIL = 1, PIP_C_IF = 2, PIP_C_LIST = 3, PIP_C_FORM = 4, PIP_C_NEW = 5,
+       PIP_C_DIV = 6, PIP_C_VAL = 7, PIP_C_ERROR = 8 };
+/* problem flags (traiter flags, source/funcall.h:34-35, + our own) */
+enum { PIP_F_INT = 1, PIP_F_DUAL = 2, PIP_F_DEEPEST = 4 };
+
+#define PIP_SOL_SIZE 4096
+#define PIP_MAXCOL 512
+#define PIP_MAXPARM 50
+#define PIP_MAX_DET 4
+
+/* per-problem status.  0/1 and 1000+exit-code are the reference's verdicts (see
+ * include/piplib_b200.h); the 4xxx codes are internal scheduling states that never reach the
+ * caller: the host re-runs such a problem in a larger size class. */
+enum {
+  PIP_ST_OK = 0,
+  PIP_ST_VOID = 1,
+  PIP_ST_FATAL = 1000,           /* + exit code of the reference */
+  PIP_ST_FAULT = 2000,           /* division by zero: the reference dies of SIGFPE */
+  PIP_ST_PENDING = 4000,         /* not solved yet (warp arena exhausted / not reached) */
+  PIP_ST_CAPACITY = 4001,        /* exceeded the working-set capacity of its size class */
+  PIP_ST_UNSUPPORTED = 4002
+};
+
+typedef struct {
+  int nvar, nparm, ni, nc;       /* unknowns, parameters, tableau rows, context rows */
+  int bigparm;                   /* tableau column of the big parameter or -1 */
+  int flags;                     /* PIP_F_* */
+  pip_i64 off;                   /* word offset into the input pool: ni*(nvar+nparm+1) tableau
+                                    words (row-major, .dat column order) then nc*(nparm+1) */
+} PipProblem;
+
+typedef struct {
+  int status;
+  int ncells;
+  pip_i64 cell_off;              /* index of the first cell in the cell pool */
+  unsigned pivots;               /* successful pivots incl. sub-solves */
+  unsigned cuts;
+  unsigned subsolves;            /* non-parametric feasibility solves (compa_test, context) */
+  unsigned splits;
+  unsigned max_rows, max_cols;   /* largest nligne x ncol seen by a pivot */
+  unsigned wrapped;              /* # pivots during which some 64-bit product wrapped */
+  unsigned elem_updates_lo, elem_updates_hi;
+  unsigned pad;
+} PipResult;
+
+typedef struct {
+  int kind;
+  int pad;
+  pip_i64 p1, p2;
+} PipCell;
+
+/* launch parameters of the warp-per-problem kernels */
+typedef struct {
+  const PipProblem *prob;
+  const pip_i64 *pool;
+  const int *order;              /* optional permutation of problem indices (may be NULL) */
+  int nprob;
+  PipResult *res;
+  PipCell *cells;                /* cell pool, cells_per_warp per warp */
+  pip_i64 cells_per_warp;
+  pip_i64 *stack;                /* split-frame stack pool (global memory) */
+  pip_i64 stack_words_per_warp;
+  pip_i64 *gwork;                /* working arenas in global memory (class G) or NULL (class S) */
+  int work_words;                /* words of working arena per warp */
+  unsigned *queue;               /* [0] next problem, [1] retired warps */
+  int sol_size, maxcol, maxparm;
+  int slack_level;
+} PipLaunch;
+
+#endif

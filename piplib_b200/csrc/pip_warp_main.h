@@ -1,0 +1,46 @@
+/* Persistent warp loop: pull problem indices from a device-side queue, solve, append the
+ * solution cells to this warp's window of the cell pool, write the per-problem record.
+ * A warp retires when its window can no longer hold a worst-case solution (SOL_SIZE cells);
+ * problems nobody solved keep status PIP_ST_PENDING and the host launches again for them. */
+#ifndef PIP_WARP_MAIN_H
+#define PIP_WARP_MAIN_H
+
+#include "pip_solver.h"
+
+PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
+{
+  const int lane = W::lane();
+  PipCell *window = L.cells + (pip_i64)warp_id * L.cells_per_warp;
+  pip_i64 *stk = L.stack + (pip_i64)warp_id * L.stack_words_per_warp;
+  pip_i64 used = 0;
+  for (;;) {
+    if (L.cells_per_warp - used < (pip_i64)L.sol_size) break;
+    unsigned q = 0;
+    if (lane == 0) q = W::atomic_add(&L.queue[0], 1u);
+    q = (unsigned)W::shfl((int)q, 0);
+    if (q >= (unsigned)L.nprob) break;
+    const int p = L.order ? L.order[q] : (int)q;
+    const PipProblem P = L.prob[p];
+    PipStats st;
+    st.pivots = st.cuts = st.subsolves = st.splits = st.max_rows = st.max_cols = 0;
+    st.elem_updates = 0;
+    int status = PIP_ST_OK, ncell = 0;
+    pip_solve_one(P, L.pool + P.off, arena, L.work_words, L.slack_level, window + used, stk,
+                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, st);
+    if (lane == 0) {
+      PipResult r;
+      r.status = status; r.ncells = ncell;
+      r.cell_off = (pip_i64)warp_id * L.cells_per_warp + used;
+      r.pivots = st.pivots; r.cuts = st.cuts; r.subsolves = st.subsolves; r.splits = st.splits;
+      r.max_rows = st.max_rows; r.max_cols = st.max_cols; r.wrapped = 0;
+      r.elem_updates_lo = (unsigned)(st.elem_updates & 0xffffffffull);
+      r.elem_updates_hi = (unsigned)(st.elem_updates >> 32);
+      r.pad = 0;
+      L.res[p] = r;
+    }
+    used += ncell;
+    W::sync();
+  }
+}
+
+#endif

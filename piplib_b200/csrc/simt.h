@@ -1,0 +1,78 @@
+/* Warp-level primitives used by the solver core.
+ *
+ * On the device they are the sm_100a intrinsics.  With -DPIP_EMU (tests/emu only, a debugging
+ * aid that runs the *device source* on the CPU with 32 cooperative fibers per warp) they are
+ * provided by tests/emu/emu_runtime.cpp.  The product library is never built with PIP_EMU.
+ */
+#ifndef PIP_SIMT_H
+#define PIP_SIMT_H
+
+#include <stdint.h>
+
+#if defined(PIP_EMU)
+
+#define PIP_DEV static inline
+#define PIP_DEVNI static __attribute__((noinline))
+#define PIP_HD static inline
+#define PIP_ASSUME_SHARED(p) ((void)0)
+
+namespace pipemu {
+int lane();
+void barrier();
+unsigned ballot(bool p);
+long long shfl64(long long v, int src);
+unsigned redmin(unsigned v);
+unsigned redmax(unsigned v);
+unsigned atomic_add(unsigned *p, unsigned v);
+}  // namespace pipemu
+
+struct W {
+  static inline int lane() { return pipemu::lane(); }
+  static inline void sync() { pipemu::barrier(); }
+  static inline unsigned ballot(bool p) { return pipemu::ballot(p); }
+  static inline bool any(bool p) { return pipemu::ballot(p) != 0; }
+  static inline int shfl(int v, int src) { return (int)pipemu::shfl64(v, src); }
+  static inline long long shfl64(long long v, int src) { return pipemu::shfl64(v, src); }
+  static inline unsigned redmin(unsigned v) { return pipemu::redmin(v); }
+  static inline unsigned redmax(unsigned v) { return pipemu::redmax(v); }
+  static inline unsigned atomic_add(unsigned *p, unsigned v) { return pipemu::atomic_add(p, v); }
+};
+
+static inline int pip_ffs(unsigned m) { return __builtin_ffs((int)m); }
+static inline int pip_popc(unsigned m) { return __builtin_popcount(m); }
+static inline int pip_clzll(unsigned long long v) { return v ? __builtin_clzll(v) : 64; }
+static inline int pip_ctzll(unsigned long long v) { return v ? __builtin_ctzll(v) : 64; }
+static inline long long pip_mulhi(long long a, long long b) { return (long long)(((__int128)a * b) >> 64); }
+static inline double pip_ll2d(long long v) { return (double)v; }
+static inline unsigned pip_f2u(float f) { unsigned u; __builtin_memcpy(&u, &f, 4); return u; }
+
+#else  /* device */
+
+#define PIP_DEV __device__ __forceinline__
+#define PIP_DEVNI __device__ __noinline__
+#define PIP_HD __host__ __device__ __forceinline__
+#define PIP_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+
+struct W {
+  static __device__ __forceinline__ int lane() { return (int)(threadIdx.x & 31u); }
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+  static __device__ __forceinline__ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+  static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+  static __device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  static __device__ __forceinline__ long long shfl64(long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  static __device__ __forceinline__ unsigned redmin(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
+  static __device__ __forceinline__ unsigned redmax(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+  static __device__ __forceinline__ unsigned atomic_add(unsigned *p, unsigned v) { return atomicAdd(p, v); }
+};
+
+static __device__ __forceinline__ int pip_ffs(unsigned m) { return __ffs((int)m); }
+static __device__ __forceinline__ int pip_popc(unsigned m) { return __popc(m); }
+static __device__ __forceinline__ int pip_clzll(unsigned long long v) { return __clzll((long long)v); }
+static __device__ __forceinline__ int pip_ctzll(unsigned long long v) { return v ? __ffsll((long long)v) - 1 : 64; }
+static __device__ __forceinline__ long long pip_mulhi(long long a, long long b) { return __mul64hi(a, b); }
+static __device__ __forceinline__ double pip_ll2d(long long v) { return __ll2double_rn(v); }
+static __device__ __forceinline__ unsigned pip_f2u(float f) { return __float_as_uint(f); }
+
+#endif
+
+#endif
