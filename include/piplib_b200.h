@@ -1,0 +1,121 @@
+/* piplib-b200: the batched C-ABI (new; not in the reference) + status vocabulary.
+ *
+ * Everything here is plain C: pointers, sizes, ints.  No CUDA or torch types cross the boundary.
+ *
+ * Entry points and the reference interface each one replaces or extends:
+ *
+ *   pip_solve_batch_dp        n independent pip_solve_dp calls (source/piplib.c:722-880) in one
+ *                             device batch; out[i] is the same tree pip_solve_dp would return.
+ *   pip_traiter_batch_dp      n independent runs of the CLI's per-problem body
+ *                             (source/maind.c:150-232: tab_get x2, tab_simplify, context check,
+ *                             traiter_xx) on already-lexed tableaus; returns raw solution cells
+ *                             ({flags, param1, param2}, source/sol.c:37-40).
+ *   pip_solve_dense_dp        pip_solve_batch_dp for a batch whose problems share one shape,
+ *                             given as two dense int64 arrays (no PipMatrix objects); returns
+ *                             cells or a hash per problem.  This is the bulk path used by
+ *                             bench.py (host buffers in, host buffers out).
+ *   pip_device_*              the same batch with inputs/outputs resident in device memory
+ *                             (kernel-only timing; pointers are CUdeviceptr values as integers).
+ *   pip_quast_serialize_dp    PipQuast -> int64 stream (test/interop helper).
+ *
+ * Status codes (per problem):
+ *   0       solved
+ *   1       the context is empty: pip_solve_dp returns NULL, the CLI prints "void"
+ *   1000+c  the reference prints a message and calls exit(c) (source/traiter.c:424-427,441-444:
+ *           "Integer overflow" c=1; source/traiter.c:174-177,710-713: "Too much parameters"
+ *           c=1/2; source/integrer.c:324-327: "Too many variables" c=3; source/sol.c:97-100:
+ *           "The solution is too complex! : sol" c=26; assert(ok_var) integrer.c:499: c=134)
+ *   2000    the reference dies of a division by zero (SIGFPE) after a silent int64 wrap
+ *   4001    problem exceeds the largest device size class (never seen on the fixtures)
+ *   4002    option not implemented on the device (Compute_dual, Deepest_cut)
+ * pip_solve_dp (batch of one) keeps the reference behaviour: message on stderr + exit(c).
+ */
+#ifndef PIPLIB_B200_H
+#define PIPLIB_B200_H
+
+#include <piplib/piplib.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define PIP_STATUS_OK 0
+#define PIP_STATUS_VOID 1
+#define PIP_STATUS_FATAL 1000
+#define PIP_STATUS_FAULT 2000
+#define PIP_STATUS_TOO_LARGE 4001
+#define PIP_STATUS_UNSUPPORTED 4002
+
+typedef struct {
+  int kind;                 /* Free0 Nil1 If2 List3 Form4 New5 Div6 Val7 (source/sol.c:42-50) */
+  int pad;
+  long long p1, p2;
+} PipCell_dp;
+
+typedef struct {
+  int nvar, nparm, ni, nc;  /* .dat header fields Nn Np Nl Nm (doc/piplib.texi:570-586) */
+  int bigparm;              /* Bg: tableau column of the big parameter, or -1 */
+  int nq;                   /* 1 integer, 0 rational */
+} PipTableauHeader_dp;
+
+typedef struct {
+  unsigned long long pivots, cuts, subsolves, splits, elem_updates;
+  unsigned max_rows, max_cols;
+  double seconds_h2d, seconds_kernel, seconds_d2h, seconds_host;
+  float device_ms;          /* CUDA-event time from the first to the last kernel of the batch */
+  int launches;             /* kernels launched by the last batch call */
+  int rounds;               /* solve launches (size-class escalations included) */
+  unsigned long long h2d_bytes, d2h_bytes;
+} PipBatchStats_dp;
+
+/* n x pip_solve_dp.  options may be NULL (defaults) ; contexts[i] may be NULL (no parameters).
+ * out[i] receives the tree (NULL when status[i] != 0); returns 0 or a negative CUDA/system error. */
+int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const *contexts,
+                       const int *bignums, const PipOptions_dp *options,
+                       PipQuast_dp **out, int *status);
+
+/* n x (maind.c per-problem body).  tab[i]: ni x (nvar+nparm+1) row-major, .dat column order
+ * [unknowns | constant | parameters]; ctx[i]: nc x (nparm+1).  cells_out must hold cell_cap cells;
+ * cell_off[i]/ncells[i] locate problem i's cells.  Returns 0, -2 if cell_cap is too small (then
+ * *cells_needed says how many), or a negative error. */
+int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long *const *tab,
+                         const long long *const *ctx, int *status, PipCell_dp *cells_out,
+                         long long cell_cap, long long *cell_off, int *ncells, long long *cells_needed);
+
+/* Dense batch through the pip_solve_dp path: dom is [n][dom_rows][dom_cols] (PolyLib rows),
+ * ctx is [n][ctx_rows][ctx_cols] or NULL (has_ctx=0).  Host buffers in, host buffers out:
+ *   status[i]  as above
+ *   hashes[i]  (optional) FNV-1a over the serialised quast words (the function tests/ and
+ *              oracle/ apply to the reference's trees); 0 when status[i] is fatal
+ *   ser        (optional) the serialised quasts back to back, ser_off[i]..ser_off[i+1]
+ *              (ser_off has n+1 entries); returns -2 when ser_cap is too small. */
+int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long *dom,
+                       int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
+                       int bignum, const PipOptions_dp *options,
+                       int *status, unsigned long long *hashes,
+                       long long *ser, long long ser_cap, long long *ser_off);
+
+/* Device-resident variant of the dense batch: converted and uploaded once by create(); run()
+ * executes only kernels (plus the 56-byte-per-problem status records the size-class ladder
+ * needs); the solution cells stay in HBM unless fetch_cells is set. */
+typedef struct pip_device_batch pip_device_batch;
+pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_cols, const long long *dom,
+                                          int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
+                                          int bignum, const PipOptions_dp *options);
+int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms);
+/* results of the last run: status always; hashes only if that run fetched the cells */
+int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long long *hashes);
+void pip_device_batch_destroy(pip_device_batch *b);
+
+void pip_last_batch_stats_dp(PipBatchStats_dp *out);
+
+/* PipQuast -> int64 stream; returns the number of words (may exceed cap: nothing past cap is written) */
+long pip_quast_serialize_dp(const PipQuast_dp *q, long long *out, long cap);
+
+int pip_set_device_dp(int device);                     /* select the CUDA device (default 0) */
+const char *pip_b200_version(void);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif

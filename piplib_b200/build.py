@@ -1,0 +1,68 @@
+"""Build the in-tree shared library piplib_b200/lib/libpiplib_dp.so for sm_100a.
+
+nvcc cross-compiles without a GPU.  The library is named like the reference's int64 build
+(libpiplib_dp.so, Makefile.am:24-25 of the reference) so that `-lpiplib_dp` keeps working.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libpiplib_dp.so")
+CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+NVCC = os.path.join(CUDA, "bin", "nvcc")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fwrapv", "-Xptxas", "-v"]
+SOURCES_CU = ["pip_kernels.cu"]
+SOURCES_CPP = ["pip_engine.cpp", "pip_host.cpp"]
+HEADERS = ["pip_types.h", "simt.h", "pip_arith.h", "pip_solver.h", "pip_warp_main.h", "pip_kernels.h",
+           "pip_engine.h", os.path.join("..", "..", "include", "piplib_b200.h"),
+           os.path.join("..", "..", "include", "piplib", "piplib.h")]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for f in SOURCES_CU + SOURCES_CPP + HEADERS:
+        if os.path.getmtime(os.path.join(CSRC, f)) > t:
+            return True
+    return os.path.getmtime(os.path.abspath(__file__)) > t
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    objs = []
+    inc = ["-I", os.path.join(HERE, "..", "include"), "-I", CSRC]
+    for f in SOURCES_CU:
+        o = os.path.join(LIBDIR, f + ".o")
+        cmd = [NVCC] + NVCC_FLAGS + inc + ["-c", os.path.join(CSRC, f), "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed on " + f)
+        with open(os.path.join(LIBDIR, f + ".ptxas.txt"), "w") as fh:
+            fh.write(r.stdout + r.stderr)
+        objs.append(o)
+    for f in SOURCES_CPP:
+        o = os.path.join(LIBDIR, f + ".o")
+        cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-fwrapv", "-Wall", "-pthread",
+               "-I", os.path.join(CUDA, "include")] + inc + ["-c", os.path.join(CSRC, f), "-o", o]
+        subprocess.check_call(cmd)
+        objs.append(o)
+    cmd = ["g++", "-shared", "-o", LIB] + objs + ["-L", os.path.join(CUDA, "lib64"), "-lcudart",
+                                                   "-pthread", "-Wl,-rpath," + os.path.join(CUDA, "lib64")]
+    subprocess.check_call(cmd)
+    for o in objs:
+        os.remove(o)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

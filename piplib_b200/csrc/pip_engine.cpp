@@ -1,0 +1,290 @@
+/* Host-side batch engine (see pip_engine.h).  Plain CUDA runtime; no torch, no CPU solver. */
+#include "pip_engine.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "pip_kernels.h"
+
+void pip_cuda_check(cudaError_t e, const char *what)
+{
+  if (e != cudaSuccess)
+    throw std::runtime_error(std::string("piplib-b200: CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+#define CK(x) pip_cuda_check((x), #x)
+
+namespace {
+
+double now_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes)
+  {
+    if (bytes <= cap) return;
+    if (p) CK(cudaFree(p));
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CK(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes)
+  {
+    if (bytes <= cap) return;
+    if (p) CK(cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+    cap = want;
+  }
+};
+
+/* the size-class ladder */
+struct ClassSpec { int level; int shared; long long words; int warps; int warps_per_cta; long long stack_words; };
+const long long S_MAX_WORDS = 3328;          /* 26 KB: at least 8 warps of class S per SM */
+const ClassSpec G_LADDER[] = {
+    {3, 0, 1ll << 15, 148 * 8, 4, 1ll << 17},
+    {4, 0, 1ll << 17, 148 * 4, 4, 1ll << 19},
+    {5, 0, 1ll << 19, 148 * 2, 2, 1ll << 21},
+    {6, 0, 1ll << 22, 148, 1, 1ll << 23},
+    {7, 0, 1ll << 24, 32, 1, 1ll << 25},
+    {8, 0, 1ll << 26, 8, 1, 1ll << 27},
+};
+const int N_G = sizeof(G_LADDER) / sizeof(G_LADDER[0]);
+
+}  // namespace
+
+struct PipEngine::Impl {
+  std::mutex mu;
+  int device = 0, sm_count = 0;
+  size_t smem_optin = 0;
+  bool inited = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total;
+  PinBuf h_res, h_total;
+  std::vector<PinBuf> h_chunks;     /* one per round, reused across calls */
+
+  void init()
+  {
+    if (inited) return;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      throw std::runtime_error("piplib-b200: this library is built for sm_100a (B200) only; device is sm_" +
+                               std::to_string(prop.major) + std::to_string(prop.minor));
+    sm_count = prop.multiProcessorCount;
+    smem_optin = prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    inited = true;
+  }
+};
+
+PipEngine::PipEngine() : impl_(new Impl) {}
+PipEngine &PipEngine::get() { static PipEngine e; return e; }
+int PipEngine::set_device(int dev)
+{
+  std::lock_guard<std::mutex> g(impl_->mu);
+  if (impl_->inited && dev != impl_->device) return -1;
+  impl_->device = dev;
+  return 0;
+}
+int PipEngine::sm_count() { std::lock_guard<std::mutex> g(impl_->mu); impl_->init(); return impl_->sm_count; }
+cudaStream_t PipEngine::stream() { std::lock_guard<std::mutex> g(impl_->mu); impl_->init(); return impl_->stream; }
+
+void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
+{
+  Impl &E = *impl_;
+  std::lock_guard<std::mutex> g(E.mu);
+  E.init();
+  CK(cudaSetDevice(E.device));
+  const size_t n = in.n;
+  out.res.assign(n, PipResult());
+  out.base.assign(n, nullptr);
+  out.times = PipBatchTimes();
+  if (n == 0) return;
+  const double t_begin = now_s();
+  cudaStream_t s = E.stream;
+
+  /* ---- inputs ------------------------------------------------------------------------- */
+  const PipProblem *d_prob = in.d_prob;
+  const pip_i64 *d_pool = in.d_pool;
+  double t0 = now_s();
+  if (!d_prob) {
+    E.d_prob.reserve(n * sizeof(PipProblem));
+    CK(cudaMemcpyAsync(E.d_prob.p, in.h_prob, n * sizeof(PipProblem), cudaMemcpyHostToDevice, s));
+    d_prob = (const PipProblem *)E.d_prob.p;
+    out.times.h2d_bytes += n * sizeof(PipProblem);
+  }
+  if (!d_pool) {
+    E.d_pool.reserve(std::max<size_t>(in.pool_words, 1) * sizeof(pip_i64));
+    CK(cudaMemcpyAsync(E.d_pool.p, in.h_pool, in.pool_words * sizeof(pip_i64), cudaMemcpyHostToDevice, s));
+    d_pool = (const pip_i64 *)E.d_pool.p;
+    out.times.h2d_bytes += in.pool_words * sizeof(pip_i64);
+  }
+  /* per-problem records start as PENDING */
+  E.h_res.reserve(n * sizeof(PipResult));
+  PipResult *h_res = (PipResult *)E.h_res.p;
+  memset(h_res, 0, n * sizeof(PipResult));
+  for (size_t i = 0; i < n; i++) h_res[i].status = PIP_ST_PENDING;
+  E.d_res.reserve(n * sizeof(PipResult));
+  CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
+  out.times.h2d_bytes += n * sizeof(PipResult);
+  E.d_queue.reserve(64);
+  E.d_total.reserve(64);
+  E.h_total.reserve(64);
+  CK(cudaStreamSynchronize(s));
+  out.times.h2d = now_s() - t0;
+
+  /* ---- plan: class S for everything whose level-2 working set fits a shared-memory arena */
+  std::vector<int> cls(n);              /* -1 = class S, k = G_LADDER[k] */
+  long long s_words = 0, est_cells_total = 0;
+  for (size_t i = 0; i < n; i++) {
+    const PipProblem &P = in.h_prob[i];
+    long long w = pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2);
+    if (w <= S_MAX_WORDS) { cls[i] = -1; s_words = std::max(s_words, w); }
+    else {
+      int k = 0;
+      while (k < N_G - 1 && pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, G_LADDER[k].level) > G_LADDER[k].words) k++;
+      cls[i] = k;
+    }
+    est_cells_total += 3ll * (1 + P.nvar * (2 + P.nparm)) + 32;
+  }
+  s_words = (s_words + 1) & ~1ll;
+
+  CK(cudaEventRecord(E.ev0, s));
+  std::vector<int> order;
+  order.reserve(n);
+  int round = 0;
+  for (int k = -1; k < N_G; k++) {
+    for (int attempt = 0; attempt < 64; attempt++) {
+      order.clear();
+      for (size_t i = 0; i < n; i++) if (cls[i] == k) order.push_back((int)i);
+      if (order.empty()) break;
+      const int m = (int)order.size();
+      /* geometry of this round */
+      ClassSpec cs;
+      int ctas;
+      if (k < 0) {
+        cs.level = 2; cs.shared = 1; cs.words = std::max<long long>(s_words, 64);
+        cs.warps_per_cta = 4;
+        cs.stack_words = 1ll << 14;
+        size_t smem = (size_t)cs.warps_per_cta * cs.words * sizeof(pip_i64);
+        if (smem > E.smem_optin) { cs.warps_per_cta = 1; smem = (size_t)cs.words * sizeof(pip_i64); }
+        int per_sm = 1;
+        CK(pip_solve_occupancy(1, cs.warps_per_cta, smem, &per_sm));
+        if (per_sm < 1) per_sm = 1;
+        ctas = E.sm_count * per_sm;
+        int need = (m + cs.warps_per_cta - 1) / cs.warps_per_cta;
+        if (ctas > need) ctas = need;
+        cs.warps = ctas * cs.warps_per_cta;
+      } else {
+        cs = G_LADDER[k];
+        int need_warps = std::min(cs.warps, m);
+        ctas = (need_warps + cs.warps_per_cta - 1) / cs.warps_per_cta;
+        cs.warps = ctas * cs.warps_per_cta;
+      }
+      /* cell pool: every warp must be able to hold one worst-case solution */
+      long long est = (k < 0 && attempt == 0) ? (est_cells_total * (long long)m / (long long)n) : 0;
+      long long per_warp = std::max<long long>(in.sol_size, (est + est / 4) / cs.warps + 1);
+      if (attempt > 0) per_warp = std::max<long long>(per_warp, 4ll * in.sol_size);
+      E.d_cells.reserve((size_t)per_warp * cs.warps * sizeof(PipCell));
+      E.d_stack.reserve((size_t)cs.stack_words * cs.warps * sizeof(pip_i64));
+      if (!cs.shared) E.d_gwork.reserve((size_t)cs.words * cs.warps * sizeof(pip_i64));
+      E.d_order.reserve((size_t)m * sizeof(int));
+      E.d_off.reserve((size_t)m * sizeof(long long));
+      CK(cudaMemcpyAsync(E.d_order.p, order.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, s));
+      CK(cudaMemsetAsync(E.d_queue.p, 0, 16, s));
+
+      PipLaunch L;
+      memset(&L, 0, sizeof L);
+      L.prob = d_prob; L.pool = d_pool; L.order = (const int *)E.d_order.p; L.nprob = m;
+      L.res = (PipResult *)E.d_res.p;
+      L.cells = (PipCell *)E.d_cells.p; L.cells_per_warp = per_warp;
+      L.stack = (pip_i64 *)E.d_stack.p; L.stack_words_per_warp = cs.stack_words;
+      L.gwork = cs.shared ? nullptr : (pip_i64 *)E.d_gwork.p;
+      L.work_words = (int)cs.words;
+      L.queue = (unsigned *)E.d_queue.p;
+      L.sol_size = in.sol_size; L.maxcol = in.maxcol; L.maxparm = PIP_MAXPARM;
+      L.slack_level = cs.level;
+      double tk = now_s();
+      CK(pip_launch_solve(&L, cs.shared, ctas, cs.warps_per_cta, s));
+      out.times.launches++;
+      /* compact this round's cells */
+      CK(pip_launch_gather((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
+                           (long long *)E.d_off.p, nullptr, m, (long long *)E.d_total.p, 0, s));
+      out.times.launches++;
+      CK(cudaMemcpyAsync(E.h_total.p, E.d_total.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      const long long total = *(long long *)E.h_total.p;
+      E.d_compact.reserve((size_t)std::max<long long>(total, 1) * sizeof(PipCell));
+      CK(pip_launch_gather((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
+                           (long long *)E.d_off.p, (PipCell *)E.d_compact.p, m, (long long *)E.d_total.p, 1, s));
+      out.times.launches++;
+      CK(cudaEventRecord(E.ev1, s));
+      CK(cudaStreamSynchronize(s));
+      out.times.kernel += now_s() - tk;
+      /* fetch records (+ cells) */
+      double td = now_s();
+      CK(cudaMemcpyAsync(h_res, E.d_res.p, n * sizeof(PipResult), cudaMemcpyDeviceToHost, s));
+      out.times.d2h_bytes += n * sizeof(PipResult);
+      if ((size_t)round >= E.h_chunks.size()) E.h_chunks.resize(round + 1);
+      PinBuf &chunk = E.h_chunks[round];
+      if (in.fetch_cells && total > 0) {
+        chunk.reserve((size_t)total * sizeof(PipCell));
+        CK(cudaMemcpyAsync(chunk.p, E.d_compact.p, (size_t)total * sizeof(PipCell), cudaMemcpyDeviceToHost, s));
+        out.times.d2h_bytes += (size_t)total * sizeof(PipCell);
+      }
+      CK(cudaStreamSynchronize(s));
+      out.times.d2h += now_s() - td;
+      round++;
+      out.times.rounds++;
+      /* classify */
+      int pending = 0;
+      for (int q = 0; q < m; q++) {
+        const int i = order[q];
+        const PipResult &r = h_res[i];
+        if (r.status == PIP_ST_PENDING) { pending++; continue; }
+        if (r.status == PIP_ST_CAPACITY && k + 1 < N_G) { cls[i] = k + 1; h_res[i].status = PIP_ST_PENDING; continue; }
+        cls[i] = 1000;                       /* final */
+        out.res[i] = r;
+        out.base[i] = (const PipCell *)chunk.p;
+      }
+      if (pending == 0) {
+        /* re-arm the escalated problems on the device */
+        bool any_escalated = false;
+        for (int q = 0; q < m; q++) if (cls[order[q]] == k + 1) { any_escalated = true; break; }
+        if (any_escalated) {
+          CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
+          CK(cudaStreamSynchronize(s));
+        }
+        break;
+      }
+      CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    }
+  }
+  CK(cudaEventElapsedTime(&out.times.device_ms, E.ev0, E.ev1));
+  /* anything still unsolved is too large for the ladder */
+  for (size_t i = 0; i < n; i++)
+    if (cls[i] != 1000) { out.res[i] = PipResult(); out.res[i].status = PIP_ST_CAPACITY; }
+  out.times.total = now_s() - t_begin;
+}

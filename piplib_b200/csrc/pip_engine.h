@@ -1,0 +1,56 @@
+/* Host-side batch engine: owns the device buffers, drives the size-class ladder
+ * (S: shared-memory arenas, G3..G8: global-memory arenas of growing capacity), compacts and
+ * fetches the solution cells.  Internal to the library (the C-ABI is include/piplib_b200.h). */
+#ifndef PIP_ENGINE_H
+#define PIP_ENGINE_H
+
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "pip_types.h"
+
+struct PipBatchIn {
+  size_t n = 0;
+  const PipProblem *h_prob = nullptr;   /* host descriptors: always required (class planning) */
+  const pip_i64 *h_pool = nullptr;      /* host pool, uploaded unless d_pool is given */
+  size_t pool_words = 0;
+  const PipProblem *d_prob = nullptr;   /* optional device-resident copies */
+  const pip_i64 *d_pool = nullptr;
+  bool fetch_cells = true;              /* copy the compacted cells back to the host */
+  int sol_size = PIP_SOL_SIZE, maxcol = PIP_MAXCOL;
+};
+
+struct PipBatchTimes {
+  double h2d = 0, kernel = 0, d2h = 0, total = 0;   /* seconds, wall clock around synchronised phases */
+  float device_ms = 0;                               /* CUDA-event time first launch -> last kernel */
+  int launches = 0, rounds = 0;
+  size_t h2d_bytes = 0, d2h_bytes = 0;
+};
+
+struct PipBatchOut {
+  std::vector<PipResult> res;           /* cell_off indexes cells_of() storage */
+  std::vector<const PipCell *> base;    /* per problem: base pointer of its round's host chunk */
+  PipBatchTimes times;
+  const PipCell *cells_of(size_t i) const { return base[i] + res[i].cell_off; }
+};
+
+class PipEngine {
+ public:
+  static PipEngine &get();
+  /* Runs the whole ladder.  Host cell storage referenced by `out` is engine-owned pinned memory,
+   * valid until the next run() call.  Throws std::runtime_error on CUDA errors. */
+  void run(const PipBatchIn &in, PipBatchOut &out);
+  int set_device(int dev);
+  int sm_count();
+  cudaStream_t stream();
+  struct Impl;
+
+ private:
+  PipEngine();
+  Impl *impl_;
+};
+
+void pip_cuda_check(cudaError_t e, const char *what);
+
+#endif

@@ -1,0 +1,813 @@
+/* The C-ABI of piplib-b200 (include/piplib/piplib.h, include/piplib_b200.h).
+ *
+ * Host side of the boundary only: PolyLib matrix -> tableau conversion, option rewriting,
+ * cell stream -> PipQuast decoding, printers, allocation.  All solving happens on the GPU
+ * (pip_engine.cpp + pip_kernels.cu); there is no CPU solver in this library.
+ *
+ * Reference behaviour restated here (paths relative to the reference tree):
+ *   pip_solve_xx            source/piplib.c:722-880
+ *   tab_Matrix2Tableau_xx   source/tab.c:292-393
+ *   sol_quast_edit_xx & co  source/sol.c:435-734   sol_simplify_xx source/sol.c:236-288
+ *   printers / alloc / free source/piplib.c:176-619
+ */
+#include <ctype.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <thread>
+#include <vector>
+
+#include "../../include/piplib_b200.h"
+#include "pip_engine.h"
+
+typedef long long I;
+
+namespace {
+
+enum { S_SHIFT = 1, S_NEGATE = 2, S_REMOVE = 4, S_DUAL = 8 };   /* source/sol.h:35-48 */
+
+I gcd_abs(I a, I b)
+{
+  unsigned long long x = a < 0 ? 0ull - (unsigned long long)a : (unsigned long long)a;
+  unsigned long long y = b < 0 ? 0ull - (unsigned long long)b : (unsigned long long)b;
+  while (y) { unsigned long long r = x % y; x = y; y = r; }
+  return (I)x;
+}
+
+void *xmalloc(size_t n)
+{
+  void *p = malloc(n ? n : 1);
+  if (!p) { fprintf(stderr, "Memory Overflow.\n"); exit(1); }
+  return p;
+}
+
+/* what pip_solve derives from (domain, context, Bg, options) before any tableau exists,
+ * source/piplib.c:758-797 */
+struct Shape {
+  int Np, Nn, Nl, Nm, Bg, Shift, Urs, sol_flags, nq, flags;
+  bool has_ctx;
+};
+
+struct MatView { int rows, cols; const I *const *row; const I *dense; };
+inline I MV(const MatView &m, int i, int j) { return m.row ? m.row[i][j] : m.dense[(size_t)i * m.cols + j]; }
+
+Shape derive_shape(const MatView &dom, const MatView *ctx, int Bg, const PipOptions_dp &o)
+{
+  Shape s;
+  memset(&s, 0, sizeof s);
+  s.has_ctx = ctx != nullptr;
+  s.Np = ctx ? ctx->cols - 2 : 0;
+  s.Nn = dom.cols - s.Np - 2;
+  s.Nl = dom.rows;
+  for (int i = 0; i < dom.rows; i++) if (MV(dom, i, 0) == 0) s.Nl++;
+  if (o.Maximize) { s.sol_flags |= S_SHIFT | S_NEGATE; s.Shift = 1; }
+  else if (o.Urs_unknowns) { s.sol_flags |= S_SHIFT; s.Shift = -1; }
+  if (o.Urs_parms) { s.Urs = s.Np - (Bg >= 0); s.Np += s.Urs; }
+  if (o.Maximize || o.Urs_unknowns)
+    if (Bg < 0) { Bg = dom.cols - 1; s.Np++; s.sol_flags |= S_REMOVE; }
+  s.Bg = Bg;
+  s.Nm = 0;
+  if (ctx) { s.Nm = ctx->rows; for (int i = 0; i < ctx->rows; i++) if (MV(*ctx, i, 0) == 0) s.Nm++; }
+  s.nq = o.Nq;
+  s.flags = 0;
+  if (o.Nq) s.flags |= PIP_F_INT;
+  else if (o.Compute_dual) { s.flags |= PIP_F_DUAL; s.sol_flags |= S_DUAL; }
+  if (o.Deepest_cut) s.flags |= PIP_F_DEEPEST;
+  return s;
+}
+
+/* tab_Matrix2Tableau_xx (source/tab.c:292-393) writing `width`-wide rows to out.
+ * ctx_mode: the matrix is the context (n == -1 in the reference). */
+void matrix_to_rows(const MatView &mx, I *out, int width, int Nv, bool ctx_mode, int Shift, int Bg, int Urs)
+{
+  const int ctx = ctx_mode ? 1 : 0;
+  int ncolm = mx.cols - 1;
+  const bool isnew = Shift && (Bg + ctx > 0) && ((unsigned)(Bg + ctx) > (unsigned)(mx.cols - 2));
+  if (isnew) ncolm++;
+  int cst;
+  if (ctx) { Shift = 0; cst = Nv + Urs; } else cst = Nv;
+  int cur = 0;
+  for (int i = 0; i < mx.rows; i++) {
+    I *r = out + (size_t)cur * width;
+    for (int j = 0; j < width; j++) r[j] = 0;
+    I big = 0;
+    const bool ineq = MV(mx, i, 0) != 0;
+    int j;
+    for (j = 0; j < Nv; j++) {
+      if (isnew && j == Bg) continue;
+      if (Shift) big += MV(mx, i, 1 + j);
+      r[j] = Shift > 0 ? -MV(mx, i, 1 + j) : MV(mx, i, 1 + j);
+    }
+    int k = Nv + 1;
+    for (j = Nv + 1; j < ncolm; j++) {
+      if (isnew && j == Bg) continue;
+      r[j] = MV(mx, i, k);
+      k++;
+    }
+    for (j = 0; j < Urs; j++) {
+      int pos_n = ncolm - ctx + j, pos = pos_n - Urs;
+      if (pos <= Bg) --pos;
+      r[pos_n] = -r[pos];
+    }
+    r[cst] = MV(mx, i, mx.cols - 1);
+    if (Shift) {
+      if (Shift < 0) big = -big;
+      if (isnew) r[Bg] = big; else r[Bg] += big;
+    }
+    cur++;
+    if (!ineq) {
+      I *r2 = out + (size_t)cur * width;
+      for (j = 0; j < width; j++) r2[j] = -r[j];
+      cur++;
+    }
+  }
+}
+
+/* words one problem contributes to the pool */
+size_t problem_words(const Shape &s) { return (size_t)s.Nl * (s.Nn + s.Np + 1) + (size_t)s.Nm * (s.Np + 1); }
+
+void fill_problem(const MatView &dom, const MatView *ctx, const Shape &s, PipProblem &P, I *pool, size_t off)
+{
+  P.nvar = s.Nn; P.nparm = s.Np; P.ni = s.Nl; P.nc = s.Nm; P.bigparm = s.Bg; P.flags = s.flags; P.off = (I)off;
+  I *tab = pool + off;
+  matrix_to_rows(dom, tab, s.Nn + s.Np + 1, s.Nn, false, s.Shift, s.Bg, s.Urs);
+  if (ctx && s.Nm)
+    matrix_to_rows(*ctx, tab + (size_t)s.Nl * (s.Nn + s.Np + 1), s.Np + 1, s.Np - s.Urs, true, s.Shift, s.Bg - s.Nn - 1, s.Urs);
+}
+
+/* ---- cells -> tree: source/sol.c:435-734 ------------------------------------------------- */
+struct Cells { std::vector<PipCell> own; const PipCell *c; int n; };
+
+int skip_obj(const PipCell *c, int i);
+int skip_new(const PipCell *c, int i) { return c[i].kind != PIP_C_NEW ? i : skip_obj(c, i + 1); }
+int skip_obj(const PipCell *c, int i)
+{
+  while (c[i].kind == PIP_C_FREE || c[i].kind == PIP_C_ERROR) i++;
+  switch (c[i].kind) {
+  case PIP_C_NIL: case PIP_C_VAL: i++; break;
+  case PIP_C_NEW: i = skip_new(c, i); break;
+  case PIP_C_IF: i = skip_obj(c, i + 1); i = skip_obj(c, i); i = skip_obj(c, i); break;
+  case PIP_C_LIST: case PIP_C_FORM: { int n = (int)c[i].p1; i++; while (n--) i = skip_obj(c, i); break; }
+  case PIP_C_DIV: i = skip_obj(c, i + 1); i = skip_obj(c, i); break;
+  }
+  return skip_new(c, i);
+}
+/* sol_simplify_xx, source/sol.c:272-288 (works on a private copy of the cells) */
+void simplify_cells(PipCell *c, int &ncell, int i)
+{
+  if (c[i].kind != PIP_C_IF) return;
+  int j = skip_obj(c, i + 1), k = skip_obj(c, j);
+  simplify_cells(c, ncell, k);
+  simplify_cells(c, ncell, j);
+  if (c[j].kind == PIP_C_NIL && c[k].kind == PIP_C_NIL) {
+    c[i].kind = PIP_C_NIL;
+    if (k >= ncell - 1) ncell = i + 1;
+    else for (int l = i + 1; l <= k; l++) c[l].kind = PIP_C_FREE;
+  }
+}
+
+PipVector_dp *decode_vector(const PipCell *c, int *i, int Bg, int Urs_p, int flags)
+{
+  int n = (int)c[*i].p1, unbounded = 0;
+  if (flags & S_REMOVE) --n;
+  n -= Urs_p;
+  const int first_urs = Urs_p + (Bg >= 0);
+  PipVector_dp *v = (PipVector_dp *)xmalloc(sizeof *v);
+  v->nb_elements = n;
+  v->the_vector = (I *)xmalloc(sizeof(I) * (n > 0 ? n : 0));
+  v->the_deno = (I *)xmalloc(sizeof(I) * (n > 0 ? n : 0));
+  for (int j = 0, k = 0; k < n; j++) {
+    (*i)++;
+    I N = c[*i].p1, D = c[*i].p2, d = gcd_abs(N, D);
+    if ((flags & S_SHIFT) && j == Bg) { N -= D; if (N != 0) unbounded = 1; }
+    if ((flags & S_REMOVE) && j == Bg) continue;
+    if (first_urs <= j && j < first_urs + Urs_p) continue;
+    v->the_vector[k] = d ? N / d : 0;
+    if (flags & S_NEGATE) v->the_vector[k] = -v->the_vector[k];
+    v->the_deno[k] = (d == D) ? 1 : (d ? D / d : 0);
+    k++;
+  }
+  if (unbounded) for (int k = 0; k < n; k++) v->the_deno[k] = 0;
+  (*i)++;
+  return v;
+}
+
+PipQuast_dp *decode_quast(const PipCell *c, int *i, PipQuast_dp *father, int Bg, int Urs_p, int flags)
+{
+  while (c[*i].kind == PIP_C_FREE) (*i)++;
+  PipQuast_dp *q = (PipQuast_dp *)xmalloc(sizeof *q);
+  q->newparm = nullptr; q->list = nullptr; q->condition = nullptr;
+  q->next_then = q->next_else = nullptr; q->father = father;
+  PipNewparm_dp *last = nullptr;
+  while (c[*i].kind == PIP_C_NEW) {                  /* sol_newparm_edit_xx, source/sol.c:525-577 */
+    const int newcell = *i;
+    (*i) += 2;
+    PipNewparm_dp *np = (PipNewparm_dp *)xmalloc(sizeof *np);
+    np->vector = decode_vector(c, i, Bg, Urs_p, flags & S_REMOVE);
+    np->rank = (int)c[newcell].p1;
+    np->deno = c[*i].p1;
+    if (flags & S_REMOVE) np->rank--;
+    np->rank -= Urs_p;
+    np->next = nullptr;
+    if (last) last->next = np; else q->newparm = np;
+    last = np;
+    (*i)++;
+  }
+  const int kind = c[*i].kind;
+  const int nb = (int)c[*i].p1;
+  (*i)++;
+  if (kind == PIP_C_LIST) {                           /* sol_list_edit_xx, source/sol.c:591-638 */
+    PipList_dp *head = (PipList_dp *)xmalloc(sizeof *head), *cur = head;
+    head->next = nullptr; head->vector = nullptr;
+    if (nb > 0) {
+      head->vector = decode_vector(c, i, Bg, Urs_p, flags);
+      for (int e = 1; e < nb; e++) {
+        PipList_dp *l = (PipList_dp *)xmalloc(sizeof *l);
+        l->vector = decode_vector(c, i, Bg, Urs_p, flags);
+        l->next = nullptr;
+        cur->next = l; cur = l;
+      }
+    }
+    q->list = head;
+    if (flags & S_DUAL) q->next_then = decode_quast(c, i, q, Bg, Urs_p, 0);
+  } else if (kind == PIP_C_NIL) {
+  } else if (kind == PIP_C_IF) {
+    q->condition = decode_vector(c, i, Bg, Urs_p, flags & S_REMOVE);
+    q->next_then = decode_quast(c, i, q, Bg, Urs_p, flags);
+    q->next_else = decode_quast(c, i, q, Bg, Urs_p, flags);
+  } else {
+    fprintf(stderr, "\nAie !!! Flag %d inattendu.\n", kind);
+    exit(1);
+  }
+  return q;
+}
+
+/* serialisation (the word format of oracle/ref_harness.c) */
+struct Ser { I *out; long cap, len; unsigned long long h; bool hashing; };
+inline void sput(Ser &s, I v)
+{
+  if (s.hashing) {
+    unsigned long long x = (unsigned long long)v;
+    for (int i = 0; i < 8; i++) { s.h ^= (x >> (8 * i)) & 0xff; s.h *= 0x100000001b3ULL; }
+  }
+  if (s.out && s.len < s.cap) s.out[s.len] = v;
+  s.len++;
+}
+void ser_vec(Ser &s, const PipVector_dp *v)
+{
+  sput(s, v->nb_elements);
+  for (int i = 0; i < v->nb_elements; i++) { sput(s, v->the_vector[i]); sput(s, v->the_deno[i]); }
+}
+void ser_quast(Ser &s, const PipQuast_dp *q)
+{
+  if (!q) { sput(s, -1); return; }
+  long n = 0;
+  for (const PipNewparm_dp *np = q->newparm; np; np = np->next) n++;
+  sput(s, n);
+  for (const PipNewparm_dp *np = q->newparm; np; np = np->next) { sput(s, np->rank); sput(s, np->deno); ser_vec(s, np->vector); }
+  if (q->condition) { sput(s, 2); ser_vec(s, q->condition); ser_quast(s, q->next_then); ser_quast(s, q->next_else); }
+  else if (q->list) {
+    sput(s, 1);
+    n = 0; for (const PipList_dp *l = q->list; l; l = l->next) n++;
+    sput(s, n);
+    for (const PipList_dp *l = q->list; l; l = l->next) { sput(s, l->vector != nullptr); if (l->vector) ser_vec(s, l->vector); }
+    sput(s, q->next_then != nullptr);
+    if (q->next_then) ser_quast(s, q->next_then);
+  } else sput(s, 0);
+}
+
+const char *fatal_message(int status)
+{
+  switch (status) {
+  case PIP_ST_FATAL + 1: return "Integer overflow\n";
+  case PIP_ST_FATAL + 2: return "Too much parameters\n";
+  case PIP_ST_FATAL + 3: return "Too many variables\n";
+  case PIP_ST_FATAL + 26: return "The solution is too complex! : sol\n";
+  case PIP_ST_FAULT: return "Floating point exception\n";
+  case PIP_ST_CAPACITY: return "piplib-b200: problem exceeds the largest device size class\n";
+  case PIP_ST_UNSUPPORTED: return "piplib-b200: option not implemented on the device (Compute_dual / Deepest_cut)\n";
+  }
+  return "piplib-b200: solver error\n";
+}
+
+PipBatchStats_dp g_stats;
+
+void account(const PipBatchOut &out, double host_seconds)
+{
+  PipBatchStats_dp s;
+  memset(&s, 0, sizeof s);
+  for (const PipResult &r : out.res) {
+    s.pivots += r.pivots; s.cuts += r.cuts; s.subsolves += r.subsolves; s.splits += r.splits;
+    s.elem_updates += ((unsigned long long)r.elem_updates_hi << 32) | r.elem_updates_lo;
+    s.max_rows = std::max(s.max_rows, r.max_rows);
+    s.max_cols = std::max(s.max_cols, r.max_cols);
+  }
+  s.seconds_h2d = out.times.h2d; s.seconds_kernel = out.times.kernel; s.seconds_d2h = out.times.d2h;
+  s.seconds_host = host_seconds;
+  s.launches = out.times.launches; s.rounds = out.times.rounds;
+  s.device_ms = out.times.device_ms;
+  s.h2d_bytes = out.times.h2d_bytes; s.d2h_bytes = out.times.d2h_bytes;
+  g_stats = s;
+}
+
+template <class F>
+void parallel_for(size_t n, F f)
+{
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>(hw ? hw : 1, (n + 255) / 256);
+  if (nt <= 1) { f(0, n); return; }
+  std::vector<std::thread> th;
+  size_t chunk = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; t++) {
+    size_t a = t * chunk, b = std::min(n, a + chunk);
+    if (a >= b) break;
+    th.emplace_back([=] { f(a, b); });
+  }
+  for (auto &t : th) t.join();
+}
+
+const PipOptions_dp DEFAULT_OPTIONS = {1, 0, 0, 0, 0, 0, 0, 0};
+
+}  // namespace
+
+extern "C" {
+
+/* ---- reference API ------------------------------------------------------------------------ */
+void pip_init_dp(void) {}
+void pip_close_dp(void) {}
+
+PipOptions_dp *pip_options_init_dp(void)
+{
+  PipOptions_dp *o = (PipOptions_dp *)xmalloc(sizeof *o);
+  *o = DEFAULT_OPTIONS;
+  return o;
+}
+void pip_options_free_dp(PipOptions_dp *o) { free(o); }
+void pip_options_print_dp(FILE *f, PipOptions_dp *o)
+{
+  fprintf(f, "Option setting is:\n");
+  fprintf(f, "Nq          =%d\n", o->Nq);
+  fprintf(f, "Verbose     =%d\n", o->Verbose);
+  fprintf(f, "Simplify    =%d\n", o->Simplify);
+  fprintf(f, "Deepest_cut =%d\n", o->Deepest_cut);
+  fprintf(f, "Maximize    =%d\n", o->Maximize);
+  fprintf(f, "Urs_parms   =%d\n", o->Urs_parms);
+  fprintf(f, "Urs_unknowns=%d\n", o->Urs_unknowns);
+  fprintf(f, "\n");
+}
+
+PipMatrix_dp *pip_matrix_alloc_dp(unsigned rows, unsigned cols)
+{
+  PipMatrix_dp *m = (PipMatrix_dp *)xmalloc(sizeof *m);
+  m->NbRows = rows; m->NbColumns = cols; m->p_Init_size = (int)(rows * cols);
+  m->p = nullptr; m->p_Init = nullptr;
+  if (rows && cols) {
+    m->p = (I **)xmalloc(sizeof(I *) * rows);
+    m->p_Init = (I *)xmalloc(sizeof(I) * (size_t)rows * cols);
+    memset(m->p_Init, 0, sizeof(I) * (size_t)rows * cols);
+    for (unsigned i = 0; i < rows; i++) m->p[i] = m->p_Init + (size_t)i * cols;
+  }
+  return m;
+}
+void pip_matrix_free_dp(PipMatrix_dp *m)
+{
+  if (!m) return;
+  free(m->p_Init); free(m->p); free(m);
+}
+void pip_matrix_print_dp(FILE *f, PipMatrix_dp *m)
+{
+  fprintf(f, "%d %d\n", m->NbRows, m->NbColumns);
+  for (unsigned i = 0; i < m->NbRows; i++) {
+    for (unsigned j = 0; j < m->NbColumns; j++) fprintf(f, " %lld", m->p[i][j]);
+    fprintf(f, "\n");
+  }
+}
+/* pip_matrix_read_xx, source/piplib.c:576-619: '#' comment lines, "rows cols", then one row per line */
+PipMatrix_dp *pip_matrix_read_dp(FILE *f)
+{
+  char s[1024];
+  unsigned rows = 0, cols = 0;
+  for (;;) {
+    if (!fgets(s, sizeof s, f)) { fprintf(stderr, "Not enough rows.\n"); exit(1); }
+    if (*s == '#' || *s == '\n') continue;
+    if (sscanf(s, " %u %u", &rows, &cols) >= 2) break;
+  }
+  PipMatrix_dp *m = pip_matrix_alloc_dp(rows, cols);
+  for (unsigned i = 0; i < rows; i++) {
+    char *c;
+    for (;;) {
+      if (!fgets(s, sizeof s, f)) { fprintf(stderr, "Not enough rows.\n"); exit(1); }
+      c = s;
+      while (isspace((unsigned char)*c) && *c != '\n') c++;
+      if (*c != '#' && *c != '\n' && *c != 0) break;
+    }
+    for (unsigned j = 0; j < cols; j++) {
+      char tok[1024]; int used = 0;
+      if (*c == 0 || *c == '#' || *c == '\n' || sscanf(c, "%1023s%n", tok, &used) < 1) {
+        fprintf(stderr, "Not enough columns.\n"); exit(1);
+      }
+      long long v = 0; sscanf(tok, "%lld", &v);
+      m->p[i][j] = v;
+      c += used;
+    }
+  }
+  return m;
+}
+
+void pip_vector_print_dp(FILE *f, PipVector_dp *v)
+{
+  if (!v) return;
+  fprintf(f, "#[");
+  for (int i = 0; i < v->nb_elements; i++) {
+    fprintf(f, " %lld", v->the_vector[i]);
+    if (v->the_deno[i] != 1) fprintf(f, "/%lld", v->the_deno[i]);
+  }
+  fprintf(f, "]");
+}
+void pip_newparm_print_dp(FILE *f, PipNewparm_dp *np, int indent)
+{
+  for (; np; np = np->next) {
+    for (int i = 0; i < indent; i++) fprintf(f, " ");
+    fprintf(f, "(newparm %d (div ", np->rank);
+    pip_vector_print_dp(f, np->vector);
+    fprintf(f, " %lld))\n", np->deno);
+  }
+}
+void pip_list_print_dp(FILE *f, PipList_dp *l, int indent)
+{
+  for (int i = 0; i < indent; i++) fprintf(f, " ");
+  if (!l) { fprintf(f, "()\n"); return; }
+  fprintf(f, "(list\n");
+  for (; l; l = l->next)
+    if (l->vector) {
+      for (int i = 0; i < indent + 1; i++) fprintf(f, " ");
+      pip_vector_print_dp(f, l->vector);
+      fprintf(f, "\n");
+    }
+  for (int i = 0; i < indent; i++) fprintf(f, " ");
+  fprintf(f, ")\n");
+}
+void pip_quast_print_dp(FILE *f, PipQuast_dp *q, int indent)
+{
+  const int ni = indent >= 0 ? indent + 1 : indent;
+  if (!q) { for (int i = 0; i < indent; i++) fprintf(f, " "); fprintf(f, "void\n"); return; }
+  pip_newparm_print_dp(f, q->newparm, indent);
+  if (!q->condition) {
+    pip_list_print_dp(f, q->list, indent);
+    if (q->next_then) pip_quast_print_dp(f, q->next_then, ni);
+  } else {
+    for (int i = 0; i < indent; i++) fprintf(f, " ");
+    fprintf(f, "(if ");
+    pip_vector_print_dp(f, q->condition);
+    fprintf(f, "\n");
+    pip_quast_print_dp(f, q->next_then, ni);
+    pip_quast_print_dp(f, q->next_else, ni);
+    for (int i = 0; i < indent; i++) fprintf(f, " ");
+    fprintf(f, ")\n");
+  }
+}
+
+void pip_vector_free_dp(PipVector_dp *v) { if (v) { free(v->the_vector); free(v->the_deno); free(v); } }
+void pip_newparm_free_dp(PipNewparm_dp *np)
+{
+  while (np) { PipNewparm_dp *n = np->next; pip_vector_free_dp(np->vector); free(np); np = n; }
+}
+void pip_list_free_dp(PipList_dp *l)
+{
+  while (l) { PipList_dp *n = l->next; pip_vector_free_dp(l->vector); free(l); l = n; }
+}
+void pip_quast_free_dp(PipQuast_dp *q)
+{
+  if (!q) return;
+  pip_newparm_free_dp(q->newparm);
+  pip_list_free_dp(q->list);
+  pip_vector_free_dp(q->condition);
+  pip_quast_free_dp(q->next_then);
+  pip_quast_free_dp(q->next_else);
+  free(q);
+}
+
+long pip_quast_serialize_dp(const PipQuast_dp *q, long long *out, long cap)
+{
+  Ser s = {out, cap, 0, 0, false};
+  ser_quast(s, q);
+  return s.len;
+}
+
+int pip_set_device_dp(int device) { return PipEngine::get().set_device(device); }
+const char *pip_b200_version(void) { return "piplib-b200 0.1 (sm_100a)"; }
+void pip_last_batch_stats_dp(PipBatchStats_dp *out) { if (out) *out = g_stats; }
+
+/* ---- batch entry points -------------------------------------------------------------------- */
+
+static PipQuast_dp *decode_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify)
+{
+  const PipResult &r = bo.res[i];
+  const PipCell *c = bo.cells_of(i);
+  int at = 0;
+  if (simplify) {
+    std::vector<PipCell> copy(c, c + r.ncells);
+    int n = r.ncells;
+    simplify_cells(copy.data(), n, 0);
+    return decode_quast(copy.data(), &at, nullptr, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
+  }
+  return decode_quast(c, &at, nullptr, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
+}
+
+int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const *contexts,
+                       const int *bignums, const PipOptions_dp *options, PipQuast_dp **out, int *status)
+{
+  if (n <= 0) return 0;
+  const PipOptions_dp &o = options ? *options : DEFAULT_OPTIONS;
+  try {
+    std::vector<Shape> shapes(n);
+    std::vector<PipProblem> prob(n);
+    std::vector<size_t> off(n + 1, 0);
+    std::vector<int> live;            /* problems that reach the device */
+    for (int i = 0; i < n; i++) {
+      out[i] = nullptr;
+      if (!domains[i]) { status[i] = PIP_STATUS_VOID; off[i + 1] = off[i]; continue; }
+      MatView d = {(int)domains[i]->NbRows, (int)domains[i]->NbColumns, domains[i]->p, nullptr};
+      MatView c, *cp = nullptr;
+      if (contexts && contexts[i]) { c = {(int)contexts[i]->NbRows, (int)contexts[i]->NbColumns, contexts[i]->p, nullptr}; cp = &c; }
+      shapes[i] = derive_shape(d, cp, bignums ? bignums[i] : -1, o);
+      off[i + 1] = off[i] + problem_words(shapes[i]);
+      live.push_back(i);
+    }
+    std::vector<I> pool(off[n] + 1);
+    std::vector<PipProblem> lp(live.size());
+    parallel_for(live.size(), [&](size_t a, size_t b) {
+      for (size_t q = a; q < b; q++) {
+        int i = live[q];
+        MatView d = {(int)domains[i]->NbRows, (int)domains[i]->NbColumns, domains[i]->p, nullptr};
+        MatView c, *cp = nullptr;
+        if (contexts && contexts[i]) { c = {(int)contexts[i]->NbRows, (int)contexts[i]->NbColumns, contexts[i]->p, nullptr}; cp = &c; }
+        fill_problem(d, cp, shapes[i], lp[q], pool.data(), off[i]);
+      }
+    });
+    PipBatchIn in;
+    in.n = live.size(); in.h_prob = lp.data(); in.h_pool = pool.data(); in.pool_words = off[n];
+    PipBatchOut bo;
+    PipEngine::get().run(in, bo);
+    double t0 = 0;
+    {
+      struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); t0 = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    parallel_for(live.size(), [&](size_t a, size_t b) {
+      for (size_t q = a; q < b; q++) {
+        int i = live[q];
+        status[i] = bo.res[q].status;
+        if (status[i] == PIP_ST_OK) out[i] = decode_one(bo, q, shapes[i], o.Simplify);
+      }
+    });
+    {
+      struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+      account(bo, ts.tv_sec + 1e-9 * ts.tv_nsec - t0);
+    }
+  } catch (const std::exception &e) {
+    fprintf(stderr, "%s\n", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+PipQuast_dp *pip_solve_dp(PipMatrix_dp *domain, PipMatrix_dp *context, int Bg, PipOptions_dp *options)
+{
+  if (!domain) return nullptr;
+  PipQuast_dp *q = nullptr;
+  int status = 0;
+  PipMatrix_dp *doms[1] = {domain}, *ctxs[1] = {context};
+  int bgs[1] = {Bg};
+  if (pip_solve_batch_dp(1, doms, ctxs, bgs, options, &q, &status) != 0) exit(1);
+  if (status == PIP_ST_OK || status == PIP_ST_VOID) return q;
+  /* the reference reports every error with a message and exit(code) */
+  fputs(fatal_message(status), stderr);
+  exit(status >= PIP_ST_FATAL && status < PIP_ST_FAULT ? status - PIP_ST_FATAL : 1);
+}
+
+int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long *const *tab,
+                         const long long *const *ctx, int *status, PipCell_dp *cells_out,
+                         long long cell_cap, long long *cell_off, int *ncells, long long *cells_needed)
+{
+  if (n <= 0) return 0;
+  try {
+    std::vector<PipProblem> prob(n);
+    std::vector<size_t> off(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+      const PipTableauHeader_dp &h = hdr[i];
+      off[i + 1] = off[i] + (size_t)h.ni * (h.nvar + h.nparm + 1) + (size_t)h.nc * (h.nparm + 1);
+    }
+    std::vector<I> pool(off[n] + 1);
+    for (int i = 0; i < n; i++) {
+      const PipTableauHeader_dp &h = hdr[i];
+      size_t tw = (size_t)h.ni * (h.nvar + h.nparm + 1), cw = (size_t)h.nc * (h.nparm + 1);
+      if (tw) memcpy(pool.data() + off[i], tab[i], tw * sizeof(I));
+      if (cw) memcpy(pool.data() + off[i] + tw, ctx[i], cw * sizeof(I));
+      PipProblem &P = prob[i];
+      P.nvar = h.nvar; P.nparm = h.nparm; P.ni = h.ni; P.nc = h.nc; P.bigparm = h.bigparm;
+      P.flags = h.nq ? PIP_F_INT : 0; P.off = (I)off[i];
+    }
+    PipBatchIn in;
+    in.n = n; in.h_prob = prob.data(); in.h_pool = pool.data(); in.pool_words = off[n];
+    PipBatchOut bo;
+    PipEngine::get().run(in, bo);
+    long long total = 0;
+    for (int i = 0; i < n; i++) total += bo.res[i].ncells;
+    if (cells_needed) *cells_needed = total;
+    long long at = 0;
+    for (int i = 0; i < n; i++) {
+      status[i] = bo.res[i].status;
+      ncells[i] = bo.res[i].ncells;
+      cell_off[i] = at;
+      if (at + bo.res[i].ncells <= cell_cap && bo.res[i].ncells)
+        memcpy(cells_out + at, bo.cells_of(i), sizeof(PipCell) * bo.res[i].ncells);
+      at += bo.res[i].ncells;
+    }
+    account(bo, 0);
+    if (total > cell_cap) return -2;
+  } catch (const std::exception &e) {
+    fprintf(stderr, "%s\n", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+/* ---- dense batches -------------------------------------------------------------------------- */
+namespace {
+struct DenseBatch {
+  long long n = 0;
+  std::vector<Shape> shapes;
+  std::vector<PipProblem> prob;
+  std::vector<I> pool;
+  size_t pool_words = 0;
+  int simplify = 0;
+  PipOptions_dp opt;
+};
+
+void build_dense(DenseBatch &B, long long n, int dr, int dc, const I *dom, int has_ctx, int cr, int cc,
+                 const I *ctx, int bignum, const PipOptions_dp *options)
+{
+  B.n = n;
+  B.opt = options ? *options : DEFAULT_OPTIONS;
+  B.simplify = B.opt.Simplify;
+  B.shapes.resize(n);
+  B.prob.resize(n);
+  std::vector<size_t> off(n + 1, 0);
+  for (long long i = 0; i < n; i++) {
+    MatView d = {dr, dc, nullptr, dom + (size_t)i * dr * dc};
+    MatView c = {cr, cc, nullptr, has_ctx ? ctx + (size_t)i * cr * cc : nullptr};
+    B.shapes[i] = derive_shape(d, has_ctx ? &c : nullptr, bignum, B.opt);
+    off[i + 1] = off[i] + problem_words(B.shapes[i]);
+  }
+  B.pool.resize(off[n] + 1);
+  B.pool_words = off[n];
+  parallel_for((size_t)n, [&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      MatView d = {dr, dc, nullptr, dom + i * dr * dc};
+      MatView c = {cr, cc, nullptr, has_ctx ? ctx + i * cr * cc : nullptr};
+      fill_problem(d, has_ctx ? &c : nullptr, B.shapes[i], B.prob[i], B.pool.data(), off[i]);
+    }
+  });
+}
+
+/* decode every solved problem, hash / serialise its quast; returns words needed */
+long long emit_results(const DenseBatch &B, const PipBatchOut &bo, int *status, unsigned long long *hashes,
+                       long long *ser, long long ser_cap, long long *ser_off)
+{
+  const size_t n = (size_t)B.n;
+  std::vector<long long> words(n, 0);
+  /* pass 1: hash + size */
+  parallel_for(n, [&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      status[i] = bo.res[i].status;
+      unsigned long long h = 0;
+      long long w = 0;
+      if (status[i] == PIP_ST_OK || status[i] == PIP_ST_VOID) {
+        PipQuast_dp *q = status[i] == PIP_ST_OK ? decode_one(bo, i, B.shapes[i], B.simplify) : nullptr;
+        Ser s = {nullptr, 0, 0, 0xcbf29ce484222325ULL, true};
+        ser_quast(s, q);
+        h = s.h; w = s.len;
+        pip_quast_free_dp(q);
+      }
+      if (hashes) hashes[i] = h;
+      words[i] = w;
+    }
+  });
+  long long total = 0;
+  if (ser_off) {
+    for (size_t i = 0; i < n; i++) { ser_off[i] = total; total += words[i]; }
+    ser_off[n] = total;
+  } else for (size_t i = 0; i < n; i++) total += words[i];
+  if (ser && ser_off && total <= ser_cap) {
+    parallel_for(n, [&](size_t a, size_t b) {
+      for (size_t i = a; i < b; i++) {
+        if (!(status[i] == PIP_ST_OK || status[i] == PIP_ST_VOID)) continue;
+        PipQuast_dp *q = status[i] == PIP_ST_OK ? decode_one(bo, i, B.shapes[i], B.simplify) : nullptr;
+        Ser s = {ser + ser_off[i], (long)words[i], 0, 0, false};
+        ser_quast(s, q);
+        pip_quast_free_dp(q);
+      }
+    });
+  }
+  return total;
+}
+
+double wall()
+{
+  struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+}  // namespace
+
+int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long *dom,
+                       int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
+                       int bignum, const PipOptions_dp *options,
+                       int *status, unsigned long long *hashes,
+                       long long *ser, long long ser_cap, long long *ser_off)
+{
+  if (n <= 0) return 0;
+  try {
+    double t0 = wall();
+    DenseBatch B;
+    build_dense(B, n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum, options);
+    double t1 = wall();
+    PipBatchIn in;
+    in.n = (size_t)n; in.h_prob = B.prob.data(); in.h_pool = B.pool.data(); in.pool_words = B.pool_words;
+    PipBatchOut bo;
+    PipEngine::get().run(in, bo);
+    double t2 = wall();
+    long long total = emit_results(B, bo, status, hashes, ser, ser_cap, ser_off);
+    account(bo, (t1 - t0) + (wall() - t2));
+    if (ser && total > ser_cap) return -2;
+  } catch (const std::exception &e) {
+    fprintf(stderr, "%s\n", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+struct pip_device_batch {
+  DenseBatch B;
+  PipProblem *d_prob = nullptr;
+  I *d_pool = nullptr;
+  PipBatchOut last;
+  bool fetched = false;
+};
+
+pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_cols, const long long *dom,
+                                          int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
+                                          int bignum, const PipOptions_dp *options)
+{
+  try {
+    pip_device_batch *b = new pip_device_batch;
+    build_dense(b->B, n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum, options);
+    PipEngine::get().sm_count();                      /* initialises the device */
+    pip_cuda_check(cudaMalloc((void **)&b->d_prob, sizeof(PipProblem) * (size_t)n), "cudaMalloc(problems)");
+    pip_cuda_check(cudaMalloc((void **)&b->d_pool, sizeof(I) * (b->B.pool_words + 1)), "cudaMalloc(pool)");
+    pip_cuda_check(cudaMemcpy(b->d_prob, b->B.prob.data(), sizeof(PipProblem) * (size_t)n, cudaMemcpyHostToDevice), "H2D problems");
+    pip_cuda_check(cudaMemcpy(b->d_pool, b->B.pool.data(), sizeof(I) * b->B.pool_words, cudaMemcpyHostToDevice), "H2D pool");
+    return b;
+  } catch (const std::exception &e) {
+    fprintf(stderr, "%s\n", e.what());
+    return nullptr;
+  }
+}
+
+int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
+{
+  try {
+    PipBatchIn in;
+    in.n = (size_t)b->B.n; in.h_prob = b->B.prob.data();
+    in.d_prob = b->d_prob; in.d_pool = b->d_pool;
+    in.fetch_cells = fetch_cells != 0;
+    PipEngine::get().run(in, b->last);
+    b->fetched = fetch_cells != 0;
+    if (device_ms) *device_ms = b->last.times.device_ms;
+    account(b->last, 0);
+  } catch (const std::exception &e) {
+    fprintf(stderr, "%s\n", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long long *hashes)
+{
+  if (b->last.res.size() != (size_t)b->B.n) return -1;
+  if (hashes && !b->fetched) return -3;
+  if (hashes) emit_results(b->B, b->last, status, hashes, nullptr, 0, nullptr);
+  else for (size_t i = 0; i < (size_t)b->B.n; i++) status[i] = b->last.res[i].status;
+  return 0;
+}
+
+void pip_device_batch_destroy(pip_device_batch *b)
+{
+  if (!b) return;
+  cudaFree(b->d_prob); cudaFree(b->d_pool);
+  delete b;
+}
+
+}  // extern "C"

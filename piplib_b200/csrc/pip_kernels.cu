@@ -1,0 +1,131 @@
+/* sm_100a kernels of the batched PipLib solver core and their launch wrappers.
+ *
+ *   pip_solve_kernel<true>   size class S: one problem per warp, working set in shared memory
+ *   pip_solve_kernel<false>  size class G: one problem per warp, working set in global memory
+ *                            (L1/L2 resident; for tableaus that outgrow a shared-memory arena)
+ *   pip_gather_kernel        compacts the per-warp cell windows into one contiguous stream in
+ *                            problem order, so the device-to-host copy is a single memcpy
+ *   pip_scan kernels         exclusive scan of the per-problem cell counts
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pip_kernels.h"
+#include "pip_warp_main.h"
+
+extern __shared__ __align__(16) unsigned char pip_smem[];
+
+template <bool SH>
+__global__ void __launch_bounds__(PIP_WARPS_PER_CTA_MAX * 32)
+pip_solve_kernel(const PipLaunch L)
+{
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int warp_id = blockIdx.x * warps_per_cta + warp_in_cta;
+  pip_i64 *arena;
+  if (SH) arena = (pip_i64 *)pip_smem + (size_t)warp_in_cta * L.work_words;
+  else arena = L.gwork + (size_t)warp_id * L.work_words;
+  pip_warp_main(L, warp_id, arena);
+}
+
+extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, int ctas, int warps_per_cta,
+                                        cudaStream_t stream)
+{
+  if (shared_class) {
+    size_t smem = (size_t)warps_per_cta * L->work_words * sizeof(pip_i64);
+    cudaError_t e = cudaFuncSetAttribute(pip_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pip_solve_kernel<true><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
+  } else {
+    pip_solve_kernel<false><<<ctas, warps_per_cta * 32, 0, stream>>>(*L);
+  }
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t pip_solve_occupancy(int shared_class, int warps_per_cta, size_t smem_bytes, int *ctas_per_sm)
+{
+  if (shared_class) {
+    cudaError_t e = cudaFuncSetAttribute(pip_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<true>, warps_per_cta * 32, smem_bytes);
+  }
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<false>, warps_per_cta * 32, 0);
+}
+
+/* words of working arena a problem needs at a slack level (host-side planning) */
+extern "C" long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level)
+{
+  PipLayout L;
+  pip_layout(nvar, nparm, ni, nc, flags, level, 0x7fffffff, L);
+  return L.total;
+}
+
+/* ---- cell gather ------------------------------------------------------------------------ */
+/* one warp per problem: copy its cells (24-byte records = 3 words) to out[dst_off[p]...] */
+__global__ void pip_gather_kernel(PipResult *res, const int *order, const PipCell *cells,
+                                  const long long *dst_off, PipCell *out, int nprob)
+{
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int q = warp; q < nprob; q += nwarps) {
+    const int p = order ? order[q] : q;
+    const PipResult r = res[p];
+    const long long *src = (const long long *)(cells + r.cell_off);
+    long long *dst = (long long *)(out + dst_off[q]);
+    const int words = r.ncells * 3;
+    for (int w = lane; w < words; w += 32) dst[w] = src[w];
+    __syncwarp();
+    if (lane == 0) res[p].cell_off = dst_off[q];      /* now relative to the compact stream */
+  }
+}
+
+/* single-CTA exclusive scan of ncells (n up to a few million: 1024 threads, chunked) */
+__global__ void pip_scan_kernel(const PipResult *res, const int *order, long long *dst_off, int nprob, long long *total)
+{
+  __shared__ long long warp_sums[32];
+  __shared__ long long carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nprob; base += blockDim.x) {
+    const int i = base + tid;
+    long long v = (i < nprob) ? (long long)res[order ? order[i] : i].ncells : 0;
+    long long x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      long long s = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+      }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const long long before = carry + (wid ? warp_sums[wid - 1] : 0) + (x - v);
+    if (i < nprob) dst_off[i] = before;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry = before + v;
+    __syncthreads();
+  }
+  if (tid == 0) *total = carry;
+}
+
+extern "C" cudaError_t pip_launch_gather(PipResult *res, const int *order, const PipCell *cells, long long *dst_off,
+                                         PipCell *out, int nprob, long long *total, int phase,
+                                         cudaStream_t stream)
+{
+  if (phase == 0) pip_scan_kernel<<<1, 1024, 0, stream>>>(res, order, dst_off, nprob, total);
+  else {
+    int blocks = (nprob + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    pip_gather_kernel<<<blocks, 256, 0, stream>>>(res, order, cells, dst_off, out, nprob);
+  }
+  return cudaGetLastError();
+}

@@ -1,0 +1,22 @@
+/* internal launch interface between the host layer (pip_host.cpp) and the kernels */
+#ifndef PIP_KERNELS_H
+#define PIP_KERNELS_H
+
+#include <cuda_runtime.h>
+
+#include "pip_types.h"
+
+#define PIP_WARPS_PER_CTA_MAX 8
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, int ctas, int warps_per_cta, cudaStream_t stream);
+cudaError_t pip_solve_occupancy(int shared_class, int warps_per_cta, size_t smem_bytes, int *ctas_per_sm);
+cudaError_t pip_launch_gather(PipResult *res, const int *order, const PipCell *cells, long long *dst_off,
+                              PipCell *out, int nprob, long long *total, int phase, cudaStream_t stream);
+long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -48,7 +48,7 @@ struct PipStats {
 };
 
 /* capacity slack per level: {new parameters, main cut rows, extra context rows, sub cut rows} */
-PIP_DEV void pip_slack(int level, int &dp, int &dr, int &dx, int &ds)
+PIP_HD void pip_slack(int level, int &dp, int &dr, int &dx, int &ds)
 {
   if (level >= 3) {
     const int k = level - 3 > 5 ? 5 : level - 3;      /* classes G3..G8 grow geometrically */
@@ -67,7 +67,7 @@ struct PipLayout {
 };
 
 /* Carve the arena for one problem.  Returns false when even this slack level does not fit. */
-PIP_DEV bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level, int words, PipLayout &L)
+PIP_HD bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level, int words, PipLayout &L)
 {
   int dp, dr, dx, ds;
   pip_slack(level, dp, dr, dx, ds);

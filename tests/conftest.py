@@ -7,6 +7,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+EMU = os.path.join(ROOT, "tests", "emu")
+if EMU not in sys.path:
+    sys.path.insert(0, EMU)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 

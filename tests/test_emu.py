@@ -1,0 +1,49 @@
+"""The device source of the solver (piplib_b200/csrc/pip_solver.h) executed on the CPU by the
+fiber emulator in tests/emu (32 cooperative fibers = one warp), against the reference's golden
+vectors.  This keeps the kernel logic under test in the no-GPU CI run; it is a debugging aid,
+not a product path (the shared library has no CPU solver).  Lane scheduling order is permuted
+to expose missing warp synchronisation."""
+import pytest
+
+from conftest import load_golden
+from oracle import pyoracle as po
+import emu
+
+CLI = [c for c in load_golden("cli_suite.json")
+       if "pipFile" not in c["name"] and not c["name"].startswith(("boulet", "challenges"))]
+RCLI = load_golden("random_cli.json")
+HEAVY = {"randt64", "randt108", "randt334"}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    emu.build()
+
+
+@pytest.mark.parametrize("order_mode", [0, 1, 2])
+def test_cli_fixtures(order_mode):
+    out = emu.solve_tableau_cases(CLI, slack_level=3, work_words=1 << 18, order_mode=order_mode)
+    bad = []
+    for c, (st, cells, _) in zip(CLI, out):
+        if st != c["ref_status"] or cells != c["ref_cells"]:
+            bad.append(c["name"])
+        elif c["golden_ll"] is not None:
+            text = po.cli_output_text(c["comment"], st, [tuple(x) for x in cells])
+            if po.strip_ws_lines(text) != po.strip_ws_lines(c["golden_ll"]):
+                bad.append(c["name"] + ":text")
+    assert not bad, bad
+
+
+def test_random_tableaus():
+    cases = [c for c in RCLI if c["name"] not in HEAVY]
+    out = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=2)
+    bad = [c["name"] for c, (st, cells, _) in zip(cases, out)
+           if st != c["ref_status"] or cells != c["ref_cells"]]
+    assert not bad, bad
+
+
+def test_capacity_escalation_is_reported():
+    """a too-small arena must yield the internal CAPACITY status, never a wrong answer."""
+    c = [x for x in load_golden("cli_suite.json") if x["name"] == "bouleti"][0]
+    (st, cells, _), = emu.solve_tableau_cases([c], slack_level=2, work_words=2048)
+    assert st == 4001 and cells == []

@@ -1,0 +1,111 @@
+"""Parity of the CUDA path (through the C-ABI) with the reference: golden .ll files, live
+reference answers recorded in tests/golden/, and the oracle on seeded synthetic batches."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+CLI = [c for c in load_golden("cli_suite.json") if "pipFile_1" not in c["name"]]
+LIB = load_golden("lib_suite.json")
+RLIB = load_golden("random_lib.json")
+RCLI = load_golden("random_cli.json")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from piplib_b200 import api as a
+    from piplib_b200 import build
+    build.build()
+    return a
+
+
+def test_cli_suite(api):
+    """test/*.dat (+challenges) in ONE batch: cells bit-exact, text token-exact vs the .ll"""
+    out = api.traiter_batch(CLI)
+    bad = []
+    for c, (st, cells) in zip(CLI, out):
+        if st != c["ref_status"] or cells != c["ref_cells"]:
+            bad.append((c["name"], st, c["ref_status"], len(cells), len(c["ref_cells"])))
+        elif c["golden_ll"] is not None:
+            text = po.cli_output_text(c["comment"], st, [tuple(x) for x in cells])
+            if po.strip_ws_lines(text) != po.strip_ws_lines(c["golden_ll"]):
+                bad.append((c["name"], "text"))
+    assert not bad, bad
+
+
+def _lib_problem(c):
+    return dict(dom=c["dom"], ctx=c["ctx"], ctx_cols=c["ctx_shape"][1] if c["ctx_shape"] else None,
+                bignum=c["bignum"])
+
+
+def test_lib_suite(api):
+    """example/*.pip and the option variants (Maximize, Urs_*, Rational, Simplify)"""
+    bad = []
+    for c in LIB:
+        st, ser = api.solve_batch([_lib_problem(c)], **c["opts"])[0]
+        if st != c["ref_status"] or ser != c["ref_ser"]:
+            bad.append((c["name"], st))
+        elif c["golden_ll"] is not None:
+            text = po.example_output_text(c, ser)
+            if po.strip_ws_lines(text) != po.strip_ws_lines(c["golden_ll"]):
+                bad.append((c["name"], "text"))
+    assert not bad, bad
+
+
+def test_pip_solve_and_printer(api):
+    """the reference call sequence of example/example.c:84-92 on example/max.pip"""
+    c = [x for x in LIB if x["name"] == "max"][0]
+    L = api.lib()
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fclose.argtypes = [C.c_void_p]
+    dom = np.asarray(c["dom"], dtype=np.int64)
+    d = api._matrix(dom.shape[0], dom.shape[1], dom)
+    x = api._matrix(c["ctx_shape"][0], c["ctx_shape"][1], np.zeros(0))
+    o = L.pip_options_init_dp()
+    q = L.pip_solve_dp(d, x, c["bignum"], o)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "out.txt").encode()
+        f = libc.fopen(path, b"w")
+        L.pip_quast_print_dp(C.c_void_p(f), C.c_void_p(q), 0)
+        libc.fclose(C.c_void_p(f))
+        text = open(path).read()
+    assert text == po.quast_print_text(c["ref_ser"])
+    L.pip_quast_free_dp(q)
+    L.pip_options_free_dp(o)
+    L.pip_matrix_free_dp(d)
+    L.pip_matrix_free_dp(x)
+
+
+def test_random_lib(api):
+    groups = {}
+    for c in RLIB:
+        groups.setdefault(tuple(sorted(c["opts"].items())), []).append(c)
+    bad = []
+    for opts, cases in groups.items():
+        out = api.solve_batch([_lib_problem(c) for c in cases], **dict(opts))
+        bad += [c["name"] for c, r in zip(cases, out) if r != (c["ref_status"], c["ref_ser"])]
+    assert not bad, bad
+
+
+def test_random_cli(api):
+    out = api.traiter_batch(RCLI)
+    bad = [(c["name"], st, c["ref_status"]) for c, (st, cells) in zip(RCLI, out)
+           if st != c["ref_status"] or cells != c["ref_cells"]]
+    assert not bad, bad
+
+
+def test_batch_equals_singles(api):
+    """pip_solve_batch must give the same trees as n sequential pip_solve calls"""
+    cases = [c for c in LIB if c["opts"] == {"Nq": 1, "Maximize": 0, "Urs_parms": 0,
+                                             "Urs_unknowns": 0, "Compute_dual": 0}]
+    one = api.solve_batch([_lib_problem(c) for c in cases])
+    for c, r in zip(cases, one):
+        assert r == api.solve_batch([_lib_problem(c)])[0] == (c["ref_status"], c["ref_ser"])
