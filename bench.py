@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of piplib-b200 on BASELINE.json's headline configuration.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--workload NAME]
+  python bench.py --impl reference ...      (the reference's own CPU path, all host cores)
+
+A "step" is one pass of the solver over one batch of B synthetic problems per GPU (weak
+scaling: every rank solves its own B problems; no data-path collective exists).
+  value   problems/s, whole job, inputs already resident in HBM (kernels only, CUDA events)
+  e2e     problems/s through the C-ABI call pip_solve_dense_dp with HOST buffers: PolyLib
+          matrices in, serialised quasts + hashes out, host<->device copies inside the region
+The workload is configs[1] of BASELINE.json: ~16 unknowns x 24 constraints, 3 parameters
+(piplib_b200/synth.py: loopnest16x24p3), data = synthetic.  Inputs (4 GB per 10^6 problems) are
+far larger than L2, so no explicit L2 flush is needed between steps.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from piplib_b200 import synth  # noqa: E402
+
+METRIC = "problems_per_sec"
+UNIT = "problems/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.samples = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 9:
+                    self.samples.append(f)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for f in self.samples:
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arms (the checker libraries; never the thing shipped)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, first, count, dom, ctx, core = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    from oracle import pyoracle as po
+    if kind == "reference":
+        sec, st, h = po.Ref().bench_dense(first, count, dom, ctx, -1)
+        piv = 0
+    else:
+        sec, st, h, stats = po.Port().bench_dense(first, count, dom, ctx, -1)
+        piv = stats.pivots
+    return sec, st, h, piv
+
+
+def cpu_arm(dom, ctx, sample, cores):
+    """reference CPU path on `cores` processes (one per core: the library is not re-entrant,
+    SURVEY.md 8b), static split of problems [0, sample)."""
+    from oracle import pyoracle as po
+    kind = "reference" if os.path.exists(po.REF_SO) else "port"
+    if kind == "port":
+        po.build(ref=False, port=True)
+    per = (sample + cores - 1) // cores
+    jobs = []
+    for c in range(cores):
+        a, b = c * per, min(sample, (c + 1) * per)
+        if a < b:
+            jobs.append((kind, a, b - a, dom, ctx, c))
+    ctxm = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctxm.Pool(len(jobs)) as pool:
+        outs = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    tmax = max(o[0] for o in outs)
+    status = np.concatenate([o[1] for o in outs])
+    hashes = np.concatenate([o[2] for o in outs])
+    return dict(kind=kind, seconds=tmax, wall=wall, status=status, hashes=hashes, cores=len(jobs),
+                n=sample)
+
+
+def port_pivots(dom, ctx, sample):
+    """pivot count of a sample (the reference has no counter; the oracle restatement, which gives
+    bit-identical answers, counts them)."""
+    from oracle import pyoracle as po
+    po.build(ref=False, port=True)
+    sec, st, h, stats = po.Port().bench_dense(0, sample, dom, ctx, -1)
+    return stats.pivots, stats.elem_updates
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PIP_BENCH_BATCH", 1000000)))
+    ap.add_argument("--workload", default="loopnest16x24p3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--check", type=int, default=4096, help="problems cross-checked against the oracle")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    W = max(a.warmup, 0)
+    K = max(a.steps, 1)
+    B = a.batch
+    config = {"workload": "%s: %d problems/GPU/step, 16 unknowns x 24 constraints, 3 parameters, "
+                          "int64, pip_solve path (Nq=1)" % (a.workload, B),
+              "batch_per_gpu": B, "l2": "inputs (%.1f GB/step) exceed L2; no flush needed" %
+              (B * 24 * 21 * 8 / 1e9), "seed": a.seed}
+
+    # ---------------- reference arm: the reference's own CPU implementation ----------------
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sample = a.cpu_sample or min(B, cores * 4096)
+        dom, ctx = synth.generate(a.workload, sample, seed=a.seed, first=0)
+        for _ in range(W):
+            cpu_arm(dom, ctx, min(sample, cores * 256), cores)
+        tot_s, r = 0.0, None
+        for _ in range(K):
+            r = cpu_arm(dom, ctx, sample, cores)
+            tot_s += r["seconds"]
+        value = sample * K / tot_s
+        pivots, _ = port_pivots(dom, ctx, min(sample, 4096))
+        ppp = pivots / min(sample, 4096)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+                "steps": K, "warmup": W, "ms_per_step": 1e3 * tot_s / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": config, "pivots_per_sec": value * ppp,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": "first %d problems of the workload per step, one process "
+                                           "per core" % sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm ---------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from piplib_b200 import api, build
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- piplib-b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api.set_device(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dom, ctx = synth.generate(a.workload, B, seed=a.seed, first=rank * B)
+
+    # parity gate before any timing: a slice of this rank's batch against the oracle
+    ncheck = min(a.check, B)
+    if ncheck:
+        from oracle import pyoracle as po
+        po.build(ref=False, port=True)
+        _, st_o, h_o, stats_o = po.Port().bench_dense(0, ncheck, dom[:ncheck], ctx[:ncheck], -1)
+        r = api.solve_dense(dom[:ncheck], ctx[:ncheck], -1)
+        st_g = np.where(r["status"] == 1, 0, r["status"])
+        if not (np.array_equal(st_g, st_o) and np.array_equal(r["hashes"][st_o == 0], h_o[st_o == 0])):
+            raise SystemExit("bench.py: GPU results differ from the oracle -- refusing to time")
+
+    # kernel-only: inputs resident in HBM
+    db = api.DeviceBatch(dom, ctx, -1)
+    for _ in range(max(W, 3)):
+        db.run(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    stats = None
+    for _ in range(K):
+        dev_ms += db.run(False)
+        stats = api.last_stats()
+        launches += stats.launches
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    status, _ = db.results(False)
+    pivots_step = int(stats.pivots)
+    elem_step = int(stats.elem_updates)
+    cells_step = int(stats.cells)
+    rounds = int(stats.rounds)
+    db.close()
+
+    # end to end through the C-ABI with host buffers
+    e2e_s, h2d_b, d2h_b = None, 0, 0
+    if not a.no_e2e:
+        for _ in range(max(W, 3)):
+            api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(K):
+            api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+            s2 = api.last_stats()
+            h2d_b, d2h_b = int(s2.h2d_bytes), int(s2.d2h_bytes)
+        barrier()
+        e2e_s = time.perf_counter() - t1
+    if rank == 0:
+        sampler.stop()
+
+    # max over ranks
+    t = torch.tensor([dev_ms, wall_ms, e2e_s or 0.0], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(pivots_step), float(elem_step)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms, e2e_max = [float(x) for x in t.tolist()]
+    pivots_all, elem_all = [float(x) for x in cnt.tolist()]
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        total_problems = B * world * K
+        value = total_problems / (dev_ms / 1e3)
+        ms_per_step = dev_ms / K
+        # algorithmic HBM traffic of the solve kernel: every problem's input words are read once
+        # and its solution cells written once (the working set itself lives in shared memory)
+        in_bytes = dom.shape[1] * (dom.shape[2] - 1) * 8 + ctx.shape[1] * (ctx.shape[2] - 1) * 8 + 32
+        alg_bytes = float(B) * (in_bytes + 56) + 24.0 * cells_step
+        achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
+        uniq, counts = np.unique(status, return_counts=True)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+            "pivots_per_sec": pivots_all * K / (dev_ms / 1e3),
+            "elem_updates_per_sec": elem_all * K / (dev_ms / 1e3),
+            "pivots_per_problem": pivots_all / (B * world),
+            "wall_ms_per_step": wall_ms / K,
+            "rounds_per_step": rounds,
+            "status_counts": {str(int(u)): int(c) for u, c in zip(uniq, counts)},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+                         "note": "class-S kernel keeps the tableau in shared memory: HBM sees only "
+                                 "inputs+cells; the binding resource is the INT pipe / issue slots "
+                                 "(see elem_updates_per_sec and profiles/)"},
+        }
+        if e2e_max:
+            line["e2e"] = {"value": B * world * K / e2e_max, "unit": UNIT,
+                           "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                           "api": "pip_solve_dense_dp (host PolyLib matrices in, serialised quasts out)"}
+        if world == 1:
+            sample = a.cpu_sample or min(B, cores * 2048)
+            r = cpu_arm(dom, ctx, sample, cores)
+            line["cpu_baseline"] = {"value": sample / r["seconds"], "unit": UNIT, "cores": r["cores"],
+                                    "kind": r["kind"],
+                                    "sample": "first %d problems of the batch, one process per core, "
+                                              "pip_solve loop" % sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

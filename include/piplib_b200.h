@@ -66,6 +66,7 @@ typedef struct {
   int launches;             /* kernels launched by the last batch call */
   int rounds;               /* solve launches (size-class escalations included) */
   unsigned long long h2d_bytes, d2h_bytes;
+  unsigned long long cells;  /* solution cells produced by the batch */
 } PipBatchStats_dp;
 
 /* n x pip_solve_dp.  options may be NULL (defaults) ; contexts[i] may be NULL (no parameters).

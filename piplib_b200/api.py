@@ -41,7 +41,8 @@ class PipBatchStats(C.Structure):
                 ("seconds_h2d", C.c_double), ("seconds_kernel", C.c_double),
                 ("seconds_d2h", C.c_double), ("seconds_host", C.c_double),
                 ("device_ms", C.c_float), ("launches", C.c_int), ("rounds", C.c_int),
-                ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong)]
+                ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
+                ("cells", C.c_ulonglong)]
 
 
 _lib = None

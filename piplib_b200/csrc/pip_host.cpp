@@ -300,6 +300,7 @@ void account(const PipBatchOut &out, double host_seconds)
   PipBatchStats_dp s;
   memset(&s, 0, sizeof s);
   for (const PipResult &r : out.res) {
+    s.cells += (unsigned long long)r.ncells;
     s.pivots += r.pivots; s.cuts += r.cuts; s.subsolves += r.subsolves; s.splits += r.splits;
     s.elem_updates += ((unsigned long long)r.elem_updates_hi << 32) | r.elem_updates_lo;
     s.max_rows = std::max(s.max_rows, r.max_rows);

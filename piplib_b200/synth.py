@@ -1,0 +1,89 @@
+"""Synthetic problem families for the BASELINE.json configurations.
+
+Purely random coefficient matrices are useless as a benchmark (a quarter of them die with "solution
+too complex"), so the families are *structured*: loop-nest shaped
+polyhedra (bounds, parametric bounds, a few couplings) perturbed by a counter-based RNG.
+Problem i of a family depends only on (seed, i): chunks of CHUNK problems are generated from
+Philox streams keyed by (seed, chunk index), so any rank can generate any index range.
+
+All generators return PolyLib-format dense arrays:
+  dom [n, rows, 1 + nvar + nparm + 1]   row = [eq(0)/ineq(1) | unknowns | parameters | constant]
+  ctx [n, crows, 1 + nparm + 1]
+"""
+import numpy as np
+
+CHUNK = 1 << 14
+
+
+def _rng(seed, chunk):
+    return np.random.Generator(np.random.Philox(key=[int(seed) & (2**64 - 1), int(chunk)]))
+
+
+def _loopnest_chunk(rng, m, nvar, nrows, nparm):
+    ncol = 1 + nvar + nparm + 1
+    dom = np.zeros((m, nrows, ncol), dtype=np.int64)
+    dom[:, :, 0] = 1
+    ar = np.arange(m)
+    X0, P0, K = 1, 1 + nvar, ncol - 1
+    # rows 0..nvar-1: one bound per unknown, lower (x_i >= c) or parametric upper (x_i <= p_j + c)
+    for i in range(min(nvar, nrows)):
+        upper = rng.random(m) < 0.5
+        pj = rng.integers(0, nparm, size=m)
+        c_lo = rng.integers(0, 5, size=m)
+        c_up = rng.integers(-4, 13, size=m)
+        dom[ar, i, X0 + i] = np.where(upper, -1, 1)
+        dom[ar[upper], i, P0 + pj[upper]] = 1
+        dom[:, i, K] = np.where(upper, c_up, -c_lo)
+    # remaining rows: couplings a*x_i - b*x_k (+/- p_j) + c >= 0 with small coefficients
+    for r in range(nvar, nrows):
+        i = rng.integers(0, nvar, size=m)
+        k = (i + 1 + rng.integers(0, nvar - 1, size=m)) % nvar
+        a = rng.integers(1, 3, size=m)
+        b = rng.integers(1, 3, size=m)
+        s = np.where(rng.random(m) < 0.5, 1, -1)
+        dom[ar, r, X0 + i] = s * a
+        dom[ar, r, X0 + k] = -s * b
+        withp = rng.random(m) < 0.5
+        pj = rng.integers(0, nparm, size=m)
+        ps = np.where(rng.random(m) < 0.7, 1, -1)
+        dom[ar[withp], r, P0 + pj[withp]] = ps[withp]
+        third = rng.random(m) < 0.3
+        t = (k + 1 + rng.integers(0, nvar - 2, size=m)) % nvar
+        t = np.where(t == i, (t + 1) % nvar, t)
+        t = np.where(t == k, (t + 1) % nvar, t)
+        dom[ar[third], r, X0 + t[third]] += rng.integers(-2, 3, size=m)[third]
+        dom[:, r, K] = rng.integers(-4, 13, size=m)
+    # context: p_j >= c_j
+    ctx = np.zeros((m, nparm, 1 + nparm + 1), dtype=np.int64)
+    ctx[:, :, 0] = 1
+    for j in range(nparm):
+        ctx[:, j, 1 + j] = 1
+        ctx[:, j, -1] = -rng.integers(0, 9, size=m)
+    return dom, ctx
+
+
+def loopnest(n, seed=2026, nvar=16, nrows=24, nparm=3, first=0):
+    """BASELINE config 2: ~16 unknowns x 24 constraints, a few parameters."""
+    doms, ctxs = [], []
+    lo = first
+    hi = first + n
+    c = lo // CHUNK
+    while c * CHUNK < hi:
+        d, x = _loopnest_chunk(_rng(seed, c), CHUNK, nvar, nrows, nparm)
+        a = max(lo, c * CHUNK) - c * CHUNK
+        b = min(hi, (c + 1) * CHUNK) - c * CHUNK
+        doms.append(d[a:b])
+        ctxs.append(x[a:b])
+        c += 1
+    return np.ascontiguousarray(np.concatenate(doms)), np.ascontiguousarray(np.concatenate(ctxs))
+
+
+WORKLOADS = {
+    "loopnest16x24p3": dict(fn=loopnest, kw=dict(nvar=16, nrows=24, nparm=3)),
+    "loopnest8x12p2": dict(fn=loopnest, kw=dict(nvar=8, nrows=12, nparm=2)),
+}
+
+
+def generate(name, n, seed=2026, first=0):
+    w = WORKLOADS[name]
+    return w["fn"](n, seed=seed, first=first, **w["kw"])
