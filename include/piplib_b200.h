@@ -67,6 +67,7 @@ typedef struct {
   int rounds;               /* solve launches (size-class escalations included) */
   unsigned long long h2d_bytes, d2h_bytes;
   unsigned long long cells;  /* solution cells produced by the batch */
+  unsigned long long phase_cycles[16]; /* per-phase warp cycles, profile build only (else 0) */
 } PipBatchStats_dp;
 
 /* n x pip_solve_dp.  options may be NULL (defaults) ; contexts[i] may be NULL (no parameters).

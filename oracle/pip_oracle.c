@@ -48,6 +48,11 @@ typedef struct {
 
 static void fatal(Ctx *c, int code) { longjmp(c->env, code); }
 
+/* exploration aid for workload design (never used in parity runs): give up after this many
+ * pivots with status 3001; 0 = unlimited like the reference */
+static long long pio_pivot_cap = 0;
+void piporacle_set_pivot_cap(long long cap) { pio_pivot_cap = cap; }
+
 /* ---- integer helpers: source/integrer.c:41-89, include/piplib/piplib.h:128-169 ---------- */
 static I gcd_abs(I a, I b)
 {
@@ -298,6 +303,7 @@ static int pivot_step(Ctx *c, Tab *t, int pivi, int nvar, int nparm, int ni)
     t->det[i] = ppivot;
   }
   c->st->pivots++;
+  if (pio_pivot_cap && c->st->pivots > pio_pivot_cap) fatal(c, 3001);
 
   prow = &AT(t, pivi, 0);
   for (k = 0; k < nligne; k++) {

@@ -13,7 +13,8 @@ import numpy as np
 from .ctypes_defs import CELL_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpiplib_dp.so")
+LIB_PATH = os.environ.get("PIPLIB_B200_LIB") or os.path.join(HERE, "lib", "libpiplib_dp.so")
+PHASES = ["load", "sort", "scan", "buildsub", "choose", "update", "swap", "cut", "frame", "emit", "other"]
 
 I64P = C.POINTER(C.c_longlong)
 
@@ -42,7 +43,7 @@ class PipBatchStats(C.Structure):
                 ("seconds_d2h", C.c_double), ("seconds_host", C.c_double),
                 ("device_ms", C.c_float), ("launches", C.c_int), ("rounds", C.c_int),
                 ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
-                ("cells", C.c_ulonglong)]
+                ("cells", C.c_ulonglong), ("phase_cycles", C.c_ulonglong * 16)]
 
 
 _lib = None

@@ -23,46 +23,52 @@ HEADERS = ["pip_types.h", "simt.h", "pip_arith.h", "pip_solver.h", "pip_warp_mai
            os.path.join("..", "..", "include", "piplib", "piplib.h")]
 
 
-def _stale():
-    if not os.path.exists(LIB):
+def _stale(lib=None):
+    lib = lib or LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     for f in SOURCES_CU + SOURCES_CPP + HEADERS:
         if os.path.getmtime(os.path.join(CSRC, f)) > t:
             return True
     return os.path.getmtime(os.path.abspath(__file__)) > t
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
-        return LIB
+def build(force=False, verbose=False, profile=False):
+    """profile=True builds libpiplib_dp_prof.so with per-phase clock64 accounting compiled in."""
+    global LIB
+    lib = os.path.join(LIBDIR, "libpiplib_dp_prof.so") if profile else LIB
+    if not force and not _stale(lib):
+        return lib
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
+    extra = ["-DPIP_PROFILE"] if profile else []
     inc = ["-I", os.path.join(HERE, "..", "include"), "-I", CSRC]
     for f in SOURCES_CU:
         o = os.path.join(LIBDIR, f + ".o")
-        cmd = [NVCC] + NVCC_FLAGS + inc + ["-c", os.path.join(CSRC, f), "-o", o]
+        o = os.path.join(LIBDIR, f + (".prof" if profile else "") + ".o")
+        cmd = [NVCC] + NVCC_FLAGS + extra + inc + ["-c", os.path.join(CSRC, f), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError("nvcc failed on " + f)
-        with open(os.path.join(LIBDIR, f + ".ptxas.txt"), "w") as fh:
+        with open(os.path.join(LIBDIR, f + (".prof" if profile else "") + ".ptxas.txt"), "w") as fh:
             fh.write(r.stdout + r.stderr)
         objs.append(o)
     for f in SOURCES_CPP:
-        o = os.path.join(LIBDIR, f + ".o")
-        cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-fwrapv", "-Wall", "-pthread",
+        o = os.path.join(LIBDIR, f + (".prof" if profile else "") + ".o")
+        cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-fwrapv", "-Wall", "-pthread"] + extra + [
                "-I", os.path.join(CUDA, "include")] + inc + ["-c", os.path.join(CSRC, f), "-o", o]
         subprocess.check_call(cmd)
         objs.append(o)
-    cmd = ["g++", "-shared", "-o", LIB] + objs + ["-L", os.path.join(CUDA, "lib64"), "-lcudart",
+    cmd = ["g++", "-shared", "-o", lib] + objs + ["-L", os.path.join(CUDA, "lib64"), "-lcudart",
                                                    "-pthread", "-Wl,-rpath," + os.path.join(CUDA, "lib64")]
     subprocess.check_call(cmd)
     for o in objs:
         os.remove(o)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, profile="--profile" in sys.argv))

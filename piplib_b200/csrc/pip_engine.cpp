@@ -76,7 +76,7 @@ struct PipEngine::Impl {
   bool inited = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total;
+  DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total, d_prof;
   PinBuf h_res, h_total;
   std::vector<PinBuf> h_chunks;     /* one per round, reused across calls */
 
@@ -149,6 +149,8 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
   CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
   out.times.h2d_bytes += n * sizeof(PipResult);
   E.d_queue.reserve(64);
+  E.d_prof.reserve(sizeof(unsigned long long) * PIP_NPHASE);
+  CK(cudaMemsetAsync(E.d_prof.p, 0, sizeof(unsigned long long) * PIP_NPHASE, s));
   E.d_total.reserve(64);
   E.h_total.reserve(64);
   CK(cudaStreamSynchronize(s));
@@ -204,7 +206,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       }
       /* cell pool: every warp must be able to hold one worst-case solution */
       long long est = (k < 0 && attempt == 0) ? (est_cells_total * (long long)m / (long long)n) : 0;
-      long long per_warp = std::max<long long>(in.sol_size, (est + est / 4) / cs.warps + 1);
+      long long per_warp = (est + est / 4) / cs.warps + 1 + in.sol_size;
       if (attempt > 0) per_warp = std::max<long long>(per_warp, 4ll * in.sol_size);
       E.d_cells.reserve((size_t)per_warp * cs.warps * sizeof(PipCell));
       E.d_stack.reserve((size_t)cs.stack_words * cs.warps * sizeof(pip_i64));
@@ -225,6 +227,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       L.queue = (unsigned *)E.d_queue.p;
       L.sol_size = in.sol_size; L.maxcol = in.maxcol; L.maxparm = PIP_MAXPARM;
       L.slack_level = cs.level;
+      L.prof = (unsigned long long *)E.d_prof.p;
       double tk = now_s();
       CK(pip_launch_solve(&L, cs.shared, ctas, cs.warps_per_cta, s));
       out.times.launches++;
@@ -283,6 +286,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
     }
   }
   CK(cudaEventElapsedTime(&out.times.device_ms, E.ev0, E.ev1));
+  CK(cudaMemcpy(out.times.phase_cycles, E.d_prof.p, sizeof(unsigned long long) * PIP_NPHASE, cudaMemcpyDeviceToHost));
   /* anything still unsolved is too large for the ladder */
   for (size_t i = 0; i < n; i++)
     if (cls[i] != 1000) { out.res[i] = PipResult(); out.res[i].status = PIP_ST_CAPACITY; }

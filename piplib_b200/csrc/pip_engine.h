@@ -26,6 +26,7 @@ struct PipBatchTimes {
   float device_ms = 0;                               /* CUDA-event time first launch -> last kernel */
   int launches = 0, rounds = 0;
   size_t h2d_bytes = 0, d2h_bytes = 0;
+  unsigned long long phase_cycles[PIP_NPHASE] = {0};   /* profile build only */
 };
 
 struct PipBatchOut {

@@ -311,6 +311,7 @@ void account(const PipBatchOut &out, double host_seconds)
   s.launches = out.times.launches; s.rounds = out.times.rounds;
   s.device_ms = out.times.device_ms;
   s.h2d_bytes = out.times.h2d_bytes; s.d2h_bytes = out.times.d2h_bytes;
+  for (int k = 0; k < PIP_NPHASE && k < 16; k++) s.phase_cycles[k] = out.times.phase_cycles[k];
   g_stats = s;
 }
 

@@ -45,7 +45,19 @@ struct PipTab {          /* warp-uniform, lives in registers */
 struct PipStats {
   unsigned pivots, cuts, subsolves, splits, max_rows, max_cols;
   unsigned long long elem_updates;
+#ifdef PIP_PROFILE
+  long long lap;                 /* clock64 of the last phase boundary */
+  unsigned long long cyc[PIP_NPHASE];
+#endif
 };
+
+/* phase accounting (only in the -DPIP_PROFILE build, libpiplib_dp_prof.so): a lap timer, every
+ * PIP_LAP(st, phase) charges the cycles since the previous lap to `phase` */
+#ifdef PIP_PROFILE
+#define PIP_LAP(st, ph) do { long long n_ = clock64(); (st).cyc[ph] += (unsigned long long)(n_ - (st).lap); (st).lap = n_; } while (0)
+#else
+#define PIP_LAP(st, ph) do { } while (0)
+#endif
 
 /* capacity slack per level: {new parameters, main cut rows, extra context rows, sub cut rows} */
 PIP_HD void pip_slack(int level, int &dp, int &dr, int &dx, int &ds)
@@ -329,6 +341,7 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
   pip_i64 *den = pip_den(B, T);
   pip_i64 pivot;
   const int pivj = pip_choose_column(B, T, pivi, pivot);
+  PIP_LAP(st, PIP_PH_CHOOSE);
   if (pivj < 0) return -1;
 
   const int pslot = PIP_LINK(fl[pivi]);
@@ -401,6 +414,7 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
   }
   if (W::any(fault)) return PIP_ST_FAULT;
   W::sync();
+  PIP_LAP(st, PIP_PH_UPDATE);
   /* the Unit position owning pivj takes the pivot row's slot, source/traiter.c:503-516 */
   int ku = nl;
   for (int base = 0; base < nl; base += 32) {
@@ -431,6 +445,7 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
     }
   }
   W::sync();
+  PIP_LAP(st, PIP_PH_SWAP);
   return 0;
 }
 
@@ -546,6 +561,7 @@ PIP_DEV void pip_solve_one(const PipProblem &P, const pip_i64 *in, pip_i64 *B, i
     }
   }
 
+  PIP_LAP(st, PIP_PH_LOAD);
   /* context emptiness check, source/piplib.c:818-826 / source/maind.c:199-204 */
   if (nc > 0) { ret_site = 0; goto BUILD_SUB; }
   goto ENTRY;
@@ -585,19 +601,22 @@ BUILD_SUB:
     T = S;
     level = 1;
     W::sync();
+    PIP_LAP(st, PIP_PH_BUILDSUB);
   }
 
 ENTRY:
   /* traiter_xx entry, source/traiter.c:643-656 (the private context copy is implicit) */
   if (level) st.subsolves++;
   pip_sort_rows(B, T, L.tmp);
+  PIP_LAP(st, PIP_PH_SORT);
 
 LOOP:
   {
     const int nl = T.nvar + T.ni;
     pivi = pip_first_flag(B, T, PIP_MINUS, 0, nl);
-    if (pivi < nl) goto PIVOT;
+    if (pivi < nl) { PIP_LAP(st, PIP_PH_SCAN); goto PIVOT; }
     pivi = pip_exam_coef(B, T, level ? -1 : P.bigparm);
+    PIP_LAP(st, PIP_PH_SCAN);
     if (pivi < nl) goto PIVOT;
     if (T.nparm == 0) goto NONNEG;
     /* compa_test_xx, source/traiter.c:162-243 */
@@ -716,6 +735,7 @@ AFTER_COMPA:
     nc++;
     depth++;
     st.splits++;
+    PIP_LAP(st, PIP_PH_FRAME);
     goto ENTRY;
   }
 
@@ -809,6 +829,7 @@ NONNEG:
       }
       break;
     }
+    PIP_LAP(st, PIP_PH_CUT);
     if (verdict > 0) { pivi = verdict; goto PIVOT; }
     if (level) { feasible = (verdict == 0); goto SUB_DONE; }
     if (verdict == 0) {
@@ -816,6 +837,7 @@ NONNEG:
       if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
       pip_emit_solution(B, T, out, ncell);
       ncell += total;
+      PIP_LAP(st, PIP_PH_EMIT);
     } else {
       if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
       if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
@@ -826,6 +848,7 @@ NONNEG:
 
 PIVOT:
   {
+    PIP_LAP(st, PIP_PH_OTHER);
     int rc = pip_pivot(B, T, pivi, st);
     if (rc == 0) goto LOOP;
     if (rc > 0) { status = rc; goto DONE; }
@@ -871,11 +894,13 @@ LEAF:
     if (lane == 0) fl[pivi] = PIP_MKFL(PIP_MINUS, PIP_LINK(fl[pivi]));
     W::sync();
     nc++;
+    PIP_LAP(st, PIP_PH_FRAME);
     goto PIVOT;
   }
 
 DONE:
   W::sync();
+  PIP_LAP(st, PIP_PH_OTHER);
   status_out = status;
   ncell_out = (status == PIP_ST_OK) ? ncell : 0;
 }

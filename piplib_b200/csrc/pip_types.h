@@ -21,6 +21,10 @@ enum { PIP_C_FREE = 0, PIP_C_NIL = 1, PIP_C_IF = 2, PIP_C_LIST = 3, PIP_C_FORM =
 /* problem flags (traiter flags, source/funcall.h:34-35, + our own) */
 enum { PIP_F_INT = 1, PIP_F_DUAL = 2, PIP_F_DEEPEST = 4 };
 
+/* phases of the -DPIP_PROFILE cycle accounting */
+enum { PIP_PH_LOAD = 0, PIP_PH_SORT, PIP_PH_SCAN, PIP_PH_BUILDSUB, PIP_PH_CHOOSE, PIP_PH_UPDATE, PIP_PH_SWAP,
+       PIP_PH_CUT, PIP_PH_FRAME, PIP_PH_EMIT, PIP_PH_OTHER, PIP_NPHASE };
+
 #define PIP_SOL_SIZE 4096
 #define PIP_MAXCOL 512
 #define PIP_MAXPARM 50
@@ -83,6 +87,7 @@ typedef struct {
   unsigned *queue;               /* [0] next problem, [1] retired warps */
   int sol_size, maxcol, maxparm;
   int slack_level;
+  unsigned long long *prof;      /* [PIP_NPHASE] cycle sums (profile build only) or NULL */
 } PipLaunch;
 
 #endif

@@ -24,6 +24,10 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
     PipStats st;
     st.pivots = st.cuts = st.subsolves = st.splits = st.max_rows = st.max_cols = 0;
     st.elem_updates = 0;
+#ifdef PIP_PROFILE
+    for (int k = 0; k < PIP_NPHASE; k++) st.cyc[k] = 0;
+    st.lap = clock64();
+#endif
     int status = PIP_ST_OK, ncell = 0;
     pip_solve_one(P, L.pool + P.off, arena, L.work_words, L.slack_level, window + used, stk,
                   L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, st);
@@ -37,6 +41,9 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
       r.elem_updates_hi = (unsigned)(st.elem_updates >> 32);
       r.pad = 0;
       L.res[p] = r;
+#ifdef PIP_PROFILE
+      if (L.prof) for (int k = 0; k < PIP_NPHASE; k++) atomicAdd(&L.prof[k], st.cyc[k]);
+#endif
     }
     used += ncell;
     W::sync();

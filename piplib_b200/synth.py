@@ -19,7 +19,7 @@ def _rng(seed, chunk):
     return np.random.Generator(np.random.Philox(key=[int(seed) & (2**64 - 1), int(chunk)]))
 
 
-def _loopnest_chunk(rng, m, nvar, nrows, nparm):
+def _loopnest_chunk(rng, m, nvar, nrows, nparm, p2=0.05, p3=0.05):
     ncol = 1 + nvar + nparm + 1
     dom = np.zeros((m, nrows, ncol), dtype=np.int64)
     dom[:, :, 0] = 1
@@ -38,8 +38,8 @@ def _loopnest_chunk(rng, m, nvar, nrows, nparm):
     for r in range(nvar, nrows):
         i = rng.integers(0, nvar, size=m)
         k = (i + 1 + rng.integers(0, nvar - 1, size=m)) % nvar
-        a = rng.integers(1, 3, size=m)
-        b = rng.integers(1, 3, size=m)
+        a = 1 + (rng.random(m) < p2)
+        b = 1 + (rng.random(m) < p2)
         s = np.where(rng.random(m) < 0.5, 1, -1)
         dom[ar, r, X0 + i] = s * a
         dom[ar, r, X0 + k] = -s * b
@@ -47,7 +47,7 @@ def _loopnest_chunk(rng, m, nvar, nrows, nparm):
         pj = rng.integers(0, nparm, size=m)
         ps = np.where(rng.random(m) < 0.7, 1, -1)
         dom[ar[withp], r, P0 + pj[withp]] = ps[withp]
-        third = rng.random(m) < 0.3
+        third = rng.random(m) < p3
         t = (k + 1 + rng.integers(0, nvar - 2, size=m)) % nvar
         t = np.where(t == i, (t + 1) % nvar, t)
         t = np.where(t == k, (t + 1) % nvar, t)
@@ -62,14 +62,20 @@ def _loopnest_chunk(rng, m, nvar, nrows, nparm):
     return dom, ctx
 
 
-def loopnest(n, seed=2026, nvar=16, nrows=24, nparm=3, first=0):
-    """BASELINE config 2: ~16 unknowns x 24 constraints, a few parameters."""
+def loopnest(n, seed=2026, nvar=16, nrows=24, nparm=3, first=0, p2=0.05, p3=0.05):
+    """BASELINE config 2: ~16 unknowns x 24 constraints, a few parameters.
+
+    p2 = probability that a coupling coefficient is 2 instead of 1, p3 = probability of a third
+    unknown in a coupling.  Both drive the Gomory-cut rate; at the defaults a problem needs ~60
+    pivots, ~0.9 cuts and ~2.4 splits on average and one in ~6000 ends "solution too complex".
+    Larger values grow a heavy tail of run-away cut chains on which the reference itself spends
+    minutes per problem (measured: p2=0.5,p3=0.3 -> 1 in 20000), useless for a throughput figure."""
     doms, ctxs = [], []
     lo = first
     hi = first + n
     c = lo // CHUNK
     while c * CHUNK < hi:
-        d, x = _loopnest_chunk(_rng(seed, c), CHUNK, nvar, nrows, nparm)
+        d, x = _loopnest_chunk(_rng(seed, c), CHUNK, nvar, nrows, nparm, p2, p3)
         a = max(lo, c * CHUNK) - c * CHUNK
         b = min(hi, (c + 1) * CHUNK) - c * CHUNK
         doms.append(d[a:b])
