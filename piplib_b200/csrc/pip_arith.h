@@ -17,7 +17,7 @@
 
 PIP_HD pip_u64 pip_uabs(pip_i64 v) { return v < 0 ? 0ull - (pip_u64)v : (pip_u64)v; }
 
-PIP_HD pip_u64 pip_gcd_u64(pip_u64 a, pip_u64 b)
+PIP_HDNI pip_u64 pip_gcd_u64(pip_u64 a, pip_u64 b)
 {
   while (b) {
     if (((a | b) >> 32) == 0) {            /* both fit 32 bits: stay on the 32-bit path */
@@ -32,14 +32,14 @@ PIP_HD pip_u64 pip_gcd_u64(pip_u64 a, pip_u64 b)
 PIP_HD pip_i64 pip_gcd(pip_i64 a, pip_i64 b) { return (pip_i64)pip_gcd_u64(pip_uabs(a), pip_uabs(b)); }
 
 /* C truncating division, b != 0 */
-PIP_HD pip_i64 pip_div(pip_i64 a, pip_i64 b)
+PIP_HDNI pip_i64 pip_div(pip_i64 a, pip_i64 b)
 {
   if (a == (pip_i64)(int)a && b == (pip_i64)(int)b && (int)a != (-2147483647 - 1))
     return (pip_i64)((int)a / (int)b);
   return a / b;
 }
 /* C remainder, b != 0 */
-PIP_HD pip_i64 pip_rem(pip_i64 a, pip_i64 b)
+PIP_HDNI pip_i64 pip_rem(pip_i64 a, pip_i64 b)
 {
   if (a == (pip_i64)(int)a && b == (pip_i64)(int)b && (int)a != (-2147483647 - 1))
     return (pip_i64)((int)a % (int)b);
@@ -80,7 +80,7 @@ struct PipExactDiv {
   pip_u64 inv;
   int shift;
 };
-PIP_HD PipExactDiv pip_exact_prepare(pip_i64 g)
+PIP_HDNI PipExactDiv pip_exact_prepare(pip_i64 g)
 {
   PipExactDiv e;
   pip_u64 u = (pip_u64)g;

@@ -16,7 +16,7 @@
 extern __shared__ __align__(16) unsigned char pip_smem[];
 
 template <bool SH>
-__global__ void __launch_bounds__(PIP_WARPS_PER_CTA_MAX * 32)
+__global__ void __launch_bounds__(PIP_CTA_THREADS, PIP_MIN_CTAS)
 pip_solve_kernel(const PipLaunch L)
 {
   const int warp_in_cta = threadIdx.x >> 5;

@@ -6,7 +6,11 @@
 
 #include "pip_types.h"
 
-#define PIP_WARPS_PER_CTA_MAX 8
+#define PIP_WARPS_PER_CTA_MAX 4
+#define PIP_CTA_THREADS (PIP_WARPS_PER_CTA_MAX * 32)
+#ifndef PIP_MIN_CTAS
+#define PIP_MIN_CTAS 4      /* <= 128 registers per thread */
+#endif
 
 #ifdef __cplusplus
 extern "C" {

@@ -121,9 +121,8 @@ PIP_DEV pip_i64 *pip_den(pip_i64 *B, const PipTab &T) { return B + T.den; }
 PIP_DEV pip_i64 *pip_row(pip_i64 *B, const PipTab &T, int slot) { return B + T.data + slot * T.stride; }
 
 /* chercher_xx, source/traiter.c:39-44: first position in [from, n) whose flag meets the mask */
-PIP_DEV int pip_first_flag(pip_i64 *B, const PipTab &T, int mask, int from, int n)
+PIP_DEVNI int pip_first_flag_impl(const int *fl, int mask, int from, int n)
 {
-  const int *fl = pip_fl(B, T);
   const int lane = W::lane();
   for (int base = from & ~31; base < n; base += 32) {
     int k = base + lane;
@@ -134,8 +133,37 @@ PIP_DEV int pip_first_flag(pip_i64 *B, const PipTab &T, int mask, int from, int 
   return n;
 }
 
+PIP_DEV int pip_first_flag(pip_i64 *B, const PipTab &T, int mask, int from, int n)
+{
+  return pip_first_flag_impl(pip_fl(B, T), mask, from, n);
+}
+
+/* warp-cooperative 2-D copy (rows x cols words) between arbitrary strides; one out-of-line copy
+ * of this loop serves problem load, sub-tableau construction and the frame stack */
+PIP_DEVNI void pip_copy2d(pip_i64 *dst, int dstride, const pip_i64 *src, int sstride, int rows, int cols)
+{
+  if (cols <= 0) return;
+  int r = 0, j = W::lane();
+  while (j >= cols) { j -= cols; r++; }
+  while (r < rows) {
+    dst[r * dstride + j] = src[r * sstride + j];
+    j += 32;
+    while (j >= cols) { j -= cols; r++; }
+  }
+}
+
+/* one term of the row "size" with a non-unit denominator: |(int)(double(v)/double(d))| or 0
+ * when the conversion is out of range (source/traiter.c:580-584) */
+PIP_DEVNI unsigned pip_size_term(pip_i64 v, pip_i64 d)
+{
+  double t = pip_ll2d(v) / pip_ll2d(d);
+  double a = t < 0 ? -t : t;
+  if (a < 2147483648.0) return (unsigned)(int)a;
+  return 0u;
+}
+
 /* tab_simplify_xx, source/tab.c:396-427 on `rows` rows of `width` words (lane = row) */
-PIP_DEV bool pip_simplify_rows(pip_i64 *base, int rows, int stride, int width, int cst)
+PIP_DEVNI bool pip_simplify_rows(pip_i64 *base, int rows, int stride, int width, int cst)
 {
   bool fault = false;
   for (int r = W::lane(); r < rows; r += 32) {
@@ -176,11 +204,9 @@ PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
         if (u < 2147483648ull && (unsigned)u > s) s = (unsigned)u;
       }
     } else {
-      double dd = pip_ll2d(d);
       for (int j = 0; j < T.nvar; j++) {
-        double t = pip_ll2d(row[j]) / dd;
-        double a = t < 0 ? -t : t;
-        if (a < 2147483648.0) { unsigned v = (unsigned)(int)a; if (v > s) s = v; }
+        unsigned v = pip_size_term(row[j], d);
+        if (v > s) s = v;
       }
     }
     sz[k] = (float)(double)s;
@@ -455,7 +481,7 @@ PIP_DEV void pip_put(PipCell *out, int idx, int kind, pip_i64 p1, pip_i64 p2)
 }
 
 /* solution_xx, source/traiter.c:255-271: 1 + nvar*(2+nparm) cells, lane-parallel */
-PIP_DEV void pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int at)
+PIP_DEVNI void pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int at)
 {
   const int per = T.nparm + 2, total = 1 + T.nvar * per;
   const int *fl = pip_fl(B, T);
@@ -543,15 +569,8 @@ PIP_DEV void pip_solve_one(const PipProblem &P, const pip_i64 *in, pip_i64 *B, i
       if (k < P.nvar) { fl[k] = PIP_MKFL(PIP_UNIT, k); den[k] = 1; }
       else { fl[k] = PIP_MKFL(PIP_UNKNOWN, k - P.nvar); den[k] = 1; }
     }
-    for (int e = lane; e < P.ni * ncol; e += 32) {
-      int r = e / ncol, j = e - r * ncol;
-      pip_row(B, T, r)[j] = in[e];
-    }
-    const pip_i64 *cin = in + (pip_i64)P.ni * ncol;
-    for (int e = lane; e < P.nc * (P.nparm + 1); e += 32) {
-      int r = e / (P.nparm + 1), j = e - r * (P.nparm + 1);
-      ctx[r * cstride + j] = cin[e];
-    }
+    pip_copy2d(B + T.data, T.stride, in, ncol, P.ni, ncol);
+    pip_copy2d(ctx, cstride, in + (pip_i64)P.ni * ncol, P.nparm + 1, P.nc, P.nparm + 1);
     if (lane == 0) { B[L.m.det] = 1; B[L.s.det] = 1; }
     W::sync();
     if (integer) {
@@ -582,10 +601,7 @@ BUILD_SUB:
       sfl[k] = k < np ? PIP_MKFL(PIP_UNIT, k) : PIP_MKFL(PIP_UNKNOWN, k - np);
       sden[k] = 1;
     }
-    for (int e = lane; e < nc * (np + 1); e += 32) {
-      int r = e / (np + 1), j = e - r * (np + 1);
-      pip_row(B, S, r)[j] = ctx[r * cstride + j];
-    }
+    pip_copy2d(B + S.data, S.stride, ctx, cstride, nc, np + 1);
     if (extra) {
       const int f = pip_fl(B, M)[ci];
       const pip_i64 *row = pip_row(B, M, PIP_LINK(f));
@@ -718,15 +734,9 @@ AFTER_COMPA:
       int *qi = (int *)q;
       for (int k = lane; k < nl; k += 32) qi[k] = fl[k];
       q += (nl + 1) / 2;
-      for (int e = lane; e < T.ni * ncol; e += 32) {
-        int r = e / ncol, j = e - r * ncol;
-        q[e] = pip_row(B, T, r)[j];
-      }
+      pip_copy2d(q, ncol, B + T.data, T.stride, T.ni, ncol);
       q += (pip_i64)T.ni * ncol;
-      for (int e = lane; e < (nc + 1) * (np + 1); e += 32) {
-        int r = e / (np + 1), j = e - r * (np + 1);
-        q[e] = ctx[r * cstride + j];
-      }
+      pip_copy2d(q, np + 1, ctx, cstride, nc + 1, np + 1);
       top += fsize;
     }
     W::sync();
@@ -877,16 +887,13 @@ LEAF:
     const int *qi = (const int *)q;
     for (int k = lane; k < nl; k += 32) fl[k] = qi[k];
     q += (nl + 1) / 2;
-    for (int e = lane; e < T.ni * ncol; e += 32) {
-      int r = e / ncol, j = e - r * ncol;
-      pip_row(B, T, r)[j] = q[e];
-    }
+    pip_copy2d(B + T.data, T.stride, q, ncol, T.ni, ncol);
     q += (pip_i64)T.ni * ncol;
-    for (int e = lane; e < (nc + 1) * (np + 1); e += 32) {
-      int r = e / (np + 1), j = e - r * (np + 1);
-      pip_i64 v = q[e];
-      if (r == nc) v = (j < np) ? -v : -(v + 1);          /* the negated condition */
-      ctx[r * cstride + j] = v;
+    pip_copy2d(ctx, cstride, q, np + 1, nc + 1, np + 1);
+    W::sync();
+    for (int j = lane; j <= np; j += 32) {                 /* the negated condition */
+      pip_i64 v = ctx[nc * cstride + j];
+      ctx[nc * cstride + j] = (j < np) ? -v : -(v + 1);
     }
     top -= fsize;
     depth--;

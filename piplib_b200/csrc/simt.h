@@ -14,6 +14,7 @@
 #define PIP_DEV static inline
 #define PIP_DEVNI static __attribute__((noinline))
 #define PIP_HD static inline
+#define PIP_HDNI static __attribute__((noinline))
 #define PIP_ASSUME_SHARED(p) ((void)0)
 
 namespace pipemu {
@@ -51,6 +52,7 @@ static inline unsigned pip_f2u(float f) { unsigned u; __builtin_memcpy(&u, &f, 4
 #define PIP_DEV __device__ __forceinline__
 #define PIP_DEVNI __device__ __noinline__
 #define PIP_HD __host__ __device__ __forceinline__
+#define PIP_HDNI __host__ __device__ __noinline__
 #define PIP_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 
 struct W {
