@@ -245,8 +245,9 @@ int pipref_solve_ser(int dom_rows, int dom_cols, const long long *dom,
 
 static unsigned long long fnv(unsigned long long h, long long v)
 {
-  int i; unsigned long long x = (unsigned long long)v;
-  for (i = 0; i < 8; i++) { h ^= (x >> (8 * i)) & 0xff; h *= 0x100000001b3ULL; }
+  h ^= (unsigned long long)v;
+  h *= 0x9E3779B97F4A7C15ULL;
+  h ^= h >> 32;
   return h;
 }
 static unsigned long long hash_h;

@@ -238,9 +238,9 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       CK(cudaMemcpyAsync(E.h_total.p, E.d_total.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       const long long total = *(long long *)E.h_total.p;
-      E.d_compact.reserve((size_t)std::max<long long>(total, 1) * sizeof(PipCell));
+      E.d_compact.reserve((size_t)std::max<long long>(total, 1) * sizeof(pip_u64));
       CK(pip_launch_gather((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
-                           (long long *)E.d_off.p, (PipCell *)E.d_compact.p, m, (long long *)E.d_total.p, 1, s));
+                           (long long *)E.d_off.p, (pip_u64 *)E.d_compact.p, m, (long long *)E.d_total.p, 1, s));
       out.times.launches++;
       CK(cudaEventRecord(E.ev1, s));
       CK(cudaStreamSynchronize(s));
@@ -252,9 +252,9 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       if ((size_t)round >= E.h_chunks.size()) E.h_chunks.resize(round + 1);
       PinBuf &chunk = E.h_chunks[round];
       if (in.fetch_cells && total > 0) {
-        chunk.reserve((size_t)total * sizeof(PipCell));
-        CK(cudaMemcpyAsync(chunk.p, E.d_compact.p, (size_t)total * sizeof(PipCell), cudaMemcpyDeviceToHost, s));
-        out.times.d2h_bytes += (size_t)total * sizeof(PipCell);
+        chunk.reserve((size_t)total * sizeof(pip_u64));
+        CK(cudaMemcpyAsync(chunk.p, E.d_compact.p, (size_t)total * sizeof(pip_u64), cudaMemcpyDeviceToHost, s));
+        out.times.d2h_bytes += (size_t)total * sizeof(pip_u64);
       }
       CK(cudaStreamSynchronize(s));
       out.times.d2h += now_s() - td;
@@ -269,7 +269,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         if (r.status == PIP_ST_CAPACITY && k + 1 < N_G) { cls[i] = k + 1; h_res[i].status = PIP_ST_PENDING; continue; }
         cls[i] = 1000;                       /* final */
         out.res[i] = r;
-        out.base[i] = (const PipCell *)chunk.p;
+        out.base[i] = (const pip_u64 *)chunk.p;
       }
       if (pending == 0) {
         /* re-arm the escalated problems on the device */

@@ -29,11 +29,28 @@ struct PipBatchTimes {
   unsigned long long phase_cycles[PIP_NPHASE] = {0};   /* profile build only */
 };
 
+/* read-only view of one problem's cells in the wire format (pip_types.h) */
+struct PipCellView {
+  const pip_u64 *w;
+  bool wide;
+  int n;
+  int kind(int i) const { return wide ? (int)(w[3 * i] & 0xffffffffull) : PIP_CELL_KIND(w[i]); }
+  pip_i64 p1(int i) const { return wide ? (pip_i64)w[3 * i + 1] : PIP_CELL_P1(w[i]); }
+  pip_i64 p2(int i) const { return wide ? (pip_i64)w[3 * i + 2] : PIP_CELL_P2(w[i]); }
+};
+
 struct PipBatchOut {
-  std::vector<PipResult> res;           /* cell_off indexes cells_of() storage */
-  std::vector<const PipCell *> base;    /* per problem: base pointer of its round's host chunk */
+  std::vector<PipResult> res;           /* cell_off = word offset into the round's host chunk */
+  std::vector<const pip_u64 *> base;    /* per problem: base pointer of its round's host chunk */
   PipBatchTimes times;
-  const PipCell *cells_of(size_t i) const { return base[i] + res[i].cell_off; }
+  PipCellView cells_of(size_t i) const
+  {
+    PipCellView v;
+    v.w = base[i] ? base[i] + res[i].cell_off : nullptr;
+    v.wide = (res[i].rflags & PIP_RES_WIDE) != 0;
+    v.n = res[i].ncells;
+    return v;
+  }
 };
 
 class PipEngine {

@@ -139,7 +139,13 @@ void fill_problem(const MatView &dom, const MatView *ctx, const Shape &s, PipPro
 }
 
 /* ---- cells -> tree: source/sol.c:435-734 ------------------------------------------------- */
-struct Cells { std::vector<PipCell> own; const PipCell *c; int n; };
+/* cell accessors: the wire view (PipCellView) or a private unpacked copy (Simplify) */
+struct ArrCells {
+  const PipCell *c;
+  int kind(int i) const { return c[i].kind; }
+  I p1(int i) const { return c[i].p1; }
+  I p2(int i) const { return c[i].p2; }
+};
 
 int skip_obj(const PipCell *c, int i);
 int skip_new(const PipCell *c, int i) { return c[i].kind != PIP_C_NEW ? i : skip_obj(c, i + 1); }
@@ -169,9 +175,10 @@ void simplify_cells(PipCell *c, int &ncell, int i)
   }
 }
 
-PipVector_dp *decode_vector(const PipCell *c, int *i, int Bg, int Urs_p, int flags)
+template <class C>
+PipVector_dp *decode_vector(const C &c, int *i, int Bg, int Urs_p, int flags)
 {
-  int n = (int)c[*i].p1, unbounded = 0;
+  int n = (int)c.p1(*i), unbounded = 0;
   if (flags & S_REMOVE) --n;
   n -= Urs_p;
   const int first_urs = Urs_p + (Bg >= 0);
@@ -181,7 +188,7 @@ PipVector_dp *decode_vector(const PipCell *c, int *i, int Bg, int Urs_p, int fla
   v->the_deno = (I *)xmalloc(sizeof(I) * (n > 0 ? n : 0));
   for (int j = 0, k = 0; k < n; j++) {
     (*i)++;
-    I N = c[*i].p1, D = c[*i].p2, d = gcd_abs(N, D);
+    I N = c.p1(*i), D = c.p2(*i), d = gcd_abs(N, D);
     if ((flags & S_SHIFT) && j == Bg) { N -= D; if (N != 0) unbounded = 1; }
     if ((flags & S_REMOVE) && j == Bg) continue;
     if (first_urs <= j && j < first_urs + Urs_p) continue;
@@ -195,20 +202,21 @@ PipVector_dp *decode_vector(const PipCell *c, int *i, int Bg, int Urs_p, int fla
   return v;
 }
 
-PipQuast_dp *decode_quast(const PipCell *c, int *i, PipQuast_dp *father, int Bg, int Urs_p, int flags)
+template <class C>
+PipQuast_dp *decode_quast(const C &c, int *i, PipQuast_dp *father, int Bg, int Urs_p, int flags)
 {
-  while (c[*i].kind == PIP_C_FREE) (*i)++;
+  while (c.kind(*i) == PIP_C_FREE) (*i)++;
   PipQuast_dp *q = (PipQuast_dp *)xmalloc(sizeof *q);
   q->newparm = nullptr; q->list = nullptr; q->condition = nullptr;
   q->next_then = q->next_else = nullptr; q->father = father;
   PipNewparm_dp *last = nullptr;
-  while (c[*i].kind == PIP_C_NEW) {                  /* sol_newparm_edit_xx, source/sol.c:525-577 */
+  while (c.kind(*i) == PIP_C_NEW) {                  /* sol_newparm_edit_xx, source/sol.c:525-577 */
     const int newcell = *i;
     (*i) += 2;
     PipNewparm_dp *np = (PipNewparm_dp *)xmalloc(sizeof *np);
     np->vector = decode_vector(c, i, Bg, Urs_p, flags & S_REMOVE);
-    np->rank = (int)c[newcell].p1;
-    np->deno = c[*i].p1;
+    np->rank = (int)c.p1(newcell);
+    np->deno = c.p1(*i);
     if (flags & S_REMOVE) np->rank--;
     np->rank -= Urs_p;
     np->next = nullptr;
@@ -216,8 +224,8 @@ PipQuast_dp *decode_quast(const PipCell *c, int *i, PipQuast_dp *father, int Bg,
     last = np;
     (*i)++;
   }
-  const int kind = c[*i].kind;
-  const int nb = (int)c[*i].p1;
+  const int kind = c.kind(*i);
+  const int nb = (int)c.p1(*i);
   (*i)++;
   if (kind == PIP_C_LIST) {                           /* sol_list_edit_xx, source/sol.c:591-638 */
     PipList_dp *head = (PipList_dp *)xmalloc(sizeof *head), *cur = head;
@@ -250,8 +258,9 @@ struct Ser { I *out; long cap, len; unsigned long long h; bool hashing; };
 inline void sput(Ser &s, I v)
 {
   if (s.hashing) {
-    unsigned long long x = (unsigned long long)v;
-    for (int i = 0; i < 8; i++) { s.h ^= (x >> (8 * i)) & 0xff; s.h *= 0x100000001b3ULL; }
+    s.h ^= (unsigned long long)v;
+    s.h *= 0x9E3779B97F4A7C15ULL;
+    s.h ^= s.h >> 32;
   }
   if (s.out && s.len < s.cap) s.out[s.len] = v;
   s.len++;
@@ -277,6 +286,85 @@ void ser_quast(Ser &s, const PipQuast_dp *q)
     sput(s, q->next_then != nullptr);
     if (q->next_then) ser_quast(s, q->next_then);
   } else sput(s, 0);
+}
+
+/* cells -> serialised quast words without building the tree (the bulk path): the same decode
+ * rules as decode_vector / decode_quast above */
+template <class C>
+void ser_vector_direct(Ser &s, const C &c, int *i, int Bg, int Urs_p, int flags)
+{
+  int n = (int)c.p1(*i), unbounded = 0;
+  if (flags & S_REMOVE) --n;
+  n -= Urs_p;
+  const int first_urs = Urs_p + (Bg >= 0);
+  /* the unbounded marker rewrites every denominator, so it must be known before emitting */
+  if (flags & S_SHIFT) {
+    int t = *i;
+    for (int j = 0, k = 0; k < n; j++) {
+      t++;
+      if (j == Bg && c.p1(t) - c.p2(t) != 0) unbounded = 1;
+      if ((flags & S_REMOVE) && j == Bg) continue;
+      if (first_urs <= j && j < first_urs + Urs_p) continue;
+      k++;
+    }
+  }
+  sput(s, n);
+  for (int j = 0, k = 0; k < n; j++) {
+    (*i)++;
+    I N = c.p1(*i), D = c.p2(*i), d = (D == 1) ? 1 : gcd_abs(N, D);
+    if ((flags & S_SHIFT) && j == Bg) N -= D;
+    if ((flags & S_REMOVE) && j == Bg) continue;
+    if (first_urs <= j && j < first_urs + Urs_p) continue;
+    I num = d ? N / d : 0;
+    if (flags & S_NEGATE) num = -num;
+    sput(s, num);
+    sput(s, unbounded ? 0 : ((d == D) ? 1 : (d ? D / d : 0)));
+    k++;
+  }
+  (*i)++;
+}
+
+template <class C>
+void ser_quast_direct(Ser &s, const C &c, int *i, int Bg, int Urs_p, int flags)
+{
+  while (c.kind(*i) == PIP_C_FREE) (*i)++;
+  int n = 0;
+  for (int t = *i; c.kind(t) == PIP_C_NEW; t += (int)c.p1(t + 2) + 4) n++;   /* New Div Form Val*m Val */
+  sput(s, n);
+  for (int k = 0; k < n; k++) {
+    const int newcell = *i;
+    (*i) += 2;
+    int rank = (int)c.p1(newcell);
+    if (flags & S_REMOVE) rank--;
+    rank -= Urs_p;
+    sput(s, rank);
+    sput(s, c.p1(*i + (int)c.p1(*i) + 1));          /* the divisor follows the form */
+    ser_vector_direct(s, c, i, Bg, Urs_p, flags & S_REMOVE);
+    (*i)++;
+  }
+  const int kind = c.kind(*i);
+  const int nb = (int)c.p1(*i);
+  (*i)++;
+  if (kind == PIP_C_LIST) {
+    sput(s, 1);
+    if (nb == 0) { sput(s, 1); sput(s, 0); }
+    else {
+      sput(s, nb);
+      for (int e = 0; e < nb; e++) { sput(s, 1); ser_vector_direct(s, c, i, Bg, Urs_p, flags); }
+    }
+    if (flags & S_DUAL) { sput(s, 1); ser_quast_direct(s, c, i, Bg, Urs_p, 0); }
+    else sput(s, 0);
+  } else if (kind == PIP_C_NIL) {
+    sput(s, 0);
+  } else if (kind == PIP_C_IF) {
+    sput(s, 2);
+    ser_vector_direct(s, c, i, Bg, Urs_p, flags & S_REMOVE);
+    ser_quast_direct(s, c, i, Bg, Urs_p, flags);
+    ser_quast_direct(s, c, i, Bg, Urs_p, flags);
+  } else {
+    fprintf(stderr, "\nAie !!! Flag %d inattendu.\n", kind);
+    exit(1);
+  }
 }
 
 const char *fatal_message(int status)
@@ -505,18 +593,43 @@ void pip_last_batch_stats_dp(PipBatchStats_dp *out) { if (out) *out = g_stats; }
 
 /* ---- batch entry points -------------------------------------------------------------------- */
 
+static void unpack_cells(const PipCellView &v, std::vector<PipCell> &out)
+{
+  out.resize(v.n);
+  for (int i = 0; i < v.n; i++) { out[i].kind = v.kind(i); out[i].pad = 0; out[i].p1 = v.p1(i); out[i].p2 = v.p2(i); }
+}
+
 static PipQuast_dp *decode_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify)
 {
-  const PipResult &r = bo.res[i];
-  const PipCell *c = bo.cells_of(i);
+  const PipCellView v = bo.cells_of(i);
   int at = 0;
   if (simplify) {
-    std::vector<PipCell> copy(c, c + r.ncells);
-    int n = r.ncells;
+    std::vector<PipCell> copy;
+    unpack_cells(v, copy);
+    int n = v.n;
     simplify_cells(copy.data(), n, 0);
-    return decode_quast(copy.data(), &at, nullptr, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
+    ArrCells a = {copy.data()};
+    return decode_quast(a, &at, nullptr, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
   }
-  return decode_quast(c, &at, nullptr, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
+  return decode_quast(v, &at, nullptr, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
+}
+
+/* serialise problem i straight from its cells (status OK or VOID) */
+static void serialize_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify, Ser &out)
+{
+  if (bo.res[i].status == PIP_ST_VOID) { sput(out, -1); return; }
+  const PipCellView v = bo.cells_of(i);
+  int at = 0;
+  if (simplify) {
+    std::vector<PipCell> copy;
+    unpack_cells(v, copy);
+    int n = v.n;
+    simplify_cells(copy.data(), n, 0);
+    ArrCells a = {copy.data()};
+    ser_quast_direct(out, a, &at, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
+    return;
+  }
+  ser_quast_direct(out, v, &at, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
 }
 
 int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const *contexts,
@@ -624,8 +737,13 @@ int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long 
       status[i] = bo.res[i].status;
       ncells[i] = bo.res[i].ncells;
       cell_off[i] = at;
-      if (at + bo.res[i].ncells <= cell_cap && bo.res[i].ncells)
-        memcpy(cells_out + at, bo.cells_of(i), sizeof(PipCell) * bo.res[i].ncells);
+      if (at + bo.res[i].ncells <= cell_cap && bo.res[i].ncells) {
+        const PipCellView v = bo.cells_of(i);
+        for (int k = 0; k < v.n; k++) {
+          PipCell_dp &o = cells_out[at + k];
+          o.kind = v.kind(k); o.pad = 0; o.p1 = v.p1(k); o.p2 = v.p2(k);
+        }
+      }
       at += bo.res[i].ncells;
     }
     account(bo, 0);
@@ -675,44 +793,68 @@ void build_dense(DenseBatch &B, long long n, int dr, int dc, const I *dom, int h
   });
 }
 
-/* decode every solved problem, hash / serialise its quast; returns words needed */
+/* serialise every solved problem straight from its cells: one pass per thread range into a
+ * thread-private buffer (hash + length on the fly), then one copy into the caller's stream */
 long long emit_results(const DenseBatch &B, const PipBatchOut &bo, int *status, unsigned long long *hashes,
                        long long *ser, long long ser_cap, long long *ser_off)
 {
   const size_t n = (size_t)B.n;
   std::vector<long long> words(n, 0);
-  /* pass 1: hash + size */
-  parallel_for(n, [&](size_t a, size_t b) {
+  const bool keep = ser != nullptr && ser_off != nullptr;
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t nt = std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, (n + 255) / 256));
+  const size_t per = (n + nt - 1) / nt;
+  std::vector<std::vector<I>> bufs(nt);
+  std::vector<std::thread> th;
+  auto work = [&](size_t t) {
+    const size_t a = t * per, b = std::min(n, a + per);
+    std::vector<I> &buf = bufs[t];
+    std::vector<I> tmp;
+    if (keep) buf.reserve((b > a ? b - a : 0) * 256);
     for (size_t i = a; i < b; i++) {
       status[i] = bo.res[i].status;
       unsigned long long h = 0;
       long long w = 0;
       if (status[i] == PIP_ST_OK || status[i] == PIP_ST_VOID) {
-        PipQuast_dp *q = status[i] == PIP_ST_OK ? decode_one(bo, i, B.shapes[i], B.simplify) : nullptr;
-        Ser s = {nullptr, 0, 0, 0xcbf29ce484222325ULL, true};
-        ser_quast(s, q);
-        h = s.h; w = s.len;
-        pip_quast_free_dp(q);
+        if (keep) {
+          const size_t at = buf.size();
+          const size_t guess = (size_t)bo.res[i].ncells * 3 + 8;
+          buf.resize(at + guess);
+          Ser s = {buf.data() + at, (long)guess, 0, 0xcbf29ce484222325ULL, true};
+          serialize_one(bo, i, B.shapes[i], B.simplify, s);
+          buf.resize(at + (size_t)s.len);
+          h = s.h; w = s.len;
+        } else {
+          Ser s = {nullptr, 0, 0, 0xcbf29ce484222325ULL, true};
+          serialize_one(bo, i, B.shapes[i], B.simplify, s);
+          h = s.h; w = s.len;
+        }
       }
       if (hashes) hashes[i] = h;
       words[i] = w;
     }
-  });
+  };
+  if (nt == 1) work(0);
+  else {
+    for (size_t t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+  }
   long long total = 0;
   if (ser_off) {
     for (size_t i = 0; i < n; i++) { ser_off[i] = total; total += words[i]; }
     ser_off[n] = total;
   } else for (size_t i = 0; i < n; i++) total += words[i];
-  if (ser && ser_off && total <= ser_cap) {
-    parallel_for(n, [&](size_t a, size_t b) {
-      for (size_t i = a; i < b; i++) {
-        if (!(status[i] == PIP_ST_OK || status[i] == PIP_ST_VOID)) continue;
-        PipQuast_dp *q = status[i] == PIP_ST_OK ? decode_one(bo, i, B.shapes[i], B.simplify) : nullptr;
-        Ser s = {ser + ser_off[i], (long)words[i], 0, 0, false};
-        ser_quast(s, q);
-        pip_quast_free_dp(q);
-      }
-    });
+  if (keep && total <= ser_cap) {
+    th.clear();
+    auto copy = [&](size_t t) {
+      const size_t a = t * per;
+      if (a < n && !bufs[t].empty()) memcpy(ser + ser_off[a], bufs[t].data(), bufs[t].size() * sizeof(I));
+    };
+    if (nt == 1) copy(0);
+    else {
+      for (size_t t = 0; t < nt; t++) th.emplace_back(copy, t);
+      for (auto &x : th) x.join();
+    }
   }
   return total;
 }

@@ -61,9 +61,10 @@ extern "C" long long pip_layout_words(int nvar, int nparm, int ni, int nc, int f
 }
 
 /* ---- cell gather ------------------------------------------------------------------------ */
-/* one warp per problem: copy its cells (24-byte records = 3 words) to out[dst_off[p]...] */
+/* one warp per problem: move its cells from the warp windows to the compact word stream at
+ * dst_off[q], packing each cell into one word unless the problem is flagged wide */
 __global__ void pip_gather_kernel(PipResult *res, const int *order, const PipCell *cells,
-                                  const long long *dst_off, PipCell *out, int nprob)
+                                  const long long *dst_off, pip_u64 *out, int nprob)
 {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,12 +72,16 @@ __global__ void pip_gather_kernel(PipResult *res, const int *order, const PipCel
   for (int q = warp; q < nprob; q += nwarps) {
     const int p = order ? order[q] : q;
     const PipResult r = res[p];
-    const long long *src = (const long long *)(cells + r.cell_off);
-    long long *dst = (long long *)(out + dst_off[q]);
-    const int words = r.ncells * 3;
-    for (int w = lane; w < words; w += 32) dst[w] = src[w];
+    const PipCell *src = cells + r.cell_off;
+    pip_u64 *dst = out + dst_off[q];
+    if (r.rflags & PIP_RES_WIDE) {
+      const pip_u64 *s3 = (const pip_u64 *)src;
+      for (int w = lane; w < r.ncells * 3; w += 32) dst[w] = s3[w];
+    } else {
+      for (int c = lane; c < r.ncells; c += 32) dst[c] = PIP_CELL_PACK(src[c].kind, src[c].p1, src[c].p2);
+    }
     __syncwarp();
-    if (lane == 0) res[p].cell_off = dst_off[q];      /* now relative to the compact stream */
+    if (lane == 0) res[p].cell_off = dst_off[q];      /* now a word offset into the compact stream */
   }
 }
 
@@ -90,7 +95,11 @@ __global__ void pip_scan_kernel(const PipResult *res, const int *order, long lon
   __syncthreads();
   for (int base = 0; base < nprob; base += blockDim.x) {
     const int i = base + tid;
-    long long v = (i < nprob) ? (long long)res[order ? order[i] : i].ncells : 0;
+    long long v = 0;
+    if (i < nprob) {
+      const PipResult &r = res[order ? order[i] : i];
+      v = (long long)r.ncells * ((r.rflags & PIP_RES_WIDE) ? 3 : 1);
+    }
     long long x = v;
     for (int o = 1; o < 32; o <<= 1) {
       long long y = __shfl_up_sync(0xffffffffu, x, o);
@@ -117,7 +126,7 @@ __global__ void pip_scan_kernel(const PipResult *res, const int *order, long lon
 }
 
 extern "C" cudaError_t pip_launch_gather(PipResult *res, const int *order, const PipCell *cells, long long *dst_off,
-                                         PipCell *out, int nprob, long long *total, int phase,
+                                         pip_u64 *out, int nprob, long long *total, int phase,
                                          cudaStream_t stream)
 {
   if (phase == 0) pip_scan_kernel<<<1, 1024, 0, stream>>>(res, order, dst_off, nprob, total);

@@ -475,14 +475,17 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
   return 0;
 }
 
-PIP_DEV void pip_put(PipCell *out, int idx, int kind, pip_i64 p1, pip_i64 p2)
+/* append one cell; returns true when it does not fit the packed wire format */
+PIP_DEV bool pip_put(PipCell *out, int idx, int kind, pip_i64 p1, pip_i64 p2)
 {
   out[idx].kind = kind; out[idx].pad = 0; out[idx].p1 = p1; out[idx].p2 = p2;
+  return !PIP_CELL_FITS(p1, p2);
 }
 
 /* solution_xx, source/traiter.c:255-271: 1 + nvar*(2+nparm) cells, lane-parallel */
-PIP_DEVNI void pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int at)
+PIP_DEVNI bool pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int at)
 {
+  bool wide = false;
   const int per = T.nparm + 2, total = 1 + T.nvar * per;
   const int *fl = pip_fl(B, T);
   const pip_i64 *den = pip_den(B, T);
@@ -493,8 +496,9 @@ PIP_DEVNI void pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int 
     int j = (r == per - 1) ? T.nvar : T.nvar + r;
     int f = fl[i];
     pip_i64 d = den[i];
-    pip_put(out, at + c, PIP_C_VAL, pip_entry(B, T, f, d, j), d);
+    wide = pip_put(out, at + c, PIP_C_VAL, pip_entry(B, T, f, d, j), d) || wide;
   }
+  return wide;
 }
 
 /* has_cut_xx, source/integrer.c:230-254 (serial, one lane) */
@@ -538,7 +542,7 @@ PIP_DEV int pip_find_parm(const pip_i64 *ctx, int cstride, int nr, int nparm, pi
 PIP_DEV void pip_solve_one(const PipProblem &P, const pip_i64 *in, pip_i64 *B, int words, int slack_level,
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
-                           int &status_out, int &ncell_out, PipStats &st)
+                           int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st)
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
@@ -554,7 +558,8 @@ PIP_DEV void pip_solve_one(const PipProblem &P, const pip_i64 *in, pip_i64 *B, i
   int nc = P.nc;
   int ncell = 0, status = PIP_ST_OK;
   int ret_site = 0, ci = 0, cplus = 0, critic = 0, pivi = 0, depth = 0;
-  bool feasible = false;
+  bool feasible = false, wide = false;
+  rflags_out = 0;
   pip_i64 top = 0;
   pip_i64 *ctx = B + L.ctx;
   pip_i64 *cut = B + L.cut;
@@ -709,7 +714,7 @@ AFTER_COMPA:
       if (j < np) v = pip_div(row[T.nvar + 1 + j], g);
       else v = integer ? pip_floor_q(row[T.nvar], g) : pip_div(row[T.nvar], g);
       crow[j] = v;
-      pip_put(out, ncell + 2 + j, PIP_C_VAL, v, 1);
+      wide = pip_put(out, ncell + 2 + j, PIP_C_VAL, v, 1) || wide;
     }
     if (lane == 0) {
       pip_put(out, ncell, PIP_C_IF, 0, 0);
@@ -753,7 +758,7 @@ NONNEG:
   if (level == 0 && !integer) {
     const int total = 1 + T.nvar * (T.nparm + 2);
     if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
-    pip_emit_solution(B, T, out, ncell);
+    wide = pip_emit_solution(B, T, out, ncell) || wide;
     ncell += total;
     goto LEAF;
   }
@@ -801,9 +806,9 @@ NONNEG:
             pip_put(out, ncell, PIP_C_NEW, np, 0);
             pip_put(out, ncell + 1, PIP_C_DIV, 0, 0);
             pip_put(out, ncell + 2, PIP_C_FORM, np + 1, 0);
-            for (int j = 0; j < np; j++) pip_put(out, ncell + 3 + j, PIP_C_VAL, -c[1 + j], 1);
-            pip_put(out, ncell + 3 + np, PIP_C_VAL, -c[0], 1);
-            pip_put(out, ncell + 4 + np, PIP_C_VAL, c[1 + np], 1);
+            for (int j = 0; j < np; j++) wide = pip_put(out, ncell + 3 + j, PIP_C_VAL, -c[1 + j], 1) || wide;
+            wide = pip_put(out, ncell + 3 + np, PIP_C_VAL, -c[0], 1) || wide;
+            wide = pip_put(out, ncell + 4 + np, PIP_C_VAL, c[1 + np], 1) || wide;
             for (int k = 0; k < nc; k++) { pip_i64 *r = ctx + k * cstride; r[np + 1] = r[np]; r[np] = 0; }
             pip_i64 *r0 = ctx + nc * cstride, *r1 = r0 + cstride;
             for (int j = 0; j < np; j++) { r0[j] = -c[1 + j]; r1[j] = c[1 + j]; }
@@ -845,7 +850,7 @@ NONNEG:
     if (verdict == 0) {
       const int total = 1 + T.nvar * (T.nparm + 2);
       if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
-      pip_emit_solution(B, T, out, ncell);
+      wide = pip_emit_solution(B, T, out, ncell) || wide;
       ncell += total;
       PIP_LAP(st, PIP_PH_EMIT);
     } else {
@@ -910,6 +915,7 @@ DONE:
   PIP_LAP(st, PIP_PH_OTHER);
   status_out = status;
   ncell_out = (status == PIP_ST_OK) ? ncell : 0;
+  rflags_out = W::any(wide) ? PIP_RES_WIDE : 0u;
 }
 
 #endif

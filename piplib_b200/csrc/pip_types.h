@@ -54,7 +54,8 @@ typedef struct {
 typedef struct {
   int status;
   int ncells;
-  pip_i64 cell_off;              /* index of the first cell in the cell pool */
+  pip_i64 cell_off;              /* first cell in the cell pool; after the gather: word offset
+                                    into the compact stream */
   unsigned pivots;               /* successful pivots incl. sub-solves */
   unsigned cuts;
   unsigned subsolves;            /* non-parametric feasibility solves (compa_test, context) */
@@ -62,7 +63,7 @@ typedef struct {
   unsigned max_rows, max_cols;   /* largest nligne x ncol seen by a pivot */
   unsigned wrapped;              /* # pivots during which some 64-bit product wrapped */
   unsigned elem_updates_lo, elem_updates_hi;
-  unsigned pad;
+  unsigned rflags;               /* PIP_RES_* */
 } PipResult;
 
 typedef struct {
@@ -70,6 +71,17 @@ typedef struct {
   int pad;
   pip_i64 p1, p2;
 } PipCell;
+
+/* Wire format of the solution cells after the device-side gather: one 64-bit word per cell,
+ *   bits 0-3 kind | bits 4-19 param2 (unsigned, denominators) | bits 20-63 param1 (signed),
+ * unless some cell of the problem does not fit (PIP_RES_WIDE in PipResult.rflags): then the
+ * problem's cells are shipped as raw {kind, param1, param2} triples (3 words per cell). */
+#define PIP_RES_WIDE 1u
+#define PIP_CELL_FITS(p1, p2) ((pip_u64)(p2) < 65536ull && (p1) >= -(1ll << 43) && (p1) < (1ll << 43))
+#define PIP_CELL_PACK(kind, p1, p2) ((pip_u64)(unsigned)(kind) | ((pip_u64)(p2) << 4) | ((pip_u64)(p1) << 20))
+#define PIP_CELL_KIND(w) ((int)((w) & 15ull))
+#define PIP_CELL_P2(w) ((pip_i64)(((w) >> 4) & 0xffffull))
+#define PIP_CELL_P1(w) (((pip_i64)(w)) >> 20)
 
 /* launch parameters of the warp-per-problem kernels */
 typedef struct {

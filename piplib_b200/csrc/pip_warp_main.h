@@ -29,8 +29,9 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
     st.lap = clock64();
 #endif
     int status = PIP_ST_OK, ncell = 0;
+    unsigned rflags = 0;
     pip_solve_one(P, L.pool + P.off, arena, L.work_words, L.slack_level, window + used, stk,
-                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, st);
+                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st);
     if (lane == 0) {
       PipResult r;
       r.status = status; r.ncells = ncell;
@@ -39,7 +40,7 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
       r.max_rows = st.max_rows; r.max_cols = st.max_cols; r.wrapped = 0;
       r.elem_updates_lo = (unsigned)(st.elem_updates & 0xffffffffull);
       r.elem_updates_hi = (unsigned)(st.elem_updates >> 32);
-      r.pad = 0;
+      r.rflags = rflags;
       L.res[p] = r;
 #ifdef PIP_PROFILE
       if (L.prof) for (int k = 0; k < PIP_NPHASE; k++) atomicAdd(&L.prof[k], st.cyc[k]);
