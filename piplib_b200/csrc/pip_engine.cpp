@@ -69,6 +69,8 @@ const int N_G = sizeof(G_LADDER) / sizeof(G_LADDER[0]);
 
 }  // namespace
 
+static int g_device = 0;
+
 struct PipEngine::Impl {
   std::mutex mu;
   int device = 0, sm_count = 0;
@@ -77,12 +79,13 @@ struct PipEngine::Impl {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total, d_prof;
-  PinBuf h_res, h_total;
+  PinBuf h_res, h_total, h_input;
   std::vector<PinBuf> h_chunks;     /* one per round, reused across calls */
 
   void init()
   {
     if (inited) return;
+    device = g_device;
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -99,13 +102,27 @@ struct PipEngine::Impl {
 };
 
 PipEngine::PipEngine() : impl_(new Impl) {}
-PipEngine &PipEngine::get() { static PipEngine e; return e; }
+PipEngine &PipEngine::lane(int i)
+{
+  static PipEngine e[MAX_LANES];
+  if (i < 0) i = 0;
+  return e[i % MAX_LANES];
+}
 int PipEngine::set_device(int dev)
 {
   std::lock_guard<std::mutex> g(impl_->mu);
   if (impl_->inited && dev != impl_->device) return -1;
-  impl_->device = dev;
+  g_device = dev;
   return 0;
+}
+void *PipEngine::pinned_input(size_t bytes)
+{
+  Impl &E = *impl_;
+  std::lock_guard<std::mutex> g(E.mu);
+  E.init();
+  CK(cudaSetDevice(E.device));
+  E.h_input.reserve(bytes);
+  return E.h_input.p;
 }
 int PipEngine::sm_count() { std::lock_guard<std::mutex> g(impl_->mu); impl_->init(); return impl_->sm_count; }
 cudaStream_t PipEngine::stream() { std::lock_guard<std::mutex> g(impl_->mu); impl_->init(); return impl_->stream; }
@@ -126,7 +143,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
 
   /* ---- inputs ------------------------------------------------------------------------- */
   const PipProblem *d_prob = in.d_prob;
-  const pip_i64 *d_pool = in.d_pool;
+  const void *d_pool = in.d_pool;
   double t0 = now_s();
   if (!d_prob) {
     E.d_prob.reserve(n * sizeof(PipProblem));
@@ -135,10 +152,11 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
     out.times.h2d_bytes += n * sizeof(PipProblem);
   }
   if (!d_pool) {
-    E.d_pool.reserve(std::max<size_t>(in.pool_words, 1) * sizeof(pip_i64));
-    CK(cudaMemcpyAsync(E.d_pool.p, in.h_pool, in.pool_words * sizeof(pip_i64), cudaMemcpyHostToDevice, s));
-    d_pool = (const pip_i64 *)E.d_pool.p;
-    out.times.h2d_bytes += in.pool_words * sizeof(pip_i64);
+    const size_t pool_bytes = in.pool_words << in.elem_log2;
+    E.d_pool.reserve(std::max<size_t>(pool_bytes, 8));
+    CK(cudaMemcpyAsync(E.d_pool.p, in.h_pool, pool_bytes, cudaMemcpyHostToDevice, s));
+    d_pool = E.d_pool.p;
+    out.times.h2d_bytes += pool_bytes;
   }
   /* per-problem records start as PENDING */
   E.h_res.reserve(n * sizeof(PipResult));
@@ -218,7 +236,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
 
       PipLaunch L;
       memset(&L, 0, sizeof L);
-      L.prob = d_prob; L.pool = d_pool; L.order = (const int *)E.d_order.p; L.nprob = m;
+      L.prob = d_prob; L.pool = d_pool; L.pool_elem_log2 = in.elem_log2; L.order = (const int *)E.d_order.p; L.nprob = m;
       L.res = (PipResult *)E.d_res.p;
       L.cells = (PipCell *)E.d_cells.p; L.cells_per_warp = per_warp;
       L.stack = (pip_i64 *)E.d_stack.p; L.stack_words_per_warp = cs.stack_words;

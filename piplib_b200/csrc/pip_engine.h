@@ -13,10 +13,11 @@
 struct PipBatchIn {
   size_t n = 0;
   const PipProblem *h_prob = nullptr;   /* host descriptors: always required (class planning) */
-  const pip_i64 *h_pool = nullptr;      /* host pool, uploaded unless d_pool is given */
-  size_t pool_words = 0;
+  const void *h_pool = nullptr;         /* host pool, uploaded unless d_pool is given */
+  size_t pool_words = 0;                /* elements in the pool */
+  int elem_log2 = 3;                    /* log2(bytes per pool element): 0, 2 or 3 */
   const PipProblem *d_prob = nullptr;   /* optional device-resident copies */
-  const pip_i64 *d_pool = nullptr;
+  const void *d_pool = nullptr;
   bool fetch_cells = true;              /* copy the compacted cells back to the host */
   int sol_size = PIP_SOL_SIZE, maxcol = PIP_MAXCOL;
 };
@@ -55,7 +56,13 @@ struct PipBatchOut {
 
 class PipEngine {
  public:
-  static PipEngine &get();
+  static PipEngine &get() { return lane(0); }
+  /* independent engines (own stream + buffers) so that batches can be pipelined: while one lane
+   * waits for its kernels, another converts inputs or decodes results */
+  enum { MAX_LANES = 4 };
+  static PipEngine &lane(int i);
+  /* engine-owned pinned staging for the input pool (valid until the next call on this lane) */
+  void *pinned_input(size_t bytes);
   /* Runs the whole ladder.  Host cell storage referenced by `out` is engine-owned pinned memory,
    * valid until the next run() call.  Throws std::runtime_error on CUDA errors. */
   void run(const PipBatchIn &in, PipBatchOut &out);

@@ -81,7 +81,8 @@ Shape derive_shape(const MatView &dom, const MatView *ctx, int Bg, const PipOpti
 
 /* tab_Matrix2Tableau_xx (source/tab.c:292-393) writing `width`-wide rows to out.
  * ctx_mode: the matrix is the context (n == -1 in the reference). */
-void matrix_to_rows(const MatView &mx, I *out, int width, int Nv, bool ctx_mode, int Shift, int Bg, int Urs)
+template <class T>
+void matrix_to_rows(const MatView &mx, T *out, int width, int Nv, bool ctx_mode, int Shift, int Bg, int Urs)
 {
   const int ctx = ctx_mode ? 1 : 0;
   int ncolm = mx.cols - 1;
@@ -91,7 +92,7 @@ void matrix_to_rows(const MatView &mx, I *out, int width, int Nv, bool ctx_mode,
   if (ctx) { Shift = 0; cst = Nv + Urs; } else cst = Nv;
   int cur = 0;
   for (int i = 0; i < mx.rows; i++) {
-    I *r = out + (size_t)cur * width;
+    T *r = out + (size_t)cur * width;
     for (int j = 0; j < width; j++) r[j] = 0;
     I big = 0;
     const bool ineq = MV(mx, i, 0) != 0;
@@ -99,28 +100,28 @@ void matrix_to_rows(const MatView &mx, I *out, int width, int Nv, bool ctx_mode,
     for (j = 0; j < Nv; j++) {
       if (isnew && j == Bg) continue;
       if (Shift) big += MV(mx, i, 1 + j);
-      r[j] = Shift > 0 ? -MV(mx, i, 1 + j) : MV(mx, i, 1 + j);
+      r[j] = (T)(Shift > 0 ? -MV(mx, i, 1 + j) : MV(mx, i, 1 + j));
     }
     int k = Nv + 1;
     for (j = Nv + 1; j < ncolm; j++) {
       if (isnew && j == Bg) continue;
-      r[j] = MV(mx, i, k);
+      r[j] = (T)MV(mx, i, k);
       k++;
     }
     for (j = 0; j < Urs; j++) {
       int pos_n = ncolm - ctx + j, pos = pos_n - Urs;
       if (pos <= Bg) --pos;
-      r[pos_n] = -r[pos];
+      r[pos_n] = (T)(-r[pos]);
     }
-    r[cst] = MV(mx, i, mx.cols - 1);
+    r[cst] = (T)MV(mx, i, mx.cols - 1);
     if (Shift) {
       if (Shift < 0) big = -big;
-      if (isnew) r[Bg] = big; else r[Bg] += big;
+      if (isnew) r[Bg] = (T)big; else r[Bg] = (T)(r[Bg] + big);
     }
     cur++;
     if (!ineq) {
-      I *r2 = out + (size_t)cur * width;
-      for (j = 0; j < width; j++) r2[j] = -r[j];
+      T *r2 = out + (size_t)cur * width;
+      for (j = 0; j < width; j++) r2[j] = (T)(-r[j]);
       cur++;
     }
   }
@@ -129,10 +130,11 @@ void matrix_to_rows(const MatView &mx, I *out, int width, int Nv, bool ctx_mode,
 /* words one problem contributes to the pool */
 size_t problem_words(const Shape &s) { return (size_t)s.Nl * (s.Nn + s.Np + 1) + (size_t)s.Nm * (s.Np + 1); }
 
-void fill_problem(const MatView &dom, const MatView *ctx, const Shape &s, PipProblem &P, I *pool, size_t off)
+template <class T>
+void fill_problem(const MatView &dom, const MatView *ctx, const Shape &s, PipProblem &P, T *pool, size_t off)
 {
   P.nvar = s.Nn; P.nparm = s.Np; P.ni = s.Nl; P.nc = s.Nm; P.bigparm = s.Bg; P.flags = s.flags; P.off = (I)off;
-  I *tab = pool + off;
+  T *tab = pool + off;
   matrix_to_rows(dom, tab, s.Nn + s.Np + 1, s.Nn, false, s.Shift, s.Bg, s.Urs);
   if (ctx && s.Nm)
     matrix_to_rows(*ctx, tab + (size_t)s.Nl * (s.Nn + s.Np + 1), s.Np + 1, s.Np - s.Urs, true, s.Shift, s.Bg - s.Nn - 1, s.Urs);
@@ -755,116 +757,171 @@ int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long 
   return 0;
 }
 
+}  // extern "C"
+
 /* ---- dense batches -------------------------------------------------------------------------- */
 namespace {
-struct DenseBatch {
-  long long n = 0;
-  std::vector<Shape> shapes;
-  std::vector<PipProblem> prob;
-  std::vector<I> pool;
-  size_t pool_words = 0;
-  int simplify = 0;
-  PipOptions_dp opt;
-};
-
-void build_dense(DenseBatch &B, long long n, int dr, int dc, const I *dom, int has_ctx, int cr, int cc,
-                 const I *ctx, int bignum, const PipOptions_dp *options)
-{
-  B.n = n;
-  B.opt = options ? *options : DEFAULT_OPTIONS;
-  B.simplify = B.opt.Simplify;
-  B.shapes.resize(n);
-  B.prob.resize(n);
-  std::vector<size_t> off(n + 1, 0);
-  for (long long i = 0; i < n; i++) {
-    MatView d = {dr, dc, nullptr, dom + (size_t)i * dr * dc};
-    MatView c = {cr, cc, nullptr, has_ctx ? ctx + (size_t)i * cr * cc : nullptr};
-    B.shapes[i] = derive_shape(d, has_ctx ? &c : nullptr, bignum, B.opt);
-    off[i + 1] = off[i] + problem_words(B.shapes[i]);
-  }
-  B.pool.resize(off[n] + 1);
-  B.pool_words = off[n];
-  parallel_for((size_t)n, [&](size_t a, size_t b) {
-    for (size_t i = a; i < b; i++) {
-      MatView d = {dr, dc, nullptr, dom + i * dr * dc};
-      MatView c = {cr, cc, nullptr, has_ctx ? ctx + i * cr * cc : nullptr};
-      fill_problem(d, has_ctx ? &c : nullptr, B.shapes[i], B.prob[i], B.pool.data(), off[i]);
-    }
-  });
-}
-
-/* serialise every solved problem straight from its cells: one pass per thread range into a
- * thread-private buffer (hash + length on the fly), then one copy into the caller's stream */
-long long emit_results(const DenseBatch &B, const PipBatchOut &bo, int *status, unsigned long long *hashes,
-                       long long *ser, long long ser_cap, long long *ser_off)
-{
-  const size_t n = (size_t)B.n;
-  std::vector<long long> words(n, 0);
-  const bool keep = ser != nullptr && ser_off != nullptr;
-  unsigned hw = std::thread::hardware_concurrency();
-  const size_t nt = std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, (n + 255) / 256));
-  const size_t per = (n + nt - 1) / nt;
-  std::vector<std::vector<I>> bufs(nt);
-  std::vector<std::thread> th;
-  auto work = [&](size_t t) {
-    const size_t a = t * per, b = std::min(n, a + per);
-    std::vector<I> &buf = bufs[t];
-    std::vector<I> tmp;
-    if (keep) buf.reserve((b > a ? b - a : 0) * 256);
-    for (size_t i = a; i < b; i++) {
-      status[i] = bo.res[i].status;
-      unsigned long long h = 0;
-      long long w = 0;
-      if (status[i] == PIP_ST_OK || status[i] == PIP_ST_VOID) {
-        if (keep) {
-          const size_t at = buf.size();
-          const size_t guess = (size_t)bo.res[i].ncells * 3 + 8;
-          buf.resize(at + guess);
-          Ser s = {buf.data() + at, (long)guess, 0, 0xcbf29ce484222325ULL, true};
-          serialize_one(bo, i, B.shapes[i], B.simplify, s);
-          buf.resize(at + (size_t)s.len);
-          h = s.h; w = s.len;
-        } else {
-          Ser s = {nullptr, 0, 0, 0xcbf29ce484222325ULL, true};
-          serialize_one(bo, i, B.shapes[i], B.simplify, s);
-          h = s.h; w = s.len;
-        }
-      }
-      if (hashes) hashes[i] = h;
-      words[i] = w;
-    }
-  };
-  if (nt == 1) work(0);
-  else {
-    for (size_t t = 0; t < nt; t++) th.emplace_back(work, t);
-    for (auto &x : th) x.join();
-  }
-  long long total = 0;
-  if (ser_off) {
-    for (size_t i = 0; i < n; i++) { ser_off[i] = total; total += words[i]; }
-    ser_off[n] = total;
-  } else for (size_t i = 0; i < n; i++) total += words[i];
-  if (keep && total <= ser_cap) {
-    th.clear();
-    auto copy = [&](size_t t) {
-      const size_t a = t * per;
-      if (a < n && !bufs[t].empty()) memcpy(ser + ser_off[a], bufs[t].data(), bufs[t].size() * sizeof(I));
-    };
-    if (nt == 1) copy(0);
-    else {
-      for (size_t t = 0; t < nt; t++) th.emplace_back(copy, t);
-      for (auto &x : th) x.join();
-    }
-  }
-  return total;
-}
 
 double wall()
 {
   struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
+
+struct DenseArgs {
+  long long n; int dr, dc; const I *dom; int has_ctx, cr, cc; const I *ctx; int bignum; PipOptions_dp opt;
+};
+
+/* one pipeline unit: problems [first, first + n) of a dense batch */
+struct DenseChunk {
+  size_t first = 0, n = 0;
+  std::vector<Shape> shapes;
+  std::vector<PipProblem> prob;
+  std::vector<size_t> off;
+  size_t pool_elems = 0;
+  int elem_log2 = 3;
+  PipBatchOut out;
+  std::vector<std::vector<I>> bufs;     /* serialised words, one buffer per worker range */
+  std::vector<long long> words;         /* per problem */
+  size_t per = 0;                       /* problems per worker range */
+};
+
+unsigned host_threads()
+{
+  unsigned hw = std::thread::hardware_concurrency();
+  return hw ? hw : 1;
+}
+
+template <class F>
+void parallel_ranges(size_t n, size_t nt, F f)
+{
+  nt = std::max<size_t>(1, std::min(nt, (n + 63) / 64));
+  const size_t per = (n + nt - 1) / nt;
+  if (nt == 1) { f(0, 0, n); return; }
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < nt; t++) {
+    size_t a = t * per, b = std::min(n, a + per);
+    if (a >= b) break;
+    th.emplace_back([=] { f(t, a, b); });
+  }
+  for (auto &x : th) x.join();
+}
+
+/* shapes + offsets + the narrowest element width that holds every tableau entry of the chunk */
+void plan_chunk(const DenseArgs &A, DenseChunk &C, size_t nthreads, bool allow_narrow)
+{
+  const size_t n = C.n;
+  C.shapes.resize(n);
+  C.prob.resize(n);
+  C.off.assign(n + 1, 0);
+  std::vector<I> maxabs(nthreads + 1, 0);
+  parallel_ranges(n, nthreads, [&](size_t t, size_t a, size_t b) {
+    I m = 0;
+    for (size_t i = a; i < b; i++) {
+      const size_t g = C.first + i;
+      MatView d = {A.dr, A.dc, nullptr, A.dom + g * A.dr * A.dc};
+      MatView c = {A.cr, A.cc, nullptr, A.has_ctx ? A.ctx + g * A.cr * A.cc : nullptr};
+      C.shapes[i] = derive_shape(d, A.has_ctx ? &c : nullptr, A.bignum, A.opt);
+      if (allow_narrow) {
+        const I *p = d.dense;
+        for (size_t k = 0, e = (size_t)A.dr * A.dc; k < e; k++) { I v = p[k] < 0 ? -p[k] : p[k]; if (v > m) m = v; }
+        if (A.has_ctx) {
+          p = c.dense;
+          for (size_t k = 0, e = (size_t)A.cr * A.cc; k < e; k++) { I v = p[k] < 0 ? -p[k] : p[k]; if (v > m) m = v; }
+        }
+      }
+    }
+    maxabs[t] = m;
+  });
+  for (size_t i = 0; i < n; i++) C.off[i + 1] = C.off[i] + problem_words(C.shapes[i]);
+  C.pool_elems = C.off[n];
+  C.elem_log2 = 3;
+  if (allow_narrow) {
+    I m = 0;
+    for (I v : maxabs) m = std::max(m, v);
+    /* the big-parameter column holds a sum of up to dc coefficients (source/tab.c:345-376) */
+    const I bound = m * (I)(A.dc + 1);
+    if (m >= 0 && bound < 127) C.elem_log2 = 0;
+    else if (m >= 0 && m < (1ll << 40) && bound < 2147483647ll) C.elem_log2 = 2;
+  }
+}
+
+template <class T>
+void convert_chunk_t(const DenseArgs &A, DenseChunk &C, T *pool, size_t nthreads)
+{
+  parallel_ranges(C.n, nthreads, [&](size_t, size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      const size_t g = C.first + i;
+      MatView d = {A.dr, A.dc, nullptr, A.dom + g * A.dr * A.dc};
+      MatView c = {A.cr, A.cc, nullptr, A.has_ctx ? A.ctx + g * A.cr * A.cc : nullptr};
+      fill_problem(d, A.has_ctx ? &c : nullptr, C.shapes[i], C.prob[i], pool, C.off[i]);
+    }
+  });
+}
+void convert_chunk(const DenseArgs &A, DenseChunk &C, void *pool, size_t nthreads)
+{
+  if (C.elem_log2 == 0) convert_chunk_t(A, C, (signed char *)pool, nthreads);
+  else if (C.elem_log2 == 2) convert_chunk_t(A, C, (int *)pool, nthreads);
+  else convert_chunk_t(A, C, (I *)pool, nthreads);
+}
+
+/* serialise every solved problem of the chunk straight from its cells: one pass per worker
+ * range into a private buffer, hash and length on the fly */
+void emit_chunk(const DenseArgs &A, DenseChunk &C, int *status, unsigned long long *hashes, bool keep, size_t nthreads)
+{
+  const size_t n = C.n;
+  C.words.assign(n, 0);
+  nthreads = std::max<size_t>(1, std::min(nthreads, (n + 63) / 64));
+  C.per = (n + nthreads - 1) / nthreads;
+  C.bufs.assign(nthreads, std::vector<I>());
+  const int simplify = A.opt.Simplify;
+  parallel_ranges(n, nthreads, [&](size_t t, size_t a, size_t b) {
+    std::vector<I> &buf = C.bufs[t];
+    size_t used = 0;
+    if (keep) {
+      size_t cells = 0;
+      for (size_t i = a; i < b; i++) cells += (size_t)C.out.res[i].ncells;
+      buf.resize(cells * 2 + (b - a) * 8 + 64);          /* >= the words any decode can produce */
+    }
+    for (size_t i = a; i < b; i++) {
+      const int st = C.out.res[i].status;
+      status[C.first + i] = st;
+      unsigned long long h = 0;
+      long long w = 0;
+      if (st == PIP_ST_OK || st == PIP_ST_VOID) {
+        Ser s = {keep ? buf.data() + used : nullptr, keep ? (long)(buf.size() - used) : 0, 0, 0xcbf29ce484222325ULL, true};
+        serialize_one(C.out, i, C.shapes[i], simplify, s);
+        h = s.h; w = s.len;
+        if (keep) used += (size_t)s.len;
+      }
+      if (hashes) hashes[C.first + i] = h;
+      C.words[i] = w;
+    }
+    if (keep) buf.resize(used);
+  });
+}
+
+void add_times(PipBatchOut &acc, const PipBatchOut &o)
+{
+  acc.times.h2d += o.times.h2d; acc.times.kernel += o.times.kernel; acc.times.d2h += o.times.d2h;
+  acc.times.device_ms += o.times.device_ms; acc.times.launches += o.times.launches; acc.times.rounds += o.times.rounds;
+  acc.times.h2d_bytes += o.times.h2d_bytes; acc.times.d2h_bytes += o.times.d2h_bytes;
+  for (int k = 0; k < PIP_NPHASE; k++) acc.times.phase_cycles[k] += o.times.phase_cycles[k];
+  acc.res.insert(acc.res.end(), o.res.begin(), o.res.end());
+}
+
 }  // namespace
+
+extern "C" {
+
+/* PIPLIB_B200_CHUNK / PIPLIB_B200_LANES tune the pipeline of the dense path */
+static size_t env_size(const char *name, size_t dflt)
+{
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  long long x = atoll(v);
+  return x > 0 ? (size_t)x : dflt;
+}
 
 int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long *dom,
                        int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
@@ -874,18 +931,68 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
 {
   if (n <= 0) return 0;
   try {
-    double t0 = wall();
-    DenseBatch B;
-    build_dense(B, n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum, options);
-    double t1 = wall();
-    PipBatchIn in;
-    in.n = (size_t)n; in.h_prob = B.prob.data(); in.h_pool = B.pool.data(); in.pool_words = B.pool_words;
-    PipBatchOut bo;
-    PipEngine::get().run(in, bo);
-    double t2 = wall();
-    long long total = emit_results(B, bo, status, hashes, ser, ser_cap, ser_off);
-    account(bo, (t1 - t0) + (wall() - t2));
-    if (ser && total > ser_cap) return -2;
+    const double t0 = wall();
+    DenseArgs A = {n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum,
+                   options ? *options : DEFAULT_OPTIONS};
+    const size_t CH = env_size("PIPLIB_B200_CHUNK", 1u << 16);
+    const size_t nchunks = ((size_t)n + CH - 1) / CH;
+    const size_t lanes = std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 2), PipEngine::MAX_LANES), nchunks);
+    const size_t nthreads = std::max<size_t>(1, host_threads());
+    const bool keep = ser != nullptr && ser_off != nullptr;
+    std::vector<DenseChunk> chunks(nchunks);
+    for (size_t c = 0; c < nchunks; c++) { chunks[c].first = c * CH; chunks[c].n = std::min(CH, (size_t)n - c * CH); }
+    std::vector<std::string> errors(lanes);
+    auto lane_main = [&](size_t lane) {
+      try {
+        PipEngine &E = PipEngine::lane((int)lane);
+        for (size_t c = lane; c < nchunks; c += lanes) {
+          DenseChunk &C = chunks[c];
+          plan_chunk(A, C, nthreads, true);
+          void *pool = E.pinned_input((C.pool_elems + 8) << C.elem_log2);
+          convert_chunk(A, C, pool, nthreads);
+          PipBatchIn in;
+          in.n = C.n; in.h_prob = C.prob.data(); in.h_pool = pool; in.pool_words = C.pool_elems;
+          in.elem_log2 = C.elem_log2;
+          E.run(in, C.out);
+          emit_chunk(A, C, status, hashes, keep, nthreads);
+          /* the cell chunks are engine-owned and reused by the next run on this lane: drop the views */
+          C.out.base.clear();
+        }
+      } catch (const std::exception &e) { errors[lane] = e.what(); }
+    };
+    if (lanes <= 1) lane_main(0);
+    else {
+      std::vector<std::thread> th;
+      for (size_t l = 0; l < lanes; l++) th.emplace_back(lane_main, l);
+      for (auto &x : th) x.join();
+    }
+    for (const std::string &e : errors) if (!e.empty()) throw std::runtime_error(e);
+    /* assemble */
+    long long total = 0;
+    for (size_t c = 0; c < nchunks; c++)
+      for (size_t i = 0; i < chunks[c].n; i++) {
+        if (ser_off) ser_off[chunks[c].first + i] = total;
+        total += chunks[c].words[i];
+      }
+    if (ser_off) ser_off[n] = total;
+    if (keep && total <= ser_cap) {
+      std::vector<std::thread> th;
+      for (size_t c = 0; c < nchunks; c++)
+        for (size_t t = 0; t < chunks[c].bufs.size(); t++) {
+          const size_t a = chunks[c].first + t * chunks[c].per;
+          if (a >= (size_t)n || chunks[c].bufs[t].empty()) continue;
+          const std::vector<I> *b = &chunks[c].bufs[t];
+          I *dst = ser + ser_off[a];
+          th.emplace_back([=] { memcpy(dst, b->data(), b->size() * sizeof(I)); });
+          if (th.size() >= nthreads) { for (auto &x : th) x.join(); th.clear(); }
+        }
+      for (auto &x : th) x.join();
+    }
+    PipBatchOut acc;
+    for (size_t c = 0; c < nchunks; c++) add_times(acc, chunks[c].out);
+    const double tt = wall() - t0;
+    account(acc, tt - acc.times.h2d - acc.times.kernel - acc.times.d2h);
+    if (keep && total > ser_cap) return -2;
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());
     return -1;
@@ -894,10 +1001,10 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
 }
 
 struct pip_device_batch {
-  DenseBatch B;
+  DenseArgs A;
+  DenseChunk C;
   PipProblem *d_prob = nullptr;
-  I *d_pool = nullptr;
-  PipBatchOut last;
+  void *d_pool = nullptr;
   bool fetched = false;
 };
 
@@ -907,12 +1014,18 @@ pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_col
 {
   try {
     pip_device_batch *b = new pip_device_batch;
-    build_dense(b->B, n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum, options);
-    PipEngine::get().sm_count();                      /* initialises the device */
+    b->A = {n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum, options ? *options : DEFAULT_OPTIONS};
+    b->C.first = 0; b->C.n = (size_t)n;
+    const size_t nthreads = host_threads();
+    plan_chunk(b->A, b->C, nthreads, true);
+    PipEngine &E = PipEngine::get();
+    void *pool = E.pinned_input((b->C.pool_elems + 8) << b->C.elem_log2);
+    convert_chunk(b->A, b->C, pool, nthreads);
     pip_cuda_check(cudaMalloc((void **)&b->d_prob, sizeof(PipProblem) * (size_t)n), "cudaMalloc(problems)");
-    pip_cuda_check(cudaMalloc((void **)&b->d_pool, sizeof(I) * (b->B.pool_words + 1)), "cudaMalloc(pool)");
-    pip_cuda_check(cudaMemcpy(b->d_prob, b->B.prob.data(), sizeof(PipProblem) * (size_t)n, cudaMemcpyHostToDevice), "H2D problems");
-    pip_cuda_check(cudaMemcpy(b->d_pool, b->B.pool.data(), sizeof(I) * b->B.pool_words, cudaMemcpyHostToDevice), "H2D pool");
+    pip_cuda_check(cudaMalloc(&b->d_pool, (b->C.pool_elems + 8) << b->C.elem_log2), "cudaMalloc(pool)");
+    pip_cuda_check(cudaMemcpy(b->d_prob, b->C.prob.data(), sizeof(PipProblem) * (size_t)n, cudaMemcpyHostToDevice), "H2D problems");
+    pip_cuda_check(cudaMemcpy(b->d_pool, pool, b->C.pool_elems << b->C.elem_log2, cudaMemcpyHostToDevice), "H2D pool");
+    b->A.dom = nullptr; b->A.ctx = nullptr;          /* the caller's arrays are not kept */
     return b;
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());
@@ -924,13 +1037,13 @@ int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
 {
   try {
     PipBatchIn in;
-    in.n = (size_t)b->B.n; in.h_prob = b->B.prob.data();
-    in.d_prob = b->d_prob; in.d_pool = b->d_pool;
+    in.n = b->C.n; in.h_prob = b->C.prob.data();
+    in.d_prob = b->d_prob; in.d_pool = b->d_pool; in.elem_log2 = b->C.elem_log2;
     in.fetch_cells = fetch_cells != 0;
-    PipEngine::get().run(in, b->last);
+    PipEngine::get().run(in, b->C.out);
     b->fetched = fetch_cells != 0;
-    if (device_ms) *device_ms = b->last.times.device_ms;
-    account(b->last, 0);
+    if (device_ms) *device_ms = b->C.out.times.device_ms;
+    account(b->C.out, 0);
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());
     return -1;
@@ -940,10 +1053,10 @@ int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
 
 int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long long *hashes)
 {
-  if (b->last.res.size() != (size_t)b->B.n) return -1;
+  if (b->C.out.res.size() != b->C.n) return -1;
   if (hashes && !b->fetched) return -3;
-  if (hashes) emit_results(b->B, b->last, status, hashes, nullptr, 0, nullptr);
-  else for (size_t i = 0; i < (size_t)b->B.n; i++) status[i] = b->last.res[i].status;
+  if (hashes) emit_chunk(b->A, b->C, status, hashes, false, host_threads());
+  else for (size_t i = 0; i < b->C.n; i++) status[i] = b->C.out.res[i].status;
   return 0;
 }
 

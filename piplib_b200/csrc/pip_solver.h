@@ -152,6 +152,25 @@ PIP_DEVNI void pip_copy2d(pip_i64 *dst, int dstride, const pip_i64 *src, int sst
   }
 }
 
+/* problem load: like pip_copy2d but the source elements are int8 / int32 / int64 (the host ships
+ * the narrowest width that holds the whole batch) */
+PIP_DEVNI void pip_load2d(pip_i64 *dst, int dstride, const void *src, int elem_log2, pip_i64 src_off, int rows, int cols)
+{
+  if (cols <= 0) return;
+  int r = 0, j = W::lane();
+  while (j >= cols) { j -= cols; r++; }
+  while (r < rows) {
+    const pip_i64 k = src_off + (pip_i64)r * cols + j;
+    pip_i64 v;
+    if (elem_log2 == 3) v = ((const pip_i64 *)src)[k];
+    else if (elem_log2 == 2) v = ((const int *)src)[k];
+    else v = ((const signed char *)src)[k];
+    dst[r * dstride + j] = v;
+    j += 32;
+    while (j >= cols) { j -= cols; r++; }
+  }
+}
+
 /* one term of the row "size" with a non-unit denominator: |(int)(double(v)/double(d))| or 0
  * when the conversion is out of range (source/traiter.c:580-584) */
 PIP_DEVNI unsigned pip_size_term(pip_i64 v, pip_i64 d)
@@ -539,7 +558,7 @@ PIP_DEV int pip_find_parm(const pip_i64 *ctx, int cstride, int nr, int nparm, pi
 
 /* The solver for one problem.  `B` is the warp's working arena (`words` words), `out` the
  * warp's cell window (at least sol_size cells free), `stk` the warp's frame stack. */
-PIP_DEV void pip_solve_one(const PipProblem &P, const pip_i64 *in, pip_i64 *B, int words, int slack_level,
+PIP_DEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, int words, int slack_level,
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
                            int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st)
@@ -574,8 +593,8 @@ PIP_DEV void pip_solve_one(const PipProblem &P, const pip_i64 *in, pip_i64 *B, i
       if (k < P.nvar) { fl[k] = PIP_MKFL(PIP_UNIT, k); den[k] = 1; }
       else { fl[k] = PIP_MKFL(PIP_UNKNOWN, k - P.nvar); den[k] = 1; }
     }
-    pip_copy2d(B + T.data, T.stride, in, ncol, P.ni, ncol);
-    pip_copy2d(ctx, cstride, in + (pip_i64)P.ni * ncol, P.nparm + 1, P.nc, P.nparm + 1);
+    pip_load2d(B + T.data, T.stride, pool, elem_log2, P.off, P.ni, ncol);
+    pip_load2d(ctx, cstride, pool, elem_log2, P.off + (pip_i64)P.ni * ncol, P.nc, P.nparm + 1);
     if (lane == 0) { B[L.m.det] = 1; B[L.s.det] = 1; }
     W::sync();
     if (integer) {

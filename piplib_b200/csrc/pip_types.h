@@ -86,7 +86,8 @@ typedef struct {
 /* launch parameters of the warp-per-problem kernels */
 typedef struct {
   const PipProblem *prob;
-  const pip_i64 *pool;
+  const void *pool;              /* input words, 1 << pool_elem_log2 bytes each (int8/int32/int64) */
+  int pool_elem_log2;
   const int *order;              /* optional permutation of problem indices (may be NULL) */
   int nprob;
   PipResult *res;

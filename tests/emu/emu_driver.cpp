@@ -22,7 +22,7 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
   EmuArgs e;
   unsigned queue[2] = {0, 0};
   memset(&e, 0, sizeof e);
-  e.L.prob = prob; e.L.pool = pool; e.L.order = 0; e.L.nprob = nprob; e.L.res = res;
+  e.L.prob = prob; e.L.pool = pool; e.L.pool_elem_log2 = 3; e.L.order = 0; e.L.nprob = nprob; e.L.res = res;
   e.L.cells = cells; e.L.cells_per_warp = cells_cap;
   e.L.stack = (pip_i64 *)malloc(sizeof(pip_i64) * stack_words);
   e.L.stack_words_per_warp = stack_words;
