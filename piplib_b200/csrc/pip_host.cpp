@@ -840,7 +840,7 @@ void plan_chunk(const DenseArgs &A, DenseChunk &C, size_t nthreads, bool allow_n
     I m = 0;
     for (I v : maxabs) m = std::max(m, v);
     /* the big-parameter column holds a sum of up to dc coefficients (source/tab.c:345-376) */
-    const I bound = m * (I)(A.dc + 1);
+    const I bound = (A.opt.Maximize || A.opt.Urs_unknowns) ? m * (I)(A.dc + 1) : m;
     if (m >= 0 && bound < 127) C.elem_log2 = 0;
     else if (m >= 0 && m < (1ll << 40) && bound < 2147483647ll) C.elem_log2 = 2;
   }

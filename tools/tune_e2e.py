@@ -1,0 +1,24 @@
+"""GPU tuning aid: e2e throughput of pip_solve_dense_dp for several chunk / lane settings."""
+import os
+import sys
+import time
+
+sys.path.insert(0, ".")
+from piplib_b200 import api, synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
+dom, ctx = synth.generate("loopnest16x24p3", n)
+for chunk, lanes in [(65536, 1), (65536, 2), (65536, 3), (32768, 3), (131072, 2), (131072, 3), (32768, 4)]:
+    os.environ["PIPLIB_B200_CHUNK"] = str(chunk)
+    os.environ["PIPLIB_B200_LANES"] = str(lanes)
+    best = 1e9
+    for it in range(4):
+        t = time.perf_counter()
+        api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+        dt = time.perf_counter() - t
+        if it:
+            best = min(best, dt)
+    s = api.last_stats()
+    print("chunk %6d lanes %d: %.3f s -> %.0f problems/s (kernel %.3f h2d %.3f d2h %.3f host %.3f; h2d %.0f MB d2h %.0f MB)"
+          % (chunk, lanes, best, n / best, s.seconds_kernel, s.seconds_h2d, s.seconds_d2h, s.seconds_host,
+             s.h2d_bytes / 1e6, s.d2h_bytes / 1e6), flush=True)
