@@ -124,6 +124,7 @@ PIP_DEV pip_i64 *pip_row(pip_i64 *B, const PipTab &T, int slot) { return B + T.d
 PIP_DEVNI int pip_first_flag_impl(const int *fl, int mask, int from, int n)
 {
   const int lane = W::lane();
+  #pragma unroll 1
   for (int base = from & ~31; base < n; base += 32) {
     int k = base + lane;
     bool p = (k >= from && k < n) && ((fl[k] & mask) != 0);
@@ -185,15 +186,18 @@ PIP_DEVNI unsigned pip_size_term(pip_i64 v, pip_i64 d)
 PIP_DEVNI bool pip_simplify_rows(pip_i64 *base, int rows, int stride, int width, int cst)
 {
   bool fault = false;
+  #pragma unroll 1
   for (int r = W::lane(); r < rows; r += 32) {
     pip_i64 *row = base + r * stride;
     pip_i64 g = 0;
+    #pragma unroll 1
     for (int j = 0; j < width; j++) {
       if (j == cst) continue;
       g = pip_gcd(g, row[j]);
       if (g == 1) break;
     }
     if (g == 0 || g == 1) continue;
+    #pragma unroll 1
     for (int j = 0; j < width; j++)
       row[j] = (j == cst) ? pip_floor_q(row[j], g) : pip_div(row[j], g);
   }
@@ -211,6 +215,7 @@ PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
   pip_i64 *den = pip_den(B, T);
   float *sz = (float *)(B + tmpoff);
   unsigned smax_u = 0;
+  #pragma unroll 1
   for (int k = T.nvar + lane; k < nl; k += 32) {
     int f = fl[k];
     if (f & PIP_UNIT) continue;
@@ -218,11 +223,13 @@ PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
     pip_i64 d = den[k];
     unsigned s = 0;
     if (d == 1) {
+      #pragma unroll 1
       for (int j = 0; j < T.nvar; j++) {
         pip_u64 u = pip_uabs(row[j]);
         if (u < 2147483648ull && (unsigned)u > s) s = (unsigned)u;
       }
     } else {
+      #pragma unroll 1
       for (int j = 0; j < T.nvar; j++) {
         unsigned v = pip_size_term(row[j], d);
         if (v > s) s = v;
@@ -234,10 +241,55 @@ PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
   smax_u = W::redmax(smax_u);
   const double smax = (double)smax_u;
   W::sync();
+  if (T.ni <= 32) {
+    /* register-resident selection sort: lane r holds the record of position nvar + r; a swap
+     * is a pair of shuffles, no shared-memory traffic and no barriers */
+    const int k = T.nvar + lane;
+    const bool in = lane < T.ni;
+    int f = in ? fl[k] : PIP_UNIT;
+    pip_i64 d = in ? den[k] : 0;
+    unsigned sb = in ? pip_f2u(sz[k]) : 0u;
+    const bool movable = in && !(f & PIP_UNIT);
+    /* nothing moves when the movable rows are already in non-decreasing order */
+    {
+      unsigned pm = movable ? sb : 0u;                    /* inclusive prefix max over movable rows */
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = (unsigned)W::shfl_up((int)pm, o);
+        if (lane >= o && y > pm) pm = y;
+      }
+      unsigned before = (unsigned)W::shfl_up((int)pm, 1);
+      if (lane == 0) before = 0u;
+      if (!W::any(movable && sb < before)) return;
+    }
+    bool moved = false;
+    #pragma unroll 1
+    for (int r = 0; r < T.ni; r++) {
+      const bool unit_r = (W::shfl(f, r) & PIP_UNIT) != 0;
+      if (unit_r) continue;
+      unsigned key = 0xffffffffu;
+      if (movable && lane >= r && (double)pip_u2f(sb) < smax) key = sb;
+      const unsigned m = W::redmin(key);
+      if (m == 0xffffffffu) break;                         /* no candidate left for any later r */
+      const int src = pip_ffs(W::ballot(key == m)) - 1;
+      if (src != r) {
+        const int partner = lane == r ? src : lane == src ? r : lane;
+        f = W::shfl(f, partner);
+        d = W::shfl64(d, partner);
+        sb = (unsigned)W::shfl((int)sb, partner);
+        moved = true;
+      }
+    }
+    if (moved && in) { fl[k] = f; den[k] = d; }
+    W::sync();
+    return;
+  }
+  #pragma unroll 1
   for (int i = T.nvar; i < nl; i++) {
     if (fl[i] & PIP_UNIT) continue;            /* uniform read */
     unsigned best = 0xffffffffu;
     int bestk = i;
+    #pragma unroll 1
     for (int base = i & ~31; base < nl; base += 32) {
       int k = base + lane;
       unsigned key = 0xffffffffu;
@@ -271,6 +323,7 @@ PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
   const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
   int *fl = pip_fl(B, T);
   if (bigparm >= 0) {
+    #pragma unroll 1
     for (int base = 0; base < nl; base += 32) {
       int k = base + lane;
       int f = k < nl ? fl[k] : 0;
@@ -287,6 +340,7 @@ PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
     }
     W::sync();
   }
+  #pragma unroll 1
   for (int base = 0; base < nl; base += 32) {
     int k = base + lane;
     int f = k < nl ? fl[k] : 0;
@@ -294,6 +348,7 @@ PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
     int ff = PIP_ZERO;
     if (unk) {
       const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+      #pragma unroll 1
       for (int j = T.nvar + 1; j < ncol; j++) {
         pip_i64 v = row[j];
         int fff = v < 0 ? PIP_MINUS : v > 0 ? PIP_PLUS : PIP_ZERO;
@@ -336,6 +391,7 @@ PIP_DEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, pip_i64 &pi
   const pip_i64 *prow = pip_row(B, T, PIP_LINK(fl[pivi]));
   int pivj = -1;
   pip_i64 pivot = 0;
+  #pragma unroll 1
   for (int cb = 0; cb < T.nvar; cb += 32) {
     int jc = cb + lane;
     unsigned cand = W::ballot(jc < T.nvar && prow[jc] > 0);
@@ -345,6 +401,7 @@ PIP_DEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, pip_i64 &pi
       pip_i64 foo = prow[j];
       if (pivj < 0) { pivj = j; pivot = foo; continue; }
       bool neg = false;
+      #pragma unroll 1
       for (int base = 0; base < nl; base += 32) {
         int k = base + lane;
         pip_i64 x = 0;
@@ -399,7 +456,9 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
     pip_i64 ppivot = pip_div(pivot, d), dppiv = pip_div(dpiv, d);
     pip_i64 *det = B + T.det;
     pip_i64 dv[PIP_MAX_DET];
+    #pragma unroll 1
     for (int i = 0; i < PIP_MAX_DET; i++) dv[i] = i < T.ldet ? det[i] : 0;
+    #pragma unroll 1
     for (int i = 0; i < PIP_MAX_DET; i++) {
       if (i >= T.ldet) break;
       pip_i64 g = pip_gcd(dv[i], dppiv);
@@ -410,6 +469,7 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
     if (dppiv != 1) return PIP_ST_FATAL + 1;            /* "Integer overflow" */
     int i = 0;
     const int bp = pip_bitlen(ppivot);
+    #pragma unroll 1
     for (; i < T.ldet; i++)
       if (pip_bitlen(dv[i]) + bp < 64) { dv[i] = (pip_i64)((pip_u64)dv[i] * (pip_u64)ppivot); break; }
     if (i >= T.ldet) {
@@ -425,43 +485,70 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
   if ((unsigned)ncol > st.max_cols) st.max_cols = ncol;
   st.elem_updates += (unsigned long long)(T.ni - 1) * ncol;
 
-  /* rank-1 update of every stored row but the pivot row, source/traiter.c:467-502 */
+  /* rank-1 update of every stored row but the pivot row (source/traiter.c:467-502), fused with
+   * the re-flagging from the sign of the new pivot-column entry (source/traiter.c:518-529) */
   bool fault = false;
+  #pragma unroll 1
   for (int k = lane; k < nl; k += 32) {
     if (k == pivi) continue;
-    int f = fl[k];
+    const int f = fl[k];
     if (f & PIP_UNIT) continue;
     pip_i64 *row = pip_row(B, T, PIP_LINK(f));
     pip_i64 foo = row[pivj];
     const pip_i64 dk = den[k];
-    if (foo == 0 && dk == 1) continue;        /* the update is the identity and g stays 1 */
+    if (foo == 0 && dk == 1) continue;        /* identity update, g stays 1, sign Zero: no re-flag */
     pip_i64 lpiv = pivot;
     if (foo == 0) lpiv = 1;                    /* gcd(pivot,0) = pivot */
-    else {
+    else if (pivot != 1 && foo != 1 && foo != -1) {
       pip_i64 d = pip_gcd(pivot, foo);
       if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
     }
-    pip_i64 g = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
-    const pip_i64 newden = g;
+    const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
+    pip_i64 g = newden;
+    /* a power-of-two g folds into one OR: gcd(2^a, z_0..z_n) = lowest set bit of (2^a | z_0 | .. | z_n) */
+    const bool pow2 = g > 1 && (g & (g - 1)) == 0;
+    pip_u64 orz = 0;
+    pip_i64 zp = 0;
+    #pragma unroll 2
     for (int j = 0; j < ncol; j++) {
       pip_i64 z;
-      if (j == pivj) z = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
+      if (j == pivj) { z = (pip_i64)((pip_u64)dpiv * (pip_u64)foo); zp = z; }
       else z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
       row[j] = z;
-      if (g != 1) g = pip_gcd(g, z);
+      if (pow2) orz |= (pip_u64)z;
+      else if (g != 1) g = pip_gcd(g, z);
     }
+    if (pow2) { orz |= (pip_u64)g; g = (pip_i64)(orz & (0ull - orz)); }
     if (g != 1) {
       if (g == 0) { fault = true; continue; }
-      PipExactDiv e = pip_exact_prepare(g);
-      for (int j = 0; j < ncol; j++) row[j] = pip_exact_apply(row[j], e);
-      den[k] = pip_exact_apply(newden, e);
+      if ((g & (g - 1)) == 0) {
+        int sh = 0;
+        while (((pip_u64)g >> sh) != 1ull) sh++;
+        #pragma unroll 2
+        for (int j = 0; j < ncol; j++) row[j] = row[j] >> sh;
+        den[k] = newden >> sh;
+      } else {
+        PipExactDiv e = pip_exact_prepare(g);
+        #pragma unroll 2
+        for (int j = 0; j < ncol; j++) row[j] = pip_exact_apply(row[j], e);
+        den[k] = pip_exact_apply(newden, e);
+      }
     } else den[k] = newden;
+    /* sign of the new entry in column pivj = sign of zp (g > 0) */
+    int ff = PIP_FLAG(f);
+    const int fff = zp < 0 ? PIP_MINUS : zp == 0 ? PIP_ZERO : PIP_PLUS;
+    if (fff != PIP_ZERO && fff != ff) {
+      if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
+      else ff = PIP_UNKNOWN;
+      fl[k] = PIP_MKFL(ff, PIP_LINK(f));
+    }
   }
   if (W::any(fault)) return PIP_ST_FAULT;
   W::sync();
   PIP_LAP(st, PIP_PH_UPDATE);
   /* the Unit position owning pivj takes the pivot row's slot, source/traiter.c:503-516 */
   int ku = nl;
+  #pragma unroll 1
   for (int base = 0; base < nl; base += 32) {
     int k = base + lane;
     int f = k < nl ? fl[k] : 0;
@@ -469,6 +556,7 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
     if (m) { ku = base + pip_ffs(m) - 1; break; }
   }
   if (ku >= nl) return PIP_ST_FAULT;
+  #pragma unroll 1
   for (int j = lane; j < ncol; j += 32) prow[j] = (j == pivj) ? dpiv : -prow[j];
   W::sync();
   if (lane == 0) {
@@ -476,20 +564,8 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
     fl[pivi] = PIP_MKFL(PIP_UNIT | PIP_ZERO, pivj); den[pivi] = 1;
   }
   W::sync();
-  /* re-flag from the sign of the pivot-column entry, source/traiter.c:518-529 */
-  for (int k = lane; k < nl; k += 32) {
-    int f = fl[k];
-    if (f & PIP_UNIT) continue;
-    int ff = PIP_FLAG(f);
-    pip_i64 v = pip_row(B, T, PIP_LINK(f))[pivj];
-    int fff = v < 0 ? PIP_MINUS : v == 0 ? PIP_ZERO : PIP_PLUS;
-    if (fff != PIP_ZERO && fff != ff) {
-      if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
-      else ff = PIP_UNKNOWN;
-      fl[k] = PIP_MKFL(ff, PIP_LINK(f));
-    }
-  }
-  W::sync();
+  /* (the new row at ku keeps Plus: its pivot-column entry is dpiv > 0; every other row was
+   * re-flagged inside the update loop) */
   PIP_LAP(st, PIP_PH_SWAP);
   return 0;
 }
@@ -508,6 +584,7 @@ PIP_DEVNI bool pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int 
   const int per = T.nparm + 2, total = 1 + T.nvar * per;
   const int *fl = pip_fl(B, T);
   const pip_i64 *den = pip_den(B, T);
+  #pragma unroll 1
   for (int c = W::lane(); c < total; c += 32) {
     if (c == 0) { pip_put(out, at, PIP_C_LIST, T.nvar, 0); continue; }
     int i = (c - 1) / per, r = (c - 1) % per;
@@ -523,13 +600,16 @@ PIP_DEVNI bool pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int 
 /* has_cut_xx, source/integrer.c:230-254 (serial, one lane) */
 PIP_DEV bool pip_has_cut(const pip_i64 *ctx, int cstride, int nr, int nparm, int p, const pip_i64 *cut)
 {
+  #pragma unroll 1
   for (int row = 0; row < nr; row++) {
     const pip_i64 *r = ctx + row * cstride;
     if (r[p] != cut[1 + nparm]) continue;
     if (r[nparm] != cut[0]) continue;
     int col;
+    #pragma unroll 1
     for (col = p + 1; col < nparm; col++) if (r[col] != 0) break;
     if (col < nparm) continue;
+    #pragma unroll 1
     for (col = 0; col < p; col++) if (r[col] != cut[1 + col]) break;
     if (col < p) continue;
     return true;
@@ -542,12 +622,15 @@ PIP_DEV int pip_find_parm(const pip_i64 *ctx, int cstride, int nr, int nparm, pi
 {
   if (cut[1 + nparm - 1] != 0) return -1;
   cut[0] = cut[0] + cut[1 + nparm] - 1;
+  #pragma unroll 1
   for (int p = nparm - 1; p >= 0; p--) {
     if (cut[1 + p] != 0) break;
     if (!pip_has_cut(ctx, cstride, nr, nparm, p, cut)) continue;
     cut[0] = cut[0] + 1 - cut[1 + nparm];
+    #pragma unroll 1
     for (int c = 0; c < nparm + 2; c++) cut[c] = -cut[c];
     bool found = pip_has_cut(ctx, cstride, nr, nparm, p, cut);
+    #pragma unroll 1
     for (int c = 0; c < nparm + 2; c++) cut[c] = -cut[c];
     if (found) return p;
     cut[0] = cut[0] + cut[1 + nparm] - 1;
@@ -589,6 +672,7 @@ PIP_DEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2,
     const int ncol = P.nvar + P.nparm + 1;
     int *fl = pip_fl(B, T);
     pip_i64 *den = pip_den(B, T);
+    #pragma unroll 1
     for (int k = lane; k < P.nvar + P.ni; k += 32) {
       if (k < P.nvar) { fl[k] = PIP_MKFL(PIP_UNIT, k); den[k] = 1; }
       else { fl[k] = PIP_MKFL(PIP_UNKNOWN, k - P.nvar); den[k] = 1; }
@@ -621,6 +705,7 @@ BUILD_SUB:
     if (np + nc + extra > S.pcap || nc + extra > S.rcap || np + 1 > S.stride) { status = PIP_ST_CAPACITY; goto DONE; }
     int *sfl = pip_fl(B, S);
     pip_i64 *sden = pip_den(B, S);
+    #pragma unroll 1
     for (int k = lane; k < np + nc + extra; k += 32) {
       sfl[k] = k < np ? PIP_MKFL(PIP_UNIT, k) : PIP_MKFL(PIP_UNKNOWN, k - np);
       sden[k] = 1;
@@ -630,6 +715,7 @@ BUILD_SUB:
       const int f = pip_fl(B, M)[ci];
       const pip_i64 *row = pip_row(B, M, PIP_LINK(f));
       pip_i64 *nr = pip_row(B, S, nc);
+      #pragma unroll 1
       for (int j = lane; j <= np; j += 32) {
         pip_i64 v = (j < np) ? row[M.nvar + 1 + j] : row[M.nvar];
         if (ret_site == 1) { if (j == np && !critic) v -= 1; }
@@ -671,6 +757,7 @@ COMPA_NEXT:
     if (ci >= nl) goto AFTER_COMPA;
     const pip_i64 *row = pip_row(B, T, PIP_LINK(pip_fl(B, T)[ci]));
     bool pos = false;
+    #pragma unroll 1
     for (int j = lane; j < T.nvar; j += 32) pos = pos || row[j] > 0;
     critic = W::any(pos) ? 0 : 1;
     ret_site = 1;
@@ -724,10 +811,12 @@ AFTER_COMPA:
     int *fl = pip_fl(B, T);
     const pip_i64 *row = pip_row(B, T, PIP_LINK(fl[pivi]));
     pip_i64 g = 0;
+    #pragma unroll 1
     for (int j = 0; j < np; j++) g = pip_gcd(g, row[T.nvar + 1 + j]);
     if (!integer) g = pip_gcd(g, row[T.nvar]);
     if (g == 0) { status = PIP_ST_FAULT; goto DONE; }
     pip_i64 *crow = ctx + nc * cstride;
+    #pragma unroll 1
     for (int j = lane; j <= np; j += 32) {
       pip_i64 v;
       if (j < np) v = pip_div(row[T.nvar + 1 + j], g);
@@ -748,14 +837,17 @@ AFTER_COMPA:
       pip_i64 *F = stk + top;
       if (lane == 0) {
         F[0] = T.nvar; F[1] = np; F[2] = T.ni; F[3] = nc; F[4] = pivi; F[5] = T.ldet;
+        #pragma unroll 1
         for (int k = 0; k < PIP_MAX_DET; k++) F[8 + k] = B[T.det + k];
         F[fsize - 1] = fsize;
       }
       pip_i64 *q = F + 12;
       const pip_i64 *den = pip_den(B, T);
+      #pragma unroll 1
       for (int k = lane; k < nl; k += 32) q[k] = den[k];
       q += nl;
       int *qi = (int *)q;
+      #pragma unroll 1
       for (int k = lane; k < nl; k += 32) qi[k] = fl[k];
       q += (nl + 1) / 2;
       pip_copy2d(q, ncol, B + T.data, T.stride, T.ni, ncol);
@@ -788,6 +880,7 @@ NONNEG:
     int *fl = pip_fl(B, T);
     pip_i64 *den = pip_den(B, T);
     int verdict = 0;     /* 0 integral, -1 none, >0 cut row */
+    #pragma unroll 1
     for (int i = 0; i < nvar; i++) {
       const pip_i64 D = den[i];
       const int f = fl[i];
@@ -797,6 +890,7 @@ NONNEG:
       const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
       bool okv = false, okc = false, okp = false;
       W::sync();
+      #pragma unroll 1
       for (int j = lane; j < ncol; j += 32) {
         pip_i64 v = row[j], x;
         if (j < nvar) { x = pip_mod(v, D); okv = okv || x > 0; }
@@ -825,16 +919,20 @@ NONNEG:
             pip_put(out, ncell, PIP_C_NEW, np, 0);
             pip_put(out, ncell + 1, PIP_C_DIV, 0, 0);
             pip_put(out, ncell + 2, PIP_C_FORM, np + 1, 0);
+            #pragma unroll 1
             for (int j = 0; j < np; j++) wide = pip_put(out, ncell + 3 + j, PIP_C_VAL, -c[1 + j], 1) || wide;
             wide = pip_put(out, ncell + 3 + np, PIP_C_VAL, -c[0], 1) || wide;
             wide = pip_put(out, ncell + 4 + np, PIP_C_VAL, c[1 + np], 1) || wide;
+            #pragma unroll 1
             for (int k = 0; k < nc; k++) { pip_i64 *r = ctx + k * cstride; r[np + 1] = r[np]; r[np] = 0; }
             pip_i64 *r0 = ctx + nc * cstride, *r1 = r0 + cstride;
+            #pragma unroll 1
             for (int j = 0; j < np; j++) { r0[j] = -c[1 + j]; r1[j] = c[1 + j]; }
             r0[np] = -c[1 + np]; r1[np] = c[1 + np];
             r0[np + 1] = -c[0]; r1[np + 1] = c[0] - 1 + c[1 + np];
           }
           /* the new parameter's tableau column starts at zero in every stored row */
+          #pragma unroll 1
           for (int r = lane; r < T.ni; r += 32) pip_row(B, T, r)[ncol] = 0;
           ncell += np + 5;
           parm = np;
@@ -846,6 +944,7 @@ NONNEG:
       }
       {
         pip_i64 *nr = pip_row(B, T, T.ni);
+        #pragma unroll 1
         for (int j = lane; j < ncol; j += 32) nr[j] = cut[j];
         W::sync();
         if (lane == 0) {
@@ -906,15 +1005,18 @@ LEAF:
     pip_i64 *den = pip_den(B, T);
     if (lane == 0) for (int k = 0; k < PIP_MAX_DET; k++) B[T.det + k] = F[8 + k];
     const pip_i64 *q = F + 12;
+    #pragma unroll 1
     for (int k = lane; k < nl; k += 32) den[k] = q[k];
     q += nl;
     const int *qi = (const int *)q;
+    #pragma unroll 1
     for (int k = lane; k < nl; k += 32) fl[k] = qi[k];
     q += (nl + 1) / 2;
     pip_copy2d(B + T.data, T.stride, q, ncol, T.ni, ncol);
     q += (pip_i64)T.ni * ncol;
     pip_copy2d(ctx, cstride, q, np + 1, nc + 1, np + 1);
     W::sync();
+    #pragma unroll 1
     for (int j = lane; j <= np; j += 32) {                 /* the negated condition */
       pip_i64 v = ctx[nc * cstride + j];
       ctx[nc * cstride + j] = (j < np) ? -v : -(v + 1);

@@ -34,6 +34,7 @@ struct W {
   static inline bool any(bool p) { return pipemu::ballot(p) != 0; }
   static inline int shfl(int v, int src) { return (int)pipemu::shfl64(v, src); }
   static inline long long shfl64(long long v, int src) { return pipemu::shfl64(v, src); }
+  static inline int shfl_up(int v, int d) { int l = pipemu::lane(); int r = (int)pipemu::shfl64(v, l >= d ? l - d : l); return r; }
   static inline unsigned redmin(unsigned v) { return pipemu::redmin(v); }
   static inline unsigned redmax(unsigned v) { return pipemu::redmax(v); }
   static inline unsigned atomic_add(unsigned *p, unsigned v) { return pipemu::atomic_add(p, v); }
@@ -46,6 +47,7 @@ static inline int pip_ctzll(unsigned long long v) { return v ? __builtin_ctzll(v
 static inline long long pip_mulhi(long long a, long long b) { return (long long)(((__int128)a * b) >> 64); }
 static inline double pip_ll2d(long long v) { return (double)v; }
 static inline unsigned pip_f2u(float f) { unsigned u; __builtin_memcpy(&u, &f, 4); return u; }
+static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
 
 #else  /* device */
 
@@ -62,6 +64,7 @@ struct W {
   static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
   static __device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
   static __device__ __forceinline__ long long shfl64(long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  static __device__ __forceinline__ int shfl_up(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
   static __device__ __forceinline__ unsigned redmin(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
   static __device__ __forceinline__ unsigned redmax(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
   static __device__ __forceinline__ unsigned atomic_add(unsigned *p, unsigned v) { return atomicAdd(p, v); }
@@ -74,6 +77,7 @@ static __device__ __forceinline__ int pip_ctzll(unsigned long long v) { return v
 static __device__ __forceinline__ long long pip_mulhi(long long a, long long b) { return __mul64hi(a, b); }
 static __device__ __forceinline__ double pip_ll2d(long long v) { return __ll2double_rn(v); }
 static __device__ __forceinline__ unsigned pip_f2u(float f) { return __float_as_uint(f); }
+static __device__ __forceinline__ float pip_u2f(unsigned u) { return __uint_as_float(u); }
 
 #endif
 
