@@ -372,6 +372,56 @@ PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
   return nl;
 }
 
+/* chercher(Minus) + exam_coef for a tableau of at most 32 positions: one register-resident pass
+ * (source/traiter.c:669-680); returns the pivot row or nl */
+PIP_DEV int pip_scan32(pip_i64 *B, const PipTab &T, int bigparm)
+{
+  const int lane = W::lane();
+  const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
+  int *fl = pip_fl(B, T);
+  int f = lane < nl ? fl[lane] : 0;
+  unsigned m = W::ballot((f & PIP_MINUS) != 0);
+  if (m) return pip_ffs(m) - 1;
+  const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+  bool dirty = false;
+  if (bigparm >= 0) {
+    const bool unk = PIP_FLAG(f) == PIP_UNKNOWN;
+    const pip_i64 v = unk ? row[bigparm] : 0;
+    m = W::ballot(unk && v < 0);
+    const int first = m ? pip_ffs(m) - 1 : 32;
+    if (unk && v > 0 && lane < first) { f = PIP_MKFL(PIP_PLUS, PIP_LINK(f)); fl[lane] = f; }
+    if (m) {
+      if (lane == first) fl[lane] = PIP_MKFL(PIP_MINUS, PIP_LINK(f));
+      W::sync();
+      return first;
+    }
+  }
+  const bool unk = PIP_FLAG(f) == PIP_UNKNOWN;
+  int ff = PIP_ZERO;
+  if (unk) {
+    #pragma unroll 1
+    for (int j = T.nvar + 1; j < ncol; j++) {
+      const pip_i64 v = row[j];
+      const int fff = v < 0 ? PIP_MINUS : v > 0 ? PIP_PLUS : PIP_ZERO;
+      if (fff != PIP_ZERO && fff != ff) {
+        if (ff == PIP_ZERO) ff = fff;
+        else { ff = PIP_UNKNOWN; break; }
+      }
+    }
+    const pip_i64 c = row[T.nvar];
+    const int fff = c < 0 ? PIP_MINUS : c > 0 ? PIP_PLUS : PIP_ZERO;
+    if (ff == PIP_PLUS) { if (fff == PIP_MINUS) ff = PIP_UNKNOWN; }
+    else if (ff == PIP_ZERO) ff = fff;
+    else if (ff == PIP_MINUS) { if (fff != PIP_MINUS) ff = PIP_UNKNOWN; }
+    dirty = true;
+  }
+  m = W::ballot(unk && ff == PIP_MINUS);
+  const int first = m ? pip_ffs(m) - 1 : 32;
+  if (dirty && lane <= first) fl[lane] = PIP_MKFL(ff, PIP_LINK(f));
+  W::sync();
+  return m ? first : nl;
+}
+
 /* valeur_xx, source/traiter.c:246-252 */
 PIP_DEV pip_i64 pip_entry(pip_i64 *B, const PipTab &T, int f, pip_i64 d, int j)
 {
@@ -505,20 +555,27 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
     }
     const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
     pip_i64 g = newden;
-    /* a power-of-two g folds into one OR: gcd(2^a, z_0..z_n) = lowest set bit of (2^a | z_0 | .. | z_n) */
-    const bool pow2 = g > 1 && (g & (g - 1)) == 0;
+    /* pass 1: pure arithmetic.  The generic formula gives 0 in column pivj (foo*lpiv == pivot*foo'),
+     * the real value dpiv*foo' is patched in afterwards, so the loop body has no special case */
     pip_u64 orz = 0;
-    pip_i64 zp = 0;
-    #pragma unroll 2
+    #pragma unroll 4
     for (int j = 0; j < ncol; j++) {
-      pip_i64 z;
-      if (j == pivj) { z = (pip_i64)((pip_u64)dpiv * (pip_u64)foo); zp = z; }
-      else z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
+      const pip_i64 z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
       row[j] = z;
-      if (pow2) orz |= (pip_u64)z;
-      else if (g != 1) g = pip_gcd(g, z);
+      orz |= (pip_u64)z;
     }
-    if (pow2) { orz |= (pip_u64)g; g = (pip_i64)(orz & (0ull - orz)); }
+    const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
+    row[pivj] = zp;
+    orz |= (pip_u64)zp;
+    /* pass 2 (only when the row has a common factor to shed): g = gcd(newden, z_0 .. z_n).
+     * A power-of-two g folds into the OR: gcd(2^a, z..) = lowest set bit of (2^a | z_0 | ..) */
+    if (g != 1) {
+      if ((g & (g - 1)) == 0 && g > 0) { orz |= (pip_u64)g; g = (pip_i64)(orz & (0ull - orz)); }
+      else {
+        #pragma unroll 1
+        for (int j = 0; j < ncol && g != 1; j++) g = pip_gcd(g, row[j]);
+      }
+    }
     if (g != 1) {
       if (g == 0) { fault = true; continue; }
       if ((g & (g - 1)) == 0) {
@@ -739,9 +796,11 @@ ENTRY:
 LOOP:
   {
     const int nl = T.nvar + T.ni;
-    pivi = pip_first_flag(B, T, PIP_MINUS, 0, nl);
-    if (pivi < nl) { PIP_LAP(st, PIP_PH_SCAN); goto PIVOT; }
-    pivi = pip_exam_coef(B, T, level ? -1 : P.bigparm);
+    if (nl <= 32) pivi = pip_scan32(B, T, level ? -1 : P.bigparm);
+    else {
+      pivi = pip_first_flag(B, T, PIP_MINUS, 0, nl);
+      if (pivi >= nl) pivi = pip_exam_coef(B, T, level ? -1 : P.bigparm);
+    }
     PIP_LAP(st, PIP_PH_SCAN);
     if (pivi < nl) goto PIVOT;
     if (T.nparm == 0) goto NONNEG;
