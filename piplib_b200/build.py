@@ -34,30 +34,35 @@ def _stale(lib=None):
     return os.path.getmtime(os.path.abspath(__file__)) > t
 
 
-def build(force=False, verbose=False, profile=False):
-    """profile=True builds libpiplib_dp_prof.so with per-phase clock64 accounting compiled in."""
+def build(force=False, verbose=False, profile=False, variant=None, defines=()):
+    """profile=True builds libpiplib_dp_prof.so with per-phase clock64 accounting compiled in;
+    variant="x" + defines builds an experimental libpiplib_dp_x.so (tuning only)."""
     global LIB
     lib = os.path.join(LIBDIR, "libpiplib_dp_prof.so") if profile else LIB
+    if variant:
+        lib = os.path.join(LIBDIR, "libpiplib_dp_%s.so" % variant)
     if not force and not _stale(lib):
         return lib
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
-    extra = ["-DPIP_PROFILE"] if profile else []
+    extra = (["-DPIP_PROFILE"] if profile else []) + ["-D" + d for d in defines]
+    if variant:
+        profile = variant          # distinct object / log names
     inc = ["-I", os.path.join(HERE, "..", "include"), "-I", CSRC]
     for f in SOURCES_CU:
         o = os.path.join(LIBDIR, f + ".o")
-        o = os.path.join(LIBDIR, f + (".prof" if profile else "") + ".o")
+        o = os.path.join(LIBDIR, f + (".%s" % profile if profile else "") + ".o")
         cmd = [NVCC] + NVCC_FLAGS + extra + inc + ["-c", os.path.join(CSRC, f), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError("nvcc failed on " + f)
-        with open(os.path.join(LIBDIR, f + (".prof" if profile else "") + ".ptxas.txt"), "w") as fh:
+        with open(os.path.join(LIBDIR, f + (".%s" % profile if profile else "") + ".ptxas.txt"), "w") as fh:
             fh.write(r.stdout + r.stderr)
         objs.append(o)
     for f in SOURCES_CPP:
-        o = os.path.join(LIBDIR, f + (".prof" if profile else "") + ".o")
+        o = os.path.join(LIBDIR, f + (".%s" % profile if profile else "") + ".o")
         cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-fwrapv", "-Wall", "-pthread"] + extra + [
                "-I", os.path.join(CUDA, "include")] + inc + ["-c", os.path.join(CSRC, f), "-o", o]
         subprocess.check_call(cmd)
@@ -71,4 +76,11 @@ def build(force=False, verbose=False, profile=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True, profile="--profile" in sys.argv))
+    var, defs = None, []
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):
+            var = a.split("=", 1)[1]
+        if a.startswith("-D"):
+            defs.append(a[2:])
+    print(build(force="--force" in sys.argv, verbose=True, profile="--profile" in sys.argv, variant=var,
+                defines=defs))
