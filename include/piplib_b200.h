@@ -89,13 +89,15 @@ int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long 
  *   status[i]  as above
  *   hashes[i]  (optional) FNV-1a over the serialised quast words (the function tests/ and
  *              oracle/ apply to the reference's trees); 0 when status[i] is fatal
- *   ser        (optional) the serialised quasts back to back, ser_off[i]..ser_off[i+1]
- *              (ser_off has n+1 entries); returns -2 when ser_cap is too small. */
+ *   ser        (optional) the serialised quasts: problem i occupies
+ *              ser[ser_off[i] .. ser_off[i] + ser_len[i]); spans are packed without gaps but, as
+ *              chunks of the batch finish in any order, not in problem order.  ser_off has n+1
+ *              entries, ser_off[n] = words used/needed; returns -2 when ser_cap is too small. */
 int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long *dom,
                        int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
                        int bignum, const PipOptions_dp *options,
                        int *status, unsigned long long *hashes,
-                       long long *ser, long long ser_cap, long long *ser_off);
+                       long long *ser, long long ser_cap, long long *ser_off, long long *ser_len);
 
 /* Device-resident variant of the dense batch: converted and uploaded once by create(); run()
  * executes only kernels (plus the 56-byte-per-problem status records the size-class ladder

@@ -204,7 +204,7 @@ def traiter_batch(cases):
     return out
 
 
-def solve_dense(dom, ctx, bignum=-1, want_hashes=True, want_ser=False, **opts):
+def solve_dense(dom, ctx, bignum=-1, want_hashes=True, want_ser=False, ser_cap_hint=None, **opts):
     """dom: [n, rows, cols] int64 (host); ctx: [n, rows, cols] or None.
     Returns dict(status, hashes, ser, ser_off)."""
     L = lib()
@@ -219,27 +219,29 @@ def solve_dense(dom, ctx, bignum=-1, want_hashes=True, want_ser=False, **opts):
     status = np.zeros(n, dtype=np.int32)
     hashes = np.zeros(n, dtype=np.uint64) if want_hashes else None
     o = make_options(**opts)
-    ser = ser_off = None
+    ser = ser_off = ser_len = None
     cap = 0
     if want_ser:
         ser_off = np.zeros(n + 1, dtype=np.int64)
-        cap = 512 * n + 1024
-        ser = np.zeros(cap, dtype=np.int64)
+        ser_len = np.zeros(n, dtype=np.int64)
+        cap = (ser_cap_hint or 448) * n + 1024
+        ser = np.empty(cap, dtype=np.int64)
     while True:
         rc = L.pip_solve_dense_dp(C.c_longlong(n), dr, dc, dom.ctypes.data_as(C.c_void_p), has, cr, cc, cp,
                                   int(bignum), C.byref(o), status.ctypes.data_as(C.c_void_p),
                                   hashes.ctypes.data_as(C.c_void_p) if want_hashes else None,
                                   ser.ctypes.data_as(C.c_void_p) if want_ser else None,
                                   C.c_longlong(cap),
-                                  ser_off.ctypes.data_as(C.c_void_p) if want_ser else None)
+                                  ser_off.ctypes.data_as(C.c_void_p) if want_ser else None,
+                                  ser_len.ctypes.data_as(C.c_void_p) if want_ser else None)
         if rc == -2:
             cap = int(ser_off[n]) + 16
-            ser = np.zeros(cap, dtype=np.int64)
+            ser = np.empty(cap, dtype=np.int64)
             continue
         if rc != 0:
             raise RuntimeError("pip_solve_dense_dp failed: %d" % rc)
         break
-    return dict(status=status, hashes=hashes, ser=ser, ser_off=ser_off)
+    return dict(status=status, hashes=hashes, ser=ser, ser_off=ser_off, ser_len=ser_len)
 
 
 class DeviceBatch:

@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <stdexcept>
 #include <thread>
 #include <vector>
@@ -81,9 +82,12 @@ Shape derive_shape(const MatView &dom, const MatView *ctx, int Bg, const PipOpti
 
 /* tab_Matrix2Tableau_xx (source/tab.c:292-393) writing `width`-wide rows to out.
  * ctx_mode: the matrix is the context (n == -1 in the reference). */
+/* returns false when some value does not fit the element type T */
 template <class T>
-void matrix_to_rows(const MatView &mx, T *out, int width, int Nv, bool ctx_mode, int Shift, int Bg, int Urs)
+bool matrix_to_rows(const MatView &mx, T *out, int width, int Nv, bool ctx_mode, int Shift, int Bg, int Urs)
 {
+  I lost = 0;
+#define PIP_ST(dst, val) do { const I v_ = (val); const T t_ = (T)v_; (dst) = t_; lost |= ((I)t_ ^ v_); } while (0)
   const int ctx = ctx_mode ? 1 : 0;
   int ncolm = mx.cols - 1;
   const bool isnew = Shift && (Bg + ctx > 0) && ((unsigned)(Bg + ctx) > (unsigned)(mx.cols - 2));
@@ -100,44 +104,47 @@ void matrix_to_rows(const MatView &mx, T *out, int width, int Nv, bool ctx_mode,
     for (j = 0; j < Nv; j++) {
       if (isnew && j == Bg) continue;
       if (Shift) big += MV(mx, i, 1 + j);
-      r[j] = (T)(Shift > 0 ? -MV(mx, i, 1 + j) : MV(mx, i, 1 + j));
+      PIP_ST(r[j], Shift > 0 ? -MV(mx, i, 1 + j) : MV(mx, i, 1 + j));
     }
     int k = Nv + 1;
     for (j = Nv + 1; j < ncolm; j++) {
       if (isnew && j == Bg) continue;
-      r[j] = (T)MV(mx, i, k);
+      PIP_ST(r[j], MV(mx, i, k));
       k++;
     }
     for (j = 0; j < Urs; j++) {
       int pos_n = ncolm - ctx + j, pos = pos_n - Urs;
       if (pos <= Bg) --pos;
-      r[pos_n] = (T)(-r[pos]);
+      PIP_ST(r[pos_n], -(I)r[pos]);
     }
-    r[cst] = (T)MV(mx, i, mx.cols - 1);
+    PIP_ST(r[cst], MV(mx, i, mx.cols - 1));
     if (Shift) {
       if (Shift < 0) big = -big;
-      if (isnew) r[Bg] = (T)big; else r[Bg] = (T)(r[Bg] + big);
+      if (isnew) PIP_ST(r[Bg], big); else PIP_ST(r[Bg], (I)r[Bg] + big);
     }
     cur++;
     if (!ineq) {
       T *r2 = out + (size_t)cur * width;
-      for (j = 0; j < width; j++) r2[j] = (T)(-r[j]);
+      for (j = 0; j < width; j++) PIP_ST(r2[j], -(I)r[j]);
       cur++;
     }
   }
+#undef PIP_ST
+  return lost == 0;
 }
 
 /* words one problem contributes to the pool */
 size_t problem_words(const Shape &s) { return (size_t)s.Nl * (s.Nn + s.Np + 1) + (size_t)s.Nm * (s.Np + 1); }
 
 template <class T>
-void fill_problem(const MatView &dom, const MatView *ctx, const Shape &s, PipProblem &P, T *pool, size_t off)
+bool fill_problem(const MatView &dom, const MatView *ctx, const Shape &s, PipProblem &P, T *pool, size_t off)
 {
   P.nvar = s.Nn; P.nparm = s.Np; P.ni = s.Nl; P.nc = s.Nm; P.bigparm = s.Bg; P.flags = s.flags; P.off = (I)off;
   T *tab = pool + off;
-  matrix_to_rows(dom, tab, s.Nn + s.Np + 1, s.Nn, false, s.Shift, s.Bg, s.Urs);
+  bool ok = matrix_to_rows(dom, tab, s.Nn + s.Np + 1, s.Nn, false, s.Shift, s.Bg, s.Urs);
   if (ctx && s.Nm)
-    matrix_to_rows(*ctx, tab + (size_t)s.Nl * (s.Nn + s.Np + 1), s.Np + 1, s.Np - s.Urs, true, s.Shift, s.Bg - s.Nn - 1, s.Urs);
+    ok = matrix_to_rows(*ctx, tab + (size_t)s.Nl * (s.Nn + s.Np + 1), s.Np + 1, s.Np - s.Urs, true, s.Shift, s.Bg - s.Nn - 1, s.Urs) && ok;
+  return ok;
 }
 
 /* ---- cells -> tree: source/sol.c:435-734 ------------------------------------------------- */
@@ -807,98 +814,164 @@ void parallel_ranges(size_t n, size_t nt, F f)
   for (auto &x : th) x.join();
 }
 
-/* shapes + offsets + the narrowest element width that holds every tableau entry of the chunk */
-void plan_chunk(const DenseArgs &A, DenseChunk &C, size_t nthreads, bool allow_narrow)
+/* shapes + offsets of a chunk */
+void plan_chunk(const DenseArgs &A, DenseChunk &C, size_t nthreads)
 {
   const size_t n = C.n;
   C.shapes.resize(n);
   C.prob.resize(n);
   C.off.assign(n + 1, 0);
-  std::vector<I> maxabs(nthreads + 1, 0);
-  parallel_ranges(n, nthreads, [&](size_t t, size_t a, size_t b) {
-    I m = 0;
+  parallel_ranges(n, nthreads, [&](size_t, size_t a, size_t b) {
     for (size_t i = a; i < b; i++) {
       const size_t g = C.first + i;
       MatView d = {A.dr, A.dc, nullptr, A.dom + g * A.dr * A.dc};
       MatView c = {A.cr, A.cc, nullptr, A.has_ctx ? A.ctx + g * A.cr * A.cc : nullptr};
       C.shapes[i] = derive_shape(d, A.has_ctx ? &c : nullptr, A.bignum, A.opt);
-      if (allow_narrow) {
-        const I *p = d.dense;
-        for (size_t k = 0, e = (size_t)A.dr * A.dc; k < e; k++) { I v = p[k] < 0 ? -p[k] : p[k]; if (v > m) m = v; }
-        if (A.has_ctx) {
-          p = c.dense;
-          for (size_t k = 0, e = (size_t)A.cr * A.cc; k < e; k++) { I v = p[k] < 0 ? -p[k] : p[k]; if (v > m) m = v; }
-        }
-      }
     }
-    maxabs[t] = m;
   });
   for (size_t i = 0; i < n; i++) C.off[i + 1] = C.off[i] + problem_words(C.shapes[i]);
   C.pool_elems = C.off[n];
   C.elem_log2 = 3;
-  if (allow_narrow) {
-    I m = 0;
-    for (I v : maxabs) m = std::max(m, v);
-    /* the big-parameter column holds a sum of up to dc coefficients (source/tab.c:345-376) */
-    const I bound = (A.opt.Maximize || A.opt.Urs_unknowns) ? m * (I)(A.dc + 1) : m;
-    if (m >= 0 && bound < 127) C.elem_log2 = 0;
-    else if (m >= 0 && m < (1ll << 40) && bound < 2147483647ll) C.elem_log2 = 2;
-  }
 }
 
 template <class T>
-void convert_chunk_t(const DenseArgs &A, DenseChunk &C, T *pool, size_t nthreads)
+bool convert_chunk_t(const DenseArgs &A, DenseChunk &C, T *pool, size_t nthreads)
 {
-  parallel_ranges(C.n, nthreads, [&](size_t, size_t a, size_t b) {
+  std::vector<char> ok(nthreads + 1, 1);
+  parallel_ranges(C.n, nthreads, [&](size_t t, size_t a, size_t b) {
+    bool good = true;
     for (size_t i = a; i < b; i++) {
       const size_t g = C.first + i;
       MatView d = {A.dr, A.dc, nullptr, A.dom + g * A.dr * A.dc};
       MatView c = {A.cr, A.cc, nullptr, A.has_ctx ? A.ctx + g * A.cr * A.cc : nullptr};
-      fill_problem(d, A.has_ctx ? &c : nullptr, C.shapes[i], C.prob[i], pool, C.off[i]);
+      good = fill_problem(d, A.has_ctx ? &c : nullptr, C.shapes[i], C.prob[i], pool, C.off[i]) && good;
     }
+    ok[t] = good;
   });
+  for (char k : ok) if (!k) return false;
+  return true;
 }
-void convert_chunk(const DenseArgs &A, DenseChunk &C, void *pool, size_t nthreads)
+/* Convert a chunk into the pinned staging area of `E`, trying the narrowest element first
+ * (int8, then int32, then int64); `hint` remembers the width that worked for earlier chunks. */
+void *convert_chunk(const DenseArgs &A, DenseChunk &C, PipEngine &E, size_t nthreads, std::atomic<int> *hint)
 {
-  if (C.elem_log2 == 0) convert_chunk_t(A, C, (signed char *)pool, nthreads);
-  else if (C.elem_log2 == 2) convert_chunk_t(A, C, (int *)pool, nthreads);
-  else convert_chunk_t(A, C, (I *)pool, nthreads);
+  int start = hint ? hint->load() : 0;
+  void *pool = E.pinned_input((C.pool_elems + 8) << 3);
+  for (int w = start;; w = (w == 0 ? 2 : 3)) {
+    bool ok;
+    if (w == 0) ok = convert_chunk_t(A, C, (signed char *)pool, nthreads);
+    else if (w == 2) ok = convert_chunk_t(A, C, (int *)pool, nthreads);
+    else ok = convert_chunk_t(A, C, (I *)pool, nthreads);
+    if (ok || w == 3) {
+      C.elem_log2 = w;
+      if (hint && w > hint->load()) hint->store(w);
+      return pool;
+    }
+  }
 }
 
-/* serialise every solved problem of the chunk straight from its cells: one pass per worker
- * range into a private buffer, hash and length on the fly */
-void emit_chunk(const DenseArgs &A, DenseChunk &C, int *status, unsigned long long *hashes, bool keep, size_t nthreads)
+/* words ser_quast_direct would emit, without touching the values (structure only) */
+template <class C>
+long long len_vector(const C &c, int *i, int Bg, int Urs_p, int flags)
+{
+  int n = (int)c.p1(*i);
+  if (flags & S_REMOVE) --n;
+  n -= Urs_p;
+  const int first_urs = Urs_p + (Bg >= 0);
+  for (int j = 0, k = 0; k < n; j++) {
+    (*i)++;
+    if ((flags & S_REMOVE) && j == Bg) continue;
+    if (first_urs <= j && j < first_urs + Urs_p) continue;
+    k++;
+  }
+  (*i)++;
+  return 1 + 2ll * (n > 0 ? n : 0);
+}
+template <class C>
+long long len_quast(const C &c, int *i, int Bg, int Urs_p, int flags)
+{
+  while (c.kind(*i) == PIP_C_FREE) (*i)++;
+  long long w = 1;
+  while (c.kind(*i) == PIP_C_NEW) {
+    (*i) += 2;
+    w += 2 + len_vector(c, i, Bg, Urs_p, flags & S_REMOVE);
+    (*i)++;
+  }
+  const int kind = c.kind(*i);
+  const int nb = (int)c.p1(*i);
+  (*i)++;
+  w += 1;
+  if (kind == PIP_C_LIST) {
+    if (nb == 0) w += 2;
+    else { w += 1; for (int e = 0; e < nb; e++) w += 1 + len_vector(c, i, Bg, Urs_p, flags); }
+    w += 1;
+    if (flags & S_DUAL) w += len_quast(c, i, Bg, Urs_p, 0);
+  } else if (kind == PIP_C_IF) {
+    w += len_vector(c, i, Bg, Urs_p, flags & S_REMOVE);
+    w += len_quast(c, i, Bg, Urs_p, flags);
+    w += len_quast(c, i, Bg, Urs_p, flags);
+  }
+  return w;
+}
+
+/* Serialise every solved problem of the chunk straight from its cells into the caller's stream.
+ * Pass 1 sizes each problem (structure walk, no arithmetic); the chunk then reserves its span of
+ * `ser` with one atomic add (chunks finish in any order, so spans are not in problem order);
+ * pass 2 decodes in place, hashing on the fly. */
+void emit_chunk(const DenseArgs &A, DenseChunk &C, int *status, unsigned long long *hashes,
+                long long *ser, long long ser_cap, long long *ser_off, long long *ser_len,
+                std::atomic<long long> *cursor, size_t nthreads)
 {
   const size_t n = C.n;
+  const bool keep = ser != nullptr && ser_off != nullptr;
+  const int simplify = A.opt.Simplify;
+  for (size_t i = 0; i < n; i++) status[C.first + i] = C.out.res[i].status;
+  if (!keep && !hashes) return;
   C.words.assign(n, 0);
   nthreads = std::max<size_t>(1, std::min(nthreads, (n + 63) / 64));
-  C.per = (n + nthreads - 1) / nthreads;
-  C.bufs.assign(nthreads, std::vector<I>());
-  const int simplify = A.opt.Simplify;
+  const size_t per = (n + nthreads - 1) / nthreads;
+  std::vector<long long> range_words(nthreads + 1, 0);
+  if (keep) {
+    parallel_ranges(n, nthreads, [&](size_t t, size_t a, size_t b) {
+      long long sum = 0;
+      for (size_t i = a; i < b; i++) {
+        const int st = C.out.res[i].status;
+        long long w = 0;
+        if (st == PIP_ST_VOID) w = 1;
+        else if (st == PIP_ST_OK) {
+          if (simplify) { Ser s = {nullptr, 0, 0, 0, false}; serialize_one(C.out, i, C.shapes[i], simplify, s); w = s.len; }
+          else {
+            const PipCellView v = C.out.cells_of(i);
+            int at = 0;
+            w = len_quast(v, &at, C.shapes[i].Bg - C.shapes[i].Nn - 1, C.shapes[i].Urs, C.shapes[i].sol_flags);
+          }
+        }
+        C.words[i] = w;
+        sum += w;
+      }
+      range_words[t] = sum;
+    });
+  }
+  long long total = 0;
+  std::vector<long long> range_base(nthreads + 1, 0);
+  for (size_t t = 0; t < nthreads; t++) { range_base[t] = total; total += range_words[t]; }
+  const long long base = keep ? cursor->fetch_add(total) : 0;
+  const bool fits = keep && base + total <= ser_cap;
   parallel_ranges(n, nthreads, [&](size_t t, size_t a, size_t b) {
-    std::vector<I> &buf = C.bufs[t];
-    size_t used = 0;
-    if (keep) {
-      size_t cells = 0;
-      for (size_t i = a; i < b; i++) cells += (size_t)C.out.res[i].ncells;
-      buf.resize(cells * 2 + (b - a) * 8 + 64);          /* >= the words any decode can produce */
-    }
+    long long at = base + range_base[t];
     for (size_t i = a; i < b; i++) {
       const int st = C.out.res[i].status;
-      status[C.first + i] = st;
       unsigned long long h = 0;
-      long long w = 0;
       if (st == PIP_ST_OK || st == PIP_ST_VOID) {
-        Ser s = {keep ? buf.data() + used : nullptr, keep ? (long)(buf.size() - used) : 0, 0, 0xcbf29ce484222325ULL, true};
-        serialize_one(C.out, i, C.shapes[i], simplify, s);
-        h = s.h; w = s.len;
-        if (keep) used += (size_t)s.len;
+        Ser s = {fits ? ser + at : nullptr, fits ? (long)C.words[i] : 0, 0, 0xcbf29ce484222325ULL, hashes != nullptr};
+        if (fits || hashes) serialize_one(C.out, i, C.shapes[i], simplify, s);
+        h = s.h;
       }
       if (hashes) hashes[C.first + i] = h;
-      C.words[i] = w;
+      if (keep) { ser_off[C.first + i] = at; if (ser_len) ser_len[C.first + i] = C.words[i]; at += C.words[i]; }
     }
-    if (keep) buf.resize(used);
   });
+  (void)per;
 }
 
 void add_times(PipBatchOut &acc, const PipBatchOut &o)
@@ -927,7 +1000,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
                        int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
                        int bignum, const PipOptions_dp *options,
                        int *status, unsigned long long *hashes,
-                       long long *ser, long long ser_cap, long long *ser_off)
+                       long long *ser, long long ser_cap, long long *ser_off, long long *ser_len)
 {
   if (n <= 0) return 0;
   try {
@@ -942,19 +1015,29 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     std::vector<DenseChunk> chunks(nchunks);
     for (size_t c = 0; c < nchunks; c++) { chunks[c].first = c * CH; chunks[c].n = std::min(CH, (size_t)n - c * CH); }
     std::vector<std::string> errors(lanes);
+    std::atomic<long long> cursor(0);
+    std::atomic<int> width_hint(0);
+    const bool timing = getenv("PIPLIB_B200_TIMING") != nullptr;
+    std::vector<double> tstage(lanes * 4, 0.0);
     auto lane_main = [&](size_t lane) {
       try {
         PipEngine &E = PipEngine::lane((int)lane);
         for (size_t c = lane; c < nchunks; c += lanes) {
           DenseChunk &C = chunks[c];
-          plan_chunk(A, C, nthreads, true);
-          void *pool = E.pinned_input((C.pool_elems + 8) << C.elem_log2);
-          convert_chunk(A, C, pool, nthreads);
+          double ta = wall();
+          plan_chunk(A, C, nthreads);
+          double tb = wall();
+          void *pool = convert_chunk(A, C, E, nthreads, &width_hint);
+          double tc = wall();
+          tstage[lane * 4 + 0] += tb - ta; tstage[lane * 4 + 1] += tc - tb;
           PipBatchIn in;
           in.n = C.n; in.h_prob = C.prob.data(); in.h_pool = pool; in.pool_words = C.pool_elems;
           in.elem_log2 = C.elem_log2;
+          double td = wall();
           E.run(in, C.out);
-          emit_chunk(A, C, status, hashes, keep, nthreads);
+          double te = wall();
+          emit_chunk(A, C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
+          tstage[lane * 4 + 2] += te - td; tstage[lane * 4 + 3] += wall() - te;
           /* the cell chunks are engine-owned and reused by the next run on this lane: drop the views */
           C.out.base.clear();
         }
@@ -967,26 +1050,15 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
       for (auto &x : th) x.join();
     }
     for (const std::string &e : errors) if (!e.empty()) throw std::runtime_error(e);
-    /* assemble */
-    long long total = 0;
-    for (size_t c = 0; c < nchunks; c++)
-      for (size_t i = 0; i < chunks[c].n; i++) {
-        if (ser_off) ser_off[chunks[c].first + i] = total;
-        total += chunks[c].words[i];
-      }
+    const double tasm0 = wall();
+    const long long total = cursor.load();
     if (ser_off) ser_off[n] = total;
-    if (keep && total <= ser_cap) {
-      std::vector<std::thread> th;
-      for (size_t c = 0; c < nchunks; c++)
-        for (size_t t = 0; t < chunks[c].bufs.size(); t++) {
-          const size_t a = chunks[c].first + t * chunks[c].per;
-          if (a >= (size_t)n || chunks[c].bufs[t].empty()) continue;
-          const std::vector<I> *b = &chunks[c].bufs[t];
-          I *dst = ser + ser_off[a];
-          th.emplace_back([=] { memcpy(dst, b->data(), b->size() * sizeof(I)); });
-          if (th.size() >= nthreads) { for (auto &x : th) x.join(); th.clear(); }
-        }
-      for (auto &x : th) x.join();
+    if (timing) {
+      for (size_t l = 0; l < lanes; l++)
+        fprintf(stderr, "[piplib-b200] lane %zu: plan %.3f convert %.3f run %.3f emit %.3f s\n", l,
+                tstage[l * 4], tstage[l * 4 + 1], tstage[l * 4 + 2], tstage[l * 4 + 3]);
+      fprintf(stderr, "[piplib-b200] assemble %.3f s, total %.3f s, %zu chunks, %zu lanes, %zu threads\n",
+              wall() - tasm0, wall() - t0, nchunks, lanes, nthreads);
     }
     PipBatchOut acc;
     for (size_t c = 0; c < nchunks; c++) add_times(acc, chunks[c].out);
@@ -1017,10 +1089,9 @@ pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_col
     b->A = {n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum, options ? *options : DEFAULT_OPTIONS};
     b->C.first = 0; b->C.n = (size_t)n;
     const size_t nthreads = host_threads();
-    plan_chunk(b->A, b->C, nthreads, true);
+    plan_chunk(b->A, b->C, nthreads);
     PipEngine &E = PipEngine::get();
-    void *pool = E.pinned_input((b->C.pool_elems + 8) << b->C.elem_log2);
-    convert_chunk(b->A, b->C, pool, nthreads);
+    void *pool = convert_chunk(b->A, b->C, E, nthreads, nullptr);
     pip_cuda_check(cudaMalloc((void **)&b->d_prob, sizeof(PipProblem) * (size_t)n), "cudaMalloc(problems)");
     pip_cuda_check(cudaMalloc(&b->d_pool, (b->C.pool_elems + 8) << b->C.elem_log2), "cudaMalloc(pool)");
     pip_cuda_check(cudaMemcpy(b->d_prob, b->C.prob.data(), sizeof(PipProblem) * (size_t)n, cudaMemcpyHostToDevice), "H2D problems");
@@ -1055,7 +1126,7 @@ int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long lon
 {
   if (b->C.out.res.size() != b->C.n) return -1;
   if (hashes && !b->fetched) return -3;
-  if (hashes) emit_chunk(b->A, b->C, status, hashes, false, host_threads());
+  if (hashes) emit_chunk(b->A, b->C, status, hashes, nullptr, 0, nullptr, nullptr, nullptr, host_threads());
   else for (size_t i = 0; i < b->C.n; i++) status[i] = b->C.out.res[i].status;
   return 0;
 }

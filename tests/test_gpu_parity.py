@@ -134,7 +134,7 @@ def test_dense_batch_vs_oracle(api, port, workload, n):
     assert int(s.pivots) == int(stats.pivots)            # same pivots, sub-solves included
     for i in range(0, n, max(1, n // 20)):
         st, ser = port.solve(dom[i], ctx[i], -1)
-        mine = [int(x) for x in r["ser"][r["ser_off"][i]:r["ser_off"][i + 1]]]
+        mine = [int(x) for x in r["ser"][r["ser_off"][i]:r["ser_off"][i] + r["ser_len"][i]]]
         assert (st, ser) == (int(st_g[i]), mine) or st != 0
 
 
