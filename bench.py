@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+from piplib_b200 import dist as pdist  # noqa: E402
 from piplib_b200 import synth  # noqa: E402
 
 METRIC = "problems_per_sec"
@@ -161,9 +162,7 @@ def main():
     ap.add_argument("--check", type=int, default=4096, help="problems cross-checked against the oracle")
     a = ap.parse_args()
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = pdist.env_rank()
     cores = os.cpu_count() or 1
     W = max(a.warmup, 0)
     K = max(a.steps, 1)
@@ -217,7 +216,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    dom, ctx = synth.generate(a.workload, B, seed=a.seed, first=rank * B)
+    first, _ = pdist.problem_range(rank, world, B)
+    dom, ctx = synth.generate(a.workload, B, seed=a.seed, first=first)
 
     # parity gate before any timing: a slice of this rank's batch against the oracle
     ncheck = min(a.check, B)
@@ -271,13 +271,9 @@ def main():
         sampler.stop()
 
     # max over ranks
-    t = torch.tensor([dev_ms, wall_ms, e2e_s or 0.0], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(pivots_step), float(elem_step)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_ms, wall_ms, e2e_max = [float(x) for x in t.tolist()]
-    pivots_all, elem_all = [float(x) for x in cnt.tolist()]
+    (dev_ms, wall_ms, e2e_max), (pivots_all, elem_all, cells_all) = pdist.reduce_stats(
+        [dev_ms, wall_ms, e2e_s or 0.0], [float(pivots_step), float(elem_step), float(cells_step)],
+        device="cuda")
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -287,7 +283,7 @@ def main():
         # algorithmic HBM traffic of the solve kernel: every problem's input words are read once
         # and its solution cells written once (the working set itself lives in shared memory)
         in_bytes = dom.shape[1] * (dom.shape[2] - 1) * 8 + ctx.shape[1] * (ctx.shape[2] - 1) * 8 + 32
-        alg_bytes = float(B) * (in_bytes + 56) + 24.0 * cells_step
+        alg_bytes = float(B) * (in_bytes + 56) + 8.0 * cells_step
         achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
         uniq, counts = np.unique(status, return_counts=True)
         line = {
