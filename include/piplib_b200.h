@@ -111,6 +111,19 @@ int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
 int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long long *hashes);
 void pip_device_batch_destroy(pip_device_batch *b);
 
+/* One LARGE non-parametric tableau solved by the whole grid (BASELINE config 4; the tableau lives
+ * in HBM, the pivot update is HBM-bound).  tab is ni x (nvar+1), .dat column order; nq as in the
+ * .dat header; cut_rows = spare rows for Gomory cuts; sol_size / maxcol = 0 keep the reference's
+ * limits (source/type.h:39,49: a 4096-unknown solution needs 8193 cells, so the stock limits end
+ * in status 1026 exactly like the reference).  Same semantics as the maind.c per-problem body. */
+typedef struct pip_large_problem pip_large_problem;
+pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long *tab, int cut_rows,
+                                       int sol_size, int maxcol);
+int pip_large_run_dp(pip_large_problem *p, float *kernel_ms);
+int pip_large_fetch_dp(pip_large_problem *p, int *status, PipCell_dp *cells, int cell_cap, int *ncells,
+                       long long *info /* [4]: pivots, cuts, skipped identity rows, final ni */);
+void pip_large_destroy_dp(pip_large_problem *p);
+
 void pip_last_batch_stats_dp(PipBatchStats_dp *out);
 
 /* PipQuast -> int64 stream; returns the number of words (may exceed cap: nothing past cap is written) */

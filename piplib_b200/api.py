@@ -78,6 +78,13 @@ def lib():
         L.pip_device_batch_results.restype = C.c_int
         L.pip_device_batch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pip_device_batch_destroy.argtypes = [C.c_void_p]
+        L.pip_large_create_dp.restype = C.c_void_p
+        L.pip_large_run_dp.restype = C.c_int
+        L.pip_large_run_dp.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.pip_large_fetch_dp.restype = C.c_int
+        L.pip_large_fetch_dp.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+        L.pip_large_destroy_dp.argtypes = [C.c_void_p]
         L.pip_last_batch_stats_dp.argtypes = [C.POINTER(PipBatchStats)]
         L.pip_set_device_dp.restype = C.c_int
         L.pip_b200_version.restype = C.c_char_p
@@ -282,6 +289,47 @@ class DeviceBatch:
     def close(self):
         if self.h:
             lib().pip_device_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LargeProblem:
+    """one large non-parametric tableau solved by the whole grid (pip_large_*_dp)."""
+
+    def __init__(self, nvar, ni, nq, tab, cut_rows=1024, sol_size=0, maxcol=0):
+        tab = np.ascontiguousarray(tab, dtype=np.int64).reshape(ni, nvar + 1)
+        self.nvar, self.ni = nvar, ni
+        self.cap = max(sol_size, 4096) + 8
+        self.h = lib().pip_large_create_dp(nvar, ni, int(nq), tab.ctypes.data_as(C.c_void_p), cut_rows,
+                                           sol_size, maxcol)
+        if not self.h:
+            raise RuntimeError("pip_large_create_dp failed")
+
+    def run(self):
+        ms = C.c_float(0)
+        if lib().pip_large_run_dp(self.h, C.byref(ms)) != 0:
+            raise RuntimeError("pip_large_run_dp failed")
+        return float(ms.value)
+
+    def fetch(self):
+        st, nc = C.c_int(0), C.c_int(0)
+        info = (C.c_longlong * 4)()
+        cells = np.zeros(self.cap, dtype=CELL_DTYPE)
+        if lib().pip_large_fetch_dp(self.h, C.byref(st), cells.ctypes.data_as(C.c_void_p), self.cap,
+                                    C.byref(nc), info) != 0:
+            raise RuntimeError("pip_large_fetch_dp failed")
+        c = cells[:nc.value]
+        return st.value, [[int(x["kind"]), int(x["p1"]), int(x["p2"])] for x in c], \
+            dict(pivots=int(info[0]), cuts=int(info[1]), skipped_rows=int(info[2]), ni=int(info[3]))
+
+    def close(self):
+        if self.h:
+            lib().pip_large_destroy_dp(self.h)
             self.h = None
 
     def __del__(self):

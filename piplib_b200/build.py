@@ -16,10 +16,10 @@ NVCC = os.path.join(CUDA, "bin", "nvcc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fwrapv", "-Xptxas", "-v"]
-SOURCES_CU = ["pip_kernels.cu"]
+SOURCES_CU = ["pip_kernels.cu", "pip_large.cu"]
 SOURCES_CPP = ["pip_engine.cpp", "pip_host.cpp"]
 HEADERS = ["pip_types.h", "simt.h", "pip_arith.h", "pip_solver.h", "pip_warp_main.h", "pip_kernels.h",
-           "pip_engine.h", os.path.join("..", "..", "include", "piplib_b200.h"),
+           "pip_engine.h", "pip_large.h", os.path.join("..", "..", "include", "piplib_b200.h"),
            os.path.join("..", "..", "include", "piplib", "piplib.h")]
 
 

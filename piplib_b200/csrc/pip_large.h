@@ -1,0 +1,556 @@
+/* Grid-per-problem solver for one large non-parametric tableau (BASELINE config 4: ~4096 x 4097
+ * int64, 134 MB, HBM-bound).  The whole grid works on one tableau that lives in global memory;
+ * a pivot is two grid-wide phases separated by cooperative grid syncs:
+ *
+ *   phase AB (CTA 0)   row pick in position order (chercher + exam_coef, source/traiter.c:669-680),
+ *                      cut generation when no row is negative (integrer case (d), source/integrer.c:
+ *                      342-481), lexicographic pivot column (choisir_piv, source/traiter.c:297-341)
+ *                      as a candidate-set filtering pass over the positions, determinant / overflow
+ *                      bookkeeping (source/traiter.c:394-447)
+ *   phase C (all CTAs) rank-1 update of every stored row against the snapshotted pivot row with the
+ *                      per-row gcd normalisation (source/traiter.c:467-502), one warp per row,
+ *                      coalesced 16-byte loads; re-flag and constant-sign bookkeeping fused in
+ *
+ * nparm = 0 only (no context, no splits): that is what "one large dense ILP tableau" is.  The
+ * position/slot model, flags and arithmetic are those of pip_solver.h.  The code is written against
+ * the tiny G:: abstraction so that tests/emu can run it on the CPU as one 32-thread CTA.
+ */
+#ifndef PIP_LARGE_H
+#define PIP_LARGE_H
+
+#include "pip_arith.h"
+#include "pip_types.h"
+#include "simt.h"
+
+#define PIPL_INF 0x7fffffff
+
+struct PipLarge {
+  /* problem */
+  int nvar, ni, flags;            /* nparm = 0 */
+  int stride;                     /* words per slot (even) */
+  int pcap, rcap;                 /* position / slot capacity */
+  int sol_size, maxcol;
+  pip_i64 *data;                  /* rcap x stride */
+  pip_i64 *den;                   /* [pcap] */
+  int *fl;                        /* [pcap] flag | link << 8 */
+  signed char *csign;             /* [pcap] sign of the constant column of each stored row */
+  /* scratch of phase AB */
+  int *cand;                      /* [nvar] compact candidate list */
+  unsigned char *member;          /* [nvar] */
+  pip_i64 *cut;                   /* [stride] */
+  /* control block (global, written by CTA 0, read by everyone after a grid sync) */
+  int *ctl;                       /* see PIPL_* below */
+  pip_i64 *ctl64;                 /* [8]: pivot, dpiv, det[4] */
+  PipCell *cells;
+  unsigned long long *prof;       /* [8] cycle counters of CTA 0: AB, C, sync */
+};
+enum { PIPL_ACTION = 0, PIPL_PIVI, PIPL_PIVJ, PIPL_STATUS, PIPL_NCELL, PIPL_NI, PIPL_LDET, PIPL_PIVOTS,
+       PIPL_CUTS, PIPL_SKIPPED_LO, PIPL_SKIPPED_HI, PIPL_NCTL = 16 };
+enum { PIPL_GO = 0, PIPL_STOP = 1 };
+
+/* ---- CTA-level helpers (shared scratch: int red[64]) ------------------------------------- */
+PIP_DEV int pipl_cta_min(int v, int *red)
+{
+  v = (int)W::redmin((unsigned)v + 0x80000000u) - (int)0x80000000u;
+  const int lane = W::lane(), wid = G::tid() >> 5, nw = (G::T() + 31) >> 5;
+  G::cta_sync();
+  if (lane == 0) red[wid] = v;
+  G::cta_sync();
+  int r = PIPL_INF;
+  for (int i = 0; i < nw; i++) r = red[i] < r ? red[i] : r;
+  return r;
+}
+PIP_DEV int pipl_cta_max(int v, int *red) { return -pipl_cta_min(-v, red); }
+PIP_DEV int pipl_cta_sum(int v, int *red)
+{
+  const int lane = W::lane(), wid = G::tid() >> 5, nw = (G::T() + 31) >> 5;
+  for (int o = 16; o > 0; o >>= 1) { int y = W::shfl_down(v, o); if (lane + o < 32) v += y; }
+  G::cta_sync();
+  if (lane == 0) red[wid] = v;
+  G::cta_sync();
+  int r = 0;
+  for (int i = 0; i < nw; i++) r += red[i];
+  return r;
+}
+
+PIP_DEV pip_i64 *pipl_row(const PipLarge &L, int slot) { return L.data + (pip_i64)slot * L.stride; }
+
+/* a/b < c/d for b, d > 0, exactly (128-bit products) */
+PIP_DEV int pipl_ratio_cmp(pip_i64 a, pip_i64 b, pip_i64 c, pip_i64 d)
+{
+  const pip_i64 lh = pip_mulhi(a, d), rh = pip_mulhi(c, b);
+  const pip_u64 ll = (pip_u64)a * (pip_u64)d, rl = (pip_u64)c * (pip_u64)b;
+  if (lh != rh) return lh < rh ? -1 : 1;
+  if (ll != rl) return ll < rl ? -1 : 1;
+  return 0;
+}
+
+/* rebuild the compact candidate list from member[] (ordered by column), returns its length */
+PIP_DEV int pipl_compact(const PipLarge &L, int *red, int *sh_base)
+{
+  const int tid = G::tid(), T = G::T();
+  int total = 0;
+  for (int base = 0; base < L.nvar; base += T) {
+    const int j = base + tid;
+    const int m = (j < L.nvar && L.member[j]) ? 1 : 0;
+    /* exclusive prefix within the CTA */
+    int x = m;
+    const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int y = W::shfl_up(x, o); if (lane >= o) x += y; }
+    G::cta_sync();
+    if (lane == 31) red[wid] = x;
+    G::cta_sync();
+    int before = 0;
+    for (int i = 0; i < wid; i++) before += red[i];
+    int all = 0;
+    for (int i = 0; i < nw; i++) all += red[i];
+    if (m) L.cand[total + before + x - 1] = j;
+    total += all;
+  }
+  G::cta_sync();
+  (void)sh_base;
+  return total;
+}
+
+/* ---- phase AB: CTA 0 ------------------------------------------------------------------------ */
+PIP_DEV void pipl_put(const PipLarge &L, int idx, int kind, pip_i64 p1, pip_i64 p2)
+{
+  L.cells[idx].kind = kind; L.cells[idx].pad = 0; L.cells[idx].p1 = p1; L.cells[idx].p2 = p2;
+}
+
+/* finish with a status (and, for OK, the solution list); CTA 0 only */
+PIP_DEV void pipl_finish(const PipLarge &L, int status, int kind /*0 none, 1 nil, 2 solution*/)
+{
+  const int tid = G::tid(), T = G::T();
+  int ncell = 0;
+  if (status == PIP_ST_OK && kind == 1) {
+    if (1 >= L.sol_size) status = PIP_ST_FATAL + 26;
+    else { if (tid == 0) pipl_put(L, 0, PIP_C_NIL, 0, 0); ncell = 1; }
+  } else if (status == PIP_ST_OK && kind == 2) {
+    const int total = 1 + 2 * L.nvar;                 /* solution_xx with nparm = 0 */
+    if (total >= L.sol_size) status = PIP_ST_FATAL + 26;
+    else {
+      for (int c = tid; c < total; c += T) {
+        if (c == 0) { pipl_put(L, 0, PIP_C_LIST, L.nvar, 0); continue; }
+        const int i = (c - 1) >> 1;
+        if ((c - 1) & 1) {
+          const int f = L.fl[i];
+          const pip_i64 d = L.den[i];
+          const pip_i64 v = (f & PIP_UNIT) ? (PIP_LINK(f) == L.nvar ? d : 0) : pipl_row(L, PIP_LINK(f))[L.nvar];
+          pipl_put(L, c, PIP_C_VAL, v, d);
+        } else pipl_put(L, c, PIP_C_FORM, 1, 0);
+      }
+      ncell = total;
+    }
+  }
+  G::cta_sync();
+  if (tid == 0) {
+    L.ctl[PIPL_STATUS] = status;
+    L.ctl[PIPL_NCELL] = status == PIP_ST_OK ? ncell : 0;
+    L.ctl[PIPL_ACTION] = PIPL_STOP;
+  }
+}
+
+/* One AB phase.  Leaves ctl[ACTION] = GO with (pivi, pivj, pivot, dpiv) or STOP with a status. */
+PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
+{
+  const int tid = G::tid(), T = G::T();
+  const int nvar = L.nvar, ncol = nvar + 1;
+  int ni = L.ctl[PIPL_NI];
+  int nl = nvar + ni;
+
+  /* the swap of the previous pivot (source/traiter.c:503-516) */
+  if (!first_call) {
+    const int pivi = L.ctl[PIPL_PIVI], pivj = L.ctl[PIPL_PIVJ];
+    const pip_i64 pivot = L.ctl64[0], dpiv = L.ctl64[1];
+    const int pslot = PIP_LINK(L.fl[pivi]);
+    pip_i64 *prow = pipl_row(L, pslot);
+    int ku = PIPL_INF;
+    for (int k = tid; k < nl; k += T) {
+      const int f = L.fl[k];
+      if ((f & PIP_UNIT) && PIP_LINK(f) == pivj) ku = k;
+    }
+    ku = pipl_cta_min(ku, red);
+    for (int j = tid; j < ncol; j += T) prow[j] = (j == pivj) ? dpiv : -prow[j];
+    G::cta_sync();
+    if (tid == 0) {
+      const pip_i64 c = prow[nvar];
+      L.fl[ku] = PIP_MKFL(PIP_PLUS, pslot); L.den[ku] = pivot;
+      L.csign[ku] = c < 0 ? -1 : c > 0 ? 1 : 0;
+      L.fl[pivi] = PIP_MKFL(PIP_UNIT | PIP_ZERO, pivj); L.den[pivi] = 1;
+    }
+    G::cta_sync();
+  }
+
+  int pivi = PIPL_INF;
+  for (;;) {
+    /* chercher(Minus) */
+    int c = PIPL_INF;
+    for (int k = tid; k < nl; k += T) if ((L.fl[k] & PIP_MINUS) && k < c) c = k;
+    pivi = pipl_cta_min(c, red);
+    if (pivi < nl) break;
+    /* exam_coef with nparm = 0: an Unknown row takes the sign of its constant; rows after the
+     * first negative one stay Unknown */
+    c = PIPL_INF;
+    for (int k = tid; k < nl; k += T) {
+      const int f = L.fl[k];
+      if (PIP_FLAG(f) == PIP_UNKNOWN && L.csign[k] < 0 && k < c) c = k;
+    }
+    const int firstneg = pipl_cta_min(c, red);
+    for (int k = tid; k < nl; k += T) {
+      const int f = L.fl[k];
+      if (PIP_FLAG(f) != PIP_UNKNOWN || k > firstneg) continue;
+      const int s = L.csign[k];
+      L.fl[k] = PIP_MKFL(s < 0 ? PIP_MINUS : s > 0 ? PIP_PLUS : PIP_ZERO, PIP_LINK(f));
+    }
+    G::cta_sync();
+    if (firstneg < nl) { pivi = firstneg; break; }
+    /* all rows non-negative */
+    if (!(L.flags & PIP_F_INT)) { pipl_finish(L, PIP_ST_OK, 2); return; }
+    /* integrer, nparm = 0: cases (a), (b), (d) */
+    if (ncol >= L.maxcol) { pipl_finish(L, PIP_ST_FATAL + 3, 0); return; }
+    int cand = PIPL_INF;
+    for (int i = tid; i < nvar; i += T) {
+      const int f = L.fl[i];
+      if (!(f & PIP_UNIT) && L.den[i] != 1 && i < cand) cand = i;
+    }
+    int verdict = 0, row_i = pipl_cta_min(cand, red);
+    while (row_i < nvar) {
+      const pip_i64 D = L.den[row_i];
+      if (D == 0) { pipl_finish(L, PIP_ST_FAULT, 0); return; }
+      const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[row_i]));
+      int okv = 0, okc = 0;
+      for (int j = tid; j < ncol; j += T) {
+        pip_i64 x;
+        if (j < nvar) { x = pip_mod(row[j], D); okv |= x > 0; }
+        else { x = -pip_mod(-row[j], D); okc |= x != 0; }
+        L.cut[j] = x;
+      }
+      okv = pipl_cta_max(okv, red);
+      okc = pipl_cta_max(okc, red);
+      if (okc) { verdict = okv ? 1 : -1; break; }
+      /* case (a): integral row, look for the next candidate */
+      cand = PIPL_INF;
+      for (int i = row_i + 1 + tid; i < nvar; i += T) {
+        const int f = L.fl[i];
+        if (!(f & PIP_UNIT) && L.den[i] != 1 && i < cand) cand = i;
+      }
+      row_i = pipl_cta_min(cand, red);
+    }
+    if (verdict == 0) { pipl_finish(L, PIP_ST_OK, 2); return; }
+    if (verdict < 0) { pipl_finish(L, PIP_ST_OK, 1); return; }
+    if (ni >= L.rcap || nl >= L.pcap) { pipl_finish(L, PIP_ST_CAPACITY, 0); return; }
+    {
+      pip_i64 *nr = pipl_row(L, ni);
+      for (int j = tid; j < ncol; j += T) nr[j] = L.cut[j];
+      G::cta_sync();
+      if (tid == 0) {
+        L.fl[nl] = PIP_MKFL(PIP_MINUS, ni);
+        L.den[nl] = L.den[row_i];
+        L.csign[nl] = L.cut[nvar] < 0 ? -1 : L.cut[nvar] > 0 ? 1 : 0;
+        L.ctl[PIPL_NI] = ni + 1;
+        L.ctl[PIPL_CUTS] = L.ctl[PIPL_CUTS] + 1;
+      }
+      G::cta_sync();
+      pivi = nl;
+      ni++; nl++;
+      break;
+    }
+  }
+
+  /* ---- choisir_piv: candidate-set filtering over the positions -------------------------------- */
+  const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
+  for (int j = tid; j < nvar; j += T) L.member[j] = prow[j] > 0 ? 1 : 0;
+  G::cta_sync();
+  int ncand = pipl_compact(L, red, 0);
+  if (ncand == 0) { pipl_finish(L, PIP_ST_OK, 1); return; }
+  int k = 0;
+  while (ncand > 1 && k < nl) {
+    const int p = k + tid;
+
+    int kind = 0;
+    if (p < nl) {
+      const int f = L.fl[p];
+      if (f & PIP_UNIT) { if (PIP_LINK(f) < nvar && L.member[PIP_LINK(f)]) kind = 1; }
+      else {
+        const pip_i64 *row = pipl_row(L, PIP_LINK(f));
+        const int j0 = L.cand[0];
+        const pip_i64 a0 = row[j0], b0 = prow[j0];
+        for (int m = 1; m < ncand; m++) {
+          const int j = L.cand[m];
+          if (pipl_ratio_cmp(row[j], prow[j], a0, b0) != 0) { kind = 2; break; }
+        }
+      }
+    }
+    const int pstar = pipl_cta_min(kind == 2 ? p : PIPL_INF, red);
+    const bool mine = kind == 1 && p < pstar;
+    const int nelim = pipl_cta_sum(mine ? 1 : 0, red);
+    if (nelim >= ncand) {
+      /* every remaining candidate's Unit row lies in this run: the last one survives */
+      const int pmax = pipl_cta_max(mine ? p : -1, red);
+      if (mine && p != pmax) L.member[PIP_LINK(L.fl[p])] = 0;
+      G::cta_sync();
+      ncand = 1;
+      break;
+    }
+    if (mine) L.member[PIP_LINK(L.fl[p])] = 0;
+    G::cta_sync();
+    if (nelim) ncand = pipl_compact(L, red, 0);
+    if (pstar < PIPL_INF) {
+      /* keep the candidates with the minimal ratio at row pstar */
+      const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pstar]));
+      /* every thread finds the minimum over its share, then the CTA reduces by index of the best */
+      int best = -1;
+      for (int m = tid; m < ncand; m += T) {
+        const int j = L.cand[m];
+        if (best < 0 || pipl_ratio_cmp(row[j], prow[j], row[best], prow[best]) < 0) best = j;
+      }
+      /* tournament across threads through the candidate indices in shared scratch */
+      int winner = best;
+      {
+        const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+        for (int o = 16; o > 0; o >>= 1) {
+          const int other = W::shfl_down(winner, o);
+          if (lane + o < 32 && other >= 0 && (winner < 0 || pipl_ratio_cmp(row[other], prow[other], row[winner], prow[winner]) < 0))
+            winner = other;
+        }
+        G::cta_sync();
+        if (lane == 0) red[wid] = winner;
+        G::cta_sync();
+        winner = -1;
+        for (int i = 0; i < nw; i++) {
+          const int o = red[i];
+          if (o >= 0 && (winner < 0 || pipl_ratio_cmp(row[o], prow[o], row[winner], prow[winner]) < 0)) winner = o;
+        }
+      }
+      for (int m = tid; m < ncand; m += T) {
+        const int j = L.cand[m];
+        if (pipl_ratio_cmp(row[j], prow[j], row[winner], prow[winner]) != 0) L.member[j] = 0;
+      }
+      G::cta_sync();
+      ncand = pipl_compact(L, red, 0);
+      k = pstar + 1;
+    } else k += T;
+  }
+  /* the survivor (smallest column if, against the theory, several remain) */
+  int pj = PIPL_INF;
+  for (int j = tid; j < nvar; j += T) if (L.member[j] && j < pj) pj = j;
+  const int pivj = pipl_cta_min(pj, red);
+  if (pivj >= nvar) { pipl_finish(L, PIP_ST_FAULT, 0); return; }
+
+  /* ---- determinant bookkeeping, source/traiter.c:394-447 (one thread) ------------------------- */
+  if (tid == 0) {
+    const pip_i64 pivot = prow[pivj], dpiv = L.den[pivi];
+    int status = PIP_ST_OK;
+    pip_i64 d = pip_gcd(pivot, dpiv);
+    if (d == 0) status = PIP_ST_FAULT;
+    else {
+      pip_i64 ppivot = pip_div(pivot, d), dppiv = pip_div(dpiv, d);
+      int ldet = L.ctl[PIPL_LDET];
+      pip_i64 *det = L.ctl64 + 2;
+      for (int i = 0; i < ldet && status == PIP_ST_OK; i++) {
+        const pip_i64 g = pip_gcd(det[i], dppiv);
+        if (g == 0) { status = PIP_ST_FAULT; break; }
+        det[i] = pip_div(det[i], g);
+        dppiv = pip_div(dppiv, g);
+      }
+      if (status == PIP_ST_OK && dppiv != 1) status = PIP_ST_FATAL + 1;
+      if (status == PIP_ST_OK) {
+        int i = 0;
+        const int bp = pip_bitlen(ppivot);
+        for (; i < ldet; i++)
+          if (pip_bitlen(det[i]) + bp < 64) { det[i] = (pip_i64)((pip_u64)det[i] * (pip_u64)ppivot); break; }
+        if (i >= ldet) {
+          ldet++;
+          if (ldet >= PIP_MAX_DET) status = PIP_ST_FATAL + 1;
+          else det[i] = ppivot;
+        }
+        L.ctl[PIPL_LDET] = ldet;
+      }
+    }
+    L.ctl64[0] = pivot; L.ctl64[1] = dpiv;
+    L.ctl[PIPL_PIVI] = pivi; L.ctl[PIPL_PIVJ] = pivj;
+    L.ctl[PIPL_STATUS] = status;
+    L.ctl[PIPL_ACTION] = status == PIP_ST_OK ? PIPL_GO : PIPL_STOP;
+    if (status == PIP_ST_OK) L.ctl[PIPL_PIVOTS] = L.ctl[PIPL_PIVOTS] + 1;
+  }
+}
+
+/* ---- phase C: every warp of the grid updates rows -------------------------------------------- */
+PIP_DEV void pipl_phase_c(const PipLarge &L, unsigned &skipped)
+{
+  const int lane = W::lane();
+  const int wpc = G::T() >> 5;
+  const int gw = G::cta() * wpc + (G::tid() >> 5), nw = G::ncta() * wpc;
+  const int nvar = L.nvar, ncol = nvar + 1, nl = nvar + L.ctl[PIPL_NI];
+  const int pivi = L.ctl[PIPL_PIVI], pivj = L.ctl[PIPL_PIVJ];
+  const pip_i64 pivot = L.ctl64[0], dpiv = L.ctl64[1];
+  const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
+  for (int k = gw; k < nl; k += nw) {
+    if (k == pivi) continue;
+    const int f = L.fl[k];
+    if (f & PIP_UNIT) continue;
+    pip_i64 *row = pipl_row(L, PIP_LINK(f));
+    pip_i64 foo = row[pivj];
+    const pip_i64 dk = L.den[k];
+    W::sync();                          /* every lane has read foo before pass 1 overwrites row[pivj] */
+    if (foo == 0 && dk == 1) { skipped++; continue; }
+    pip_i64 lpiv = pivot;
+    if (foo == 0) lpiv = 1;
+    else if (pivot != 1 && foo != 1 && foo != -1) {
+      const pip_i64 d = pip_gcd(pivot, foo);
+      if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
+    }
+    const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
+    pip_u64 orz = 0;
+    /* pass 1: z = row*lpiv - prow*foo, two words per lane per step (16-byte accesses) */
+    const int pairs = ncol >> 1;
+    pip_i64x2 *row2 = (pip_i64x2 *)row;
+    const pip_i64x2 *prow2 = (const pip_i64x2 *)prow;
+    #pragma unroll 4
+    for (int q = lane; q < pairs; q += 32) {
+      const pip_i64x2 a = row2[q], b = prow2[q];
+      pip_i64x2 z;
+      z.x = (pip_i64)((pip_u64)a.x * (pip_u64)lpiv - (pip_u64)b.x * (pip_u64)foo);
+      z.y = (pip_i64)((pip_u64)a.y * (pip_u64)lpiv - (pip_u64)b.y * (pip_u64)foo);
+      row2[q] = z;
+      orz |= (pip_u64)z.x | (pip_u64)z.y;
+    }
+    if ((ncol & 1) && lane == 0) {
+      const int j = ncol - 1;
+      const pip_i64 z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
+      row[j] = z;
+      orz |= (pip_u64)z;
+    }
+    W::sync();
+    const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
+    if (lane == 0) row[pivj] = zp;
+    orz |= (pip_u64)zp;
+    W::sync();
+    pip_i64 g = newden;
+    if (g != 1) {
+      if ((g & (g - 1)) == 0 && g > 0) {
+        orz |= (pip_u64)g;
+        const unsigned lo = W::redor((unsigned)orz), hi = W::redor((unsigned)(orz >> 32));
+        const pip_u64 all = ((pip_u64)hi << 32) | lo;
+        g = (pip_i64)(all & (0ull - all));
+      } else {
+        for (int j = lane; j < ncol && g != 1; j += 32) g = pip_gcd(g, row[j]);
+        for (int o = 16; o > 0; o >>= 1) g = pip_gcd(g, W::shfl_xor64(g, o));
+      }
+    }
+    pip_i64 nd = newden;
+    if (g != 1 && g != 0) {
+      const PipExactDiv e = pip_exact_prepare(g);
+      for (int j = lane; j < ncol; j += 32) row[j] = pip_exact_apply(row[j], e);
+      nd = pip_exact_apply(newden, e);
+      W::sync();
+    }
+    if (lane == 0) {
+      L.den[k] = nd;
+      const pip_i64 c = row[nvar];
+      L.csign[k] = c < 0 ? -1 : c > 0 ? 1 : 0;
+      int ff = PIP_FLAG(f);
+      const int fff = zp < 0 ? PIP_MINUS : zp == 0 ? PIP_ZERO : PIP_PLUS;
+      if (fff != PIP_ZERO && fff != ff) {
+        if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
+        else ff = PIP_UNKNOWN;
+        L.fl[k] = PIP_MKFL(ff, PIP_LINK(f));
+      }
+      if (g == 0) L.ctl[PIPL_STATUS] = PIP_ST_FAULT;
+    }
+  }
+}
+
+/* ---- the whole solve (called by every thread of the cooperative grid) ------------------------ */
+PIP_DEV void pipl_init_rows(const PipLarge &L, float *sz);
+PIP_DEV void pipl_sort(const PipLarge &L, float *sz, int *red);
+
+PIP_DEV void pipl_solve(const PipLarge &L, int *red)
+{
+  unsigned skipped = 0;
+  bool first = true;
+  float *sz = (float *)L.cand;                 /* scratch: pcap floats fit (cand has pcap ints) */
+  pipl_init_rows(L, sz);
+  G::grid_sync();
+  if (G::cta() == 0) pipl_sort(L, sz, red);
+  for (;;) {
+    if (G::cta() == 0) pipl_phase_ab(L, red, first);
+    first = false;
+    G::grid_sync();
+    if (L.ctl[PIPL_ACTION] == PIPL_STOP) break;
+    pipl_phase_c(L, skipped);
+    G::grid_sync();
+    if (L.ctl[PIPL_STATUS] != PIP_ST_OK) break;
+  }
+  if (W::lane() == 0 && skipped) G::atomic_add_u(&((unsigned *)L.ctl)[PIPL_SKIPPED_LO], skipped);
+}
+
+/* entry of traiter for the large problem: flags, tab_simplify (source/tab.c:396-427) and the
+ * row "size" of tab_sort_rows, one warp per row across the whole grid */
+PIP_DEV void pipl_init_rows(const PipLarge &L, float *sz)
+{
+  const int lane = W::lane();
+  const int wpc = G::T() >> 5;
+  const int gw = G::cta() * wpc + (G::tid() >> 5), nw = G::ncta() * wpc;
+  const int nvar = L.nvar, ni = L.ctl[PIPL_NI], ncol = nvar + 1;
+  for (int k = gw; k < nvar + ni; k += nw) {
+    if (k < nvar) { if (lane == 0) { L.fl[k] = PIP_MKFL(PIP_UNIT, k); L.den[k] = 1; L.csign[k] = 0; sz[k] = 0.f; } continue; }
+    pip_i64 *row = pipl_row(L, k - nvar);
+    if (L.flags & PIP_F_INT) {
+      pip_i64 g = 0;
+      for (int j = lane; j < nvar && g != 1; j += 32) g = pip_gcd(g, row[j]);
+      for (int o = 16; o > 0; o >>= 1) g = pip_gcd(g, W::shfl_xor64(g, o));
+      if (g != 0 && g != 1) {
+        for (int j = lane; j < ncol; j += 32) row[j] = (j == nvar) ? pip_floor_q(row[j], g) : pip_div(row[j], g);
+        W::sync();
+      }
+    }
+    unsigned s = 0;
+    for (int j = lane; j < nvar; j += 32) {
+      const pip_u64 u = pip_uabs(row[j]);
+      if (u < 2147483648ull && (unsigned)u > s) s = (unsigned)u;
+    }
+    s = W::redmax(s);
+    if (lane == 0) {
+      const pip_i64 c = row[nvar];
+      L.fl[k] = PIP_MKFL(PIP_UNKNOWN, k - nvar); L.den[k] = 1;
+      L.csign[k] = c < 0 ? -1 : c > 0 ? 1 : 0;
+      sz[k] = (float)(double)s;
+    }
+  }
+}
+
+/* tab_sort_rows_xx (source/traiter.c:591-614) by CTA 0: selection sort of the position records by
+ * first minimum strictly below the maximum; nothing to do when no size is below the maximum */
+PIP_DEV void pipl_sort(const PipLarge &L, float *sz, int *red)
+{
+  const int tid = G::tid(), T = G::T();
+  const int nvar = L.nvar, nl = nvar + L.ctl[PIPL_NI];
+  int mx = 0;
+  for (int k = nvar + tid; k < nl; k += T) { const int b = (int)pip_f2u(sz[k]); if (b > mx) mx = b; }
+  const int smax_bits = pipl_cta_max(mx, red);       /* sizes are non-negative floats: bit order = value order */
+  const double smax = (double)pip_u2f((unsigned)smax_bits);
+  for (int i = nvar; i < nl; i++) {
+    int best = PIPL_INF, bestk = PIPL_INF;
+    for (int k = i + tid; k < nl; k += T) {
+      const float s = sz[k];
+      if ((double)s < smax) {
+        const int b = (int)pip_f2u(s);
+        if (b < best) { best = b; bestk = k; }        /* ascending k per thread keeps the first */
+      }
+    }
+    const int m = pipl_cta_min(best, red);
+    if (m == PIPL_INF) break;                          /* no candidate left for any later i */
+    const int src = pipl_cta_min(best == m ? bestk : PIPL_INF, red);
+    if (src != i && tid == 0) {
+      const int f = L.fl[i]; L.fl[i] = L.fl[src]; L.fl[src] = f;
+      const pip_i64 d = L.den[i]; L.den[i] = L.den[src]; L.den[src] = d;
+      const signed char c = L.csign[i]; L.csign[i] = L.csign[src]; L.csign[src] = c;
+      const float s = sz[i]; sz[i] = sz[src]; sz[src] = s;
+    }
+    G::cta_sync();
+  }
+}
+
+#endif

@@ -31,9 +31,6 @@
 #include "pip_types.h"
 #include "simt.h"
 
-#define PIP_FLAG(x) ((x) & 0xff)
-#define PIP_LINK(x) ((x) >> 8)
-#define PIP_MKFL(f, l) ((f) | ((l) << 8))
 
 struct PipTab {          /* warp-uniform, lives in registers */
   int den, fl, data, det;   /* word offsets into the arena */

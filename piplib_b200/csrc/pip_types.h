@@ -15,6 +15,10 @@ typedef unsigned long long pip_u64;
 
 /* row flags */
 enum { PIP_UNIT = 1, PIP_PLUS = 2, PIP_MINUS = 4, PIP_ZERO = 8, PIP_CRITIC = 16, PIP_UNKNOWN = 32 };
+/* packed position word: flag | link << 8 (link = unit column or storage slot) */
+#define PIP_FLAG(x) ((x) & 0xff)
+#define PIP_LINK(x) ((x) >> 8)
+#define PIP_MKFL(f, l) ((f) | ((l) << 8))
 /* cell kinds */
 enum { PIP_C_FREE = 0, PIP_C_NIL = 1, PIP_C_IF = 2, PIP_C_LIST = 3, PIP_C_FORM = 4, PIP_C_NEW = 5,
        PIP_C_DIV = 6, PIP_C_VAL = 7, PIP_C_ERROR = 8 };

@@ -37,8 +37,23 @@ struct W {
   static inline int shfl_up(int v, int d) { int l = pipemu::lane(); int r = (int)pipemu::shfl64(v, l >= d ? l - d : l); return r; }
   static inline unsigned redmin(unsigned v) { return pipemu::redmin(v); }
   static inline unsigned redmax(unsigned v) { return pipemu::redmax(v); }
+  static inline unsigned redor(unsigned v) { unsigned r = 0; for (int b = 0; b < 32; b++) if (pipemu::ballot((v >> b) & 1u)) r |= 1u << b; return r; }
+  static inline int shfl_down(int v, int d) { int l = pipemu::lane(); return (int)pipemu::shfl64(v, l + d < 32 ? l + d : l); }
+  static inline long long shfl_xor64(long long v, int m) { return pipemu::shfl64(v, pipemu::lane() ^ m); }
   static inline unsigned atomic_add(unsigned *p, unsigned v) { return pipemu::atomic_add(p, v); }
 };
+
+/* CTA / grid abstraction of the large-tableau kernel: in emulation one CTA of one warp */
+struct G {
+  static inline int tid() { return pipemu::lane(); }
+  static inline int T() { return 32; }
+  static inline int cta() { return 0; }
+  static inline int ncta() { return 1; }
+  static inline void cta_sync() { pipemu::barrier(); }
+  static inline void grid_sync() { pipemu::barrier(); }
+  static inline unsigned atomic_add_u(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+};
+struct pip_i64x2 { long long x, y; };
 
 static inline int pip_ffs(unsigned m) { return __builtin_ffs((int)m); }
 static inline int pip_popc(unsigned m) { return __builtin_popcount(m); }
@@ -54,7 +69,7 @@ static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); 
 #define PIP_DEV __device__ __forceinline__
 #define PIP_DEVNI __device__ __noinline__
 #define PIP_HD __host__ __device__ __forceinline__
-#define PIP_HDNI __host__ __device__ __noinline__
+#define PIP_HDNI static __host__ __device__ __noinline__
 #define PIP_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 
 struct W {
@@ -67,8 +82,22 @@ struct W {
   static __device__ __forceinline__ int shfl_up(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
   static __device__ __forceinline__ unsigned redmin(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
   static __device__ __forceinline__ unsigned redmax(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+  static __device__ __forceinline__ unsigned redor(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
+  static __device__ __forceinline__ int shfl_down(int v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+  static __device__ __forceinline__ long long shfl_xor64(long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
   static __device__ __forceinline__ unsigned atomic_add(unsigned *p, unsigned v) { return atomicAdd(p, v); }
 };
+
+struct G {
+  static __device__ __forceinline__ int tid() { return (int)threadIdx.x; }
+  static __device__ __forceinline__ int T() { return (int)blockDim.x; }
+  static __device__ __forceinline__ int cta() { return (int)blockIdx.x; }
+  static __device__ __forceinline__ int ncta() { return (int)gridDim.x; }
+  static __device__ __forceinline__ void cta_sync() { __syncthreads(); }
+  static __device__ void grid_sync();      /* cooperative groups, defined in pip_large.cu */
+  static __device__ __forceinline__ unsigned atomic_add_u(unsigned *p, unsigned v) { return atomicAdd(p, v); }
+};
+struct __align__(16) pip_i64x2 { long long x, y; };
 
 static __device__ __forceinline__ int pip_ffs(unsigned m) { return __ffs((int)m); }
 static __device__ __forceinline__ int pip_popc(unsigned m) { return __popc(m); }

@@ -84,6 +84,23 @@ def loopnest(n, seed=2026, nvar=16, nrows=24, nparm=3, first=0, p2=0.05, p3=0.05
     return np.ascontiguousarray(np.concatenate(doms)), np.ascontiguousarray(np.concatenate(ctxs))
 
 
+def consecutive_ones(nvar, nrows, seed=2026, cmax=50):
+    """BASELINE config 4: one large tableau whose rows have the consecutive-ones property
+    (sum_{j=a..b} x_j >= c): totally unimodular, so entries stay small through hundreds of pivots
+    (dense random data overflows int64 within a few).  Returns the .dat-order tableau
+    [nrows, nvar+1] = [coefficients | constant]."""
+    rng = _rng(seed, 1 << 20)
+    a = rng.integers(0, nvar, size=nrows)
+    b = rng.integers(0, nvar, size=nrows)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    c = rng.integers(1, cmax + 1, size=nrows)
+    j = np.arange(nvar)[None, :]
+    tab = np.zeros((nrows, nvar + 1), dtype=np.int64)
+    tab[:, :nvar] = ((j >= lo[:, None]) & (j <= hi[:, None])).astype(np.int64)
+    tab[:, nvar] = -c
+    return tab
+
+
 WORKLOADS = {
     "loopnest16x24p3": dict(fn=loopnest, kw=dict(nvar=16, nrows=24, nparm=3)),
     "loopnest8x12p2": dict(fn=loopnest, kw=dict(nvar=8, nrows=12, nparm=2)),

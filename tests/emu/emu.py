@@ -14,7 +14,7 @@ SO = os.path.join(HERE, "libpipemu.so")
 def build():
     srcs = [os.path.join(HERE, f) for f in ("emu_runtime.cpp", "emu_driver.cpp")]
     subprocess.check_call(["g++", "-O2", "-g", "-fwrapv", "-DPIP_EMU", "-fPIC", "-shared", "-Wall",
-                           "-Wno-unused-function"] + srcs + ["-o", SO])
+                           "-Wno-unused-function", "-Wno-unknown-pragmas"] + srcs + ["-o", SO])
 
 
 def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_level=2, order_mode=0,
@@ -35,3 +35,19 @@ def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_le
         c = cells[r["cell_off"]:r["cell_off"] + r["ncells"]]
         out.append((int(r["status"]), [[int(x["kind"]), int(x["p1"]), int(x["p2"])] for x in c], r))
     return out
+
+
+def solve_large(case, cut_rows=64, sol_size=0, maxcol=0, order_mode=0):
+    """one non-parametric problem through the grid-per-problem code path (one emulated CTA)"""
+    assert case["nparm"] == 0
+    lib = C.CDLL(SO)
+    tab = np.ascontiguousarray(np.asarray(case["tab"], dtype=np.int64).reshape(-1))
+    cap = max(sol_size, 4096) + 8
+    cells = np.zeros(cap, dtype=CELL_DTYPE)
+    st, nc = C.c_int(0), C.c_int(0)
+    info = (C.c_longlong * 4)()
+    lib.pipemu_solve_large(case["nvar"], case["ni"], case["nq"], tab.ctypes.data_as(C.c_void_p), cut_rows,
+                           sol_size, maxcol, C.byref(st), cells.ctypes.data_as(C.c_void_p), C.byref(nc),
+                           info, order_mode)
+    c = cells[:nc.value]
+    return st.value, [[int(x["kind"]), int(x["p1"]), int(x["p2"])] for x in c], list(info)

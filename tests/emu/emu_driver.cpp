@@ -40,3 +40,46 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
   free(e.L.stack);
   return 0;
 }
+
+// ---- large-tableau solver in emulation: one CTA of one warp ---------------------------------
+#include "../../piplib_b200/csrc/pip_large.h"
+
+struct EmuLarge { PipLarge L; int red[64]; };
+static void large_entry(void *a, int) { EmuLarge *e = (EmuLarge *)a; pipl_solve(e->L, e->red); }
+
+extern "C" int pipemu_solve_large(int nvar, int ni, int nq, const pip_i64 *tab, int cut_rows, int sol_size,
+                                  int maxcol, int *status, PipCell *cells, int *ncells, long long *info,
+                                  int order_mode)
+{
+  EmuLarge e;
+  PipLarge &L = e.L;
+  memset(&e, 0, sizeof e);
+  const int ncol = nvar + 1;
+  L.nvar = nvar; L.ni = ni; L.flags = nq ? PIP_F_INT : 0;
+  L.stride = (ncol + 1) & ~1;
+  L.rcap = ni + cut_rows; L.pcap = nvar + L.rcap;
+  L.sol_size = sol_size > 0 ? sol_size : PIP_SOL_SIZE;
+  L.maxcol = maxcol > 0 ? maxcol : PIP_MAXCOL;
+  L.data = (pip_i64 *)calloc((size_t)L.rcap * L.stride + 2, 8);
+  for (int r = 0; r < ni; r++) memcpy(L.data + (size_t)r * L.stride, tab + (size_t)r * ncol, 8 * (size_t)ncol);
+  L.den = (pip_i64 *)calloc(L.pcap + 1, 8);
+  L.fl = (int *)calloc(L.pcap + 1, 4);
+  L.csign = (signed char *)calloc(L.pcap + 1, 1);
+  L.cand = (int *)calloc((L.pcap > nvar ? L.pcap : nvar) + 4, 4);
+  L.member = (unsigned char *)calloc(nvar + 16, 1);
+  L.cut = (pip_i64 *)calloc(L.stride + 2, 8);
+  int ctl[PIPL_NCTL] = {0};
+  pip_i64 ctl64[8] = {0};
+  ctl[PIPL_NI] = ni; ctl[PIPL_LDET] = 1; ctl64[2] = 1;
+  L.ctl = ctl; L.ctl64 = ctl64;
+  L.cells = cells;
+  unsigned long long prof[8] = {0};
+  L.prof = prof;
+  pipemu::set_order(order_mode);
+  pipemu::run_warp(large_entry, &e);
+  *status = ctl[PIPL_STATUS];
+  *ncells = ctl[PIPL_NCELL];
+  if (info) { info[0] = ctl[PIPL_PIVOTS]; info[1] = ctl[PIPL_CUTS]; info[2] = (unsigned)ctl[PIPL_SKIPPED_LO]; info[3] = ctl[PIPL_NI]; }
+  free(L.data); free(L.den); free(L.fl); free(L.csign); free(L.cand); free(L.member); free(L.cut);
+  return 0;
+}

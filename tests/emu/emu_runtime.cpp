@@ -7,6 +7,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef PIPEMU_TRACE
+#include <execinfo.h>
+#endif
 
 namespace pipemu {
 
@@ -60,46 +63,69 @@ static void trampoline()
 
 int lane() { return cur; }
 
-void barrier()
+static int tags[NL];
+#ifdef PIPEMU_TRACE
+static void *bt[NL][12];
+static int btn[NL];
+#endif
+static void barrier_tag(int tag)
 {
+#ifdef PIPEMU_TRACE
+  btn[cur] = backtrace(bt[cur], 12);
+#endif
+  // every lane must be at the same kind of collective: a mismatch is divergent control flow
+  // around a collective in the device source (undefined behaviour on the GPU)
+  tags[cur] = tag;
   unsigned g = gen;
-  if (++arrived == NL) { arrived = 0; gen++; }
+  if (++arrived == NL) {
+    for (int i = 0; i < NL; i++)
+      if (tags[i] != tag) {
+        fprintf(stderr, "pipemu: divergent collective: lane %d at kind %d, lane %d at kind %d\n", cur, tag, i, tags[i]);
+#ifdef PIPEMU_TRACE
+        fprintf(stderr, "--- lane %d\n", cur); backtrace_symbols_fd(bt[cur], btn[cur], 2);
+        fprintf(stderr, "--- lane %d\n", i); backtrace_symbols_fd(bt[i], btn[i], 2);
+#endif
+        abort();
+      }
+    arrived = 0; gen++;
+  }
   else while (gen == g) yield_to_sched();
 }
+void barrier() { barrier_tag(1); }
 
 unsigned ballot(bool p)
 {
   xch[cur] = p ? 1 : 0;
-  barrier();
+  barrier_tag(2);
   unsigned m = 0;
   for (int i = 0; i < NL; i++) if (xch[i]) m |= 1u << i;
-  barrier();
+  barrier_tag(2);
   return m;
 }
 long long shfl64(long long v, int src)
 {
   xch[cur] = v;
-  barrier();
+  barrier_tag(3);
   long long r = xch[src & 31];
-  barrier();
+  barrier_tag(3);
   return r;
 }
 unsigned redmin(unsigned v)
 {
   xch[cur] = v;
-  barrier();
+  barrier_tag(4);
   unsigned m = 0xffffffffu;
   for (int i = 0; i < NL; i++) if ((unsigned)xch[i] < m) m = (unsigned)xch[i];
-  barrier();
+  barrier_tag(4);
   return m;
 }
 unsigned redmax(unsigned v)
 {
   xch[cur] = v;
-  barrier();
+  barrier_tag(5);
   unsigned m = 0;
   for (int i = 0; i < NL; i++) if ((unsigned)xch[i] > m) m = (unsigned)xch[i];
-  barrier();
+  barrier_tag(5);
   return m;
 }
 unsigned atomic_add(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }

@@ -148,3 +148,36 @@ def test_device_resident_batch(api, port):
     r = api.solve_dense(dom, ctx, -1)
     assert ms > 0 and np.array_equal(st, r["status"]) and np.array_equal(h, r["hashes"])
     db.close()
+
+
+def test_large_tableau_kernel_fixtures(api):
+    """grid-per-problem cooperative kernel on every non-parametric fixture (incl. 260 cuts)"""
+    cases = [c for c in load_golden("cli_suite.json")
+             if c["nparm"] == 0 and c["nc"] == 0 and "sysmo" not in c["name"]]
+    cases += [c for c in RCLI if c["nparm"] == 0 and c["nc"] == 0][:40]
+    bad = []
+    for c in cases:
+        p = api.LargeProblem(c["nvar"], c["ni"], c["nq"], c["tab"], cut_rows=400)
+        p.run()
+        st, cells, info = p.fetch()
+        p.close()
+        if st != c["ref_status"] or cells != c["ref_cells"]:
+            bad.append((c["name"], st, c["ref_status"], len(cells), len(c["ref_cells"])))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("n", [256, 768])
+def test_large_tableau_consecutive_ones(api, port, n):
+    """config-4 shaped problem (totally unimodular rows) vs the oracle with raised limits"""
+    from piplib_b200 import synth
+    tab = synth.consecutive_ones(n, n, seed=11)
+    st_o, cells_o = port.traiter(n, 0, n, 0, -1, 1, tab, [], sol_size=1 << 16, maxcol=1 << 14)
+    p = api.LargeProblem(n, n, 1, tab, cut_rows=256, sol_size=1 << 16, maxcol=1 << 14)
+    ms = p.run()
+    st, cells, info = p.fetch()
+    ms2 = p.run()                                   # the run is repeatable (tableau restored)
+    st2, cells2, _ = p.fetch()
+    p.close()
+    assert ms > 0 and ms2 > 0
+    assert st == st_o and [tuple(x) for x in cells] == cells_o
+    assert (st2, cells2) == (st, cells) and info["pivots"] > 0
