@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(PIPL_THREADS) pip_large_kernel(const PipLarge 
 }
 
 /* restore the working tableau from the pristine copy and reset the control block */
-__global__ void pip_large_reset_kernel(pip_i64 *dst, const pip_i64 *src, size_t words, int *ctl, pip_i64 *ctl64, int ni)
+__global__ void pip_large_reset_kernel(pip_i64 *dst, const pip_i64 *src, size_t words, int *ctl, pip_i64 *ctl64, int ni,
+                                       unsigned long long *prof)
 {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
   for (size_t i = i0; i < words; i += step) dst[i] = src[i];
@@ -33,6 +34,7 @@ __global__ void pip_large_reset_kernel(pip_i64 *dst, const pip_i64 *src, size_t 
     ctl[PIPL_NI] = ni; ctl[PIPL_LDET] = 1; ctl[PIPL_STATUS] = PIP_ST_OK;
     for (int k = 0; k < 8; k++) ctl64[k] = 0;
     ctl64[2] = 1;
+    prof[0] = prof[1] = 0;
   }
 }
 
@@ -104,7 +106,7 @@ int pip_large_run_dp(pip_large_problem *P, float *kernel_ms)
 {
   try {
     const size_t used = (size_t)P->ni0 * P->L.stride;
-    pip_large_reset_kernel<<<1024, 256, 0, P->stream>>>(P->L.data, P->pristine, used, P->L.ctl, P->L.ctl64, P->ni0);
+    pip_large_reset_kernel<<<1024, 256, 0, P->stream>>>(P->L.data, P->pristine, used, P->L.ctl, P->L.ctl64, P->ni0, P->L.prof);
     CKL(cudaGetLastError());
     void *args[] = {(void *)&P->L};
     CKL(cudaEventRecord(P->e0, P->stream));
@@ -127,7 +129,12 @@ int pip_large_fetch_dp(pip_large_problem *P, int *status, PipCell_dp *cells, int
     CKL(cudaMemcpy(ctl, P->L.ctl, sizeof ctl, cudaMemcpyDeviceToHost));
     *status = ctl[PIPL_STATUS];
     *ncells = ctl[PIPL_NCELL];
-    if (info) { info[0] = ctl[PIPL_PIVOTS]; info[1] = ctl[PIPL_CUTS]; info[2] = (unsigned)ctl[PIPL_SKIPPED_LO]; info[3] = ctl[PIPL_NI]; }
+    if (info) {
+      unsigned long long prof[2];
+      CKL(cudaMemcpy(prof, P->L.prof, sizeof prof, cudaMemcpyDeviceToHost));
+      info[0] = ctl[PIPL_PIVOTS]; info[1] = ctl[PIPL_CUTS]; info[2] = (unsigned)ctl[PIPL_SKIPPED_LO]; info[3] = ctl[PIPL_NI];
+      info[4] = (long long)prof[0]; info[5] = (long long)prof[1];
+    }
     if (cells && *ncells > 0 && *ncells <= cell_cap)
       CKL(cudaMemcpy(cells, P->L.cells, sizeof(PipCell) * (size_t)*ncells, cudaMemcpyDeviceToHost));
   } catch (const std::exception &e) {

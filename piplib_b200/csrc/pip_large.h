@@ -266,46 +266,32 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
   if (ncand == 0) { pipl_finish(L, PIP_ST_OK, 1); return; }
   int k = 0;
   while (ncand > 1 && k < nl) {
+    /* one window of T positions: Unit positions strike their own column off the candidate set;
+     * the first stored row of the window filters the set to its minimal ratio (whole CTA) */
     const int p = k + tid;
-
-    int kind = 0;
-    if (p < nl) {
-      const int f = L.fl[p];
-      if (f & PIP_UNIT) { if (PIP_LINK(f) < nvar && L.member[PIP_LINK(f)]) kind = 1; }
-      else {
-        const pip_i64 *row = pipl_row(L, PIP_LINK(f));
-        const int j0 = L.cand[0];
-        const pip_i64 a0 = row[j0], b0 = prow[j0];
-        for (int m = 1; m < ncand; m++) {
-          const int j = L.cand[m];
-          if (pipl_ratio_cmp(row[j], prow[j], a0, b0) != 0) { kind = 2; break; }
-        }
-      }
-    }
-    const int pstar = pipl_cta_min(kind == 2 ? p : PIPL_INF, red);
-    const bool mine = kind == 1 && p < pstar;
+    const int f = p < nl ? L.fl[p] : PIP_UNIT;
+    const bool stored = p < nl && !(f & PIP_UNIT);
+    const int pnu = pipl_cta_min(stored ? p : PIPL_INF, red);
+    const bool mine = p < nl && p < pnu && (f & PIP_UNIT) && PIP_LINK(f) < nvar && L.member[PIP_LINK(f)];
     const int nelim = pipl_cta_sum(mine ? 1 : 0, red);
     if (nelim >= ncand) {
       /* every remaining candidate's Unit row lies in this run: the last one survives */
       const int pmax = pipl_cta_max(mine ? p : -1, red);
-      if (mine && p != pmax) L.member[PIP_LINK(L.fl[p])] = 0;
+      if (mine && p != pmax) L.member[PIP_LINK(f)] = 0;
       G::cta_sync();
       ncand = 1;
       break;
     }
-    if (mine) L.member[PIP_LINK(L.fl[p])] = 0;
+    if (mine) L.member[PIP_LINK(f)] = 0;
     G::cta_sync();
     if (nelim) ncand = pipl_compact(L, red, 0);
-    if (pstar < PIPL_INF) {
-      /* keep the candidates with the minimal ratio at row pstar */
-      const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pstar]));
-      /* every thread finds the minimum over its share, then the CTA reduces by index of the best */
+    if (pnu < PIPL_INF) {
+      const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pnu]));
       int best = -1;
       for (int m = tid; m < ncand; m += T) {
         const int j = L.cand[m];
         if (best < 0 || pipl_ratio_cmp(row[j], prow[j], row[best], prow[best]) < 0) best = j;
       }
-      /* tournament across threads through the candidate indices in shared scratch */
       int winner = best;
       {
         const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
@@ -323,13 +309,15 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
           if (o >= 0 && (winner < 0 || pipl_ratio_cmp(row[o], prow[o], row[winner], prow[winner]) < 0)) winner = o;
         }
       }
+      int removed = 0;
       for (int m = tid; m < ncand; m += T) {
         const int j = L.cand[m];
-        if (pipl_ratio_cmp(row[j], prow[j], row[winner], prow[winner]) != 0) L.member[j] = 0;
+        if (pipl_ratio_cmp(row[j], prow[j], row[winner], prow[winner]) != 0) { L.member[j] = 0; removed++; }
       }
+      removed = pipl_cta_sum(removed, red);
       G::cta_sync();
-      ncand = pipl_compact(L, red, 0);
-      k = pstar + 1;
+      if (removed) ncand = pipl_compact(L, red, 0);
+      k = pnu + 1;
     } else k += T;
   }
   /* the survivor (smallest column if, against the theory, several remain) */
@@ -474,13 +462,18 @@ PIP_DEV void pipl_solve(const PipLarge &L, int *red)
   pipl_init_rows(L, sz);
   G::grid_sync();
   if (G::cta() == 0) pipl_sort(L, sz, red);
+  long long t0 = pip_clock();
   for (;;) {
     if (G::cta() == 0) pipl_phase_ab(L, red, first);
     first = false;
     G::grid_sync();
+    const long long t1 = pip_clock();
     if (L.ctl[PIPL_ACTION] == PIPL_STOP) break;
     pipl_phase_c(L, skipped);
     G::grid_sync();
+    const long long t2 = pip_clock();
+    if (G::cta() == 0 && G::tid() == 0) { L.prof[0] += (unsigned long long)(t1 - t0); L.prof[1] += (unsigned long long)(t2 - t1); }
+    t0 = t2;
     if (L.ctl[PIPL_STATUS] != PIP_ST_OK) break;
   }
   if (W::lane() == 0 && skipped) G::atomic_add_u(&((unsigned *)L.ctl)[PIPL_SKIPPED_LO], skipped);

@@ -61,6 +61,7 @@ static inline int pip_clzll(unsigned long long v) { return v ? __builtin_clzll(v
 static inline int pip_ctzll(unsigned long long v) { return v ? __builtin_ctzll(v) : 64; }
 static inline long long pip_mulhi(long long a, long long b) { return (long long)(((__int128)a * b) >> 64); }
 static inline double pip_ll2d(long long v) { return (double)v; }
+static inline long long pip_clock() { return 0; }
 static inline unsigned pip_f2u(float f) { unsigned u; __builtin_memcpy(&u, &f, 4); return u; }
 static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
 
@@ -105,6 +106,7 @@ static __device__ __forceinline__ int pip_clzll(unsigned long long v) { return _
 static __device__ __forceinline__ int pip_ctzll(unsigned long long v) { return v ? __ffsll((long long)v) - 1 : 64; }
 static __device__ __forceinline__ long long pip_mulhi(long long a, long long b) { return __mul64hi(a, b); }
 static __device__ __forceinline__ double pip_ll2d(long long v) { return __ll2double_rn(v); }
+static __device__ __forceinline__ long long pip_clock() { return clock64(); }
 static __device__ __forceinline__ unsigned pip_f2u(float f) { return __float_as_uint(f); }
 static __device__ __forceinline__ float pip_u2f(unsigned u) { return __uint_as_float(u); }
 

@@ -17,9 +17,11 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 check = "--no-check" not in sys.argv
 tab = synth.consecutive_ones(n, n, seed=2026)
 p = api.LargeProblem(n, n, 1, tab, cut_rows=1024, sol_size=1 << 20, maxcol=1 << 16)
-for _ in range(2):
-    p.run()
-ms = [p.run() for _ in range(reps)]
+print("warm %.3f ms" % p.run(), flush=True)
+ms = []
+for _ in range(reps):
+    ms.append(p.run())
+    print("run %.3f ms" % ms[-1], flush=True)
 st, cells, info = p.fetch()
 p.close()
 best = float(np.median(ms))
@@ -34,7 +36,9 @@ if os.path.exists(pk):
     src = "measured"
 line = {"workload": "consecutive-ones %d x %d int64, Nq=1" % (n, n + 1), "status": st, "pivots": piv,
         "cuts": info["cuts"], "skipped_identity_rows": info["skipped_rows"], "kernel_ms": best,
-        "us_per_pivot": 1e3 * best / max(piv, 1), "pivots_per_sec": piv / (best / 1e3),
+        "us_per_pivot": 1e3 * best / max(piv, 1),
+        "phase_share": {"choice": info["cycles_choice"] / max(1, info["cycles_choice"] + info["cycles_update"]),
+                        "update": info["cycles_update"] / max(1, info["cycles_choice"] + info["cycles_update"])}, "pivots_per_sec": piv / (best / 1e3),
         "roofline": {"bound": "hbm", "achieved": alg / (best / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (best / 1e3) / 1e9 / peak, "peak_source": src,
                      "note": "dense 16*R*C figure; rows whose update is the identity are skipped"}}
