@@ -19,7 +19,7 @@ __device__ void G::grid_sync() { cg::this_grid().sync(); }
 
 __global__ void __launch_bounds__(PIPL_THREADS) pip_large_kernel(const PipLarge L)
 {
-  __shared__ int red[64];
+  __shared__ __align__(16) int red[64];
   pipl_solve(L, red);
 }
 
@@ -75,6 +75,9 @@ pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long
     L.den = (pip_i64 *)dalloc((size_t)L.pcap * 8);
     L.fl = (int *)dalloc((size_t)L.pcap * 4);
     L.csign = (signed char *)dalloc((size_t)L.pcap);
+    L.colpos = (int *)dalloc((size_t)nvar * 4 + 16);
+    L.sbits = (unsigned *)dalloc((size_t)((L.pcap + 31) / 32) * 4 + 16);
+    L.active = (int *)dalloc((size_t)L.pcap * 4 + 16);
     L.cand = (int *)dalloc((size_t)(L.pcap > nvar ? L.pcap : nvar) * 4 + 16);
     L.member = (unsigned char *)dalloc((size_t)nvar + 16);
     L.cut = (pip_i64 *)dalloc((size_t)L.stride * 8);

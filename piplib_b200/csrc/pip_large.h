@@ -34,6 +34,9 @@ struct PipLarge {
   pip_i64 *den;                   /* [pcap] */
   int *fl;                        /* [pcap] flag | link << 8 */
   signed char *csign;             /* [pcap] sign of the constant column of each stored row */
+  int *colpos;                    /* [nvar] position of the Unit row that owns column j */
+  unsigned *sbits;                /* [(pcap+31)/32] bitmap of the stored (non-Unit) positions */
+  int *active;                    /* [pcap] positions whose update is not the identity, this pivot */
   /* scratch of phase AB */
   int *cand;                      /* [nvar] compact candidate list */
   unsigned char *member;          /* [nvar] */
@@ -45,7 +48,7 @@ struct PipLarge {
   unsigned long long *prof;       /* [8] cycle counters of CTA 0: AB, C, sync */
 };
 enum { PIPL_ACTION = 0, PIPL_PIVI, PIPL_PIVJ, PIPL_STATUS, PIPL_NCELL, PIPL_NI, PIPL_LDET, PIPL_PIVOTS,
-       PIPL_CUTS, PIPL_SKIPPED_LO, PIPL_SKIPPED_HI, PIPL_NCTL = 16 };
+       PIPL_CUTS, PIPL_SKIPPED_LO, PIPL_SKIPPED_HI, PIPL_NACTIVE, PIPL_NEXT, PIPL_NCTL = 16 };
 enum { PIPL_GO = 0, PIPL_STOP = 1 };
 
 /* ---- CTA-level helpers (shared scratch: int red[64]) ------------------------------------- */
@@ -178,6 +181,9 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
       L.fl[ku] = PIP_MKFL(PIP_PLUS, pslot); L.den[ku] = pivot;
       L.csign[ku] = c < 0 ? -1 : c > 0 ? 1 : 0;
       L.fl[pivi] = PIP_MKFL(PIP_UNIT | PIP_ZERO, pivj); L.den[pivi] = 1;
+      L.colpos[pivj] = pivi;
+      L.sbits[pivi >> 5] &= ~(1u << (pivi & 31));
+      L.sbits[ku >> 5] |= 1u << (ku & 31);
     }
     G::cta_sync();
   }
@@ -249,6 +255,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
         L.den[nl] = L.den[row_i];
         L.csign[nl] = L.cut[nvar] < 0 ? -1 : L.cut[nvar] > 0 ? 1 : 0;
         L.ctl[PIPL_NI] = ni + 1;
+        L.sbits[nl >> 5] |= 1u << (nl & 31);
         L.ctl[PIPL_CUTS] = L.ctl[PIPL_CUTS] + 1;
       }
       G::cta_sync();
@@ -258,67 +265,93 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     }
   }
 
-  /* ---- choisir_piv: candidate-set filtering over the positions -------------------------------- */
+  /* ---- choisir_piv (source/traiter.c:297-341) as candidate-set filtering in position order ----
+   * S = columns with a positive pivot-row entry.  Walking the positions in order, a Unit position
+   * strikes its own column off S (its ratio is 1/prow > 0 against 0 for everybody else) and a
+   * stored row keeps only the columns with the minimal ratio; the last column standing wins.
+   * Unit positions are never touched one by one: between two stored rows every member whose Unit
+   * position colpos[j] lies in the gap is struck at once (if that is all of S, the one with the
+   * largest colpos survives).  The loop therefore runs once per *stored* row met before the
+   * decision -- typically once or twice. */
   const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
   for (int j = tid; j < nvar; j += T) L.member[j] = prow[j] > 0 ? 1 : 0;
   G::cta_sync();
-  int ncand = pipl_compact(L, red, 0);
+  const int ncand0 = pipl_compact(L, red, 0);
+  int ncand = ncand0;
   if (ncand == 0) { pipl_finish(L, PIP_ST_OK, 1); return; }
   int k = 0;
-  while (ncand > 1 && k < nl) {
-    /* one window of T positions: Unit positions strike their own column off the candidate set;
-     * the first stored row of the window filters the set to its minimal ratio (whole CTA) */
-    const int p = k + tid;
-    const int f = p < nl ? L.fl[p] : PIP_UNIT;
-    const bool stored = p < nl && !(f & PIP_UNIT);
-    const int pnu = pipl_cta_min(stored ? p : PIPL_INF, red);
-    const bool mine = p < nl && p < pnu && (f & PIP_UNIT) && PIP_LINK(f) < nvar && L.member[PIP_LINK(f)];
-    const int nelim = pipl_cta_sum(mine ? 1 : 0, red);
-    if (nelim >= ncand) {
-      /* every remaining candidate's Unit row lies in this run: the last one survives */
-      const int pmax = pipl_cta_max(mine ? p : -1, red);
-      if (mine && p != pmax) L.member[PIP_LINK(f)] = 0;
+  const int nwords = (nl + 31) >> 5;
+  while (ncand > 1) {
+    /* next stored position >= k */
+    int c = PIPL_INF;
+    for (int w = (k >> 5) + tid; w < nwords; w += T) {
+      unsigned bits = L.sbits[w];
+      if (w == (k >> 5)) bits &= ~0u << (k & 31);
+      if (bits) { const int pp = (w << 5) + pip_ffs(bits) - 1; if (pp < nl && pp < c) c = pp; break; }
+    }
+    const int pst = pipl_cta_min(c, red);
+    /* strike the members whose Unit position lies in [k, pst) */
+    int nel = 0, umax = -1;
+    for (int m = tid; m < ncand0; m += T) {
+      const int j = L.cand[m];
+      if (!L.member[j]) continue;
+      const int u = L.colpos[j];
+      if (u < pst) { nel++; if (u > umax) umax = u; }
+    }
+    nel = pipl_cta_sum(nel, red);
+    if (nel >= ncand) {
+      umax = pipl_cta_max(umax, red);
+      for (int m = tid; m < ncand0; m += T) {
+        const int j = L.cand[m];
+        if (L.member[j] && L.colpos[j] != umax) L.member[j] = 0;
+      }
       G::cta_sync();
       ncand = 1;
       break;
     }
-    if (mine) L.member[PIP_LINK(f)] = 0;
-    G::cta_sync();
-    if (nelim) ncand = pipl_compact(L, red, 0);
-    if (pnu < PIPL_INF) {
-      const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pnu]));
-      int best = -1;
-      for (int m = tid; m < ncand; m += T) {
+    if (nel) {
+      for (int m = tid; m < ncand0; m += T) {
         const int j = L.cand[m];
-        if (best < 0 || pipl_ratio_cmp(row[j], prow[j], row[best], prow[best]) < 0) best = j;
+        if (L.member[j] && L.colpos[j] < pst) L.member[j] = 0;
       }
-      int winner = best;
-      {
-        const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
-        for (int o = 16; o > 0; o >>= 1) {
-          const int other = W::shfl_down(winner, o);
-          if (lane + o < 32 && other >= 0 && (winner < 0 || pipl_ratio_cmp(row[other], prow[other], row[winner], prow[winner]) < 0))
-            winner = other;
-        }
-        G::cta_sync();
-        if (lane == 0) red[wid] = winner;
-        G::cta_sync();
-        winner = -1;
-        for (int i = 0; i < nw; i++) {
-          const int o = red[i];
-          if (o >= 0 && (winner < 0 || pipl_ratio_cmp(row[o], prow[o], row[winner], prow[winner]) < 0)) winner = o;
-        }
-      }
-      int removed = 0;
-      for (int m = tid; m < ncand; m += T) {
-        const int j = L.cand[m];
-        if (pipl_ratio_cmp(row[j], prow[j], row[winner], prow[winner]) != 0) { L.member[j] = 0; removed++; }
-      }
-      removed = pipl_cta_sum(removed, red);
       G::cta_sync();
-      if (removed) ncand = pipl_compact(L, red, 0);
-      k = pnu + 1;
-    } else k += T;
+      ncand -= nel;
+    }
+    if (pst >= nl || ncand <= 1) break;
+    /* keep the members with the minimal ratio at the stored row pst */
+    const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
+    int best = -1;
+    for (int m = tid; m < ncand0; m += T) {
+      const int j = L.cand[m];
+      if (!L.member[j]) continue;
+      if (best < 0 || pipl_ratio_cmp(row[j], prow[j], row[best], prow[best]) < 0) best = j;
+    }
+    int winner = best;
+    {
+      const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+      for (int o = 16; o > 0; o >>= 1) {
+        const int other = W::shfl_down(winner, o);
+        if (lane + o < 32 && other >= 0 && (winner < 0 || pipl_ratio_cmp(row[other], prow[other], row[winner], prow[winner]) < 0))
+          winner = other;
+      }
+      G::cta_sync();
+      if (lane == 0) red[wid] = winner;
+      G::cta_sync();
+      winner = -1;
+      for (int i = 0; i < nw; i++) {
+        const int o = red[i];
+        if (o >= 0 && (winner < 0 || pipl_ratio_cmp(row[o], prow[o], row[winner], prow[winner]) < 0)) winner = o;
+      }
+    }
+    int removed = 0;
+    for (int m = tid; m < ncand0; m += T) {
+      const int j = L.cand[m];
+      if (L.member[j] && pipl_ratio_cmp(row[j], prow[j], row[winner], prow[winner]) != 0) { L.member[j] = 0; removed++; }
+    }
+    removed = pipl_cta_sum(removed, red);
+    G::cta_sync();
+    ncand -= removed;
+    k = pst + 1;
   }
   /* the survivor (smallest column if, against the theory, several remain) */
   int pj = PIPL_INF;
@@ -361,28 +394,55 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     L.ctl[PIPL_STATUS] = status;
     L.ctl[PIPL_ACTION] = status == PIP_ST_OK ? PIPL_GO : PIPL_STOP;
     if (status == PIP_ST_OK) L.ctl[PIPL_PIVOTS] = L.ctl[PIPL_PIVOTS] + 1;
+    L.ctl[PIPL_NACTIVE] = 0;
+    L.ctl[PIPL_NEXT] = 0;
+  }
+  G::cta_sync();
+  /* rows whose update is not the identity (foo != 0 or a denominator to normalise,
+   * source/traiter.c:470-501): only those are visited by the update phase */
+  {
+    int nskip = 0;
+    for (int base = 0; base < nl; base += T) {
+      const int p = base + tid;
+      bool act = false;
+      if (p < nl && p != pivi) {
+        const int f = L.fl[p];
+        if (!(f & PIP_UNIT)) {
+          const pip_i64 foo = pipl_row(L, PIP_LINK(f))[pivj];
+          if (foo != 0 || L.den[p] != 1) act = true; else nskip++;
+        }
+      }
+      const unsigned m = W::ballot(act);
+      int at = 0;
+      if (W::lane() == 0 && m) at = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], (unsigned)pip_popc(m));
+      at = W::shfl(at, 0);
+      if (act) L.active[at + pip_popc(m & ((1u << W::lane()) - 1u))] = p;
+    }
+    nskip = pipl_cta_sum(nskip, red);
+    if (tid == 0) L.ctl[PIPL_SKIPPED_LO] = L.ctl[PIPL_SKIPPED_LO] + nskip;
   }
 }
 
-/* ---- phase C: every warp of the grid updates rows -------------------------------------------- */
-PIP_DEV void pipl_phase_c(const PipLarge &L, unsigned &skipped)
+/* ---- phase C: the CTAs of the grid pull active rows from a queue; one CTA updates one row ------ */
+PIP_DEV void pipl_phase_c(const PipLarge &L, int *red)
 {
-  const int lane = W::lane();
-  const int wpc = G::T() >> 5;
-  const int gw = G::cta() * wpc + (G::tid() >> 5), nw = G::ncta() * wpc;
-  const int nvar = L.nvar, ncol = nvar + 1, nl = nvar + L.ctl[PIPL_NI];
-  const int pivi = L.ctl[PIPL_PIVI], pivj = L.ctl[PIPL_PIVJ];
+  const int tid = G::tid(), T = G::T();
+  const int nvar = L.nvar, ncol = nvar + 1;
+  const int pivi = L.ctl[PIPL_PIVI], pivj = L.ctl[PIPL_PIVJ], nactive = L.ctl[PIPL_NACTIVE];
   const pip_i64 pivot = L.ctl64[0], dpiv = L.ctl64[1];
   const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
-  for (int k = gw; k < nl; k += nw) {
-    if (k == pivi) continue;
+  for (;;) {
+    G::cta_sync();
+    if (tid == 0) red[63] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NEXT], 1u);
+    G::cta_sync();
+    const int idx = red[63];
+    if (idx >= nactive) break;
+    const int k = L.active[idx];
     const int f = L.fl[k];
-    if (f & PIP_UNIT) continue;
     pip_i64 *row = pipl_row(L, PIP_LINK(f));
     pip_i64 foo = row[pivj];
     const pip_i64 dk = L.den[k];
-    W::sync();                          /* every lane has read foo before pass 1 overwrites row[pivj] */
-    if (foo == 0 && dk == 1) { skipped++; continue; }
+    G::cta_sync();                      /* every thread has read foo before pass 1 overwrites row[pivj] */
     pip_i64 lpiv = pivot;
     if (foo == 0) lpiv = 1;
     else if (pivot != 1 && foo != 1 && foo != -1) {
@@ -390,51 +450,65 @@ PIP_DEV void pipl_phase_c(const PipLarge &L, unsigned &skipped)
       if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
     }
     const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
+    const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
     pip_u64 orz = 0;
-    /* pass 1: z = row*lpiv - prow*foo, two words per lane per step (16-byte accesses) */
+    /* pass 1: z = row*lpiv - prow*foo, 16-byte accesses, the whole CTA on one row */
     const int pairs = ncol >> 1;
     pip_i64x2 *row2 = (pip_i64x2 *)row;
     const pip_i64x2 *prow2 = (const pip_i64x2 *)prow;
-    #pragma unroll 4
-    for (int q = lane; q < pairs; q += 32) {
+    #pragma unroll 2
+    for (int q = tid; q < pairs; q += T) {
       const pip_i64x2 a = row2[q], b = prow2[q];
       pip_i64x2 z;
       z.x = (pip_i64)((pip_u64)a.x * (pip_u64)lpiv - (pip_u64)b.x * (pip_u64)foo);
       z.y = (pip_i64)((pip_u64)a.y * (pip_u64)lpiv - (pip_u64)b.y * (pip_u64)foo);
+      if (2 * q == pivj) z.x = zp;
+      if (2 * q + 1 == pivj) z.y = zp;
       row2[q] = z;
       orz |= (pip_u64)z.x | (pip_u64)z.y;
     }
-    if ((ncol & 1) && lane == 0) {
+    if ((ncol & 1) && tid == 0) {
       const int j = ncol - 1;
-      const pip_i64 z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
+      pip_i64 z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
+      if (j == pivj) z = zp;
       row[j] = z;
       orz |= (pip_u64)z;
     }
-    W::sync();
-    const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
-    if (lane == 0) row[pivj] = zp;
-    orz |= (pip_u64)zp;
-    W::sync();
     pip_i64 g = newden;
-    if (g != 1) {
+    if (g != 1) {                        /* uniform over the CTA */
       if ((g & (g - 1)) == 0 && g > 0) {
         orz |= (pip_u64)g;
-        const unsigned lo = W::redor((unsigned)orz), hi = W::redor((unsigned)(orz >> 32));
+        unsigned lo = W::redor((unsigned)orz), hi = W::redor((unsigned)(orz >> 32));
+        const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+        G::cta_sync();
+        if (lane == 0) { red[2 * wid] = (int)lo; red[2 * wid + 1] = (int)hi; }
+        G::cta_sync();
+        lo = 0; hi = 0;
+        for (int i = 0; i < nw; i++) { lo |= (unsigned)red[2 * i]; hi |= (unsigned)red[2 * i + 1]; }
         const pip_u64 all = ((pip_u64)hi << 32) | lo;
         g = (pip_i64)(all & (0ull - all));
       } else {
-        for (int j = lane; j < ncol && g != 1; j += 32) g = pip_gcd(g, row[j]);
+        G::cta_sync();                   /* pass 1 stores visible */
+        for (int j = tid; j < ncol && g != 1; j += T) g = pip_gcd(g, row[j]);
         for (int o = 16; o > 0; o >>= 1) g = pip_gcd(g, W::shfl_xor64(g, o));
+        const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+        pip_i64 *red64 = (pip_i64 *)red;
+        G::cta_sync();
+        if (lane == 0) red64[wid] = g;
+        G::cta_sync();
+        g = red64[0];
+        for (int i = 1; i < nw; i++) g = pip_gcd(g, red64[i]);
       }
     }
     pip_i64 nd = newden;
     if (g != 1 && g != 0) {
+      G::cta_sync();
       const PipExactDiv e = pip_exact_prepare(g);
-      for (int j = lane; j < ncol; j += 32) row[j] = pip_exact_apply(row[j], e);
+      for (int j = tid; j < ncol; j += T) row[j] = pip_exact_apply(row[j], e);
       nd = pip_exact_apply(newden, e);
-      W::sync();
     }
-    if (lane == 0) {
+    G::cta_sync();
+    if (tid == 0) {
       L.den[k] = nd;
       const pip_i64 c = row[nvar];
       L.csign[k] = c < 0 ? -1 : c > 0 ? 1 : 0;
@@ -469,14 +543,14 @@ PIP_DEV void pipl_solve(const PipLarge &L, int *red)
     G::grid_sync();
     const long long t1 = pip_clock();
     if (L.ctl[PIPL_ACTION] == PIPL_STOP) break;
-    pipl_phase_c(L, skipped);
+    pipl_phase_c(L, red);
     G::grid_sync();
     const long long t2 = pip_clock();
     if (G::cta() == 0 && G::tid() == 0) { L.prof[0] += (unsigned long long)(t1 - t0); L.prof[1] += (unsigned long long)(t2 - t1); }
     t0 = t2;
     if (L.ctl[PIPL_STATUS] != PIP_ST_OK) break;
   }
-  if (W::lane() == 0 && skipped) G::atomic_add_u(&((unsigned *)L.ctl)[PIPL_SKIPPED_LO], skipped);
+  (void)skipped;
 }
 
 /* entry of traiter for the large problem: flags, tab_simplify (source/tab.c:396-427) and the
@@ -488,7 +562,7 @@ PIP_DEV void pipl_init_rows(const PipLarge &L, float *sz)
   const int gw = G::cta() * wpc + (G::tid() >> 5), nw = G::ncta() * wpc;
   const int nvar = L.nvar, ni = L.ctl[PIPL_NI], ncol = nvar + 1;
   for (int k = gw; k < nvar + ni; k += nw) {
-    if (k < nvar) { if (lane == 0) { L.fl[k] = PIP_MKFL(PIP_UNIT, k); L.den[k] = 1; L.csign[k] = 0; sz[k] = 0.f; } continue; }
+    if (k < nvar) { if (lane == 0) { L.fl[k] = PIP_MKFL(PIP_UNIT, k); L.den[k] = 1; L.csign[k] = 0; sz[k] = 0.f; L.colpos[k] = k; } continue; }
     pip_i64 *row = pipl_row(L, k - nvar);
     if (L.flags & PIP_F_INT) {
       pip_i64 g = 0;
@@ -524,6 +598,13 @@ PIP_DEV void pipl_sort(const PipLarge &L, float *sz, int *red)
   for (int k = nvar + tid; k < nl; k += T) { const int b = (int)pip_f2u(sz[k]); if (b > mx) mx = b; }
   const int smax_bits = pipl_cta_max(mx, red);       /* sizes are non-negative floats: bit order = value order */
   const double smax = (double)pip_u2f((unsigned)smax_bits);
+  /* the stored-position bitmap (the sort only permutes stored rows among stored positions) */
+  for (int w = tid; w < (L.pcap + 31) / 32; w += T) {
+    unsigned bits = 0;
+    for (int b = 0; b < 32; b++) { const int pp = w * 32 + b; if (pp >= nvar && pp < nl) bits |= 1u << b; }
+    L.sbits[w] = bits;
+  }
+  G::cta_sync();
   for (int i = nvar; i < nl; i++) {
     int best = PIPL_INF, bestk = PIPL_INF;
     for (int k = i + tid; k < nl; k += T) {

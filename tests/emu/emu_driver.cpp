@@ -65,6 +65,9 @@ extern "C" int pipemu_solve_large(int nvar, int ni, int nq, const pip_i64 *tab, 
   L.den = (pip_i64 *)calloc(L.pcap + 1, 8);
   L.fl = (int *)calloc(L.pcap + 1, 4);
   L.csign = (signed char *)calloc(L.pcap + 1, 1);
+  L.colpos = (int *)calloc(nvar + 4, 4);
+  L.sbits = (unsigned *)calloc((L.pcap + 31) / 32 + 4, 4);
+  L.active = (int *)calloc(L.pcap + 4, 4);
   L.cand = (int *)calloc((L.pcap > nvar ? L.pcap : nvar) + 4, 4);
   L.member = (unsigned char *)calloc(nvar + 16, 1);
   L.cut = (pip_i64 *)calloc(L.stride + 2, 8);
@@ -80,6 +83,6 @@ extern "C" int pipemu_solve_large(int nvar, int ni, int nq, const pip_i64 *tab, 
   *status = ctl[PIPL_STATUS];
   *ncells = ctl[PIPL_NCELL];
   if (info) { info[0] = ctl[PIPL_PIVOTS]; info[1] = ctl[PIPL_CUTS]; info[2] = (unsigned)ctl[PIPL_SKIPPED_LO]; info[3] = ctl[PIPL_NI]; }
-  free(L.data); free(L.den); free(L.fl); free(L.csign); free(L.cand); free(L.member); free(L.cut);
+  free(L.data); free(L.den); free(L.fl); free(L.csign); free(L.cand); free(L.member); free(L.cut); free(L.colpos); free(L.sbits); free(L.active);
   return 0;
 }
