@@ -121,8 +121,10 @@ pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long
                                        int sol_size, int maxcol);
 int pip_large_run_dp(pip_large_problem *p, float *kernel_ms);
 int pip_large_fetch_dp(pip_large_problem *p, int *status, PipCell_dp *cells, int cell_cap, int *ncells,
-                       long long *info /* [6]: pivots, cuts, skipped identity rows, final ni,
-                                          SM cycles in the row/column-choice phase, in the update phase */);
+                       long long *info /* [12]: pivots, cuts, skipped identity rows, final ni,
+                                          SM cycles in the row/column-choice phase, in the update phase,
+                                          then sub-phases: swap, row pick, column choice, determinant,
+                                          active-row list, spare */);
 void pip_large_destroy_dp(pip_large_problem *p);
 
 void pip_last_batch_stats_dp(PipBatchStats_dp *out);

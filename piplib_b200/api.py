@@ -318,7 +318,7 @@ class LargeProblem:
 
     def fetch(self):
         st, nc = C.c_int(0), C.c_int(0)
-        info = (C.c_longlong * 6)()
+        info = (C.c_longlong * 12)()
         cells = np.zeros(self.cap, dtype=CELL_DTYPE)
         if lib().pip_large_fetch_dp(self.h, C.byref(st), cells.ctypes.data_as(C.c_void_p), self.cap,
                                     C.byref(nc), info) != 0:
@@ -326,7 +326,8 @@ class LargeProblem:
         c = cells[:nc.value]
         return st.value, [[int(x["kind"]), int(x["p1"]), int(x["p2"])] for x in c], \
             dict(pivots=int(info[0]), cuts=int(info[1]), skipped_rows=int(info[2]), ni=int(info[3]),
-                 cycles_choice=int(info[4]), cycles_update=int(info[5]))
+                 cycles_choice=int(info[4]), cycles_update=int(info[5]),
+                 sub=dict(zip(['swap', 'rowpick', 'column', 'det', 'active'], [int(info[6 + i]) for i in range(5)])))
 
     def close(self):
         if self.h:

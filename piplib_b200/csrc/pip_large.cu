@@ -34,7 +34,7 @@ __global__ void pip_large_reset_kernel(pip_i64 *dst, const pip_i64 *src, size_t 
     ctl[PIPL_NI] = ni; ctl[PIPL_LDET] = 1; ctl[PIPL_STATUS] = PIP_ST_OK;
     for (int k = 0; k < 8; k++) ctl64[k] = 0;
     ctl64[2] = 1;
-    prof[0] = prof[1] = 0;
+    for (int k = 0; k < 8; k++) prof[k] = 0;
   }
 }
 
@@ -133,10 +133,11 @@ int pip_large_fetch_dp(pip_large_problem *P, int *status, PipCell_dp *cells, int
     *status = ctl[PIPL_STATUS];
     *ncells = ctl[PIPL_NCELL];
     if (info) {
-      unsigned long long prof[2];
+      unsigned long long prof[8];
       CKL(cudaMemcpy(prof, P->L.prof, sizeof prof, cudaMemcpyDeviceToHost));
       info[0] = ctl[PIPL_PIVOTS]; info[1] = ctl[PIPL_CUTS]; info[2] = (unsigned)ctl[PIPL_SKIPPED_LO]; info[3] = ctl[PIPL_NI];
       info[4] = (long long)prof[0]; info[5] = (long long)prof[1];
+      for (int k = 2; k < 8; k++) info[4 + k] = (long long)prof[k];
     }
     if (cells && *ncells > 0 && *ncells <= cell_cap)
       CKL(cudaMemcpy(cells, P->L.cells, sizeof(PipCell) * (size_t)*ncells, cudaMemcpyDeviceToHost));

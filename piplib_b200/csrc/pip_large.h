@@ -23,6 +23,9 @@
 #include "simt.h"
 
 #define PIPL_INF 0x7fffffff
+/* sub-phase timers of CTA 0 (thread 0): prof[2..7] = swap, row pick, column choice, determinant,
+ * active-row list, spare */
+#define PIPL_T(i) do { if (tid == 0) { const long long n_ = pip_clock(); L.prof[i] += (unsigned long long)(n_ - tlap); tlap = n_; } } while (0)
 
 struct PipLarge {
   /* problem */
@@ -161,6 +164,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
   const int nvar = L.nvar, ncol = nvar + 1;
   int ni = L.ctl[PIPL_NI];
   int nl = nvar + ni;
+  long long tlap = pip_clock();
 
   /* the swap of the previous pivot (source/traiter.c:503-516) */
   if (!first_call) {
@@ -188,6 +192,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     G::cta_sync();
   }
 
+  PIPL_T(2);
   int pivi = PIPL_INF;
   for (;;) {
     /* chercher(Minus) */
@@ -273,6 +278,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
    * position colpos[j] lies in the gap is struck at once (if that is all of S, the one with the
    * largest colpos survives).  The loop therefore runs once per *stored* row met before the
    * decision -- typically once or twice. */
+  PIPL_T(3);
   const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
   for (int j = tid; j < nvar; j += T) L.member[j] = prow[j] > 0 ? 1 : 0;
   G::cta_sync();
@@ -359,6 +365,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
   const int pivj = pipl_cta_min(pj, red);
   if (pivj >= nvar) { pipl_finish(L, PIP_ST_FAULT, 0); return; }
 
+  PIPL_T(4);
   /* ---- determinant bookkeeping, source/traiter.c:394-447 (one thread) ------------------------- */
   if (tid == 0) {
     const pip_i64 pivot = prow[pivj], dpiv = L.den[pivi];
@@ -398,6 +405,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     L.ctl[PIPL_NEXT] = 0;
   }
   G::cta_sync();
+  PIPL_T(5);
   /* rows whose update is not the identity (foo != 0 or a denominator to normalise,
    * source/traiter.c:470-501): only those are visited by the update phase */
   {
@@ -421,6 +429,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     nskip = pipl_cta_sum(nskip, red);
     if (tid == 0) L.ctl[PIPL_SKIPPED_LO] = L.ctl[PIPL_SKIPPED_LO] + nskip;
   }
+  PIPL_T(6);
 }
 
 /* ---- phase C: the CTAs of the grid pull active rows from a queue; one CTA updates one row ------ */

@@ -76,7 +76,7 @@ extern "C" int pipemu_solve_large(int nvar, int ni, int nq, const pip_i64 *tab, 
   ctl[PIPL_NI] = ni; ctl[PIPL_LDET] = 1; ctl64[2] = 1;
   L.ctl = ctl; L.ctl64 = ctl64;
   L.cells = cells;
-  unsigned long long prof[8] = {0};
+  unsigned long long prof[16] = {0};
   L.prof = prof;
   pipemu::set_order(order_mode);
   pipemu::run_warp(large_entry, &e);

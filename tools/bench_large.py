@@ -38,7 +38,8 @@ line = {"workload": "consecutive-ones %d x %d int64, Nq=1" % (n, n + 1), "status
         "cuts": info["cuts"], "skipped_identity_rows": info["skipped_rows"], "kernel_ms": best,
         "us_per_pivot": 1e3 * best / max(piv, 1),
         "phase_share": {"choice": info["cycles_choice"] / max(1, info["cycles_choice"] + info["cycles_update"]),
-                        "update": info["cycles_update"] / max(1, info["cycles_choice"] + info["cycles_update"])}, "pivots_per_sec": piv / (best / 1e3),
+                        "update": info["cycles_update"] / max(1, info["cycles_choice"] + info["cycles_update"]),
+                        "choice_sub_us_per_pivot": {k: v / 1965.0 / max(1, piv) for k, v in info["sub"].items()}}, "pivots_per_sec": piv / (best / 1e3),
         "roofline": {"bound": "hbm", "achieved": alg / (best / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (best / 1e3) / 1e9 / peak, "peak_source": src,
                      "note": "dense 16*R*C figure; rows whose update is the identity are skipped"}}
