@@ -288,6 +288,56 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
   int k = 0;
   const int nwords = (nl + 31) >> 5;
   while (ncand > 1) {
+    if (ncand <= 32) {
+      /* few candidates left: one warp finishes the walk with the candidates in its lanes
+       * (column, pivot-row entry and Unit position in registers), no CTA barriers */
+      ncand = pipl_compact(L, red, 0);
+      if (tid < 32) {
+        const int lane = tid;
+        bool alive = lane < ncand;
+        const int j = alive ? L.cand[lane] : 0;
+        const pip_i64 pj = alive ? prow[j] : 1;
+        const int u = alive ? L.colpos[j] : PIPL_INF;
+        const bool was = alive;
+        int n = ncand;
+        while (n > 1) {
+          int c = PIPL_INF;
+          for (int w = (k >> 5) + lane; w < nwords; w += 32) {
+            unsigned bits = L.sbits[w];
+            if (w == (k >> 5)) bits &= ~0u << (k & 31);
+            if (bits) { const int pp = (w << 5) + pip_ffs(bits) - 1; if (pp < nl) c = pp; break; }
+          }
+          const int pst = (int)W::redmin((unsigned)c);
+          const unsigned mel = W::ballot(alive && u < pst);
+          const int nel = pip_popc(mel);
+          if (nel >= n) {
+            const int umax = (int)W::redmax(alive ? (unsigned)u : 0u);
+            alive = alive && u == umax;
+            n = 1;
+            break;
+          }
+          if (alive && u < pst) alive = false;
+          n -= nel;
+          if (pst >= nl || n <= 1) break;
+          const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
+          const pip_i64 a = alive ? row[j] : 0;
+          pip_i64 ba = a, bp = pj;
+          int valid = alive ? 1 : 0;
+          for (int o = 16; o > 0; o >>= 1) {
+            const pip_i64 oa = W::shfl_xor64(ba, o), op = W::shfl_xor64(bp, o);
+            const int ov = W::shfl_xor(valid, o);
+            if (ov && (!valid || pipl_ratio_cmp(oa, op, ba, bp) < 0)) { ba = oa; bp = op; valid = 1; }
+          }
+          if (alive && pipl_ratio_cmp(a, pj, ba, bp) != 0) alive = false;
+          n = pip_popc(W::ballot(alive));
+          k = pst + 1;
+        }
+        if (was && !alive) L.member[j] = 0;
+      }
+      G::cta_sync();
+      ncand = 1;
+      break;
+    }
     /* next stored position >= k */
     int c = PIPL_INF;
     for (int w = (k >> 5) + tid; w < nwords; w += T) {
@@ -409,22 +459,31 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
   /* rows whose update is not the identity (foo != 0 or a denominator to normalise,
    * source/traiter.c:470-501): only those are visited by the update phase */
   {
+    /* four positions per thread per round, loads issued together (the walk is latency-bound) */
     int nskip = 0;
-    for (int base = 0; base < nl; base += T) {
-      const int p = base + tid;
-      bool act = false;
-      if (p < nl && p != pivi) {
-        const int f = L.fl[p];
-        if (!(f & PIP_UNIT)) {
-          const pip_i64 foo = pipl_row(L, PIP_LINK(f))[pivj];
-          if (foo != 0 || L.den[p] != 1) act = true; else nskip++;
-        }
+    for (int base = 0; base < nl; base += 4 * T) {
+      int pp[4], ff[4];
+      pip_i64 foo[4], dd[4];
+      #pragma unroll
+      for (int i = 0; i < 4; i++) { pp[i] = base + i * T + tid; ff[i] = pp[i] < nl ? L.fl[pp[i]] : PIP_UNIT; }
+      #pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const bool st = pp[i] < nl && pp[i] != pivi && !(ff[i] & PIP_UNIT);
+        foo[i] = st ? pipl_row(L, PIP_LINK(ff[i]))[pivj] : 0;
+        dd[i] = st ? L.den[pp[i]] : 1;
+        if (!st) ff[i] = PIP_UNIT;
       }
-      const unsigned m = W::ballot(act);
-      int at = 0;
-      if (W::lane() == 0 && m) at = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], (unsigned)pip_popc(m));
-      at = W::shfl(at, 0);
-      if (act) L.active[at + pip_popc(m & ((1u << W::lane()) - 1u))] = p;
+      #pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const bool st = !(ff[i] & PIP_UNIT);
+        const bool act = st && (foo[i] != 0 || dd[i] != 1);
+        if (st && !act) nskip++;
+        const unsigned m = W::ballot(act);
+        int at = 0;
+        if (W::lane() == 0 && m) at = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], (unsigned)pip_popc(m));
+        at = W::shfl(at, 0);
+        if (act) L.active[at + pip_popc(m & ((1u << W::lane()) - 1u))] = pp[i];
+      }
     }
     nskip = pipl_cta_sum(nskip, red);
     if (tid == 0) L.ctl[PIPL_SKIPPED_LO] = L.ctl[PIPL_SKIPPED_LO] + nskip;

@@ -40,6 +40,7 @@ struct W {
   static inline unsigned redor(unsigned v) { unsigned r = 0; for (int b = 0; b < 32; b++) if (pipemu::ballot((v >> b) & 1u)) r |= 1u << b; return r; }
   static inline int shfl_down(int v, int d) { int l = pipemu::lane(); return (int)pipemu::shfl64(v, l + d < 32 ? l + d : l); }
   static inline long long shfl_xor64(long long v, int m) { return pipemu::shfl64(v, pipemu::lane() ^ m); }
+  static inline int shfl_xor(int v, int m) { return (int)pipemu::shfl64(v, pipemu::lane() ^ m); }
   static inline unsigned atomic_add(unsigned *p, unsigned v) { return pipemu::atomic_add(p, v); }
 };
 
@@ -86,6 +87,7 @@ struct W {
   static __device__ __forceinline__ unsigned redor(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
   static __device__ __forceinline__ int shfl_down(int v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
   static __device__ __forceinline__ long long shfl_xor64(long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+  static __device__ __forceinline__ int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
   static __device__ __forceinline__ unsigned atomic_add(unsigned *p, unsigned v) { return atomicAdd(p, v); }
 };
 
