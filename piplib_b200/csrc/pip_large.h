@@ -23,6 +23,7 @@
 #include "simt.h"
 
 #define PIPL_INF 0x7fffffff
+#define PIPL_K 8            /* candidates per thread kept in registers by the column walk */
 /* sub-phase timers of CTA 0 (thread 0): prof[2..7] = swap, row pick, column choice, determinant,
  * active-row list, spare */
 #define PIPL_T(i) do { if (tid == 0) { const long long n_ = pip_clock(); L.prof[i] += (unsigned long long)(n_ - tlap); tlap = n_; } } while (0)
@@ -338,6 +339,89 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
       ncand = 1;
       break;
     }
+    /* many candidates: the whole CTA walks, each thread keeping up to PIPL_K candidates (column,
+     * pivot-row entry, Unit position) in registers so that one walk step costs one gather of the
+     * stored row plus a few barriers */
+    {
+      int cj[PIPL_K], cu[PIPL_K];
+      pip_i64 cp[PIPL_K];
+      unsigned alive = 0;
+      #pragma unroll
+      for (int i = 0; i < PIPL_K; i++) {
+        const int m = tid + i * T;
+        cj[i] = 0; cu[i] = PIPL_INF; cp[i] = 1;
+        if (m < ncand0 && L.member[L.cand[m]]) { cj[i] = L.cand[m]; cu[i] = L.colpos[cj[i]]; cp[i] = prow[cj[i]]; alive |= 1u << i; }
+      }
+      const bool fits = ncand0 <= PIPL_K * T;
+      pip_i64 *red64 = (pip_i64 *)red;
+      while (fits && ncand > 32) {
+        int c = PIPL_INF;
+        for (int w = (k >> 5) + tid; w < nwords; w += T) {
+          unsigned bits = L.sbits[w];
+          if (w == (k >> 5)) bits &= ~0u << (k & 31);
+          if (bits) { const int pp = (w << 5) + pip_ffs(bits) - 1; if (pp < nl) c = pp; break; }
+        }
+        const int pst = pipl_cta_min(c, red);
+        int nel = 0, umax = -1;
+        #pragma unroll
+        for (int i = 0; i < PIPL_K; i++)
+          if (((alive >> i) & 1u) && cu[i] < pst) { nel++; if (cu[i] > umax) umax = cu[i]; }
+        nel = pipl_cta_sum(nel, red);
+        if (nel >= ncand) {
+          umax = pipl_cta_max(umax, red);
+          #pragma unroll
+          for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] != umax) alive &= ~(1u << i);
+          ncand = 1;
+          break;
+        }
+        #pragma unroll
+        for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] < pst) alive &= ~(1u << i);
+        ncand -= nel;
+        if (pst >= nl || ncand <= 1) break;
+        const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
+        pip_i64 va[PIPL_K];
+        #pragma unroll
+        for (int i = 0; i < PIPL_K; i++) va[i] = ((alive >> i) & 1u) ? row[cj[i]] : 0;
+        pip_i64 ba = 0, bp = 1;
+        int valid = 0;
+        #pragma unroll
+        for (int i = 0; i < PIPL_K; i++)
+          if (((alive >> i) & 1u) && (!valid || pipl_ratio_cmp(va[i], cp[i], ba, bp) < 0)) { ba = va[i]; bp = cp[i]; valid = 1; }
+        for (int o = 16; o > 0; o >>= 1) {
+          const pip_i64 oa = W::shfl_xor64(ba, o), op = W::shfl_xor64(bp, o);
+          const int ov = W::shfl_xor(valid, o);
+          if (ov && (!valid || pipl_ratio_cmp(oa, op, ba, bp) < 0)) { ba = oa; bp = op; valid = 1; }
+        }
+        {
+          const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+          G::cta_sync();
+          if (lane == 0) { red64[2 * wid] = ba; red64[2 * wid + 1] = bp; red[96 + wid] = valid; }
+          G::cta_sync();
+          valid = 0;
+          for (int i = 0; i < nw; i++)
+            if (red[96 + i] && (!valid || pipl_ratio_cmp(red64[2 * i], red64[2 * i + 1], ba, bp) < 0 || !valid)) {
+              if (!valid || pipl_ratio_cmp(red64[2 * i], red64[2 * i + 1], ba, bp) < 0) { ba = red64[2 * i]; bp = red64[2 * i + 1]; }
+              valid = 1;
+            }
+        }
+        int removed = 0;
+        #pragma unroll
+        for (int i = 0; i < PIPL_K; i++)
+          if (((alive >> i) & 1u) && pipl_ratio_cmp(va[i], cp[i], ba, bp) != 0) { alive &= ~(1u << i); removed++; }
+        removed = pipl_cta_sum(removed, red);
+        ncand -= removed;
+        k = pst + 1;
+      }
+      /* publish the survivors */
+      #pragma unroll
+      for (int i = 0; i < PIPL_K; i++) {
+        const int m = tid + i * T;
+        if (m < ncand0 && L.member[L.cand[m]] && !((alive >> i) & 1u) && fits) L.member[L.cand[m]] = 0;
+      }
+      G::cta_sync();
+      if (fits) continue;                       /* <= 32 left (warp path) or decided */
+    }
+    /* fallback for more than PIPL_K * T candidates: everything through global memory */
     /* next stored position >= k */
     int c = PIPL_INF;
     for (int w = (k >> 5) + tid; w < nwords; w += T) {
