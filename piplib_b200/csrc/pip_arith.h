@@ -95,6 +95,7 @@ PIP_HD pip_i64 pip_exact_apply(pip_i64 z, const PipExactDiv &e)
   return (pip_i64)((pip_u64)(z >> e.shift) * e.inv);
 }
 
+#if defined(__CUDACC__) || defined(PIP_EMU)
 /* does the exact product a*b fit in int64? (informative overflow flag only) */
 PIP_DEV bool pip_mul_wraps(pip_i64 a, pip_i64 b)
 {
@@ -102,5 +103,6 @@ PIP_DEV bool pip_mul_wraps(pip_i64 a, pip_i64 b)
   pip_i64 hi = pip_mulhi(a, b);
   return hi != (lo >> 63);
 }
+#endif
 
 #endif

@@ -1,0 +1,128 @@
+/* Solution cells -> serialised quast words: one implementation for the host (pip_host.cpp) and
+ * the device (pip_serialize kernels).  Restates the decoder of the reference,
+ * sol_quast_edit_xx / sol_newparm_edit_xx / sol_list_edit_xx / sol_vector_edit_xx
+ * (source/sol.c:435-734), but emits the pre-order word stream of include/piplib_b200.h instead of
+ * a malloc'd tree.  The cell stream is itself pre-order (If, then-subtree, else-subtree), so a
+ * flat scan is enough: no recursion, which is what lets one GPU thread decode one problem.
+ *
+ *   node  := NNEWPARM { rank deno VEC }*  KIND ...
+ *   KIND  := 0 (leaf "()")  | 1 LIST | 2 VEC(condition) node(then) node(else)
+ *   LIST  := nvec { present(0/1) [VEC] }*  has_dual(0)
+ *   VEC   := n { num den }*
+ */
+#ifndef PIP_DECODE_H
+#define PIP_DECODE_H
+
+#include "pip_arith.h"
+#include "pip_types.h"
+
+enum { PIP_SOL_SHIFT = 1, PIP_SOL_NEGATE = 2, PIP_SOL_REMOVE = 4, PIP_SOL_DUAL = 8 };   /* source/sol.h:35-48 */
+
+struct PipSer {
+  pip_i64 *out;            /* may be NULL: count / hash only */
+  long long cap, len;
+  pip_u64 h;
+  int hashing;
+};
+#define PIP_HASH_INIT 0xcbf29ce484222325ULL
+
+PIP_HD void pip_sput(PipSer &s, pip_i64 v)
+{
+  if (s.hashing) {
+    s.h ^= (pip_u64)v;
+    s.h *= 0x9E3779B97F4A7C15ULL;
+    s.h ^= s.h >> 32;
+  }
+  if (s.out && s.len < s.cap) s.out[s.len] = v;
+  s.len++;
+}
+
+/* raw {kind, p1, p2} cells */
+struct PipRawCells {
+  const PipCell *c;
+  PIP_HDM int kind(int i) const { return c[i].kind; }
+  PIP_HDM pip_i64 p1(int i) const { return c[i].p1; }
+  PIP_HDM pip_i64 p2(int i) const { return c[i].p2; }
+};
+
+/* sol_vector_edit_xx, source/sol.c:435-512 */
+template <class C>
+PIP_HD void pip_ser_vector(PipSer &s, const C &c, int &i, int Bg, int Urs_p, int flags)
+{
+  int n = (int)c.p1(i), unbounded = 0;
+  if (flags & PIP_SOL_REMOVE) --n;
+  n -= Urs_p;
+  const int first_urs = Urs_p + (Bg >= 0);
+  /* the unbounded marker rewrites every denominator, so it must be known before emitting */
+  if (flags & PIP_SOL_SHIFT) {
+    int t = i;
+    for (int j = 0, k = 0; k < n; j++) {
+      t++;
+      if (j == Bg && c.p1(t) - c.p2(t) != 0) unbounded = 1;
+      if ((flags & PIP_SOL_REMOVE) && j == Bg) continue;
+      if (first_urs <= j && j < first_urs + Urs_p) continue;
+      k++;
+    }
+  }
+  pip_sput(s, n);
+  for (int j = 0, k = 0; k < n; j++) {
+    i++;
+    pip_i64 N = c.p1(i);
+    const pip_i64 D = c.p2(i);
+    const pip_i64 d = (D == 1) ? 1 : pip_gcd(N, D);
+    if ((flags & PIP_SOL_SHIFT) && j == Bg) N -= D;
+    if ((flags & PIP_SOL_REMOVE) && j == Bg) continue;
+    if (first_urs <= j && j < first_urs + Urs_p) continue;
+    pip_i64 num = d ? pip_div(N, d) : 0;
+    if (flags & PIP_SOL_NEGATE) num = -num;
+    pip_sput(s, num);
+    pip_sput(s, unbounded ? 0 : ((d == D) ? 1 : (d ? pip_div(D, d) : 0)));
+    k++;
+  }
+  i++;
+}
+
+/* the whole stream of one problem (n cells); returns false on a malformed stream */
+template <class C>
+PIP_HD bool pip_ser_cells(PipSer &s, const C &c, int n, int Bg, int Urs_p, int flags)
+{
+  int i = 0;
+  while (i < n) {
+    while (i < n && c.kind(i) == PIP_C_FREE) i++;
+    if (i >= n) break;
+    int nnew = 0;
+    for (int t = i; t < n && c.kind(t) == PIP_C_NEW; t += (int)c.p1(t + 2) + 4) nnew++;   /* New Div Form Val*m Val */
+    pip_sput(s, nnew);
+    for (int k = 0; k < nnew; k++) {
+      const int newcell = i;
+      i += 2;
+      int rank = (int)c.p1(newcell);
+      if (flags & PIP_SOL_REMOVE) rank--;
+      rank -= Urs_p;
+      pip_sput(s, rank);
+      pip_sput(s, c.p1(i + (int)c.p1(i) + 1));          /* the divisor follows the form */
+      pip_ser_vector(s, c, i, Bg, Urs_p, flags & PIP_SOL_REMOVE);
+      i++;
+    }
+    const int kind = c.kind(i);
+    const int nb = (int)c.p1(i);
+    i++;
+    if (kind == PIP_C_LIST) {
+      pip_sput(s, 1);
+      if (nb == 0) { pip_sput(s, 1); pip_sput(s, 0); }
+      else {
+        pip_sput(s, nb);
+        for (int e = 0; e < nb; e++) { pip_sput(s, 1); pip_ser_vector(s, c, i, Bg, Urs_p, flags); }
+      }
+      pip_sput(s, 0);                                    /* no dual leaf (Compute_dual is host-rejected) */
+    } else if (kind == PIP_C_NIL) {
+      pip_sput(s, 0);
+    } else if (kind == PIP_C_IF) {
+      pip_sput(s, 2);
+      pip_ser_vector(s, c, i, Bg, Urs_p, flags & PIP_SOL_REMOVE);
+    } else return false;
+  }
+  return true;
+}
+
+#endif

@@ -78,7 +78,8 @@ struct PipEngine::Impl {
   bool inited = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total, d_prof;
+  DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total, d_prof, d_parm, d_hash;
+  PinBuf h_hash;
   PinBuf h_res, h_total, h_input;
   std::vector<PinBuf> h_chunks;     /* one per round, reused across calls */
 
@@ -166,6 +167,14 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
   E.d_res.reserve(n * sizeof(PipResult));
   CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
   out.times.h2d_bytes += n * sizeof(PipResult);
+  const bool ser_mode = in.h_decode != nullptr;
+  if (ser_mode) {
+    E.d_parm.reserve(n * sizeof(PipDecodeParm));
+    CK(cudaMemcpyAsync(E.d_parm.p, in.h_decode, n * sizeof(PipDecodeParm), cudaMemcpyHostToDevice, s));
+    E.d_hash.reserve(n * sizeof(pip_u64));
+    CK(cudaMemsetAsync(E.d_hash.p, 0, n * sizeof(pip_u64), s));
+    out.times.h2d_bytes += n * sizeof(PipDecodeParm);
+  }
   E.d_queue.reserve(64);
   E.d_prof.reserve(sizeof(unsigned long long) * PIP_NPHASE);
   CK(cudaMemsetAsync(E.d_prof.p, 0, sizeof(unsigned long long) * PIP_NPHASE, s));
@@ -249,16 +258,26 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       double tk = now_s();
       CK(pip_launch_solve(&L, cs.shared, ctas, cs.warps_per_cta, s));
       out.times.launches++;
-      /* compact this round's cells */
+      /* compact this round's output: packed cells, or (device-decode mode) serialised quasts */
+      if (ser_mode) {
+        CK(pip_launch_serialize((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
+                                (const PipDecodeParm *)E.d_parm.p, nullptr, nullptr, nullptr, m, 0, s));
+        out.times.launches++;
+      }
       CK(pip_launch_gather((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
-                           (long long *)E.d_off.p, nullptr, m, (long long *)E.d_total.p, 0, s));
+                           (long long *)E.d_off.p, nullptr, m, (long long *)E.d_total.p, ser_mode ? 2 : 0, s));
       out.times.launches++;
       CK(cudaMemcpyAsync(E.h_total.p, E.d_total.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       const long long total = *(long long *)E.h_total.p;
       E.d_compact.reserve((size_t)std::max<long long>(total, 1) * sizeof(pip_u64));
-      CK(pip_launch_gather((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
-                           (long long *)E.d_off.p, (pip_u64 *)E.d_compact.p, m, (long long *)E.d_total.p, 1, s));
+      if (ser_mode)
+        CK(pip_launch_serialize((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
+                                (const PipDecodeParm *)E.d_parm.p, (const long long *)E.d_off.p,
+                                (pip_i64 *)E.d_compact.p, (pip_u64 *)E.d_hash.p, m, 1, s));
+      else
+        CK(pip_launch_gather((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
+                             (long long *)E.d_off.p, (pip_u64 *)E.d_compact.p, m, (long long *)E.d_total.p, 1, s));
       out.times.launches++;
       CK(cudaEventRecord(E.ev1, s));
       CK(cudaStreamSynchronize(s));
@@ -304,6 +323,12 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
     }
   }
   CK(cudaEventElapsedTime(&out.times.device_ms, E.ev0, E.ev1));
+  if (ser_mode) {
+    E.h_hash.reserve(n * sizeof(pip_u64));
+    CK(cudaMemcpy(E.h_hash.p, E.d_hash.p, n * sizeof(pip_u64), cudaMemcpyDeviceToHost));
+    out.hashes.assign((const pip_u64 *)E.h_hash.p, (const pip_u64 *)E.h_hash.p + n);
+    out.times.d2h_bytes += n * sizeof(pip_u64);
+  }
   CK(cudaMemcpy(out.times.phase_cycles, E.d_prof.p, sizeof(unsigned long long) * PIP_NPHASE, cudaMemcpyDeviceToHost));
   /* anything still unsolved is too large for the ladder */
   for (size_t i = 0; i < n; i++)

@@ -19,6 +19,8 @@ struct PipBatchIn {
   const PipProblem *d_prob = nullptr;   /* optional device-resident copies */
   const void *d_pool = nullptr;
   bool fetch_cells = true;              /* copy the compacted cells back to the host */
+  const PipDecodeParm *h_decode = nullptr; /* if set: decode on the device, ship serialised quast words
+                                              (+ hashes) instead of cells */
   int sol_size = PIP_SOL_SIZE, maxcol = PIP_MAXCOL;
 };
 
@@ -43,6 +45,7 @@ struct PipCellView {
 struct PipBatchOut {
   std::vector<PipResult> res;           /* cell_off = word offset into the round's host chunk */
   std::vector<const pip_u64 *> base;    /* per problem: base pointer of its round's host chunk */
+  std::vector<pip_u64> hashes;          /* device-decode mode: hash of each serialised quast */
   PipBatchTimes times;
   PipCellView cells_of(size_t i) const
   {

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/piplib_b200.h"
+#include "pip_decode.h"
 #include "pip_engine.h"
 
 typedef long long I;
@@ -297,85 +298,6 @@ void ser_quast(Ser &s, const PipQuast_dp *q)
   } else sput(s, 0);
 }
 
-/* cells -> serialised quast words without building the tree (the bulk path): the same decode
- * rules as decode_vector / decode_quast above */
-template <class C>
-void ser_vector_direct(Ser &s, const C &c, int *i, int Bg, int Urs_p, int flags)
-{
-  int n = (int)c.p1(*i), unbounded = 0;
-  if (flags & S_REMOVE) --n;
-  n -= Urs_p;
-  const int first_urs = Urs_p + (Bg >= 0);
-  /* the unbounded marker rewrites every denominator, so it must be known before emitting */
-  if (flags & S_SHIFT) {
-    int t = *i;
-    for (int j = 0, k = 0; k < n; j++) {
-      t++;
-      if (j == Bg && c.p1(t) - c.p2(t) != 0) unbounded = 1;
-      if ((flags & S_REMOVE) && j == Bg) continue;
-      if (first_urs <= j && j < first_urs + Urs_p) continue;
-      k++;
-    }
-  }
-  sput(s, n);
-  for (int j = 0, k = 0; k < n; j++) {
-    (*i)++;
-    I N = c.p1(*i), D = c.p2(*i), d = (D == 1) ? 1 : gcd_abs(N, D);
-    if ((flags & S_SHIFT) && j == Bg) N -= D;
-    if ((flags & S_REMOVE) && j == Bg) continue;
-    if (first_urs <= j && j < first_urs + Urs_p) continue;
-    I num = d ? N / d : 0;
-    if (flags & S_NEGATE) num = -num;
-    sput(s, num);
-    sput(s, unbounded ? 0 : ((d == D) ? 1 : (d ? D / d : 0)));
-    k++;
-  }
-  (*i)++;
-}
-
-template <class C>
-void ser_quast_direct(Ser &s, const C &c, int *i, int Bg, int Urs_p, int flags)
-{
-  while (c.kind(*i) == PIP_C_FREE) (*i)++;
-  int n = 0;
-  for (int t = *i; c.kind(t) == PIP_C_NEW; t += (int)c.p1(t + 2) + 4) n++;   /* New Div Form Val*m Val */
-  sput(s, n);
-  for (int k = 0; k < n; k++) {
-    const int newcell = *i;
-    (*i) += 2;
-    int rank = (int)c.p1(newcell);
-    if (flags & S_REMOVE) rank--;
-    rank -= Urs_p;
-    sput(s, rank);
-    sput(s, c.p1(*i + (int)c.p1(*i) + 1));          /* the divisor follows the form */
-    ser_vector_direct(s, c, i, Bg, Urs_p, flags & S_REMOVE);
-    (*i)++;
-  }
-  const int kind = c.kind(*i);
-  const int nb = (int)c.p1(*i);
-  (*i)++;
-  if (kind == PIP_C_LIST) {
-    sput(s, 1);
-    if (nb == 0) { sput(s, 1); sput(s, 0); }
-    else {
-      sput(s, nb);
-      for (int e = 0; e < nb; e++) { sput(s, 1); ser_vector_direct(s, c, i, Bg, Urs_p, flags); }
-    }
-    if (flags & S_DUAL) { sput(s, 1); ser_quast_direct(s, c, i, Bg, Urs_p, 0); }
-    else sput(s, 0);
-  } else if (kind == PIP_C_NIL) {
-    sput(s, 0);
-  } else if (kind == PIP_C_IF) {
-    sput(s, 2);
-    ser_vector_direct(s, c, i, Bg, Urs_p, flags & S_REMOVE);
-    ser_quast_direct(s, c, i, Bg, Urs_p, flags);
-    ser_quast_direct(s, c, i, Bg, Urs_p, flags);
-  } else {
-    fprintf(stderr, "\nAie !!! Flag %d inattendu.\n", kind);
-    exit(1);
-  }
-}
-
 const char *fatal_message(int status)
 {
   switch (status) {
@@ -623,22 +545,24 @@ static PipQuast_dp *decode_one(const PipBatchOut &bo, size_t i, const Shape &s, 
   return decode_quast(v, &at, nullptr, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
 }
 
-/* serialise problem i straight from its cells (status OK or VOID) */
+/* serialise problem i straight from its cells (status OK or VOID) with the decoder the device
+ * uses too (pip_decode.h) */
 static void serialize_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify, Ser &out)
 {
-  if (bo.res[i].status == PIP_ST_VOID) { sput(out, -1); return; }
-  const PipCellView v = bo.cells_of(i);
-  int at = 0;
-  if (simplify) {
-    std::vector<PipCell> copy;
-    unpack_cells(v, copy);
-    int n = v.n;
-    simplify_cells(copy.data(), n, 0);
-    ArrCells a = {copy.data()};
-    ser_quast_direct(out, a, &at, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
-    return;
+  PipSer ps = {out.out, out.cap, out.len, out.h, out.hashing ? 1 : 0};
+  if (bo.res[i].status == PIP_ST_VOID) pip_sput(ps, -1);
+  else {
+    const PipCellView v = bo.cells_of(i);
+    if (simplify) {
+      std::vector<PipCell> copy;
+      unpack_cells(v, copy);
+      int n = v.n;
+      simplify_cells(copy.data(), n, 0);
+      PipRawCells a = {copy.data()};
+      pip_ser_cells(ps, a, n, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
+    } else pip_ser_cells(ps, v, v.n, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
   }
-  ser_quast_direct(out, v, &at, s.Bg - s.Nn - 1, s.Urs, s.sol_flags);
+  out.len = (long)ps.len; out.h = ps.h;
 }
 
 int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const *contexts,
@@ -974,6 +898,32 @@ void emit_chunk(const DenseArgs &A, DenseChunk &C, int *status, unsigned long lo
   (void)per;
 }
 
+/* device-decode mode: the engine returned serialised quasts; reserve the chunk's span of the
+ * caller's stream and copy every problem's words into it */
+void emit_chunk_ser(DenseChunk &C, int *status, unsigned long long *hashes, long long *ser, long long ser_cap,
+                    long long *ser_off, long long *ser_len, std::atomic<long long> *cursor, size_t nthreads)
+{
+  const size_t n = C.n;
+  const bool keep = ser != nullptr && ser_off != nullptr;
+  long long total = 0;
+  C.words.assign(n, 0);
+  for (size_t i = 0; i < n; i++) { C.words[i] = total; total += C.out.res[i].ser_words; }
+  const long long base = keep ? cursor->fetch_add(total) : 0;
+  const bool fits = keep && base + total <= ser_cap;
+  parallel_ranges(n, nthreads, [&](size_t, size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      const PipResult &r = C.out.res[i];
+      status[C.first + i] = r.status;
+      if (hashes) hashes[C.first + i] = C.out.hashes[i];
+      if (keep) {
+        ser_off[C.first + i] = base + C.words[i];
+        if (ser_len) ser_len[C.first + i] = r.ser_words;
+        if (fits && r.ser_words) memcpy(ser + base + C.words[i], C.out.base[i] + r.cell_off, sizeof(I) * r.ser_words);
+      }
+    }
+  });
+}
+
 void add_times(PipBatchOut &acc, const PipBatchOut &o)
 {
   acc.times.h2d += o.times.h2d; acc.times.kernel += o.times.kernel; acc.times.d2h += o.times.d2h;
@@ -1018,6 +968,9 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     std::atomic<long long> cursor(0);
     std::atomic<int> width_hint(0);
     const bool timing = getenv("PIPLIB_B200_TIMING") != nullptr;
+    /* decode on the GPU unless the host-only Simplify post-pass is wanted (PIPLIB_B200_HOST_DECODE=1
+     * forces the host decoder, for A/B tests) */
+    const bool device_decode = !A.opt.Simplify && getenv("PIPLIB_B200_HOST_DECODE") == nullptr;
     std::vector<double> tstage(lanes * 4, 0.0);
     auto lane_main = [&](size_t lane) {
       try {
@@ -1033,10 +986,20 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
           PipBatchIn in;
           in.n = C.n; in.h_prob = C.prob.data(); in.h_pool = pool; in.pool_words = C.pool_elems;
           in.elem_log2 = C.elem_log2;
+          std::vector<PipDecodeParm> parm;
+          if (device_decode) {
+            parm.resize(C.n);
+            for (size_t i = 0; i < C.n; i++) {
+              const Shape &sh = C.shapes[i];
+              parm[i].bg = sh.Bg - sh.Nn - 1; parm[i].urs = sh.Urs; parm[i].flags = sh.sol_flags;
+            }
+            in.h_decode = parm.data();
+          }
           double td = wall();
           E.run(in, C.out);
           double te = wall();
-          emit_chunk(A, C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
+          if (device_decode) emit_chunk_ser(C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
+          else emit_chunk(A, C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
           tstage[lane * 4 + 2] += te - td; tstage[lane * 4 + 3] += wall() - te;
           /* the cell chunks are engine-owned and reused by the next run on this lane: drop the views */
           C.out.base.clear();

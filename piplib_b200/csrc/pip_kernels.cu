@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pip_decode.h"
 #include "pip_kernels.h"
 #include "pip_warp_main.h"
 
@@ -85,8 +86,46 @@ __global__ void pip_gather_kernel(PipResult *res, const int *order, const PipCel
   }
 }
 
+/* ---- device-side decode: cells -> serialised quast words (pip_decode.h) --------------------- */
+/* one thread per problem; pass 0 sizes the stream, pass 1 writes it (and its hash) */
+__global__ void pip_serialize_kernel(PipResult *res, const int *order, const PipCell *cells,
+                                     const PipDecodeParm *parm, const long long *dst_off, pip_i64 *out,
+                                     pip_u64 *hashes, int nprob, int pass)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nprob) return;
+  const int p = order ? order[q] : q;
+  const PipResult r = res[p];
+  PipSer s;
+  s.out = pass ? out + dst_off[q] : nullptr;
+  s.cap = pass ? (long long)r.ser_words : 0;
+  s.len = 0; s.h = PIP_HASH_INIT; s.hashing = pass;
+  if (r.status == PIP_ST_VOID) pip_sput(s, -1);
+  else if (r.status == PIP_ST_OK) {
+    PipRawCells c = {cells + r.cell_off};
+    const PipDecodeParm d = parm[p];
+    pip_ser_cells(s, c, r.ncells, d.bg, d.urs, d.flags);
+  }
+  if (pass == 0) res[p].ser_words = (unsigned)s.len;
+  else {
+    res[p].cell_off = dst_off[q];
+    if (hashes) hashes[p] = (r.status == PIP_ST_OK || r.status == PIP_ST_VOID) ? s.h : 0ull;
+  }
+}
+
+extern "C" cudaError_t pip_launch_serialize(PipResult *res, const int *order, const PipCell *cells,
+                                            const PipDecodeParm *parm, const long long *dst_off, pip_i64 *out,
+                                            pip_u64 *hashes, int nprob, int pass, cudaStream_t stream)
+{
+  const int threads = 128;
+  pip_serialize_kernel<<<(nprob + threads - 1) / threads, threads, 0, stream>>>(res, order, cells, parm, dst_off, out,
+                                                                               hashes, nprob, pass);
+  return cudaGetLastError();
+}
+
 /* single-CTA exclusive scan of ncells (n up to a few million: 1024 threads, chunked) */
-__global__ void pip_scan_kernel(const PipResult *res, const int *order, long long *dst_off, int nprob, long long *total)
+__global__ void pip_scan_kernel(const PipResult *res, const int *order, long long *dst_off, int nprob, long long *total,
+                                int ser_mode)
 {
   __shared__ long long warp_sums[32];
   __shared__ long long carry;
@@ -98,7 +137,7 @@ __global__ void pip_scan_kernel(const PipResult *res, const int *order, long lon
     long long v = 0;
     if (i < nprob) {
       const PipResult &r = res[order ? order[i] : i];
-      v = (long long)r.ncells * ((r.rflags & PIP_RES_WIDE) ? 3 : 1);
+      v = ser_mode ? (long long)r.ser_words : (long long)r.ncells * ((r.rflags & PIP_RES_WIDE) ? 3 : 1);
     }
     long long x = v;
     for (int o = 1; o < 32; o <<= 1) {
@@ -129,7 +168,7 @@ extern "C" cudaError_t pip_launch_gather(PipResult *res, const int *order, const
                                          pip_u64 *out, int nprob, long long *total, int phase,
                                          cudaStream_t stream)
 {
-  if (phase == 0) pip_scan_kernel<<<1, 1024, 0, stream>>>(res, order, dst_off, nprob, total);
+  if (phase == 0 || phase == 2) pip_scan_kernel<<<1, 1024, 0, stream>>>(res, order, dst_off, nprob, total, phase == 2);
   else {
     int blocks = (nprob + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;

@@ -19,6 +19,9 @@ cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, int ctas, int
 cudaError_t pip_solve_occupancy(int shared_class, int warps_per_cta, size_t smem_bytes, int *ctas_per_sm);
 cudaError_t pip_launch_gather(PipResult *res, const int *order, const PipCell *cells, long long *dst_off,
                               pip_u64 *out, int nprob, long long *total, int phase, cudaStream_t stream);
+cudaError_t pip_launch_serialize(PipResult *res, const int *order, const PipCell *cells, const PipDecodeParm *parm,
+                                 const long long *dst_off, pip_i64 *out, pip_u64 *hashes, int nprob, int pass,
+                                 cudaStream_t stream);
 long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level);
 #ifdef __cplusplus
 }

@@ -65,7 +65,7 @@ typedef struct {
   unsigned subsolves;            /* non-parametric feasibility solves (compa_test, context) */
   unsigned splits;
   unsigned max_rows, max_cols;   /* largest nligne x ncol seen by a pivot */
-  unsigned wrapped;              /* # pivots during which some 64-bit product wrapped */
+  unsigned ser_words;            /* words of the serialised quast (device-side decode), else 0 */
   unsigned elem_updates_lo, elem_updates_hi;
   unsigned rflags;               /* PIP_RES_* */
 } PipResult;
@@ -75,6 +75,12 @@ typedef struct {
   int pad;
   pip_i64 p1, p2;
 } PipCell;
+
+/* per-problem parameters of the cells -> quast decode (source/piplib.c:866-867: Bg-Nn-1, Urs_parms,
+ * sol_flags) for the device-side serialiser */
+typedef struct {
+  int bg, urs, flags;
+} PipDecodeParm;
 
 /* Wire format of the solution cells after the device-side gather: one 64-bit word per cell,
  *   bits 0-3 kind | bits 4-19 param2 (unsigned, denominators) | bits 20-63 param1 (signed),

@@ -37,7 +37,7 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
       r.status = status; r.ncells = ncell;
       r.cell_off = (pip_i64)warp_id * L.cells_per_warp + used;
       r.pivots = st.pivots; r.cuts = st.cuts; r.subsolves = st.subsolves; r.splits = st.splits;
-      r.max_rows = st.max_rows; r.max_cols = st.max_cols; r.wrapped = 0;
+      r.max_rows = st.max_rows; r.max_cols = st.max_cols; r.ser_words = 0;
       r.elem_updates_lo = (unsigned)(st.elem_updates & 0xffffffffull);
       r.elem_updates_hi = (unsigned)(st.elem_updates >> 32);
       r.rflags = rflags;

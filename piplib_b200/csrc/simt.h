@@ -14,6 +14,7 @@
 #define PIP_DEV static inline
 #define PIP_DEVNI static __attribute__((noinline))
 #define PIP_HD static inline
+#define PIP_HDM inline
 #define PIP_HDNI static __attribute__((noinline))
 #define PIP_ASSUME_SHARED(p) ((void)0)
 
@@ -66,11 +67,20 @@ static inline long long pip_clock() { return 0; }
 static inline unsigned pip_f2u(float f) { unsigned u; __builtin_memcpy(&u, &f, 4); return u; }
 static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
 
+#elif !defined(__CUDACC__)  /* plain host translation unit (g++): attributes only */
+
+#define PIP_DEV static inline
+#define PIP_DEVNI static __attribute__((noinline))
+#define PIP_HD static inline
+#define PIP_HDM inline
+#define PIP_HDNI static __attribute__((noinline, unused))
+
 #else  /* device */
 
 #define PIP_DEV __device__ __forceinline__
 #define PIP_DEVNI __device__ __noinline__
 #define PIP_HD __host__ __device__ __forceinline__
+#define PIP_HDM __host__ __device__ __forceinline__
 #define PIP_HDNI static __host__ __device__ __noinline__
 #define PIP_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 

@@ -17,7 +17,7 @@ class PipResult(C.Structure):
     _fields_ = [("status", C.c_int), ("ncells", C.c_int), ("cell_off", C.c_longlong),
                 ("pivots", C.c_uint), ("cuts", C.c_uint), ("subsolves", C.c_uint),
                 ("splits", C.c_uint), ("max_rows", C.c_uint), ("max_cols", C.c_uint),
-                ("wrapped", C.c_uint), ("elem_updates_lo", C.c_uint), ("elem_updates_hi", C.c_uint),
+                ("ser_words", C.c_uint), ("elem_updates_lo", C.c_uint), ("elem_updates_hi", C.c_uint),
                 ("pad", C.c_uint)]
 
 
@@ -29,7 +29,7 @@ PROBLEM_DTYPE = np.dtype([("nvar", "i4"), ("nparm", "i4"), ("ni", "i4"), ("nc", 
                           ("bigparm", "i4"), ("flags", "i4"), ("off", "i8")])
 RESULT_DTYPE = np.dtype([("status", "i4"), ("ncells", "i4"), ("cell_off", "i8"), ("pivots", "u4"),
                          ("cuts", "u4"), ("subsolves", "u4"), ("splits", "u4"), ("max_rows", "u4"),
-                         ("max_cols", "u4"), ("wrapped", "u4"), ("elem_updates_lo", "u4"),
+                         ("max_cols", "u4"), ("ser_words", "u4"), ("elem_updates_lo", "u4"),
                          ("elem_updates_hi", "u4"), ("pad", "u4")])
 CELL_DTYPE = np.dtype([("kind", "i4"), ("pad", "i4"), ("p1", "i8"), ("p2", "i8")])
 assert PROBLEM_DTYPE.itemsize == C.sizeof(PipProblem) == 32
