@@ -282,6 +282,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       CK(cudaEventRecord(E.ev1, s));
       CK(cudaStreamSynchronize(s));
       out.times.kernel += now_s() - tk;
+      if (round < 8) { out.times.round_s[round] = (float)(now_s() - tk); out.times.round_n[round] = m; }
       /* fetch records (+ cells) */
       double td = now_s();
       CK(cudaMemcpyAsync(h_res, E.d_res.p, n * sizeof(PipResult), cudaMemcpyDeviceToHost, s));

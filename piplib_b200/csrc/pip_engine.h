@@ -30,6 +30,8 @@ struct PipBatchTimes {
   int launches = 0, rounds = 0;
   size_t h2d_bytes = 0, d2h_bytes = 0;
   unsigned long long phase_cycles[PIP_NPHASE] = {0};   /* profile build only */
+  float round_s[8] = {0};                              /* wall seconds of each solve round */
+  int round_n[8] = {0};                                /* problems in each round */
 };
 
 /* read-only view of one problem's cells in the wire format (pip_types.h) */

@@ -1001,6 +1001,10 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
           if (device_decode) emit_chunk_ser(C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
           else emit_chunk(A, C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
           tstage[lane * 4 + 2] += te - td; tstage[lane * 4 + 3] += wall() - te;
+          if (timing)
+            fprintf(stderr, "[piplib-b200] chunk %zu lane %zu: rounds %d: %d problems %.3f s | %d problems %.3f s | %d problems %.3f s; d2h %.3f s\n", c, lane,
+                    C.out.times.rounds, C.out.times.round_n[0], C.out.times.round_s[0], C.out.times.round_n[1], C.out.times.round_s[1],
+                    C.out.times.round_n[2], C.out.times.round_s[2], C.out.times.d2h);
           /* the cell chunks are engine-owned and reused by the next run on this lane: drop the views */
           C.out.base.clear();
         }
