@@ -64,7 +64,7 @@ class PipEngine {
   static PipEngine &get() { return lane(0); }
   /* independent engines (own stream + buffers) so that batches can be pipelined: while one lane
    * waits for its kernels, another converts inputs or decodes results */
-  enum { MAX_LANES = 4 };
+  enum { MAX_LANES = 8 };
   static PipEngine &lane(int i);
   /* engine-owned pinned staging for the input pool (valid until the next call on this lane) */
   void *pinned_input(size_t bytes);

@@ -8,7 +8,7 @@ from piplib_b200 import api, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 dom, ctx = synth.generate("loopnest16x24p3", n)
-for chunk, lanes in [(131072, 3), (131072, 4), (65536, 3), (65536, 4), (98304, 4), (262144, 3), (262144, 4)]:
+for chunk, lanes in [(131072, 4), (131072, 6), (131072, 8), (65536, 6), (65536, 8), (43690, 8)]:
     os.environ["PIPLIB_B200_CHUNK"] = str(chunk)
     os.environ["PIPLIB_B200_LANES"] = str(lanes)
     best = 1e9
