@@ -211,7 +211,7 @@ def traiter_batch(cases):
     return out
 
 
-def solve_dense(dom, ctx, bignum=-1, want_hashes=True, want_ser=False, ser_cap_hint=None, **opts):
+def solve_dense(dom, ctx, bignum=-1, want_hashes=True, want_ser=False, ser_cap_hint=None, out=None, **opts):
     """dom: [n, rows, cols] int64 (host); ctx: [n, rows, cols] or None.
     Returns dict(status, hashes, ser, ser_off)."""
     L = lib()
@@ -223,16 +223,25 @@ def solve_dense(dom, ctx, bignum=-1, want_hashes=True, want_ser=False, ser_cap_h
         ctx = np.ascontiguousarray(ctx, dtype=np.int64)
         has, cr, cc = 1, ctx.shape[1], ctx.shape[2]
         cp = ctx.ctypes.data_as(C.c_void_p)
-    status = np.zeros(n, dtype=np.int32)
-    hashes = np.zeros(n, dtype=np.uint64) if want_hashes else None
+    # `out` = the dict returned by an earlier call of the same shape: its (caller-owned) result
+    # buffers are reused instead of allocating and page-faulting gigabytes again
+    reuse = out is not None and out["status"].shape[0] == n
+    status = out["status"] if reuse else np.zeros(n, dtype=np.int32)
+    hashes = None
+    if want_hashes:
+        hashes = out["hashes"] if reuse and out.get("hashes") is not None else np.zeros(n, dtype=np.uint64)
     o = make_options(**opts)
     ser = ser_off = ser_len = None
     cap = 0
     if want_ser:
-        ser_off = np.zeros(n + 1, dtype=np.int64)
-        ser_len = np.zeros(n, dtype=np.int64)
-        cap = (ser_cap_hint or 448) * n + 1024
-        ser = np.empty(cap, dtype=np.int64)
+        if reuse and out.get("ser") is not None:
+            ser, ser_off, ser_len = out["ser"], out["ser_off"], out["ser_len"]
+            cap = ser.shape[0]
+        else:
+            ser_off = np.zeros(n + 1, dtype=np.int64)
+            ser_len = np.zeros(n, dtype=np.int64)
+            cap = (ser_cap_hint or 448) * n + 1024
+            ser = np.empty(cap, dtype=np.int64)
     while True:
         rc = L.pip_solve_dense_dp(C.c_longlong(n), dr, dc, dom.ctypes.data_as(C.c_void_p), has, cr, cc, cp,
                                   int(bignum), C.byref(o), status.ctypes.data_as(C.c_void_p),
