@@ -53,6 +53,22 @@ PIP_HD pip_i64 pip_mod(pip_i64 a, pip_i64 b)
 }
 PIP_HD pip_i64 pip_floor_q(pip_i64 a, pip_i64 b) { return pip_div(a - pip_mod(a, b), b); }
 
+/* 32-bit overloads for the int32 instantiation of the solver (no 64-bit division subroutine) */
+PIP_HD int pip_gcd(int a, int b)
+{
+  unsigned x = a < 0 ? 0u - (unsigned)a : (unsigned)a, y = b < 0 ? 0u - (unsigned)b : (unsigned)b;
+  while (y) { unsigned r = x % y; x = y; y = r; }
+  return (int)x;
+}
+PIP_HD int pip_div(int a, int b) { return a / b; }
+PIP_HD int pip_mod(int a, int b)
+{
+  int m = a % b;
+  if (m < 0) m += (b < 0 ? -b : b);
+  return m;
+}
+PIP_HD int pip_floor_q(int a, int b) { return (a - pip_mod(a, b)) / b; }
+
 PIP_HD int pip_bitlen(pip_i64 x)
 {
   pip_u64 u = pip_uabs(x);

@@ -2,6 +2,7 @@
 #include "pip_engine.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -183,27 +184,34 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
   CK(cudaStreamSynchronize(s));
   out.times.h2d = now_s() - t0;
 
-  /* ---- plan: class S for everything whose level-2 working set fits a shared-memory arena */
-  std::vector<int> cls(n);              /* -1 = class S, k = G_LADDER[k] */
-  long long s_words = 0, est_cells_total = 0;
+  /* ---- plan: class S32 (int32 storage, shared memory) for problems shipped with narrow inputs,
+   * class S (int64, shared memory) for everything else whose level-2 working set fits an arena,
+   * the global-memory ladder for the rest */
+  const bool try32 = in.elem_log2 <= 2 && getenv("PIPLIB_B200_NO_INT32") == nullptr;
+  std::vector<int> cls(n);              /* -2 = class S32, -1 = class S, k = G_LADDER[k] */
+  long long s_words = 0, s32_words = 0, est_cells_total = 0;
   for (size_t i = 0; i < n; i++) {
     const PipProblem &P = in.h_prob[i];
-    long long w = pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2);
-    if (w <= S_MAX_WORDS) { cls[i] = -1; s_words = std::max(s_words, w); }
-    else {
+    long long w = pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2, 8);
+    if (w <= S_MAX_WORDS) {
+      cls[i] = try32 ? -2 : -1;
+      s_words = std::max(s_words, w);
+      if (try32) s32_words = std::max(s32_words, pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2, 4));
+    } else {
       int k = 0;
-      while (k < N_G - 1 && pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, G_LADDER[k].level) > G_LADDER[k].words) k++;
+      while (k < N_G - 1 && pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, G_LADDER[k].level, 8) > G_LADDER[k].words) k++;
       cls[i] = k;
     }
     est_cells_total += 3ll * (1 + P.nvar * (2 + P.nparm)) + 32;
   }
   s_words = (s_words + 1) & ~1ll;
+  s32_words = (s32_words + 1) & ~1ll;
 
   CK(cudaEventRecord(E.ev0, s));
   std::vector<int> order;
   order.reserve(n);
   int round = 0;
-  for (int k = -1; k < N_G; k++) {
+  for (int k = -2; k < N_G; k++) {
     for (int attempt = 0; attempt < 64; attempt++) {
       order.clear();
       for (size_t i = 0; i < n; i++) if (cls[i] == k) order.push_back((int)i);
@@ -213,13 +221,14 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       ClassSpec cs;
       int ctas;
       if (k < 0) {
-        cs.level = 2; cs.shared = 1; cs.words = std::max<long long>(s_words, 64);
+        cs.level = 2; cs.shared = (k == -2) ? 2 : 1;
+        cs.words = std::max<long long>(k == -2 ? s32_words : s_words, 64);
         cs.warps_per_cta = 4;
         cs.stack_words = 1ll << 14;
         size_t smem = (size_t)cs.warps_per_cta * cs.words * sizeof(pip_i64);
         if (smem > E.smem_optin) { cs.warps_per_cta = 1; smem = (size_t)cs.words * sizeof(pip_i64); }
         int per_sm = 1;
-        CK(pip_solve_occupancy(1, cs.warps_per_cta, smem, &per_sm));
+        CK(pip_solve_occupancy(cs.shared, cs.warps_per_cta, smem, &per_sm));
         if (per_sm < 1) per_sm = 1;
         ctas = E.sm_count * per_sm;
         int need = (m + cs.warps_per_cta - 1) / cs.warps_per_cta;
@@ -232,7 +241,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         cs.warps = ctas * cs.warps_per_cta;
       }
       /* cell pool: every warp must be able to hold one worst-case solution */
-      long long est = (k < 0 && attempt == 0) ? (est_cells_total * (long long)m / (long long)n) : 0;
+      long long est = (k < 0) ? (est_cells_total * (long long)m / (long long)n) : 0;
       long long per_warp = (est + est / 4) / cs.warps + 1 + in.sol_size;
       if (attempt > 0) per_warp = std::max<long long>(per_warp, 4ll * in.sol_size);
       E.d_cells.reserve((size_t)per_warp * cs.warps * sizeof(PipCell));
@@ -304,7 +313,8 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         const int i = order[q];
         const PipResult &r = h_res[i];
         if (r.status == PIP_ST_PENDING) { pending++; continue; }
-        if (r.status == PIP_ST_CAPACITY && k + 1 < N_G) { cls[i] = k + 1; h_res[i].status = PIP_ST_PENDING; continue; }
+        if (r.status == PIP_ST_WIDEN) { cls[i] = -1; h_res[i].status = PIP_ST_PENDING; continue; }
+        if (r.status == PIP_ST_CAPACITY && k + 1 < N_G) { cls[i] = k < 0 ? 0 : k + 1; h_res[i].status = PIP_ST_PENDING; continue; }
         cls[i] = 1000;                       /* final */
         out.res[i] = r;
         out.base[i] = (const pip_u64 *)chunk.p;
@@ -312,7 +322,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       if (pending == 0) {
         /* re-arm the escalated problems on the device */
         bool any_escalated = false;
-        for (int q = 0; q < m; q++) if (cls[order[q]] == k + 1) { any_escalated = true; break; }
+        for (int q = 0; q < m; q++) if (cls[order[q]] != 1000 && cls[order[q]] != k) { any_escalated = true; break; }
         if (any_escalated) {
           CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
           CK(cudaStreamSynchronize(s));

@@ -16,7 +16,7 @@
 
 extern __shared__ __align__(16) unsigned char pip_smem[];
 
-template <bool SH>
+template <bool SH, class V>
 __global__ void __launch_bounds__(PIP_CTA_THREADS, PIP_MIN_CTAS)
 pip_solve_kernel(const PipLaunch L)
 {
@@ -26,38 +26,51 @@ pip_solve_kernel(const PipLaunch L)
   pip_i64 *arena;
   if (SH) arena = (pip_i64 *)pip_smem + (size_t)warp_in_cta * L.work_words;
   else arena = L.gwork + (size_t)warp_id * L.work_words;
-  pip_warp_main(L, warp_id, arena);
+  pip_warp_main<V>(L, warp_id, arena);
 }
 
+/* shared_class: 0 = global-memory arena (int64), 1 = shared arena int64, 2 = shared arena int32 */
 extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, int ctas, int warps_per_cta,
                                         cudaStream_t stream)
 {
   if (shared_class) {
     size_t smem = (size_t)warps_per_cta * L->work_words * sizeof(pip_i64);
-    cudaError_t e = cudaFuncSetAttribute(pip_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    pip_solve_kernel<true><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
+    cudaError_t e;
+    if (shared_class == 2) {
+      e = cudaFuncSetAttribute(pip_solve_kernel<true, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      pip_solve_kernel<true, int><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
+    } else {
+      e = cudaFuncSetAttribute(pip_solve_kernel<true, pip_i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      pip_solve_kernel<true, pip_i64><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
+    }
   } else {
-    pip_solve_kernel<false><<<ctas, warps_per_cta * 32, 0, stream>>>(*L);
+    pip_solve_kernel<false, pip_i64><<<ctas, warps_per_cta * 32, 0, stream>>>(*L);
   }
   return cudaGetLastError();
 }
 
 extern "C" cudaError_t pip_solve_occupancy(int shared_class, int warps_per_cta, size_t smem_bytes, int *ctas_per_sm)
 {
-  if (shared_class) {
-    cudaError_t e = cudaFuncSetAttribute(pip_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (shared_class == 2) {
+    cudaError_t e = cudaFuncSetAttribute(pip_solve_kernel<true, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<true>, warps_per_cta * 32, smem_bytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<true, int>, warps_per_cta * 32, smem_bytes);
   }
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<false>, warps_per_cta * 32, 0);
+  if (shared_class) {
+    cudaError_t e = cudaFuncSetAttribute(pip_solve_kernel<true, pip_i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<true, pip_i64>, warps_per_cta * 32, smem_bytes);
+  }
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<false, pip_i64>, warps_per_cta * 32, 0);
 }
 
 /* words of working arena a problem needs at a slack level (host-side planning) */
-extern "C" long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level)
+extern "C" long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level, int vbytes)
 {
   PipLayout L;
-  pip_layout(nvar, nparm, ni, nc, flags, level, 0x7fffffff, L);
+  pip_layout(nvar, nparm, ni, nc, flags, level, 0x7fffffff, vbytes, L);
   return L.total;
 }
 

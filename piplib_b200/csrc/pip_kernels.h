@@ -22,7 +22,7 @@ cudaError_t pip_launch_gather(PipResult *res, const int *order, const PipCell *c
 cudaError_t pip_launch_serialize(PipResult *res, const int *order, const PipCell *cells, const PipDecodeParm *parm,
                                  const long long *dst_off, pip_i64 *out, pip_u64 *hashes, int nprob, int pass,
                                  cudaStream_t stream);
-long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level);
+long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level, int vbytes);
 #ifdef __cplusplus
 }
 #endif

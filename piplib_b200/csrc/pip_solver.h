@@ -76,8 +76,9 @@ struct PipLayout {
 };
 
 /* Carve the arena for one problem.  Returns false when even this slack level does not fit. */
-PIP_HD bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level, int words, PipLayout &L)
+PIP_HD bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level, int words, int vbytes, PipLayout &L)
 {
+#define PIP_W(n) ((int)(((long long)(n) * vbytes + 7) / 8))   /* words holding n stored values */
   int dp, dr, dx, ds;
   pip_slack(level, dp, dr, dx, ds);
   const bool integer = (flags & PIP_F_INT) != 0;
@@ -94,16 +95,17 @@ PIP_HD bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level
   int o = 0;
   L.m.det = o; o += 4;
   L.s.det = o; o += 4;
-  L.cut = o; o += (C + 3) & ~1;
-  L.m.den = o; o += Pm;
+  L.cut = o; o += PIP_W(C + 3);
+  L.m.den = o; o += PIP_W(Pm);
   L.m.fl = o; o += (Pm + 1) / 2;
   L.tmp = o; o += ((Pm > SP ? Pm : SP) + 1) / 2;
-  L.m.data = o; o += R * C;
-  L.ctx = o; o += XR * XC;
-  L.s.den = o; o += SP;
+  L.m.data = o; o += PIP_W(R * C);
+  L.ctx = o; o += PIP_W(XR * XC);
+  L.s.den = o; o += PIP_W(SP);
   L.s.fl = o; o += (SP + 1) / 2;
-  L.s.data = o; o += SR * XC;
+  L.s.data = o; o += PIP_W(SR * XC);
   L.total = o;
+#undef PIP_W
   L.m.stride = C; L.m.pcap = Pm; L.m.rcap = R;
   L.m.nvar = nvar; L.m.nparm = nparm; L.m.ni = ni; L.m.ldet = 1;
   L.s.stride = XC; L.s.pcap = SP; L.s.rcap = SR;
@@ -112,13 +114,40 @@ PIP_HD bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level
   return o <= words;
 }
 
+/* value-type traits: the solver is instantiated for int64 (the reference's arithmetic, wrapping)
+ * and for int32 storage with exact 64-bit intermediates (typical polyhedral problems never leave
+ * 31 bits; a value that would is flagged and the problem is re-run by the int64 instantiation, so
+ * the answers are identical by construction) */
+template <class V> struct PipVal;
+template <> struct PipVal<pip_i64> {
+  enum { bytes = 8, narrow = 0 };
+  PIP_HDM static pip_i64 mulsub(pip_i64 a, pip_i64 l, pip_i64 b, pip_i64 f, unsigned &)
+  { return (pip_i64)((pip_u64)a * (pip_u64)l - (pip_u64)b * (pip_u64)f); }
+  PIP_HDM static pip_i64 mul(pip_i64 a, pip_i64 b, unsigned &) { return (pip_i64)((pip_u64)a * (pip_u64)b); }
+  PIP_HDM static pip_i64 cross(pip_i64 p, pip_i64 a, pip_i64 b, pip_i64 f)
+  { return (pip_i64)((pip_u64)p * (pip_u64)a - (pip_u64)b * (pip_u64)f); }
+  PIP_HDM static pip_i64 store(pip_i64 v, unsigned &) { return v; }
+};
+template <> struct PipVal<int> {
+  enum { bytes = 4, narrow = 1 };
+  /* values are kept inside (-2^31+16, 2^31-16) so that the +-1 adjustments of the algorithm stay exact */
+  PIP_HDM static int store(pip_i64 z, unsigned &ovf)
+  { ovf |= (unsigned)(((pip_u64)(z + 0x7ffffff0LL)) > 0xffffffe0ULL); return (int)z; }
+  PIP_HDM static int mulsub(int a, int l, int b, int f, unsigned &ovf)
+  { return store((pip_i64)a * l - (pip_i64)b * f, ovf); }
+  PIP_HDM static int mul(int a, int b, unsigned &ovf) { return store((pip_i64)a * b, ovf); }
+  PIP_HDM static pip_i64 cross(int p, int a, int b, int f) { return (pip_i64)p * a - (pip_i64)b * f; }
+};
+
+template <class V>
+struct PipSolver {
 /* ---- small accessors ------------------------------------------------------------------- */
-PIP_DEV int *pip_fl(pip_i64 *B, const PipTab &T) { return (int *)(B + T.fl); }
-PIP_DEV pip_i64 *pip_den(pip_i64 *B, const PipTab &T) { return B + T.den; }
-PIP_DEV pip_i64 *pip_row(pip_i64 *B, const PipTab &T, int slot) { return B + T.data + slot * T.stride; }
+PIP_SDEV int *pip_fl(pip_i64 *B, const PipTab &T) { return (int *)(B + T.fl); }
+PIP_SDEV V *pip_den(pip_i64 *B, const PipTab &T) { return (V *)(B + T.den); }
+PIP_SDEV V *pip_row(pip_i64 *B, const PipTab &T, int slot) { return (V *)(B + T.data) + slot * T.stride; }
 
 /* chercher_xx, source/traiter.c:39-44: first position in [from, n) whose flag meets the mask */
-PIP_DEVNI int pip_first_flag_impl(const int *fl, int mask, int from, int n)
+PIP_SDEVNI int pip_first_flag_impl(const int *fl, int mask, int from, int n)
 {
   const int lane = W::lane();
   #pragma unroll 1
@@ -131,14 +160,14 @@ PIP_DEVNI int pip_first_flag_impl(const int *fl, int mask, int from, int n)
   return n;
 }
 
-PIP_DEV int pip_first_flag(pip_i64 *B, const PipTab &T, int mask, int from, int n)
+PIP_SDEV int pip_first_flag(pip_i64 *B, const PipTab &T, int mask, int from, int n)
 {
   return pip_first_flag_impl(pip_fl(B, T), mask, from, n);
 }
 
 /* warp-cooperative 2-D copy (rows x cols words) between arbitrary strides; one out-of-line copy
  * of this loop serves problem load, sub-tableau construction and the frame stack */
-PIP_DEVNI void pip_copy2d(pip_i64 *dst, int dstride, const pip_i64 *src, int sstride, int rows, int cols)
+PIP_SDEVNI void pip_copy2d(V *dst, int dstride, const V *src, int sstride, int rows, int cols)
 {
   if (cols <= 0) return;
   int r = 0, j = W::lane();
@@ -152,9 +181,10 @@ PIP_DEVNI void pip_copy2d(pip_i64 *dst, int dstride, const pip_i64 *src, int sst
 
 /* problem load: like pip_copy2d but the source elements are int8 / int32 / int64 (the host ships
  * the narrowest width that holds the whole batch) */
-PIP_DEVNI void pip_load2d(pip_i64 *dst, int dstride, const void *src, int elem_log2, pip_i64 src_off, int rows, int cols)
+PIP_SDEVNI unsigned pip_load2d(V *dst, int dstride, const void *src, int elem_log2, pip_i64 src_off, int rows, int cols)
 {
-  if (cols <= 0) return;
+  unsigned ovf = 0;
+  if (cols <= 0) return 0;
   int r = 0, j = W::lane();
   while (j >= cols) { j -= cols; r++; }
   while (r < rows) {
@@ -163,15 +193,16 @@ PIP_DEVNI void pip_load2d(pip_i64 *dst, int dstride, const void *src, int elem_l
     if (elem_log2 == 3) v = ((const pip_i64 *)src)[k];
     else if (elem_log2 == 2) v = ((const int *)src)[k];
     else v = ((const signed char *)src)[k];
-    dst[r * dstride + j] = v;
+    dst[r * dstride + j] = PipVal<V>::store(v, ovf);
     j += 32;
     while (j >= cols) { j -= cols; r++; }
   }
+  return ovf;
 }
 
 /* one term of the row "size" with a non-unit denominator: |(int)(double(v)/double(d))| or 0
  * when the conversion is out of range (source/traiter.c:580-584) */
-PIP_DEVNI unsigned pip_size_term(pip_i64 v, pip_i64 d)
+PIP_SDEVNI unsigned pip_size_term(pip_i64 v, pip_i64 d)
 {
   double t = pip_ll2d(v) / pip_ll2d(d);
   double a = t < 0 ? -t : t;
@@ -180,13 +211,13 @@ PIP_DEVNI unsigned pip_size_term(pip_i64 v, pip_i64 d)
 }
 
 /* tab_simplify_xx, source/tab.c:396-427 on `rows` rows of `width` words (lane = row) */
-PIP_DEVNI bool pip_simplify_rows(pip_i64 *base, int rows, int stride, int width, int cst)
+PIP_SDEVNI bool pip_simplify_rows(V *base, int rows, int stride, int width, int cst)
 {
   bool fault = false;
   #pragma unroll 1
   for (int r = W::lane(); r < rows; r += 32) {
-    pip_i64 *row = base + r * stride;
-    pip_i64 g = 0;
+    V *row = base + r * stride;
+    V g = 0;
     #pragma unroll 1
     for (int j = 0; j < width; j++) {
       if (j == cst) continue;
@@ -204,20 +235,20 @@ PIP_DEVNI bool pip_simplify_rows(pip_i64 *base, int rows, int stride, int width,
 /* tab_sort_rows_xx, source/traiter.c:556-623.  size = max_j |(int)(double(T[i][j])/double(d))|
  * stored as float; an out-of-range (int) conversion is INT_MIN on the reference's x86-64 and
  * never raises the maximum.  Selection sort by first minimum strictly below smax. */
-PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
+PIP_SDEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
 {
   const int lane = W::lane();
   const int nl = T.nvar + T.ni;
   int *fl = pip_fl(B, T);
-  pip_i64 *den = pip_den(B, T);
+  V *den = pip_den(B, T);
   float *sz = (float *)(B + tmpoff);
   unsigned smax_u = 0;
   #pragma unroll 1
   for (int k = T.nvar + lane; k < nl; k += 32) {
     int f = fl[k];
     if (f & PIP_UNIT) continue;
-    const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
-    pip_i64 d = den[k];
+    const V *row = pip_row(B, T, PIP_LINK(f));
+    V d = den[k];
     unsigned s = 0;
     if (d == 1) {
       #pragma unroll 1
@@ -244,7 +275,7 @@ PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
     const int k = T.nvar + lane;
     const bool in = lane < T.ni;
     int f = in ? fl[k] : PIP_UNIT;
-    pip_i64 d = in ? den[k] : 0;
+    V d = in ? den[k] : 0;
     unsigned sb = in ? pip_f2u(sz[k]) : 0u;
     const bool movable = in && !(f & PIP_UNIT);
     /* nothing moves when the movable rows are already in non-decreasing order */
@@ -304,7 +335,7 @@ PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
       W::sync();
       if (lane == 0) {
         int f = fl[i]; fl[i] = fl[bestk]; fl[bestk] = f;
-        pip_i64 d = den[i]; den[i] = den[bestk]; den[bestk] = d;
+        V d = den[i]; den[i] = den[bestk]; den[bestk] = d;
         float s = sz[i]; sz[i] = sz[bestk]; sz[bestk] = s;
       }
       W::sync();
@@ -314,7 +345,7 @@ PIP_DEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
 }
 
 /* exam_coef_xx, source/traiter.c:101-159.  Returns the first row proved negative or nl. */
-PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
+PIP_SDEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
 {
   const int lane = W::lane();
   const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
@@ -325,7 +356,7 @@ PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
       int k = base + lane;
       int f = k < nl ? fl[k] : 0;
       bool unk = PIP_FLAG(f) == PIP_UNKNOWN;
-      pip_i64 v = unk ? pip_row(B, T, PIP_LINK(f))[bigparm] : 0;
+      V v = unk ? pip_row(B, T, PIP_LINK(f))[bigparm] : 0;
       unsigned mneg = W::ballot(unk && v < 0);
       int first = mneg ? pip_ffs(mneg) - 1 : 32;
       if (unk && v > 0 && lane < first) fl[k] = PIP_MKFL(PIP_PLUS, PIP_LINK(f));
@@ -344,17 +375,17 @@ PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
     bool unk = PIP_FLAG(f) == PIP_UNKNOWN;
     int ff = PIP_ZERO;
     if (unk) {
-      const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+      const V *row = pip_row(B, T, PIP_LINK(f));
       #pragma unroll 1
       for (int j = T.nvar + 1; j < ncol; j++) {
-        pip_i64 v = row[j];
+        V v = row[j];
         int fff = v < 0 ? PIP_MINUS : v > 0 ? PIP_PLUS : PIP_ZERO;
         if (fff != PIP_ZERO && fff != ff) {
           if (ff == PIP_ZERO) ff = fff;
           else { ff = PIP_UNKNOWN; break; }
         }
       }
-      pip_i64 c = row[T.nvar];
+      V c = row[T.nvar];
       int fff = c < 0 ? PIP_MINUS : c > 0 ? PIP_PLUS : PIP_ZERO;
       if (ff == PIP_PLUS) { if (fff == PIP_MINUS) ff = PIP_UNKNOWN; }
       else if (ff == PIP_ZERO) ff = fff;
@@ -371,7 +402,7 @@ PIP_DEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
 
 /* chercher(Minus) + exam_coef for a tableau of at most 32 positions: one register-resident pass
  * (source/traiter.c:669-680); returns the pivot row or nl */
-PIP_DEV int pip_scan32(pip_i64 *B, const PipTab &T, int bigparm)
+PIP_SDEV int pip_scan32(pip_i64 *B, const PipTab &T, int bigparm)
 {
   const int lane = W::lane();
   const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
@@ -379,11 +410,11 @@ PIP_DEV int pip_scan32(pip_i64 *B, const PipTab &T, int bigparm)
   int f = lane < nl ? fl[lane] : 0;
   unsigned m = W::ballot((f & PIP_MINUS) != 0);
   if (m) return pip_ffs(m) - 1;
-  const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+  const V *row = pip_row(B, T, PIP_LINK(f));
   bool dirty = false;
   if (bigparm >= 0) {
     const bool unk = PIP_FLAG(f) == PIP_UNKNOWN;
-    const pip_i64 v = unk ? row[bigparm] : 0;
+    const V v = unk ? row[bigparm] : 0;
     m = W::ballot(unk && v < 0);
     const int first = m ? pip_ffs(m) - 1 : 32;
     if (unk && v > 0 && lane < first) { f = PIP_MKFL(PIP_PLUS, PIP_LINK(f)); fl[lane] = f; }
@@ -398,14 +429,14 @@ PIP_DEV int pip_scan32(pip_i64 *B, const PipTab &T, int bigparm)
   if (unk) {
     #pragma unroll 1
     for (int j = T.nvar + 1; j < ncol; j++) {
-      const pip_i64 v = row[j];
+      const V v = row[j];
       const int fff = v < 0 ? PIP_MINUS : v > 0 ? PIP_PLUS : PIP_ZERO;
       if (fff != PIP_ZERO && fff != ff) {
         if (ff == PIP_ZERO) ff = fff;
         else { ff = PIP_UNKNOWN; break; }
       }
     }
-    const pip_i64 c = row[T.nvar];
+    const V c = row[T.nvar];
     const int fff = c < 0 ? PIP_MINUS : c > 0 ? PIP_PLUS : PIP_ZERO;
     if (ff == PIP_PLUS) { if (fff == PIP_MINUS) ff = PIP_UNKNOWN; }
     else if (ff == PIP_ZERO) ff = fff;
@@ -420,7 +451,7 @@ PIP_DEV int pip_scan32(pip_i64 *B, const PipTab &T, int bigparm)
 }
 
 /* valeur_xx, source/traiter.c:246-252 */
-PIP_DEV pip_i64 pip_entry(pip_i64 *B, const PipTab &T, int f, pip_i64 d, int j)
+PIP_SDEV V pip_entry(pip_i64 *B, const PipTab &T, int f, V d, int j)
 {
   if (f & PIP_UNIT) return PIP_LINK(f) == j ? d : 0;
   return pip_row(B, T, PIP_LINK(f))[j];
@@ -429,15 +460,15 @@ PIP_DEV pip_i64 pip_entry(pip_i64 *B, const PipTab &T, int f, pip_i64 d, int j)
 /* choisir_piv_xx, source/traiter.c:297-341: lexicographic pivot column.  For each candidate
  * column the difference x_k = pivot*val(k,j) - val(k,pivj)*foo is evaluated for 32 positions at
  * a time; the first non-zero x in position order decides. */
-PIP_DEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, pip_i64 &pivot_out)
+PIP_SDEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, V &pivot_out)
 {
   const int lane = W::lane();
   const int nl = T.nvar + T.ni;
   const int *fl = pip_fl(B, T);
-  const pip_i64 *den = pip_den(B, T);
-  const pip_i64 *prow = pip_row(B, T, PIP_LINK(fl[pivi]));
+  const V *den = pip_den(B, T);
+  const V *prow = pip_row(B, T, PIP_LINK(fl[pivi]));
   int pivj = -1;
-  pip_i64 pivot = 0;
+  V pivot = 0;
   #pragma unroll 1
   for (int cb = 0; cb < T.nvar; cb += 32) {
     int jc = cb + lane;
@@ -445,7 +476,7 @@ PIP_DEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, pip_i64 &pi
     while (cand) {
       int j = cb + pip_ffs(cand) - 1;
       cand &= cand - 1;
-      pip_i64 foo = prow[j];
+      V foo = prow[j];
       if (pivj < 0) { pivj = j; pivot = foo; continue; }
       bool neg = false;
       #pragma unroll 1
@@ -454,17 +485,17 @@ PIP_DEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, pip_i64 &pi
         pip_i64 x = 0;
         if (k < nl) {
           int f = fl[k];
-          pip_i64 a, b;
+          V a, b;
           if (f & PIP_UNIT) {
             int u = PIP_LINK(f);
-            pip_i64 d = den[k];
+            V d = den[k];
             a = (u == j) ? d : 0;
             b = (u == pivj) ? d : 0;
           } else {
-            const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+            const V *row = pip_row(B, T, PIP_LINK(f));
             a = row[j]; b = row[pivj];
           }
-          x = (pip_i64)((pip_u64)pivot * (pip_u64)a - (pip_u64)b * (pip_u64)foo);
+          x = PipVal<V>::cross(pivot, a, b, foo);
         }
         unsigned nz = W::ballot(x != 0);
         if (nz) {
@@ -482,25 +513,26 @@ PIP_DEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, pip_i64 &pi
 
 /* pivoter_xx, source/traiter.c:345-548.
  * returns 0 done, -1 no positive coefficient (infeasible), or a PIP_ST_* fatal status */
-PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
+PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
 {
   const int lane = W::lane();
   const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
   int *fl = pip_fl(B, T);
-  pip_i64 *den = pip_den(B, T);
-  pip_i64 pivot;
+  V *den = pip_den(B, T);
+  V pivot;
   const int pivj = pip_choose_column(B, T, pivi, pivot);
   PIP_LAP(st, PIP_PH_CHOOSE);
   if (pivj < 0) return -1;
 
   const int pslot = PIP_LINK(fl[pivi]);
-  pip_i64 *prow = pip_row(B, T, pslot);
-  const pip_i64 dpiv = den[pivi];
-  /* determinant bookkeeping = the overflow verdict, source/traiter.c:394-447 (uniform) */
+  V *prow = pip_row(B, T, pslot);
+  const V dpiv = den[pivi];
+  /* determinant bookkeeping = the overflow verdict, source/traiter.c:394-447 (uniform, always
+   * in 64 bits: the factors grow up to 2^63) */
   {
-    pip_i64 d = pip_gcd(pivot, dpiv);
+    pip_i64 d = pip_gcd((pip_i64)pivot, (pip_i64)dpiv);
     if (d == 0) return PIP_ST_FAULT;
-    pip_i64 ppivot = pip_div(pivot, d), dppiv = pip_div(dpiv, d);
+    pip_i64 ppivot = pip_div((pip_i64)pivot, d), dppiv = pip_div((pip_i64)dpiv, d);
     pip_i64 *det = B + T.det;
     pip_i64 dv[PIP_MAX_DET];
     #pragma unroll 1
@@ -535,39 +567,40 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
   /* rank-1 update of every stored row but the pivot row (source/traiter.c:467-502), fused with
    * the re-flagging from the sign of the new pivot-column entry (source/traiter.c:518-529) */
   bool fault = false;
+  unsigned ovf = 0;
   #pragma unroll 1
   for (int k = lane; k < nl; k += 32) {
     if (k == pivi) continue;
     const int f = fl[k];
     if (f & PIP_UNIT) continue;
-    pip_i64 *row = pip_row(B, T, PIP_LINK(f));
-    pip_i64 foo = row[pivj];
-    const pip_i64 dk = den[k];
+    V *row = pip_row(B, T, PIP_LINK(f));
+    V foo = row[pivj];
+    const V dk = den[k];
     if (foo == 0 && dk == 1) continue;        /* identity update, g stays 1, sign Zero: no re-flag */
-    pip_i64 lpiv = pivot;
+    V lpiv = pivot;
     if (foo == 0) lpiv = 1;                    /* gcd(pivot,0) = pivot */
     else if (pivot != 1 && foo != 1 && foo != -1) {
-      pip_i64 d = pip_gcd(pivot, foo);
+      V d = pip_gcd(pivot, foo);
       if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
     }
-    const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
-    pip_i64 g = newden;
+    const V newden = PipVal<V>::mul(lpiv, dk, ovf);
+    V g = newden;
     /* pass 1: pure arithmetic.  The generic formula gives 0 in column pivj (foo*lpiv == pivot*foo'),
      * the real value dpiv*foo' is patched in afterwards, so the loop body has no special case */
     pip_u64 orz = 0;
     #pragma unroll 4
     for (int j = 0; j < ncol; j++) {
-      const pip_i64 z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
+      const V z = PipVal<V>::mulsub(row[j], lpiv, prow[j], foo, ovf);
       row[j] = z;
-      orz |= (pip_u64)z;
+      orz |= (pip_u64)(pip_i64)z;
     }
-    const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
+    const V zp = PipVal<V>::mul(dpiv, foo, ovf);
     row[pivj] = zp;
-    orz |= (pip_u64)zp;
+    orz |= (pip_u64)(pip_i64)zp;
     /* pass 2 (only when the row has a common factor to shed): g = gcd(newden, z_0 .. z_n).
      * A power-of-two g folds into the OR: gcd(2^a, z..) = lowest set bit of (2^a | z_0 | ..) */
     if (g != 1) {
-      if ((g & (g - 1)) == 0 && g > 0) { orz |= (pip_u64)g; g = (pip_i64)(orz & (0ull - orz)); }
+      if ((g & (g - 1)) == 0 && g > 0) { orz |= (pip_u64)(pip_i64)g; g = (V)(pip_i64)(orz & (0ull - orz)); }
       else {
         #pragma unroll 1
         for (int j = 0; j < ncol && g != 1; j++) g = pip_gcd(g, row[j]);
@@ -577,15 +610,15 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
       if (g == 0) { fault = true; continue; }
       if ((g & (g - 1)) == 0) {
         int sh = 0;
-        while (((pip_u64)g >> sh) != 1ull) sh++;
+        while (((pip_u64)(pip_i64)g >> sh) != 1ull) sh++;
         #pragma unroll 2
         for (int j = 0; j < ncol; j++) row[j] = row[j] >> sh;
         den[k] = newden >> sh;
       } else {
-        PipExactDiv e = pip_exact_prepare(g);
+        PipExactDiv e = pip_exact_prepare((pip_i64)g);
         #pragma unroll 2
-        for (int j = 0; j < ncol; j++) row[j] = pip_exact_apply(row[j], e);
-        den[k] = pip_exact_apply(newden, e);
+        for (int j = 0; j < ncol; j++) row[j] = (V)pip_exact_apply((pip_i64)row[j], e);
+        den[k] = (V)pip_exact_apply((pip_i64)newden, e);
       }
     } else den[k] = newden;
     /* sign of the new entry in column pivj = sign of zp (g > 0) */
@@ -597,6 +630,7 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
       fl[k] = PIP_MKFL(ff, PIP_LINK(f));
     }
   }
+  if (PipVal<V>::narrow && W::any(ovf != 0)) return PIP_ST_WIDEN;
   if (W::any(fault)) return PIP_ST_FAULT;
   W::sync();
   PIP_LAP(st, PIP_PH_UPDATE);
@@ -625,19 +659,19 @@ PIP_DEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
 }
 
 /* append one cell; returns true when it does not fit the packed wire format */
-PIP_DEV bool pip_put(PipCell *out, int idx, int kind, pip_i64 p1, pip_i64 p2)
+PIP_SDEV bool pip_put(PipCell *out, int idx, int kind, V p1, V p2)
 {
   out[idx].kind = kind; out[idx].pad = 0; out[idx].p1 = p1; out[idx].p2 = p2;
   return !PIP_CELL_FITS(p1, p2);
 }
 
 /* solution_xx, source/traiter.c:255-271: 1 + nvar*(2+nparm) cells, lane-parallel */
-PIP_DEVNI bool pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int at)
+PIP_SDEVNI bool pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int at)
 {
   bool wide = false;
   const int per = T.nparm + 2, total = 1 + T.nvar * per;
   const int *fl = pip_fl(B, T);
-  const pip_i64 *den = pip_den(B, T);
+  const V *den = pip_den(B, T);
   #pragma unroll 1
   for (int c = W::lane(); c < total; c += 32) {
     if (c == 0) { pip_put(out, at, PIP_C_LIST, T.nvar, 0); continue; }
@@ -645,18 +679,18 @@ PIP_DEVNI bool pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int 
     if (r == 0) { pip_put(out, at + c, PIP_C_FORM, T.nparm + 1, 0); continue; }
     int j = (r == per - 1) ? T.nvar : T.nvar + r;
     int f = fl[i];
-    pip_i64 d = den[i];
+    V d = den[i];
     wide = pip_put(out, at + c, PIP_C_VAL, pip_entry(B, T, f, d, j), d) || wide;
   }
   return wide;
 }
 
 /* has_cut_xx, source/integrer.c:230-254 (serial, one lane) */
-PIP_DEV bool pip_has_cut(const pip_i64 *ctx, int cstride, int nr, int nparm, int p, const pip_i64 *cut)
+PIP_SDEV bool pip_has_cut(const V *ctx, int cstride, int nr, int nparm, int p, const V *cut)
 {
   #pragma unroll 1
   for (int row = 0; row < nr; row++) {
-    const pip_i64 *r = ctx + row * cstride;
+    const V *r = ctx + row * cstride;
     if (r[p] != cut[1 + nparm]) continue;
     if (r[nparm] != cut[0]) continue;
     int col;
@@ -672,7 +706,7 @@ PIP_DEV bool pip_has_cut(const pip_i64 *ctx, int cstride, int nr, int nparm, int
 }
 
 /* find_parm_xx, source/integrer.c:258-291 (serial, one lane; cut = const, params, denominator) */
-PIP_DEV int pip_find_parm(const pip_i64 *ctx, int cstride, int nr, int nparm, pip_i64 *cut)
+PIP_SDEV int pip_find_parm(const V *ctx, int cstride, int nr, int nparm, V *cut)
 {
   if (cut[1 + nparm - 1] != 0) return -1;
   cut[0] = cut[0] + cut[1 + nparm] - 1;
@@ -695,7 +729,7 @@ PIP_DEV int pip_find_parm(const pip_i64 *ctx, int cstride, int nr, int nparm, pi
 
 /* The solver for one problem.  `B` is the warp's working arena (`words` words), `out` the
  * warp's cell window (at least sol_size cells free), `stk` the warp's frame stack. */
-PIP_DEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, int words, int slack_level,
+PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, int words, int slack_level,
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
                            int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st)
@@ -704,7 +738,7 @@ PIP_DEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2,
   const bool integer = (P.flags & PIP_F_INT) != 0;
   PipLayout L;
   int level_try = slack_level;
-  while (!pip_layout(P.nvar, P.nparm, P.ni, P.nc, P.flags, level_try, words, L)) {
+  while (!pip_layout(P.nvar, P.nparm, P.ni, P.nc, P.flags, level_try, words, (int)sizeof(V), L)) {
     if (--level_try < 0) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
   }
   if (P.flags & (PIP_F_DUAL | PIP_F_DEEPEST)) { status_out = PIP_ST_UNSUPPORTED; ncell_out = 0; return; }
@@ -717,26 +751,28 @@ PIP_DEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2,
   bool feasible = false, wide = false;
   rflags_out = 0;
   pip_i64 top = 0;
-  pip_i64 *ctx = B + L.ctx;
-  pip_i64 *cut = B + L.cut;
+  unsigned ovf = 0;                /* int32 instantiation: some value left the 31-bit range */
+  V *ctx = (V *)(B + L.ctx);
+  V *cut = (V *)(B + L.cut);
   const int cstride = L.cstride;
 
   /* ---- load: source/tab.c:222-248 (tab_get) + tab_simplify when an integer solution is wanted */
   {
     const int ncol = P.nvar + P.nparm + 1;
     int *fl = pip_fl(B, T);
-    pip_i64 *den = pip_den(B, T);
+    V *den = pip_den(B, T);
     #pragma unroll 1
     for (int k = lane; k < P.nvar + P.ni; k += 32) {
       if (k < P.nvar) { fl[k] = PIP_MKFL(PIP_UNIT, k); den[k] = 1; }
       else { fl[k] = PIP_MKFL(PIP_UNKNOWN, k - P.nvar); den[k] = 1; }
     }
-    pip_load2d(B + T.data, T.stride, pool, elem_log2, P.off, P.ni, ncol);
-    pip_load2d(ctx, cstride, pool, elem_log2, P.off + (pip_i64)P.ni * ncol, P.nc, P.nparm + 1);
+    ovf |= pip_load2d((V *)(B + T.data), T.stride, pool, elem_log2, P.off, P.ni, ncol);
+    ovf |= pip_load2d(ctx, cstride, pool, elem_log2, P.off + (pip_i64)P.ni * ncol, P.nc, P.nparm + 1);
     if (lane == 0) { B[L.m.det] = 1; B[L.s.det] = 1; }
     W::sync();
+    if (PipVal<V>::narrow && W::any(ovf != 0)) { status = PIP_ST_WIDEN; goto DONE; }
     if (integer) {
-      pip_simplify_rows(B + T.data, P.ni, T.stride, ncol, P.nvar);
+      pip_simplify_rows((V *)(B + T.data), P.ni, T.stride, ncol, P.nvar);
       pip_simplify_rows(ctx, P.nc, cstride, P.nparm + 1, P.nparm);
       W::sync();
     }
@@ -758,20 +794,20 @@ BUILD_SUB:
     S.nvar = np; S.nparm = 0; S.ni = nc + extra; S.ldet = 1;
     if (np + nc + extra > S.pcap || nc + extra > S.rcap || np + 1 > S.stride) { status = PIP_ST_CAPACITY; goto DONE; }
     int *sfl = pip_fl(B, S);
-    pip_i64 *sden = pip_den(B, S);
+    V *sden = pip_den(B, S);
     #pragma unroll 1
     for (int k = lane; k < np + nc + extra; k += 32) {
       sfl[k] = k < np ? PIP_MKFL(PIP_UNIT, k) : PIP_MKFL(PIP_UNKNOWN, k - np);
       sden[k] = 1;
     }
-    pip_copy2d(B + S.data, S.stride, ctx, cstride, nc, np + 1);
+    pip_copy2d((V *)(B + S.data), S.stride, ctx, cstride, nc, np + 1);
     if (extra) {
       const int f = pip_fl(B, M)[ci];
-      const pip_i64 *row = pip_row(B, M, PIP_LINK(f));
-      pip_i64 *nr = pip_row(B, S, nc);
+      const V *row = pip_row(B, M, PIP_LINK(f));
+      V *nr = pip_row(B, S, nc);
       #pragma unroll 1
       for (int j = lane; j <= np; j += 32) {
-        pip_i64 v = (j < np) ? row[M.nvar + 1 + j] : row[M.nvar];
+        V v = (j < np) ? row[M.nvar + 1 + j] : row[M.nvar];
         if (ret_site == 1) { if (j == np && !critic) v -= 1; }
         else { v = -v; if (j == np) v -= 1; }
         nr[j] = v;
@@ -811,7 +847,7 @@ COMPA_NEXT:
     const int nl = T.nvar + T.ni;
     ci = pip_first_flag(B, T, PIP_CRITIC | PIP_UNKNOWN, ci, nl);
     if (ci >= nl) goto AFTER_COMPA;
-    const pip_i64 *row = pip_row(B, T, PIP_LINK(pip_fl(B, T)[ci]));
+    const V *row = pip_row(B, T, PIP_LINK(pip_fl(B, T)[ci]));
     bool pos = false;
     #pragma unroll 1
     for (int j = lane; j < T.nvar; j += 32) pos = pos || row[j] > 0;
@@ -865,16 +901,16 @@ AFTER_COMPA:
     if (np >= maxparm) { status = PIP_ST_FATAL + 2; goto DONE; }
     if (ncell + np + 3 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
     int *fl = pip_fl(B, T);
-    const pip_i64 *row = pip_row(B, T, PIP_LINK(fl[pivi]));
-    pip_i64 g = 0;
+    const V *row = pip_row(B, T, PIP_LINK(fl[pivi]));
+    V g = 0;
     #pragma unroll 1
     for (int j = 0; j < np; j++) g = pip_gcd(g, row[T.nvar + 1 + j]);
     if (!integer) g = pip_gcd(g, row[T.nvar]);
     if (g == 0) { status = PIP_ST_FAULT; goto DONE; }
-    pip_i64 *crow = ctx + nc * cstride;
+    V *crow = ctx + nc * cstride;
     #pragma unroll 1
     for (int j = lane; j <= np; j += 32) {
-      pip_i64 v;
+      V v;
       if (j < np) v = pip_div(row[T.nvar + 1 + j], g);
       else v = integer ? pip_floor_q(row[T.nvar], g) : pip_div(row[T.nvar], g);
       crow[j] = v;
@@ -886,9 +922,13 @@ AFTER_COMPA:
     }
     ncell += np + 3;
     W::sync();
-    /* push the ELSE continuation */
+    /* push the ELSE continuation: 12 header words, den[nl], fl[nl], the ni stored rows, the
+     * nc+1 context rows (sections padded to whole 8-byte words), the frame size */
     {
-      const pip_i64 fsize = 12 + nl + (nl + 1) / 2 + (pip_i64)T.ni * ncol + (pip_i64)(nc + 1) * (np + 1) + 1;
+#define PIP_VW(n) (((pip_i64)(n) * (pip_i64)sizeof(V) + 7) / 8)
+      const pip_i64 wden = PIP_VW(nl), wfl = (nl + 1) / 2, wrows = PIP_VW((pip_i64)T.ni * ncol),
+                    wctx = PIP_VW((pip_i64)(nc + 1) * (np + 1));
+      const pip_i64 fsize = 12 + wden + wfl + wrows + wctx + 1;
       if (top + fsize > stk_cap) { status = PIP_ST_CAPACITY; goto DONE; }
       pip_i64 *F = stk + top;
       if (lane == 0) {
@@ -898,17 +938,18 @@ AFTER_COMPA:
         F[fsize - 1] = fsize;
       }
       pip_i64 *q = F + 12;
-      const pip_i64 *den = pip_den(B, T);
+      const V *den = pip_den(B, T);
+      V *qv = (V *)q;
       #pragma unroll 1
-      for (int k = lane; k < nl; k += 32) q[k] = den[k];
-      q += nl;
+      for (int k = lane; k < nl; k += 32) qv[k] = den[k];
+      q += wden;
       int *qi = (int *)q;
       #pragma unroll 1
       for (int k = lane; k < nl; k += 32) qi[k] = fl[k];
-      q += (nl + 1) / 2;
-      pip_copy2d(q, ncol, B + T.data, T.stride, T.ni, ncol);
-      q += (pip_i64)T.ni * ncol;
-      pip_copy2d(q, np + 1, ctx, cstride, nc + 1, np + 1);
+      q += wfl;
+      pip_copy2d((V *)q, ncol, (const V *)(B + T.data), T.stride, T.ni, ncol);
+      q += wrows;
+      pip_copy2d((V *)q, np + 1, ctx, cstride, nc + 1, np + 1);
       top += fsize;
     }
     W::sync();
@@ -934,21 +975,21 @@ NONNEG:
     const int nvar = T.nvar, np = T.nparm, ncol = nvar + np + 1, nl = nvar + T.ni;
     if (ncol >= maxcol) { status = PIP_ST_FATAL + 3; goto DONE; }
     int *fl = pip_fl(B, T);
-    pip_i64 *den = pip_den(B, T);
+    V *den = pip_den(B, T);
     int verdict = 0;     /* 0 integral, -1 none, >0 cut row */
     #pragma unroll 1
     for (int i = 0; i < nvar; i++) {
-      const pip_i64 D = den[i];
+      const V D = den[i];
       const int f = fl[i];
       if (D == 1) continue;
       if (f & PIP_UNIT) continue;
       if (D == 0) { status = PIP_ST_FAULT; goto DONE; }
-      const pip_i64 *row = pip_row(B, T, PIP_LINK(f));
+      const V *row = pip_row(B, T, PIP_LINK(f));
       bool okv = false, okc = false, okp = false;
       W::sync();
       #pragma unroll 1
       for (int j = lane; j < ncol; j += 32) {
-        pip_i64 v = row[j], x;
+        V v = row[j], x;
         if (j < nvar) { x = pip_mod(v, D); okv = okv || x > 0; }
         else if (j == nvar) { x = -pip_mod(-v, D); okc = okc || x != 0; }
         else if (!level && j == P.bigparm) x = 0;
@@ -970,7 +1011,7 @@ NONNEG:
           /* add_parm_xx, source/integrer.c:156-227 */
           if (nc + 2 > L.crcap || np + 2 > cstride || ncol + 1 > T.stride) { status = PIP_ST_CAPACITY; goto DONE; }
           if (ncell + np + 5 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
-          const pip_i64 *c = cut + nvar;
+          const V *c = cut + nvar;
           if (lane == 0) {
             pip_put(out, ncell, PIP_C_NEW, np, 0);
             pip_put(out, ncell + 1, PIP_C_DIV, 0, 0);
@@ -980,12 +1021,12 @@ NONNEG:
             wide = pip_put(out, ncell + 3 + np, PIP_C_VAL, -c[0], 1) || wide;
             wide = pip_put(out, ncell + 4 + np, PIP_C_VAL, c[1 + np], 1) || wide;
             #pragma unroll 1
-            for (int k = 0; k < nc; k++) { pip_i64 *r = ctx + k * cstride; r[np + 1] = r[np]; r[np] = 0; }
-            pip_i64 *r0 = ctx + nc * cstride, *r1 = r0 + cstride;
+            for (int k = 0; k < nc; k++) { V *r = ctx + k * cstride; r[np + 1] = r[np]; r[np] = 0; }
+            V *r0 = ctx + nc * cstride, *r1 = r0 + cstride;
             #pragma unroll 1
             for (int j = 0; j < np; j++) { r0[j] = -c[1 + j]; r1[j] = c[1 + j]; }
             r0[np] = -c[1 + np]; r1[np] = c[1 + np];
-            r0[np + 1] = -c[0]; r1[np + 1] = c[0] - 1 + c[1 + np];
+            r0[np + 1] = -c[0]; r1[np + 1] = PipVal<V>::store((pip_i64)c[0] - 1 + (pip_i64)c[1 + np], ovf);
           }
           /* the new parameter's tableau column starts at zero in every stored row */
           #pragma unroll 1
@@ -999,14 +1040,14 @@ NONNEG:
         if (!ok_var) { status = PIP_ST_FATAL + 134; goto DONE; }   /* assert(ok_var) */
       }
       {
-        pip_i64 *nr = pip_row(B, T, T.ni);
+        V *nr = pip_row(B, T, T.ni);
         #pragma unroll 1
         for (int j = lane; j < ncol; j += 32) nr[j] = cut[j];
         W::sync();
         if (lane == 0) {
           if (ok_parm) {
             if (parm == np) nr[ncol] = cut[ncol];           /* fresh column: 0 + D */
-            else nr[nvar + 1 + parm] += cut[ncol];
+            else nr[nvar + 1 + parm] = PipVal<V>::store((pip_i64)nr[nvar + 1 + parm] + (pip_i64)cut[ncol], ovf);
           }
           fl[nl] = PIP_MKFL(PIP_MINUS, T.ni);
           den[nl] = D;
@@ -1015,6 +1056,7 @@ NONNEG:
         st.cuts++;
         verdict = nl;
         W::sync();
+        if (PipVal<V>::narrow && W::any(ovf != 0)) { status = PIP_ST_WIDEN; goto DONE; }
       }
       break;
     }
@@ -1058,23 +1100,24 @@ LEAF:
     T.nvar = (int)F[0]; T.nparm = (int)F[1]; T.ni = (int)F[2]; nc = (int)F[3]; pivi = (int)F[4]; T.ldet = (int)F[5];
     const int np = T.nparm, ncol = T.nvar + np + 1, nl = T.nvar + T.ni;
     int *fl = pip_fl(B, T);
-    pip_i64 *den = pip_den(B, T);
+    V *den = pip_den(B, T);
     if (lane == 0) for (int k = 0; k < PIP_MAX_DET; k++) B[T.det + k] = F[8 + k];
     const pip_i64 *q = F + 12;
+    const V *qv = (const V *)q;
     #pragma unroll 1
-    for (int k = lane; k < nl; k += 32) den[k] = q[k];
-    q += nl;
+    for (int k = lane; k < nl; k += 32) den[k] = qv[k];
+    q += PIP_VW(nl);
     const int *qi = (const int *)q;
     #pragma unroll 1
     for (int k = lane; k < nl; k += 32) fl[k] = qi[k];
     q += (nl + 1) / 2;
-    pip_copy2d(B + T.data, T.stride, q, ncol, T.ni, ncol);
-    q += (pip_i64)T.ni * ncol;
-    pip_copy2d(ctx, cstride, q, np + 1, nc + 1, np + 1);
+    pip_copy2d((V *)(B + T.data), T.stride, (const V *)q, ncol, T.ni, ncol);
+    q += PIP_VW((pip_i64)T.ni * ncol);
+    pip_copy2d(ctx, cstride, (const V *)q, np + 1, nc + 1, np + 1);
     W::sync();
     #pragma unroll 1
     for (int j = lane; j <= np; j += 32) {                 /* the negated condition */
-      pip_i64 v = ctx[nc * cstride + j];
+      V v = ctx[nc * cstride + j];
       ctx[nc * cstride + j] = (j < np) ? -v : -(v + 1);
     }
     top -= fsize;
@@ -1094,5 +1137,7 @@ DONE:
   ncell_out = (status == PIP_ST_OK) ? ncell : 0;
   rflags_out = W::any(wide) ? PIP_RES_WIDE : 0u;
 }
+
+};
 
 #endif

@@ -44,7 +44,8 @@ enum {
   PIP_ST_FAULT = 2000,           /* division by zero: the reference dies of SIGFPE */
   PIP_ST_PENDING = 4000,         /* not solved yet (warp arena exhausted / not reached) */
   PIP_ST_CAPACITY = 4001,        /* exceeded the working-set capacity of its size class */
-  PIP_ST_UNSUPPORTED = 4002
+  PIP_ST_UNSUPPORTED = 4002,
+  PIP_ST_WIDEN = 4003            /* int32 instantiation: needs the int64 kernel */
 };
 
 typedef struct {

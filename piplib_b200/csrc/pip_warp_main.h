@@ -7,6 +7,7 @@
 
 #include "pip_solver.h"
 
+template <class V>
 PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
 {
   const int lane = W::lane();
@@ -30,7 +31,7 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
 #endif
     int status = PIP_ST_OK, ncell = 0;
     unsigned rflags = 0;
-    pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
+    PipSolver<V>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
                   L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st);
     if (lane == 0) {
       PipResult r;

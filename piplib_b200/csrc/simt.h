@@ -13,6 +13,8 @@
 
 #define PIP_DEV static inline
 #define PIP_DEVNI static __attribute__((noinline))
+#define PIP_SDEV static inline
+#define PIP_SDEVNI static __attribute__((noinline))
 #define PIP_HD static inline
 #define PIP_HDM inline
 #define PIP_HDNI static __attribute__((noinline))
@@ -71,6 +73,8 @@ static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); 
 
 #define PIP_DEV static inline
 #define PIP_DEVNI static __attribute__((noinline))
+#define PIP_SDEV static inline
+#define PIP_SDEVNI static __attribute__((noinline))
 #define PIP_HD static inline
 #define PIP_HDM inline
 #define PIP_HDNI static __attribute__((noinline, unused))
@@ -79,6 +83,8 @@ static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); 
 
 #define PIP_DEV __device__ __forceinline__
 #define PIP_DEVNI __device__ __noinline__
+#define PIP_SDEV static __device__ __forceinline__
+#define PIP_SDEVNI static __device__ __noinline__
 #define PIP_HD __host__ __device__ __forceinline__
 #define PIP_HDM __host__ __device__ __forceinline__
 #define PIP_HDNI static __host__ __device__ __noinline__

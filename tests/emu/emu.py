@@ -18,7 +18,7 @@ def build():
 
 
 def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_level=2, order_mode=0,
-                        sol_size=0, maxcol=0):
+                        sol_size=0, maxcol=0, narrow=0):
     lib = C.CDLL(SO)
     probs, pool = pack_tableau_problems(cases)
     n = len(probs)
@@ -28,7 +28,7 @@ def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_le
     lib.pipemu_solve_batch(probs.ctypes.data_as(C.c_void_p), n, pool.ctypes.data_as(C.c_void_p),
                            res.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p),
                            C.c_longlong(cap), work_words, C.c_longlong(stack_words), slack_level,
-                           order_mode, sol_size, maxcol)
+                           order_mode, sol_size, maxcol, narrow)
     out = []
     for i in range(n):
         r = res[i]

@@ -10,14 +10,19 @@ void run_warp(void (*fn)(void *, int), void *arg);
 void set_order(int mode);
 }
 
-struct EmuArgs { PipLaunch L; pip_i64 *arena; };
+struct EmuArgs { PipLaunch L; pip_i64 *arena; int narrow; };
 
-static void warp_entry(void *a, int) { EmuArgs *e = (EmuArgs *)a; pip_warp_main(e->L, 0, e->arena); }
+static void warp_entry(void *a, int)
+{
+  EmuArgs *e = (EmuArgs *)a;
+  if (e->narrow) pip_warp_main<int>(e->L, 0, e->arena);
+  else pip_warp_main<pip_i64>(e->L, 0, e->arena);
+}
 
 extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i64 *pool, PipResult *res,
                                   PipCell *cells, long long cells_cap, int work_words,
                                   long long stack_words, int slack_level, int order_mode,
-                                  int sol_size, int maxcol)
+                                  int sol_size, int maxcol, int narrow)
 {
   EmuArgs e;
   unsigned queue[2] = {0, 0};
@@ -31,6 +36,7 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
   e.L.maxcol = maxcol > 0 ? maxcol : PIP_MAXCOL;
   e.L.maxparm = PIP_MAXPARM;
   e.L.slack_level = slack_level;
+  e.narrow = narrow;
   e.arena = (pip_i64 *)malloc(sizeof(pip_i64) * (size_t)work_words);
   memset(e.arena, 0x5a, sizeof(pip_i64) * (size_t)work_words);   // poison: nothing may rely on zeros
   for (int i = 0; i < nprob; i++) res[i].status = PIP_ST_PENDING;
