@@ -181,3 +181,42 @@ def test_large_tableau_consecutive_ones(api, port, n):
     assert ms > 0 and ms2 > 0
     assert st == st_o and [tuple(x) for x in cells] == cells_o
     assert (st2, cells2) == (st, cells) and info["pivots"] > 0
+
+
+def test_int32_and_int64_instantiations_agree_at_scale(api, port, monkeypatch):
+    """200 000 problems of the bench workload: the int32-storage kernel (class S32, widen-and-rerun)
+    and the int64 kernel give the same status, quast hash and serialised stream for every problem;
+    a 2000-problem sample is checked against the oracle; pivot totals agree"""
+    from piplib_b200 import synth
+    n = 200000
+    dom, ctx = synth.generate("loopnest16x24p3", n, seed=2026)
+    a = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+    piv_a = int(api.last_stats().pivots)
+    monkeypatch.setenv("PIPLIB_B200_NO_INT32", "1")
+    monkeypatch.setenv("PIPLIB_B200_HOST_DECODE", "1")       # also crosses device vs host decoder
+    b = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+    piv_b = int(api.last_stats().pivots)
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["hashes"], b["hashes"])
+    assert np.array_equal(a["ser_len"], b["ser_len"])
+    assert piv_a >= piv_b          # the int32 pass re-runs the few widened problems
+    for i in range(0, n, 997):
+        x = a["ser"][a["ser_off"][i]:a["ser_off"][i] + a["ser_len"][i]]
+        y = b["ser"][b["ser_off"][i]:b["ser_off"][i] + b["ser_len"][i]]
+        assert np.array_equal(x, y)
+    m = 2000
+    _, st_o, h_o, _ = port.bench_dense(0, m, dom[:m], ctx[:m], -1)
+    st_g = np.where(a["status"][:m] == 1, 0, a["status"][:m])
+    assert np.array_equal(st_g, st_o) and np.array_equal(a["hashes"][:m][st_o == 0], h_o[st_o == 0])
+
+
+def test_edge_cases(api, port):
+    """empty batch, a problem without rows, no unknowns, a context without rows"""
+    assert api.traiter_batch([]) == []
+    r = api.solve_dense(np.zeros((0, 3, 4), dtype=np.int64), None, -1)
+    assert r["status"].shape == (0,)
+    # no constraints at all: every unknown is 0
+    st, ser = api.solve(np.zeros((0, 4), dtype=np.int64).reshape(0, 4), None, -1)
+    assert (st, ser) == port.solve(np.zeros((0, 4), dtype=np.int64), None, -1)
+    # parameters but an empty context (0 x Np+2 matrix, doc/piplib.texi:2097-2102)
+    st, ser = api.solve([[1, 1, -1, 0]], np.zeros((0, 3), dtype=np.int64), -1, ctx_cols=3)
+    assert (st, ser) == port.solve([[1, 1, -1, 0]], np.zeros((0, 3), dtype=np.int64), -1, ctx_cols=3)
