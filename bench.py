@@ -286,6 +286,11 @@ def main():
         in_bytes = dom.shape[1] * (dom.shape[2] - 1) * 8 + ctx.shape[1] * (ctx.shape[2] - 1) * 8 + 32
         alg_bytes = float(B) * (in_bytes + 56) + 8.0 * cells_step
         achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "r1_solve_kernel_traffic.json")
+        if os.path.exists(tj):
+            t = json.load(open(tj))
+            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["problems"] * B
         uniq, counts = np.unique(status, return_counts=True)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -300,7 +305,8 @@ def main():
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+                         "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
+                         "algorithmic_bytes": alg_bytes,
                          "note": "class-S kernel keeps the tableau in shared memory: HBM sees only "
                                  "inputs+cells; the binding resource is the INT pipe / issue slots "
                                  "(see elem_updates_per_sec and profiles/)"},
