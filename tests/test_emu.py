@@ -71,3 +71,19 @@ def test_large_tableau_consecutive_ones_vs_oracle(port):
     st_o, cells_o = port.traiter(nvar, 0, nvar, 0, -1, 1, tab, [])
     st, cells, info = emu.solve_large(case, cut_rows=64)
     assert st == st_o and [tuple(x) for x in cells] == cells_o and info[0] > 0
+
+
+@pytest.mark.parametrize("order_mode", [0, 2])
+def test_int32_instantiation_is_exact_or_widens(order_mode):
+    """PipSolver<int> (int32 storage, exact 64-bit intermediates): every fixture either gives the
+    reference's cells or reports WIDEN (4003), never a different answer"""
+    cases = CLI + [c for c in RCLI if c["name"] not in HEAVY]
+    out = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=order_mode, narrow=1)
+    bad, widened = [], 0
+    for c, (st, cells, _) in zip(cases, out):
+        if st == 4003:
+            widened += 1
+        elif st != c["ref_status"] or cells != c["ref_cells"]:
+            bad.append(c["name"])
+    assert not bad, bad
+    assert 0 < widened < len(cases) // 3
