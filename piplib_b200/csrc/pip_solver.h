@@ -170,12 +170,16 @@ PIP_SDEV int pip_first_flag(pip_i64 *B, const PipTab &T, int mask, int from, int
 PIP_SDEVNI void pip_copy2d(V *dst, int dstride, const V *src, int sstride, int rows, int cols)
 {
   if (cols <= 0) return;
-  int r = 0, j = W::lane();
-  while (j >= cols) { j -= cols; r++; }
+  /* lane walks the (row, column) grid in steps of 32 elements: one division up front, then a
+   * constant-time carry per step */
+  const int lane = W::lane();
+  int r = lane / cols, j = lane - r * cols;
+  const int dr = 32 / cols, dj = 32 - dr * cols;
+  #pragma unroll 1
   while (r < rows) {
     dst[r * dstride + j] = src[r * sstride + j];
-    j += 32;
-    while (j >= cols) { j -= cols; r++; }
+    r += dr; j += dj;
+    if (j >= cols) { j -= cols; r++; }
   }
 }
 
@@ -185,8 +189,10 @@ PIP_SDEVNI unsigned pip_load2d(V *dst, int dstride, const void *src, int elem_lo
 {
   unsigned ovf = 0;
   if (cols <= 0) return 0;
-  int r = 0, j = W::lane();
-  while (j >= cols) { j -= cols; r++; }
+  const int lane = W::lane();
+  int r = lane / cols, j = lane - r * cols;
+  const int dr = 32 / cols, dj = 32 - dr * cols;
+  #pragma unroll 1
   while (r < rows) {
     const pip_i64 k = src_off + (pip_i64)r * cols + j;
     pip_i64 v;
@@ -194,8 +200,8 @@ PIP_SDEVNI unsigned pip_load2d(V *dst, int dstride, const void *src, int elem_lo
     else if (elem_log2 == 2) v = ((const int *)src)[k];
     else v = ((const signed char *)src)[k];
     dst[r * dstride + j] = PipVal<V>::store(v, ovf);
-    j += 32;
-    while (j >= cols) { j -= cols; r++; }
+    r += dr; j += dj;
+    if (j >= cols) { j -= cols; r++; }
   }
   return ovf;
 }
@@ -527,37 +533,47 @@ PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
   const int pslot = PIP_LINK(fl[pivi]);
   V *prow = pip_row(B, T, pslot);
   const V dpiv = den[pivi];
-  /* determinant bookkeeping = the overflow verdict, source/traiter.c:394-447 (uniform, always
-   * in 64 bits: the factors grow up to 2^63) */
+  /* determinant bookkeeping = the overflow verdict, source/traiter.c:394-447, always in 64 bits
+   * (the factors grow up to 2^63).  The common case -- integer pivot row (dpiv == 1), unit pivot,
+   * first factor far from full -- changes nothing and is recognised up front; everything else is
+   * scalar work done by lane 0 on the factors in the arena. */
   {
-    pip_i64 d = pip_gcd((pip_i64)pivot, (pip_i64)dpiv);
-    if (d == 0) return PIP_ST_FAULT;
-    pip_i64 ppivot = pip_div((pip_i64)pivot, d), dppiv = pip_div((pip_i64)dpiv, d);
     pip_i64 *det = B + T.det;
-    pip_i64 dv[PIP_MAX_DET];
-    #pragma unroll 1
-    for (int i = 0; i < PIP_MAX_DET; i++) dv[i] = i < T.ldet ? det[i] : 0;
-    #pragma unroll 1
-    for (int i = 0; i < PIP_MAX_DET; i++) {
-      if (i >= T.ldet) break;
-      pip_i64 g = pip_gcd(dv[i], dppiv);
-      if (g == 0) return PIP_ST_FAULT;
-      dv[i] = pip_div(dv[i], g);
-      dppiv = pip_div(dppiv, g);
+    int verdict = 0, ldet = T.ldet;
+    const pip_i64 det0 = det[0];
+    const bool trivial = dpiv == 1 && pivot == 1 && det0 > -(1ll << 61) && det0 < (1ll << 61);
+    if (!trivial) {
+      if (lane == 0) {
+        pip_i64 d = (dpiv == 1) ? 1 : pip_gcd((pip_i64)pivot, (pip_i64)dpiv);
+        if (d == 0) verdict = PIP_ST_FAULT;
+        else {
+          pip_i64 ppivot = pivot, dppiv = dpiv;
+          if (d != 1) { ppivot = pip_div((pip_i64)pivot, d); dppiv = pip_div((pip_i64)dpiv, d); }
+          #pragma unroll 1
+          for (int i = 0; i < ldet && dppiv != 1; i++) {
+            const pip_i64 g = pip_gcd(det[i], dppiv);
+            if (g == 0) { verdict = PIP_ST_FAULT; break; }
+            if (g != 1) { det[i] = pip_div(det[i], g); dppiv = pip_div(dppiv, g); }
+          }
+          if (!verdict && dppiv != 1) verdict = PIP_ST_FATAL + 1;        /* "Integer overflow" */
+          if (!verdict) {
+            int i = 0;
+            const int bp = pip_bitlen(ppivot);
+            #pragma unroll 1
+            for (; i < ldet; i++)
+              if (pip_bitlen(det[i]) + bp < 64) { det[i] = (pip_i64)((pip_u64)det[i] * (pip_u64)ppivot); break; }
+            if (i >= ldet) {
+              ldet++;
+              if (ldet >= PIP_MAX_DET) verdict = PIP_ST_FATAL + 1;       /* "Integer overflow : 4" */
+              else det[i] = ppivot;
+            }
+          }
+        }
+      }
+      verdict = W::shfl(verdict, 0);
+      T.ldet = W::shfl(ldet, 0);
+      if (verdict) return verdict;
     }
-    if (dppiv != 1) return PIP_ST_FATAL + 1;            /* "Integer overflow" */
-    int i = 0;
-    const int bp = pip_bitlen(ppivot);
-    #pragma unroll 1
-    for (; i < T.ldet; i++)
-      if (pip_bitlen(dv[i]) + bp < 64) { dv[i] = (pip_i64)((pip_u64)dv[i] * (pip_u64)ppivot); break; }
-    if (i >= T.ldet) {
-      T.ldet++;
-      if (T.ldet >= PIP_MAX_DET) return PIP_ST_FATAL + 1; /* "Integer overflow : 4" */
-      dv[i] = ppivot;
-    }
-    W::sync();
-    if (lane == 0) for (int k = 0; k < PIP_MAX_DET; k++) if (k < T.ldet) det[k] = dv[k];
   }
   st.pivots++;
   if ((unsigned)nl > st.max_rows) st.max_rows = nl;
