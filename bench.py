@@ -283,7 +283,9 @@ def main():
         ms_per_step = dev_ms / K
         # algorithmic HBM traffic of the solve kernel: every problem's input words are read once
         # and its solution cells written once (the working set itself lives in shared memory)
-        in_bytes = dom.shape[1] * (dom.shape[2] - 1) * 8 + ctx.shape[1] * (ctx.shape[2] - 1) * 8 + 32
+        mx = max(int(np.abs(dom).max()), int(np.abs(ctx).max()))
+        elem = 1 if mx < 127 else 4 if mx < 2 ** 31 - 1 else 8       # the host ships the narrowest width
+        in_bytes = (dom.shape[1] * (dom.shape[2] - 1) + ctx.shape[1] * (ctx.shape[2] - 1)) * elem + 32
         alg_bytes = float(B) * (in_bytes + 56) + 8.0 * cells_step
         achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
         traffic = None

@@ -23,6 +23,8 @@ struct PipSer {
   long long cap, len;
   pip_u64 h;
   int hashing;
+  int narrow_out;          /* write 32-bit words (two per 64-bit slot) instead of 64-bit ones */
+  unsigned wide;           /* set when some word does not fit 32 bits */
 };
 #define PIP_HASH_INIT 0xcbf29ce484222325ULL
 
@@ -33,7 +35,11 @@ PIP_HD void pip_sput(PipSer &s, pip_i64 v)
     s.h *= 0x9E3779B97F4A7C15ULL;
     s.h ^= s.h >> 32;
   }
-  if (s.out && s.len < s.cap) s.out[s.len] = v;
+  s.wide |= (unsigned)(v != (pip_i64)(int)v);
+  if (s.out && s.len < s.cap) {
+    if (s.narrow_out) ((int *)s.out)[s.len] = (int)v;
+    else s.out[s.len] = v;
+  }
   s.len++;
 }
 

@@ -549,7 +549,7 @@ static PipQuast_dp *decode_one(const PipBatchOut &bo, size_t i, const Shape &s, 
  * uses too (pip_decode.h) */
 static void serialize_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify, Ser &out)
 {
-  PipSer ps = {out.out, out.cap, out.len, out.h, out.hashing ? 1 : 0};
+  PipSer ps = {out.out, out.cap, out.len, out.h, out.hashing ? 1 : 0, 0, 0};
   if (bo.res[i].status == PIP_ST_VOID) pip_sput(ps, -1);
   else {
     const PipCellView v = bo.cells_of(i);
@@ -918,7 +918,13 @@ void emit_chunk_ser(DenseChunk &C, int *status, unsigned long long *hashes, long
       if (keep) {
         ser_off[C.first + i] = base + C.words[i];
         if (ser_len) ser_len[C.first + i] = r.ser_words;
-        if (fits && r.ser_words) memcpy(ser + base + C.words[i], C.out.base[i] + r.cell_off, sizeof(I) * r.ser_words);
+        if (fits && r.ser_words) {
+          I *dst = ser + base + C.words[i];
+          if (r.rflags & PIP_RES_SER32) {
+            const int *src = (const int *)(C.out.base[i] + r.cell_off);
+            for (unsigned k = 0; k < r.ser_words; k++) dst[k] = src[k];
+          } else memcpy(dst, C.out.base[i] + r.cell_off, sizeof(I) * r.ser_words);
+        }
       }
     }
   });

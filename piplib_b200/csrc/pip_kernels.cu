@@ -110,17 +110,20 @@ __global__ void pip_serialize_kernel(PipResult *res, const int *order, const Pip
   const int p = order ? order[q] : q;
   const PipResult r = res[p];
   PipSer s;
+  const bool narrow = pass && (r.rflags & PIP_RES_SER32);
   s.out = pass ? out + dst_off[q] : nullptr;
   s.cap = pass ? (long long)r.ser_words : 0;
-  s.len = 0; s.h = PIP_HASH_INIT; s.hashing = pass;
+  s.len = 0; s.h = PIP_HASH_INIT; s.hashing = pass; s.narrow_out = narrow ? 1 : 0; s.wide = 0;
   if (r.status == PIP_ST_VOID) pip_sput(s, -1);
   else if (r.status == PIP_ST_OK) {
     PipRawCells c = {cells + r.cell_off};
     const PipDecodeParm d = parm[p];
     pip_ser_cells(s, c, r.ncells, d.bg, d.urs, d.flags);
   }
-  if (pass == 0) res[p].ser_words = (unsigned)s.len;
-  else {
+  if (pass == 0) {
+    res[p].ser_words = (unsigned)s.len;
+    if (!s.wide) res[p].rflags = r.rflags | PIP_RES_SER32;
+  } else {
     res[p].cell_off = dst_off[q];
     if (hashes) hashes[p] = (r.status == PIP_ST_OK || r.status == PIP_ST_VOID) ? s.h : 0ull;
   }
@@ -150,7 +153,8 @@ __global__ void pip_scan_kernel(const PipResult *res, const int *order, long lon
     long long v = 0;
     if (i < nprob) {
       const PipResult &r = res[order ? order[i] : i];
-      v = ser_mode ? (long long)r.ser_words : (long long)r.ncells * ((r.rflags & PIP_RES_WIDE) ? 3 : 1);
+      if (ser_mode) v = (r.rflags & PIP_RES_SER32) ? ((long long)r.ser_words + 1) / 2 : (long long)r.ser_words;
+      else v = (long long)r.ncells * ((r.rflags & PIP_RES_WIDE) ? 3 : 1);
     }
     long long x = v;
     for (int o = 1; o < 32; o <<= 1) {

@@ -88,6 +88,7 @@ typedef struct {
  * unless some cell of the problem does not fit (PIP_RES_WIDE in PipResult.rflags): then the
  * problem's cells are shipped as raw {kind, param1, param2} triples (3 words per cell). */
 #define PIP_RES_WIDE 1u
+#define PIP_RES_SER32 2u          /* device-decode mode: the quast words were shipped as int32 */
 #define PIP_CELL_FITS(p1, p2) ((pip_u64)(p2) < 65536ull && (p1) >= -(1ll << 43) && (p1) < (1ll << 43))
 #define PIP_CELL_PACK(kind, p1, p2) ((pip_u64)(unsigned)(kind) | ((pip_u64)(p2) << 4) | ((pip_u64)(p1) << 20))
 #define PIP_CELL_KIND(w) ((int)((w) & 15ull))
