@@ -8,13 +8,14 @@ from piplib_b200 import api, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 dom, ctx = synth.generate("loopnest16x24p3", n)
-for chunk, lanes in [(131072, 4), (131072, 6), (131072, 8), (65536, 6), (65536, 8), (43690, 8)]:
+for chunk, lanes in [(131072, 4), (65536, 4), (65536, 6), (65536, 8), (32768, 8), (98304, 5)]:
     os.environ["PIPLIB_B200_CHUNK"] = str(chunk)
     os.environ["PIPLIB_B200_LANES"] = str(lanes)
     best = 1e9
+    res = None
     for it in range(4):
         t = time.perf_counter()
-        api.solve_dense(dom, ctx, -1, want_hashes=False, want_ser=True)
+        res = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True, out=res)
         dt = time.perf_counter() - t
         if it:
             best = min(best, dt)
