@@ -963,9 +963,9 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     const double t0 = wall();
     DenseArgs A = {n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum,
                    options ? *options : DEFAULT_OPTIONS};
-    const size_t CH = env_size("PIPLIB_B200_CHUNK", 1u << 17);
+    const size_t CH = env_size("PIPLIB_B200_CHUNK", 1u << 16);
     const size_t nchunks = ((size_t)n + CH - 1) / CH;
-    const size_t lanes = std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 4), PipEngine::MAX_LANES), nchunks);
+    const size_t lanes = std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 6), PipEngine::MAX_LANES), nchunks);
     const size_t nthreads = std::max<size_t>(1, host_threads());
     const bool keep = ser != nullptr && ser_off != nullptr;
     std::vector<DenseChunk> chunks(nchunks);
