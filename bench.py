@@ -97,23 +97,27 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------
 # CPU arms (the checker libraries; never the thing shipped)
 # ------------------------------------------------------------------------------------------
+_CPU_DATA = None      # (dom, ctx) inherited by the forked workers (never pickled)
+
+
 def _cpu_worker(args):
-    kind, first, count, dom, ctx, core = args
+    kind, first, count, core, bg, opts = args
+    dom, ctx = _CPU_DATA
     try:
         os.sched_setaffinity(0, {core})
     except Exception:
         pass
     from oracle import pyoracle as po
     if kind == "reference":
-        sec, st, h = po.Ref().bench_dense(first, count, dom, ctx, -1)
+        sec, st, h = po.Ref().bench_dense(first, count, dom, ctx, bg, **opts)
         piv = 0
     else:
-        sec, st, h, stats = po.Port().bench_dense(first, count, dom, ctx, -1)
+        sec, st, h, stats = po.Port().bench_dense(first, count, dom, ctx, bg, **opts)
         piv = stats.pivots
     return sec, st, h, piv
 
 
-def cpu_arm(dom, ctx, sample, cores):
+def cpu_arm(dom, ctx, sample, cores, bg=-1, opts=None):
     """reference CPU path on `cores` processes (one per core: the library is not re-entrant,
     SURVEY.md 8b), static split of problems [0, sample)."""
     from oracle import pyoracle as po
@@ -125,7 +129,9 @@ def cpu_arm(dom, ctx, sample, cores):
     for c in range(cores):
         a, b = c * per, min(sample, (c + 1) * per)
         if a < b:
-            jobs.append((kind, a, b - a, dom, ctx, c))
+            jobs.append((kind, a, b - a, c, bg, opts or {}))
+    global _CPU_DATA
+    _CPU_DATA = (dom[:sample], None if ctx is None else ctx[:sample])
     ctxm = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctxm.Pool(len(jobs)) as pool:

@@ -56,15 +56,16 @@ struct PinBuf {
 };
 
 /* the size-class ladder */
-struct ClassSpec { int level; int shared; long long words; int warps; int warps_per_cta; long long stack_words; };
+/* team = 0: `warps` warps, one problem each; team = t: `warps` CTAs of t warps, one problem per CTA (class M) */
+struct ClassSpec { int level; int shared; long long words; int warps; int warps_per_cta; long long stack_words; int team; };
 const long long S_MAX_WORDS = 3328;          /* 26 KB: at least 8 warps of class S per SM */
 const ClassSpec G_LADDER[] = {
-    {3, 0, 1ll << 15, 148 * 8, 4, 1ll << 17},
-    {4, 0, 1ll << 17, 148 * 4, 4, 1ll << 19},
-    {5, 0, 1ll << 19, 148 * 2, 2, 1ll << 21},
-    {6, 0, 1ll << 22, 148, 1, 1ll << 23},
-    {7, 0, 1ll << 24, 32, 1, 1ll << 25},
-    {8, 0, 1ll << 26, 8, 1, 1ll << 27},
+    {3, 0, 1ll << 15, 148 * 8, 4, 1ll << 17, 0},
+    {4, 0, 1ll << 17, 148 * 4, 4, 1ll << 19, 4},
+    {5, 0, 1ll << 19, 148 * 2, 2, 1ll << 21, 8},
+    {6, 0, 1ll << 22, 148, 1, 1ll << 23, 16},
+    {7, 0, 1ll << 24, 32, 1, 1ll << 25, 16},
+    {8, 0, 1ll << 26, 8, 1, 1ll << 27, 16},
 };
 const int N_G = sizeof(G_LADDER) / sizeof(G_LADDER[0]);
 
@@ -236,9 +237,13 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         cs.warps = ctas * cs.warps_per_cta;
       } else {
         cs = G_LADDER[k];
+        if (getenv("PIPLIB_B200_NO_TEAM")) cs.team = 0;
         int need_warps = std::min(cs.warps, m);
-        ctas = (need_warps + cs.warps_per_cta - 1) / cs.warps_per_cta;
-        cs.warps = ctas * cs.warps_per_cta;
+        if (cs.team) { ctas = need_warps; cs.warps = ctas; cs.warps_per_cta = cs.team; }
+        else {
+          ctas = (need_warps + cs.warps_per_cta - 1) / cs.warps_per_cta;
+          cs.warps = ctas * cs.warps_per_cta;
+        }
       }
       /* cell pool: every warp must be able to hold one worst-case solution */
       long long est = (k < 0) ? (est_cells_total * (long long)m / (long long)n) : 0;
@@ -265,7 +270,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       L.slack_level = cs.level;
       L.prof = (unsigned long long *)E.d_prof.p;
       double tk = now_s();
-      CK(pip_launch_solve(&L, cs.shared, ctas, cs.warps_per_cta, s));
+      CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? 3 : cs.shared, ctas, cs.warps_per_cta, s));
       out.times.launches++;
       /* compact this round's output: packed cells, or (device-decode mode) serialised quasts */
       if (ser_mode) {
@@ -309,6 +314,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       out.times.rounds++;
       /* classify */
       int pending = 0;
+      const double t_round = now_s() - tk;
       for (int q = 0; q < m; q++) {
         const int i = order[q];
         const PipResult &r = h_res[i];
@@ -318,6 +324,12 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         cls[i] = 1000;                       /* final */
         out.res[i] = r;
         out.base[i] = (const pip_u64 *)chunk.p;
+      }
+      if (getenv("PIPLIB_B200_TIMING")) {
+        int esc = 0;
+        for (int q = 0; q < m; q++) if (cls[order[q]] != 1000) esc++;
+        fprintf(stderr, "[piplib-b200] round %d: class %d attempt %d, %d problems on %d warps (%d words/warp): %.3f s, %d not final (%d pending)\n",
+                round - 1, k, attempt, m, cs.warps, (int)cs.words, t_round, esc, pending);
       }
       if (pending == 0) {
         /* re-arm the escalated problems on the device */

@@ -29,11 +29,29 @@ pip_solve_kernel(const PipLaunch L)
   pip_warp_main<V>(L, warp_id, arena);
 }
 
-/* shared_class: 0 = global-memory arena (int64), 1 = shared arena int64, 2 = shared arena int32 */
+/* size class M: one problem per CTA, arena in global memory.  Warp 0 runs the solver, the other
+ * warps join it for the rank-1 update of every pivot on a tall tableau (pip_solver.h, PipTeam). */
+__global__ void __launch_bounds__(512, 1)
+pip_team_kernel(const PipLaunch L)
+{
+  __shared__ PipTeam team;
+  const int tid = threadIdx.x;
+  if (tid == 0) { team.nthreads = blockDim.x; team.cmd = PIP_TEAM_UPDATE; team.fault = 0; team.ovf = 0; }
+  __syncthreads();
+  if (tid < 32) {
+    pip_warp_main<pip_i64, true>(L, blockIdx.x, L.gwork + (size_t)blockIdx.x * L.work_words, &team);
+    if (tid == 0) team.cmd = PIP_TEAM_EXIT;
+    __syncwarp();
+    pip_team_barrier(team.nthreads);
+  } else pip_team_helper<pip_i64>(&team, tid);
+}
+
+/* shared_class: 0 = global-memory arena (int64), 1 = shared arena int64, 2 = shared arena int32,
+ * 3 = team (class M): `warps_per_cta` warps work on one problem, `ctas` problems in flight */
 extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, int ctas, int warps_per_cta,
                                         cudaStream_t stream)
 {
-  if (shared_class) {
+  if (shared_class == 1 || shared_class == 2) {
     size_t smem = (size_t)warps_per_cta * L->work_words * sizeof(pip_i64);
     cudaError_t e;
     if (shared_class == 2) {
@@ -45,6 +63,8 @@ extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, in
       if (e != cudaSuccess) return e;
       pip_solve_kernel<true, pip_i64><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
     }
+  } else if (shared_class == 3) {
+    pip_team_kernel<<<ctas, warps_per_cta * 32, 0, stream>>>(*L);
   } else {
     pip_solve_kernel<false, pip_i64><<<ctas, warps_per_cta * 32, 0, stream>>>(*L);
   }

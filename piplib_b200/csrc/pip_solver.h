@@ -139,7 +139,28 @@ template <> struct PipVal<int> {
   PIP_HDM static pip_i64 cross(int p, int a, int b, int f) { return (pip_i64)p * a - (pip_i64)b * f; }
 };
 
-template <class V>
+/* Team mode (size class M, tall tableaus): one CTA per problem.  Warp 0 runs the solver's state
+ * machine exactly as in the warp-per-problem classes; for the rank-1 update of a pivot -- the only
+ * phase whose cost grows with rows x columns -- it posts the pivot in this block and every warp of
+ * the CTA updates its share of the rows (thread = row position), between two named barriers. */
+struct PipTeam {
+  int cmd;                       /* PIP_TEAM_UPDATE / PIP_TEAM_EXIT */
+  int nthreads;
+  int pivi, pivj;
+  pip_i64 pivot, dpiv;
+  PipTab T;
+  pip_i64 *B;
+  unsigned ovf;
+  int fault;
+};
+enum { PIP_TEAM_UPDATE = 0, PIP_TEAM_EXIT = 1, PIP_TEAM_MIN_ROWS = 64 };
+#if defined(__CUDACC__) && !defined(PIP_EMU)
+PIP_DEV void pip_team_barrier(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+#else
+PIP_DEV void pip_team_barrier(int) {}
+#endif
+
+template <class V, bool TEAM = false>
 struct PipSolver {
 /* ---- small accessors ------------------------------------------------------------------- */
 PIP_SDEV int *pip_fl(pip_i64 *B, const PipTab &T) { return (int *)(B + T.fl); }
@@ -517,75 +538,18 @@ PIP_SDEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, V &pivot_o
   return pivj;
 }
 
-/* pivoter_xx, source/traiter.c:345-548.
- * returns 0 done, -1 no positive coefficient (infeasible), or a PIP_ST_* fatal status */
-PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
+/* rank-1 update of every stored row but the pivot row (source/traiter.c:467-502), fused with
+ * the re-flagging from the sign of the new pivot-column entry (source/traiter.c:518-529).
+ * The caller's thread handles positions first, first + step, ... */
+PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V pivot, V dpiv, int first, int step,
+                              unsigned &ovf, bool &fault)
 {
-  const int lane = W::lane();
   const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
   int *fl = pip_fl(B, T);
   V *den = pip_den(B, T);
-  V pivot;
-  const int pivj = pip_choose_column(B, T, pivi, pivot);
-  PIP_LAP(st, PIP_PH_CHOOSE);
-  if (pivj < 0) return -1;
-
-  const int pslot = PIP_LINK(fl[pivi]);
-  V *prow = pip_row(B, T, pslot);
-  const V dpiv = den[pivi];
-  /* determinant bookkeeping = the overflow verdict, source/traiter.c:394-447, always in 64 bits
-   * (the factors grow up to 2^63).  The common case -- integer pivot row (dpiv == 1), unit pivot,
-   * first factor far from full -- changes nothing and is recognised up front; everything else is
-   * scalar work done by lane 0 on the factors in the arena. */
-  {
-    pip_i64 *det = B + T.det;
-    int verdict = 0, ldet = T.ldet;
-    const pip_i64 det0 = det[0];
-    const bool trivial = dpiv == 1 && pivot == 1 && det0 > -(1ll << 61) && det0 < (1ll << 61);
-    if (!trivial) {
-      if (lane == 0) {
-        pip_i64 d = (dpiv == 1) ? 1 : pip_gcd((pip_i64)pivot, (pip_i64)dpiv);
-        if (d == 0) verdict = PIP_ST_FAULT;
-        else {
-          pip_i64 ppivot = pivot, dppiv = dpiv;
-          if (d != 1) { ppivot = pip_div((pip_i64)pivot, d); dppiv = pip_div((pip_i64)dpiv, d); }
-          #pragma unroll 1
-          for (int i = 0; i < ldet && dppiv != 1; i++) {
-            const pip_i64 g = pip_gcd(det[i], dppiv);
-            if (g == 0) { verdict = PIP_ST_FAULT; break; }
-            if (g != 1) { det[i] = pip_div(det[i], g); dppiv = pip_div(dppiv, g); }
-          }
-          if (!verdict && dppiv != 1) verdict = PIP_ST_FATAL + 1;        /* "Integer overflow" */
-          if (!verdict) {
-            int i = 0;
-            const int bp = pip_bitlen(ppivot);
-            #pragma unroll 1
-            for (; i < ldet; i++)
-              if (pip_bitlen(det[i]) + bp < 64) { det[i] = (pip_i64)((pip_u64)det[i] * (pip_u64)ppivot); break; }
-            if (i >= ldet) {
-              ldet++;
-              if (ldet >= PIP_MAX_DET) verdict = PIP_ST_FATAL + 1;       /* "Integer overflow : 4" */
-              else det[i] = ppivot;
-            }
-          }
-        }
-      }
-      verdict = W::shfl(verdict, 0);
-      T.ldet = W::shfl(ldet, 0);
-      if (verdict) return verdict;
-    }
-  }
-  st.pivots++;
-  if ((unsigned)nl > st.max_rows) st.max_rows = nl;
-  if ((unsigned)ncol > st.max_cols) st.max_cols = ncol;
-  st.elem_updates += (unsigned long long)(T.ni - 1) * ncol;
-
-  /* rank-1 update of every stored row but the pivot row (source/traiter.c:467-502), fused with
-   * the re-flagging from the sign of the new pivot-column entry (source/traiter.c:518-529) */
-  bool fault = false;
-  unsigned ovf = 0;
+  const V *prow = pip_row(B, T, PIP_LINK(fl[pivi]));
   #pragma unroll 1
-  for (int k = lane; k < nl; k += 32) {
+  for (int k = first; k < nl; k += step) {
     if (k == pivi) continue;
     const int f = fl[k];
     if (f & PIP_UNIT) continue;
@@ -646,6 +610,86 @@ PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st)
       fl[k] = PIP_MKFL(ff, PIP_LINK(f));
     }
   }
+}
+
+/* pivoter_xx, source/traiter.c:345-548.
+ * returns 0 done, -1 no positive coefficient (infeasible), or a PIP_ST_* fatal status */
+PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st, PipTeam *tm)
+{
+  const int lane = W::lane();
+  const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
+  int *fl = pip_fl(B, T);
+  V *den = pip_den(B, T);
+  V pivot;
+  const int pivj = pip_choose_column(B, T, pivi, pivot);
+  PIP_LAP(st, PIP_PH_CHOOSE);
+  if (pivj < 0) return -1;
+
+  const int pslot = PIP_LINK(fl[pivi]);
+  V *prow = pip_row(B, T, pslot);
+  const V dpiv = den[pivi];
+  /* determinant bookkeeping = the overflow verdict, source/traiter.c:394-447, always in 64 bits
+   * (the factors grow up to 2^63).  The common case -- integer pivot row (dpiv == 1), unit pivot,
+   * first factor far from full -- changes nothing and is recognised up front; everything else is
+   * scalar work done by lane 0 on the factors in the arena. */
+  {
+    pip_i64 *det = B + T.det;
+    int verdict = 0, ldet = T.ldet;
+    const pip_i64 det0 = det[0];
+    const bool trivial = dpiv == 1 && pivot == 1 && det0 > -(1ll << 61) && det0 < (1ll << 61);
+    if (!trivial) {
+      if (lane == 0) {
+        pip_i64 d = (dpiv == 1) ? 1 : pip_gcd((pip_i64)pivot, (pip_i64)dpiv);
+        if (d == 0) verdict = PIP_ST_FAULT;
+        else {
+          pip_i64 ppivot = pivot, dppiv = dpiv;
+          if (d != 1) { ppivot = pip_div((pip_i64)pivot, d); dppiv = pip_div((pip_i64)dpiv, d); }
+          #pragma unroll 1
+          for (int i = 0; i < ldet && dppiv != 1; i++) {
+            const pip_i64 g = pip_gcd(det[i], dppiv);
+            if (g == 0) { verdict = PIP_ST_FAULT; break; }
+            if (g != 1) { det[i] = pip_div(det[i], g); dppiv = pip_div(dppiv, g); }
+          }
+          if (!verdict && dppiv != 1) verdict = PIP_ST_FATAL + 1;        /* "Integer overflow" */
+          if (!verdict) {
+            int i = 0;
+            const int bp = pip_bitlen(ppivot);
+            #pragma unroll 1
+            for (; i < ldet; i++)
+              if (pip_bitlen(det[i]) + bp < 64) { det[i] = (pip_i64)((pip_u64)det[i] * (pip_u64)ppivot); break; }
+            if (i >= ldet) {
+              ldet++;
+              if (ldet >= PIP_MAX_DET) verdict = PIP_ST_FATAL + 1;       /* "Integer overflow : 4" */
+              else det[i] = ppivot;
+            }
+          }
+        }
+      }
+      verdict = W::shfl(verdict, 0);
+      T.ldet = W::shfl(ldet, 0);
+      if (verdict) return verdict;
+    }
+  }
+  st.pivots++;
+  if ((unsigned)nl > st.max_rows) st.max_rows = nl;
+  if ((unsigned)ncol > st.max_cols) st.max_cols = ncol;
+  st.elem_updates += (unsigned long long)(T.ni - 1) * ncol;
+
+  /* rank-1 update + re-flag (pip_update_rows): by this warp, or in team mode by the whole CTA */
+  bool fault = false;
+  unsigned ovf = 0;
+  if (TEAM && tm != nullptr && nl >= PIP_TEAM_MIN_ROWS) {
+    if (lane == 0) {
+      tm->cmd = PIP_TEAM_UPDATE; tm->pivi = pivi; tm->pivj = pivj; tm->pivot = (pip_i64)pivot; tm->dpiv = (pip_i64)dpiv;
+      tm->T = T; tm->B = B; tm->fault = 0;
+    }
+    W::sync();
+    pip_team_barrier(tm->nthreads);
+    pip_update_rows(B, T, pivi, pivj, pivot, dpiv, lane, tm->nthreads, ovf, fault);
+    if (fault) tm->fault = 1;
+    pip_team_barrier(tm->nthreads);
+    fault = tm->fault != 0;
+  } else pip_update_rows(B, T, pivi, pivj, pivot, dpiv, lane, 32, ovf, fault);
   if (PipVal<V>::narrow && W::any(ovf != 0)) return PIP_ST_WIDEN;
   if (W::any(fault)) return PIP_ST_FAULT;
   W::sync();
@@ -748,7 +792,7 @@ PIP_SDEV int pip_find_parm(const V *ctx, int cstride, int nr, int nparm, V *cut)
 PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, int words, int slack_level,
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
-                           int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st)
+                           int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st, PipTeam *tm = nullptr)
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
@@ -1096,7 +1140,7 @@ NONNEG:
 PIVOT:
   {
     PIP_LAP(st, PIP_PH_OTHER);
-    int rc = pip_pivot(B, T, pivi, st);
+    int rc = pip_pivot(B, T, pivi, st, tm);
     if (rc == 0) goto LOOP;
     if (rc > 0) { status = rc; goto DONE; }
     if (level) { feasible = false; goto SUB_DONE; }

@@ -7,8 +7,8 @@
 
 #include "pip_solver.h"
 
-template <class V>
-PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
+template <class V, bool TEAM = false>
+PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipTeam *tm = nullptr)
 {
   const int lane = W::lane();
   PipCell *window = L.cells + (pip_i64)warp_id * L.cells_per_warp;
@@ -31,8 +31,8 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
 #endif
     int status = PIP_ST_OK, ncell = 0;
     unsigned rflags = 0;
-    PipSolver<V>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
-                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st);
+    PipSolver<V, TEAM>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
+                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm);
     if (lane == 0) {
       PipResult r;
       r.status = status; r.ncells = ncell;
@@ -49,6 +49,22 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena)
     }
     used += ncell;
     W::sync();
+  }
+}
+
+/* helper warps of a team (class M): serve the leader's update commands until it retires */
+template <class V>
+PIP_DEV void pip_team_helper(PipTeam *tm, int tid)
+{
+  for (;;) {
+    pip_team_barrier(tm->nthreads);
+    if (tm->cmd == PIP_TEAM_EXIT) break;
+    unsigned ovf = 0;
+    bool fault = false;
+    PipSolver<V, true>::pip_update_rows(tm->B, tm->T, tm->pivi, tm->pivj, (V)tm->pivot, (V)tm->dpiv, tid, tm->nthreads,
+                                        ovf, fault);
+    if (fault) tm->fault = 1;
+    pip_team_barrier(tm->nthreads);
   }
 }
 

@@ -101,10 +101,83 @@ def consecutive_ones(nvar, nrows, seed=2026, cmax=50):
     return tab
 
 
+def _chunked(gen, n, first):
+    """problems [first, first+n) of a family whose chunk c is gen(c) -> (dom, ctx)"""
+    doms, ctxs = [], []
+    lo, hi = first, first + n
+    c = lo // CHUNK
+    while c * CHUNK < hi:
+        d, x = gen(c)
+        a = max(lo, c * CHUNK) - c * CHUNK
+        b = min(hi, (c + 1) * CHUNK) - c * CHUNK
+        doms.append(d[a:b])
+        ctxs.append(x[a:b])
+        c += 1
+    return np.ascontiguousarray(np.concatenate(doms)), np.ascontiguousarray(np.concatenate(ctxs))
+
+
+def perturbed(n, seed=2026, first=0, template="sor1d", amp=2):
+    """BASELINE config 5 (and 3, family B): a shipped problem shape with every constraint constant
+    moved by a uniform draw from [-amp, amp] (no fatal verdicts in 20 000 draws per
+    template, 4-100 pivots per problem)."""
+    from .templates import TEMPLATES
+    t = TEMPLATES[template]
+    dom0 = np.asarray(t["dom"], dtype=np.int64)
+    ctx0 = np.asarray(t["ctx"], dtype=np.int64).reshape(len(t["ctx"]), t["ctx_cols"])
+    key = sum(ord(ch) << (8 * i) for i, ch in enumerate(template[:6]))
+
+    def gen(c):
+        rng = _rng(seed ^ key, c)
+        dom = np.repeat(dom0[None], CHUNK, axis=0)
+        dom[:, :, -1] += rng.integers(-amp, amp + 1, size=(CHUNK, dom0.shape[0]))
+        ctx = np.repeat(ctx0[None], CHUNK, axis=0)
+        return dom, ctx
+    return _chunked(gen, n, first)
+
+
+def test_ni(n, seed=2026, first=0, N=10, spread=None):
+    """BASELINE config 3, family A: the test<N>i.dat shape -- row i is sum_{j<=i} (j+1) x_j >= c_i
+    with c_i around (i+1)! + 1, all-integer (deep Gomory cut chains, wide denominators)."""
+    fact = np.cumprod(np.arange(1, N + 1, dtype=np.int64))
+
+    def gen(c):
+        rng = _rng(seed ^ (0x7e57 + N), c)
+        dom = np.zeros((CHUNK, N, 1 + N + 1), dtype=np.int64)
+        dom[:, :, 0] = 1
+        for i in range(N):
+            dom[:, i, 1:2 + i] = np.arange(1, i + 2)
+            s = spread if spread is not None else max(1, int(fact[i]) // 8)
+            dom[:, i, -1] = -(fact[i] + 1 + rng.integers(-s, s + 1, size=CHUNK))
+        ctx = np.zeros((CHUNK, 0, 2), dtype=np.int64)
+        return dom, ctx
+    return _chunked(gen, n, first)
+
+
 WORKLOADS = {
     "loopnest16x24p3": dict(fn=loopnest, kw=dict(nvar=16, nrows=24, nparm=3)),
     "loopnest8x12p2": dict(fn=loopnest, kw=dict(nvar=8, nrows=12, nparm=2)),
+    # config 5: dependence-analysis shapes
+    "sor1d": dict(fn=perturbed, kw=dict(template="sor1d")),
+    "boulet": dict(fn=perturbed, kw=dict(template="boulet")),
+    "cg1": dict(fn=perturbed, kw=dict(template="cg1")),
+    "fimmel": dict(fn=perturbed, kw=dict(template="fimmel")),
+    "esced": dict(fn=perturbed, kw=dict(template="esced")),
+    "expansion": dict(fn=perturbed, kw=dict(template="expansion")),
+    # config 3: cut-heavy integer problems
+    "test10i": dict(fn=test_ni, kw=dict(N=10)),
+    "test12i": dict(fn=test_ni, kw=dict(N=12)),
+    "vivien32": dict(fn=perturbed, kw=dict(template="vivien32", amp=1)),
 }
+BIGNUM = {"expansion": 21}                   # big-parameter column of the PolyLib matrix, else -1
+OPTS = {"boulet": dict(Nq=0)}                # test/boulet.dat is the rational variant (bouleti the integer one)
+
+
+def bignum(name):
+    return BIGNUM.get(name, -1)
+
+
+def options(name):
+    return dict(OPTS.get(name, {}))
 
 
 def generate(name, n, seed=2026, first=0):

@@ -138,6 +138,28 @@ def test_dense_batch_vs_oracle(api, port, workload, n):
         assert (st, ser) == (int(st_g[i]), mine) or st != 0
 
 
+@pytest.mark.parametrize("workload,n", [("sor1d", 4000), ("cg1", 3000), ("fimmel", 1500), ("esced", 2000),
+                                        ("expansion", 300), ("boulet", 48), ("test10i", 3000),
+                                        ("test12i", 1500), ("vivien32", 24)])
+def test_config3_and_5_families_vs_oracle(api, port, workload, n):
+    """BASELINE configs 3 (cut-heavy: test<N>i-shaped, vivien32-shaped) and 5 (dependence-analysis
+    shapes with perturbed constants): status, quast hash and pivot count vs the oracle"""
+    from piplib_b200 import synth
+    dom, ctx = synth.generate(workload, n, seed=31)
+    bg, opts = synth.bignum(workload), synth.options(workload)
+    _, st_o, h_o, stats = port.bench_dense(0, n, dom, ctx, bg, **opts)
+    r = api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, **opts)
+    st_g = np.where(r["status"] == 1, 0, r["status"])
+    assert np.array_equal(st_g, st_o)
+    ok = st_o == 0
+    assert np.array_equal(r["hashes"][ok], h_o[ok])
+    assert int(api.last_stats().pivots) >= int(stats.pivots)     # > only if a class was re-run
+    for i in range(0, n, max(1, n // 8)):
+        st, ser = port.solve(dom[i], ctx[i], bg, ctx_cols=ctx.shape[2], **opts)
+        mine = [int(x) for x in r["ser"][r["ser_off"][i]:r["ser_off"][i] + r["ser_len"][i]]]
+        assert (st, ser) == (int(st_g[i]), mine) or st != 0
+
+
 def test_device_resident_batch(api, port):
     """kernel-only path (inputs resident in HBM) gives the same answers as the host-buffer path"""
     from piplib_b200 import synth
