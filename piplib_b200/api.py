@@ -14,7 +14,8 @@ from .ctypes_defs import CELL_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PIPLIB_B200_LIB") or os.path.join(HERE, "lib", "libpiplib_dp.so")
-PHASES = ["load", "sort", "scan", "buildsub", "choose", "update", "swap", "cut", "frame", "emit", "other"]
+PHASES = ["load", "sort", "scan", "buildsub", "choose", "update", "swap", "cut", "frame", "emit", "other",
+          "u_head", "u_pass1", "u_gcd", "u_div", "u_wait"]      # u_*: lane 0's share inside "update"
 
 I64P = C.POINTER(C.c_longlong)
 

@@ -17,17 +17,47 @@
 
 PIP_HD pip_u64 pip_uabs(pip_i64 v) { return v < 0 ? 0ull - (pip_u64)v : (pip_u64)v; }
 
+/* count of trailing zero bits of v != 0 (host and device) */
+PIP_HD int pip_tz64(pip_u64 v)
+{
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
+
+/* gcd of two 64-bit magnitudes; the value is the mathematical gcd, hence bit-identical to the
+ * reference's Euclid (source/integrer.c:43-50).  GPU-shaped: there is no integer divider on the SM
+ * and a 64-bit '%' is a ~150-cycle subroutine, so
+ *   - the smaller operand is always the divisor (the running row gcd against a tableau entry costs
+ *     ONE remainder when the entry is a multiple, the common case),
+ *   - a divisor that fits 32 bits takes at most one wide remainder, then Euclid on 32-bit words,
+ *   - two wide operands run the binary algorithm (subtract / count trailing zeros / shift) until
+ *     they fit. */
 PIP_HDNI pip_u64 pip_gcd_u64(pip_u64 a, pip_u64 b)
 {
-  while (b) {
-    if (((a | b) >> 32) == 0) {            /* both fit 32 bits: stay on the 32-bit path */
-      unsigned x = (unsigned)a, y = (unsigned)b;
-      while (y) { unsigned r = x % y; x = y; y = r; }
-      return x;
-    }
-    pip_u64 r = a % b; a = b; b = r;
+  if (a < b) { const pip_u64 t = a; a = b; b = t; }
+  if ((b >> 32) != 0) {                    /* both wide */
+    const int sh = pip_tz64(a | b);
+    a >>= pip_tz64(a);
+    do {
+      b >>= pip_tz64(b);
+      if (a > b) { const pip_u64 t = a; a = b; b = t; }
+      b -= a;
+    } while ((b >> 32) != 0);
+    /* a is odd, so gcd(a, b) is odd whatever power of two b holds; the common one is restored at the end */
+    if (b == 0) return a << sh;
+    unsigned y = (unsigned)b;
+    unsigned x = (a >> 32) == 0 ? (unsigned)a % y : (unsigned)(a % (pip_u64)y);
+    while (x) { const unsigned r = y % x; y = x; x = r; }
+    return (pip_u64)y << sh;
   }
-  return a;
+  if (b == 0) return a;
+  unsigned y = (unsigned)b;
+  unsigned x = (a >> 32) == 0 ? (unsigned)a % y : (unsigned)(a % (pip_u64)y);
+  while (x) { const unsigned r = y % x; y = x; x = r; }
+  return y;
 }
 PIP_HD pip_i64 pip_gcd(pip_i64 a, pip_i64 b) { return (pip_i64)pip_gcd_u64(pip_uabs(a), pip_uabs(b)); }
 
@@ -57,6 +87,9 @@ PIP_HD pip_i64 pip_floor_q(pip_i64 a, pip_i64 b) { return pip_div(a - pip_mod(a,
 PIP_HD int pip_gcd(int a, int b)
 {
   unsigned x = a < 0 ? 0u - (unsigned)a : (unsigned)a, y = b < 0 ? 0u - (unsigned)b : (unsigned)b;
+#ifndef PIP_GCD32_NOSWAP
+  if (x < y) { const unsigned t = x; x = y; y = t; }     /* the smaller operand divides first */
+#endif
   while (y) { unsigned r = x % y; x = y; y = r; }
   return (int)x;
 }

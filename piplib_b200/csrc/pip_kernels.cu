@@ -26,7 +26,7 @@ pip_solve_kernel(const PipLaunch L)
   pip_i64 *arena;
   if (SH) arena = (pip_i64 *)pip_smem + (size_t)warp_in_cta * L.work_words;
   else arena = L.gwork + (size_t)warp_id * L.work_words;
-  pip_warp_main<V>(L, warp_id, arena);
+  pip_warp_main<V, !SH>(L, warp_id, arena, nullptr);   /* !SH: the global-memory code path */
 }
 
 /* size class M: one problem per CTA, arena in global memory.  Warp 0 runs the solver, the other

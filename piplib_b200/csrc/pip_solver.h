@@ -52,8 +52,13 @@ struct PipStats {
  * PIP_LAP(st, phase) charges the cycles since the previous lap to `phase` */
 #ifdef PIP_PROFILE
 #define PIP_LAP(st, ph) do { long long n_ = clock64(); (st).cyc[ph] += (unsigned long long)(n_ - (st).lap); (st).lap = n_; } while (0)
+/* sub-phases of the update as seen by one thread (charged on top of PIP_PH_UPDATE) */
+#define PIP_ULAP(stp, ph) do { if (stp) { long long n_ = clock64(); (stp)->cyc[ph] += (unsigned long long)(n_ - ulap); ulap = n_; } } while (0)
+#define PIP_ULAP_BEGIN(stp) long long ulap = clock64()
 #else
 #define PIP_LAP(st, ph) do { } while (0)
+#define PIP_ULAP(stp, ph) do { } while (0)
+#define PIP_ULAP_BEGIN(stp) do { } while (0)
 #endif
 
 /* capacity slack per level: {new parameters, main cut rows, extra context rows, sub cut rows} */
@@ -144,7 +149,7 @@ template <> struct PipVal<int> {
  * phase whose cost grows with rows x columns -- it posts the pivot in this block and every warp of
  * the CTA updates its share of the rows (thread = row position), between two named barriers. */
 struct PipTeam {
-  int cmd;                       /* PIP_TEAM_UPDATE / PIP_TEAM_EXIT */
+  int cmd;                       /* PIP_TEAM_* */
   int nthreads;
   int pivi, pivj;
   pip_i64 pivot, dpiv;
@@ -152,14 +157,23 @@ struct PipTeam {
   pip_i64 *B;
   unsigned ovf;
   int fault;
+  /* position scans (PIP_TEAM_FIRST / PIP_TEAM_EXAM): predicate kind + argument, range, result */
+  int op_kind, op_arg, op_from, op_n;
+  int result;
 };
-enum { PIP_TEAM_UPDATE = 0, PIP_TEAM_EXIT = 1, PIP_TEAM_MIN_ROWS = 64 };
+enum { PIP_TEAM_UPDATE = 0, PIP_TEAM_EXIT = 1, PIP_TEAM_FIRST = 2, PIP_TEAM_EXAM = 3,
+       PIP_TEAM_MIN_ROWS = 64,      /* fewer positions: the leader warp updates alone */
+       PIP_TEAM_MIN_SCAN = 128 };   /* fewer positions: the leader warp scans alone */
 #if defined(__CUDACC__) && !defined(PIP_EMU)
 PIP_DEV void pip_team_barrier(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+PIP_DEV void pip_team_min(int *p, int v) { atomicMin(p, v); }
 #else
 PIP_DEV void pip_team_barrier(int) {}
+PIP_DEV void pip_team_min(int *p, int v) { if (v < *p) *p = v; }
 #endif
 
+/* TEAM = the global-memory code path (classes G and M): blocked row walks, and -- when a PipTeam
+ * block is passed -- CTA-wide update and scans.  false = shared-memory classes (and the emulator). */
 template <class V, bool TEAM = false>
 struct PipSolver {
 /* ---- small accessors ------------------------------------------------------------------- */
@@ -185,6 +199,7 @@ PIP_SDEV int pip_first_flag(pip_i64 *B, const PipTab &T, int mask, int from, int
 {
   return pip_first_flag_impl(pip_fl(B, T), mask, from, n);
 }
+
 
 /* warp-cooperative 2-D copy (rows x cols words) between arbitrary strides; one out-of-line copy
  * of this loop serves problem load, sub-tableau construction and the frame stack */
@@ -427,6 +442,90 @@ PIP_SDEV int pip_exam_coef(pip_i64 *B, const PipTab &T, int bigparm)
   return nl;
 }
 
+/* sign class of an Unknown row from its parametric part and constant (source/traiter.c:118-153) */
+PIP_SDEV int pip_classify_row(const V *row, int nvar, int ncol)
+{
+  int ff = PIP_ZERO;
+  #pragma unroll 1
+  for (int j = nvar + 1; j < ncol; j++) {
+    const V v = row[j];
+    const int fff = v < 0 ? PIP_MINUS : v > 0 ? PIP_PLUS : PIP_ZERO;
+    if (fff != PIP_ZERO && fff != ff) {
+      if (ff == PIP_ZERO) ff = fff;
+      else { ff = PIP_UNKNOWN; break; }
+    }
+  }
+  const V c = row[nvar];
+  const int fff = c < 0 ? PIP_MINUS : c > 0 ? PIP_PLUS : PIP_ZERO;
+  if (ff == PIP_PLUS) { if (fff == PIP_MINUS) ff = PIP_UNKNOWN; }
+  else if (ff == PIP_ZERO) ff = fff;
+  else if (ff == PIP_MINUS) { if (fff != PIP_MINUS) ff = PIP_UNKNOWN; }
+  return ff;
+}
+
+/* ---- team-wide position scans (class M): every thread of the CTA runs the *_body between the two
+ * barriers of a command; thread = position modulo the team size, first hit = team minimum -------- */
+PIP_SDEV void pip_team_first_body(PipTeam *tm, int tid)
+{
+  const int *fl = (const int *)(tm->B + tm->T.fl);
+  const int n = tm->op_n, kind = tm->op_kind, arg = tm->op_arg;
+  int best = n;
+  #pragma unroll 1
+  for (int k = tm->op_from + tid; k < n; k += tm->nthreads) {
+    const int f = fl[k];
+    const bool hit = kind == 0 ? (f & arg) != 0 : ((f & PIP_UNIT) != 0 && PIP_LINK(f) == arg);
+    if (hit) { best = k; break; }
+  }
+  best = (int)W::redmin((unsigned)best);
+  if (W::lane() == 0 && best < n) pip_team_min(&tm->result, best);
+}
+
+/* exam_coef_xx without a big parameter (source/traiter.c:118-157): classify the Unknown rows up to
+ * and including the first one proved negative */
+PIP_SDEV void pip_team_exam_body(PipTeam *tm, int tid)
+{
+  const PipTab T = tm->T;
+  pip_i64 *B = tm->B;
+  const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
+  int *fl = pip_fl(B, T);
+  int best = nl;
+  #pragma unroll 1
+  for (int k = tid; k < nl; k += tm->nthreads) {
+    const int f = fl[k];
+    if (PIP_FLAG(f) != PIP_UNKNOWN) continue;
+    if (pip_classify_row(pip_row(B, T, PIP_LINK(f)), T.nvar, ncol) == PIP_MINUS) { best = k; break; }
+  }
+  best = (int)W::redmin((unsigned)best);
+  if (W::lane() == 0 && best < nl) pip_team_min(&tm->result, best);
+  pip_team_barrier(tm->nthreads);
+  const int first = tm->result;
+  #pragma unroll 1
+  for (int k = tid; k < nl && k <= first; k += tm->nthreads) {
+    const int f = fl[k];
+    if (PIP_FLAG(f) != PIP_UNKNOWN) continue;
+    fl[k] = PIP_MKFL(pip_classify_row(pip_row(B, T, PIP_LINK(f)), T.nvar, ncol), PIP_LINK(f));
+  }
+}
+
+/* leader side: post a scan command, take part in it, return the team's answer */
+PIP_SDEV int pip_team_scan(PipTeam *tm, pip_i64 *B, const PipTab &T, int cmd, int kind, int arg, int from, int n)
+{
+  const int lane = W::lane();
+  W::sync();
+  if (lane == 0) {
+    tm->cmd = cmd; tm->T = T; tm->B = B; tm->op_kind = kind; tm->op_arg = arg; tm->op_from = from; tm->op_n = n;
+    tm->result = n;
+  }
+  W::sync();
+  pip_team_barrier(tm->nthreads);
+  if (cmd == PIP_TEAM_FIRST) pip_team_first_body(tm, lane);
+  else pip_team_exam_body(tm, lane);
+  pip_team_barrier(tm->nthreads);
+  const int r = tm->result;
+  W::sync();
+  return r;
+}
+
 /* chercher(Minus) + exam_coef for a tableau of at most 32 positions: one register-resident pass
  * (source/traiter.c:669-680); returns the pivot row or nl */
 PIP_SDEV int pip_scan32(pip_i64 *B, const PipTab &T, int bigparm)
@@ -542,8 +641,9 @@ PIP_SDEV int pip_choose_column(pip_i64 *B, const PipTab &T, int pivi, V &pivot_o
  * the re-flagging from the sign of the new pivot-column entry (source/traiter.c:518-529).
  * The caller's thread handles positions first, first + step, ... */
 PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V pivot, V dpiv, int first, int step,
-                              unsigned &ovf, bool &fault)
+                              unsigned &ovf, bool &fault, PipStats *stp = nullptr)
 {
+  PIP_ULAP_BEGIN(stp);
   const int nl = T.nvar + T.ni, ncol = T.nvar + T.nparm + 1;
   int *fl = pip_fl(B, T);
   V *den = pip_den(B, T);
@@ -565,6 +665,58 @@ PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V
     }
     const V newden = PipVal<V>::mul(lpiv, dk, ovf);
     V g = newden;
+    V zp;
+    PIP_ULAP(stp, PIP_PH_U_HEAD);
+    if (TEAM) {
+      /* arena in global memory (classes G / M): the row is walked in blocks of PIP_UB columns with all
+       * loads of a block issued before the first use, so a pass costs one L2 round trip per block
+       * instead of one per column (the loop is latency-bound, not bandwidth-bound) */
+      enum { PIP_UB = 8 };
+      zp = PipVal<V>::mul(dpiv, foo, ovf);
+      pip_u64 orz = (pip_u64)(pip_i64)zp;
+      #pragma unroll 1
+      for (int j0 = 0; j0 < ncol; j0 += PIP_UB) {
+        V a[PIP_UB], b[PIP_UB];
+        #pragma unroll
+        for (int u = 0; u < PIP_UB; u++) { const bool in = j0 + u < ncol; a[u] = in ? row[j0 + u] : 0; b[u] = in ? prow[j0 + u] : 0; }
+        #pragma unroll
+        for (int u = 0; u < PIP_UB; u++) {
+          V z = PipVal<V>::mulsub(a[u], lpiv, b[u], foo, ovf);
+          if (j0 + u == pivj) z = zp;
+          if (j0 + u < ncol) row[j0 + u] = z;
+          orz |= (pip_u64)(pip_i64)z;
+        }
+      }
+      PIP_ULAP(stp, PIP_PH_U_PASS1);
+      if (g != 1) {
+        if ((g & (g - 1)) == 0 && g > 0) { orz |= (pip_u64)(pip_i64)g; g = (V)(pip_i64)(orz & (0ull - orz)); }
+        else {
+          #pragma unroll 1
+          for (int j0 = 0; j0 < ncol && g != 1; j0 += PIP_UB) {
+            V a[PIP_UB];
+            #pragma unroll
+            for (int u = 0; u < PIP_UB; u++) a[u] = j0 + u < ncol ? row[j0 + u] : 0;
+            #pragma unroll 1
+            for (int u = 0; u < PIP_UB && g != 1; u++) g = pip_gcd(g, a[u]);      /* gcd(g, 0) = g */
+          }
+        }
+      }
+      PIP_ULAP(stp, PIP_PH_U_GCD);
+      if (g != 1) {
+        if (g == 0) { fault = true; continue; }
+        const PipExactDiv e = pip_exact_prepare((pip_i64)g);
+        #pragma unroll 1
+        for (int j0 = 0; j0 < ncol; j0 += PIP_UB) {
+          V a[PIP_UB];
+          #pragma unroll
+          for (int u = 0; u < PIP_UB; u++) a[u] = j0 + u < ncol ? row[j0 + u] : 0;
+          #pragma unroll
+          for (int u = 0; u < PIP_UB; u++) if (j0 + u < ncol) row[j0 + u] = (V)pip_exact_apply((pip_i64)a[u], e);
+        }
+        den[k] = (V)pip_exact_apply((pip_i64)newden, e);
+      } else den[k] = newden;
+      PIP_ULAP(stp, PIP_PH_U_DIV);
+    } else {
     /* pass 1: pure arithmetic.  The generic formula gives 0 in column pivj (foo*lpiv == pivot*foo'),
      * the real value dpiv*foo' is patched in afterwards, so the loop body has no special case */
     pip_u64 orz = 0;
@@ -574,7 +726,7 @@ PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V
       row[j] = z;
       orz |= (pip_u64)(pip_i64)z;
     }
-    const V zp = PipVal<V>::mul(dpiv, foo, ovf);
+    zp = PipVal<V>::mul(dpiv, foo, ovf);
     row[pivj] = zp;
     orz |= (pip_u64)(pip_i64)zp;
     /* pass 2 (only when the row has a common factor to shed): g = gcd(newden, z_0 .. z_n).
@@ -601,6 +753,7 @@ PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V
         den[k] = (V)pip_exact_apply((pip_i64)newden, e);
       }
     } else den[k] = newden;
+    }
     /* sign of the new entry in column pivj = sign of zp (g > 0) */
     int ff = PIP_FLAG(f);
     const int fff = zp < 0 ? PIP_MINUS : zp == 0 ? PIP_ZERO : PIP_PLUS;
@@ -685,9 +838,15 @@ PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st, PipTeam *t
     }
     W::sync();
     pip_team_barrier(tm->nthreads);
-    pip_update_rows(B, T, pivi, pivj, pivot, dpiv, lane, tm->nthreads, ovf, fault);
+    pip_update_rows(B, T, pivi, pivj, pivot, dpiv, lane, tm->nthreads, ovf, fault, lane == 0 ? &st : nullptr);
     if (fault) tm->fault = 1;
+#ifdef PIP_PROFILE
+    const long long w0_ = clock64();
+#endif
     pip_team_barrier(tm->nthreads);
+#ifdef PIP_PROFILE
+    if (lane == 0) st.cyc[PIP_PH_U_WAIT] += (unsigned long long)(clock64() - w0_);
+#endif
     fault = tm->fault != 0;
   } else pip_update_rows(B, T, pivi, pivj, pivot, dpiv, lane, 32, ovf, fault);
   if (PipVal<V>::narrow && W::any(ovf != 0)) return PIP_ST_WIDEN;
@@ -696,12 +855,15 @@ PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st, PipTeam *t
   PIP_LAP(st, PIP_PH_UPDATE);
   /* the Unit position owning pivj takes the pivot row's slot, source/traiter.c:503-516 */
   int ku = nl;
-  #pragma unroll 1
-  for (int base = 0; base < nl; base += 32) {
-    int k = base + lane;
-    int f = k < nl ? fl[k] : 0;
-    unsigned m = W::ballot((f & PIP_UNIT) && PIP_LINK(f) == pivj && k < nl);
-    if (m) { ku = base + pip_ffs(m) - 1; break; }
+  if (TEAM && tm != nullptr && nl >= PIP_TEAM_MIN_SCAN) ku = pip_team_scan(tm, B, T, PIP_TEAM_FIRST, 1, pivj, 0, nl);
+  else {
+    #pragma unroll 1
+    for (int base = 0; base < nl; base += 32) {
+      int k = base + lane;
+      int f = k < nl ? fl[k] : 0;
+      unsigned m = W::ballot((f & PIP_UNIT) && PIP_LINK(f) == pivj && k < nl);
+      if (m) { ku = base + pip_ffs(m) - 1; break; }
+    }
   }
   if (ku >= nl) return PIP_ST_FAULT;
   #pragma unroll 1
@@ -891,8 +1053,14 @@ LOOP:
     const int nl = T.nvar + T.ni;
     if (nl <= 32) pivi = pip_scan32(B, T, level ? -1 : P.bigparm);
     else {
-      pivi = pip_first_flag(B, T, PIP_MINUS, 0, nl);
-      if (pivi >= nl) pivi = pip_exam_coef(B, T, level ? -1 : P.bigparm);
+      const int bg = level ? -1 : P.bigparm;
+      if (TEAM && tm != nullptr && nl >= PIP_TEAM_MIN_SCAN) {
+        pivi = pip_team_scan(tm, B, T, PIP_TEAM_FIRST, 0, PIP_MINUS, 0, nl);
+        if (pivi >= nl) pivi = bg >= 0 ? pip_exam_coef(B, T, bg) : pip_team_scan(tm, B, T, PIP_TEAM_EXAM, 0, 0, 0, nl);
+      } else {
+        pivi = pip_first_flag(B, T, PIP_MINUS, 0, nl);
+        if (pivi >= nl) pivi = pip_exam_coef(B, T, bg);
+      }
     }
     PIP_LAP(st, PIP_PH_SCAN);
     if (pivi < nl) goto PIVOT;

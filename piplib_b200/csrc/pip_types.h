@@ -27,7 +27,8 @@ enum { PIP_F_INT = 1, PIP_F_DUAL = 2, PIP_F_DEEPEST = 4 };
 
 /* phases of the -DPIP_PROFILE cycle accounting */
 enum { PIP_PH_LOAD = 0, PIP_PH_SORT, PIP_PH_SCAN, PIP_PH_BUILDSUB, PIP_PH_CHOOSE, PIP_PH_UPDATE, PIP_PH_SWAP,
-       PIP_PH_CUT, PIP_PH_FRAME, PIP_PH_EMIT, PIP_PH_OTHER, PIP_NPHASE };
+       PIP_PH_CUT, PIP_PH_FRAME, PIP_PH_EMIT, PIP_PH_OTHER,
+       PIP_PH_U_HEAD, PIP_PH_U_PASS1, PIP_PH_U_GCD, PIP_PH_U_DIV, PIP_PH_U_WAIT, PIP_NPHASE };
 
 #define PIP_SOL_SIZE 4096
 #define PIP_MAXCOL 512

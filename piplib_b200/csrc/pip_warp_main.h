@@ -58,12 +58,17 @@ PIP_DEV void pip_team_helper(PipTeam *tm, int tid)
 {
   for (;;) {
     pip_team_barrier(tm->nthreads);
-    if (tm->cmd == PIP_TEAM_EXIT) break;
-    unsigned ovf = 0;
-    bool fault = false;
-    PipSolver<V, true>::pip_update_rows(tm->B, tm->T, tm->pivi, tm->pivj, (V)tm->pivot, (V)tm->dpiv, tid, tm->nthreads,
-                                        ovf, fault);
-    if (fault) tm->fault = 1;
+    const int cmd = tm->cmd;
+    if (cmd == PIP_TEAM_EXIT) break;
+    if (cmd == PIP_TEAM_FIRST) PipSolver<V, true>::pip_team_first_body(tm, tid);
+    else if (cmd == PIP_TEAM_EXAM) PipSolver<V, true>::pip_team_exam_body(tm, tid);
+    else {
+      unsigned ovf = 0;
+      bool fault = false;
+      PipSolver<V, true>::pip_update_rows(tm->B, tm->T, tm->pivi, tm->pivj, (V)tm->pivot, (V)tm->dpiv, tid, tm->nthreads,
+                                          ovf, fault);
+      if (fault) tm->fault = 1;
+    }
     pip_team_barrier(tm->nthreads);
   }
 }
