@@ -59,6 +59,7 @@ struct PinBuf {
 /* team = 0: `warps` warps, one problem each; team = t: `warps` CTAs of t warps, one problem per CTA (class M) */
 struct ClassSpec { int level; int shared; long long words; int warps; int warps_per_cta; long long stack_words; int team; };
 const long long S_MAX_WORDS = 3328;          /* 26 KB: at least 8 warps of class S per SM */
+const long long S32_WIDE_MAX_WORDS = 1700;   /* 13.3 KB: 16 warps of class S32 per SM stay resident */
 const ClassSpec G_LADDER[] = {
     {3, 0, 1ll << 15, 148 * 8, 4, 1ll << 17, 0},
     {4, 0, 1ll << 17, 148 * 4, 4, 1ll << 19, 4},
@@ -190,14 +191,19 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
    * the global-memory ladder for the rest */
   const bool try32 = in.elem_log2 <= 2 && getenv("PIPLIB_B200_NO_INT32") == nullptr;
   std::vector<int> cls(n);              /* -2 = class S32, -1 = class S, k = G_LADDER[k] */
-  long long s_words = 0, s32_words = 0, est_cells_total = 0;
+  long long s_words = 0, s32_words = 0, s32_wide_words = 0, est_cells_total = 0;
+  bool all_sized = true;
   for (size_t i = 0; i < n; i++) {
     const PipProblem &P = in.h_prob[i];
+    if (!(P.flags & PIP_F_SIMPLE_SER)) all_sized = false;
     long long w = pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2, 8);
     if (w <= S_MAX_WORDS) {
       cls[i] = try32 ? -2 : -1;
       s_words = std::max(s_words, w);
-      if (try32) s32_words = std::max(s32_words, pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2, 4));
+      if (try32) {
+        s32_words = std::max(s32_words, pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2, 4));
+        s32_wide_words = std::max(s32_wide_words, pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, PIP_LEVEL_S_WIDE, 4));
+      }
     } else {
       int k = 0;
       while (k < N_G - 1 && pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, G_LADDER[k].level, 8) > G_LADDER[k].words) k++;
@@ -207,6 +213,10 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
   }
   s_words = (s_words + 1) & ~1ll;
   s32_words = (s32_words + 1) & ~1ll;
+  /* the int32 class leaves shared memory unused at 16 warps per SM: spend it on capacity slack, so
+   * fewer problems have to be re-run in a global-memory class */
+  const bool s32_wide = try32 && s32_wide_words <= S32_WIDE_MAX_WORDS && getenv("PIPLIB_B200_NO_WIDE_SLACK") == nullptr;
+  if (s32_wide) s32_words = (s32_wide_words + 1) & ~1ll;
 
   CK(cudaEventRecord(E.ev0, s));
   std::vector<int> order;
@@ -222,7 +232,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       ClassSpec cs;
       int ctas;
       if (k < 0) {
-        cs.level = 2; cs.shared = (k == -2) ? 2 : 1;
+        cs.level = (k == -2 && s32_wide) ? PIP_LEVEL_S_WIDE : 2; cs.shared = (k == -2) ? 2 : 1;
         cs.words = std::max<long long>(k == -2 ? s32_words : s_words, 64);
         cs.warps_per_cta = 4;
         cs.stack_words = 1ll << 14;
@@ -273,7 +283,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? 3 : cs.shared, ctas, cs.warps_per_cta, s));
       out.times.launches++;
       /* compact this round's output: packed cells, or (device-decode mode) serialised quasts */
-      if (ser_mode) {
+      if (ser_mode && !all_sized) {      /* sizing pass, unless the solver sized every stream itself */
         CK(pip_launch_serialize((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
                                 (const PipDecodeParm *)E.d_parm.p, nullptr, nullptr, nullptr, m, 0, s));
         out.times.launches++;

@@ -141,6 +141,7 @@ template <class T>
 bool fill_problem(const MatView &dom, const MatView *ctx, const Shape &s, PipProblem &P, T *pool, size_t off)
 {
   P.nvar = s.Nn; P.nparm = s.Np; P.ni = s.Nl; P.nc = s.Nm; P.bigparm = s.Bg; P.flags = s.flags; P.off = (I)off;
+  if (s.sol_flags == 0 && s.Urs == 0) P.flags |= PIP_F_SIMPLE_SER;      /* decode without column surgery */
   T *tab = pool + off;
   bool ok = matrix_to_rows(dom, tab, s.Nn + s.Np + 1, s.Nn, false, s.Shift, s.Bg, s.Urs);
   if (ctx && s.Nm)
@@ -314,10 +315,9 @@ const char *fatal_message(int status)
 
 PipBatchStats_dp g_stats;
 
-void account(const PipBatchOut &out, double host_seconds)
+/* add one engine run to a statistics record (the per-problem counters are summed, not kept) */
+void accumulate(PipBatchStats_dp &s, const PipBatchOut &out)
 {
-  PipBatchStats_dp s;
-  memset(&s, 0, sizeof s);
   for (const PipResult &r : out.res) {
     s.cells += (unsigned long long)r.ncells;
     s.pivots += r.pivots; s.cuts += r.cuts; s.subsolves += r.subsolves; s.splits += r.splits;
@@ -325,12 +325,29 @@ void account(const PipBatchOut &out, double host_seconds)
     s.max_rows = std::max(s.max_rows, r.max_rows);
     s.max_cols = std::max(s.max_cols, r.max_cols);
   }
-  s.seconds_h2d = out.times.h2d; s.seconds_kernel = out.times.kernel; s.seconds_d2h = out.times.d2h;
+  s.seconds_h2d += out.times.h2d; s.seconds_kernel += out.times.kernel; s.seconds_d2h += out.times.d2h;
+  s.launches += out.times.launches; s.rounds += out.times.rounds;
+  s.device_ms += out.times.device_ms;
+  s.h2d_bytes += out.times.h2d_bytes; s.d2h_bytes += out.times.d2h_bytes;
+  for (int k = 0; k < PIP_NPHASE && k < 16; k++) s.phase_cycles[k] += out.times.phase_cycles[k];
+}
+void merge_stats(PipBatchStats_dp &s, const PipBatchStats_dp &o)
+{
+  s.cells += o.cells; s.pivots += o.pivots; s.cuts += o.cuts; s.subsolves += o.subsolves; s.splits += o.splits;
+  s.elem_updates += o.elem_updates;
+  s.max_rows = std::max(s.max_rows, o.max_rows); s.max_cols = std::max(s.max_cols, o.max_cols);
+  s.seconds_h2d += o.seconds_h2d; s.seconds_kernel += o.seconds_kernel; s.seconds_d2h += o.seconds_d2h;
+  s.launches += o.launches; s.rounds += o.rounds; s.device_ms += o.device_ms;
+  s.h2d_bytes += o.h2d_bytes; s.d2h_bytes += o.d2h_bytes;
+  for (int k = 0; k < 16; k++) s.phase_cycles[k] += o.phase_cycles[k];
+}
+
+void account(const PipBatchOut &out, double host_seconds)
+{
+  PipBatchStats_dp s;
+  memset(&s, 0, sizeof s);
+  accumulate(s, out);
   s.seconds_host = host_seconds;
-  s.launches = out.times.launches; s.rounds = out.times.rounds;
-  s.device_ms = out.times.device_ms;
-  s.h2d_bytes = out.times.h2d_bytes; s.d2h_bytes = out.times.d2h_bytes;
-  for (int k = 0; k < PIP_NPHASE && k < 16; k++) s.phase_cycles[k] = out.times.phase_cycles[k];
   g_stats = s;
 }
 
@@ -930,15 +947,6 @@ void emit_chunk_ser(DenseChunk &C, int *status, unsigned long long *hashes, long
   });
 }
 
-void add_times(PipBatchOut &acc, const PipBatchOut &o)
-{
-  acc.times.h2d += o.times.h2d; acc.times.kernel += o.times.kernel; acc.times.d2h += o.times.d2h;
-  acc.times.device_ms += o.times.device_ms; acc.times.launches += o.times.launches; acc.times.rounds += o.times.rounds;
-  acc.times.h2d_bytes += o.times.h2d_bytes; acc.times.d2h_bytes += o.times.d2h_bytes;
-  for (int k = 0; k < PIP_NPHASE; k++) acc.times.phase_cycles[k] += o.times.phase_cycles[k];
-  acc.res.insert(acc.res.end(), o.res.begin(), o.res.end());
-}
-
 }  // namespace
 
 extern "C" {
@@ -964,12 +972,30 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     DenseArgs A = {n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum,
                    options ? *options : DEFAULT_OPTIONS};
     const size_t CH = env_size("PIPLIB_B200_CHUNK", 1u << 16);
-    const size_t nchunks = ((size_t)n + CH - 1) / CH;
+    /* chunk schedule: full chunks of CH problems, with a geometric ramp at both ends (CH/8, CH/4,
+     * CH/2) so that the GPU starts after one small conversion and the last copy-out is short */
+    std::vector<size_t> sizes;
+    {
+      const size_t ramp = env_size("PIPLIB_B200_RAMP", 3);
+      size_t left = (size_t)n;
+      std::vector<size_t> head, tail;
+      for (size_t k = ramp; k >= 1 && left > 4 * CH; k--) {
+        const size_t sz = std::max<size_t>(CH >> k, 1024);
+        head.push_back(sz); left -= sz;
+        tail.push_back(sz); left -= sz;
+      }
+      sizes = head;
+      while (left > 0) { const size_t sz = std::min(CH, left); sizes.push_back(sz); left -= sz; }
+      for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
+    }
+    const size_t nchunks = sizes.size();
     const size_t lanes = std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 6), PipEngine::MAX_LANES), nchunks);
-    const size_t nthreads = std::max<size_t>(1, host_threads());
+    /* host threads per lane: the lanes' conversion / copy-out phases overlap, so each gets a share */
+    const size_t nthreads = std::max<size_t>(1, env_size("PIPLIB_B200_THREADS", std::max<size_t>(2, (2 * host_threads() + lanes - 1) / lanes)));
     const bool keep = ser != nullptr && ser_off != nullptr;
-    std::vector<DenseChunk> chunks(nchunks);
-    for (size_t c = 0; c < nchunks; c++) { chunks[c].first = c * CH; chunks[c].n = std::min(CH, (size_t)n - c * CH); }
+    std::vector<DenseChunk> chunks(lanes);          /* per-lane scratch, reused from chunk to chunk */
+    std::vector<size_t> firsts(nchunks + 1, 0);
+    for (size_t c = 0; c < nchunks; c++) firsts[c + 1] = firsts[c] + sizes[c];
     std::vector<std::string> errors(lanes);
     std::atomic<long long> cursor(0);
     std::atomic<int> width_hint(0);
@@ -978,11 +1004,14 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
      * forces the host decoder, for A/B tests) */
     const bool device_decode = !A.opt.Simplify && getenv("PIPLIB_B200_HOST_DECODE") == nullptr;
     std::vector<double> tstage(lanes * 4, 0.0);
+    std::vector<PipBatchStats_dp> lane_stats(lanes);
+    for (auto &ls : lane_stats) memset(&ls, 0, sizeof ls);
     auto lane_main = [&](size_t lane) {
       try {
         PipEngine &E = PipEngine::lane((int)lane);
         for (size_t c = lane; c < nchunks; c += lanes) {
-          DenseChunk &C = chunks[c];
+          DenseChunk &C = chunks[lane];
+          C.first = firsts[c]; C.n = sizes[c];
           double ta = wall();
           plan_chunk(A, C, nthreads);
           double tb = wall();
@@ -1007,6 +1036,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
           if (device_decode) emit_chunk_ser(C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
           else emit_chunk(A, C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
           tstage[lane * 4 + 2] += te - td; tstage[lane * 4 + 3] += wall() - te;
+          accumulate(lane_stats[lane], C.out);
           if (timing)
             fprintf(stderr, "[piplib-b200] chunk %zu lane %zu: rounds %d: %d problems %.3f s | %d problems %.3f s | %d problems %.3f s; d2h %.3f s\n", c, lane,
                     C.out.times.rounds, C.out.times.round_n[0], C.out.times.round_s[0], C.out.times.round_n[1], C.out.times.round_s[1],
@@ -1033,10 +1063,11 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
       fprintf(stderr, "[piplib-b200] assemble %.3f s, total %.3f s, %zu chunks, %zu lanes, %zu threads\n",
               wall() - tasm0, wall() - t0, nchunks, lanes, nthreads);
     }
-    PipBatchOut acc;
-    for (size_t c = 0; c < nchunks; c++) add_times(acc, chunks[c].out);
-    const double tt = wall() - t0;
-    account(acc, tt - acc.times.h2d - acc.times.kernel - acc.times.d2h);
+    PipBatchStats_dp acc;
+    memset(&acc, 0, sizeof acc);
+    for (size_t l = 0; l < lanes; l++) merge_stats(acc, lane_stats[l]);
+    acc.seconds_host = (wall() - t0) - acc.seconds_h2d - acc.seconds_kernel - acc.seconds_d2h;
+    g_stats = acc;
     if (keep && total > ser_cap) return -2;
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());

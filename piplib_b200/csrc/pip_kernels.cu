@@ -146,6 +146,10 @@ __global__ void pip_serialize_kernel(PipResult *res, const int *order, const Pip
   } else {
     res[p].cell_off = dst_off[q];
     if (hashes) hashes[p] = (r.status == PIP_ST_OK || r.status == PIP_ST_VOID) ? s.h : 0ull;
+    /* a stream sized by the solver (PIP_RES_SIZED) must come out exactly that long and, when it was
+     * promised narrow, fit 32-bit words: anything else is a bug, never a silent truncation */
+    if ((r.rflags & PIP_RES_SIZED) && (s.len != (long long)r.ser_words || (narrow && s.wide)))
+      res[p].status = PIP_ST_FAULT + 1;
   }
 }
 

@@ -64,7 +64,8 @@ struct PipStats {
 /* capacity slack per level: {new parameters, main cut rows, extra context rows, sub cut rows} */
 PIP_HD void pip_slack(int level, int &dp, int &dr, int &dx, int &ds)
 {
-  if (level >= 3) {
+  if (level == PIP_LEVEL_S_WIDE) { dp = 6; dr = 32; dx = 24; ds = 24; }   /* int32 shared class: spare shared memory */
+  else if (level >= 3) {
     const int k = level - 3 > 5 ? 5 : level - 3;      /* classes G3..G8 grow geometrically */
     dp = 6 << k; dr = 64 << (2 * k); dx = 24 << (2 * k); ds = 24 << (2 * k);
   }
@@ -954,14 +955,16 @@ PIP_SDEV int pip_find_parm(const V *ctx, int cstride, int nr, int nparm, V *cut)
 PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, int words, int slack_level,
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
-                           int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st, PipTeam *tm = nullptr)
+                           int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st, PipTeam *tm = nullptr,
+                           unsigned *nwords_out = nullptr)
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
   PipLayout L;
   int level_try = slack_level;
   while (!pip_layout(P.nvar, P.nparm, P.ni, P.nc, P.flags, level_try, words, (int)sizeof(V), L)) {
-    if (--level_try < 0) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
+    level_try = level_try == PIP_LEVEL_S_WIDE ? 2 : level_try - 1;
+    if (level_try < 0) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
   }
   if (P.flags & (PIP_F_DUAL | PIP_F_DEEPEST)) { status_out = PIP_ST_UNSUPPORTED; ncell_out = 0; return; }
 
@@ -969,6 +972,9 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
   int level = 0;                  /* 0 = main problem, 1 = compatibility / context sub-solve */
   int nc = P.nc;
   int ncell = 0, status = PIP_ST_OK;
+  /* words of the serialised quast (pip_decode.h) when no column surgery applies (PIP_F_SIMPLE_SER):
+   * a node costs 2 (newparm count, kind), a vector of n forms 1 + 2n */
+  unsigned nwords = 0;
   int ret_site = 0, ci = 0, cplus = 0, critic = 0, pivi = 0, depth = 0;
   bool feasible = false, wide = false;
   rflags_out = 0;
@@ -1149,6 +1155,7 @@ AFTER_COMPA:
       pip_put(out, ncell + 1, PIP_C_FORM, np + 1, 0);
     }
     ncell += np + 3;
+    nwords += 2 * np + 5;
     W::sync();
     /* push the ELSE continuation: 12 header words, den[nl], fl[nl], the ni stored rows, the
      * nc+1 context rows (sections padded to whole 8-byte words), the frame size */
@@ -1196,6 +1203,7 @@ NONNEG:
     if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
     wide = pip_emit_solution(B, T, out, ncell) || wide;
     ncell += total;
+    nwords += T.nvar ? 4 + T.nvar * (2 * T.nparm + 4) : 5;
     goto LEAF;
   }
   /* integrer_xx, source/integrer.c:305-534 */
@@ -1260,6 +1268,7 @@ NONNEG:
           #pragma unroll 1
           for (int r = lane; r < T.ni; r += 32) pip_row(B, T, r)[ncol] = 0;
           ncell += np + 5;
+          nwords += 2 * np + 5;
           parm = np;
           T.nparm = np + 1;
           nc += 2;
@@ -1296,11 +1305,13 @@ NONNEG:
       if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
       wide = pip_emit_solution(B, T, out, ncell) || wide;
       ncell += total;
+      nwords += T.nvar ? 4 + T.nvar * (2 * T.nparm + 4) : 5;
       PIP_LAP(st, PIP_PH_EMIT);
     } else {
       if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
       if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
       ncell += 1;
+      nwords += 2;
     }
     goto LEAF;
   }
@@ -1315,6 +1326,7 @@ PIVOT:
     if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
     if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
     ncell += 1;
+    nwords += 2;
   }
 
 LEAF:
@@ -1363,6 +1375,7 @@ DONE:
   PIP_LAP(st, PIP_PH_OTHER);
   status_out = status;
   ncell_out = (status == PIP_ST_OK) ? ncell : 0;
+  if (nwords_out) *nwords_out = status == PIP_ST_OK ? nwords : status == PIP_ST_VOID ? 1u : 0u;
   rflags_out = W::any(wide) ? PIP_RES_WIDE : 0u;
 }
 

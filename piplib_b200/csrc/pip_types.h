@@ -23,13 +23,15 @@ enum { PIP_UNIT = 1, PIP_PLUS = 2, PIP_MINUS = 4, PIP_ZERO = 8, PIP_CRITIC = 16,
 enum { PIP_C_FREE = 0, PIP_C_NIL = 1, PIP_C_IF = 2, PIP_C_LIST = 3, PIP_C_FORM = 4, PIP_C_NEW = 5,
        PIP_C_DIV = 6, PIP_C_VAL = 7, PIP_C_ERROR = 8 };
 /* problem flags (traiter flags, source/funcall.h:34-35, + our own) */
-enum { PIP_F_INT = 1, PIP_F_DUAL = 2, PIP_F_DEEPEST = 4 };
+enum { PIP_F_INT = 1, PIP_F_DUAL = 2, PIP_F_DEEPEST = 4,
+       PIP_F_SIMPLE_SER = 8 };    /* cells -> quast words without column surgery: the solver sizes the stream itself */
 
 /* phases of the -DPIP_PROFILE cycle accounting */
 enum { PIP_PH_LOAD = 0, PIP_PH_SORT, PIP_PH_SCAN, PIP_PH_BUILDSUB, PIP_PH_CHOOSE, PIP_PH_UPDATE, PIP_PH_SWAP,
        PIP_PH_CUT, PIP_PH_FRAME, PIP_PH_EMIT, PIP_PH_OTHER,
        PIP_PH_U_HEAD, PIP_PH_U_PASS1, PIP_PH_U_GCD, PIP_PH_U_DIV, PIP_PH_U_WAIT, PIP_NPHASE };
 
+#define PIP_LEVEL_S_WIDE 100       /* slack level of the int32 shared-memory class when it has room (pip_slack) */
 #define PIP_SOL_SIZE 4096
 #define PIP_MAXCOL 512
 #define PIP_MAXPARM 50
@@ -90,6 +92,7 @@ typedef struct {
  * problem's cells are shipped as raw {kind, param1, param2} triples (3 words per cell). */
 #define PIP_RES_WIDE 1u
 #define PIP_RES_SER32 2u          /* device-decode mode: the quast words were shipped as int32 */
+#define PIP_RES_SIZED 4u          /* ser_words was computed by the solver (PIP_F_SIMPLE_SER) */
 #define PIP_CELL_FITS(p1, p2) ((pip_u64)(p2) < 65536ull && (p1) >= -(1ll << 43) && (p1) < (1ll << 43))
 #define PIP_CELL_PACK(kind, p1, p2) ((pip_u64)(unsigned)(kind) | ((pip_u64)(p2) << 4) | ((pip_u64)(p1) << 20))
 #define PIP_CELL_KIND(w) ((int)((w) & 15ull))

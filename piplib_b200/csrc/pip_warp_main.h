@@ -30,15 +30,20 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
     st.lap = clock64();
 #endif
     int status = PIP_ST_OK, ncell = 0;
-    unsigned rflags = 0;
+    unsigned rflags = 0, nwords = 0;
     PipSolver<V, TEAM>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
-                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm);
+                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm, &nwords);
     if (lane == 0) {
       PipResult r;
       r.status = status; r.ncells = ncell;
       r.cell_off = (pip_i64)warp_id * L.cells_per_warp + used;
       r.pivots = st.pivots; r.cuts = st.cuts; r.subsolves = st.subsolves; r.splits = st.splits;
       r.max_rows = st.max_rows; r.max_cols = st.max_cols; r.ser_words = 0;
+      if (P.flags & PIP_F_SIMPLE_SER) {
+        /* int32 storage keeps every value inside 31 bits, so the quast words fit int32 too */
+        r.ser_words = nwords;
+        rflags |= PIP_RES_SIZED | (PipVal<V>::narrow ? PIP_RES_SER32 : 0u);
+      }
       r.elem_updates_lo = (unsigned)(st.elem_updates & 0xffffffffull);
       r.elem_updates_hi = (unsigned)(st.elem_updates >> 32);
       r.rflags = rflags;

@@ -8,9 +8,13 @@ from piplib_b200 import api, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 dom, ctx = synth.generate("loopnest16x24p3", n)
-for chunk, lanes in [(131072, 4), (65536, 4), (65536, 6), (65536, 8), (32768, 8), (98304, 5)]:
+grid = [(65536, 6, 16, 0), (65536, 6, 16, 3), (65536, 6, 6, 3), (65536, 6, 4, 3), (65536, 4, 8, 3), (65536, 8, 4, 3),
+        (32768, 6, 6, 3), (32768, 8, 4, 2), (131072, 4, 8, 3)]
+for chunk, lanes, threads, ramp in grid:
     os.environ["PIPLIB_B200_CHUNK"] = str(chunk)
     os.environ["PIPLIB_B200_LANES"] = str(lanes)
+    os.environ["PIPLIB_B200_THREADS"] = str(threads)
+    os.environ["PIPLIB_B200_RAMP"] = str(ramp)
     best = 1e9
     res = None
     for it in range(4):
@@ -20,6 +24,6 @@ for chunk, lanes in [(131072, 4), (65536, 4), (65536, 6), (65536, 8), (32768, 8)
         if it:
             best = min(best, dt)
     s = api.last_stats()
-    print("chunk %6d lanes %d: %.3f s -> %.0f problems/s (kernel %.3f h2d %.3f d2h %.3f host %.3f; h2d %.0f MB d2h %.0f MB)"
-          % (chunk, lanes, best, n / best, s.seconds_kernel, s.seconds_h2d, s.seconds_d2h, s.seconds_host,
+    print("chunk %6d lanes %d threads %d ramp %d: %.3f s -> %.0f problems/s (kernel %.3f h2d %.3f d2h %.3f host %.3f; h2d %.0f MB d2h %.0f MB)"
+          % (chunk, lanes, threads, ramp, best, n / best, s.seconds_kernel, s.seconds_h2d, s.seconds_d2h, s.seconds_host,
              s.h2d_bytes / 1e6, s.d2h_bytes / 1e6), flush=True)
