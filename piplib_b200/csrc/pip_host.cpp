@@ -971,7 +971,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     const double t0 = wall();
     DenseArgs A = {n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum,
                    options ? *options : DEFAULT_OPTIONS};
-    const size_t CH = env_size("PIPLIB_B200_CHUNK", 1u << 16);
+    const size_t CH = env_size("PIPLIB_B200_CHUNK", 1u << 17);
     /* chunk schedule: full chunks of CH problems, with a geometric ramp at both ends (CH/8, CH/4,
      * CH/2) so that the GPU starts after one small conversion and the last copy-out is short */
     std::vector<size_t> sizes;
@@ -989,7 +989,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
       for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
     }
     const size_t nchunks = sizes.size();
-    const size_t lanes = std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 6), PipEngine::MAX_LANES), nchunks);
+    const size_t lanes = std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 4), PipEngine::MAX_LANES), nchunks);
     /* host threads per lane: the lanes' conversion / copy-out phases overlap, so each gets a share */
     const size_t nthreads = std::max<size_t>(1, env_size("PIPLIB_B200_THREADS", std::max<size_t>(2, (2 * host_threads() + lanes - 1) / lanes)));
     const bool keep = ser != nullptr && ser_off != nullptr;
