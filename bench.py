@@ -153,6 +153,29 @@ def port_pivots(dom, ctx, sample):
     return stats.pivots, stats.elem_updates
 
 
+def large_tableau_line(pk, pk_src, n=4096, reps=2):
+    """BASELINE config 4 (the HBM-bound kernel of the path): one n x (n+1) int64 tableau solved by the
+    whole grid, cooperative launch, CUDA events inside the library.  Algorithmic bytes per pivot =
+    16*R*C + 8*C + 8*R (dense figure)."""
+    from piplib_b200 import api
+    tab = synth.consecutive_ones(n, n, seed=2026)
+    p = api.LargeProblem(n, n, 1, tab, cut_rows=1024, sol_size=1 << 20, maxcol=1 << 16)
+    p.run()
+    ms = min(p.run() for _ in range(reps))
+    st, cells, info = p.fetch()
+    p.close()
+    piv = max(1, info["pivots"])
+    R, C = n - 1, n + 1
+    alg = (16.0 * R * C + 8.0 * C + 8.0 * R) * piv
+    ach = alg / (ms / 1e3) / 1e9
+    return {"workload": "consecutive-ones %d x %d int64, Nq=1, one problem over the whole grid" % (n, n + 1),
+            "status": st, "pivots": info["pivots"], "kernel_ms": ms, "us_per_pivot": 1e3 * ms / piv,
+            "pivots_per_sec": piv / (ms / 1e3),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / pk["hbm_gbs"], "peak_source": pk_src, "traffic": None,
+                         "note": "dense algorithmic figure; identity row updates are skipped, see profiles/"}}
+
+
 # ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -165,6 +188,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-large", action="store_true", help="skip the config-4 large-tableau measurement")
     ap.add_argument("--check", type=int, default=4096, help="problems cross-checked against the oracle")
     a = ap.parse_args()
 
@@ -319,10 +343,23 @@ def main():
                                  "inputs+cells; the binding resource is the INT pipe / issue slots "
                                  "(see elem_updates_per_sec and profiles/)"},
         }
+        if traffic is not None and t.get("warp_instructions"):
+            # the binding resource of the shared-memory-resident kernel: warp-instruction issue slots.
+            # instructions per problem come from the committed ncu capture of this kernel and workload
+            # (profiles/), the rate is this run's; peak = SMs x 4 schedulers x 1 instruction/cycle x clock
+            ipp = t["warp_instructions"] / t["problems"]
+            clk = (line["clocks"].get("sm_mhz") or pk.get("sm_max_mhz") or 1965.0) * 1e6
+            peak_issue = 148 * 4 * clk
+            line["issue_roofline"] = {"bound": "issue", "achieved": ipp * value / world, "peak": peak_issue,
+                                      "unit": "warp-instructions/s per GPU", "frac": ipp * value / world / peak_issue,
+                                      "warp_instructions_per_problem": ipp,
+                                      "source": "profiles/r1_solve_kernel_traffic.json (ncu smsp__inst_executed.sum)"}
         if e2e_max:
             line["e2e"] = {"value": B * world * K / e2e_max, "unit": UNIT,
                            "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
                            "api": "pip_solve_dense_dp (host PolyLib matrices in, serialised quasts out)"}
+        if world == 1 and not a.no_large:
+            line["config4_large_tableau"] = large_tableau_line(pk, pk_src)
         if world == 1:
             sample = a.cpu_sample or min(B, cores * 2048)
             r = cpu_arm(dom, ctx, sample, cores)

@@ -24,6 +24,7 @@ enum { T_INT = 1, T_DUAL = 2 };                                                 
 enum { S_SHIFT = 1, S_NEGATE = 2, S_REMOVE = 4, S_DUAL = 8 };                              /* source/sol.h:35-48 */
 #define MAX_DET 4   /* source/tab.h:70 */
 
+typedef struct { int rows, cols; const I *p; } Mat;      /* a PolyLib matrix view */
 typedef struct {
   int height, width;     /* row positions, columns */
   int *flag, *link;      /* link: unit column (Unit position) or storage row */
@@ -39,6 +40,8 @@ typedef struct {
   int *cf; I *c1, *c2; int ncell;     /* solution cells (source/sol.c:37-102) */
   int sol_size, maxcol, maxparm;      /* source/type.h:39,49,50 */
   int deepest_cut;
+  int in_dual;               /* serialiser: inside the dual list of a leaf */
+  const Mat *dual_dom;       /* Compute_dual with equalities: the domain (flags the equality rows) */
   int depth;
   jmp_buf env;
   pio_stats *st;
@@ -643,7 +646,6 @@ pirouette:
 }
 
 /* ---- boundary: source/tab.c:292-427 ------------------------------------------------------- */
-typedef struct { int rows, cols; const I *p; } Mat;
 #define M(m, i, j) ((m)->p[(size_t)(i) * (m)->cols + (j)])
 
 /* tab_Matrix2Tableau_xx, source/tab.c:292-393 */
@@ -808,11 +810,34 @@ static void ser_node(Ctx *c, Ser *s, int *i, int bg, int urs, int flags)
     int ne = (int)c->c1[*i - 1];
     sput(s, 1);
     if (ne == 0) { sput(s, 1); sput(s, 0); }     /* one list element with a NULL vector */
-    else {
+    else if (c->in_dual && c->dual_dom) {
+      /* pip_quast_equalities_dual_xx, source/piplib.c:651-690: an equality row was solved as two
+       * inequalities; keep the first dual value when it is non-zero, else minus the second */
+      const Mat *dm = c->dual_dom;
+      int r, kept = ne, e = 0;
+      for (r = 0; r < dm->rows; r++) if (M(dm, r, 0) == 0) kept--;
+      sput(s, kept);
+      for (r = 0; r < dm->rows && e < ne; r++) {
+        Ser drop = {NULL, 0, 0};
+        if (M(dm, r, 0) != 0) { sput(s, 1); ser_vector(c, s, i, bg, urs, flags); e++; continue; }
+        if (c->c1[*i + 1] != 0) {                  /* Form 1, Val: the value cell follows the form */
+          sput(s, 1); ser_vector(c, s, i, bg, urs, flags);
+          ser_vector(c, &drop, i, bg, urs, flags);
+        } else {
+          long at;
+          ser_vector(c, &drop, i, bg, urs, flags);
+          sput(s, 1);
+          at = s->len;
+          ser_vector(c, s, i, bg, urs, flags);
+          if (at + 1 < s->cap) s->out[at + 1] = -s->out[at + 1];
+        }
+        e += 2;
+      }
+    } else {
       sput(s, ne);
       for (k = 0; k < ne; k++) { sput(s, 1); ser_vector(c, s, i, bg, urs, flags); }
     }
-    if (flags & S_DUAL) { sput(s, 1); ser_node(c, s, i, bg, urs, 0); }
+    if (flags & S_DUAL) { sput(s, 1); c->in_dual = 1; ser_node(c, s, i, bg, urs, 0); c->in_dual = 0; }
     else sput(s, 0);
   } else if (kind == K_NIL) {
     sput(s, 0);
@@ -852,6 +877,10 @@ int piporacle_traiter(int nvar, int nparm, int ni, int nc, int bigparm, int nq,
   memset(st, 0, sizeof(*st));
   ctx_init(&c, st, sol_size, maxcol);
   *ncells = 0;
+  /* nq: bit 0 = integer solution wanted (the .dat field); test-only extensions: bit 1 = TRAITER_DUAL
+   * (rational problems), bit 2 = deepest cuts */
+  c.deepest_cut = (nq >> 2) & 1;
+  nq &= 3;
   rc = setjmp(c.env);
   if (rc) { ctx_done(&c); return rc; }
   ineq = tab_new(&c, ni, ncol, nvar);
@@ -859,13 +888,13 @@ int piporacle_traiter(int nvar, int nparm, int ni, int nc, int bigparm, int nq,
     ineq->flag[nvar + i] = F_UNKNOWN; ineq->den[nvar + i] = 1;
     for (j = 0; j < ncol; j++) AT(ineq, nvar + i, j) = tab[(size_t)i * ncol + j];
   }
-  if (nq) simplify(&c, ineq, nvar);
+  if (nq & 1) simplify(&c, ineq, nvar);
   context = tab_new(&c, nc, nparm + 1, 0);
   for (i = 0; i < nc; i++) {
     context->flag[i] = F_UNKNOWN; context->den[i] = 1;
     for (j = 0; j < nparm + 1; j++) AT(context, i, j) = ctx[(size_t)i * (nparm + 1) + j];
   }
-  if (nq) simplify(&c, context, nparm);
+  if (nq & 1) simplify(&c, context, nparm);
   if (nc) {
     Tab *t = expand(&c, context, nparm, nc, nparm + 1, nparm, 0, 0);
     solve(&c, t, NULL, nparm, 0, nc, 0, -1, T_INT);
@@ -873,7 +902,7 @@ int piporacle_traiter(int nvar, int nparm, int ni, int nc, int bigparm, int nq,
     c.ncell = 0;
   }
   if (nonvoid) {
-    solve(&c, ineq, context, nvar, nparm, ni, nc, bigparm, nq ? T_INT : 0);
+    solve(&c, ineq, context, nvar, nparm, ni, nc, bigparm, (nq & 1) ? T_INT : (nq & 2) ? T_DUAL : 0);
     for (i = 0; i < c.ncell && i < cap; i++) { cell_flags[i] = c.cf[i]; cell_p1[i] = c.c1[i]; cell_p2[i] = c.c2[i]; }
     *ncells = c.ncell;
   }
@@ -918,9 +947,9 @@ static int lib_solve(Ctx *c, const Mat *dom, const Mat *par, int bg, const int *
   else if (dual) { flags |= T_DUAL; sol_flags |= S_DUAL; }
   solve(c, ineq, context, nn, np, nl, nm, bg, flags);
   if (simp) sol_simplify(c, 0);
+  c->dual_dom = ((sol_flags & S_DUAL) && nl > dom->rows) ? dom : NULL;     /* source/piplib.c:867-868 */
   ser_node(c, s, &xq, bg - nn - 1, urs, sol_flags);
-  /* pip_quast_equalities_dual_xx (source/piplib.c:651-690) is not restated: parity for
-   * Compute_dual with equalities is out of the pinned set */
+
   return PIO_OK;
 }
 

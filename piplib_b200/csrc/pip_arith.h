@@ -83,6 +83,23 @@ PIP_HD pip_i64 pip_mod(pip_i64 a, pip_i64 b)
 }
 PIP_HD pip_i64 pip_floor_q(pip_i64 a, pip_i64 b) { return pip_div(a - pip_mod(a, b), b); }
 
+/* bezout_xx, source/integrer.c:98-150: z in [0, delta) with z*y = x (mod delta), 0 when y is not a
+ * unit modulo delta.  Wrapping products like the reference's. */
+PIP_HDNI pip_i64 pip_bezout(pip_i64 x, pip_i64 y, pip_i64 delta)
+{
+  pip_i64 a = 1, b = 0, c = 0, d = 1, u = y, v = delta;
+  for (;;) {
+    const pip_i64 r = pip_mod(u, v);
+    if (r == 0) break;
+    const pip_i64 q = pip_div(u - r, v);
+    u = v; v = r;
+    const pip_i64 e = (pip_i64)((pip_u64)a - (pip_u64)q * (pip_u64)c), f = (pip_i64)((pip_u64)b - (pip_u64)q * (pip_u64)d);
+    a = c; b = d; c = e; d = f;
+  }
+  if (v != 1) return 0;
+  return pip_mod((pip_i64)((pip_u64)c * (pip_u64)x), delta);
+}
+
 /* 32-bit overloads for the int32 instantiation of the solver (no 64-bit division subroutine) */
 PIP_HD int pip_gcd(int a, int b)
 {

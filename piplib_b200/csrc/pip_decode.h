@@ -93,9 +93,12 @@ template <class C>
 PIP_HD bool pip_ser_cells(PipSer &s, const C &c, int n, int Bg, int Urs_p, int flags)
 {
   int i = 0;
+  bool dual_node = false;          /* the node being decoded is the dual list of the previous leaf */
+  const int all_flags = flags;
   while (i < n) {
     while (i < n && c.kind(i) == PIP_C_FREE) i++;
     if (i >= n) break;
+    flags = dual_node ? 0 : all_flags;                 /* sol_quast_edit_xx(i, solution, Bg, Urs_p, 0), source/sol.c:706-708 */
     int nnew = 0;
     for (int t = i; t < n && c.kind(t) == PIP_C_NEW; t += (int)c.p1(t + 2) + 4) nnew++;   /* New Div Form Val*m Val */
     pip_sput(s, nnew);
@@ -120,12 +123,15 @@ PIP_HD bool pip_ser_cells(PipSer &s, const C &c, int n, int Bg, int Urs_p, int f
         pip_sput(s, nb);
         for (int e = 0; e < nb; e++) { pip_sput(s, 1); pip_ser_vector(s, c, i, Bg, Urs_p, flags); }
       }
-      pip_sput(s, 0);                                    /* no dual leaf (Compute_dual is host-rejected) */
+      if (!dual_node && (all_flags & PIP_SOL_DUAL)) { pip_sput(s, 1); dual_node = true; }   /* the dual list follows */
+      else { pip_sput(s, 0); dual_node = false; }
     } else if (kind == PIP_C_NIL) {
       pip_sput(s, 0);
+      dual_node = false;
     } else if (kind == PIP_C_IF) {
       pip_sput(s, 2);
       pip_ser_vector(s, c, i, Bg, Urs_p, flags & PIP_SOL_REMOVE);
+      dual_node = false;
     } else return false;
   }
   return true;

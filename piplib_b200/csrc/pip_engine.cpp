@@ -197,7 +197,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
     const PipProblem &P = in.h_prob[i];
     if (!(P.flags & PIP_F_SIMPLE_SER)) all_sized = false;
     long long w = pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2, 8);
-    if (w <= S_MAX_WORDS) {
+    if (w <= S_MAX_WORDS && !(P.flags & (PIP_F_DUAL | PIP_F_DEEPEST))) {   /* options: global-memory classes only */
       cls[i] = try32 ? -2 : -1;
       s_words = std::max(s_words, w);
       if (try32) {

@@ -547,6 +547,31 @@ static void unpack_cells(const PipCellView &v, std::vector<PipCell> &out)
   for (int i = 0; i < v.n; i++) { out[i].kind = v.kind(i); out[i].pad = 0; out[i].p1 = v.p1(i); out[i].p2 = v.p2(i); }
 }
 
+/* pip_quast_equalities_dual_xx, source/piplib.c:651-690: an equality was solved as a pair of
+ * inequalities; keep one dual value per equality (negated when it belongs to the negative half) */
+static void equalities_dual(PipQuast_dp *sol, const MatView &dom)
+{
+  if (!sol) return;
+  if (sol->condition) { equalities_dual(sol->next_then, dom); equalities_dual(sol->next_else, dom); }
+  if (!sol->list || !sol->next_then || !sol->next_then->list) return;
+  PipList_dp **lp = &sol->next_then->list;
+  for (int i = 0; i < dom.rows; i++) {
+    if (MV(dom, i, 0) != 0) { lp = &(*lp)->next; continue; }
+    if ((*lp)->vector->the_vector[0] != 0) {
+      lp = &(*lp)->next;
+      PipList_dp *l = *lp;
+      *lp = l->next; l->next = nullptr;
+      pip_list_free_dp(l);
+    } else {
+      PipList_dp *l = *lp;
+      *lp = l->next; l->next = nullptr;
+      pip_list_free_dp(l);
+      (*lp)->vector->the_vector[0] = -(*lp)->vector->the_vector[0];
+      lp = &(*lp)->next;
+    }
+  }
+}
+
 static PipQuast_dp *decode_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify)
 {
   const PipCellView v = bo.cells_of(i);
@@ -564,8 +589,17 @@ static PipQuast_dp *decode_one(const PipBatchOut &bo, size_t i, const Shape &s, 
 
 /* serialise problem i straight from its cells (status OK or VOID) with the decoder the device
  * uses too (pip_decode.h) */
-static void serialize_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify, Ser &out)
+static void serialize_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify, Ser &out,
+                          const MatView *dom = nullptr)
 {
+  if (dom && (s.sol_flags & S_DUAL) && s.Nl > dom->rows && bo.res[i].status == PIP_ST_OK) {
+    /* Compute_dual with equalities: the post-pass works on the tree (source/piplib.c:867-868) */
+    PipQuast_dp *q = decode_one(bo, i, s, simplify);
+    equalities_dual(q, *dom);
+    ser_quast(out, q);
+    pip_quast_free_dp(q);
+    return;
+  }
   PipSer ps = {out.out, out.cap, out.len, out.h, out.hashing ? 1 : 0, 0, 0};
   if (bo.res[i].status == PIP_ST_VOID) pip_sput(ps, -1);
   else {
@@ -625,7 +659,13 @@ int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const 
       for (size_t q = a; q < b; q++) {
         int i = live[q];
         status[i] = bo.res[q].status;
-        if (status[i] == PIP_ST_OK) out[i] = decode_one(bo, q, shapes[i], o.Simplify);
+        if (status[i] == PIP_ST_OK) {
+          out[i] = decode_one(bo, q, shapes[i], o.Simplify);
+          if ((shapes[i].sol_flags & S_DUAL) && shapes[i].Nl > (int)domains[i]->NbRows) {
+            MatView d = {(int)domains[i]->NbRows, (int)domains[i]->NbColumns, domains[i]->p, nullptr};
+            equalities_dual(out[i], d);
+          }
+        }
       }
     });
     {
@@ -880,7 +920,13 @@ void emit_chunk(const DenseArgs &A, DenseChunk &C, int *status, unsigned long lo
         long long w = 0;
         if (st == PIP_ST_VOID) w = 1;
         else if (st == PIP_ST_OK) {
-          if (simplify) { Ser s = {nullptr, 0, 0, 0, false}; serialize_one(C.out, i, C.shapes[i], simplify, s); w = s.len; }
+          const bool dualeq = (C.shapes[i].sol_flags & S_DUAL) && C.shapes[i].Nl > A.dr;
+          if (simplify || dualeq) {
+            MatView d = {A.dr, A.dc, nullptr, A.dom ? A.dom + (C.first + i) * A.dr * A.dc : nullptr};
+            Ser s = {nullptr, 0, 0, 0, false};
+            serialize_one(C.out, i, C.shapes[i], simplify, s, A.dom ? &d : nullptr);
+            w = s.len;
+          }
           else {
             const PipCellView v = C.out.cells_of(i);
             int at = 0;
@@ -905,7 +951,8 @@ void emit_chunk(const DenseArgs &A, DenseChunk &C, int *status, unsigned long lo
       unsigned long long h = 0;
       if (st == PIP_ST_OK || st == PIP_ST_VOID) {
         Ser s = {fits ? ser + at : nullptr, fits ? (long)C.words[i] : 0, 0, 0xcbf29ce484222325ULL, hashes != nullptr};
-        if (fits || hashes) serialize_one(C.out, i, C.shapes[i], simplify, s);
+        MatView d = {A.dr, A.dc, nullptr, A.dom ? A.dom + (C.first + i) * A.dr * A.dc : nullptr};
+        if (fits || hashes) serialize_one(C.out, i, C.shapes[i], simplify, s, A.dom ? &d : nullptr);
         h = s.h;
       }
       if (hashes) hashes[C.first + i] = h;
@@ -1002,7 +1049,8 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     const bool timing = getenv("PIPLIB_B200_TIMING") != nullptr;
     /* decode on the GPU unless the host-only Simplify post-pass is wanted (PIPLIB_B200_HOST_DECODE=1
      * forces the host decoder, for A/B tests) */
-    const bool device_decode = !A.opt.Simplify && getenv("PIPLIB_B200_HOST_DECODE") == nullptr;
+    const bool device_decode = !A.opt.Simplify && !(A.opt.Compute_dual && !A.opt.Nq) &&
+                               getenv("PIPLIB_B200_HOST_DECODE") == nullptr;
     std::vector<double> tstage(lanes * 4, 0.0);
     std::vector<PipBatchStats_dp> lane_stats(lanes);
     for (auto &ls : lane_stats) memset(&ls, 0, sizeof ls);

@@ -110,6 +110,7 @@ PIP_HD bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level
   L.s.den = o; o += PIP_W(SP);
   L.s.fl = o; o += (SP + 1) / 2;
   L.s.data = o; o += PIP_W(SR * XC);
+  if (flags & PIP_F_DUAL) o += (R + 1) / 2;     /* Compute_dual: pos[] of the entry sort, the last (R+1)/2 words */
   L.total = o;
 #undef PIP_W
   L.m.stride = C; L.m.pcap = Pm; L.m.rcap = R;
@@ -286,6 +287,7 @@ PIP_SDEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
   V *den = pip_den(B, T);
   float *sz = (float *)(B + tmpoff);
   unsigned smax_u = 0;
+
   #pragma unroll 1
   for (int k = T.nvar + lane; k < nl; k += 32) {
     int f = fl[k];
@@ -385,6 +387,119 @@ PIP_SDEV void pip_sort_rows(pip_i64 *B, const PipTab &T, int tmpoff)
     }
   }
   W::sync();
+}
+
+/* ---- cold paths (PipOptions the polyhedral tools rarely set), out of line so that the hot code of
+ * the instruction-supply-bound kernel keeps its layout ---------------------------------------- */
+
+/* tab_sort_rows_xx with TRAITER_DUAL, source/traiter.c:556-623: the same selection sort, one step at
+ * a time on lane 0, recording pos[r] = position of input row r after the sort (no Unit row exists in
+ * the constraint range at the entry of a split-free solve) */
+PIP_SDEVNI void pip_sort_rows_dual(pip_i64 *B, const PipTab &T, int tmpoff, int *pos)
+{
+  const int lane = W::lane();
+  const int nl = T.nvar + T.ni;
+  int *fl = pip_fl(B, T);
+  V *den = pip_den(B, T);
+  float *sz = (float *)(B + tmpoff);
+  unsigned smax_u = 0;
+  #pragma unroll 1
+  for (int k = T.nvar + lane; k < nl; k += 32) {
+    const V *row = pip_row(B, T, PIP_LINK(fl[k]));
+    const V d = den[k];
+    unsigned s = 0;
+    #pragma unroll 1
+    for (int j = 0; j < T.nvar; j++) {
+      unsigned v;
+      if (d == 1) { const pip_u64 u = pip_uabs(row[j]); v = u < 2147483648ull ? (unsigned)u : 0u; }
+      else v = pip_size_term(row[j], d);
+      if (v > s) s = v;
+    }
+    sz[k] = (float)(double)s;
+    pos[k - T.nvar] = k;
+    if (s > smax_u) smax_u = s;
+  }
+  smax_u = W::redmax(smax_u);
+  const double smax = (double)smax_u;
+  W::sync();
+  if (lane == 0) {
+    #pragma unroll 1
+    for (int i = T.nvar; i < nl; i++) {
+      double s = smax;
+      int pivi = i;
+      #pragma unroll 1
+      for (int j = i; j < nl; j++) if ((double)sz[j] < s) { s = (double)sz[j]; pivi = j; }
+      if (pivi == i) continue;
+      const int f = fl[i]; fl[i] = fl[pivi]; fl[pivi] = f;
+      const V d = den[i]; den[i] = den[pivi]; den[pivi] = d;
+      const float t = sz[i]; sz[i] = sz[pivi]; sz[pivi] = t;
+      int ri = -1, rb = -1;                            /* the two input rows trade positions */
+      #pragma unroll 1
+      for (int r = 0; r < T.ni; r++) { if (pos[r] == i) ri = r; else if (pos[r] == pivi) rb = r; }
+      if (ri >= 0) pos[ri] = pivi;
+      if (rb >= 0) pos[rb] = i;
+    }
+  }
+  W::sync();
+}
+
+/* solution_dual_xx, source/traiter.c:274-294: one form per input row; a row that left the basis (its
+ * position is Unit) reports the entry of position 0 in the column it owns.  Without cuts the tableau
+ * height is nvar + ni, so the list has ni forms (1 + 2 ni cells at out[at..]). */
+PIP_SDEVNI bool pip_emit_dual(pip_i64 *B, const PipTab &T, const int *pos, PipCell *out, int at)
+{
+  bool wide = false;
+  const int dtotal = 1 + 2 * T.ni;
+  const int *fl = pip_fl(B, T);
+  const V *den = pip_den(B, T);
+  const int f0 = fl[0];
+  const V d0 = den[0];
+  #pragma unroll 1
+  for (int c = W::lane(); c < dtotal; c += 32) {
+    if (c == 0) { pip_put(out, at, PIP_C_LIST, T.ni, 0); continue; }
+    const int i = (c - 1) >> 1;
+    if (((c - 1) & 1) == 0) { pip_put(out, at + c, PIP_C_FORM, 1, 0); continue; }
+    const int fp = fl[pos[i]];
+    if (fp & PIP_UNIT) wide = pip_put(out, at + c, PIP_C_VAL, pip_entry(B, T, f0, d0, PIP_LINK(fp)), d0) || wide;
+    else pip_put(out, at + c, PIP_C_VAL, 0, 1);
+  }
+  return wide;
+}
+
+/* Gondran's deepest cut, source/integrer.c:417-438 (constant cuts only): multiply the cut by the unit
+ * lambda of Z/D that maximises its depth; lambda is scalar work for lane 0.  Returns false on a
+ * division by zero (the reference would die of SIGFPE). */
+PIP_SDEVNI bool pip_deepest_cut(V *cut, int nvar, V D, unsigned &ovf)
+{
+  const int lane = W::lane();
+  pip_i64 lambda = 0;
+  int bad = 0;
+  const pip_i64 D64 = (pip_i64)D;
+  if (lane == 0) {
+    const pip_i64 tt = -(pip_i64)cut[nvar];
+    const pip_i64 delta = pip_gcd(tt, D64);
+    if (delta == 0) bad = 1;
+    else {
+      const pip_i64 tau = pip_div(tt, delta), dd = pip_div(D64, delta);
+      lambda = pip_bezout(dd - 1, tau, dd);
+      int guard = 0;
+      while (pip_gcd(lambda, D64) != 1) {
+        lambda = (pip_i64)((pip_u64)lambda + (pip_u64)dd);
+        if (++guard > (1 << 22)) { bad = 1; break; }
+      }
+    }
+  }
+  if (W::shfl(bad, 0)) return false;
+  lambda = W::shfl64(lambda, 0);
+  #pragma unroll 1
+  for (int j = lane; j < nvar; j += 32)
+    cut[j] = PipVal<V>::store(pip_mod((pip_i64)((pip_u64)lambda * (pip_u64)(pip_i64)cut[j]), D64), ovf);
+  if (lane == 0) {
+    const pip_i64 tt = pip_mod((pip_i64)((pip_u64)(pip_i64)cut[nvar] * (pip_u64)lambda), D64);
+    cut[nvar] = PipVal<V>::store(-(D64 - tt), ovf);
+  }
+  W::sync();
+  return true;
 }
 
 /* exam_coef_xx, source/traiter.c:101-159.  Returns the first row proved negative or nl. */
@@ -966,7 +1081,15 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
     level_try = level_try == PIP_LEVEL_S_WIDE ? 2 : level_try - 1;
     if (level_try < 0) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
   }
-  if (P.flags & (PIP_F_DUAL | PIP_F_DEEPEST)) { status_out = PIP_ST_UNSUPPORTED; ncell_out = 0; return; }
+  /* Compute_dual with parameters: the reference re-sorts the copy made at a split with Unit rows in
+   * the constraint range and reads ineq[] entries it never wrote (source/traiter.c:585 vs 616-617),
+   * so its answer is undefined; only the split-free case is implemented */
+  if ((P.flags & PIP_F_DUAL) && (P.nparm > 0 || P.nc > 0)) { status_out = PIP_ST_UNSUPPORTED; ncell_out = 0; return; }
+  /* the rarely-set options live in the global-memory instantiations only (TEAM), so that the code of
+   * the instruction-supply-bound shared-memory kernels is not touched by them; a problem that asks
+   * for one here is handed to the next class like any other that does not fit */
+  if (!TEAM && (P.flags & (PIP_F_DUAL | PIP_F_DEEPEST))) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
+  const bool dual = TEAM && (P.flags & PIP_F_DUAL) != 0 && !integer;
 
   PipTab T = L.m, M = L.m;       /* current tableau, saved main tableau while in a sub-solve */
   int level = 0;                  /* 0 = main problem, 1 = compatibility / context sub-solve */
@@ -1051,7 +1174,8 @@ BUILD_SUB:
 ENTRY:
   /* traiter_xx entry, source/traiter.c:643-656 (the private context copy is implicit) */
   if (level) st.subsolves++;
-  pip_sort_rows(B, T, L.tmp);
+  if (dual && level == 0) pip_sort_rows_dual(B, T, L.tmp, (int *)(B + L.total - (L.m.rcap + 1) / 2));
+  else pip_sort_rows(B, T, L.tmp);
   PIP_LAP(st, PIP_PH_SORT);
 
 LOOP:
@@ -1204,6 +1328,12 @@ NONNEG:
     wide = pip_emit_solution(B, T, out, ncell) || wide;
     ncell += total;
     nwords += T.nvar ? 4 + T.nvar * (2 * T.nparm + 4) : 5;
+    if (dual) {
+      const int dtotal = 1 + 2 * T.ni;
+      if (ncell + dtotal >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+      wide = pip_emit_dual(B, T, (const int *)(B + L.total - (L.m.rcap + 1) / 2), out, ncell) || wide;
+      ncell += dtotal;
+    }
     goto LEAF;
   }
   /* integrer_xx, source/integrer.c:305-534 */
@@ -1238,6 +1368,7 @@ NONNEG:
       if (!ok_parm && !ok_const) continue;                  /* case (a) */
       if (!ok_parm && !ok_var) { verdict = -1; break; }     /* case (b) */
       if (T.ni >= T.rcap || nl >= T.pcap) { status = PIP_ST_CAPACITY; goto DONE; }
+      if (TEAM && (P.flags & PIP_F_DEEPEST) && !ok_parm && !pip_deepest_cut(cut, nvar, D, ovf)) { status = PIP_ST_FAULT; goto DONE; }
       int parm = -1;
       if (ok_parm) {                                         /* case (e), source/integrer.c:493-520 */
         if (lane == 0) parm = pip_find_parm(ctx, cstride, nc, np, cut + nvar);

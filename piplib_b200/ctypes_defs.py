@@ -49,7 +49,7 @@ def pack_tableau_problems(cases):
         assert tab.size == c["ni"] * (c["nvar"] + c["nparm"] + 1)
         assert ctx.size == c["nc"] * (c["nparm"] + 1)
         probs[i] = (c["nvar"], c["nparm"], c["ni"], c["nc"], c["bigparm"],
-                    F_INT if c["nq"] else 0, off)
+                    (F_INT if c["nq"] & 1 else (2 if c["nq"] & 2 else 0)) | (4 if c["nq"] & 4 else 0), off)
         chunks += [tab, ctx]
         off += tab.size + ctx.size
     pool = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.int64)

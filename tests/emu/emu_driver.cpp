@@ -15,7 +15,8 @@ struct EmuArgs { PipLaunch L; pip_i64 *arena; int narrow; };
 static void warp_entry(void *a, int)
 {
   EmuArgs *e = (EmuArgs *)a;
-  if (e->narrow) pip_warp_main<int>(e->L, 0, e->arena);
+  if (e->narrow == 2) pip_warp_main<pip_i64, true>(e->L, 0, e->arena, nullptr);   // the global-memory code path (classes G / M)
+  else if (e->narrow) pip_warp_main<int>(e->L, 0, e->arena);
   else pip_warp_main<pip_i64>(e->L, 0, e->arena);
 }
 

@@ -42,6 +42,15 @@ def test_random_tableaus():
     assert not bad, bad
 
 
+def test_global_memory_code_path():
+    """the instantiation used by the global-memory classes (blocked row walks, options compiled in)"""
+    cases = CLI + [c for c in RCLI if c["name"] not in HEAVY]
+    out = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=2, narrow=2)
+    bad = [c["name"] for c, (st, cells, _) in zip(cases, out)
+           if st != c["ref_status"] or cells != c["ref_cells"]]
+    assert not bad, bad
+
+
 def test_capacity_escalation_is_reported():
     """a too-small arena must yield the internal CAPACITY status, never a wrong answer."""
     c = [x for x in load_golden("cli_suite.json") if x["name"] == "bouleti"][0]
@@ -87,3 +96,24 @@ def test_int32_instantiation_is_exact_or_widens(order_mode):
             bad.append(c["name"])
     assert not bad, bad
     assert 0 < widened < len(cases) // 3
+
+
+def test_deepest_cut_and_dual_in_emulation(port):
+    """PipOptions the fixtures never exercise, device source vs the oracle (itself pinned against the
+    live reference by tests/golden/options_suite.json): Deepest_cut on every integer tableau,
+    Compute_dual on the rational ones without parameters (nq bit 2 / bit 1, tests only)"""
+    base = CLI + [c for c in RCLI if c["name"] not in HEAVY]
+    deep = [dict(c, nq=5) for c in base if c["nq"] == 1]
+    dual = [dict(c, nq=2) for c in base if c["nparm"] == 0 and c["nc"] == 0]
+    assert len(deep) > 100 and len(dual) > 60
+    for cases in (deep, dual):
+        out = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=2, narrow=2)
+        bad = []
+        for c, (st, cells, _) in zip(cases, out):
+            st_o, cells_o = port.traiter(c["nvar"], c["nparm"], c["ni"], c["nc"], c["bigparm"], c["nq"],
+                                         c["tab"], c["ctx"])
+            if st_o >= 3000 or st == 4001:        # oracle time-out / CAPACITY: re-run one class up by the host
+                continue
+            if st != st_o or [tuple(x) for x in cells] != cells_o:
+                bad.append((c["name"], st, st_o))
+        assert not bad, bad

@@ -16,6 +16,7 @@ CLI = [c for c in load_golden("cli_suite.json") if "pipFile_1" not in c["name"]]
 LIB = load_golden("lib_suite.json")
 RLIB = load_golden("random_lib.json")
 RCLI = load_golden("random_cli.json")
+OPTS = load_golden("options_suite.json")
 
 
 @pytest.fixture(scope="module")
@@ -100,6 +101,37 @@ def test_random_lib(api):
         out = api.solve_batch([_lib_problem(c) for c in cases], **dict(opts))
         bad += [c["name"] for c, r in zip(cases, out) if _norm(r) != (c["ref_status"], c["ref_ser"])]
     assert not bad, bad
+
+
+def test_options_suite(api):
+    """Deepest_cut (device: Gondran's multiplier on constant cuts) and Compute_dual (device: row
+    positions tracked through the entry sort, dual list at the leaf; host: equalities post-pass)
+    against live answers of the reference; batch entry point and the dense entry point"""
+    groups = {}
+    for c in OPTS:
+        groups.setdefault(tuple(sorted(c["opts"].items())), []).append(c)
+    bad = []
+    for opts, cases in groups.items():
+        out = api.solve_batch([_lib_problem(c) for c in cases], **dict(opts))
+        bad += [(c["name"], r[0]) for c, r in zip(cases, out) if _norm(r) != (c["ref_status"], c["ref_ser"])]
+    assert not bad, bad
+    # dense entry point: same shapes batched together, serialised stream word for word
+    dense = {}
+    for c in OPTS:
+        if c["ctx"] is None or c["ctx_shape"] is None:
+            dense.setdefault((tuple(c["dom_shape"]), tuple(sorted(c["opts"].items()))), []).append(c)
+    checked = 0
+    for (shape, opts), cases in dense.items():
+        dom = np.asarray([c["dom"] for c in cases], dtype=np.int64).reshape(len(cases), *shape)
+        r = api.solve_dense(dom, None, -1, want_hashes=True, want_ser=True, **dict(opts))
+        for k, c in enumerate(cases):
+            st = int(r["status"][k])
+            mine = [int(x) for x in r["ser"][r["ser_off"][k]:r["ser_off"][k] + r["ser_len"][k]]]
+            assert (0 if st == 1 else st) == c["ref_status"], c["name"]
+            if c["ref_status"] == 0:
+                assert mine == c["ref_ser"], c["name"]
+            checked += 1
+    assert checked > 50
 
 
 def test_random_cli(api):

@@ -149,17 +149,69 @@ def random_cli_cases(ref, n, seed):
     return cases
 
 
+def options_suite(ref, n, seed):
+    """the options the reference's own tests never exercise (SURVEY.md 8c "unpinned"): Deepest_cut on
+    every integer example and on random integer problems; Compute_dual on random rational problems
+    without parameters (with parameters the reference reads uninitialised memory, source/traiter.c:585
+    vs 616-617), a share of them with equalities (pip_quast_equalities_dual_xx)."""
+    cases = []
+    for f in sorted(glob.glob(REF + "/example/*.pip")):
+        name = os.path.basename(f)[:-4]
+        p = po.parse_pip(open(f).read())
+        if not p["opts"].get("Nq", 1):
+            continue
+        opts = dict(p["opts"])
+        opts["Deepest_cut"] = 1
+        st, ser = ref.solve(p["dom"], p["ctx"], p["bignum"], ctx_cols=p["ctx_shape"][1], **opts)
+        c = dict(p)
+        c.update(name=name + "@Deepest_cut=1", opts=opts, ref_status=st, ref_ser=ser, golden_ll=None)
+        cases.append(c)
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        deepest = i % 2 == 0
+        nn = int(rng.integers(1, 6))
+        npar = int(rng.integers(0, 3)) if deepest else 0
+        nl = int(rng.integers(1, 8))
+        nm = int(rng.integers(0, 3)) if npar else 0
+        lim = int(rng.choice([1, 2, 3, 7, 30]))
+        dom = rng.integers(-lim, lim + 1, size=(nl, nn + npar + 2))
+        dom[:, 0] = (rng.random(nl) > 0.2).astype(np.int64)
+        dom[:, -1] = rng.integers(-6, 20, size=nl)
+        ctx = rng.integers(-lim, lim + 1, size=(nm, npar + 2))
+        if nm:
+            ctx[:, 0] = 1
+            ctx[:, -1] = rng.integers(-2, 9, size=nm)
+        if deepest:
+            opts = {"Nq": 1, "Deepest_cut": 1}
+            have_ctx = bool(npar) or rng.random() < 0.5
+        else:
+            opts = {"Nq": 0, "Compute_dual": 1}
+            have_ctx = False
+        st, ser = ref.solve(dom, ctx if have_ctx else None, -1, ctx_cols=npar + 2, **opts)
+        if len(ser) > 4000 or st >= 3000:
+            continue
+        cases.append(dict(name="opt%d" % i, dom_shape=list(dom.shape), dom=dom.tolist(),
+                          ctx_shape=[nm, npar + 2] if have_ctx else None,
+                          ctx=ctx.tolist() if have_ctx else None, bignum=-1, opts=opts,
+                          ref_status=st, ref_ser=ser))
+    return cases
+
+
 def main():
     po.build()
     ref = po.Ref()
     ref.lib.pipref_set_timeout_ms(3000)       # run-away random problems are dropped (status 3000)
     os.makedirs(OUT, exist_ok=True)
-    suites = {
+    if "--options-only" in sys.argv:
+        suites = {"options_suite.json": options_suite(ref, 400, 777)}
+    else:
+      suites = {
+        "options_suite.json": options_suite(ref, 400, 777),
         "cli_suite.json": cli_suite(ref),
         "lib_suite.json": lib_suite(ref),
         "random_lib.json": random_lib_cases(ref, 400, 20261018),
         "random_cli.json": random_cli_cases(ref, 400, 4242),
-    }
+      }
     for fn, cases in suites.items():
         path = os.path.join(OUT, fn)
         with open(path, "w") as f:
