@@ -55,7 +55,8 @@ typedef struct {
 typedef struct {
   int nvar, nparm, ni, nc;  /* .dat header fields Nn Np Nl Nm (doc/piplib.texi:570-586) */
   int bigparm;              /* Bg: tableau column of the big parameter, or -1 */
-  int nq;                   /* 1 integer, 0 rational */
+  int nq;                   /* bit 0: 1 integer, 0 rational (the .dat field); bit 1: rational with dual
+                               variables (TRAITER_DUAL, no parameters); bit 2: deepest cuts (pip -d) */
 } PipTableauHeader_dp;
 
 typedef struct {
@@ -83,6 +84,10 @@ int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const 
 int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long *const *tab,
                          const long long *const *ctx, int *status, PipCell_dp *cells_out,
                          long long cell_cap, long long *cell_off, int *ncells, long long *cells_needed);
+
+/* sol_simplify_xx (source/sol.c:272-288; `pip -z`) on one problem's cells as returned by
+ * pip_traiter_batch_dp: cells may turn Free (kind 0) and *ncells may shrink.  Host only. */
+void pip_cells_simplify_dp(PipCell_dp *cells, int *ncells);
 
 /* Dense batch through the pip_solve_dp path: dom is [n][dom_rows][dom_cols] (PolyLib rows),
  * ctx is [n][ctx_rows][ctx_cols] or NULL (has_ctx=0).  Host buffers in, host buffers out:

@@ -18,7 +18,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC,-fwrapv", "-Xptxas", "-v"]
 SOURCES_CU = ["pip_kernels.cu", "pip_large.cu"]
 SOURCES_CPP = ["pip_engine.cpp", "pip_host.cpp"]
-HEADERS = ["pip_types.h", "simt.h", "pip_arith.h", "pip_solver.h", "pip_warp_main.h", "pip_kernels.h",
+SOURCES_CLI = ["pip_cli.cpp"]
+HEADERS = ["pip_types.h", "simt.h", "pip_arith.h", "pip_decode.h", "pip_solver.h", "pip_warp_main.h", "pip_kernels.h",
            "pip_engine.h", "pip_large.h", os.path.join("..", "..", "include", "piplib_b200.h"),
            os.path.join("..", "..", "include", "piplib", "piplib.h")]
 
@@ -28,7 +29,7 @@ def _stale(lib=None):
     if not os.path.exists(lib):
         return True
     t = os.path.getmtime(lib)
-    for f in SOURCES_CU + SOURCES_CPP + HEADERS:
+    for f in SOURCES_CU + SOURCES_CPP + SOURCES_CLI + HEADERS:
         if os.path.getmtime(os.path.join(CSRC, f)) > t:
             return True
     return os.path.getmtime(os.path.abspath(__file__)) > t
@@ -72,7 +73,22 @@ def build(force=False, verbose=False, profile=False, variant=None, defines=()):
     subprocess.check_call(cmd)
     for o in objs:
         os.remove(o)
+    if not profile and not variant:
+        build_cli()
     return lib
+
+
+BINDIR = os.path.join(HERE, "bin")
+CLI = os.path.join(BINDIR, "pip64")
+
+
+def build_cli():
+    """pip64: the reference's command-line tool (source/maind.c) over the batch library"""
+    os.makedirs(BINDIR, exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-Wall", "-I", os.path.join(HERE, "..", "include"),
+                           os.path.join(CSRC, "pip_cli.cpp"), "-o", CLI, "-L", LIBDIR, "-lpiplib_dp",
+                           "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath," + os.path.join(CUDA, "lib64")])
+    return CLI
 
 
 if __name__ == "__main__":

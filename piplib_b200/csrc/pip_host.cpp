@@ -713,7 +713,8 @@ int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long 
       if (cw) memcpy(pool.data() + off[i] + tw, ctx[i], cw * sizeof(I));
       PipProblem &P = prob[i];
       P.nvar = h.nvar; P.nparm = h.nparm; P.ni = h.ni; P.nc = h.nc; P.bigparm = h.bigparm;
-      P.flags = h.nq ? PIP_F_INT : 0; P.off = (I)off[i];
+      P.flags = ((h.nq & 1) ? PIP_F_INT : (h.nq & 2) ? PIP_F_DUAL : 0) | ((h.nq & 4) ? PIP_F_DEEPEST : 0);
+      P.off = (I)off[i];
     }
     PipBatchIn in;
     in.n = n; in.h_prob = prob.data(); in.h_pool = pool.data(); in.pool_words = off[n];
@@ -743,6 +744,15 @@ int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long 
     return -1;
   }
   return 0;
+}
+
+/* sol_simplify_xx (source/sol.c:272-288) on a problem's cells as returned by pip_traiter_batch_dp:
+ * the `-z` option of the CLI.  Cells may become Free (kind 0); *ncells may shrink. */
+void pip_cells_simplify_dp(PipCell_dp *cells, int *ncells)
+{
+  if (!cells || !ncells || *ncells <= 0) return;
+  static_assert(sizeof(PipCell_dp) == sizeof(PipCell), "cell layouts must agree");
+  simplify_cells((PipCell *)cells, *ncells, 0);
 }
 
 }  // extern "C"
