@@ -54,8 +54,8 @@ struct Problem {
   std::string comment;              /* echo of balance_xx */
   int nvar = 0, nparm = 0, ni = 0, nc = 0, bigparm = -1, nq = 0;
   std::vector<long long> tab, ctx;
-  bool syntax_error = false;        /* escape_xx was taken: print "\nSyntax error\n)\n" */
-  int escape_level = 1;
+  bool syntax_error = false;        /* escape_xx was taken ... */
+  bool escape_closed = false;       /* ... and found its closing parenthesis: "\nSyntax error\n)\n" is printed */
 };
 
 /* balance_xx, source/maind.c:49-61 */
@@ -220,10 +220,10 @@ int main(int argc, char **argv)
     long long h[6];
     bool ok = true;
     for (int k = 0; k < 6 && ok; k++) if (lx.scan(&h[k]) < 0) ok = false;
-    if (!ok) { P.syntax_error = true; escape(lx, 1); probs.push_back(P); continue; }
+    if (!ok) { P.syntax_error = true; P.escape_closed = escape(lx, 1); probs.push_back(P); continue; }
     P.nvar = (int)h[0]; P.nparm = (int)h[1]; P.ni = (int)h[2]; P.nc = (int)h[3]; P.bigparm = (int)h[4]; P.nq = (int)h[5];
-    if (!tab_get(lx, P.ni, P.nvar + P.nparm + 1, P.tab)) { P.syntax_error = true; escape(lx, 2); probs.push_back(P); continue; }
-    if (!tab_get(lx, P.nc, P.nparm + 1, P.ctx)) { P.syntax_error = true; escape(lx, 2); probs.push_back(P); continue; }
+    if (!tab_get(lx, P.ni, P.nvar + P.nparm + 1, P.tab)) { P.syntax_error = true; P.escape_closed = escape(lx, 2); probs.push_back(P); continue; }
+    if (!tab_get(lx, P.nc, P.nparm + 1, P.ctx)) { P.syntax_error = true; P.escape_closed = escape(lx, 2); probs.push_back(P); continue; }
     probs.push_back(P);
   }
 
@@ -274,7 +274,7 @@ int main(int argc, char **argv)
   for (size_t i = 0; i < probs.size(); i++) {
     const Problem &P = probs[i];
     fprintf(out, "(%s", P.comment.c_str());
-    if (P.syntax_error) { fprintf(out, "\nSyntax error\n)\n"); continue; }
+    if (P.syntax_error) { if (P.escape_closed) fprintf(out, "\nSyntax error\n)\n"); continue; }
     const int st = status[q];
     if (st == 1) fprintf(out, "void\n");                              /* empty context */
     else if (st != 0) {
