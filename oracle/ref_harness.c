@@ -286,11 +286,11 @@ double pipref_bench_dense(long first, long count,
   o->Nq = opts[0]; o->Verbose = -1; o->Simplify = opts[2]; o->Deepest_cut = opts[3];
   o->Maximize = opts[4]; o->Urs_parms = opts[5]; o->Urs_unknowns = opts[6]; o->Compute_dual = opts[7];
   quiet_begin();
-  guard_on();
   for (i = first; i < first + count; i++) {
     PipQuast_dp *q = NULL; int rc;
     size_t dsz = (size_t)dom_rows * dom_cols, csz = (size_t)ctx_rows * ctx_cols;
     pipref_armed = 1;
+    guard_on();                          /* the time limit (if any) is per problem */
     rc = setjmp(pipref_env);
     if (rc) {
       pipref_armed = 0; after_fatal();
@@ -303,6 +303,7 @@ double pipref_bench_dense(long first, long count,
     if (C && csz) memcpy(C->p_Init, ctx + (size_t)i * csz, sizeof(long long) * csz);
     q = pip_solve_dp(D, C, bg, o);
     clock_gettime(CLOCK_MONOTONIC, &t1);
+    guard_off();
     pipref_armed = 0;
     total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     if (status) status[i - first] = 0;

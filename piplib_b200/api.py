@@ -337,7 +337,7 @@ class LargeProblem:
         return st.value, [[int(x["kind"]), int(x["p1"]), int(x["p2"])] for x in c], \
             dict(pivots=int(info[0]), cuts=int(info[1]), skipped_rows=int(info[2]), ni=int(info[3]),
                  cycles_choice=int(info[4]), cycles_update=int(info[5]),
-                 sub=dict(zip(['swap', 'rowpick', 'column', 'det', 'active'], [int(info[6 + i]) for i in range(5)])))
+                 sub=dict(zip(['swap', 'rowpick', 'column', 'det', 'active', 'spare'], [int(info[6 + i]) for i in range(6)])))
 
     def close(self):
         if self.h:

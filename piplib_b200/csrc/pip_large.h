@@ -24,6 +24,7 @@
 
 #define PIPL_INF 0x7fffffff
 #define PIPL_K 8            /* candidates per thread kept in registers by the column walk */
+#define PIPL_AL 8           /* positions per thread per round of the active-row list */
 /* sub-phase timers of CTA 0 (thread 0): prof[2..7] = swap, row pick, column choice, determinant,
  * active-row list, spare */
 #define PIPL_T(i) do { if (tid == 0) { const long long n_ = pip_clock(); L.prof[i] += (unsigned long long)(n_ - tlap); tlap = n_; } } while (0)
@@ -92,31 +93,46 @@ PIP_DEV int pipl_ratio_cmp(pip_i64 a, pip_i64 b, pip_i64 c, pip_i64 d)
   return 0;
 }
 
-/* rebuild the compact candidate list from member[] (ordered by column), returns its length */
+/* the next PIPL_WIN stored (non-Unit) positions at or after k, in order (PIPL_INF-padded); every
+ * thread computes the same list from the bitmap */
+#define PIPL_WIN 8
+PIP_DEV void pipl_window(const PipLarge &L, int k, int nl, int nwords, int *wp)
+{
+  int w = k >> 5;
+  unsigned bits = w < nwords ? (L.sbits[w] & (~0u << (k & 31))) : 0u;
+  #pragma unroll
+  for (int b = 0; b < PIPL_WIN; b++) {
+    while (!bits && w + 1 < nwords) { w++; bits = L.sbits[w]; }
+    if (bits) {
+      const int pp = (w << 5) + pip_ffs(bits) - 1;
+      bits &= bits - 1;
+      wp[b] = pp < nl ? pp : PIPL_INF;
+    } else wp[b] = PIPL_INF;
+  }
+}
+
+/* rebuild the compact candidate list from member[] (ordered by column), returns its length: every
+ * thread owns a contiguous run of columns, one exclusive scan across the CTA */
 PIP_DEV int pipl_compact(const PipLarge &L, int *red, int *sh_base)
 {
   const int tid = G::tid(), T = G::T();
-  int total = 0;
-  for (int base = 0; base < L.nvar; base += T) {
-    const int j = base + tid;
-    const int m = (j < L.nvar && L.member[j]) ? 1 : 0;
-    /* exclusive prefix within the CTA */
-    int x = m;
-    const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
-    for (int o = 1; o < 32; o <<= 1) { int y = W::shfl_up(x, o); if (lane >= o) x += y; }
-    G::cta_sync();
-    if (lane == 31) red[wid] = x;
-    G::cta_sync();
-    int before = 0;
-    for (int i = 0; i < wid; i++) before += red[i];
-    int all = 0;
-    for (int i = 0; i < nw; i++) all += red[i];
-    if (m) L.cand[total + before + x - 1] = j;
-    total += all;
-  }
+  const int per = (L.nvar + T - 1) / T;
+  const int j0 = tid * per, j1 = j0 + per < L.nvar ? j0 + per : L.nvar;
+  int m = 0;
+  for (int j = j0; j < j1; j++) m += L.member[j] ? 1 : 0;
+  int x = m;
+  const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+  for (int o = 1; o < 32; o <<= 1) { int y = W::shfl_up(x, o); if (lane >= o) x += y; }
+  G::cta_sync();
+  if (lane == 31) red[wid] = x;
+  G::cta_sync();
+  int before = 0, all = 0;
+  for (int i = 0; i < nw; i++) { if (i < wid) before += red[i]; all += red[i]; }
+  int at = before + x - m;
+  for (int j = j0; j < j1; j++) if (L.member[j]) L.cand[at++] = j;
   G::cta_sync();
   (void)sh_base;
-  return total;
+  return all;
 }
 
 /* ---- phase AB: CTA 0 ------------------------------------------------------------------------ */
@@ -173,12 +189,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     const pip_i64 pivot = L.ctl64[0], dpiv = L.ctl64[1];
     const int pslot = PIP_LINK(L.fl[pivi]);
     pip_i64 *prow = pipl_row(L, pslot);
-    int ku = PIPL_INF;
-    for (int k = tid; k < nl; k += T) {
-      const int f = L.fl[k];
-      if ((f & PIP_UNIT) && PIP_LINK(f) == pivj) ku = k;
-    }
-    ku = pipl_cta_min(ku, red);
+    const int ku = L.colpos[pivj];          /* the Unit position that owns the pivot column */
     for (int j = tid; j < ncol; j += T) prow[j] = (j == pivj) ? dpiv : -prow[j];
     G::cta_sync();
     if (tid == 0) {
@@ -302,13 +313,25 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
         const bool was = alive;
         int n = ncand;
         while (n > 1) {
-          int c = PIPL_INF;
-          for (int w = (k >> 5) + lane; w < nwords; w += 32) {
-            unsigned bits = L.sbits[w];
-            if (w == (k >> 5)) bits &= ~0u << (k & 31);
-            if (bits) { const int pp = (w << 5) + pip_ffs(bits) - 1; if (pp < nl) c = pp; break; }
+          /* skip the rows that are zero in every column still in play, PIPL_WIN rows per step */
+          int pst = PIPL_INF;
+          for (;;) {
+            int wp[PIPL_WIN];
+            pipl_window(L, k, nl, nwords, wp);
+            if (wp[0] == PIPL_INF) break;
+            pip_i64 v[PIPL_WIN];
+            #pragma unroll
+            for (int b = 0; b < PIPL_WIN; b++)
+              v[b] = (alive && wp[b] < u) ? pipl_row(L, PIP_LINK(L.fl[wp[b]]))[j] : 0;
+            int first = PIPL_WIN;
+            #pragma unroll
+            for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0) first = b;
+            first = (int)W::redmin((unsigned)first);
+            if (first < PIPL_WIN) { pst = wp[first]; break; }
+            if (wp[PIPL_WIN - 1] == PIPL_INF) break;
+            if (pip_popc(W::ballot(alive && u > wp[PIPL_WIN - 1])) <= 1) break;     /* decided by the Unit positions */
+            k = wp[PIPL_WIN - 1] + 1;
           }
-          const int pst = (int)W::redmin((unsigned)c);
           const unsigned mel = W::ballot(alive && u < pst);
           const int nel = pip_popc(mel);
           if (nel >= n) {
@@ -330,6 +353,10 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
             if (ov && (!valid || pipl_ratio_cmp(oa, op, ba, bp) < 0)) { ba = oa; bp = op; valid = 1; }
           }
           if (alive && pipl_ratio_cmp(a, pj, ba, bp) != 0) alive = false;
+#ifdef PIPL_WALK_STATS
+          { const int n2 = pip_popc(W::ballot(alive));
+            if (lane == 0) L.prof[7] += 1ull + ((ba == 0) ? (1ull << 20) : 0ull) + ((ba == 0 && n2 == n) ? (1ull << 40) : 0ull); }
+#endif
           n = pip_popc(W::ballot(alive));
           k = pst + 1;
         }
@@ -355,13 +382,43 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
       const bool fits = ncand0 <= PIPL_K * T;
       pip_i64 *red64 = (pip_i64 *)red;
       while (fits && ncand > 32) {
-        int c = PIPL_INF;
-        for (int w = (k >> 5) + tid; w < nwords; w += T) {
-          unsigned bits = L.sbits[w];
-          if (w == (k >> 5)) bits &= ~0u << (k & 31);
-          if (bits) { const int pp = (w << 5) + pip_ffs(bits) - 1; if (pp < nl) c = pp; break; }
+        /* Skip ahead to the first stored row that can discriminate: a row whose entries are zero in
+         * every column still in play (97 % of the rows met on consecutive-ones tableaus) leaves the
+         * candidate set alone, so the walk examines PIPL_WIN rows per step -- all gathers of a window
+         * in flight together, one reduction -- and only stops at a row with a non-zero entry.
+         * Candidates whose Unit position lies before a row are out of play at that row; they are
+         * struck (lazily) by the cu < pst test below. */
+        int pst = PIPL_INF;
+        for (;;) {
+          int wp[PIPL_WIN];
+          pipl_window(L, k, nl, nwords, wp);
+          if (wp[0] == PIPL_INF) break;
+          const pip_i64 *wr[PIPL_WIN];
+          #pragma unroll
+          for (int b = 0; b < PIPL_WIN; b++) wr[b] = wp[b] != PIPL_INF ? pipl_row(L, PIP_LINK(L.fl[wp[b]])) : prow;
+          int first = PIPL_WIN;
+          #pragma unroll
+          for (int i = 0; i < PIPL_K; i++) {
+            if (!((alive >> i) & 1u)) continue;
+            pip_i64 v[PIPL_WIN];
+            #pragma unroll
+            for (int b = 0; b < PIPL_WIN; b++) v[b] = wp[b] < cu[i] ? wr[b][cj[i]] : 0;      /* PIPL_INF < cu never holds */
+            #pragma unroll
+            for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0 && b < first) first = b;
+          }
+          first = pipl_cta_min(first, red);
+          if (first < PIPL_WIN) { pst = wp[first]; break; }
+          if (wp[PIPL_WIN - 1] == PIPL_INF) break;               /* no stored row left */
+          /* the Unit positions passed so far may already have decided the walk: with at most one
+           * candidate still in play beyond this window the survivor is the one with the last Unit
+           * position, which the pst = PIPL_INF case below picks */
+          int inplay = 0;
+          #pragma unroll
+          for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] > wp[PIPL_WIN - 1]) inplay++;
+          inplay = pipl_cta_sum(inplay, red);
+          if (inplay <= 1) break;
+          k = wp[PIPL_WIN - 1] + 1;
         }
-        const int pst = pipl_cta_min(c, red);
         int nel = 0, umax = -1;
         #pragma unroll
         for (int i = 0; i < PIPL_K; i++)
@@ -411,6 +468,9 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
         removed = pipl_cta_sum(removed, red);
         ncand -= removed;
         k = pst + 1;
+#ifdef PIPL_WALK_STATS
+        if (tid == 0) L.prof[7] += 1ull + ((ba == 0) ? (1ull << 20) : 0ull) + ((ba == 0 && removed == 0) ? (1ull << 40) : 0ull);
+#endif
       }
       /* publish the survivors */
       #pragma unroll
@@ -543,30 +603,38 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
   /* rows whose update is not the identity (foo != 0 or a denominator to normalise,
    * source/traiter.c:470-501): only those are visited by the update phase */
   {
-    /* four positions per thread per round, loads issued together (the walk is latency-bound) */
+    /* PIPL_AL positions per thread per round, loads issued together (the walk is latency-bound) */
     int nskip = 0;
-    for (int base = 0; base < nl; base += 4 * T) {
-      int pp[4], ff[4];
-      pip_i64 foo[4], dd[4];
+    for (int base = 0; base < nl; base += PIPL_AL * T) {
+      int pp[PIPL_AL], ff[PIPL_AL];
+      pip_i64 foo[PIPL_AL], dd[PIPL_AL];
       #pragma unroll
-      for (int i = 0; i < 4; i++) { pp[i] = base + i * T + tid; ff[i] = pp[i] < nl ? L.fl[pp[i]] : PIP_UNIT; }
+      for (int i = 0; i < PIPL_AL; i++) { pp[i] = base + i * T + tid; ff[i] = pp[i] < nl ? L.fl[pp[i]] : PIP_UNIT; }
       #pragma unroll
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < PIPL_AL; i++) {
         const bool st = pp[i] < nl && pp[i] != pivi && !(ff[i] & PIP_UNIT);
         foo[i] = st ? pipl_row(L, PIP_LINK(ff[i]))[pivj] : 0;
         dd[i] = st ? L.den[pp[i]] : 1;
         if (!st) ff[i] = PIP_UNIT;
       }
+      /* one queue reservation per warp per round (the order of the work queue is free) */
+      unsigned am[PIPL_AL];
+      int total = 0;
       #pragma unroll
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < PIPL_AL; i++) {
         const bool st = !(ff[i] & PIP_UNIT);
         const bool act = st && (foo[i] != 0 || dd[i] != 1);
         if (st && !act) nskip++;
-        const unsigned m = W::ballot(act);
-        int at = 0;
-        if (W::lane() == 0 && m) at = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], (unsigned)pip_popc(m));
-        at = W::shfl(at, 0);
-        if (act) L.active[at + pip_popc(m & ((1u << W::lane()) - 1u))] = pp[i];
+        am[i] = W::ballot(act);
+        total += pip_popc(am[i]);
+      }
+      int at = 0;
+      if (W::lane() == 0 && total) at = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], (unsigned)total);
+      at = W::shfl(at, 0);
+      #pragma unroll
+      for (int i = 0; i < PIPL_AL; i++) {
+        if ((am[i] >> W::lane()) & 1u) L.active[at + pip_popc(am[i] & ((1u << W::lane()) - 1u))] = pp[i];
+        at += pip_popc(am[i]);
       }
     }
     nskip = pipl_cta_sum(nskip, red);

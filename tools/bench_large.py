@@ -39,7 +39,7 @@ line = {"workload": "consecutive-ones %d x %d int64, Nq=1" % (n, n + 1), "status
         "us_per_pivot": 1e3 * best / max(piv, 1),
         "phase_share": {"choice": info["cycles_choice"] / max(1, info["cycles_choice"] + info["cycles_update"]),
                         "update": info["cycles_update"] / max(1, info["cycles_choice"] + info["cycles_update"]),
-                        "choice_sub_us_per_pivot": {k: v / 1965.0 / max(1, piv) for k, v in info["sub"].items()}}, "pivots_per_sec": piv / (best / 1e3),
+                        "choice_sub_us_per_pivot": {k: v / 1965.0 / max(1, piv) for k, v in info["sub"].items() if k != "spare"}}, "pivots_per_sec": piv / (best / 1e3),
         "roofline": {"bound": "hbm", "achieved": alg / (best / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (best / 1e3) / 1e9 / peak, "peak_source": src,
                      "note": "dense 16*R*C figure; rows whose update is the identity are skipped"}}
@@ -52,4 +52,7 @@ if check:
     dt = time.perf_counter() - t
     line["cpu_baseline"] = {"seconds": dt, "pivots_per_sec": stats.pivots / dt, "cores": 1, "kind": "port"}
     line["parity"] = bool(st_o == st and [tuple(x) for x in cells] == cells_o and stats.pivots == piv)
+w = info["sub"].get("spare", 0)
+if w:
+    line["walk_stats"] = {"rows_walked": w & 0xfffff, "min_ratio_zero": (w >> 20) & 0xfffff, "no_strike": (w >> 40) & 0xfffff}
 print(json.dumps(line))
