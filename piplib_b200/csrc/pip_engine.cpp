@@ -330,7 +330,13 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         const PipResult &r = h_res[i];
         if (r.status == PIP_ST_PENDING) { pending++; continue; }
         if (r.status == PIP_ST_WIDEN) { cls[i] = -1; h_res[i].status = PIP_ST_PENDING; continue; }
-        if (r.status == PIP_ST_CAPACITY && k + 1 < N_G) { cls[i] = k < 0 ? 0 : k + 1; h_res[i].status = PIP_ST_PENDING; continue; }
+        if (r.status == PIP_ST_CAPACITY && k + 1 < N_G) {
+          /* the wide int32 class already has half of G3's cut rows and all of its context rows: what
+           * outgrew it goes straight to the first team class (4x the rows) instead of failing G3 too */
+          cls[i] = k < 0 ? ((k == -2 && s32_wide) ? 1 : 0) : k + 1;
+          h_res[i].status = PIP_ST_PENDING;
+          continue;
+        }
         cls[i] = 1000;                       /* final */
         out.res[i] = r;
         out.base[i] = (const pip_u64 *)chunk.p;

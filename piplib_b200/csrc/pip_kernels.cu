@@ -10,7 +10,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include "pip_decode.h"
+#include "pip_decode_warp.h"
 #include "pip_kernels.h"
 #include "pip_warp_main.h"
 
@@ -153,10 +156,62 @@ __global__ void pip_serialize_kernel(PipResult *res, const int *order, const Pip
   }
 }
 
+/* pass 1 with one warp per problem (pip_decode_warp.h): cells staged in shared memory by a coalesced
+ * copy, warp-uniform parse, lane-parallel vectors, words out through a hashed shared-memory tile */
+#define PIP_WS_WARPS 8
+#define PIP_WS_WORDS_PER_WARP (PIP_WS_TILE + 3 * PIP_WS_CELLS)
+__global__ void __launch_bounds__(32 * PIP_WS_WARPS)
+pip_serialize_warp_kernel(PipResult *res, const int *order, const PipCell *cells, const PipDecodeParm *parm,
+                          const long long *dst_off, pip_i64 *out, pip_u64 *hashes, int nprob)
+{
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pip_i64 *tile = (pip_i64 *)pip_smem + (size_t)wid * PIP_WS_WORDS_PER_WARP;
+  pip_i64 *stage = tile + PIP_WS_TILE;
+  for (int q = blockIdx.x * PIP_WS_WARPS + wid; q < nprob; q += gridDim.x * PIP_WS_WARPS) {
+    const int p = order ? order[q] : q;
+    const PipResult r = res[p];
+    const bool narrow = (r.rflags & PIP_RES_SER32) != 0;
+    PipWarpSer s;
+    s.tile = tile; s.out = out + dst_off[q]; s.cap = (long long)r.ser_words; s.len = 0; s.fill = 0;
+    s.h = PIP_HASH_INIT; s.narrow_out = narrow ? 1 : 0; s.wide = 0;
+    if (r.status == PIP_ST_VOID) pip_wput(s, -1);
+    else if (r.status == PIP_ST_OK) {
+      const PipCell *src = cells + r.cell_off;
+      if (r.ncells <= PIP_WS_CELLS) {
+        const pip_i64 *g = (const pip_i64 *)src;
+        for (int k = lane; k < 3 * (int)r.ncells; k += 32) stage[k] = g[k];
+        __syncwarp();
+        src = (const PipCell *)stage;
+      }
+      PipRawCells c = {src};
+      const PipDecodeParm d = parm[p];
+      pip_wser_cells(s, c, r.ncells, d.bg, d.urs, d.flags);
+    }
+    pip_wser_flush(s);
+    if (lane == 0) {
+      res[p].cell_off = dst_off[q];
+      if (hashes) hashes[p] = (r.status == PIP_ST_OK || r.status == PIP_ST_VOID) ? s.h : 0ull;
+      if ((r.rflags & PIP_RES_SIZED) && (s.len != (long long)r.ser_words || (narrow && s.wide)))
+        res[p].status = PIP_ST_FAULT + 1;
+    }
+    __syncwarp();
+  }
+}
+
 extern "C" cudaError_t pip_launch_serialize(PipResult *res, const int *order, const PipCell *cells,
                                             const PipDecodeParm *parm, const long long *dst_off, pip_i64 *out,
                                             pip_u64 *hashes, int nprob, int pass, cudaStream_t stream)
 {
+  static const bool thread_decode = getenv("PIPLIB_B200_THREAD_DECODE") != nullptr;   /* A/B aid */
+  if (pass == 1 && !thread_decode) {
+    const size_t smem = sizeof(pip_i64) * PIP_WS_WARPS * PIP_WS_WORDS_PER_WARP;
+    cudaError_t e = cudaFuncSetAttribute(pip_serialize_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int blocks = (nprob + PIP_WS_WARPS - 1) / PIP_WS_WARPS;
+    if (blocks > 148 * 3) blocks = 148 * 3;
+    pip_serialize_warp_kernel<<<blocks, 32 * PIP_WS_WARPS, smem, stream>>>(res, order, cells, parm, dst_off, out, hashes, nprob);
+    return cudaGetLastError();
+  }
   const int threads = 128;
   pip_serialize_kernel<<<(nprob + threads - 1) / threads, threads, 0, stream>>>(res, order, cells, parm, dst_off, out,
                                                                                hashes, nprob, pass);

@@ -116,10 +116,13 @@ def _chunked(gen, n, first):
     return np.ascontiguousarray(np.concatenate(doms)), np.ascontiguousarray(np.concatenate(ctxs))
 
 
-def perturbed(n, seed=2026, first=0, template="sor1d", amp=2):
+def perturbed(n, seed=2026, first=0, template="sor1d", amp=2, salt=0, unperturbed=()):
     """BASELINE config 5 (and 3, family B): a shipped problem shape with every constraint constant
     moved by a uniform draw from [-amp, amp] (no fatal verdicts in 20 000 draws per
-    template, 4-100 pivots per problem)."""
+    template, 4-100 pivots per problem).  `unperturbed` lists draws replaced by the template itself:
+    the ones on which the reference does not terminate (a context sub-solve whose Gomory cuts never
+    converge: it grows until the machine is out of memory), found by tools/certify_workload.py and
+    recorded in tests/golden/workload_<name>_*.json."""
     from .templates import TEMPLATES
     t = TEMPLATES[template]
     dom0 = np.asarray(t["dom"], dtype=np.int64)
@@ -127,9 +130,12 @@ def perturbed(n, seed=2026, first=0, template="sor1d", amp=2):
     key = sum(ord(ch) << (8 * i) for i, ch in enumerate(template[:6]))
 
     def gen(c):
-        rng = _rng(seed ^ key, c)
+        rng = _rng(seed ^ key ^ (salt << 48), c)
         dom = np.repeat(dom0[None], CHUNK, axis=0)
         dom[:, :, -1] += rng.integers(-amp, amp + 1, size=(CHUNK, dom0.shape[0]))
+        for g in unperturbed:
+            if c * CHUNK <= g < (c + 1) * CHUNK:
+                dom[g - c * CHUNK] = dom0
         ctx = np.repeat(ctx0[None], CHUNK, axis=0)
         return dom, ctx
     return _chunked(gen, n, first)
@@ -158,7 +164,7 @@ WORKLOADS = {
     "loopnest8x12p2": dict(fn=loopnest, kw=dict(nvar=8, nrows=12, nparm=2)),
     # config 5: dependence-analysis shapes
     "sor1d": dict(fn=perturbed, kw=dict(template="sor1d")),
-    "boulet": dict(fn=perturbed, kw=dict(template="boulet")),
+    "boulet": dict(fn=perturbed, kw=dict(template="boulet", unperturbed=(15234,))),
     "cg1": dict(fn=perturbed, kw=dict(template="cg1")),
     "fimmel": dict(fn=perturbed, kw=dict(template="fimmel")),
     "esced": dict(fn=perturbed, kw=dict(template="esced")),

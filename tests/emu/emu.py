@@ -51,3 +51,21 @@ def solve_large(case, cut_rows=64, sol_size=0, maxcol=0, order_mode=0):
                            info, order_mode)
     c = cells[:nc.value]
     return st.value, [[int(x["kind"]), int(x["p1"]), int(x["p2"])] for x in c], list(info)
+
+
+def decode(which, cells, bg, urs, flags, cap=1 << 16, narrow=0, order_mode=0, pad=64):
+    """cells -> serialised quast words by the thread decoder (which=0, pip_decode.h) or by the
+    warp-per-problem decoder (which=1, pip_decode_warp.h, 32 emulated lanes)"""
+    lib = C.CDLL(SO)
+    n = len(cells)
+    arr = np.zeros(n + pad, dtype=CELL_DTYPE)
+    for i, (k, a, b) in enumerate(cells):
+        arr[i] = (k, 0, a, b)
+    out = np.zeros(cap, dtype=np.int64)
+    ln, h, w = C.c_longlong(0), C.c_ulonglong(0), C.c_uint(0)
+    ok = lib.pipemu_decode(which, arr.ctypes.data_as(C.c_void_p), n, bg, urs, flags,
+                           out.ctypes.data_as(C.c_void_p), C.c_longlong(cap), narrow, C.byref(ln), C.byref(h),
+                           C.byref(w), order_mode)
+    m = min(ln.value, cap)
+    words = out[:m].copy() if not narrow else out.view(np.int32)[:m].astype(np.int64)
+    return ok, ln.value, h.value, w.value, words

@@ -93,3 +93,48 @@ extern "C" int pipemu_solve_large(int nvar, int ni, int nq, const pip_i64 *tab, 
   free(L.data); free(L.den); free(L.fl); free(L.csign); free(L.cand); free(L.member); free(L.cut); free(L.colpos); free(L.sbits); free(L.active);
   return 0;
 }
+
+// ---- warp-per-problem decoder in emulation, next to the thread decoder it must agree with ----
+#include "../../piplib_b200/csrc/pip_decode_warp.h"
+
+struct EmuDecode {
+  const PipCell *cells; int n, bg, urs, flags;
+  pip_i64 *tile; pip_i64 *out; long long cap; int narrow;
+  long long len; pip_u64 h; unsigned wide; int ok;
+};
+static void decode_entry(void *a, int)
+{
+  EmuDecode *e = (EmuDecode *)a;
+  PipWarpSer s;
+  s.tile = e->tile; s.out = e->out; s.cap = e->cap; s.len = 0; s.fill = 0; s.h = PIP_HASH_INIT;
+  s.narrow_out = e->narrow; s.wide = 0;
+  PipRawCells c = {e->cells};
+  const bool ok = pip_wser_cells(s, c, e->n, e->bg, e->urs, e->flags);
+  pip_wser_flush(s);
+  if (W::lane() == 0) { e->len = s.len; e->h = s.h; e->wide = s.wide; e->ok = ok ? 1 : 0; }
+}
+
+// which = 0: pip_ser_cells (one thread, the host/device reference decoder), 1: the warp decoder
+extern "C" int pipemu_decode(int which, const PipCell *cells, int n, int bg, int urs, int flags, long long *out,
+                             long long cap, int narrow, long long *len, unsigned long long *hash, unsigned *wide,
+                             int order_mode)
+{
+  if (which == 0) {
+    PipSer s;
+    s.out = out; s.cap = cap; s.len = 0; s.h = PIP_HASH_INIT; s.hashing = 1; s.narrow_out = narrow; s.wide = 0;
+    PipRawCells c = {cells};
+    const bool ok = pip_ser_cells(s, c, n, bg, urs, flags);
+    *len = s.len; *hash = s.h; *wide = s.wide;
+    return ok ? 1 : 0;
+  }
+  EmuDecode e;
+  memset(&e, 0, sizeof e);
+  e.cells = cells; e.n = n; e.bg = bg; e.urs = urs; e.flags = flags; e.out = out; e.cap = cap; e.narrow = narrow;
+  e.tile = (pip_i64 *)malloc(sizeof(pip_i64) * PIP_WS_TILE);
+  memset(e.tile, 0x5a, sizeof(pip_i64) * PIP_WS_TILE);
+  pipemu::set_order(order_mode);
+  pipemu::run_warp(decode_entry, &e);
+  free(e.tile);
+  *len = e.len; *hash = e.h; *wide = e.wide;
+  return e.ok;
+}

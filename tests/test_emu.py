@@ -117,3 +117,36 @@ def test_deepest_cut_and_dual_in_emulation(port):
             if st != st_o or [tuple(x) for x in cells] != cells_o:
                 bad.append((c["name"], st, st_o))
         assert not bad, bad
+
+
+def test_warp_decoder_agrees_with_thread_decoder():
+    """pip_decode_warp.h (one warp per problem, lane-parallel vectors, tiled output) against
+    pip_decode.h on every golden cell stream, under every combination of the decode parameters
+    (big-parameter column, Urs_parms, SHIFT / NEGATE / REMOVE) and both output widths."""
+    import random
+    rng = random.Random(7)
+    streams = [c["ref_cells"] for c in CLI + RCLI if c["ref_status"] == 0 and c["ref_cells"]]
+    streams += [[[3, 0, 0]], [[1, 0, 0]], []]
+    # a vector longer than the tile (scalar path) and one that exactly fills it
+    for m in (200, 127):
+        streams.append([[3, 1, 0], [4, m, 0]] + [[7, 6 * j - 5, 1 + (j % 4)] for j in range(m)])
+    checked = 0
+    for cells in streams:
+        # parameter combinations the library can produce: REMOVE / SHIFT need a big-parameter column
+        # inside every vector, the Urs_parms copies sit right after it (source/piplib.c:850-867)
+        shortest = min([c[1] for c in cells if c[0] == 4] + [64])
+        for trial in range(6):
+            urs = rng.choice([0, 0, 1, 2])
+            bg = rng.choice([-1, 0, 1, shortest - 2 - 2 * urs])
+            flags = rng.choice([0, 1, 2, 3, 5, 7, 4])
+            if bg < 0 or bg + 1 + 2 * urs > shortest - 1:
+                bg, urs, flags = -1, 0, flags & 2
+            if trial == 0:
+                bg, urs, flags = -1, 0, 0
+            narrow = trial & 1
+            a = emu.decode(0, cells, bg, urs, flags, narrow=narrow)
+            b = emu.decode(1, cells, bg, urs, flags, narrow=narrow, order_mode=trial % 3)
+            assert a[:4] == b[:4], (cells[:12], bg, urs, flags)
+            assert (a[4] == b[4]).all(), (cells[:12], bg, urs, flags)
+            checked += 1
+    assert checked > 300

@@ -28,14 +28,14 @@ def work(args):
     dom, ctx = synth.generate(name, n, first=first)
     ser = np.zeros(1 << 20, dtype=np.int64)
     nn = C.c_long(0)
-    opts = po.opts_array()
+    opts = po.opts_array(**synth.options(name))
     hist, worst, slow = {}, 0.0, []
     dr, dc = dom.shape[1], dom.shape[2]
     cr, cc = ctx.shape[1], ctx.shape[2]
     for i in range(n):
         t = time.perf_counter()
         st = L.pipref_solve_ser(dr, dc, dom[i].ctypes.data_as(C.c_void_p), 1, cr, cc,
-                                ctx[i].ctypes.data_as(C.c_void_p), -1, opts,
+                                ctx[i].ctypes.data_as(C.c_void_p), synth.bignum(name), opts,
                                 ser.ctypes.data_as(C.c_void_p), C.c_long(1 << 20), C.byref(nn), None, C.c_long(0))
         dt = time.perf_counter() - t
         hist[st] = hist.get(st, 0) + 1
