@@ -19,7 +19,7 @@ __device__ void G::grid_sync() { cg::this_grid().sync(); }
 
 __global__ void __launch_bounds__(PIPL_THREADS) pip_large_kernel(const PipLarge L)
 {
-  __shared__ __align__(16) int red[128];
+  __shared__ __align__(16) int red[128 + 6 * PIPL_LCAP];
   pipl_solve(L, red);
 }
 

@@ -23,7 +23,15 @@
 #include "simt.h"
 
 #define PIPL_INF 0x7fffffff
+#if defined(PIPL_WALK_STATS) && defined(__CUDACC__)
+__device__ unsigned long long pipl_dbg[8];   /* diagnostic build only: walks, candidates, window steps / stops (CTA, warp) */
+#define PIPL_DBG(i, v) do { if (G::tid() == 0) pipl_dbg[i] += (unsigned long long)(v); } while (0)
+#else
+#define PIPL_DBG(i, v) do { } while (0)
+#endif
 #define PIPL_K 8            /* candidates per thread kept in registers by the column walk */
+#define PIPL_KEEP 5          /* rows a CTA updates itself before it shares through the overflow queue */
+#define PIPL_LCAP 128        /* local list capacity of the update phase; red[] holds 128 + 6 * PIPL_LCAP ints */
 #define PIPL_AL 8           /* positions per thread per round of the active-row list */
 /* sub-phase timers of CTA 0 (thread 0): prof[2..7] = swap, row pick, column choice, determinant,
  * active-row list, spare */
@@ -53,7 +61,7 @@ struct PipLarge {
   unsigned long long *prof;       /* [8] cycle counters of CTA 0: AB, C, sync */
 };
 enum { PIPL_ACTION = 0, PIPL_PIVI, PIPL_PIVJ, PIPL_STATUS, PIPL_NCELL, PIPL_NI, PIPL_LDET, PIPL_PIVOTS,
-       PIPL_CUTS, PIPL_SKIPPED_LO, PIPL_SKIPPED_HI, PIPL_NACTIVE, PIPL_NEXT, PIPL_NCTL = 16 };
+       PIPL_CUTS, PIPL_SKIPPED_LO, PIPL_SKIPPED_HI, PIPL_NACTIVE, PIPL_NEXT, PIPL_PUSHED, PIPL_NCTL = 16 };
 enum { PIPL_GO = 0, PIPL_STOP = 1 };
 
 /* ---- CTA-level helpers (shared scratch: int red[64]) ------------------------------------- */
@@ -171,6 +179,11 @@ PIP_DEV void pipl_finish(const PipLarge &L, int status, int kind /*0 none, 1 nil
     L.ctl[PIPL_STATUS] = status;
     L.ctl[PIPL_NCELL] = status == PIP_ST_OK ? ncell : 0;
     L.ctl[PIPL_ACTION] = PIPL_STOP;
+#if defined(PIPL_WALK_STATS) && defined(__CUDACC__)
+    printf("walk stats: walks %llu, candidates %llu, CTA path: window steps %llu stops %llu (candidates left after stops %llu); warp path: window steps %llu stops %llu\n",
+           pipl_dbg[0], pipl_dbg[1], pipl_dbg[2], pipl_dbg[3], pipl_dbg[6], pipl_dbg[4], pipl_dbg[5]);
+    for (int i = 0; i < 8; i++) pipl_dbg[i] = 0;
+#endif
   }
 }
 
@@ -207,19 +220,28 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
   PIPL_T(2);
   int pivi = PIPL_INF;
   for (;;) {
-    /* chercher(Minus) */
-    int c = PIPL_INF;
-    for (int k = tid; k < nl; k += T) if ((L.fl[k] & PIP_MINUS) && k < c) c = k;
-    pivi = pipl_cta_min(c, red);
-    if (pivi < nl) break;
-    /* exam_coef with nparm = 0: an Unknown row takes the sign of its constant; rows after the
-     * first negative one stay Unknown */
-    c = PIPL_INF;
+    /* chercher(Minus), and in the same sweep the first Unknown row with a negative constant (what
+     * exam_coef with nparm = 0 would stop at: an Unknown row takes the sign of its constant, rows
+     * after the first negative one stay Unknown) */
+    int c = PIPL_INF, c2 = PIPL_INF;
     for (int k = tid; k < nl; k += T) {
       const int f = L.fl[k];
-      if (PIP_FLAG(f) == PIP_UNKNOWN && L.csign[k] < 0 && k < c) c = k;
+      if ((f & PIP_MINUS) && k < c) c = k;
+      if (PIP_FLAG(f) == PIP_UNKNOWN && L.csign[k] < 0 && k < c2) c2 = k;
     }
-    const int firstneg = pipl_cta_min(c, red);
+    {
+      c = (int)W::redmin((unsigned)c);
+      c2 = (int)W::redmin((unsigned)c2);
+      const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+      G::cta_sync();
+      if (lane == 0) { red[wid] = c; red[32 + wid] = c2; }
+      G::cta_sync();
+      c = PIPL_INF; c2 = PIPL_INF;
+      for (int i = 0; i < nw; i++) { c = red[i] < c ? red[i] : c; c2 = red[32 + i] < c2 ? red[32 + i] : c2; }
+    }
+    pivi = c;
+    if (pivi < nl) break;
+    const int firstneg = c2;
     for (int k = tid; k < nl; k += T) {
       const int f = L.fl[k];
       if (PIP_FLAG(f) != PIP_UNKNOWN || k > firstneg) continue;
@@ -292,158 +314,70 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
    * decision -- typically once or twice. */
   PIPL_T(3);
   const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
-  for (int j = tid; j < nvar; j += T) L.member[j] = prow[j] > 0 ? 1 : 0;
-  G::cta_sync();
-  const int ncand0 = pipl_compact(L, red, 0);
-  int ncand = ncand0;
-  if (ncand == 0) { pipl_finish(L, PIP_ST_OK, 1); return; }
-  int k = 0;
   const int nwords = (nl + 31) >> 5;
-  while (ncand > 1) {
-    if (ncand <= 32) {
-      /* few candidates left: one warp finishes the walk with the candidates in its lanes
-       * (column, pivot-row entry and Unit position in registers), no CTA barriers */
-      ncand = pipl_compact(L, red, 0);
-      if (tid < 32) {
-        const int lane = tid;
-        bool alive = lane < ncand;
-        const int j = alive ? L.cand[lane] : 0;
-        const pip_i64 pj = alive ? prow[j] : 1;
-        const int u = alive ? L.colpos[j] : PIPL_INF;
-        const bool was = alive;
-        int n = ncand;
-        while (n > 1) {
-          /* skip the rows that are zero in every column still in play, PIPL_WIN rows per step */
-          int pst = PIPL_INF;
-          for (;;) {
-            int wp[PIPL_WIN];
-            pipl_window(L, k, nl, nwords, wp);
-            if (wp[0] == PIPL_INF) break;
-            pip_i64 v[PIPL_WIN];
-            #pragma unroll
-            for (int b = 0; b < PIPL_WIN; b++)
-              v[b] = (alive && wp[b] < u) ? pipl_row(L, PIP_LINK(L.fl[wp[b]]))[j] : 0;
-            int first = PIPL_WIN;
-            #pragma unroll
-            for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0) first = b;
-            first = (int)W::redmin((unsigned)first);
-            if (first < PIPL_WIN) { pst = wp[first]; break; }
-            if (wp[PIPL_WIN - 1] == PIPL_INF) break;
-            if (pip_popc(W::ballot(alive && u > wp[PIPL_WIN - 1])) <= 1) break;     /* decided by the Unit positions */
-            k = wp[PIPL_WIN - 1] + 1;
-          }
-          const unsigned mel = W::ballot(alive && u < pst);
-          const int nel = pip_popc(mel);
-          if (nel >= n) {
-            const int umax = (int)W::redmax(alive ? (unsigned)u : 0u);
-            alive = alive && u == umax;
-            n = 1;
-            break;
-          }
-          if (alive && u < pst) alive = false;
-          n -= nel;
-          if (pst >= nl || n <= 1) break;
-          const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
-          const pip_i64 a = alive ? row[j] : 0;
-          pip_i64 ba = a, bp = pj;
-          int valid = alive ? 1 : 0;
-          for (int o = 16; o > 0; o >>= 1) {
-            const pip_i64 oa = W::shfl_xor64(ba, o), op = W::shfl_xor64(bp, o);
-            const int ov = W::shfl_xor(valid, o);
-            if (ov && (!valid || pipl_ratio_cmp(oa, op, ba, bp) < 0)) { ba = oa; bp = op; valid = 1; }
-          }
-          if (alive && pipl_ratio_cmp(a, pj, ba, bp) != 0) alive = false;
-#ifdef PIPL_WALK_STATS
-          { const int n2 = pip_popc(W::ballot(alive));
-            if (lane == 0) L.prof[7] += 1ull + ((ba == 0) ? (1ull << 20) : 0ull) + ((ba == 0 && n2 == n) ? (1ull << 40) : 0ull); }
-#endif
-          n = pip_popc(W::ballot(alive));
-          k = pst + 1;
-        }
-        if (was && !alive) L.member[j] = 0;
-      }
-      G::cta_sync();
-      ncand = 1;
-      break;
-    }
-    /* many candidates: the whole CTA walks, each thread keeping up to PIPL_K candidates (column,
-     * pivot-row entry, Unit position) in registers so that one walk step costs one gather of the
-     * stored row plus a few barriers */
-    {
-      int cj[PIPL_K], cu[PIPL_K];
-      pip_i64 cp[PIPL_K];
-      unsigned alive = 0;
-      #pragma unroll
-      for (int i = 0; i < PIPL_K; i++) {
-        const int m = tid + i * T;
-        cj[i] = 0; cu[i] = PIPL_INF; cp[i] = 1;
-        if (m < ncand0 && L.member[L.cand[m]]) { cj[i] = L.cand[m]; cu[i] = L.colpos[cj[i]]; cp[i] = prow[cj[i]]; alive |= 1u << i; }
-      }
-      const bool fits = ncand0 <= PIPL_K * T;
+  int pivj = PIPL_INF;
+  bool decided = false;
+  /* Usual case (about 100 positive entries in the pivot row of a 4096-column tableau): at most one
+   * candidate per thread.  The candidates are collected in shared memory, live in registers (column,
+   * pivot-row entry, Unit position, alive) for the whole walk, and the survivor comes out of one
+   * reduction -- no member[] / cand[] round trips through global memory. */
+  {
+    int *scnt = red + 126, *scj = red + 128;
+    const int cap = T < 6 * PIPL_LCAP ? T : 6 * PIPL_LCAP;
+    if (tid == 0) *scnt = 0;
+    G::cta_sync();
+    for (int j = tid; j < nvar; j += T)
+      if (prow[j] > 0) { const int at = (int)G::atomic_add_u((unsigned *)scnt, 1u); if (at < cap) scj[at] = j; }
+    G::cta_sync();
+    const int n0 = *scnt;
+    if (n0 == 0) { pipl_finish(L, PIP_ST_OK, 1); return; }
+    if (n0 <= cap) {
+      decided = true;
+      PIPL_DBG(0, 1); PIPL_DBG(1, n0);
+      bool alive = tid < n0;
+      int cj = alive ? scj[tid] : 0;
+      const pip_i64 cp = alive ? prow[cj] : 1;
+      int cu = alive ? L.colpos[cj] : PIPL_INF;
+      int ncand = n0, k = 0;
       pip_i64 *red64 = (pip_i64 *)red;
-      while (fits && ncand > 32) {
-        /* Skip ahead to the first stored row that can discriminate: a row whose entries are zero in
-         * every column still in play (97 % of the rows met on consecutive-ones tableaus) leaves the
-         * candidate set alone, so the walk examines PIPL_WIN rows per step -- all gathers of a window
-         * in flight together, one reduction -- and only stops at a row with a non-zero entry.
-         * Candidates whose Unit position lies before a row are out of play at that row; they are
-         * struck (lazily) by the cu < pst test below. */
+      G::cta_sync();
+      while (ncand > 32) {
         int pst = PIPL_INF;
         for (;;) {
           int wp[PIPL_WIN];
           pipl_window(L, k, nl, nwords, wp);
           if (wp[0] == PIPL_INF) break;
-          const pip_i64 *wr[PIPL_WIN];
-          #pragma unroll
-          for (int b = 0; b < PIPL_WIN; b++) wr[b] = wp[b] != PIPL_INF ? pipl_row(L, PIP_LINK(L.fl[wp[b]])) : prow;
+          PIPL_DBG(2, 1);
           int first = PIPL_WIN;
-          #pragma unroll
-          for (int i = 0; i < PIPL_K; i++) {
-            if (!((alive >> i) & 1u)) continue;
+          if (alive) {
             pip_i64 v[PIPL_WIN];
             #pragma unroll
-            for (int b = 0; b < PIPL_WIN; b++) v[b] = wp[b] < cu[i] ? wr[b][cj[i]] : 0;      /* PIPL_INF < cu never holds */
+            for (int b = 0; b < PIPL_WIN; b++) v[b] = wp[b] < cu ? pipl_row(L, PIP_LINK(L.fl[wp[b]]))[cj] : 0;
             #pragma unroll
-            for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0 && b < first) first = b;
+            for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0) first = b;
           }
           first = pipl_cta_min(first, red);
           if (first < PIPL_WIN) { pst = wp[first]; break; }
-          if (wp[PIPL_WIN - 1] == PIPL_INF) break;               /* no stored row left */
-          /* the Unit positions passed so far may already have decided the walk: with at most one
-           * candidate still in play beyond this window the survivor is the one with the last Unit
-           * position, which the pst = PIPL_INF case below picks */
-          int inplay = 0;
-          #pragma unroll
-          for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] > wp[PIPL_WIN - 1]) inplay++;
-          inplay = pipl_cta_sum(inplay, red);
+          if (wp[PIPL_WIN - 1] == PIPL_INF) break;
+          const int inplay = pipl_cta_sum((alive && cu > wp[PIPL_WIN - 1]) ? 1 : 0, red);
           if (inplay <= 1) break;
           k = wp[PIPL_WIN - 1] + 1;
         }
-        int nel = 0, umax = -1;
-        #pragma unroll
-        for (int i = 0; i < PIPL_K; i++)
-          if (((alive >> i) & 1u) && cu[i] < pst) { nel++; if (cu[i] > umax) umax = cu[i]; }
-        nel = pipl_cta_sum(nel, red);
+        const bool struck = alive && cu < pst;
+        const int nel = pipl_cta_sum(struck ? 1 : 0, red);
         if (nel >= ncand) {
-          umax = pipl_cta_max(umax, red);
-          #pragma unroll
-          for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] != umax) alive &= ~(1u << i);
+          const int umax = pipl_cta_max(struck ? cu : -1, red);
+          if (alive && cu != umax) alive = false;
           ncand = 1;
           break;
         }
-        #pragma unroll
-        for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] < pst) alive &= ~(1u << i);
+        if (struck) alive = false;
         ncand -= nel;
         if (pst >= nl || ncand <= 1) break;
         const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
-        pip_i64 va[PIPL_K];
-        #pragma unroll
-        for (int i = 0; i < PIPL_K; i++) va[i] = ((alive >> i) & 1u) ? row[cj[i]] : 0;
-        pip_i64 ba = 0, bp = 1;
-        int valid = 0;
-        #pragma unroll
-        for (int i = 0; i < PIPL_K; i++)
-          if (((alive >> i) & 1u) && (!valid || pipl_ratio_cmp(va[i], cp[i], ba, bp) < 0)) { ba = va[i]; bp = cp[i]; valid = 1; }
+        const pip_i64 va = alive ? row[cj] : 0;
+        pip_i64 ba = va, bp = cp;
+        int valid = alive ? 1 : 0;
         for (int o = 16; o > 0; o >>= 1) {
           const pip_i64 oa = W::shfl_xor64(ba, o), op = W::shfl_xor64(bp, o);
           const int ov = W::shfl_xor(valid, o);
@@ -456,107 +390,356 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
           G::cta_sync();
           valid = 0;
           for (int i = 0; i < nw; i++)
-            if (red[96 + i] && (!valid || pipl_ratio_cmp(red64[2 * i], red64[2 * i + 1], ba, bp) < 0 || !valid)) {
-              if (!valid || pipl_ratio_cmp(red64[2 * i], red64[2 * i + 1], ba, bp) < 0) { ba = red64[2 * i]; bp = red64[2 * i + 1]; }
-              valid = 1;
+            if (red[96 + i] && (!valid || pipl_ratio_cmp(red64[2 * i], red64[2 * i + 1], ba, bp) < 0)) {
+              ba = red64[2 * i]; bp = red64[2 * i + 1]; valid = 1;
             }
         }
-        int removed = 0;
-        #pragma unroll
-        for (int i = 0; i < PIPL_K; i++)
-          if (((alive >> i) & 1u) && pipl_ratio_cmp(va[i], cp[i], ba, bp) != 0) { alive &= ~(1u << i); removed++; }
-        removed = pipl_cta_sum(removed, red);
-        ncand -= removed;
+        const bool out = alive && pipl_ratio_cmp(va, cp, ba, bp) != 0;
+        if (out) alive = false;
+        ncand -= pipl_cta_sum(out ? 1 : 0, red);
         k = pst + 1;
-#ifdef PIPL_WALK_STATS
-        if (tid == 0) L.prof[7] += 1ull + ((ba == 0) ? (1ull << 20) : 0ull) + ((ba == 0 && removed == 0) ? (1ull << 40) : 0ull);
-#endif
+        PIPL_DBG(3, 1); PIPL_DBG(6, ncand);
       }
-      /* publish the survivors */
-      #pragma unroll
-      for (int i = 0; i < PIPL_K; i++) {
-        const int m = tid + i * T;
-        if (m < ncand0 && L.member[L.cand[m]] && !((alive >> i) & 1u) && fits) L.member[L.cand[m]] = 0;
-      }
-      G::cta_sync();
-      if (fits) continue;                       /* <= 32 left (warp path) or decided */
+      if (ncand > 1) {
+        /* at most 32 left: warp 0 finishes the walk on its own, no CTA barriers */
+        G::cta_sync();
+        if (tid == 0) *scnt = 0;
+        G::cta_sync();
+        if (alive) scj[G::atomic_add_u((unsigned *)scnt, 1u)] = cj;
+        G::cta_sync();
+        if (tid < 32) {
+          const int lane = tid;
+          int n = *scnt;
+          alive = lane < n;
+          cj = alive ? scj[lane] : 0;
+          const pip_i64 pj = alive ? prow[cj] : 1;
+          const int u = alive ? L.colpos[cj] : PIPL_INF;
+          while (n > 1) {
+            int pst = PIPL_INF;
+            for (;;) {
+              int wp[PIPL_WIN];
+              pipl_window(L, k, nl, nwords, wp);
+              if (wp[0] == PIPL_INF) break;
+              PIPL_DBG(4, 1);
+              pip_i64 v[PIPL_WIN];
+              #pragma unroll
+              for (int b = 0; b < PIPL_WIN; b++)
+                v[b] = (alive && wp[b] < u) ? pipl_row(L, PIP_LINK(L.fl[wp[b]]))[cj] : 0;
+              int first = PIPL_WIN;
+              #pragma unroll
+              for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0) first = b;
+              first = (int)W::redmin((unsigned)first);
+              if (first < PIPL_WIN) { pst = wp[first]; break; }
+              if (wp[PIPL_WIN - 1] == PIPL_INF) break;
+              if (pip_popc(W::ballot(alive && u > wp[PIPL_WIN - 1])) <= 1) break;
+              k = wp[PIPL_WIN - 1] + 1;
+            }
+            const unsigned mel = W::ballot(alive && u < pst);
+            const int nel = pip_popc(mel);
+            if (nel >= n) {
+              const int umax = (int)W::redmax(alive ? (unsigned)u : 0u);
+              alive = alive && u == umax;
+              n = 1;
+              break;
+            }
+            if (alive && u < pst) alive = false;
+            n -= nel;
+            if (pst >= nl || n <= 1) break;
+            const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
+            const pip_i64 a = alive ? row[cj] : 0;
+            pip_i64 ba = a, bp = pj;
+            int valid = alive ? 1 : 0;
+            for (int o = 16; o > 0; o >>= 1) {
+              const pip_i64 oa = W::shfl_xor64(ba, o), op = W::shfl_xor64(bp, o);
+              const int ov = W::shfl_xor(valid, o);
+              if (ov && (!valid || pipl_ratio_cmp(oa, op, ba, bp) < 0)) { ba = oa; bp = op; valid = 1; }
+            }
+            if (alive && pipl_ratio_cmp(a, pj, ba, bp) != 0) alive = false;
+            n = pip_popc(W::ballot(alive));
+            k = pst + 1;
+            PIPL_DBG(5, 1);
+          }
+          const int best = (int)W::redmin(alive ? (unsigned)cj : (unsigned)PIPL_INF);
+          if (lane == 0) red[125] = best;
+        }
+        G::cta_sync();
+        pivj = red[125];
+      } else pivj = pipl_cta_min(alive ? cj : PIPL_INF, red);
     }
-    /* fallback for more than PIPL_K * T candidates: everything through global memory */
-    /* next stored position >= k */
-    int c = PIPL_INF;
-    for (int w = (k >> 5) + tid; w < nwords; w += T) {
-      unsigned bits = L.sbits[w];
-      if (w == (k >> 5)) bits &= ~0u << (k & 31);
-      if (bits) { const int pp = (w << 5) + pip_ffs(bits) - 1; if (pp < nl && pp < c) c = pp; break; }
-    }
-    const int pst = pipl_cta_min(c, red);
-    /* strike the members whose Unit position lies in [k, pst) */
-    int nel = 0, umax = -1;
-    for (int m = tid; m < ncand0; m += T) {
-      const int j = L.cand[m];
-      if (!L.member[j]) continue;
-      const int u = L.colpos[j];
-      if (u < pst) { nel++; if (u > umax) umax = u; }
-    }
-    nel = pipl_cta_sum(nel, red);
-    if (nel >= ncand) {
-      umax = pipl_cta_max(umax, red);
-      for (int m = tid; m < ncand0; m += T) {
-        const int j = L.cand[m];
-        if (L.member[j] && L.colpos[j] != umax) L.member[j] = 0;
-      }
-      G::cta_sync();
-      ncand = 1;
-      break;
-    }
-    if (nel) {
-      for (int m = tid; m < ncand0; m += T) {
-        const int j = L.cand[m];
-        if (L.member[j] && L.colpos[j] < pst) L.member[j] = 0;
-      }
-      G::cta_sync();
-      ncand -= nel;
-    }
-    if (pst >= nl || ncand <= 1) break;
-    /* keep the members with the minimal ratio at the stored row pst */
-    const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
-    int best = -1;
-    for (int m = tid; m < ncand0; m += T) {
-      const int j = L.cand[m];
-      if (!L.member[j]) continue;
-      if (best < 0 || pipl_ratio_cmp(row[j], prow[j], row[best], prow[best]) < 0) best = j;
-    }
-    int winner = best;
-    {
-      const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
-      for (int o = 16; o > 0; o >>= 1) {
-        const int other = W::shfl_down(winner, o);
-        if (lane + o < 32 && other >= 0 && (winner < 0 || pipl_ratio_cmp(row[other], prow[other], row[winner], prow[winner]) < 0))
-          winner = other;
-      }
-      G::cta_sync();
-      if (lane == 0) red[wid] = winner;
-      G::cta_sync();
-      winner = -1;
-      for (int i = 0; i < nw; i++) {
-        const int o = red[i];
-        if (o >= 0 && (winner < 0 || pipl_ratio_cmp(row[o], prow[o], row[winner], prow[winner]) < 0)) winner = o;
-      }
-    }
-    int removed = 0;
-    for (int m = tid; m < ncand0; m += T) {
-      const int j = L.cand[m];
-      if (L.member[j] && pipl_ratio_cmp(row[j], prow[j], row[winner], prow[winner]) != 0) { L.member[j] = 0; removed++; }
-    }
-    removed = pipl_cta_sum(removed, red);
-    G::cta_sync();
-    ncand -= removed;
-    k = pst + 1;
   }
-  /* the survivor (smallest column if, against the theory, several remain) */
-  int pj = PIPL_INF;
-  for (int j = tid; j < nvar; j += T) if (L.member[j] && j < pj) pj = j;
-  const int pivj = pipl_cta_min(pj, red);
+  if (!decided) {
+    /* more positive entries than threads: candidate set in global memory (member[], cand[]) */
+    for (int j = tid; j < nvar; j += T) L.member[j] = prow[j] > 0 ? 1 : 0;
+    G::cta_sync();
+    const int ncand0 = pipl_compact(L, red, 0);
+    int ncand = ncand0;
+    if (ncand == 0) { pipl_finish(L, PIP_ST_OK, 1); return; }
+    PIPL_DBG(0, 1); PIPL_DBG(1, ncand0);
+    int k = 0;
+    while (ncand > 1) {
+      if (ncand <= 32) {
+        /* few candidates left: one warp finishes the walk with the candidates in its lanes
+         * (column, pivot-row entry and Unit position in registers), no CTA barriers */
+        ncand = pipl_compact(L, red, 0);
+        if (tid < 32) {
+          const int lane = tid;
+          bool alive = lane < ncand;
+          const int j = alive ? L.cand[lane] : 0;
+          const pip_i64 pj = alive ? prow[j] : 1;
+          const int u = alive ? L.colpos[j] : PIPL_INF;
+          const bool was = alive;
+          int n = ncand;
+          while (n > 1) {
+            /* skip the rows that are zero in every column still in play, PIPL_WIN rows per step */
+            int pst = PIPL_INF;
+            for (;;) {
+              int wp[PIPL_WIN];
+              pipl_window(L, k, nl, nwords, wp);
+              if (wp[0] == PIPL_INF) break;
+              PIPL_DBG(4, 1);
+              pip_i64 v[PIPL_WIN];
+              #pragma unroll
+              for (int b = 0; b < PIPL_WIN; b++)
+                v[b] = (alive && wp[b] < u) ? pipl_row(L, PIP_LINK(L.fl[wp[b]]))[j] : 0;
+              int first = PIPL_WIN;
+              #pragma unroll
+              for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0) first = b;
+              first = (int)W::redmin((unsigned)first);
+              if (first < PIPL_WIN) { pst = wp[first]; break; }
+              if (wp[PIPL_WIN - 1] == PIPL_INF) break;
+              if (pip_popc(W::ballot(alive && u > wp[PIPL_WIN - 1])) <= 1) break;     /* decided by the Unit positions */
+              k = wp[PIPL_WIN - 1] + 1;
+            }
+            const unsigned mel = W::ballot(alive && u < pst);
+            const int nel = pip_popc(mel);
+            if (nel >= n) {
+              const int umax = (int)W::redmax(alive ? (unsigned)u : 0u);
+              alive = alive && u == umax;
+              n = 1;
+              break;
+            }
+            if (alive && u < pst) alive = false;
+            n -= nel;
+            if (pst >= nl || n <= 1) break;
+            const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
+            const pip_i64 a = alive ? row[j] : 0;
+            pip_i64 ba = a, bp = pj;
+            int valid = alive ? 1 : 0;
+            for (int o = 16; o > 0; o >>= 1) {
+              const pip_i64 oa = W::shfl_xor64(ba, o), op = W::shfl_xor64(bp, o);
+              const int ov = W::shfl_xor(valid, o);
+              if (ov && (!valid || pipl_ratio_cmp(oa, op, ba, bp) < 0)) { ba = oa; bp = op; valid = 1; }
+            }
+            if (alive && pipl_ratio_cmp(a, pj, ba, bp) != 0) alive = false;
+  #ifdef PIPL_WALK_STATS
+            { const int n2 = pip_popc(W::ballot(alive));
+              if (lane == 0) L.prof[7] += 1ull + ((ba == 0) ? (1ull << 20) : 0ull) + ((ba == 0 && n2 == n) ? (1ull << 40) : 0ull); }
+            PIPL_DBG(5, 1);
+  #endif
+            n = pip_popc(W::ballot(alive));
+            k = pst + 1;
+          }
+          if (was && !alive) L.member[j] = 0;
+        }
+        G::cta_sync();
+        ncand = 1;
+        break;
+      }
+      /* many candidates: the whole CTA walks, each thread keeping up to PIPL_K candidates (column,
+       * pivot-row entry, Unit position) in registers so that one walk step costs one gather of the
+       * stored row plus a few barriers */
+      {
+        int cj[PIPL_K], cu[PIPL_K];
+        pip_i64 cp[PIPL_K];
+        unsigned alive = 0;
+        #pragma unroll
+        for (int i = 0; i < PIPL_K; i++) {
+          const int m = tid + i * T;
+          cj[i] = 0; cu[i] = PIPL_INF; cp[i] = 1;
+          if (m < ncand0 && L.member[L.cand[m]]) { cj[i] = L.cand[m]; cu[i] = L.colpos[cj[i]]; cp[i] = prow[cj[i]]; alive |= 1u << i; }
+        }
+        const bool fits = ncand0 <= PIPL_K * T;
+        pip_i64 *red64 = (pip_i64 *)red;
+        while (fits && ncand > 32) {
+          /* Skip ahead to the first stored row that can discriminate: a row whose entries are zero in
+           * every column still in play (97 % of the rows met on consecutive-ones tableaus) leaves the
+           * candidate set alone, so the walk examines PIPL_WIN rows per step -- all gathers of a window
+           * in flight together, one reduction -- and only stops at a row with a non-zero entry.
+           * Candidates whose Unit position lies before a row are out of play at that row; they are
+           * struck (lazily) by the cu < pst test below. */
+          int pst = PIPL_INF;
+          for (;;) {
+            int wp[PIPL_WIN];
+            pipl_window(L, k, nl, nwords, wp);
+            if (wp[0] == PIPL_INF) break;
+            PIPL_DBG(2, 1);
+            const pip_i64 *wr[PIPL_WIN];
+            #pragma unroll
+            for (int b = 0; b < PIPL_WIN; b++) wr[b] = wp[b] != PIPL_INF ? pipl_row(L, PIP_LINK(L.fl[wp[b]])) : prow;
+            int first = PIPL_WIN;
+            #pragma unroll
+            for (int i = 0; i < PIPL_K; i++) {
+              if (!((alive >> i) & 1u)) continue;
+              pip_i64 v[PIPL_WIN];
+              #pragma unroll
+              for (int b = 0; b < PIPL_WIN; b++) v[b] = wp[b] < cu[i] ? wr[b][cj[i]] : 0;      /* PIPL_INF < cu never holds */
+              #pragma unroll
+              for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0 && b < first) first = b;
+            }
+            first = pipl_cta_min(first, red);
+            if (first < PIPL_WIN) { pst = wp[first]; break; }
+            if (wp[PIPL_WIN - 1] == PIPL_INF) break;               /* no stored row left */
+            /* the Unit positions passed so far may already have decided the walk: with at most one
+             * candidate still in play beyond this window the survivor is the one with the last Unit
+             * position, which the pst = PIPL_INF case below picks */
+            int inplay = 0;
+            #pragma unroll
+            for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] > wp[PIPL_WIN - 1]) inplay++;
+            inplay = pipl_cta_sum(inplay, red);
+            if (inplay <= 1) break;
+            k = wp[PIPL_WIN - 1] + 1;
+          }
+          int nel = 0, umax = -1;
+          #pragma unroll
+          for (int i = 0; i < PIPL_K; i++)
+            if (((alive >> i) & 1u) && cu[i] < pst) { nel++; if (cu[i] > umax) umax = cu[i]; }
+          nel = pipl_cta_sum(nel, red);
+          if (nel >= ncand) {
+            umax = pipl_cta_max(umax, red);
+            #pragma unroll
+            for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] != umax) alive &= ~(1u << i);
+            ncand = 1;
+            break;
+          }
+          #pragma unroll
+          for (int i = 0; i < PIPL_K; i++) if (((alive >> i) & 1u) && cu[i] < pst) alive &= ~(1u << i);
+          ncand -= nel;
+          if (pst >= nl || ncand <= 1) break;
+          const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
+          pip_i64 va[PIPL_K];
+          #pragma unroll
+          for (int i = 0; i < PIPL_K; i++) va[i] = ((alive >> i) & 1u) ? row[cj[i]] : 0;
+          pip_i64 ba = 0, bp = 1;
+          int valid = 0;
+          #pragma unroll
+          for (int i = 0; i < PIPL_K; i++)
+            if (((alive >> i) & 1u) && (!valid || pipl_ratio_cmp(va[i], cp[i], ba, bp) < 0)) { ba = va[i]; bp = cp[i]; valid = 1; }
+          for (int o = 16; o > 0; o >>= 1) {
+            const pip_i64 oa = W::shfl_xor64(ba, o), op = W::shfl_xor64(bp, o);
+            const int ov = W::shfl_xor(valid, o);
+            if (ov && (!valid || pipl_ratio_cmp(oa, op, ba, bp) < 0)) { ba = oa; bp = op; valid = 1; }
+          }
+          {
+            const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+            G::cta_sync();
+            if (lane == 0) { red64[2 * wid] = ba; red64[2 * wid + 1] = bp; red[96 + wid] = valid; }
+            G::cta_sync();
+            valid = 0;
+            for (int i = 0; i < nw; i++)
+              if (red[96 + i] && (!valid || pipl_ratio_cmp(red64[2 * i], red64[2 * i + 1], ba, bp) < 0 || !valid)) {
+                if (!valid || pipl_ratio_cmp(red64[2 * i], red64[2 * i + 1], ba, bp) < 0) { ba = red64[2 * i]; bp = red64[2 * i + 1]; }
+                valid = 1;
+              }
+          }
+          int removed = 0;
+          #pragma unroll
+          for (int i = 0; i < PIPL_K; i++)
+            if (((alive >> i) & 1u) && pipl_ratio_cmp(va[i], cp[i], ba, bp) != 0) { alive &= ~(1u << i); removed++; }
+          removed = pipl_cta_sum(removed, red);
+          ncand -= removed;
+          k = pst + 1;
+  #ifdef PIPL_WALK_STATS
+          if (tid == 0) L.prof[7] += 1ull + ((ba == 0) ? (1ull << 20) : 0ull) + ((ba == 0 && removed == 0) ? (1ull << 40) : 0ull);
+          PIPL_DBG(3, 1); PIPL_DBG(6, ncand);
+  #endif
+        }
+        /* publish the survivors */
+        #pragma unroll
+        for (int i = 0; i < PIPL_K; i++) {
+          const int m = tid + i * T;
+          if (m < ncand0 && L.member[L.cand[m]] && !((alive >> i) & 1u) && fits) L.member[L.cand[m]] = 0;
+        }
+        G::cta_sync();
+        if (fits) continue;                       /* <= 32 left (warp path) or decided */
+      }
+      /* fallback for more than PIPL_K * T candidates: everything through global memory */
+      /* next stored position >= k */
+      int c = PIPL_INF;
+      for (int w = (k >> 5) + tid; w < nwords; w += T) {
+        unsigned bits = L.sbits[w];
+        if (w == (k >> 5)) bits &= ~0u << (k & 31);
+        if (bits) { const int pp = (w << 5) + pip_ffs(bits) - 1; if (pp < nl && pp < c) c = pp; break; }
+      }
+      const int pst = pipl_cta_min(c, red);
+      /* strike the members whose Unit position lies in [k, pst) */
+      int nel = 0, umax = -1;
+      for (int m = tid; m < ncand0; m += T) {
+        const int j = L.cand[m];
+        if (!L.member[j]) continue;
+        const int u = L.colpos[j];
+        if (u < pst) { nel++; if (u > umax) umax = u; }
+      }
+      nel = pipl_cta_sum(nel, red);
+      if (nel >= ncand) {
+        umax = pipl_cta_max(umax, red);
+        for (int m = tid; m < ncand0; m += T) {
+          const int j = L.cand[m];
+          if (L.member[j] && L.colpos[j] != umax) L.member[j] = 0;
+        }
+        G::cta_sync();
+        ncand = 1;
+        break;
+      }
+      if (nel) {
+        for (int m = tid; m < ncand0; m += T) {
+          const int j = L.cand[m];
+          if (L.member[j] && L.colpos[j] < pst) L.member[j] = 0;
+        }
+        G::cta_sync();
+        ncand -= nel;
+      }
+      if (pst >= nl || ncand <= 1) break;
+      /* keep the members with the minimal ratio at the stored row pst */
+      const pip_i64 *row = pipl_row(L, PIP_LINK(L.fl[pst]));
+      int best = -1;
+      for (int m = tid; m < ncand0; m += T) {
+        const int j = L.cand[m];
+        if (!L.member[j]) continue;
+        if (best < 0 || pipl_ratio_cmp(row[j], prow[j], row[best], prow[best]) < 0) best = j;
+      }
+      int winner = best;
+      {
+        const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+        for (int o = 16; o > 0; o >>= 1) {
+          const int other = W::shfl_down(winner, o);
+          if (lane + o < 32 && other >= 0 && (winner < 0 || pipl_ratio_cmp(row[other], prow[other], row[winner], prow[winner]) < 0))
+            winner = other;
+        }
+        G::cta_sync();
+        if (lane == 0) red[wid] = winner;
+        G::cta_sync();
+        winner = -1;
+        for (int i = 0; i < nw; i++) {
+          const int o = red[i];
+          if (o >= 0 && (winner < 0 || pipl_ratio_cmp(row[o], prow[o], row[winner], prow[winner]) < 0)) winner = o;
+        }
+      }
+      int removed = 0;
+      for (int m = tid; m < ncand0; m += T) {
+        const int j = L.cand[m];
+        if (L.member[j] && pipl_ratio_cmp(row[j], prow[j], row[winner], prow[winner]) != 0) { L.member[j] = 0; removed++; }
+      }
+      removed = pipl_cta_sum(removed, red);
+      G::cta_sync();
+      ncand -= removed;
+      k = pst + 1;
+    }
+    /* the survivor (smallest column if, against the theory, several remain) */
+    int pj = PIPL_INF;
+    for (int j = tid; j < nvar; j += T) if (L.member[j] && j < pj) pj = j;
+    pivj = pipl_cta_min(pj, red);
+
+  }
   if (pivj >= nvar) { pipl_finish(L, PIP_ST_FAULT, 0); return; }
 
   PIPL_T(4);
@@ -597,150 +780,171 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     if (status == PIP_ST_OK) L.ctl[PIPL_PIVOTS] = L.ctl[PIPL_PIVOTS] + 1;
     L.ctl[PIPL_NACTIVE] = 0;
     L.ctl[PIPL_NEXT] = 0;
+    L.ctl[PIPL_PUSHED] = 0;
   }
   G::cta_sync();
   PIPL_T(5);
-  /* rows whose update is not the identity (foo != 0 or a denominator to normalise,
-   * source/traiter.c:470-501): only those are visited by the update phase */
-  {
-    /* PIPL_AL positions per thread per round, loads issued together (the walk is latency-bound) */
-    int nskip = 0;
-    for (int base = 0; base < nl; base += PIPL_AL * T) {
-      int pp[PIPL_AL], ff[PIPL_AL];
-      pip_i64 foo[PIPL_AL], dd[PIPL_AL];
-      #pragma unroll
-      for (int i = 0; i < PIPL_AL; i++) { pp[i] = base + i * T + tid; ff[i] = pp[i] < nl ? L.fl[pp[i]] : PIP_UNIT; }
-      #pragma unroll
-      for (int i = 0; i < PIPL_AL; i++) {
-        const bool st = pp[i] < nl && pp[i] != pivi && !(ff[i] & PIP_UNIT);
-        foo[i] = st ? pipl_row(L, PIP_LINK(ff[i]))[pivj] : 0;
-        dd[i] = st ? L.den[pp[i]] : 1;
-        if (!st) ff[i] = PIP_UNIT;
-      }
-      /* one queue reservation per warp per round (the order of the work queue is free) */
-      unsigned am[PIPL_AL];
-      int total = 0;
-      #pragma unroll
-      for (int i = 0; i < PIPL_AL; i++) {
-        const bool st = !(ff[i] & PIP_UNIT);
-        const bool act = st && (foo[i] != 0 || dd[i] != 1);
-        if (st && !act) nskip++;
-        am[i] = W::ballot(act);
-        total += pip_popc(am[i]);
-      }
-      int at = 0;
-      if (W::lane() == 0 && total) at = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], (unsigned)total);
-      at = W::shfl(at, 0);
-      #pragma unroll
-      for (int i = 0; i < PIPL_AL; i++) {
-        if ((am[i] >> W::lane()) & 1u) L.active[at + pip_popc(am[i] & ((1u << W::lane()) - 1u))] = pp[i];
-        at += pip_popc(am[i]);
-      }
-    }
-    nskip = pipl_cta_sum(nskip, red);
-    if (tid == 0) L.ctl[PIPL_SKIPPED_LO] = L.ctl[PIPL_SKIPPED_LO] + nskip;
-  }
   PIPL_T(6);
 }
 
-/* ---- phase C: the CTAs of the grid pull active rows from a queue; one CTA updates one row ------ */
-PIP_DEV void pipl_phase_c(const PipLarge &L, int *red)
+/* ---- phase C: rank-1 update of the stored rows (source/traiter.c:461-502), all CTAs --------------
+ * Every CTA looks at its own stripe of positions (cta, cta + ncta, ...), one position per thread, and
+ * keeps the rows whose update is not the identity (pivot-column entry != 0 or a denominator to
+ * normalise) in a shared-memory list together with what the scan already loaded.  It updates up to
+ * PIPL_KEEP of them itself, the whole CTA on one row; what is left over goes to a grid-wide overflow
+ * queue that the CTAs drain once everybody has published (ctl[PUSHED] == ncta).  No single-CTA list
+ * phase, no atomic per row on the common path. */
+
+PIP_DEV void pipl_update_row(const PipLarge &L, int *red, int k, int f, pip_i64 foo, pip_i64 dk, const pip_i64 *prow,
+                             pip_i64 pivot, pip_i64 dpiv, int pivj)
 {
   const int tid = G::tid(), T = G::T();
   const int nvar = L.nvar, ncol = nvar + 1;
-  const int pivi = L.ctl[PIPL_PIVI], pivj = L.ctl[PIPL_PIVJ], nactive = L.ctl[PIPL_NACTIVE];
+  pip_i64 *row = pipl_row(L, PIP_LINK(f));
+  pip_i64 lpiv = pivot;
+  if (foo == 0) lpiv = 1;
+  else if (pivot != 1 && foo != 1 && foo != -1) {
+    const pip_i64 d = pip_gcd(pivot, foo);
+    if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
+  }
+  const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
+  const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
+  pip_u64 orz = 0;
+  /* pass 1: z = row*lpiv - prow*foo, 16-byte accesses, the whole CTA on one row */
+  const int pairs = ncol >> 1;
+  pip_i64x2 *row2 = (pip_i64x2 *)row;
+  const pip_i64x2 *prow2 = (const pip_i64x2 *)prow;
+  #pragma unroll 2
+  for (int q = tid; q < pairs; q += T) {
+    const pip_i64x2 a = row2[q], b = prow2[q];
+    pip_i64x2 z;
+    z.x = (pip_i64)((pip_u64)a.x * (pip_u64)lpiv - (pip_u64)b.x * (pip_u64)foo);
+    z.y = (pip_i64)((pip_u64)a.y * (pip_u64)lpiv - (pip_u64)b.y * (pip_u64)foo);
+    if (2 * q == pivj) z.x = zp;
+    if (2 * q + 1 == pivj) z.y = zp;
+    row2[q] = z;
+    orz |= (pip_u64)z.x | (pip_u64)z.y;
+  }
+  if ((ncol & 1) && tid == 0) {
+    const int j = ncol - 1;
+    pip_i64 z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
+    if (j == pivj) z = zp;
+    row[j] = z;
+    orz |= (pip_u64)z;
+  }
+  pip_i64 g = newden;
+  if (g != 1) {                        /* uniform over the CTA */
+    if ((g & (g - 1)) == 0 && g > 0) {
+      orz |= (pip_u64)g;
+      unsigned lo = W::redor((unsigned)orz), hi = W::redor((unsigned)(orz >> 32));
+      const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+      G::cta_sync();
+      if (lane == 0) { red[2 * wid] = (int)lo; red[2 * wid + 1] = (int)hi; }
+      G::cta_sync();
+      lo = 0; hi = 0;
+      for (int i = 0; i < nw; i++) { lo |= (unsigned)red[2 * i]; hi |= (unsigned)red[2 * i + 1]; }
+      const pip_u64 all = ((pip_u64)hi << 32) | lo;
+      g = (pip_i64)(all & (0ull - all));
+    } else {
+      G::cta_sync();                   /* pass 1 stores visible */
+      for (int j = tid; j < ncol && g != 1; j += T) g = pip_gcd(g, row[j]);
+      for (int o = 16; o > 0; o >>= 1) g = pip_gcd(g, W::shfl_xor64(g, o));
+      const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+      pip_i64 *red64 = (pip_i64 *)red;
+      G::cta_sync();
+      if (lane == 0) red64[wid] = g;
+      G::cta_sync();
+      g = red64[0];
+      for (int i = 1; i < nw; i++) g = pip_gcd(g, red64[i]);
+    }
+  }
+  pip_i64 nd = newden;
+  if (g != 1 && g != 0) {
+    G::cta_sync();
+    const PipExactDiv e = pip_exact_prepare(g);
+    for (int j = tid; j < ncol; j += T) row[j] = pip_exact_apply(row[j], e);
+    nd = pip_exact_apply(newden, e);
+  }
+  G::cta_sync();
+  if (tid == 0) {
+    L.den[k] = nd;
+    const pip_i64 c = row[nvar];
+    L.csign[k] = c < 0 ? -1 : c > 0 ? 1 : 0;
+    int ff = PIP_FLAG(f);
+    const int fff = zp < 0 ? PIP_MINUS : zp == 0 ? PIP_ZERO : PIP_PLUS;
+    if (fff != PIP_ZERO && fff != ff) {
+      if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
+      else ff = PIP_UNKNOWN;
+      L.fl[k] = PIP_MKFL(ff, PIP_LINK(f));
+    }
+    if (g == 0) L.ctl[PIPL_STATUS] = PIP_ST_FAULT;
+  }
+}
+
+PIP_DEV void pipl_phase_c(const PipLarge &L, int *red)
+{
+  const int tid = G::tid(), T = G::T(), cta = G::cta(), ncta = G::ncta();
+  const int nl = L.nvar + L.ctl[PIPL_NI];
+  const int pivi = L.ctl[PIPL_PIVI], pivj = L.ctl[PIPL_PIVJ];
   const pip_i64 pivot = L.ctl64[0], dpiv = L.ctl64[1];
   const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
+  int *lcnt = red + 127, *lk = red + 128, *lf = red + 128 + PIPL_LCAP;
+  pip_i64 *lfoo = (pip_i64 *)(red + 128 + 2 * PIPL_LCAP), *lden = lfoo + PIPL_LCAP;
+  if (tid == 0) *lcnt = 0;
+  G::cta_sync();
+  /* scan the stripe: every load of a position is issued by its own thread, one round trip in all */
+  int nskip = 0;
+  for (int p = cta + tid * ncta; p < nl; p += T * ncta) {
+    const int f = L.fl[p];
+    if (p == pivi || (f & PIP_UNIT)) continue;
+    const pip_i64 foo = pipl_row(L, PIP_LINK(f))[pivj];
+    const pip_i64 dk = L.den[p];
+    if (foo == 0 && dk == 1) { nskip++; continue; }
+    const int at = (int)G::atomic_add_u((unsigned *)lcnt, 1u);
+    if (at < PIPL_LCAP) { lk[at] = p; lf[at] = f; lfoo[at] = foo; lden[at] = dk; }
+    else L.active[G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], 1u)] = p;     /* never on sane grids */
+  }
+  nskip = pipl_cta_sum(nskip, red);                /* also orders the list stores before the reads */
+  int nloc = *lcnt < PIPL_LCAP ? *lcnt : PIPL_LCAP;
+  const int keep = nloc < PIPL_KEEP ? nloc : PIPL_KEEP;
+  /* publish the left-overs, then tell the grid this CTA has nothing more to add */
+  if (nloc > keep) {
+    if (tid == 0) red[63] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], (unsigned)(nloc - keep));
+    G::cta_sync();
+    const int at = red[63];
+    for (int i = keep + tid; i < nloc; i += T) L.active[at + i - keep] = lk[i];
+  }
+  G::cta_sync();
+  if (tid == 0) {
+    if (nskip) G::atomic_add_u((unsigned *)&L.ctl[PIPL_SKIPPED_LO], (unsigned)nskip);
+    G::fence();
+    G::atomic_add_u((unsigned *)&L.ctl[PIPL_PUSHED], 1u);
+  }
+  /* own rows */
+  for (int i = 0; i < keep; i++) {
+    pipl_update_row(L, red, lk[i], lf[i], lfoo[i], lden[i], prow, pivot, dpiv, pivj);
+    G::cta_sync();
+  }
+  /* overflow queue, once every CTA has published */
+  if (tid == 0) {
+    while ((int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_PUSHED], 0u) < ncta) G::relax();
+    red[62] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], 0u);
+  }
+  G::cta_sync();
+  G::fence();
+  const int nactive = red[62];
   for (;;) {
     G::cta_sync();
     if (tid == 0) red[63] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NEXT], 1u);
     G::cta_sync();
     const int idx = red[63];
     if (idx >= nactive) break;
-    const int k = L.active[idx];
+    const int k = G::load_int(&L.active[idx]);
     const int f = L.fl[k];
-    pip_i64 *row = pipl_row(L, PIP_LINK(f));
-    pip_i64 foo = row[pivj];
+    const pip_i64 foo = pipl_row(L, PIP_LINK(f))[pivj];
     const pip_i64 dk = L.den[k];
     G::cta_sync();                      /* every thread has read foo before pass 1 overwrites row[pivj] */
-    pip_i64 lpiv = pivot;
-    if (foo == 0) lpiv = 1;
-    else if (pivot != 1 && foo != 1 && foo != -1) {
-      const pip_i64 d = pip_gcd(pivot, foo);
-      if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
-    }
-    const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
-    const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
-    pip_u64 orz = 0;
-    /* pass 1: z = row*lpiv - prow*foo, 16-byte accesses, the whole CTA on one row */
-    const int pairs = ncol >> 1;
-    pip_i64x2 *row2 = (pip_i64x2 *)row;
-    const pip_i64x2 *prow2 = (const pip_i64x2 *)prow;
-    #pragma unroll 2
-    for (int q = tid; q < pairs; q += T) {
-      const pip_i64x2 a = row2[q], b = prow2[q];
-      pip_i64x2 z;
-      z.x = (pip_i64)((pip_u64)a.x * (pip_u64)lpiv - (pip_u64)b.x * (pip_u64)foo);
-      z.y = (pip_i64)((pip_u64)a.y * (pip_u64)lpiv - (pip_u64)b.y * (pip_u64)foo);
-      if (2 * q == pivj) z.x = zp;
-      if (2 * q + 1 == pivj) z.y = zp;
-      row2[q] = z;
-      orz |= (pip_u64)z.x | (pip_u64)z.y;
-    }
-    if ((ncol & 1) && tid == 0) {
-      const int j = ncol - 1;
-      pip_i64 z = (pip_i64)((pip_u64)row[j] * (pip_u64)lpiv - (pip_u64)prow[j] * (pip_u64)foo);
-      if (j == pivj) z = zp;
-      row[j] = z;
-      orz |= (pip_u64)z;
-    }
-    pip_i64 g = newden;
-    if (g != 1) {                        /* uniform over the CTA */
-      if ((g & (g - 1)) == 0 && g > 0) {
-        orz |= (pip_u64)g;
-        unsigned lo = W::redor((unsigned)orz), hi = W::redor((unsigned)(orz >> 32));
-        const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
-        G::cta_sync();
-        if (lane == 0) { red[2 * wid] = (int)lo; red[2 * wid + 1] = (int)hi; }
-        G::cta_sync();
-        lo = 0; hi = 0;
-        for (int i = 0; i < nw; i++) { lo |= (unsigned)red[2 * i]; hi |= (unsigned)red[2 * i + 1]; }
-        const pip_u64 all = ((pip_u64)hi << 32) | lo;
-        g = (pip_i64)(all & (0ull - all));
-      } else {
-        G::cta_sync();                   /* pass 1 stores visible */
-        for (int j = tid; j < ncol && g != 1; j += T) g = pip_gcd(g, row[j]);
-        for (int o = 16; o > 0; o >>= 1) g = pip_gcd(g, W::shfl_xor64(g, o));
-        const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
-        pip_i64 *red64 = (pip_i64 *)red;
-        G::cta_sync();
-        if (lane == 0) red64[wid] = g;
-        G::cta_sync();
-        g = red64[0];
-        for (int i = 1; i < nw; i++) g = pip_gcd(g, red64[i]);
-      }
-    }
-    pip_i64 nd = newden;
-    if (g != 1 && g != 0) {
-      G::cta_sync();
-      const PipExactDiv e = pip_exact_prepare(g);
-      for (int j = tid; j < ncol; j += T) row[j] = pip_exact_apply(row[j], e);
-      nd = pip_exact_apply(newden, e);
-    }
-    G::cta_sync();
-    if (tid == 0) {
-      L.den[k] = nd;
-      const pip_i64 c = row[nvar];
-      L.csign[k] = c < 0 ? -1 : c > 0 ? 1 : 0;
-      int ff = PIP_FLAG(f);
-      const int fff = zp < 0 ? PIP_MINUS : zp == 0 ? PIP_ZERO : PIP_PLUS;
-      if (fff != PIP_ZERO && fff != ff) {
-        if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
-        else ff = PIP_UNKNOWN;
-        L.fl[k] = PIP_MKFL(ff, PIP_LINK(f));
-      }
-      if (g == 0) L.ctl[PIPL_STATUS] = PIP_ST_FAULT;
-    }
+    pipl_update_row(L, red, k, f, foo, dk, prow, pivot, dpiv, pivj);
   }
 }
 

@@ -56,6 +56,9 @@ struct G {
   static inline void cta_sync() { pipemu::barrier(); }
   static inline void grid_sync() { pipemu::barrier(); }
   static inline unsigned atomic_add_u(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+  static inline void fence() {}
+  static inline void relax() {}
+  static inline int load_int(const int *p) { return *p; }
 };
 struct pip_i64x2 { long long x, y; };
 
@@ -115,6 +118,9 @@ struct G {
   static __device__ __forceinline__ void cta_sync() { __syncthreads(); }
   static __device__ void grid_sync();      /* cooperative groups, defined in pip_large.cu */
   static __device__ __forceinline__ unsigned atomic_add_u(unsigned *p, unsigned v) { return atomicAdd(p, v); }
+  static __device__ __forceinline__ void fence() { __threadfence(); }
+  static __device__ __forceinline__ void relax() { __nanosleep(32); }
+  static __device__ __forceinline__ int load_int(const int *p) { return __ldcg(p); }
 };
 struct __align__(16) pip_i64x2 { long long x, y; };
 

@@ -51,7 +51,7 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
 // ---- large-tableau solver in emulation: one CTA of one warp ---------------------------------
 #include "../../piplib_b200/csrc/pip_large.h"
 
-struct EmuLarge { PipLarge L; long long align_; int red[128]; };
+struct EmuLarge { PipLarge L; long long align_; int red[128 + 6 * PIPL_LCAP]; };
 static void large_entry(void *a, int) { EmuLarge *e = (EmuLarge *)a; pipl_solve(e->L, e->red); }
 
 extern "C" int pipemu_solve_large(int nvar, int ni, int nq, const pip_i64 *tab, int cut_rows, int sol_size,
