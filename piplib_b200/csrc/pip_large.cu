@@ -2,6 +2,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <stdexcept>
@@ -19,8 +20,9 @@ __device__ void G::grid_sync() { cg::this_grid().sync(); }
 
 __global__ void __launch_bounds__(PIPL_THREADS) pip_large_kernel(const PipLarge L)
 {
-  __shared__ __align__(16) int red[128 + 6 * PIPL_LCAP];
-  pipl_solve(L, red);
+  __shared__ __align__(16) int red[PIPL_RED_INTS];
+  extern __shared__ __align__(128) unsigned char pipl_dyn[];
+  pipl_solve(L, red, L.staged ? (pip_i64 *)pipl_dyn : nullptr);
 }
 
 /* restore the working tableau from the pristine copy and reset the control block */
@@ -44,6 +46,7 @@ struct pip_large_problem {
   size_t words = 0;
   int ni0 = 0;
   int grid = 0;
+  size_t dyn = 0;                 /* dynamic shared memory: staging buffers of the update phase */
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   std::vector<void *> allocs;
@@ -93,8 +96,13 @@ pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long
     CKL(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     CKL(cudaEventCreate(&P->e0));
     CKL(cudaEventCreate(&P->e1));
+    /* staged update (cp.async.bulk): the pivot row + one row per group of warps in shared memory */
+    P->dyn = (size_t)(PIPL_NG + 1) * L.stride * sizeof(pip_i64);
+    if (P->dyn > 200 * 1024 || getenv("PIPLIB_B200_NO_TMA")) P->dyn = 0;
+    L.staged = P->dyn ? 1 : 0;
+    if (P->dyn) CKL(cudaFuncSetAttribute(pip_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->dyn));
     int per_sm = 0;
-    CKL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pip_large_kernel, PIPL_THREADS, 0));
+    CKL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pip_large_kernel, PIPL_THREADS, P->dyn));
     if (per_sm < 1) per_sm = 1;
     P->grid = PipEngine::get().sm_count() * per_sm;
     return P;
@@ -113,7 +121,8 @@ int pip_large_run_dp(pip_large_problem *P, float *kernel_ms)
     CKL(cudaGetLastError());
     void *args[] = {(void *)&P->L};
     CKL(cudaEventRecord(P->e0, P->stream));
-    CKL(cudaLaunchCooperativeKernel((void *)pip_large_kernel, dim3(P->grid), dim3(PIPL_THREADS), args, 0, P->stream));
+    if (P->dyn) CKL(cudaFuncSetAttribute(pip_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->dyn));
+    CKL(cudaLaunchCooperativeKernel((void *)pip_large_kernel, dim3(P->grid), dim3(PIPL_THREADS), args, P->dyn, P->stream));
     CKL(cudaEventRecord(P->e1, P->stream));
     CKL(cudaStreamSynchronize(P->stream));
     if (kernel_ms) CKL(cudaEventElapsedTime(kernel_ms, P->e0, P->e1));

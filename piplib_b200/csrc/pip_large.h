@@ -26,12 +26,23 @@
 #if defined(PIPL_WALK_STATS) && defined(__CUDACC__)
 __device__ unsigned long long pipl_dbg[8];   /* diagnostic build only: walks, candidates, window steps / stops (CTA, warp) */
 #define PIPL_DBG(i, v) do { if (G::tid() == 0) pipl_dbg[i] += (unsigned long long)(v); } while (0)
+__device__ unsigned long long pipl_cdbg[8];  /* update-phase laps of CTA 0 */
+#define PIPL_CLAP(i) do { if (G::cta() == 0 && G::tid() == 0) { const long long n_ = pip_clock(); pipl_cdbg[i] += (unsigned long long)(n_ - clap); clap = n_; } } while (0)
+#define PIPL_CLAP_BEGIN long long clap = pip_clock()
 #else
+#define PIPL_CLAP(i) do { } while (0)
+#define PIPL_CLAP_BEGIN do { } while (0)
 #define PIPL_DBG(i, v) do { } while (0)
 #endif
 #define PIPL_K 8            /* candidates per thread kept in registers by the column walk */
-#define PIPL_KEEP 5          /* rows a CTA updates itself before it shares through the overflow queue */
-#define PIPL_LCAP 128        /* local list capacity of the update phase; red[] holds 128 + 6 * PIPL_LCAP ints */
+#ifndef PIPL_NG
+#define PIPL_NG 4            /* groups of warps per CTA in the update phase (one row per group at a time) */
+#endif
+#ifndef PIPL_KEEP
+#define PIPL_KEEP (2 * PIPL_NG)   /* rows a CTA updates itself before it shares through the overflow queue */
+#endif
+#define PIPL_LCAP 128        /* local list capacity of the update phase */
+#define PIPL_RED_INTS (128 + 6 * PIPL_LCAP + 64 * PIPL_NG + 2 * (PIPL_NG + 1))   /* shared scratch of the kernel, in ints */
 #define PIPL_AL 8           /* positions per thread per round of the active-row list */
 /* sub-phase timers of CTA 0 (thread 0): prof[2..7] = swap, row pick, column choice, determinant,
  * active-row list, spare */
@@ -40,6 +51,7 @@ __device__ unsigned long long pipl_dbg[8];   /* diagnostic build only: walks, ca
 struct PipLarge {
   /* problem */
   int nvar, ni, flags;            /* nparm = 0 */
+  int staged;                     /* rows go through shared memory (cp.async.bulk), see pipl_update_row_staged */
   int stride;                     /* words per slot (even) */
   int pcap, rcap;                 /* position / slot capacity */
   int sol_size, maxcol;
@@ -182,7 +194,10 @@ PIP_DEV void pipl_finish(const PipLarge &L, int status, int kind /*0 none, 1 nil
 #if defined(PIPL_WALK_STATS) && defined(__CUDACC__)
     printf("walk stats: walks %llu, candidates %llu, CTA path: window steps %llu stops %llu (candidates left after stops %llu); warp path: window steps %llu stops %llu\n",
            pipl_dbg[0], pipl_dbg[1], pipl_dbg[2], pipl_dbg[3], pipl_dbg[6], pipl_dbg[4], pipl_dbg[5]);
-    for (int i = 0; i < 8; i++) pipl_dbg[i] = 0;
+    printf("update phase, CTA 0, us per pivot: scan %.2f publish %.2f own rows %.2f wait %.2f overflow %.2f\n",
+           pipl_cdbg[0] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_cdbg[1] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_cdbg[2] / 1965.0 / L.ctl[PIPL_PIVOTS],
+           pipl_cdbg[3] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_cdbg[4] / 1965.0 / L.ctl[PIPL_PIVOTS]);
+    for (int i = 0; i < 8; i++) { pipl_dbg[i] = 0; pipl_cdbg[i] = 0; }
 #endif
   }
 }
@@ -795,10 +810,15 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
  * queue that the CTAs drain once everybody has published (ctl[PUSHED] == ncta).  No single-CTA list
  * phase, no atomic per row on the common path. */
 
-PIP_DEV void pipl_update_row(const PipLarge &L, int *red, int k, int f, pip_i64 foo, pip_i64 dk, const pip_i64 *prow,
+/* a group of warps of the CTA working on one row: group-local thread id, size, named barrier, scratch */
+struct PiplGroup { int tid, T, bar; int *red; };
+PIP_DEV void pipl_gsync(const PiplGroup &g) { G::group_sync(g.bar, g.T); }
+
+PIP_DEV void pipl_update_row(const PipLarge &L, const PiplGroup &grp, int k, int f, pip_i64 foo, pip_i64 dk, const pip_i64 *prow,
                              pip_i64 pivot, pip_i64 dpiv, int pivj)
 {
-  const int tid = G::tid(), T = G::T();
+  const int tid = grp.tid, T = grp.T;
+  int *red = grp.red;
   const int nvar = L.nvar, ncol = nvar + 1;
   pip_i64 *row = pipl_row(L, PIP_LINK(f));
   pip_i64 lpiv = pivot;
@@ -810,11 +830,11 @@ PIP_DEV void pipl_update_row(const PipLarge &L, int *red, int k, int f, pip_i64 
   const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
   const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
   pip_u64 orz = 0;
-  /* pass 1: z = row*lpiv - prow*foo, 16-byte accesses, the whole CTA on one row */
+  /* pass 1: z = row*lpiv - prow*foo, 16-byte accesses, the whole group on one row */
   const int pairs = ncol >> 1;
   pip_i64x2 *row2 = (pip_i64x2 *)row;
   const pip_i64x2 *prow2 = (const pip_i64x2 *)prow;
-  #pragma unroll 2
+  #pragma unroll 4
   for (int q = tid; q < pairs; q += T) {
     const pip_i64x2 a = row2[q], b = prow2[q];
     pip_i64x2 z;
@@ -833,39 +853,39 @@ PIP_DEV void pipl_update_row(const PipLarge &L, int *red, int k, int f, pip_i64 
     orz |= (pip_u64)z;
   }
   pip_i64 g = newden;
-  if (g != 1) {                        /* uniform over the CTA */
+  if (g != 1) {                        /* uniform over the group */
     if ((g & (g - 1)) == 0 && g > 0) {
       orz |= (pip_u64)g;
       unsigned lo = W::redor((unsigned)orz), hi = W::redor((unsigned)(orz >> 32));
       const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
-      G::cta_sync();
+      pipl_gsync(grp);
       if (lane == 0) { red[2 * wid] = (int)lo; red[2 * wid + 1] = (int)hi; }
-      G::cta_sync();
+      pipl_gsync(grp);
       lo = 0; hi = 0;
       for (int i = 0; i < nw; i++) { lo |= (unsigned)red[2 * i]; hi |= (unsigned)red[2 * i + 1]; }
       const pip_u64 all = ((pip_u64)hi << 32) | lo;
       g = (pip_i64)(all & (0ull - all));
     } else {
-      G::cta_sync();                   /* pass 1 stores visible */
+      pipl_gsync(grp);                 /* pass 1 stores visible */
       for (int j = tid; j < ncol && g != 1; j += T) g = pip_gcd(g, row[j]);
       for (int o = 16; o > 0; o >>= 1) g = pip_gcd(g, W::shfl_xor64(g, o));
       const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
       pip_i64 *red64 = (pip_i64 *)red;
-      G::cta_sync();
+      pipl_gsync(grp);
       if (lane == 0) red64[wid] = g;
-      G::cta_sync();
+      pipl_gsync(grp);
       g = red64[0];
       for (int i = 1; i < nw; i++) g = pip_gcd(g, red64[i]);
     }
   }
   pip_i64 nd = newden;
   if (g != 1 && g != 0) {
-    G::cta_sync();
+    pipl_gsync(grp);
     const PipExactDiv e = pip_exact_prepare(g);
     for (int j = tid; j < ncol; j += T) row[j] = pip_exact_apply(row[j], e);
     nd = pip_exact_apply(newden, e);
   }
-  G::cta_sync();
+  pipl_gsync(grp);
   if (tid == 0) {
     L.den[k] = nd;
     const pip_i64 c = row[nvar];
@@ -881,7 +901,105 @@ PIP_DEV void pipl_update_row(const PipLarge &L, int *red, int k, int f, pip_i64 
   }
 }
 
-PIP_DEV void pipl_phase_c(const PipLarge &L, int *red)
+/* The same update with the row staged in shared memory by the TMA engine (cp.async.bulk, one
+ * instruction for the whole 32 KB row: every byte of the row is in flight at once, which no number of
+ * per-thread 16-byte loads reaches at 124 registers per thread).  `srow` receives the row, `sprow` holds
+ * the pivot row (staged once per pivot and CTA).  A row that needs no normalisation is written
+ * straight to global memory; otherwise z stays in shared memory until its gcd is known, so every row
+ * is read once and written once. */
+PIP_DEV void pipl_update_row_staged(const PipLarge &L, const PiplGroup &grp, int k, int f, pip_i64 foo, pip_i64 dk,
+                                    const pip_i64 *sprow, pip_i64 *srow, unsigned long long *mbar, unsigned &parity,
+                                    pip_i64 pivot, pip_i64 dpiv, int pivj)
+{
+  const int tid = grp.tid, T = grp.T;
+  int *red = grp.red;
+  const int nvar = L.nvar, ncol = nvar + 1;
+  pip_i64 *row = pipl_row(L, PIP_LINK(f));
+  if (tid == 0) { G::proxy_fence(); G::bulk_g2s(srow, row, (unsigned)(L.stride * sizeof(pip_i64)), mbar); }
+  pip_i64 lpiv = pivot;
+  if (foo == 0) lpiv = 1;
+  else if (pivot != 1 && foo != 1 && foo != -1) {
+    const pip_i64 d = pip_gcd(pivot, foo);
+    if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
+  }
+  const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
+  const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
+  const bool direct = newden == 1;             /* nothing to normalise: z goes straight to global memory */
+  G::mbar_wait(mbar, parity);
+  parity ^= 1u;
+  pip_u64 orz = 0;
+  const int pairs = L.stride >> 1;             /* the padding word of an odd row is computed too (0 * x - 0 * y) */
+  pip_i64x2 *row2 = (pip_i64x2 *)row, *srow2 = (pip_i64x2 *)srow;
+  const pip_i64x2 *sprow2 = (const pip_i64x2 *)sprow;
+  #pragma unroll 4
+  for (int q = tid; q < pairs; q += T) {
+    const pip_i64x2 a = srow2[q], b = sprow2[q];
+    pip_i64x2 z;
+    z.x = (pip_i64)((pip_u64)a.x * (pip_u64)lpiv - (pip_u64)b.x * (pip_u64)foo);
+    z.y = (pip_i64)((pip_u64)a.y * (pip_u64)lpiv - (pip_u64)b.y * (pip_u64)foo);
+    if (2 * q == pivj) z.x = zp;
+    if (2 * q + 1 == pivj) z.y = zp;
+    if (2 * q >= ncol) z.x = a.x;
+    if (2 * q + 1 >= ncol) z.y = a.y;
+    if (direct) row2[q] = z; else srow2[q] = z;
+    if ((nvar >> 1) == q) { const pip_i64 c = (nvar & 1) ? z.y : z.x; red[60] = c < 0 ? -1 : c > 0 ? 1 : 0; }
+    if (2 * q < ncol) orz |= (pip_u64)z.x;
+    if (2 * q + 1 < ncol) orz |= (pip_u64)z.y;
+  }
+  pip_i64 g = newden, nd = newden;
+  if (!direct) {
+    if ((g & (g - 1)) == 0 && g > 0) {
+      orz |= (pip_u64)g;
+      unsigned lo = W::redor((unsigned)orz), hi = W::redor((unsigned)(orz >> 32));
+      const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+      pipl_gsync(grp);
+      if (lane == 0) { red[2 * wid] = (int)lo; red[2 * wid + 1] = (int)hi; }
+      pipl_gsync(grp);
+      lo = 0; hi = 0;
+      for (int i = 0; i < nw; i++) { lo |= (unsigned)red[2 * i]; hi |= (unsigned)red[2 * i + 1]; }
+      const pip_u64 all = ((pip_u64)hi << 32) | lo;
+      g = (pip_i64)(all & (0ull - all));
+    } else {
+      pipl_gsync(grp);                 /* pass 1 stores visible */
+      for (int j = tid; j < ncol && g != 1; j += T) g = pip_gcd(g, srow[j]);
+      for (int o = 16; o > 0; o >>= 1) g = pip_gcd(g, W::shfl_xor64(g, o));
+      const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+      pip_i64 *red64 = (pip_i64 *)red;
+      pipl_gsync(grp);
+      if (lane == 0) red64[wid] = g;
+      pipl_gsync(grp);
+      g = red64[0];
+      for (int i = 1; i < nw; i++) g = pip_gcd(g, red64[i]);
+    }
+    if (g != 1 && g != 0) {
+      const PipExactDiv e = pip_exact_prepare(g);
+      for (int q = tid; q < pairs; q += T) {
+        pip_i64x2 z = srow2[q];
+        if (2 * q < ncol) z.x = pip_exact_apply(z.x, e);
+        if (2 * q + 1 < ncol) z.y = pip_exact_apply(z.y, e);
+        row2[q] = z;
+      }
+      nd = pip_exact_apply(newden, e);
+    } else {
+      for (int q = tid; q < pairs; q += T) row2[q] = srow2[q];
+    }
+  }
+  pipl_gsync(grp);                     /* red[60] and every read of the staging buffer are done */
+  if (tid == 0) {
+    L.den[k] = nd;
+    L.csign[k] = (signed char)red[60];  /* the sign of the constant does not change with the division by g > 0 */
+    int ff = PIP_FLAG(f);
+    const int fff = zp < 0 ? PIP_MINUS : zp == 0 ? PIP_ZERO : PIP_PLUS;
+    if (fff != PIP_ZERO && fff != ff) {
+      if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
+      else ff = PIP_UNKNOWN;
+      L.fl[k] = PIP_MKFL(ff, PIP_LINK(f));
+    }
+    if (g == 0) L.ctl[PIPL_STATUS] = PIP_ST_FAULT;
+  }
+}
+
+PIP_DEV void pipl_phase_c(const PipLarge &L, int *red, pip_i64 *stage, unsigned &par_prow, unsigned &par_row)
 {
   const int tid = G::tid(), T = G::T(), cta = G::cta(), ncta = G::ncta();
   const int nl = L.nvar + L.ctl[PIPL_NI];
@@ -890,7 +1008,13 @@ PIP_DEV void pipl_phase_c(const PipLarge &L, int *red)
   const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
   int *lcnt = red + 127, *lk = red + 128, *lf = red + 128 + PIPL_LCAP;
   pip_i64 *lfoo = (pip_i64 *)(red + 128 + 2 * PIPL_LCAP), *lden = lfoo + PIPL_LCAP;
-  if (tid == 0) *lcnt = 0;
+  PIPL_CLAP_BEGIN;
+  /* staged mode: mbarriers behind the group scratch, buffers = pivot row + one row per group */
+  unsigned long long *mbar = (unsigned long long *)(red + 128 + 6 * PIPL_LCAP + 64 * PIPL_NG);
+  if (tid == 0) {
+    *lcnt = 0;
+    if (stage) { G::proxy_fence(); G::bulk_g2s(stage, prow, (unsigned)(L.stride * sizeof(pip_i64)), mbar); }
+  }
   G::cta_sync();
   /* scan the stripe: every load of a position is issued by its own thread, one round trip in all */
   int nskip = 0;
@@ -905,6 +1029,7 @@ PIP_DEV void pipl_phase_c(const PipLarge &L, int *red)
     else L.active[G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], 1u)] = p;     /* never on sane grids */
   }
   nskip = pipl_cta_sum(nskip, red);                /* also orders the list stores before the reads */
+  PIPL_CLAP(0);
   int nloc = *lcnt < PIPL_LCAP ? *lcnt : PIPL_LCAP;
   const int keep = nloc < PIPL_KEEP ? nloc : PIPL_KEEP;
   /* publish the left-overs, then tell the grid this CTA has nothing more to add */
@@ -920,43 +1045,64 @@ PIP_DEV void pipl_phase_c(const PipLarge &L, int *red)
     G::fence();
     G::atomic_add_u((unsigned *)&L.ctl[PIPL_PUSHED], 1u);
   }
+  PIPL_CLAP(1);
+  /* the CTA splits into PIPL_NG groups of warps, one row per group at a time (a row is 32 KB: its
+   * update is one load round trip, so rows in flight are what fills the memory pipes) */
+  const int ng = T >= 32 * PIPL_NG ? PIPL_NG : 1;
+  PiplGroup grp;
+  grp.T = T / ng;
+  const int gid = tid / grp.T;
+  grp.tid = tid - gid * grp.T; grp.bar = 1 + gid; grp.red = red + 128 + 6 * PIPL_LCAP + 64 * gid;
+  pip_i64 *srow = stage ? stage + (pip_i64)(1 + gid) * L.stride : nullptr;
+  if (stage) { G::mbar_wait(mbar, par_prow); par_prow ^= 1u; }
   /* own rows */
-  for (int i = 0; i < keep; i++) {
-    pipl_update_row(L, red, lk[i], lf[i], lfoo[i], lden[i], prow, pivot, dpiv, pivj);
-    G::cta_sync();
+  for (int i = gid; i < keep; i += ng) {
+    if (stage) pipl_update_row_staged(L, grp, lk[i], lf[i], lfoo[i], lden[i], stage, srow, mbar + 1 + gid, par_row, pivot, dpiv, pivj);
+    else pipl_update_row(L, grp, lk[i], lf[i], lfoo[i], lden[i], prow, pivot, dpiv, pivj);
+    pipl_gsync(grp);
   }
+  PIPL_CLAP(2);
   /* overflow queue, once every CTA has published */
-  if (tid == 0) {
+  if (grp.tid == 0) {
     while ((int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_PUSHED], 0u) < ncta) G::relax();
-    red[62] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], 0u);
+    grp.red[62] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], 0u);
   }
-  G::cta_sync();
+  pipl_gsync(grp);
   G::fence();
-  const int nactive = red[62];
+  PIPL_CLAP(3);
+  const int nactive = grp.red[62];
   for (;;) {
-    G::cta_sync();
-    if (tid == 0) red[63] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NEXT], 1u);
-    G::cta_sync();
-    const int idx = red[63];
+    pipl_gsync(grp);
+    if (grp.tid == 0) grp.red[63] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NEXT], 1u);
+    pipl_gsync(grp);
+    const int idx = grp.red[63];
     if (idx >= nactive) break;
     const int k = G::load_int(&L.active[idx]);
     const int f = L.fl[k];
     const pip_i64 foo = pipl_row(L, PIP_LINK(f))[pivj];
     const pip_i64 dk = L.den[k];
-    G::cta_sync();                      /* every thread has read foo before pass 1 overwrites row[pivj] */
-    pipl_update_row(L, red, k, f, foo, dk, prow, pivot, dpiv, pivj);
+    pipl_gsync(grp);                    /* every thread has read foo before pass 1 overwrites row[pivj] */
+    if (stage) pipl_update_row_staged(L, grp, k, f, foo, dk, stage, srow, mbar + 1 + gid, par_row, pivot, dpiv, pivj);
+    else pipl_update_row(L, grp, k, f, foo, dk, prow, pivot, dpiv, pivj);
   }
+  G::cta_sync();
+  PIPL_CLAP(4);
 }
 
 /* ---- the whole solve (called by every thread of the cooperative grid) ------------------------ */
 PIP_DEV void pipl_init_rows(const PipLarge &L, float *sz);
 PIP_DEV void pipl_sort(const PipLarge &L, float *sz, int *red);
 
-PIP_DEV void pipl_solve(const PipLarge &L, int *red)
+PIP_DEV void pipl_solve(const PipLarge &L, int *red, pip_i64 *stage = nullptr)
 {
-  unsigned skipped = 0;
+  unsigned skipped = 0, par_prow = 0, par_row = 0;
   bool first = true;
   float *sz = (float *)L.cand;                 /* scratch: pcap floats fit (cand has pcap ints) */
+  if (stage) {
+    unsigned long long *mbar = (unsigned long long *)(red + 128 + 6 * PIPL_LCAP + 64 * PIPL_NG);
+    if (G::tid() == 0) { for (int i = 0; i <= PIPL_NG; i++) G::mbar_init(mbar + i, 1); G::proxy_fence(); }
+    G::cta_sync();
+  }
   pipl_init_rows(L, sz);
   G::grid_sync();
   if (G::cta() == 0) pipl_sort(L, sz, red);
@@ -967,7 +1113,7 @@ PIP_DEV void pipl_solve(const PipLarge &L, int *red)
     G::grid_sync();
     const long long t1 = pip_clock();
     if (L.ctl[PIPL_ACTION] == PIPL_STOP) break;
-    pipl_phase_c(L, red);
+    pipl_phase_c(L, red, stage, par_prow, par_row);
     G::grid_sync();
     const long long t2 = pip_clock();
     if (G::cta() == 0 && G::tid() == 0) { L.prof[0] += (unsigned long long)(t1 - t0); L.prof[1] += (unsigned long long)(t2 - t1); }

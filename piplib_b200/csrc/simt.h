@@ -56,6 +56,13 @@ struct G {
   static inline void cta_sync() { pipemu::barrier(); }
   static inline void grid_sync() { pipemu::barrier(); }
   static inline unsigned atomic_add_u(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+  static inline void group_sync(int, int) { pipemu::barrier(); }
+  /* bulk (TMA) copy global -> shared signalled on an mbarrier: in emulation a memcpy by the issuing
+   * fiber, the wait is a rendezvous of the warp */
+  static inline void mbar_init(unsigned long long *, int) {}
+  static inline void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *) { __builtin_memcpy(dst, src, bytes); }
+  static inline void mbar_wait(unsigned long long *, unsigned) { pipemu::barrier(); }
+  static inline void proxy_fence() {}
   static inline void fence() {}
   static inline void relax() {}
   static inline int load_int(const int *p) { return *p; }
@@ -118,7 +125,30 @@ struct G {
   static __device__ __forceinline__ void cta_sync() { __syncthreads(); }
   static __device__ void grid_sync();      /* cooperative groups, defined in pip_large.cu */
   static __device__ __forceinline__ unsigned atomic_add_u(unsigned *p, unsigned v) { return atomicAdd(p, v); }
+  static __device__ __forceinline__ void group_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
   static __device__ __forceinline__ void fence() { __threadfence(); }
+  /* cp.async.bulk (the TMA engine's 1-D copy) global -> shared, completion counted in bytes on an mbarrier */
+  static __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  }
+  static __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+  {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+  }
+  static __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+  {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    } while (!ok);
+  }
+  static __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
   static __device__ __forceinline__ void relax() { __nanosleep(32); }
   static __device__ __forceinline__ int load_int(const int *p) { return __ldcg(p); }
 };

@@ -37,7 +37,7 @@ def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_le
     return out
 
 
-def solve_large(case, cut_rows=64, sol_size=0, maxcol=0, order_mode=0):
+def solve_large(case, cut_rows=64, sol_size=0, maxcol=0, order_mode=0, staged=0):
     """one non-parametric problem through the grid-per-problem code path (one emulated CTA)"""
     assert case["nparm"] == 0
     lib = C.CDLL(SO)
@@ -46,6 +46,7 @@ def solve_large(case, cut_rows=64, sol_size=0, maxcol=0, order_mode=0):
     cells = np.zeros(cap, dtype=CELL_DTYPE)
     st, nc = C.c_int(0), C.c_int(0)
     info = (C.c_longlong * 4)()
+    lib.pipemu_large_staged(staged)
     lib.pipemu_solve_large(case["nvar"], case["ni"], case["nq"], tab.ctypes.data_as(C.c_void_p), cut_rows,
                            sol_size, maxcol, C.byref(st), cells.ctypes.data_as(C.c_void_p), C.byref(nc),
                            info, order_mode)

@@ -51,8 +51,11 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
 // ---- large-tableau solver in emulation: one CTA of one warp ---------------------------------
 #include "../../piplib_b200/csrc/pip_large.h"
 
-struct EmuLarge { PipLarge L; long long align_; int red[128 + 6 * PIPL_LCAP]; };
-static void large_entry(void *a, int) { EmuLarge *e = (EmuLarge *)a; pipl_solve(e->L, e->red); }
+struct EmuLarge { PipLarge L; long long align_; int red[PIPL_RED_INTS]; pip_i64 *stage; };
+static void large_entry(void *a, int) { EmuLarge *e = (EmuLarge *)a; pipl_solve(e->L, e->red, e->stage); }
+
+static int g_large_staged = 0;
+extern "C" void pipemu_large_staged(int on) { g_large_staged = on; }
 
 extern "C" int pipemu_solve_large(int nvar, int ni, int nq, const pip_i64 *tab, int cut_rows, int sol_size,
                                   int maxcol, int *status, PipCell *cells, int *ncells, long long *info,
@@ -85,8 +88,12 @@ extern "C" int pipemu_solve_large(int nvar, int ni, int nq, const pip_i64 *tab, 
   L.cells = cells;
   unsigned long long prof[16] = {0};
   L.prof = prof;
+  // the staged (TMA) form of the row update or the direct one (pipemu_large_staged)
+  e.stage = g_large_staged ? (pip_i64 *)calloc((size_t)(PIPL_NG + 1) * L.stride, 8) : nullptr;
+  L.staged = e.stage ? 1 : 0;
   pipemu::set_order(order_mode);
   pipemu::run_warp(large_entry, &e);
+  free(e.stage);
   *status = ctl[PIPL_STATUS];
   *ncells = ctl[PIPL_NCELL];
   if (info) { info[0] = ctl[PIPL_PIVOTS]; info[1] = ctl[PIPL_CUTS]; info[2] = (unsigned)ctl[PIPL_SKIPPED_LO]; info[3] = ctl[PIPL_NI]; }

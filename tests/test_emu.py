@@ -58,7 +58,8 @@ def test_capacity_escalation_is_reported():
     assert st == 4001 and cells == []
 
 
-def test_large_tableau_path_on_nonparametric_fixtures():
+@pytest.mark.parametrize("staged", [0, 1])
+def test_large_tableau_path_on_nonparametric_fixtures(staged):
     """the grid-per-problem code path (pip_large.h, here one emulated CTA) on every non-parametric
     fixture incl. vivien32 (260 cuts) and the random tableaus: same cells as the reference"""
     cases = [c for c in load_golden("cli_suite.json")
@@ -66,19 +67,20 @@ def test_large_tableau_path_on_nonparametric_fixtures():
     cases += [c for c in RCLI if c["nparm"] == 0 and c["nc"] == 0]
     bad = []
     for c in cases:
-        st, cells, info = emu.solve_large(c, cut_rows=400, order_mode=2)
+        st, cells, info = emu.solve_large(c, cut_rows=400, order_mode=2, staged=staged)
         if st != c["ref_status"] or cells != c["ref_cells"]:
             bad.append(c["name"])
     assert len(cases) > 100 and not bad, bad
 
 
-def test_large_tableau_consecutive_ones_vs_oracle(port):
+@pytest.mark.parametrize("staged", [0, 1])
+def test_large_tableau_consecutive_ones_vs_oracle(port, staged):
     from piplib_b200 import synth
     nvar = 96
     tab = synth.consecutive_ones(nvar, nvar, seed=3)
     case = dict(nvar=nvar, nparm=0, ni=nvar, nc=0, bigparm=-1, nq=1, tab=tab.tolist(), ctx=[])
     st_o, cells_o = port.traiter(nvar, 0, nvar, 0, -1, 1, tab, [])
-    st, cells, info = emu.solve_large(case, cut_rows=64)
+    st, cells, info = emu.solve_large(case, cut_rows=64, staged=staged)
     assert st == st_o and [tuple(x) for x in cells] == cells_o and info[0] > 0
 
 
