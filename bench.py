@@ -168,12 +168,20 @@ def large_tableau_line(pk, pk_src, n=4096, reps=2):
     R, C = n - 1, n + 1
     alg = (16.0 * R * C + 8.0 * C + 8.0 * R) * piv
     ach = alg / (ms / 1e3) / 1e9
+    traffic = None            # DRAM bytes per launch from the committed ncu --set full capture (same n, same seed)
+    tj = os.path.join(ROOT, "profiles", "r1_large_kernel_traffic.json")
+    if os.path.exists(tj):
+        t = json.load(open(tj))
+        if t.get("n") == n and t.get("pivots") == info["pivots"]:
+            traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
     return {"workload": "consecutive-ones %d x %d int64, Nq=1, one problem over the whole grid" % (n, n + 1),
             "status": st, "pivots": info["pivots"], "kernel_ms": ms, "us_per_pivot": 1e3 * ms / piv,
             "pivots_per_sec": piv / (ms / 1e3),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / pk["hbm_gbs"], "peak_source": pk_src, "traffic": None,
-                         "note": "dense algorithmic figure; identity row updates are skipped, see profiles/"}}
+                         "frac": ach / pk["hbm_gbs"], "peak_source": pk_src, "traffic": traffic,
+                         "algorithmic_bytes": alg,
+                         "note": "dense algorithmic figure 16*R*C+8*C+8*R per pivot; rows whose update is the identity "
+                                 "are skipped, so DRAM traffic is far below it (profiles/r1_large_kernel_traffic.json)"}}
 
 
 # ------------------------------------------------------------------------------------------

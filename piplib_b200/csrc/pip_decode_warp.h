@@ -116,7 +116,7 @@ PIP_DEV void pip_wser_vector(PipWarpSer &s, const C &c, int &i, int Bg, int Urs_
         const pip_i64 D = c.p2(i + 1 + j);
         const pip_i64 d = (D == 1) ? 1 : pip_gcd(N, D);
         if ((flags & PIP_SOL_SHIFT) && j == Bg) N -= D;
-        pip_i64 num = d ? pip_div(N, d) : 0;
+        pip_i64 num = d == 1 ? N : (d ? pip_div(N, d) : 0);       /* the 64-bit division is a call: not for d = 1 */
         if (flags & PIP_SOL_NEGATE) num = -num;
         s.tile[base + 1 + 2 * k] = num;
         s.tile[base + 2 + 2 * k] = unbounded ? 0 : ((d == D) ? 1 : (d ? pip_div(D, d) : 0));

@@ -21,6 +21,10 @@
 #include <thread>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 #include "../../include/piplib_b200.h"
 #include "pip_decode.h"
 #include "pip_engine.h"
@@ -825,8 +829,28 @@ void plan_chunk(const DenseArgs &A, DenseChunk &C, size_t nthreads)
   C.elem_log2 = 3;
 }
 
+/* Optimistic plan without a pass over the inputs: every problem of a dense batch has the same
+ * dimensions and options, so unless the number of equality rows varies (each becomes two tableau
+ * rows, source/tab.c:327-337) every problem has the shape of the first one and offsets are
+ * arithmetic.  convert_chunk_t checks the assumption problem by problem while the rows are in the
+ * cache anyway and reports a mismatch; the caller then falls back to plan_chunk. */
+void plan_chunk_uniform(const DenseArgs &A, DenseChunk &C)
+{
+  const size_t n = C.n, g = C.first;
+  MatView d = {A.dr, A.dc, nullptr, A.dom + g * A.dr * A.dc};
+  MatView c = {A.cr, A.cc, nullptr, A.has_ctx ? A.ctx + g * A.cr * A.cc : nullptr};
+  const Shape s0 = derive_shape(d, A.has_ctx ? &c : nullptr, A.bignum, A.opt);
+  const size_t w0 = problem_words(s0);
+  C.shapes.assign(n, s0);
+  C.prob.resize(n);
+  C.off.resize(n + 1);
+  for (size_t i = 0; i <= n; i++) C.off[i] = i * w0;
+  C.pool_elems = C.off[n];
+  C.elem_log2 = 3;
+}
+
 template <class T>
-bool convert_chunk_t(const DenseArgs &A, DenseChunk &C, T *pool, size_t nthreads)
+bool convert_chunk_t(const DenseArgs &A, DenseChunk &C, T *pool, size_t nthreads, std::atomic<int> *mismatch)
 {
   std::vector<char> ok(nthreads + 1, 1);
   parallel_ranges(C.n, nthreads, [&](size_t t, size_t a, size_t b) {
@@ -835,6 +859,10 @@ bool convert_chunk_t(const DenseArgs &A, DenseChunk &C, T *pool, size_t nthreads
       const size_t g = C.first + i;
       MatView d = {A.dr, A.dc, nullptr, A.dom + g * A.dr * A.dc};
       MatView c = {A.cr, A.cc, nullptr, A.has_ctx ? A.ctx + g * A.cr * A.cc : nullptr};
+      if (mismatch) {
+        const Shape si = derive_shape(d, A.has_ctx ? &c : nullptr, A.bignum, A.opt);
+        if (si.Nl != C.shapes[i].Nl || si.Nm != C.shapes[i].Nm) { mismatch->store(1); break; }
+      }
       good = fill_problem(d, A.has_ctx ? &c : nullptr, C.shapes[i], C.prob[i], pool, C.off[i]) && good;
     }
     ok[t] = good;
@@ -844,15 +872,17 @@ bool convert_chunk_t(const DenseArgs &A, DenseChunk &C, T *pool, size_t nthreads
 }
 /* Convert a chunk into the pinned staging area of `E`, trying the narrowest element first
  * (int8, then int32, then int64); `hint` remembers the width that worked for earlier chunks. */
-void *convert_chunk(const DenseArgs &A, DenseChunk &C, PipEngine &E, size_t nthreads, std::atomic<int> *hint)
+void *convert_chunk(const DenseArgs &A, DenseChunk &C, PipEngine &E, size_t nthreads, std::atomic<int> *hint,
+                    std::atomic<int> *mismatch = nullptr)
 {
   int start = hint ? hint->load() : 0;
   void *pool = E.pinned_input((C.pool_elems + 8) << 3);
   for (int w = start;; w = (w == 0 ? 2 : 3)) {
     bool ok;
-    if (w == 0) ok = convert_chunk_t(A, C, (signed char *)pool, nthreads);
-    else if (w == 2) ok = convert_chunk_t(A, C, (int *)pool, nthreads);
-    else ok = convert_chunk_t(A, C, (I *)pool, nthreads);
+    if (w == 0) ok = convert_chunk_t(A, C, (signed char *)pool, nthreads, mismatch);
+    else if (w == 2) ok = convert_chunk_t(A, C, (int *)pool, nthreads, mismatch);
+    else ok = convert_chunk_t(A, C, (I *)pool, nthreads, mismatch);
+    if (mismatch && mismatch->load()) return pool;
     if (ok || w == 3) {
       C.elem_log2 = w;
       if (hint && w > hint->load()) hint->store(w);
@@ -995,12 +1025,21 @@ void emit_chunk_ser(DenseChunk &C, int *status, unsigned long long *hashes, long
         if (fits && r.ser_words) {
           I *dst = ser + base + C.words[i];
           if (r.rflags & PIP_RES_SER32) {
+            /* the caller's stream is write-only here and far larger than the caches: streaming stores,
+             * so that widening 1.6 GB of int32 words does not first read 3.2 GB of destination lines */
             const int *src = (const int *)(C.out.base[i] + r.cell_off);
+#if defined(__x86_64__)
+            for (unsigned k = 0; k < r.ser_words; k++) _mm_stream_si64((long long *)dst + k, (long long)src[k]);
+#else
             for (unsigned k = 0; k < r.ser_words; k++) dst[k] = src[k];
+#endif
           } else memcpy(dst, C.out.base[i] + r.cell_off, sizeof(I) * r.ser_words);
         }
       }
     }
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
   });
 }
 
@@ -1056,6 +1095,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     std::vector<std::string> errors(lanes);
     std::atomic<long long> cursor(0);
     std::atomic<int> width_hint(0);
+    std::atomic<int> uniform_hint(getenv("PIPLIB_B200_EXACT_PLAN") ? 0 : 1);
     const bool timing = getenv("PIPLIB_B200_TIMING") != nullptr;
     /* decode on the GPU unless the host-only Simplify post-pass is wanted (PIPLIB_B200_HOST_DECODE=1
      * forces the host decoder, for A/B tests) */
@@ -1071,9 +1111,16 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
           DenseChunk &C = chunks[lane];
           C.first = firsts[c]; C.n = sizes[c];
           double ta = wall();
-          plan_chunk(A, C, nthreads);
+          const bool optimistic = uniform_hint.load() != 0;
+          if (optimistic) plan_chunk_uniform(A, C); else plan_chunk(A, C, nthreads);
           double tb = wall();
-          void *pool = convert_chunk(A, C, E, nthreads, &width_hint);
+          std::atomic<int> mismatch(0);
+          void *pool = convert_chunk(A, C, E, nthreads, &width_hint, optimistic ? &mismatch : nullptr);
+          if (mismatch.load()) {            /* the number of equality rows varies: exact plan, convert again */
+            uniform_hint.store(0);
+            plan_chunk(A, C, nthreads);
+            pool = convert_chunk(A, C, E, nthreads, &width_hint);
+          }
           double tc = wall();
           tstage[lane * 4 + 0] += tb - ta; tstage[lane * 4 + 1] += tc - tb;
           PipBatchIn in;

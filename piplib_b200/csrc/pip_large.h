@@ -29,7 +29,12 @@ __device__ unsigned long long pipl_dbg[8];   /* diagnostic build only: walks, ca
 __device__ unsigned long long pipl_cdbg[8];  /* update-phase laps of CTA 0 */
 #define PIPL_CLAP(i) do { if (G::cta() == 0 && G::tid() == 0) { const long long n_ = pip_clock(); pipl_cdbg[i] += (unsigned long long)(n_ - clap); clap = n_; } } while (0)
 #define PIPL_CLAP_BEGIN long long clap = pip_clock()
+__device__ unsigned long long pipl_adbg[16];  /* choice-phase laps of CTA 0 */
+#define PIPL_ALAP(i) do { if (G::tid() == 0) { const long long n_ = pip_clock(); pipl_adbg[i] += (unsigned long long)(n_ - alap); alap = n_; } } while (0)
+#define PIPL_ALAP_BEGIN long long alap = pip_clock()
 #else
+#define PIPL_ALAP(i) do { } while (0)
+#define PIPL_ALAP_BEGIN do { } while (0)
 #define PIPL_CLAP(i) do { } while (0)
 #define PIPL_CLAP_BEGIN do { } while (0)
 #define PIPL_DBG(i, v) do { } while (0)
@@ -41,6 +46,7 @@ __device__ unsigned long long pipl_cdbg[8];  /* update-phase laps of CTA 0 */
 #ifndef PIPL_KEEP
 #define PIPL_KEEP (2 * PIPL_NG)   /* rows a CTA updates itself before it shares through the overflow queue */
 #endif
+#define PIPL_RP 16           /* positions per thread per round of the row-pick sweep */
 #define PIPL_LCAP 128        /* local list capacity of the update phase */
 #define PIPL_RED_INTS (128 + 6 * PIPL_LCAP + 64 * PIPL_NG + 2 * (PIPL_NG + 1))   /* shared scratch of the kernel, in ints */
 #define PIPL_AL 8           /* positions per thread per round of the active-row list */
@@ -115,14 +121,16 @@ PIP_DEV int pipl_ratio_cmp(pip_i64 a, pip_i64 b, pip_i64 c, pip_i64 d)
 
 /* the next PIPL_WIN stored (non-Unit) positions at or after k, in order (PIPL_INF-padded); every
  * thread computes the same list from the bitmap */
-#define PIPL_WIN 8
-PIP_DEV void pipl_window(const PipLarge &L, int k, int nl, int nwords, int *wp)
+#ifndef PIPL_WIN
+#define PIPL_WIN 4            /* measured on B200, 4096 x 4097: 4 rows per step 41.6 us per pivot, 3: 43.3, 8: 44.0, 2: 46.3, 16: 49.9 */
+#endif
+PIP_DEV void pipl_window(const unsigned *sb, int k, int nl, int nwords, int *wp)
 {
   int w = k >> 5;
-  unsigned bits = w < nwords ? (L.sbits[w] & (~0u << (k & 31))) : 0u;
+  unsigned bits = w < nwords ? (sb[w] & (~0u << (k & 31))) : 0u;
   #pragma unroll
   for (int b = 0; b < PIPL_WIN; b++) {
-    while (!bits && w + 1 < nwords) { w++; bits = L.sbits[w]; }
+    while (!bits && w + 1 < nwords) { w++; bits = sb[w]; }
     if (bits) {
       const int pp = (w << 5) + pip_ffs(bits) - 1;
       bits &= bits - 1;
@@ -197,13 +205,18 @@ PIP_DEV void pipl_finish(const PipLarge &L, int status, int kind /*0 none, 1 nil
     printf("update phase, CTA 0, us per pivot: scan %.2f publish %.2f own rows %.2f wait %.2f overflow %.2f\n",
            pipl_cdbg[0] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_cdbg[1] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_cdbg[2] / 1965.0 / L.ctl[PIPL_PIVOTS],
            pipl_cdbg[3] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_cdbg[4] / 1965.0 / L.ctl[PIPL_PIVOTS]);
+    printf("choice phase, us per pivot: sweep %.2f reduce %.2f reflag %.2f | prow scan %.2f registers %.2f CTA walk %.2f warp finish %.2f (other %.2f)\n",
+           pipl_adbg[0] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_adbg[1] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_adbg[2] / 1965.0 / L.ctl[PIPL_PIVOTS],
+           pipl_adbg[4] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_adbg[5] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_adbg[6] / 1965.0 / L.ctl[PIPL_PIVOTS],
+           pipl_adbg[7] / 1965.0 / L.ctl[PIPL_PIVOTS], pipl_adbg[3] / 1965.0 / L.ctl[PIPL_PIVOTS]);
     for (int i = 0; i < 8; i++) { pipl_dbg[i] = 0; pipl_cdbg[i] = 0; }
+    for (int i = 0; i < 16; i++) pipl_adbg[i] = 0;
 #endif
   }
 }
 
 /* One AB phase.  Leaves ctl[ACTION] = GO with (pivi, pivj, pivot, dpiv) or STOP with a status. */
-PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
+PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call, pip_i64 *stage)
 {
   const int tid = G::tid(), T = G::T();
   const int nvar = L.nvar, ncol = nvar + 1;
@@ -232,18 +245,40 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     G::cta_sync();
   }
 
+  /* the bitmap of the stored positions is walked word by word, each word a dependent load: CTA 0 keeps
+   * a copy in shared memory (the staging buffers of the update phase are idle during this phase) */
+  const bool sbs = stage && (size_t)((L.pcap + 31) >> 5) * sizeof(unsigned) <= (size_t)(PIPL_NG + 1) * L.stride * sizeof(pip_i64);
+  unsigned *sbw = sbs ? (unsigned *)stage : L.sbits;
+  const unsigned *sb = sbw;
+  if (sbs) for (int w = tid; w < ((L.pcap + 31) >> 5); w += T) sbw[w] = L.sbits[w];
   PIPL_T(2);
+  PIPL_ALAP_BEGIN;
   int pivi = PIPL_INF;
   for (;;) {
     /* chercher(Minus), and in the same sweep the first Unknown row with a negative constant (what
      * exam_coef with nparm = 0 would stop at: an Unknown row takes the sign of its constant, rows
      * after the first negative one stay Unknown) */
     int c = PIPL_INF, c2 = PIPL_INF;
-    for (int k = tid; k < nl; k += T) {
-      const int f = L.fl[k];
-      if ((f & PIP_MINUS) && k < c) c = k;
-      if (PIP_FLAG(f) == PIP_UNKNOWN && L.csign[k] < 0 && k < c2) c2 = k;
+    /* PIPL_RP positions per thread per round, every load of a round issued before the first use (the
+     * sweep is one L2 round trip per round, not one per position) */
+    for (int base = 0; base < nl; base += PIPL_RP * T) {
+      int f[PIPL_RP];
+      signed char sg[PIPL_RP];
+      #pragma unroll
+      for (int i = 0; i < PIPL_RP; i++) {
+        const int k = base + i * T + tid;
+        f[i] = k < nl ? L.fl[k] : 0;
+        sg[i] = k < nl ? L.csign[k] : (signed char)0;
+      }
+      #pragma unroll
+      for (int i = PIPL_RP - 1; i >= 0; i--) {
+        const int k = base + i * T + tid;
+        if (k >= nl) continue;
+        if ((f[i] & PIP_MINUS) && k < c) c = k;
+        if (PIP_FLAG(f[i]) == PIP_UNKNOWN && sg[i] < 0 && k < c2) c2 = k;
+      }
     }
+    PIPL_ALAP(0);
     {
       c = (int)W::redmin((unsigned)c);
       c2 = (int)W::redmin((unsigned)c2);
@@ -255,6 +290,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
       for (int i = 0; i < nw; i++) { c = red[i] < c ? red[i] : c; c2 = red[32 + i] < c2 ? red[32 + i] : c2; }
     }
     pivi = c;
+    PIPL_ALAP(1);
     if (pivi < nl) break;
     const int firstneg = c2;
     for (int k = tid; k < nl; k += T) {
@@ -264,6 +300,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
       L.fl[k] = PIP_MKFL(s < 0 ? PIP_MINUS : s > 0 ? PIP_PLUS : PIP_ZERO, PIP_LINK(f));
     }
     G::cta_sync();
+    PIPL_ALAP(2);
     if (firstneg < nl) { pivi = firstneg; break; }
     /* all rows non-negative */
     if (!(L.flags & PIP_F_INT)) { pipl_finish(L, PIP_ST_OK, 2); return; }
@@ -310,6 +347,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
         L.csign[nl] = L.cut[nvar] < 0 ? -1 : L.cut[nvar] > 0 ? 1 : 0;
         L.ctl[PIPL_NI] = ni + 1;
         L.sbits[nl >> 5] |= 1u << (nl & 31);
+        if (sbs) sbw[nl >> 5] |= 1u << (nl & 31);
         L.ctl[PIPL_CUTS] = L.ctl[PIPL_CUTS] + 1;
       }
       G::cta_sync();
@@ -328,6 +366,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
    * largest colpos survives).  The loop therefore runs once per *stored* row met before the
    * decision -- typically once or twice. */
   PIPL_T(3);
+  PIPL_ALAP(3);
   const pip_i64 *prow = pipl_row(L, PIP_LINK(L.fl[pivi]));
   const int nwords = (nl + 31) >> 5;
   int pivj = PIPL_INF;
@@ -341,9 +380,16 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     const int cap = T < 6 * PIPL_LCAP ? T : 6 * PIPL_LCAP;
     if (tid == 0) *scnt = 0;
     G::cta_sync();
-    for (int j = tid; j < nvar; j += T)
-      if (prow[j] > 0) { const int at = (int)G::atomic_add_u((unsigned *)scnt, 1u); if (at < cap) scj[at] = j; }
+    for (int base = 0; base < nvar; base += PIPL_AL * T) {
+      pip_i64 pv[PIPL_AL];
+      #pragma unroll
+      for (int i = 0; i < PIPL_AL; i++) { const int j = base + i * T + tid; pv[i] = j < nvar ? prow[j] : 0; }
+      #pragma unroll
+      for (int i = 0; i < PIPL_AL; i++)
+        if (pv[i] > 0) { const int at = (int)G::atomic_add_u((unsigned *)scnt, 1u); if (at < cap) scj[at] = base + i * T + tid; }
+    }
     G::cta_sync();
+    PIPL_ALAP(4);
     const int n0 = *scnt;
     if (n0 == 0) { pipl_finish(L, PIP_ST_OK, 1); return; }
     if (n0 <= cap) {
@@ -360,7 +406,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
         int pst = PIPL_INF;
         for (;;) {
           int wp[PIPL_WIN];
-          pipl_window(L, k, nl, nwords, wp);
+          pipl_window(sb, k, nl, nwords, wp);
           if (wp[0] == PIPL_INF) break;
           PIPL_DBG(2, 1);
           int first = PIPL_WIN;
@@ -433,7 +479,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
             int pst = PIPL_INF;
             for (;;) {
               int wp[PIPL_WIN];
-              pipl_window(L, k, nl, nwords, wp);
+              pipl_window(sb, k, nl, nwords, wp);
               if (wp[0] == PIPL_INF) break;
               PIPL_DBG(4, 1);
               pip_i64 v[PIPL_WIN];
@@ -509,7 +555,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
             int pst = PIPL_INF;
             for (;;) {
               int wp[PIPL_WIN];
-              pipl_window(L, k, nl, nwords, wp);
+              pipl_window(sb, k, nl, nwords, wp);
               if (wp[0] == PIPL_INF) break;
               PIPL_DBG(4, 1);
               pip_i64 v[PIPL_WIN];
@@ -585,7 +631,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
           int pst = PIPL_INF;
           for (;;) {
             int wp[PIPL_WIN];
-            pipl_window(L, k, nl, nwords, wp);
+            pipl_window(sb, k, nl, nwords, wp);
             if (wp[0] == PIPL_INF) break;
             PIPL_DBG(2, 1);
             const pip_i64 *wr[PIPL_WIN];
@@ -681,7 +727,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
       /* next stored position >= k */
       int c = PIPL_INF;
       for (int w = (k >> 5) + tid; w < nwords; w += T) {
-        unsigned bits = L.sbits[w];
+        unsigned bits = sb[w];
         if (w == (k >> 5)) bits &= ~0u << (k & 31);
         if (bits) { const int pp = (w << 5) + pip_ffs(bits) - 1; if (pp < nl && pp < c) c = pp; break; }
       }
@@ -755,6 +801,7 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call)
     pivj = pipl_cta_min(pj, red);
 
   }
+  PIPL_ALAP(7);
   if (pivj >= nvar) { pipl_finish(L, PIP_ST_FAULT, 0); return; }
 
   PIPL_T(4);
@@ -1108,7 +1155,7 @@ PIP_DEV void pipl_solve(const PipLarge &L, int *red, pip_i64 *stage = nullptr)
   if (G::cta() == 0) pipl_sort(L, sz, red);
   long long t0 = pip_clock();
   for (;;) {
-    if (G::cta() == 0) pipl_phase_ab(L, red, first);
+    if (G::cta() == 0) pipl_phase_ab(L, red, first, stage);
     first = false;
     G::grid_sync();
     const long long t1 = pip_clock();

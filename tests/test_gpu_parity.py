@@ -192,6 +192,28 @@ def test_config3_and_5_families_vs_oracle(api, port, workload, n):
         assert (st, ser) == (int(st_g[i]), mine) or st != 0
 
 
+def test_dense_batch_with_varying_equality_rows(api, port):
+    """the dense path plans a chunk from its first problem (same shape assumed for all) and checks the
+    assumption while converting: a batch where the number of equality rows varies from problem to
+    problem must fall back to the exact plan and still match the oracle"""
+    from piplib_b200 import synth
+    n = 1500
+    dom, ctx = synth.generate("loopnest8x12p2", n, seed=11)
+    dom = dom.copy()
+    rng = np.random.default_rng(5)
+    for i in range(n):                       # turn 0..2 inequality rows of every second problem into equalities
+        if i % 2:
+            for r in rng.choice(dom.shape[1], size=int(rng.integers(0, 3)), replace=False):
+                dom[i, r, 0] = 0
+    _, st_o, h_o, stats = port.bench_dense(0, n, dom, ctx, -1)
+    r = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+    st_g = np.where(r["status"] == 1, 0, r["status"])
+    assert np.array_equal(st_g, st_o)
+    ok = st_o == 0
+    assert ok.sum() > n // 8
+    assert np.array_equal(r["hashes"][ok], h_o[ok])
+
+
 def test_device_resident_batch(api, port):
     """kernel-only path (inputs resident in HBM) gives the same answers as the host-buffer path"""
     from piplib_b200 import synth
