@@ -11,6 +11,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "../../include/piplib_b200.h"
 #include "pip_kernels.h"
 
 void pip_cuda_check(cudaError_t e, const char *what)
@@ -73,6 +74,8 @@ const int N_G = sizeof(G_LADDER) / sizeof(G_LADDER[0]);
 }  // namespace
 
 static int g_device = 0;
+/* the device the library works on (pip_set_device_dp); no lock: callable from inside PipEngine::run */
+int pip_engine_device() { return g_device; }
 
 struct PipEngine::Impl {
   std::mutex mu;
@@ -130,6 +133,56 @@ void *PipEngine::pinned_input(size_t bytes)
 }
 int PipEngine::sm_count() { std::lock_guard<std::mutex> g(impl_->mu); impl_->init(); return impl_->sm_count; }
 cudaStream_t PipEngine::stream() { std::lock_guard<std::mutex> g(impl_->mu); impl_->init(); return impl_->stream; }
+
+/* Top of the ladder for non-parametric problems: the few that are still open when the classes with
+ * thousands of cut rows are reached get the whole grid, one after the other (class L, pip_large.h),
+ * instead of one CTA each with the other SMs idle.  Writes the record and the cells of problem
+ * order[q] where warp q of a team round would have put them. */
+static bool large_eligible(const PipProblem &P)
+{
+  return P.nparm == 0 && P.nc == 0 && P.bigparm < 0 && !(P.flags & (PIP_F_DUAL | PIP_F_DEEPEST));
+}
+
+static void run_large_round(const PipBatchIn &in, const std::vector<int> &order, PipCell *d_cells, long long per_warp,
+                            PipResult *d_res, cudaStream_t s)
+{
+  std::vector<long long> tab;
+  std::vector<PipCell_dp> cells((size_t)in.sol_size + 8);
+  for (size_t q = 0; q < order.size(); q++) {
+    const int i = order[q];
+    const PipProblem &P = in.h_prob[i];
+    const int ncol = P.nvar + 1;
+    tab.resize((size_t)P.ni * ncol);
+    for (size_t w = 0; w < tab.size(); w++) {
+      const size_t at = (size_t)P.off + w;
+      tab[w] = in.elem_log2 == 0 ? (long long)((const signed char *)in.h_pool)[at]
+             : in.elem_log2 == 2 ? (long long)((const int *)in.h_pool)[at] : ((const long long *)in.h_pool)[at];
+    }
+    PipResult r;
+    memset(&r, 0, sizeof r);
+    r.status = PIP_ST_CAPACITY;
+    r.cell_off = (pip_i64)q * per_warp;
+    pip_large_problem *lp = pip_large_create_dp(P.nvar, P.ni, (P.flags & PIP_F_INT) ? 1 : 0, tab.data(), 1 << 16,
+                                                in.sol_size, in.maxcol);
+    if (!lp) throw std::runtime_error("piplib-b200: large-tableau class: allocation failed");
+    int st = 0, nc = 0;
+    long long info[12] = {0};
+    const bool ok = pip_large_run_dp(lp, nullptr) == 0 &&
+                    pip_large_fetch_dp(lp, &st, cells.data(), (int)cells.size(), &nc, info) == 0;
+    pip_large_destroy_dp(lp);
+    if (!ok) throw std::runtime_error("piplib-b200: large-tableau class: launch failed");
+    r.status = st;
+    r.ncells = st == PIP_ST_OK ? nc : 0;
+    r.pivots = (unsigned)info[0]; r.cuts = (unsigned)info[1];
+    r.max_rows = (unsigned)(P.nvar + info[3]); r.max_cols = (unsigned)ncol;
+    bool wide = false;
+    for (int c = 0; c < r.ncells; c++) wide = wide || !PIP_CELL_FITS(cells[c].p1, cells[c].p2);
+    r.rflags = wide ? PIP_RES_WIDE : 0u;
+    if (r.ncells) CK(cudaMemcpyAsync(d_cells + r.cell_off, cells.data(), sizeof(PipCell) * (size_t)r.ncells, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_res + i, &r, sizeof r, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));        /* cells / r are reused by the next problem */
+  }
+}
 
 void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
 {
@@ -280,10 +333,20 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       L.slack_level = cs.level;
       L.prof = (unsigned long long *)E.d_prof.p;
       double tk = now_s();
-      CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? 3 : cs.shared, ctas, cs.warps_per_cta, s));
-      out.times.launches++;
+      /* PIPLIB_B200_LARGE_FROM=<class index> moves the hand-over (tests), a negative value disables it */
+      const char *lf = getenv("PIPLIB_B200_LARGE_FROM");
+      const int large_from = lf && *lf ? atoi(lf) : 3;
+      bool use_large = large_from >= 0 && k >= large_from && m <= 4 && in.h_pool && in.elem_log2 <= 3;
+      for (int q = 0; q < m && use_large; q++) use_large = large_eligible(in.h_prob[order[q]]);
+      if (use_large) {
+        run_large_round(in, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
+        out.times.launches += m;
+      } else {
+        CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? 3 : cs.shared, ctas, cs.warps_per_cta, s));
+        out.times.launches++;
+      }
       /* compact this round's output: packed cells, or (device-decode mode) serialised quasts */
-      if (ser_mode && !all_sized) {      /* sizing pass, unless the solver sized every stream itself */
+      if (ser_mode && (!all_sized || use_large)) {      /* sizing pass, unless the solver sized every stream itself */
         CK(pip_launch_serialize((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
                                 (const PipDecodeParm *)E.d_parm.p, nullptr, nullptr, nullptr, m, 0, s));
         out.times.launches++;
@@ -344,8 +407,8 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       if (getenv("PIPLIB_B200_TIMING")) {
         int esc = 0;
         for (int q = 0; q < m; q++) if (cls[order[q]] != 1000) esc++;
-        fprintf(stderr, "[piplib-b200] round %d: class %d attempt %d, %d problems on %d warps (%d words/warp): %.3f s, %d not final (%d pending)\n",
-                round - 1, k, attempt, m, cs.warps, (int)cs.words, t_round, esc, pending);
+        fprintf(stderr, "[piplib-b200] round %d: class %d attempt %d, %d problems on %d warps (%d words/warp): %.3f s, %d not final (%d pending)%s\n",
+                round - 1, k, attempt, m, cs.warps, (int)cs.words, t_round, esc, pending, use_large ? " [whole-grid kernel]" : "");
       }
       if (pending == 0) {
         /* re-arm the escalated problems on the device */

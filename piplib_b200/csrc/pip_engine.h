@@ -82,5 +82,6 @@ class PipEngine {
 };
 
 void pip_cuda_check(cudaError_t e, const char *what);
+int pip_engine_device();
 
 #endif

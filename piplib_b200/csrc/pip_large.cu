@@ -60,7 +60,13 @@ pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long
                                        int sol_size, int maxcol)
 {
   try {
-    PipEngine::get().sm_count();
+    /* no PipEngine call here: the batch engine runs this from inside PipEngine::run (lock held) */
+    const int dev = pip_engine_device();
+    CKL(cudaSetDevice(dev));
+    int sms = 0, major = 0;
+    CKL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CKL(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major < 10) throw std::runtime_error("piplib-b200: this library is built for sm_100a (B200) only");
     pip_large_problem *P = new pip_large_problem;
     PipLarge &L = P->L;
     memset(&L, 0, sizeof L);
@@ -104,7 +110,7 @@ pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long
     int per_sm = 0;
     CKL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pip_large_kernel, PIPL_THREADS, P->dyn));
     if (per_sm < 1) per_sm = 1;
-    P->grid = PipEngine::get().sm_count() * per_sm;
+    P->grid = sms * per_sm;
     return P;
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());

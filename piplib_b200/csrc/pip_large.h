@@ -1142,7 +1142,7 @@ PIP_DEV void pipl_sort(const PipLarge &L, float *sz, int *red);
 
 PIP_DEV void pipl_solve(const PipLarge &L, int *red, pip_i64 *stage = nullptr)
 {
-  unsigned skipped = 0, par_prow = 0, par_row = 0;
+  unsigned par_prow = 0, par_row = 0;
   bool first = true;
   float *sz = (float *)L.cand;                 /* scratch: pcap floats fit (cand has pcap ints) */
   if (stage) {
@@ -1167,7 +1167,6 @@ PIP_DEV void pipl_solve(const PipLarge &L, int *red, pip_i64 *stage = nullptr)
     t0 = t2;
     if (L.ctl[PIPL_STATUS] != PIP_ST_OK) break;
   }
-  (void)skipped;
 }
 
 /* entry of traiter for the large problem: flags, tab_simplify (source/tab.c:396-427) and the

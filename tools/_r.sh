@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_v12.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_v12.log; tail -2 gpurun_out/pytest_gpu_v12.log
-python tools/e2e_timing.py 1000000 2>&1 | grep "^e2e\|lane 0:" | tail -4
-PIPLIB_B200_EXACT_PLAN=1 python tools/e2e_timing.py 1000000 2>&1 | grep "^e2e\|lane 0:" | tail -4
+timeout 200 python -m pytest tests -m gpu -x -q -k "ladder" > gpurun_out/pytest_gpu_v13.log 2>&1; tail -3 gpurun_out/pytest_gpu_v13.log
+PIPLIB_B200_TIMING=1 timeout 120 python tools/rounds.py vivien32 4000 2>&1 | tail -11
