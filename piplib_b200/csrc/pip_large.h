@@ -1073,7 +1073,7 @@ PIP_DEV void pipl_phase_c(const PipLarge &L, int *red, pip_i64 *stage, unsigned 
     if (foo == 0 && dk == 1) { nskip++; continue; }
     const int at = (int)G::atomic_add_u((unsigned *)lcnt, 1u);
     if (at < PIPL_LCAP) { lk[at] = p; lf[at] = f; lfoo[at] = foo; lden[at] = dk; }
-    else L.active[G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], 1u)] = p;     /* never on sane grids */
+    else L.active[G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], 1u)] = p;     /* tall tableaus only: > 128 active rows per stripe */
   }
   nskip = pipl_cta_sum(nskip, red);                /* also orders the list stores before the reads */
   PIPL_CLAP(0);
