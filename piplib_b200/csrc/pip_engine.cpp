@@ -138,6 +138,9 @@ cudaStream_t PipEngine::stream() { std::lock_guard<std::mutex> g(impl_->mu); imp
  * thousands of cut rows are reached get the whole grid, one after the other (class L, pip_large.h),
  * instead of one CTA each with the other SMs idle.  Writes the record and the cells of problem
  * order[q] where warp q of a team round would have put them. */
+#ifndef PIP_LARGE_FROM_DEFAULT
+#define PIP_LARGE_FROM_DEFAULT -1     /* off until the hand-over has been measured on the GPU */
+#endif
 static bool large_eligible(const PipProblem &P)
 {
   return P.nparm == 0 && P.nc == 0 && P.bigparm < 0 && !(P.flags & (PIP_F_DUAL | PIP_F_DEEPEST));
@@ -335,7 +338,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       double tk = now_s();
       /* PIPLIB_B200_LARGE_FROM=<class index> moves the hand-over (tests), a negative value disables it */
       const char *lf = getenv("PIPLIB_B200_LARGE_FROM");
-      const int large_from = lf && *lf ? atoi(lf) : 3;
+      const int large_from = lf && *lf ? atoi(lf) : PIP_LARGE_FROM_DEFAULT;
       bool use_large = large_from >= 0 && k >= large_from && m <= 4 && in.h_pool && in.elem_log2 <= 3;
       for (int q = 0; q < m && use_large; q++) use_large = large_eligible(in.h_prob[order[q]]);
       if (use_large) {
