@@ -139,28 +139,36 @@ cudaStream_t PipEngine::stream() { std::lock_guard<std::mutex> g(impl_->mu); imp
  * instead of one CTA each with the other SMs idle.  Writes the record and the cells of problem
  * order[q] where warp q of a team round would have put them. */
 #ifndef PIP_LARGE_FROM_DEFAULT
-#define PIP_LARGE_FROM_DEFAULT -1     /* off until the hand-over has been measured on the GPU */
+#define PIP_LARGE_FROM_DEFAULT 3      /* measured: vivien32-shaped batch 5.44 -> 3.90 s (its last 2 problems 2.87 -> 1.31 s) */
 #endif
 static bool large_eligible(const PipProblem &P)
 {
   return P.nparm == 0 && P.nc == 0 && P.bigparm < 0 && !(P.flags & (PIP_F_DUAL | PIP_F_DEEPEST));
 }
 
-static void run_large_round(const PipBatchIn &in, const std::vector<int> &order, PipCell *d_cells, long long per_warp,
-                            PipResult *d_res, cudaStream_t s)
+static void run_large_round(const PipBatchIn &in, const void *d_pool, const std::vector<int> &order, PipCell *d_cells,
+                            long long per_warp, PipResult *d_res, cudaStream_t s)
 {
   std::vector<long long> tab;
+  std::vector<unsigned char> raw;
   std::vector<PipCell_dp> cells((size_t)in.sol_size + 8);
   for (size_t q = 0; q < order.size(); q++) {
     const int i = order[q];
     const PipProblem &P = in.h_prob[i];
     const int ncol = P.nvar + 1;
     tab.resize((size_t)P.ni * ncol);
-    for (size_t w = 0; w < tab.size(); w++) {
-      const size_t at = (size_t)P.off + w;
-      tab[w] = in.elem_log2 == 0 ? (long long)((const signed char *)in.h_pool)[at]
-             : in.elem_log2 == 2 ? (long long)((const int *)in.h_pool)[at] : ((const long long *)in.h_pool)[at];
+    /* the problem's words: from the host pool, or (device-resident batches) fetched from the device pool */
+    const size_t esz = (size_t)1 << in.elem_log2;
+    const unsigned char *src = in.h_pool ? (const unsigned char *)in.h_pool + (size_t)P.off * esz : nullptr;
+    if (!src) {
+      raw.resize(tab.size() * esz);
+      CK(cudaMemcpyAsync(raw.data(), (const unsigned char *)d_pool + (size_t)P.off * esz, raw.size(), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      src = raw.data();
     }
+    for (size_t w = 0; w < tab.size(); w++)
+      tab[w] = in.elem_log2 == 0 ? (long long)((const signed char *)src)[w]
+             : in.elem_log2 == 2 ? (long long)((const int *)src)[w] : ((const long long *)src)[w];
     PipResult r;
     memset(&r, 0, sizeof r);
     r.status = PIP_ST_CAPACITY;
@@ -339,10 +347,10 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       /* PIPLIB_B200_LARGE_FROM=<class index> moves the hand-over (tests), a negative value disables it */
       const char *lf = getenv("PIPLIB_B200_LARGE_FROM");
       const int large_from = lf && *lf ? atoi(lf) : PIP_LARGE_FROM_DEFAULT;
-      bool use_large = large_from >= 0 && k >= large_from && m <= 4 && in.h_pool && in.elem_log2 <= 3;
+      bool use_large = large_from >= 0 && k >= large_from && m <= 4 && in.elem_log2 <= 3;
       for (int q = 0; q < m && use_large; q++) use_large = large_eligible(in.h_prob[order[q]]);
       if (use_large) {
-        run_large_round(in, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
+        run_large_round(in, d_pool, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
         out.times.launches += m;
       } else {
         CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? 3 : cs.shared, ctas, cs.warps_per_cta, s));

@@ -298,7 +298,6 @@ def test_edge_cases(api, port):
     assert (st, ser) == port.solve([[1, 1, -1, 0]], np.zeros((0, 3), dtype=np.int64), -1, ctx_cols=3)
 
 
-@pytest.mark.skipif(not os.environ.get("PIPLIB_B200_TEST_HANDOVER"), reason="hand-over to the grid kernel: opt-in until verified on a B200")
 def test_ladder_hands_stragglers_to_the_grid_kernel(api, monkeypatch):
     """the last few non-parametric problems of a batch that reach the big global-memory classes are
     solved by the whole-grid kernel (class L) instead of one CTA each: same cells.  The hand-over
