@@ -1046,6 +1046,66 @@ PIP_DEV void pipl_update_row_staged(const PipLarge &L, const PiplGroup &grp, int
   }
 }
 
+/* Short rows (at most 64 words: the tall, narrow tableaus that cut chains produce -- thousands of rows
+ * of a few dozen columns): one WARP per row, each lane owns columns lane and lane + 32, the pivot row's
+ * two entries stay in registers for the whole phase, the row gcd is a shuffle reduction.  No shared
+ * memory, no barrier. */
+PIP_DEV void pipl_update_row_warp(const PipLarge &L, int k, int f, pip_i64 foo, pip_i64 dk, pip_i64 b0, pip_i64 b1,
+                                  pip_i64 pivot, pip_i64 dpiv, int pivj)
+{
+  const int lane = W::lane();
+  const int nvar = L.nvar, ncol = nvar + 1;
+  const int j0 = lane, j1 = lane + 32;
+  pip_i64 *row = pipl_row(L, PIP_LINK(f));
+  const pip_i64 a0 = j0 < ncol ? row[j0] : 0, a1 = j1 < ncol ? row[j1] : 0;
+  pip_i64 lpiv = pivot;
+  if (foo == 0) lpiv = 1;
+  else if (pivot != 1 && foo != 1 && foo != -1) {
+    const pip_i64 d = pip_gcd(pivot, foo);
+    if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
+  }
+  const pip_i64 newden = (pip_i64)((pip_u64)lpiv * (pip_u64)dk);
+  const pip_i64 zp = (pip_i64)((pip_u64)dpiv * (pip_u64)foo);
+  pip_i64 z0 = (pip_i64)((pip_u64)a0 * (pip_u64)lpiv - (pip_u64)b0 * (pip_u64)foo);
+  pip_i64 z1 = (pip_i64)((pip_u64)a1 * (pip_u64)lpiv - (pip_u64)b1 * (pip_u64)foo);
+  if (j0 == pivj) z0 = zp;
+  if (j1 == pivj) z1 = zp;
+  if (j0 >= ncol) z0 = 0;
+  if (j1 >= ncol) z1 = 0;
+  pip_i64 g = newden, nd = newden;
+  if (g != 1) {
+    if ((g & (g - 1)) == 0 && g > 0) {
+      const pip_u64 orz = (pip_u64)z0 | (pip_u64)z1 | (pip_u64)g;
+      const pip_u64 all = ((pip_u64)W::redor((unsigned)(orz >> 32)) << 32) | W::redor((unsigned)orz);
+      g = (pip_i64)(all & (0ull - all));
+    } else {
+      if (g != 1) g = pip_gcd(g, z0);
+      if (g != 1) g = pip_gcd(g, z1);
+      for (int o = 16; o > 0; o >>= 1) g = pip_gcd(g, W::shfl_xor64(g, o));
+    }
+    if (g != 1 && g != 0) {
+      const PipExactDiv e = pip_exact_prepare(g);
+      z0 = pip_exact_apply(z0, e); z1 = pip_exact_apply(z1, e);
+      nd = pip_exact_apply(newden, e);
+    }
+  }
+  if (j0 < ncol) row[j0] = z0;
+  if (j1 < ncol) row[j1] = z1;
+  const pip_i64 c = W::shfl64(nvar < 32 ? z0 : z1, nvar & 31);
+  if (lane == 0) {
+    L.den[k] = nd;
+    L.csign[k] = c < 0 ? -1 : c > 0 ? 1 : 0;
+    int ff = PIP_FLAG(f);
+    const int fff = zp < 0 ? PIP_MINUS : zp == 0 ? PIP_ZERO : PIP_PLUS;
+    if (fff != PIP_ZERO && fff != ff) {
+      if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
+      else ff = PIP_UNKNOWN;
+      L.fl[k] = PIP_MKFL(ff, PIP_LINK(f));
+    }
+    if (g == 0) L.ctl[PIPL_STATUS] = PIP_ST_FAULT;
+  }
+}
+
 PIP_DEV void pipl_phase_c(const PipLarge &L, int *red, pip_i64 *stage, unsigned &par_prow, unsigned &par_row)
 {
   const int tid = G::tid(), T = G::T(), cta = G::cta(), ncta = G::ncta();
@@ -1078,7 +1138,8 @@ PIP_DEV void pipl_phase_c(const PipLarge &L, int *red, pip_i64 *stage, unsigned 
   nskip = pipl_cta_sum(nskip, red);                /* also orders the list stores before the reads */
   PIPL_CLAP(0);
   int nloc = *lcnt < PIPL_LCAP ? *lcnt : PIPL_LCAP;
-  const int keep = nloc < PIPL_KEEP ? nloc : PIPL_KEEP;
+  const bool skinny = L.stride <= 64;               /* short rows: a warp per row, nothing to share (below) */
+  const int keep = (skinny || nloc < PIPL_KEEP) ? nloc : PIPL_KEEP;
   /* publish the left-overs, then tell the grid this CTA has nothing more to add */
   if (nloc > keep) {
     if (tid == 0) red[63] = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], (unsigned)(nloc - keep));
@@ -1093,6 +1154,36 @@ PIP_DEV void pipl_phase_c(const PipLarge &L, int *red, pip_i64 *stage, unsigned 
     G::atomic_add_u((unsigned *)&L.ctl[PIPL_PUSHED], 1u);
   }
   PIPL_CLAP(1);
+  if (skinny) {
+    const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+    const int ncol = L.nvar + 1;
+    const pip_i64 b0 = lane < ncol ? prow[lane] : 0, b1 = lane + 32 < ncol ? prow[lane + 32] : 0;
+    if (stage) { G::mbar_wait(mbar, par_prow); par_prow ^= 1u; }      /* the staging of the pivot row was issued: drain it */
+    for (int i = wid; i < keep; i += nw) pipl_update_row_warp(L, lk[i], lf[i], lfoo[i], lden[i], b0, b1, pivot, dpiv, pivj);
+    /* rows beyond the local list's capacity (stripes with more than PIPL_LCAP active rows) */
+    int nactive = 0;
+    if (lane == 0) {
+      while ((int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_PUSHED], 0u) < ncta) G::relax();
+      nactive = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NACTIVE], 0u);
+    }
+    nactive = W::shfl(nactive, 0);
+    G::fence();
+    while (nactive > 0) {
+      int idx = 0;
+      if (lane == 0) idx = (int)G::atomic_add_u((unsigned *)&L.ctl[PIPL_NEXT], 1u);
+      idx = W::shfl(idx, 0);
+      if (idx >= nactive) break;
+      const int k = G::load_int(&L.active[idx]);
+      const int f = L.fl[k];
+      const pip_i64 foo = pipl_row(L, PIP_LINK(f))[pivj];
+      const pip_i64 dk = L.den[k];
+      W::sync();
+      pipl_update_row_warp(L, k, f, foo, dk, b0, b1, pivot, dpiv, pivj);
+    }
+    G::cta_sync();
+    PIPL_CLAP(4);
+    return;
+  }
   /* the CTA splits into PIPL_NG groups of warps, one row per group at a time (a row is 32 KB: its
    * update is one load round trip, so rows in flight are what fills the memory pipes) */
   const int ng = T >= 32 * PIPL_NG ? PIPL_NG : 1;
