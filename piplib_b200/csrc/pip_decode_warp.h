@@ -29,31 +29,42 @@ struct PipWarpSer {
   unsigned wide;
 };
 
-/* hash the tile (the chain of pip_sput, in order), note words that leave 32 bits, write it out */
-PIP_DEV void pip_wser_flush(PipWarpSer &s)
+/* hash the tile (the chain of pip_sput, in order), note words that leave 32 bits, write it out.
+ * Out of line and by value: the flush is reached from every place a word is put, and inlining it
+ * there made the kernel 11 k instructions long -- an instruction-cache problem, not a decoder. */
+struct PipFlushOut { pip_u64 h; unsigned wide; };
+PIP_DEVNI PipFlushOut pip_wser_flush_tile(const pip_i64 *tile, int n, pip_u64 h, pip_i64 *out, long long base, long long cap,
+                                        int narrow_out)
 {
   W::sync();
-  const int lane = W::lane(), n = s.fill;
-  pip_u64 h = s.h;
+  const int lane = W::lane();
   for (int k = 0; k < n; k++) {
-    h ^= (pip_u64)s.tile[k];
+    h ^= (pip_u64)tile[k];
     h *= 0x9E3779B97F4A7C15ULL;
     h ^= h >> 32;
   }
-  s.h = h;
-  const long long base = s.len - n;
   bool w = false;
   for (int k = lane; k < n; k += 32) {
-    const pip_i64 v = s.tile[k];
+    const pip_i64 v = tile[k];
     w = w || (v != (pip_i64)(int)v);
-    if (s.out && base + k < s.cap) {
-      if (s.narrow_out) ((int *)s.out)[base + k] = (int)v;
-      else s.out[base + k] = v;
+    if (out && base + k < cap) {
+      if (narrow_out) ((int *)out)[base + k] = (int)v;
+      else out[base + k] = v;
     }
   }
-  if (W::any(w)) s.wide = 1;
-  s.fill = 0;
+  PipFlushOut r;
+  r.h = h;
+  r.wide = W::any(w) ? 1u : 0u;
   W::sync();
+  return r;
+}
+
+PIP_DEV void pip_wser_flush(PipWarpSer &s)
+{
+  const PipFlushOut r = pip_wser_flush_tile(s.tile, s.fill, s.h, s.out, s.len - s.fill, s.cap, s.narrow_out);
+  s.h = r.h;
+  s.wide |= r.wide;
+  s.fill = 0;
 }
 
 PIP_DEV void pip_wput(PipWarpSer &s, pip_i64 v)

@@ -8,8 +8,8 @@ from piplib_b200 import api, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 dom, ctx = synth.generate("loopnest16x24p3", n)
-grid = [(131072, 4, 8, 3), (131072, 4, 12, 3), (131072, 3, 8, 3), (131072, 5, 6, 3), (131072, 4, 8, 4),
-        (262144, 3, 8, 4), (262144, 4, 8, 5), (196608, 4, 8, 4), (98304, 5, 6, 3)]
+grid = [(131072, 4, 8, 3), (131072, 4, 16, 3), (131072, 6, 8, 3), (131072, 5, 8, 3), (196608, 4, 8, 4),
+        (262144, 4, 8, 4), (262144, 3, 12, 4), (98304, 6, 8, 3), (65536, 8, 6, 2)]
 for chunk, lanes, threads, ramp in grid:
     os.environ["PIPLIB_B200_CHUNK"] = str(chunk)
     os.environ["PIPLIB_B200_LANES"] = str(lanes)
