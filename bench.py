@@ -246,7 +246,19 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- piplib-b200 has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout when the communicator comes up (NCCL_DEBUG=VERSION):
+        # stdout carries exactly one JSON line, so fd 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     api.set_device(local)
 
     def barrier():
