@@ -205,10 +205,14 @@ def main():
     W = max(a.warmup, 0)
     K = max(a.steps, 1)
     B = a.batch
-    config = {"workload": "%s: %d problems/GPU/step, 16 unknowns x 24 constraints, 3 parameters, "
-                          "int64, pip_solve path (Nq=1)" % (a.workload, B),
+    # shape of the workload from one generated problem (PolyLib rows: flag, unknowns, parameters, constant)
+    d1, c1 = synth.generate(a.workload, 1, seed=a.seed)
+    nparm = max(c1.shape[2] - 2, 0)
+    config = {"workload": "%s: %d problems/GPU/step, %d unknowns x %d constraints, %d parameters, "
+                          "int64, pip_solve path (Nq=%d)" % (a.workload, B, d1.shape[2] - 2 - nparm, d1.shape[1], nparm,
+                                                             synth.options(a.workload).get("Nq", 1)),
               "batch_per_gpu": B, "l2": "inputs (%.1f GB/step) exceed L2; no flush needed" %
-              (B * 24 * 21 * 8 / 1e9), "seed": a.seed}
+              (B * (d1.shape[1] * d1.shape[2] + c1.shape[1] * c1.shape[2]) * 8 / 1e9), "seed": a.seed}
 
     # ---------------- reference arm: the reference's own CPU implementation ----------------
     if a.impl == "reference":
