@@ -202,7 +202,7 @@ extern "C" cudaError_t pip_launch_serialize(PipResult *res, const int *order, co
                                             const PipDecodeParm *parm, const long long *dst_off, pip_i64 *out,
                                             pip_u64 *hashes, int nprob, int pass, cudaStream_t stream)
 {
-  static const bool thread_decode = getenv("PIPLIB_B200_THREAD_DECODE") != nullptr;   /* A/B aid */
+  const bool thread_decode = getenv("PIPLIB_B200_THREAD_DECODE") != nullptr;   /* A/B aid */
   if (pass == 1 && !thread_decode) {
     const size_t smem = sizeof(pip_i64) * PIP_WS_WARPS * PIP_WS_WORDS_PER_WARP;
     cudaError_t e = cudaFuncSetAttribute(pip_serialize_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

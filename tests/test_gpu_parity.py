@@ -298,6 +298,35 @@ def test_edge_cases(api, port):
     assert (st, ser) == port.solve([[1, 1, -1, 0]], np.zeros((0, 3), dtype=np.int64), -1, ctx_cols=3)
 
 
+@pytest.mark.parametrize("knob", ["PIPLIB_B200_THREAD_DECODE", "PIPLIB_B200_HOST_DECODE", "PIPLIB_B200_EXACT_PLAN",
+                                  "PIPLIB_B200_NO_INT32", "PIPLIB_B200_NO_WIDE_SLACK", "PIPLIB_B200_NO_TMA"])
+def test_alternative_paths_give_the_same_answers(api, port, monkeypatch, knob):
+    """every run-time knob of INTEGRATION.md section 7 selects another route to the same answer: the
+    thread-per-problem and the host decoder, the exact planning pass, the int64 shared-memory class,
+    the narrow capacity slack, the large kernel without shared-memory staging"""
+    from piplib_b200 import synth
+    monkeypatch.setenv(knob, "1")
+    n = 1500
+    dom, ctx = synth.generate("loopnest8x12p2", n, seed=23)
+    _, st_o, h_o, stats = port.bench_dense(0, n, dom, ctx, -1)
+    r = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+    st_g = np.where(r["status"] == 1, 0, r["status"])
+    assert np.array_equal(st_g, st_o)
+    assert np.array_equal(r["hashes"][st_o == 0], h_o[st_o == 0])
+    for i in range(0, n, n // 10):
+        st, ser = port.solve(dom[i], ctx[i], -1)
+        mine = [int(x) for x in r["ser"][r["ser_off"][i]:r["ser_off"][i] + r["ser_len"][i]]]
+        assert (st, ser) == (int(st_g[i]), mine) or st != 0
+    m = 160
+    tab = synth.consecutive_ones(m, m, seed=9)
+    st_l, cells_l = port.traiter(m, 0, m, 0, -1, 1, tab, [])
+    lp = api.LargeProblem(m, m, 1, tab, cut_rows=64)
+    lp.run()
+    st, cells, info = lp.fetch()
+    lp.close()
+    assert st == st_l and [tuple(x) for x in cells] == cells_l
+
+
 def test_ladder_hands_stragglers_to_the_grid_kernel(api, monkeypatch):
     """the last few non-parametric problems of a batch that reach the big global-memory classes are
     solved by the whole-grid kernel (class L) instead of one CTA each: same cells.  The hand-over
