@@ -261,9 +261,9 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call, pip_i64
     int c = PIPL_INF, c2 = PIPL_INF;
     /* PIPL_RP positions per thread per round, every load of a round issued before the first use (the
      * sweep is one L2 round trip per round, not one per position) */
+    int f[PIPL_RP];
+    signed char sg[PIPL_RP];
     for (int base = 0; base < nl; base += PIPL_RP * T) {
-      int f[PIPL_RP];
-      signed char sg[PIPL_RP];
       #pragma unroll
       for (int i = 0; i < PIPL_RP; i++) {
         const int k = base + i * T + tid;
@@ -293,11 +293,21 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call, pip_i64
     PIPL_ALAP(1);
     if (pivi < nl) break;
     const int firstneg = c2;
-    for (int k = tid; k < nl; k += T) {
-      const int f = L.fl[k];
-      if (PIP_FLAG(f) != PIP_UNKNOWN || k > firstneg) continue;
-      const int s = L.csign[k];
-      L.fl[k] = PIP_MKFL(s < 0 ? PIP_MINUS : s > 0 ? PIP_PLUS : PIP_ZERO, PIP_LINK(f));
+    if (nl <= PIPL_RP * T) {
+      /* one round: the flags and signs of the sweep are still in registers */
+      #pragma unroll
+      for (int i = 0; i < PIPL_RP; i++) {
+        const int k = i * T + tid;
+        if (k >= nl || PIP_FLAG(f[i]) != PIP_UNKNOWN || k > firstneg) continue;
+        L.fl[k] = PIP_MKFL(sg[i] < 0 ? PIP_MINUS : sg[i] > 0 ? PIP_PLUS : PIP_ZERO, PIP_LINK(f[i]));
+      }
+    } else {
+      for (int k = tid; k < nl; k += T) {
+        const int fk = L.fl[k];
+        if (PIP_FLAG(fk) != PIP_UNKNOWN || k > firstneg) continue;
+        const int s = L.csign[k];
+        L.fl[k] = PIP_MKFL(s < 0 ? PIP_MINUS : s > 0 ? PIP_PLUS : PIP_ZERO, PIP_LINK(fk));
+      }
     }
     G::cta_sync();
     PIPL_ALAP(2);
