@@ -181,7 +181,9 @@ def large_tableau_line(pk, pk_src, n=4096, reps=2):
                          "frac": ach / pk["hbm_gbs"], "peak_source": pk_src, "traffic": traffic,
                          "algorithmic_bytes": alg,
                          "note": "dense algorithmic figure 16*R*C+8*C+8*R per pivot; rows whose update is the identity "
-                                 "are skipped, so DRAM traffic is far below it (profiles/r1_large_kernel_traffic.json)"}}
+                                 "are skipped, so DRAM traffic is far below it (profiles/r1_large_kernel_traffic.json) "
+                                 "and the fraction can pass 1: it compares the pivot time with one streaming pass "
+                                 "over the dense tableau"}}
 
 
 # ------------------------------------------------------------------------------------------
