@@ -7,9 +7,13 @@
  *                      342-481), lexicographic pivot column (choisir_piv, source/traiter.c:297-341)
  *                      as a candidate-set filtering pass over the positions, determinant / overflow
  *                      bookkeeping (source/traiter.c:394-447)
- *   phase C (all CTAs) rank-1 update of every stored row against the snapshotted pivot row with the
- *                      per-row gcd normalisation (source/traiter.c:467-502), one warp per row,
- *                      coalesced 16-byte loads; re-flag and constant-sign bookkeeping fused in
+ *   phase C (all CTAs) rank-1 update of every stored row against the pivot row with the per-row gcd
+ *                      normalisation (source/traiter.c:467-502); re-flag and constant-sign bookkeeping
+ *                      fused in.  Every CTA scans its own stripe of positions for the rows whose update
+ *                      is not the identity, stages the pivot row and then one row per group of warps
+ *                      in shared memory with cp.async.bulk (TMA engine, mbarrier completion) and
+ *                      writes each row back once with 16-byte stores; rows beyond PIPL_KEEP per CTA
+ *                      are shared through an overflow queue.  Short rows (<= 64 words) take a warp each.
  *
  * nparm = 0 only (no context, no splits): that is what "one large dense ILP tableau" is.  The
  * position/slot model, flags and arithmetic are those of pip_solver.h.  The code is written against
@@ -49,9 +53,9 @@ __device__ unsigned long long pipl_adbg[16];  /* choice-phase laps of CTA 0 */
 #define PIPL_RP 16           /* positions per thread per round of the row-pick sweep */
 #define PIPL_LCAP 128        /* local list capacity of the update phase */
 #define PIPL_RED_INTS (128 + 6 * PIPL_LCAP + 64 * PIPL_NG + 2 * (PIPL_NG + 1))   /* shared scratch of the kernel, in ints */
-#define PIPL_AL 8           /* positions per thread per round of the active-row list */
+#define PIPL_AL 8           /* pivot-row entries per thread per round of the candidate scan */
 /* sub-phase timers of CTA 0 (thread 0): prof[2..7] = swap, row pick, column choice, determinant,
- * active-row list, spare */
+ * (the single-CTA active-row list of earlier versions: now ~0), spare */
 #define PIPL_T(i) do { if (tid == 0) { const long long n_ = pip_clock(); L.prof[i] += (unsigned long long)(n_ - tlap); tlap = n_; } } while (0)
 
 struct PipLarge {
