@@ -235,7 +235,13 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call, pip_i64
     const int pslot = PIP_LINK(L.fl[pivi]);
     pip_i64 *prow = pipl_row(L, pslot);
     const int ku = L.colpos[pivj];          /* the Unit position that owns the pivot column */
-    for (int j = tid; j < ncol; j += T) prow[j] = (j == pivj) ? dpiv : -prow[j];
+    for (int base = 0; base < ncol; base += PIPL_AL * T) {        /* loads of a round first: one round trip */
+      pip_i64 v[PIPL_AL];
+      #pragma unroll
+      for (int i = 0; i < PIPL_AL; i++) { const int j = base + i * T + tid; v[i] = j < ncol ? prow[j] : 0; }
+      #pragma unroll
+      for (int i = 0; i < PIPL_AL; i++) { const int j = base + i * T + tid; if (j < ncol) prow[j] = (j == pivj) ? dpiv : -v[i]; }
+    }
     G::cta_sync();
     if (tid == 0) {
       const pip_i64 c = prow[nvar];
@@ -431,10 +437,20 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call, pip_i64
             #pragma unroll
             for (int b = PIPL_WIN - 1; b >= 0; b--) if (v[b] != 0) first = b;
           }
-          first = pipl_cta_min(first, red);
+          /* one exchange for both questions of the step: the first row with a non-zero entry, and how many
+           * candidates are still in play beyond this window (cu > PIPL_INF never holds) */
+          int inplay = pip_popc(W::ballot(alive && cu > wp[PIPL_WIN - 1]));
+          first = (int)W::redmin((unsigned)first);
+          {
+            const int lane = W::lane(), wid = tid >> 5, nw = (T + 31) >> 5;
+            G::cta_sync();
+            if (lane == 0) { red[wid] = first; red[32 + wid] = inplay; }
+            G::cta_sync();
+            first = PIPL_WIN; inplay = 0;
+            for (int i = 0; i < nw; i++) { first = red[i] < first ? red[i] : first; inplay += red[32 + i]; }
+          }
           if (first < PIPL_WIN) { pst = wp[first]; break; }
           if (wp[PIPL_WIN - 1] == PIPL_INF) break;
-          const int inplay = pipl_cta_sum((alive && cu > wp[PIPL_WIN - 1]) ? 1 : 0, red);
           if (inplay <= 1) break;
           k = wp[PIPL_WIN - 1] + 1;
         }
