@@ -839,13 +839,15 @@ PIP_DEV void pipl_phase_ab(const PipLarge &L, int *red, bool first_call, pip_i64
   if (tid == 0) {
     const pip_i64 pivot = prow[pivj], dpiv = L.den[pivi];
     int status = PIP_ST_OK;
-    pip_i64 d = pip_gcd(pivot, dpiv);
+    /* unit pivots on integer rows are the rule: gcd(x, +-1) = 1 and x / 1 = x need no 64-bit gcd or division */
+    const bool unit = dpiv == 1 || pivot == 1 || pivot == -1;
+    pip_i64 d = unit ? 1 : pip_gcd(pivot, dpiv);
     if (d == 0) status = PIP_ST_FAULT;
     else {
-      pip_i64 ppivot = pip_div(pivot, d), dppiv = pip_div(dpiv, d);
+      pip_i64 ppivot = d == 1 ? pivot : pip_div(pivot, d), dppiv = d == 1 ? dpiv : pip_div(dpiv, d);
       int ldet = L.ctl[PIPL_LDET];
       pip_i64 *det = L.ctl64 + 2;
-      for (int i = 0; i < ldet && status == PIP_ST_OK; i++) {
+      for (int i = 0; dppiv != 1 && i < ldet && status == PIP_ST_OK; i++) {
         const pip_i64 g = pip_gcd(det[i], dppiv);
         if (g == 0) { status = PIP_ST_FAULT; break; }
         det[i] = pip_div(det[i], g);
