@@ -10,7 +10,7 @@ scaling: every rank solves its own B problems; no data-path collective exists, S
   e2e     problems/s through the C-ABI call pip_solve_dense_dp with HOST buffers: PolyLib
           matrices in, serialised quasts + hashes out, host<->device copies inside the region
 The workload is configs[1] of BASELINE.json: ~16 unknowns x 24 constraints, 3 parameters
-(piplib_b200/synth.py: loopnest16x24p3), data = synthetic.  Inputs (4 GB per 10^6 problems) are
+(workloads/synth.py: loopnest16x24p3), data = synthetic.  Inputs (4 GB per 10^6 problems) are
 far larger than L2, so no explicit L2 flush is needed between steps.
 """
 import argparse
@@ -29,7 +29,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from piplib_b200 import dist as pdist  # noqa: E402
-from piplib_b200 import synth  # noqa: E402
+from workloads import synth  # noqa: E402
 
 METRIC = "problems_per_sec"
 UNIT = "problems/s"
@@ -95,95 +95,71 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arms (the checker libraries; never the thing shipped)
+# CPU arms (the checker libraries; never the thing shipped): oracle/cpu_arm.py
 # ------------------------------------------------------------------------------------------
-_CPU_DATA = None      # (dom, ctx) inherited by the forked workers (never pickled)
+from oracle.cpu_arm import cpu_arm, same_answers, usable_cores  # noqa: E402
 
 
-def _cpu_worker(args):
-    kind, first, count, core, bg, opts = args
-    dom, ctx = _CPU_DATA
-    try:
-        os.sched_setaffinity(0, {core})
-    except Exception:
-        pass
-    from oracle import pyoracle as po
-    if kind == "reference":
-        sec, st, h = po.Ref().bench_dense(first, count, dom, ctx, bg, **opts)
-        piv = 0
-    else:
-        sec, st, h, stats = po.Port().bench_dense(first, count, dom, ctx, bg, **opts)
-        piv = stats.pivots
-    return sec, st, h, piv
-
-
-def cpu_arm(dom, ctx, sample, cores, bg=-1, opts=None):
-    """reference CPU path on `cores` processes (one per core: the library is not re-entrant,
-    SURVEY.md 8b), static split of problems [0, sample)."""
-    from oracle import pyoracle as po
-    kind = "reference" if os.path.exists(po.REF_SO) else "port"
-    if kind == "port":
-        po.build(ref=False, port=True)
-    per = (sample + cores - 1) // cores
-    jobs = []
-    for c in range(cores):
-        a, b = c * per, min(sample, (c + 1) * per)
-        if a < b:
-            jobs.append((kind, a, b - a, c, bg, opts or {}))
-    global _CPU_DATA
-    _CPU_DATA = (dom[:sample], None if ctx is None else ctx[:sample])
-    ctxm = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctxm.Pool(len(jobs)) as pool:
-        outs = pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    tmax = max(o[0] for o in outs)
-    status = np.concatenate([o[1] for o in outs])
-    hashes = np.concatenate([o[2] for o in outs])
-    return dict(kind=kind, seconds=tmax, wall=wall, status=status, hashes=hashes, cores=len(jobs),
-                n=sample)
-
-
-def port_pivots(dom, ctx, sample):
-    """pivot count of a sample (the reference has no counter; the oracle restatement, which gives
-    bit-identical answers, counts them)."""
-    from oracle import pyoracle as po
-    po.build(ref=False, port=True)
-    sec, st, h, stats = po.Port().bench_dense(0, sample, dom, ctx, -1)
-    return stats.pivots, stats.elem_updates
-
-
-def large_tableau_line(pk, pk_src, n=4096, reps=2):
+def large_tableau_line(pk, pk_src, n=4096, reps=2, cpu=True):
     """BASELINE config 4 (the HBM-bound kernel of the path): one n x (n+1) int64 tableau solved by the
     whole grid, cooperative launch, CUDA events inside the library.  Algorithmic bytes per pivot =
-    16*R*C + 8*C + 8*R (dense figure)."""
+    16*R*C + 8*C + 8*R (dense figure).  Refuses to report unless the cells equal the ones
+    the unmodified reference (raised limits) produced for this very tableau (tests/golden/)."""
     from piplib_b200 import api
-    tab = synth.consecutive_ones(n, n, seed=2026)
-    p = api.LargeProblem(n, n, 1, tab, cut_rows=1024, sol_size=1 << 20, maxcol=1 << 16)
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "large_consecutive_ones_%d.json" % n)))
+    tab = synth.consecutive_ones(n, n, seed=g["seed"])
+    p = api.LargeProblem(n, n, g["nq"], tab, cut_rows=1024, sol_size=1 << 20, maxcol=1 << 16)
     p.run()
     ms = min(p.run() for _ in range(reps))
     st, cells, info = p.fetch()
     p.close()
+    if st != g["status"] or cells != g["cells"] or info["pivots"] != g["pivots"]:
+        raise SystemExit("bench.py: config 4: the %d x %d tableau's answer differs from the reference's -- "
+                         "refusing to report" % (n, n + 1))
     piv = max(1, info["pivots"])
     R, C = n - 1, n + 1
     alg = (16.0 * R * C + 8.0 * C + 8.0 * R) * piv
     ach = alg / (ms / 1e3) / 1e9
-    traffic = None            # DRAM bytes per launch from the committed ncu --set full capture (same n, same seed)
-    tj = os.path.join(ROOT, "profiles", "r1_large_kernel_traffic.json")
-    if os.path.exists(tj):
-        t = json.load(open(tj))
-        if t.get("n") == n and t.get("pivots") == info["pivots"]:
-            traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
-    return {"workload": "consecutive-ones %d x %d int64, Nq=1, one problem over the whole grid" % (n, n + 1),
-            "status": st, "pivots": info["pivots"], "kernel_ms": ms, "us_per_pivot": 1e3 * ms / piv,
-            "pivots_per_sec": piv / (ms / 1e3),
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / pk["hbm_gbs"], "peak_source": pk_src, "traffic": traffic,
-                         "algorithmic_bytes": alg,
-                         "note": "dense algorithmic figure 16*R*C+8*C+8*R per pivot; rows whose update is the identity "
-                                 "are skipped, so DRAM traffic is far below it (profiles/r1_large_kernel_traffic.json) "
-                                 "and the fraction can pass 1: it compares the pivot time with one streaming pass "
-                                 "over the dense tableau"}}
+    rows_total = float(R) * piv
+    out = {"workload": "consecutive-ones %d x %d int64, Nq=1, one problem over the whole grid" % (n, n + 1),
+           "status": st, "pivots": info["pivots"], "kernel_ms": ms, "us_per_pivot": 1e3 * ms / piv,
+           "pivots_per_sec": piv / (ms / 1e3),
+           "parity": "cells, status and pivot count equal to the unmodified reference built with raised "
+                     "limits (tests/golden/large_consecutive_ones_%d.json)" % n,
+           "identity_rows_skipped_frac": info["skipped_rows"] / rows_total,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / pk["hbm_gbs"], "peak_source": pk_src, "traffic": None,
+                        "algorithmic_bytes": alg,
+                        "note": "dense algorithmic figure 16*R*C+8*C+8*R per pivot (SURVEY.md 8d convention); rows "
+                                "whose update is the identity are skipped (identity_rows_skipped_frac), so the "
+                                "fraction can pass 1; frac_dram is the honest one: DRAM bytes of the ncu capture "
+                                "per second of this run against the same peak"}}
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        if name.endswith("large_kernel_traffic.json"):       # newest round first
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if t.get("n") == n and t.get("pivots") == info["pivots"]:
+                traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
+                out["roofline"]["traffic"] = traffic
+                out["roofline"]["traffic_source"] = "profiles/" + name
+                out["roofline"]["frac_dram"] = traffic / (ms / 1e3) / 1e9 / pk["hbm_gbs"]
+                break
+    if cpu:
+        # the reference's CPU path on this very tableau: one core by construction (it cannot split a tableau)
+        from oracle import pyoracle as po
+        t0 = time.perf_counter()
+        if os.path.exists(po.REF_BIG_SO):
+            st_c, cells_c = po.Ref(big=True).traiter(n, 0, n, 0, -1, g["nq"], tab, [], cap=1 << 20)
+            kind = "reference"
+        else:
+            po.build(ref=False, port=True)
+            st_c, cells_c = po.Port().traiter(n, 0, n, 0, -1, g["nq"], tab, [], sol_size=1 << 20, maxcol=1 << 16)
+            kind = "port"
+        dt = time.perf_counter() - t0
+        if st_c != st or [list(c) for c in cells_c] != cells:
+            raise SystemExit("bench.py: config 4: CPU baseline and GPU disagree")
+        out["cpu_baseline"] = {"value": piv / dt, "unit": "pivots/s", "cores": 1, "kind": kind, "seconds": dt,
+                               "sample": "the whole problem (%d pivots), raised SOL_SIZE/MAXCOL" % piv}
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -199,11 +175,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-large", action="store_true", help="skip the config-4 large-tableau measurement")
-    ap.add_argument("--check", type=int, default=4096, help="problems cross-checked against the oracle")
+    ap.add_argument("--check", type=int, default=65536,
+                    help="problems of every rank's own range cross-checked against the reference before timing")
     a = ap.parse_args()
 
     rank, world, local = pdist.env_rank()
-    cores = os.cpu_count() or 1
+    cores = len(usable_cores())
+    bg, opts = synth.bignum(a.workload), synth.options(a.workload)
     W = max(a.warmup, 0)
     K = max(a.steps, 1)
     B = a.batch
@@ -220,17 +198,17 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        sample = a.cpu_sample or min(B, cores * 4096)
+        sample = a.cpu_sample or min(B, cores * 16384)        # >= 0.5 s of work per core and step
         dom, ctx = synth.generate(a.workload, sample, seed=a.seed, first=0)
         for _ in range(W):
-            cpu_arm(dom, ctx, min(sample, cores * 256), cores)
+            cpu_arm(dom, ctx, min(sample, cores * 1024), cores, bg=bg, opts=opts)
         tot_s, r = 0.0, None
         for _ in range(K):
-            r = cpu_arm(dom, ctx, sample, cores)
+            r = cpu_arm(dom, ctx, sample, cores, bg=bg, opts=opts)
             tot_s += r["seconds"]
         value = sample * K / tot_s
-        pivots, _ = port_pivots(dom, ctx, min(sample, 4096))
-        ppp = pivots / min(sample, 4096)
+        ppp = cpu_arm(dom, ctx, min(sample, cores * 1024), cores, bg=bg, opts=opts, kind="port")["pivots"] / \
+            min(sample, cores * 1024)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
                 "steps": K, "warmup": W, "ms_per_step": 1e3 * tot_s / K, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -275,19 +253,22 @@ def main():
     first, _ = pdist.problem_range(rank, world, B)
     dom, ctx = synth.generate(a.workload, B, seed=a.seed, first=first)
 
-    # parity gate before any timing: a slice of this rank's batch against the oracle
+    # parity gate before any timing: the first `check` problems of THIS rank's range against the
+    # unmodified reference (oracle/_ref; the oracle port where it is absent), on this rank's share of the cores
     ncheck = min(a.check, B)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    my_cores = usable_cores()
+    share = max(1, len(my_cores) // max(1, local_world))
+    my_cores = my_cores[(local % max(1, local_world)) * share:][:share] or my_cores[:1]
     if ncheck:
-        from oracle import pyoracle as po
-        po.build(ref=False, port=True)
-        _, st_o, h_o, stats_o = po.Port().bench_dense(0, ncheck, dom[:ncheck], ctx[:ncheck], -1)
-        r = api.solve_dense(dom[:ncheck], ctx[:ncheck], -1)
-        st_g = np.where(r["status"] == 1, 0, r["status"])
-        if not (np.array_equal(st_g, st_o) and np.array_equal(r["hashes"][st_o == 0], h_o[st_o == 0])):
-            raise SystemExit("bench.py: GPU results differ from the oracle -- refusing to time")
+        gate = cpu_arm(dom, ctx, ncheck, my_cores, bg=bg, opts=opts)
+        r = api.solve_dense(dom[:ncheck], None if ctx is None else ctx[:ncheck], bg, **opts)
+        if not same_answers(r["status"], r["hashes"], gate):
+            raise SystemExit("bench.py: GPU results differ from the %s on problems [%d, %d) -- refusing to time"
+                             % (gate["kind"], first, first + ncheck))
 
     # kernel-only: inputs resident in HBM
-    db = api.DeviceBatch(dom, ctx, -1)
+    db = api.DeviceBatch(dom, ctx, bg, **opts)
     for _ in range(max(W, 3)):
         db.run(False)
     sampler = ClockSampler(local)
@@ -311,15 +292,15 @@ def main():
     db.close()
 
     # end to end through the C-ABI with host buffers
-    e2e_s, h2d_b, d2h_b = None, 0, 0
+    e2e_s, h2d_b, d2h_b, res = None, 0, 0, None
     if not a.no_e2e:
-        res = None                     # caller-owned result buffers, reused across steps
+        # caller-owned result buffers, reused across steps
         for _ in range(max(W, 3)):
-            res = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True, out=res)
+            res = api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, out=res, **opts)
         barrier()
         t1 = time.perf_counter()
         for _ in range(K):
-            res = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True, out=res)
+            res = api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, out=res, **opts)
             s2 = api.last_stats()
             h2d_b, d2h_b = int(s2.h2d_bytes), int(s2.d2h_bytes)
         barrier()
@@ -344,11 +325,16 @@ def main():
         in_bytes = (dom.shape[1] * (dom.shape[2] - 1) + ctx.shape[1] * (ctx.shape[2] - 1)) * elem + 32
         alg_bytes = float(B) * (in_bytes + 56) + 8.0 * cells_step
         achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
-        traffic = None
-        tj = os.path.join(ROOT, "profiles", "r1_solve_kernel_traffic.json")
-        if os.path.exists(tj):
-            t = json.load(open(tj))
-            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["problems"] * B
+        # per-problem DRAM traffic / warp instructions of the solve kernel from the newest committed ncu
+        # capture OF THIS WORKLOAD (profiles/*solve_kernel_traffic.json); none for other workloads
+        traffic, t = None, None
+        for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+            if name.endswith("solve_kernel_traffic.json"):
+                tt = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if tt.get("workload", "loopnest16x24p3") == a.workload:
+                    t, t_src = tt, "profiles/" + name
+                    traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["problems"] * B
+                    break
         uniq, counts = np.unique(status, return_counts=True)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -379,7 +365,7 @@ def main():
             line["issue_roofline"] = {"bound": "issue", "achieved": ipp * value / world, "peak": peak_issue,
                                       "unit": "warp-instructions/s per GPU", "frac": ipp * value / world / peak_issue,
                                       "warp_instructions_per_problem": ipp,
-                                      "source": "profiles/r1_solve_kernel_traffic.json (ncu smsp__inst_executed.sum)"}
+                                      "source": t_src + " (ncu smsp__inst_executed.sum, same workload)"}
         if e2e_max:
             line["e2e"] = {"value": B * world * K / e2e_max, "unit": UNIT,
                            "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
@@ -387,12 +373,18 @@ def main():
         if world == 1 and not a.no_large:
             line["config4_large_tableau"] = large_tableau_line(pk, pk_src)
         if world == 1:
-            sample = a.cpu_sample or min(B, cores * 2048)
-            r = cpu_arm(dom, ctx, sample, cores)
+            # the reference's CPU path on the same inputs, >= 1 s of work per core; its statuses and
+            # hashes are compared with what the timed e2e call returned for the same problems
+            sample = a.cpu_sample or min(B, cores * 32768)
+            r = cpu_arm(dom, ctx, sample, cores, bg=bg, opts=opts)
+            if res is not None and not same_answers(res["status"], res["hashes"], r):
+                raise SystemExit("bench.py: the timed e2e results differ from the %s on the first %d problems"
+                                 % (r["kind"], sample))
             line["cpu_baseline"] = {"value": sample / r["seconds"], "unit": UNIT, "cores": r["cores"],
                                     "kind": r["kind"],
                                     "sample": "first %d problems of the batch, one process per core, "
-                                              "pip_solve loop" % sample}
+                                              "pip_solve loop; statuses and quast hashes equal to the timed "
+                                              "GPU run's" % sample}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -106,6 +106,12 @@ void pip_close_dp(void);
 
 PipQuast_dp *pip_solve_dp(PipMatrix_dp *domain, PipMatrix_dp *parameters, int bignum, PipOptions_dp *options);
 
+/* reference include/piplib/piplib.h:398-402 (source/sol.c:664-734): decode the quast starting at cell
+ * *i of the solution space.  The reference reads its global sol_space (the cells of the last solve);
+ * here that is the cells of the last pip_solve_dp on the calling thread (Bg = bignum - Nn - 1, flags
+ * as in source/sol.h:35-48), or whatever pip_cells_bind_dp (piplib_b200.h) bound. */
+PipQuast_dp *sol_quast_edit_dp(int *i, PipQuast_dp *father, int Bg, int Urs_p, int flags);
+
 #if defined(__cplusplus)
 }
 #endif
@@ -137,5 +143,7 @@ PipQuast_dp *pip_solve_dp(PipMatrix_dp *domain, PipMatrix_dp *parameters, int bi
 #define pip_init pip_init_dp
 #define pip_close pip_close_dp
 #define pip_solve pip_solve_dp
+#define sol_quast_edit sol_quast_edit_dp
+#define pip_solve_batch pip_solve_batch_dp      /* the batched entry point (piplib_b200.h) */
 
 #endif

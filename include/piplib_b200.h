@@ -89,6 +89,11 @@ int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long 
  * pip_traiter_batch_dp: cells may turn Free (kind 0) and *ncells may shrink.  Host only. */
 void pip_cells_simplify_dp(PipCell_dp *cells, int *ncells);
 
+/* make `cells` the solution space sol_quast_edit_dp (piplib.h) decodes from on this thread: the pair
+ * replaces the reference's sol_init/traiter/sol_quast_edit sequence (source/piplib.c:853-867) for a
+ * caller that drives the tableau-level entry point itself.  The cells are copied. */
+void pip_cells_bind_dp(const PipCell_dp *cells, int ncells);
+
 /* Dense batch through the pip_solve_dp path: dom is [n][dom_rows][dom_cols] (PolyLib rows),
  * ctx is [n][ctx_rows][ctx_cols] or NULL (has_ctx=0).  Host buffers in, host buffers out:
  *   status[i]  as above

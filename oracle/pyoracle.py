@@ -18,6 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libpipref.so")
+REF_BIG_SO = os.path.join(HERE, "_ref", "libpipref_big.so")     # same sources, SOL_SIZE / MAXCOL raised by -D
 PORT_SO = os.path.join(HERE, "libpiporacle.so")
 
 # solution cell kinds, source/sol.c:42-50
@@ -33,7 +34,7 @@ def build(ref=True, port=True):
     if port:
         targets.append("libpiporacle.so")
     if ref and os.path.isdir("/root/reference/source"):
-        targets.append("ref")
+        targets += ["ref", "refbig"]
     if targets:
         subprocess.check_call(["make", "-s", "-C", HERE] + targets)
 
@@ -60,8 +61,8 @@ class _Lib:
 class Ref(_Lib):
     """the real reference (oracle/_ref)."""
 
-    def __init__(self):
-        super().__init__(REF_SO)
+    def __init__(self, big=False):
+        super().__init__(REF_BIG_SO if big else REF_SO)
         L = self.lib
         L.pipref_traiter.restype = C.c_int
         L.pipref_solve_ser.restype = C.c_int

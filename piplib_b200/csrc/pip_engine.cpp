@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <stdexcept>
@@ -73,7 +74,7 @@ const int N_G = sizeof(G_LADDER) / sizeof(G_LADDER[0]);
 
 }  // namespace
 
-static int g_device = 0;
+static std::atomic<int> g_device(0);
 /* the device the library works on (pip_set_device_dp); no lock: callable from inside PipEngine::run */
 int pip_engine_device() { return g_device; }
 
@@ -117,8 +118,12 @@ PipEngine &PipEngine::lane(int i)
 }
 int PipEngine::set_device(int dev)
 {
-  std::lock_guard<std::mutex> g(impl_->mu);
-  if (impl_->inited && dev != impl_->device) return -1;
+  /* refused once ANY lane works on another device (lanes initialise lazily, each from g_device) */
+  for (int l = 0; l < MAX_LANES; l++) {
+    Impl &E = *lane(l).impl_;
+    std::lock_guard<std::mutex> g(E.mu);
+    if (E.inited && dev != E.device) return -1;
+  }
   g_device = dev;
   return 0;
 }
@@ -287,11 +292,17 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
   order.reserve(n);
   int round = 0;
   for (int k = -2; k < N_G; k++) {
-    for (int attempt = 0; attempt < 64; attempt++) {
+    int last_open = -1;                 /* problems of this class still open after the previous attempt */
+    for (int attempt = 0;; attempt++) {
       order.clear();
       for (size_t i = 0; i < n; i++) if (cls[i] == k) order.push_back((int)i);
       if (order.empty()) break;
       const int m = (int)order.size();
+      /* every attempt must retire at least one problem (a warp always has room for one worst-case
+       * solution): anything else is a scheduling bug, never a verdict */
+      if (last_open >= 0 && m >= last_open)
+        throw std::runtime_error("piplib-b200: size class made no progress (" + std::to_string(m) + " problems open)");
+      last_open = m;
       /* geometry of this round */
       ClassSpec cs;
       int ctas;
@@ -320,7 +331,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         }
       }
       /* cell pool: every warp must be able to hold one worst-case solution */
-      long long est = (k < 0) ? (est_cells_total * (long long)m / (long long)n) : 0;
+      long long est = est_cells_total * (long long)m / (long long)n;
       long long per_warp = (est + est / 4) / cs.warps + 1 + in.sol_size;
       if (attempt > 0) per_warp = std::max<long long>(per_warp, 4ll * in.sol_size);
       E.d_cells.reserve((size_t)per_warp * cs.warps * sizeof(PipCell));
@@ -404,7 +415,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         const PipResult &r = h_res[i];
         if (r.status == PIP_ST_PENDING) { pending++; continue; }
         if (r.status == PIP_ST_WIDEN) { cls[i] = -1; h_res[i].status = PIP_ST_PENDING; continue; }
-        if (r.status == PIP_ST_CAPACITY && k + 1 < N_G) {
+        if (r.status == PIP_ST_CAPACITY && k + 1 < N_G && !use_large) {   /* class L has no larger class above it */
           /* the wide int32 class already has half of G3's cut rows and all of its context rows: what
            * outgrew it goes straight to the first team class (4x the rows) instead of failing G3 too */
           cls[i] = k < 0 ? ((k == -2 && s32_wide) ? 1 : 0) : k + 1;

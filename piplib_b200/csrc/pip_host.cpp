@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 #include <vector>
@@ -317,7 +318,11 @@ const char *fatal_message(int status)
   return "piplib-b200: solver error\n";
 }
 
+/* statistics of the last batch call: written and read under g_stats_mu (callers may solve from
+ * several threads) */
 PipBatchStats_dp g_stats;
+std::mutex g_stats_mu;
+void publish_stats(const PipBatchStats_dp &s) { std::lock_guard<std::mutex> g(g_stats_mu); g_stats = s; }
 
 /* add one engine run to a statistics record (the per-problem counters are summed, not kept) */
 void accumulate(PipBatchStats_dp &s, const PipBatchOut &out)
@@ -352,7 +357,7 @@ void account(const PipBatchOut &out, double host_seconds)
   memset(&s, 0, sizeof s);
   accumulate(s, out);
   s.seconds_host = host_seconds;
-  g_stats = s;
+  publish_stats(s);
 }
 
 template <class F>
@@ -541,7 +546,12 @@ long pip_quast_serialize_dp(const PipQuast_dp *q, long long *out, long cap)
 
 int pip_set_device_dp(int device) { return PipEngine::get().set_device(device); }
 const char *pip_b200_version(void) { return "piplib-b200 0.1 (sm_100a)"; }
-void pip_last_batch_stats_dp(PipBatchStats_dp *out) { if (out) *out = g_stats; }
+void pip_last_batch_stats_dp(PipBatchStats_dp *out)
+{
+  if (!out) return;
+  std::lock_guard<std::mutex> g(g_stats_mu);
+  *out = g_stats;
+}
 
 /* ---- batch entry points -------------------------------------------------------------------- */
 
@@ -575,6 +585,12 @@ static void equalities_dual(PipQuast_dp *sol, const MatView &dom)
     }
   }
 }
+
+/* the reference keeps the cells of the last solve in its global sol_space until the next solve
+ * (source/sol.c:54-55), which is what the exported sol_quast_edit_xx reads; ours is per thread and
+ * holds the cells of the last pip_solve_dp / batch-of-one on this thread (pip_cells_bind_dp binds
+ * any other stream) */
+static thread_local std::vector<PipCell> t_sol_space;
 
 static PipQuast_dp *decode_one(const PipBatchOut &bo, size_t i, const Shape &s, int simplify)
 {
@@ -664,6 +680,11 @@ int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const 
         int i = live[q];
         status[i] = bo.res[q].status;
         if (status[i] == PIP_ST_OK) {
+          if (n == 1) {
+            unpack_cells(bo.cells_of(q), t_sol_space);
+            int nc1 = (int)t_sol_space.size();
+            if (o.Simplify && nc1) { simplify_cells(t_sol_space.data(), nc1, 0); t_sol_space.resize(nc1); }
+          }
           out[i] = decode_one(bo, q, shapes[i], o.Simplify);
           if ((shapes[i].sol_flags & S_DUAL) && shapes[i].Nl > (int)domains[i]->NbRows) {
             MatView d = {(int)domains[i]->NbRows, (int)domains[i]->NbColumns, domains[i]->p, nullptr};
@@ -748,6 +769,21 @@ int pip_traiter_batch_dp(int n, const PipTableauHeader_dp *hdr, const long long 
     return -1;
   }
   return 0;
+}
+
+/* sol_quast_edit_xx, include/piplib/piplib.h:398-402 / source/sol.c:664-734: decode the quast that
+ * starts at cell *i of the current solution space (the cells of the last pip_solve_dp on this thread,
+ * or the stream bound with pip_cells_bind_dp); *i is left behind the decoded object */
+PipQuast_dp *sol_quast_edit_dp(int *i, PipQuast_dp *father, int Bg, int Urs_p, int flags)
+{
+  if (!i || *i < 0 || (size_t)*i >= t_sol_space.size()) return nullptr;
+  ArrCells a = {t_sol_space.data()};
+  return decode_quast(a, i, father, Bg, Urs_p, flags);
+}
+void pip_cells_bind_dp(const PipCell_dp *cells, int ncells)
+{
+  static_assert(sizeof(PipCell_dp) == sizeof(PipCell), "cell layouts must agree");
+  t_sol_space.assign((const PipCell *)cells, (const PipCell *)cells + (ncells > 0 ? ncells : 0));
 }
 
 /* sol_simplify_xx (source/sol.c:272-288) on a problem's cells as returned by pip_traiter_batch_dp:
@@ -1172,7 +1208,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     memset(&acc, 0, sizeof acc);
     for (size_t l = 0; l < lanes; l++) merge_stats(acc, lane_stats[l]);
     acc.seconds_host = (wall() - t0) - acc.seconds_h2d - acc.seconds_kernel - acc.seconds_d2h;
-    g_stats = acc;
+    publish_stats(acc);
     if (keep && total > ser_cap) return -2;
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());

@@ -12,12 +12,29 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "pip_decode.h"
 #include "pip_decode_warp.h"
 #include "pip_kernels.h"
 #include "pip_warp_main.h"
 
 extern __shared__ __align__(16) unsigned char pip_smem[];
+
+/* cudaFuncAttributeMaxDynamicSharedMemorySize is process-wide per kernel while launches come from
+ * several engine lanes at once: the limit is only ever raised, under one lock, so that no lane can
+ * lower it between another lane's query and its launch */
+static std::mutex g_attr_mu;
+template <class K>
+static cudaError_t pip_raise_dynamic_smem(K kernel, size_t bytes, size_t &high_water)
+{
+  std::lock_guard<std::mutex> g(g_attr_mu);
+  if (bytes <= high_water) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) high_water = bytes;
+  return e;
+}
+static size_t g_smem_s32 = 0, g_smem_s64 = 0, g_smem_ws = 0;
 
 template <bool SH, class V>
 __global__ void __launch_bounds__(PIP_CTA_THREADS, PIP_MIN_CTAS)
@@ -58,11 +75,11 @@ extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, in
     size_t smem = (size_t)warps_per_cta * L->work_words * sizeof(pip_i64);
     cudaError_t e;
     if (shared_class == 2) {
-      e = cudaFuncSetAttribute(pip_solve_kernel<true, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = pip_raise_dynamic_smem(pip_solve_kernel<true, int>, smem, g_smem_s32);
       if (e != cudaSuccess) return e;
       pip_solve_kernel<true, int><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
     } else {
-      e = cudaFuncSetAttribute(pip_solve_kernel<true, pip_i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = pip_raise_dynamic_smem(pip_solve_kernel<true, pip_i64>, smem, g_smem_s64);
       if (e != cudaSuccess) return e;
       pip_solve_kernel<true, pip_i64><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
     }
@@ -77,12 +94,12 @@ extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, in
 extern "C" cudaError_t pip_solve_occupancy(int shared_class, int warps_per_cta, size_t smem_bytes, int *ctas_per_sm)
 {
   if (shared_class == 2) {
-    cudaError_t e = cudaFuncSetAttribute(pip_solve_kernel<true, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = pip_raise_dynamic_smem(pip_solve_kernel<true, int>, smem_bytes, g_smem_s32);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<true, int>, warps_per_cta * 32, smem_bytes);
   }
   if (shared_class) {
-    cudaError_t e = cudaFuncSetAttribute(pip_solve_kernel<true, pip_i64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = pip_raise_dynamic_smem(pip_solve_kernel<true, pip_i64>, smem_bytes, g_smem_s64);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_solve_kernel<true, pip_i64>, warps_per_cta * 32, smem_bytes);
   }
@@ -205,7 +222,7 @@ extern "C" cudaError_t pip_launch_serialize(PipResult *res, const int *order, co
   const bool thread_decode = getenv("PIPLIB_B200_THREAD_DECODE") != nullptr;   /* A/B aid */
   if (pass == 1 && !thread_decode) {
     const size_t smem = sizeof(pip_i64) * PIP_WS_WARPS * PIP_WS_WORDS_PER_WARP;
-    cudaError_t e = cudaFuncSetAttribute(pip_serialize_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pip_raise_dynamic_smem(pip_serialize_warp_kernel, smem, g_smem_ws);
     if (e != cudaSuccess) return e;
     int blocks = (nprob + PIP_WS_WARPS - 1) / PIP_WS_WARPS;
     if (blocks > 148 * 3) blocks = 148 * 3;

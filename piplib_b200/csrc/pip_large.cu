@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <stdexcept>
 #include <vector>
 
@@ -54,11 +55,24 @@ struct pip_large_problem {
 
 #define CKL(x) pip_cuda_check((x), #x)
 
+/* the dynamic shared-memory limit of the kernel is process-wide: only ever raised, under a lock
+ * (several problems may be created / run from different threads) */
+static std::mutex g_large_attr_mu;
+static size_t g_large_smem = 0;
+static void pip_large_raise_smem(size_t bytes)
+{
+  std::lock_guard<std::mutex> g(g_large_attr_mu);
+  if (bytes <= g_large_smem) return;
+  CKL(cudaFuncSetAttribute(pip_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  g_large_smem = bytes;
+}
+
 extern "C" {
 
 pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long *tab, int cut_rows,
                                        int sol_size, int maxcol)
 {
+  pip_large_problem *P = nullptr;
   try {
     /* no PipEngine call here: the batch engine runs this from inside PipEngine::run (lock held) */
     const int dev = pip_engine_device();
@@ -67,7 +81,7 @@ pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long
     CKL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CKL(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major < 10) throw std::runtime_error("piplib-b200: this library is built for sm_100a (B200) only");
-    pip_large_problem *P = new pip_large_problem;
+    P = new pip_large_problem;
     PipLarge &L = P->L;
     memset(&L, 0, sizeof L);
     const int ncol = nvar + 1;
@@ -106,7 +120,7 @@ pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long
     P->dyn = (size_t)(PIPL_NG + 1) * L.stride * sizeof(pip_i64);
     if (P->dyn > 200 * 1024 || getenv("PIPLIB_B200_NO_TMA")) P->dyn = 0;
     L.staged = P->dyn ? 1 : 0;
-    if (P->dyn) CKL(cudaFuncSetAttribute(pip_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->dyn));
+    if (P->dyn) pip_large_raise_smem(P->dyn);
     int per_sm = 0;
     CKL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pip_large_kernel, PIPL_THREADS, P->dyn));
     if (per_sm < 1) per_sm = 1;
@@ -114,6 +128,7 @@ pip_large_problem *pip_large_create_dp(int nvar, int ni, int nq, const long long
     return P;
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());
+    pip_large_destroy_dp(P);          /* whatever was allocated before the failure */
     return nullptr;
   }
 }
@@ -127,7 +142,7 @@ int pip_large_run_dp(pip_large_problem *P, float *kernel_ms)
     CKL(cudaGetLastError());
     void *args[] = {(void *)&P->L};
     CKL(cudaEventRecord(P->e0, P->stream));
-    if (P->dyn) CKL(cudaFuncSetAttribute(pip_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->dyn));
+    if (P->dyn) pip_large_raise_smem(P->dyn);
     CKL(cudaLaunchCooperativeKernel((void *)pip_large_kernel, dim3(P->grid), dim3(PIPL_THREADS), args, P->dyn, P->stream));
     CKL(cudaEventRecord(P->e1, P->stream));
     CKL(cudaStreamSynchronize(P->stream));

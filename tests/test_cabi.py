@@ -21,7 +21,7 @@ def _declared_functions():
         text = open(os.path.join(ROOT, hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         text = "\n".join(ln for ln in text.split("\n") if not ln.strip().startswith("#"))
-        for m in re.finditer(r"\b(pip_[a-z0-9_]+)\s*\(", text):
+        for m in re.finditer(r"\b((?:pip|sol)_[a-z0-9_]+)\s*\(", text):
             names.add(m.group(1))
     return sorted(names)
 
@@ -30,19 +30,72 @@ def test_exports_every_declared_symbol(libpath):
     lib = C.CDLL(libpath)
     names = _declared_functions()
     assert "pip_solve_dp" in names and "pip_solve_batch_dp" in names and len(names) >= 25
+    assert "sol_quast_edit_dp" in names
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
 
 
-def test_struct_layouts_match_reference():
-    # include/piplib/piplib.h:194-329 of the reference on LP64: 32/24/32/16/48/32 bytes
-    from piplib_b200 import api
-    assert C.sizeof(api.PipMatrix) == 32
-    assert C.sizeof(api.PipOptions) == 32
+# sizeof / offsetof of the six public structs on LP64 with the int64 Entier, derived from the
+# reference's include/piplib/piplib.h:194-207 (PipMatrix), 218-222 (PipVector), 234-239 (PipNewparm),
+# 249-252 (PipList), 265-272 (PipQuast), 283-327 (PipOptions)
+LAYOUT = {
+    "PipMatrix": (32, {"NbRows": 0, "NbColumns": 4, "p": 8, "p_Init": 16, "p_Init_size": 24}),
+    "PipVector": (24, {"nb_elements": 0, "the_vector": 8, "the_deno": 16}),
+    "PipNewparm": (32, {"rank": 0, "vector": 8, "deno": 16, "next": 24}),
+    "PipList": (16, {"vector": 0, "next": 8}),
+    "PipQuast": (48, {"newparm": 0, "list": 8, "condition": 16, "next_then": 24, "next_else": 32, "father": 40}),
+    "PipOptions": (32, {"Nq": 0, "Verbose": 4, "Simplify": 8, "Deepest_cut": 12, "Maximize": 16,
+                        "Urs_parms": 20, "Urs_unknowns": 24, "Compute_dual": 28}),
+}
 
-    class V(C.Structure):
-        _fields_ = [("n", C.c_int), ("a", C.c_void_p), ("b", C.c_void_p)]
-    assert C.sizeof(V) == 24
+
+def _probe_layout(include_dir, tmp_path, tag, extra=()):
+    """compile a probe against a header tree and return {struct: (size, {field: offset})}"""
+    import json
+    import subprocess
+    src = ["#include <stdio.h>", "#include <stddef.h>", "#include <piplib/piplib64.h>", "int main(void){", 'printf("{");']
+    first = True
+    for name, (_, fields) in LAYOUT.items():
+        src.append('printf("%s\\"%s\\": [%%zu, {", sizeof(%s));' % ("" if first else ", ", name, name))
+        first = False
+        for k, f in enumerate(fields):
+            src.append('printf("%s\\"%s\\": %%zu", offsetof(%s, %s));' % ("" if k == 0 else ", ", f, name, f))
+        src.append('printf("}]");')
+    src += ['printf("}\\n");', "return 0;}"]
+    c = tmp_path / ("probe_%s.c" % tag)
+    c.write_text("\n".join(src))
+    exe = tmp_path / ("probe_%s" % tag)
+    subprocess.check_call(["gcc", "-w", "-I", include_dir, *extra, str(c), "-o", str(exe)])
+    out = json.loads(subprocess.check_output([str(exe)]).decode())
+    return {k: (v[0], v[1]) for k, v in out.items()}
+
+
+def test_struct_layouts_match_reference(tmp_path):
+    """all six structs: size and every field offset, our header against the values derived from the
+    reference header -- and, where the reference tree exists (this container), against a probe compiled
+    with the reference's own piplib64.h"""
+    ours = _probe_layout(os.path.join(ROOT, "include"), tmp_path, "ours")
+    assert ours == {k: (v[0], v[1]) for k, v in LAYOUT.items()}
+    if os.path.isdir("/root/reference/include/piplib"):
+        ref = _probe_layout("/root/reference/include", tmp_path, "ref")
+        assert ref == ours
+    from piplib_b200 import api
+    assert C.sizeof(api.PipMatrix) == 32 and C.sizeof(api.PipOptions) == 32
+
+
+def test_reference_example_compiles_against_our_headers(libpath, tmp_path):
+    """the reference's only in-tree caller (example/example.c) builds unchanged against include/ and
+    links with -lpiplib_dp; the committed copy of that program is oracle-side test infrastructure
+    (tests/fixtures/), never product"""
+    import subprocess
+    src = "/root/reference/example/example.c"
+    if not os.path.exists(src):
+        pytest.skip("reference tree not present on this box")
+    exe = tmp_path / "example_dp"
+    subprocess.check_call(["gcc", "-w", "-I", os.path.join(ROOT, "include"), src, "-o", str(exe),
+                           "-L", os.path.dirname(libpath), "-lpiplib_dp",
+                           "-Wl,-rpath," + os.path.dirname(libpath), "-Wl,-rpath,/usr/local/cuda/lib64"])
+    assert exe.exists()
 
 
 def test_host_side_objects_without_gpu(libpath):

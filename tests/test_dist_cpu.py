@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from piplib_b200 import dist as pdist
-from piplib_b200 import synth
+from workloads import synth
 
 
 def _free_port():

@@ -75,7 +75,7 @@ def test_large_tableau_path_on_nonparametric_fixtures(staged):
 
 @pytest.mark.parametrize("staged", [0, 1])
 def test_large_tableau_consecutive_ones_vs_oracle(port, staged):
-    from piplib_b200 import synth
+    from workloads import synth
     nvar = 96
     tab = synth.consecutive_ones(nvar, nvar, seed=3)
     case = dict(nvar=nvar, nparm=0, ni=nvar, nc=0, bigparm=-1, nq=1, tab=tab.tolist(), ctx=[])

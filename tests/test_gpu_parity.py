@@ -154,7 +154,7 @@ def test_batch_equals_singles(api):
 def test_dense_batch_vs_oracle(api, port, workload, n):
     """seeded synthetic batch of the bench workload: status + quast hash per problem vs the oracle,
     and the serialised stream of a few problems word for word"""
-    from piplib_b200 import synth
+    from workloads import synth
     dom, ctx = synth.generate(workload, n, seed=77)
     _, st_o, h_o, stats = port.bench_dense(0, n, dom, ctx, -1)
     r = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
@@ -176,7 +176,7 @@ def test_dense_batch_vs_oracle(api, port, workload, n):
 def test_config3_and_5_families_vs_oracle(api, port, workload, n):
     """BASELINE configs 3 (cut-heavy: test<N>i-shaped, vivien32-shaped) and 5 (dependence-analysis
     shapes with perturbed constants): status, quast hash and pivot count vs the oracle"""
-    from piplib_b200 import synth
+    from workloads import synth
     dom, ctx = synth.generate(workload, n, seed=31)
     bg, opts = synth.bignum(workload), synth.options(workload)
     _, st_o, h_o, stats = port.bench_dense(0, n, dom, ctx, bg, **opts)
@@ -196,7 +196,7 @@ def test_dense_batch_with_varying_equality_rows(api, port):
     """the dense path plans a chunk from its first problem (same shape assumed for all) and checks the
     assumption while converting: a batch where the number of equality rows varies from problem to
     problem must fall back to the exact plan and still match the oracle"""
-    from piplib_b200 import synth
+    from workloads import synth
     n = 1500
     dom, ctx = synth.generate("loopnest8x12p2", n, seed=11)
     dom = dom.copy()
@@ -216,7 +216,7 @@ def test_dense_batch_with_varying_equality_rows(api, port):
 
 def test_device_resident_batch(api, port):
     """kernel-only path (inputs resident in HBM) gives the same answers as the host-buffer path"""
-    from piplib_b200 import synth
+    from workloads import synth
     dom, ctx = synth.generate("loopnest8x12p2", 4000, seed=5)
     db = api.DeviceBatch(dom, ctx, -1)
     ms = db.run(True)
@@ -245,7 +245,7 @@ def test_large_tableau_kernel_fixtures(api):
 @pytest.mark.parametrize("n", [256, 768])
 def test_large_tableau_consecutive_ones(api, port, n):
     """config-4 shaped problem (totally unimodular rows) vs the oracle with raised limits"""
-    from piplib_b200 import synth
+    from workloads import synth
     tab = synth.consecutive_ones(n, n, seed=11)
     st_o, cells_o = port.traiter(n, 0, n, 0, -1, 1, tab, [], sol_size=1 << 16, maxcol=1 << 14)
     p = api.LargeProblem(n, n, 1, tab, cut_rows=256, sol_size=1 << 16, maxcol=1 << 14)
@@ -263,7 +263,7 @@ def test_int32_and_int64_instantiations_agree_at_scale(api, port, monkeypatch):
     """200 000 problems of the bench workload: the int32-storage kernel (class S32, widen-and-rerun)
     and the int64 kernel give the same status, quast hash and serialised stream for every problem;
     a 2000-problem sample is checked against the oracle; pivot totals agree"""
-    from piplib_b200 import synth
+    from workloads import synth
     n = 200000
     dom, ctx = synth.generate("loopnest16x24p3", n, seed=2026)
     a = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
@@ -304,7 +304,7 @@ def test_alternative_paths_give_the_same_answers(api, port, monkeypatch, knob):
     """every run-time knob of INTEGRATION.md section 7 selects another route to the same answer: the
     thread-per-problem and the host decoder, the exact planning pass, the int64 shared-memory class,
     the narrow capacity slack, the large kernel without shared-memory staging"""
-    from piplib_b200 import synth
+    from workloads import synth
     monkeypatch.setenv(knob, "1")
     n = 1500
     dom, ctx = synth.generate("loopnest8x12p2", n, seed=23)
@@ -343,3 +343,54 @@ def test_ladder_hands_stragglers_to_the_grid_kernel(api, monkeypatch):
     monkeypatch.setenv("PIPLIB_B200_LARGE_FROM", "-1")
     (st, cells), = api.traiter_batch([heavy[0]])
     assert (st, cells) == (heavy[0]["ref_status"], heavy[0]["ref_cells"])
+
+
+# ---- parity at the sizes the bench quotes ("headline sizes are not parity-checked") ----
+
+def test_full_bench_batch_vs_reference(api):
+    """BASELINE config 2 at its full size: the WHOLE 10^6-problem loopnest16x24p3 batch of bench.py
+    (seed 2026) through pip_solve_dense_dp against the unmodified reference (oracle/_ref, one process
+    per host core): status and quast hash of every problem; total pivots against the oracle port."""
+    from oracle import cpu_arm as ca
+    from workloads import synth
+    n = 1000000
+    dom, ctx = synth.generate("loopnest16x24p3", n, seed=2026)
+    r = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=False)
+    piv_gpu = int(api.last_stats().pivots)
+    ref = ca.cpu_arm(dom, ctx, n)
+    assert ref["n"] == n
+    assert ca.same_answers(r["status"], r["hashes"], ref), "GPU differs from the %s on the full batch" % ref["kind"]
+    port = ca.cpu_arm(dom, ctx, n, kind="port")
+    assert ca.same_answers(r["status"], r["hashes"], port)
+    # the int32 class re-runs the few problems it hands to the int64 class: their pivots count twice
+    assert piv_gpu >= port["pivots"] and piv_gpu - port["pivots"] < port["pivots"] // 1000
+
+
+def test_c5_family_full_batch_vs_reference(api):
+    """BASELINE config 5 family (sor1d-shaped, perturbed constants) at 10^6 problems, every problem
+    against the unmodified reference"""
+    from oracle import cpu_arm as ca
+    from workloads import synth
+    n = 1000000
+    dom, ctx = synth.generate("sor1d", n, seed=2026)
+    bg, opts = synth.bignum("sor1d"), synth.options("sor1d")
+    r = api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=False, **opts)
+    ref = ca.cpu_arm(dom, ctx, n, bg=bg, opts=opts)
+    assert ca.same_answers(r["status"], r["hashes"], ref)
+
+
+def test_large_tableau_4096_vs_reference_golden(api):
+    """BASELINE config 4 at its full size (4096 x 4097, the tableau bench.py times): cells and status
+    identical to the unmodified reference built with raised limits (tests/golden/
+    large_consecutive_ones_4096.json, tools/make_golden_large.py), pivot count identical to the oracle
+    port's"""
+    from workloads import synth
+    g = load_golden("large_consecutive_ones_4096.json")
+    n = g["n"]
+    tab = synth.consecutive_ones(n, n, seed=g["seed"])
+    p = api.LargeProblem(n, n, g["nq"], tab, cut_rows=1024, sol_size=1 << 20, maxcol=1 << 16)
+    p.run()
+    st, cells, info = p.fetch()
+    p.close()
+    assert st == g["status"] and info["pivots"] == g["pivots"] and info["cuts"] == g["cuts"]
+    assert cells == g["cells"]

@@ -1,9 +1,9 @@
-"""Synthetic families (piplib_b200/synth.py): index-addressable and deterministic, and every family
+"""Synthetic families (workloads/synth.py): index-addressable and deterministic, and every family
 is something the reference can actually solve (checked with the oracle on a few problems)."""
 import numpy as np
 import pytest
 
-from piplib_b200 import synth
+from workloads import synth
 
 
 @pytest.mark.parametrize("name", sorted(synth.WORKLOADS))

@@ -17,7 +17,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from piplib_b200 import api, build, synth  # noqa: E402
+from piplib_b200 import api, build  # noqa: E402
+from workloads import synth  # noqa: E402
 
 DEFAULT_N = {"sor1d": 1000000, "cg1": 1000000, "fimmel": 200000, "esced": 500000, "expansion": 100000,
              "boulet": 20000, "test10i": 500000, "test12i": 500000, "vivien32": 4000}

@@ -10,7 +10,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, ".")
-from piplib_b200 import api, synth  # noqa: E402
+from piplib_b200 import api  # noqa: E402
+from workloads import synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3

@@ -17,7 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import pyoracle as po  # noqa: E402
-from piplib_b200 import synth  # noqa: E402
+from workloads import synth  # noqa: E402
 
 
 def work(args):

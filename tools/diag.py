@@ -6,7 +6,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, ".")
-from piplib_b200 import api, synth  # noqa: E402
+from piplib_b200 import api  # noqa: E402
+from workloads import synth  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "loopnest16x24p3"
 sizes = [int(x) for x in sys.argv[2:]] or [20000]

@@ -1,7 +1,8 @@
 import os, sys, time
 sys.path.insert(0, ".")
 os.environ["PIPLIB_B200_TIMING"] = "1"
-from piplib_b200 import api, synth
+from piplib_b200 import api  # noqa: E402
+from workloads import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 dom, ctx = synth.generate("loopnest16x24p3", n)
 r = None

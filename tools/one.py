@@ -4,7 +4,8 @@ import os, sys
 os.environ.setdefault("PIPLIB_B200_TIMING", "1")
 sys.path.insert(0, ".")
 import numpy as np
-from piplib_b200 import api, synth
+from piplib_b200 import api  # noqa: E402
+from workloads import synth
 name = sys.argv[1]
 idx = [int(x) for x in sys.argv[2:]]
 dom, ctx = synth.generate(name, max(idx) + 1)

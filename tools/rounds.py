@@ -2,7 +2,8 @@
 import os, sys
 os.environ["PIPLIB_B200_TIMING"] = "1"
 sys.path.insert(0, ".")
-from piplib_b200 import api, synth
+from piplib_b200 import api  # noqa: E402
+from workloads import synth
 name, n = sys.argv[1], int(sys.argv[2])
 dom, ctx = synth.generate(name, n)
 db = api.DeviceBatch(dom, ctx, synth.bignum(name), **synth.options(name))

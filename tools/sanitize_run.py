@@ -7,7 +7,8 @@ import sys
 import numpy as np
 
 sys.path.insert(0, ".")
-from piplib_b200 import api, synth  # noqa: E402
+from piplib_b200 import api  # noqa: E402
+from workloads import synth  # noqa: E402
 
 cases = json.load(open("tests/golden/cli_suite.json"))
 light = [c for c in cases if c["name"] in ("max", "rairoi", "test7i", "loz", "invert", "pairi", "linear", "lineri",

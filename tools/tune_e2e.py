@@ -4,7 +4,8 @@ import sys
 import time
 
 sys.path.insert(0, ".")
-from piplib_b200 import api, synth  # noqa: E402
+from piplib_b200 import api  # noqa: E402
+from workloads import synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 dom, ctx = synth.generate("loopnest16x24p3", n)
