@@ -33,6 +33,8 @@
 #ifndef PIPLIB_B200_H
 #define PIPLIB_B200_H
 
+#include <stddef.h>
+
 #include <piplib/piplib.h>
 
 #if defined(__cplusplus)
@@ -108,6 +110,21 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
                        int bignum, const PipOptions_dp *options,
                        int *status, unsigned long long *hashes,
                        long long *ser, long long ser_cap, long long *ser_off, long long *ser_len);
+
+/* Page-lock a caller buffer (cudaHostRegister, visible to every device) so that pip_solve_dense_dp moves
+ * it by DMA alone: input arrays `dom` / `ctx` registered this way are uploaded as they are and converted to
+ * tableaus on the device (tab_Matrix2Tableau_xx, source/tab.c:292-393, as a kernel); an output stream
+ * `ser` registered this way receives the serialised quasts straight from the device.  Buffers allocated
+ * page-locked by the caller (cudaHostAlloc, torch pin_memory) are recognised without this call.  Pageable
+ * buffers keep working: they are converted / widened by the host thread pool through pinned staging.
+ * The answers are identical either way.  Returns 0 or -1. */
+int pip_pin_buffer_dp(void *p, size_t bytes);
+int pip_unpin_buffer_dp(void *p);
+
+/* Devices pip_solve_dense_dp spreads a batch over (one process, several GPUs): the chunks of a batch go
+ * to whichever device has a free lane (a shared queue: dynamic balance across the GPUs), results land in
+ * the caller's arrays as for one device.  n = 0 returns to the single default device (pip_set_device_dp). */
+int pip_set_devices_dp(int n, const int *devices);
 
 /* Device-resident variant of the dense batch: converted and uploaded once by create(); run()
  * executes only kernels (plus the 56-byte-per-problem status records the size-class ladder

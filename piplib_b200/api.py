@@ -88,6 +88,11 @@ def lib():
         L.pip_large_destroy_dp.argtypes = [C.c_void_p]
         L.pip_last_batch_stats_dp.argtypes = [C.POINTER(PipBatchStats)]
         L.pip_set_device_dp.restype = C.c_int
+        L.pip_set_devices_dp.restype = C.c_int
+        L.pip_pin_buffer_dp.restype = C.c_int
+        L.pip_pin_buffer_dp.argtypes = [C.c_void_p, C.c_size_t]
+        L.pip_unpin_buffer_dp.restype = C.c_int
+        L.pip_unpin_buffer_dp.argtypes = [C.c_void_p]
         L.pip_b200_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -95,6 +100,28 @@ def lib():
 
 def set_device(dev):
     return lib().pip_set_device_dp(int(dev))
+
+
+def set_devices(devs):
+    """devices pip_solve_dense_dp spreads its chunks over (one process, several GPUs); [] = default"""
+    arr = (C.c_int * max(1, len(devs)))(*devs)
+    rc = lib().pip_set_devices_dp(len(devs), arr)
+    if rc != 0:
+        raise RuntimeError("pip_set_devices_dp failed")
+
+
+def pin(a):
+    """page-lock a numpy array in place (cudaHostRegister): pip_solve_dense_dp then moves it by DMA alone"""
+    if a is None or a.nbytes == 0:
+        return a
+    if lib().pip_pin_buffer_dp(a.ctypes.data, a.nbytes) != 0:
+        raise RuntimeError("pip_pin_buffer_dp failed")
+    return a
+
+
+def unpin(a):
+    if a is not None and a.nbytes:
+        lib().pip_unpin_buffer_dp(a.ctypes.data)
 
 
 def last_stats():
@@ -252,13 +279,27 @@ def solve_dense(dom, ctx, bignum=-1, want_hashes=True, want_ser=False, ser_cap_h
                                   ser_off.ctypes.data_as(C.c_void_p) if want_ser else None,
                                   ser_len.ctypes.data_as(C.c_void_p) if want_ser else None)
         if rc == -2:
+            was_pinned = reuse and out.get("ser") is ser
             cap = int(ser_off[n]) + 16
             ser = np.empty(cap, dtype=np.int64)
+            if was_pinned:
+                pin(ser)
             continue
         if rc != 0:
             raise RuntimeError("pip_solve_dense_dp failed: %d" % rc)
         break
     return dict(status=status, hashes=hashes, ser=ser, ser_off=ser_off, ser_len=ser_len)
+
+
+def alloc_result(n, words_per_problem=448, pinned=False):
+    """caller-owned result buffers for solve_dense(out=...); pinned=True page-locks the quast stream so
+    that the device writes it by DMA"""
+    out = dict(status=np.zeros(n, dtype=np.int32), hashes=np.zeros(n, dtype=np.uint64),
+               ser=np.empty(words_per_problem * n + 1024, dtype=np.int64),
+               ser_off=np.zeros(n + 1, dtype=np.int64), ser_len=np.zeros(n, dtype=np.int64))
+    if pinned:
+        pin(out["ser"])
+    return out
 
 
 class DeviceBatch:

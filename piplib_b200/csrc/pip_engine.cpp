@@ -61,7 +61,10 @@ struct PinBuf {
 /* team = 0: `warps` warps, one problem each; team = t: `warps` CTAs of t warps, one problem per CTA (class M) */
 struct ClassSpec { int level; int shared; long long words; int warps; int warps_per_cta; long long stack_words; int team; };
 const long long S_MAX_WORDS = 3328;          /* 26 KB: at least 8 warps of class S per SM */
-const long long S32_WIDE_MAX_WORDS = 1700;   /* 13.3 KB: 16 warps of class S32 per SM stay resident */
+#ifndef PIP_S32_WIDE_MAX_WORDS
+#define PIP_S32_WIDE_MAX_WORDS 1700          /* 13.3 KB: 16 warps of class S32 per SM stay resident */
+#endif
+const long long S32_WIDE_MAX_WORDS = PIP_S32_WIDE_MAX_WORDS;
 const ClassSpec G_LADDER[] = {
     {3, 0, 1ll << 15, 148 * 8, 4, 1ll << 17, 0},
     {4, 0, 1ll << 17, 148 * 4, 4, 1ll << 19, 4},
@@ -75,25 +78,30 @@ const int N_G = sizeof(G_LADDER) / sizeof(G_LADDER[0]);
 }  // namespace
 
 static std::atomic<int> g_device(0);
-/* the device the library works on (pip_set_device_dp); no lock: callable from inside PipEngine::run */
-int pip_engine_device() { return g_device; }
+/* the device the calling thread works on: the engine's own device while one of its runs is in progress
+ * (the whole-grid class is entered from inside PipEngine::run), else the default of pip_set_device_dp */
+static thread_local int t_run_device = -1;
+int pip_engine_device() { return t_run_device >= 0 ? t_run_device : g_device.load(); }
 
 struct PipEngine::Impl {
   std::mutex mu;
-  int device = 0, sm_count = 0;
+  int device = -1, sm_count = 0;
   size_t smem_optin = 0;
   bool inited = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total, d_prof, d_parm, d_hash;
+  DevBuf d_so_status, d_so_hash, d_so_off, d_so_len, d_so_ctl;     /* stream_out: per-problem arrays, control + stats */
+  DevBuf d_scratch[4];
+  PinBuf h_scratch[4];
   PinBuf h_hash;
-  PinBuf h_res, h_total, h_input;
+  PinBuf h_res, h_total, h_input, h_ctl;
   std::vector<PinBuf> h_chunks;     /* one per round, reused across calls */
 
   void init()
   {
     if (inited) return;
-    device = g_device;
+    if (device < 0) device = g_device.load();
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -110,23 +118,26 @@ struct PipEngine::Impl {
 };
 
 PipEngine::PipEngine() : impl_(new Impl) {}
-PipEngine &PipEngine::lane(int i)
+PipEngine &PipEngine::at(int device, int i)
 {
-  static PipEngine e[MAX_LANES];
+  /* engines are created on first use and live for the process: [device][lane] */
+  static std::mutex mu;
+  static PipEngine *table[MAX_DEVICES][MAX_LANES] = {{nullptr}};
+  if (device < 0 || device >= MAX_DEVICES) throw std::runtime_error("piplib-b200: device index out of range");
   if (i < 0) i = 0;
-  return e[i % MAX_LANES];
+  i %= MAX_LANES;
+  std::lock_guard<std::mutex> g(mu);
+  if (!table[device][i]) { table[device][i] = new PipEngine; table[device][i]->impl_->device = device; }
+  return *table[device][i];
 }
+PipEngine &PipEngine::lane(int i) { return at(g_device.load(), i); }
 int PipEngine::set_device(int dev)
 {
-  /* refused once ANY lane works on another device (lanes initialise lazily, each from g_device) */
-  for (int l = 0; l < MAX_LANES; l++) {
-    Impl &E = *lane(l).impl_;
-    std::lock_guard<std::mutex> g(E.mu);
-    if (E.inited && dev != E.device) return -1;
-  }
-  g_device = dev;
+  if (dev < 0 || dev >= MAX_DEVICES) return -1;
+  g_device = dev;          /* engines are per device: the default only selects which set serves the next call */
   return 0;
 }
+int PipEngine::device_id() { return impl_->device; }
 void *PipEngine::pinned_input(size_t bytes)
 {
   Impl &E = *impl_;
@@ -135,6 +146,24 @@ void *PipEngine::pinned_input(size_t bytes)
   CK(cudaSetDevice(E.device));
   E.h_input.reserve(bytes);
   return E.h_input.p;
+}
+void *PipEngine::device_scratch(int which, size_t bytes)
+{
+  Impl &E = *impl_;
+  std::lock_guard<std::mutex> g(E.mu);
+  E.init();
+  CK(cudaSetDevice(E.device));
+  E.d_scratch[which & 3].reserve(bytes);
+  return E.d_scratch[which & 3].p;
+}
+void *PipEngine::pinned_scratch(int which, size_t bytes)
+{
+  Impl &E = *impl_;
+  std::lock_guard<std::mutex> g(E.mu);
+  E.init();
+  CK(cudaSetDevice(E.device));
+  E.h_scratch[which & 3].reserve(bytes);
+  return E.h_scratch[which & 3].p;
 }
 int PipEngine::sm_count() { std::lock_guard<std::mutex> g(impl_->mu); impl_->init(); return impl_->sm_count; }
 cudaStream_t PipEngine::stream() { std::lock_guard<std::mutex> g(impl_->mu); impl_->init(); return impl_->stream; }
@@ -151,7 +180,8 @@ static bool large_eligible(const PipProblem &P)
   return P.nparm == 0 && P.nc == 0 && P.bigparm < 0 && !(P.flags & (PIP_F_DUAL | PIP_F_DEEPEST));
 }
 
-static void run_large_round(const PipBatchIn &in, const void *d_pool, const std::vector<int> &order, PipCell *d_cells,
+static void run_large_round(const PipBatchIn &in, const PipProblem *h_prob, const void *d_pool, int elem_log2,
+                            const std::vector<int> &order, PipCell *d_cells,
                             long long per_warp, PipResult *d_res, cudaStream_t s)
 {
   std::vector<long long> tab;
@@ -159,12 +189,12 @@ static void run_large_round(const PipBatchIn &in, const void *d_pool, const std:
   std::vector<PipCell_dp> cells((size_t)in.sol_size + 8);
   for (size_t q = 0; q < order.size(); q++) {
     const int i = order[q];
-    const PipProblem &P = in.h_prob[i];
+    const PipProblem &P = h_prob[i];
     const int ncol = P.nvar + 1;
     tab.resize((size_t)P.ni * ncol);
     /* the problem's words: from the host pool, or (device-resident batches) fetched from the device pool */
-    const size_t esz = (size_t)1 << in.elem_log2;
-    const unsigned char *src = in.h_pool ? (const unsigned char *)in.h_pool + (size_t)P.off * esz : nullptr;
+    const size_t esz = (size_t)1 << elem_log2;
+    const unsigned char *src = (in.h_pool && elem_log2 == in.elem_log2) ? (const unsigned char *)in.h_pool + (size_t)P.off * esz : nullptr;
     if (!src) {
       raw.resize(tab.size() * esz);
       CK(cudaMemcpyAsync(raw.data(), (const unsigned char *)d_pool + (size_t)P.off * esz, raw.size(), cudaMemcpyDeviceToHost, s));
@@ -172,8 +202,8 @@ static void run_large_round(const PipBatchIn &in, const void *d_pool, const std:
       src = raw.data();
     }
     for (size_t w = 0; w < tab.size(); w++)
-      tab[w] = in.elem_log2 == 0 ? (long long)((const signed char *)src)[w]
-             : in.elem_log2 == 2 ? (long long)((const int *)src)[w] : ((const long long *)src)[w];
+      tab[w] = elem_log2 == 0 ? (long long)((const signed char *)src)[w]
+             : elem_log2 == 2 ? (long long)((const int *)src)[w] : ((const long long *)src)[w];
     PipResult r;
     memset(&r, 0, sizeof r);
     r.status = PIP_ST_CAPACITY;
@@ -200,16 +230,30 @@ static void run_large_round(const PipBatchIn &in, const void *d_pool, const std:
   }
 }
 
+namespace {
+struct RunDeviceScope {          /* pip_engine_device() answers with this engine's device while it runs */
+  int saved;
+  explicit RunDeviceScope(int d) : saved(t_run_device) { t_run_device = d; }
+  ~RunDeviceScope() { t_run_device = saved; }
+};
+}  // namespace
+
 void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
 {
   Impl &E = *impl_;
   std::lock_guard<std::mutex> g(E.mu);
   E.init();
   CK(cudaSetDevice(E.device));
+  RunDeviceScope scope(E.device);
   const size_t n = in.n;
-  out.res.assign(n, PipResult());
-  out.base.assign(n, nullptr);
+  const bool stream_out = in.stream_out;
+  const bool ser_mode = in.h_decode != nullptr || in.uniform_decode != nullptr;
+  if (stream_out && !ser_mode) throw std::runtime_error("piplib-b200: stream_out needs the device decoder");
+  if (!in.h_prob && !(in.uniform && in.d_prob)) throw std::runtime_error("piplib-b200: batch without descriptors");
+  if (stream_out) { out.res.clear(); out.base.clear(); out.hashes.clear(); }
+  else { out.res.assign(n, PipResult()); out.base.assign(n, nullptr); }
   out.times = PipBatchTimes();
+  out.dev = PipDeviceOut();
   if (n == 0) return;
   const double t_begin = now_s();
   cudaStream_t s = E.stream;
@@ -217,6 +261,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
   /* ---- inputs ------------------------------------------------------------------------- */
   const PipProblem *d_prob = in.d_prob;
   const void *d_pool = in.d_pool;
+  int elem_log2 = in.elem_log2;
   double t0 = now_s();
   if (!d_prob) {
     E.d_prob.reserve(n * sizeof(PipProblem));
@@ -231,43 +276,68 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
     d_pool = E.d_pool.p;
     out.times.h2d_bytes += pool_bytes;
   }
-  /* per-problem records start as PENDING */
-  E.h_res.reserve(n * sizeof(PipResult));
-  PipResult *h_res = (PipResult *)E.h_res.p;
-  memset(h_res, 0, n * sizeof(PipResult));
-  for (size_t i = 0; i < n; i++) h_res[i].status = PIP_ST_PENDING;
+  /* per-problem records start as PENDING (written on the device: nothing to upload) */
   E.d_res.reserve(n * sizeof(PipResult));
-  CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
-  out.times.h2d_bytes += n * sizeof(PipResult);
-  const bool ser_mode = in.h_decode != nullptr;
-  if (ser_mode) {
+  CK(pip_launch_init_results((PipResult *)E.d_res.p, (long long)n, s));
+  PipResult *h_res = nullptr;            /* host mirror, fetched only when some problem has to change class */
+  auto need_h_res = [&]() {
+    if (h_res) return;
+    E.h_res.reserve(n * sizeof(PipResult));
+    h_res = (PipResult *)E.h_res.p;
+  };
+  if (in.h_decode) {
     E.d_parm.reserve(n * sizeof(PipDecodeParm));
     CK(cudaMemcpyAsync(E.d_parm.p, in.h_decode, n * sizeof(PipDecodeParm), cudaMemcpyHostToDevice, s));
+    out.times.h2d_bytes += n * sizeof(PipDecodeParm);
+  }
+  const PipDecodeParm *d_parm = in.h_decode ? (const PipDecodeParm *)E.d_parm.p : nullptr;
+  if (ser_mode && !stream_out) {
     E.d_hash.reserve(n * sizeof(pip_u64));
     CK(cudaMemsetAsync(E.d_hash.p, 0, n * sizeof(pip_u64), s));
-    out.times.h2d_bytes += n * sizeof(PipDecodeParm);
+  }
+  PipStreamOut so;
+  memset(&so, 0, sizeof so);
+  long long slots_done = 0;              /* stream_out: slots reserved by the rounds completed so far */
+  unsigned long long stats_prev[8] = {0};   /* ... and the device counters at the end of the last good round */
+  unsigned long long *h_ctl = nullptr;
+  if (stream_out) {
+    E.d_so_status.reserve(n * sizeof(int));
+    E.d_so_hash.reserve(n * sizeof(pip_u64));
+    E.d_so_off.reserve(n * sizeof(long long));
+    E.d_so_len.reserve(n * sizeof(long long));
+    E.d_so_ctl.reserve((PIP_SO_NCTL + 8) * sizeof(unsigned long long));
+    CK(cudaMemsetAsync(E.d_so_ctl.p, 0, (PIP_SO_NCTL + 8) * sizeof(unsigned long long), s));
+    E.h_ctl.reserve((PIP_SO_NCTL + 8) * sizeof(unsigned long long));
+    h_ctl = (unsigned long long *)E.h_ctl.p;
+    const long long hint = in.words_hint > 0 ? in.words_hint : (long long)n * (in.words64 ? 640 : 384);
+    E.d_compact.reserve((size_t)std::max<long long>(hint, 1024) * sizeof(pip_u64));
+    so.ctl = (unsigned long long *)E.d_so_ctl.p;
+    so.stats = so.ctl + PIP_SO_NCTL;
+    so.cap = (long long)(E.d_compact.cap / sizeof(pip_u64));
+    so.words64 = in.words64 ? 1 : 0;
+    so.status = (int *)E.d_so_status.p; so.hash = (pip_u64 *)E.d_so_hash.p;
+    so.off = (long long *)E.d_so_off.p; so.len = (long long *)E.d_so_len.p;
   }
   E.d_queue.reserve(64);
   E.d_prof.reserve(sizeof(unsigned long long) * PIP_NPHASE);
   CK(cudaMemsetAsync(E.d_prof.p, 0, sizeof(unsigned long long) * PIP_NPHASE, s));
   E.d_total.reserve(64);
   E.h_total.reserve(64);
-  CK(cudaStreamSynchronize(s));
-  out.times.h2d = now_s() - t0;
+  out.times.h2d = now_s() - t0;          /* enqueue time only: the copies overlap what follows on the stream */
 
   /* ---- plan: class S32 (int32 storage, shared memory) for problems shipped with narrow inputs,
    * class S (int64, shared memory) for everything else whose level-2 working set fits an arena,
-   * the global-memory ladder for the rest */
+   * the global-memory ladder for the rest.  A uniform batch is planned once from its shape. */
   const bool try32 = in.elem_log2 <= 2 && getenv("PIPLIB_B200_NO_INT32") == nullptr;
   std::vector<int> cls(n);              /* -2 = class S32, -1 = class S, k = G_LADDER[k] */
   long long s_words = 0, s32_words = 0, s32_wide_words = 0, est_cells_total = 0;
   bool all_sized = true;
-  for (size_t i = 0; i < n; i++) {
-    const PipProblem &P = in.h_prob[i];
+  auto plan_one = [&](const PipProblem &P) -> int {
     if (!(P.flags & PIP_F_SIMPLE_SER)) all_sized = false;
+    int c;
     long long w = pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2, 8);
     if (w <= S_MAX_WORDS && !(P.flags & (PIP_F_DUAL | PIP_F_DEEPEST))) {   /* options: global-memory classes only */
-      cls[i] = try32 ? -2 : -1;
+      c = try32 ? -2 : -1;
       s_words = std::max(s_words, w);
       if (try32) {
         s32_words = std::max(s32_words, pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, 2, 4));
@@ -276,9 +346,20 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
     } else {
       int k = 0;
       while (k < N_G - 1 && pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, G_LADDER[k].level, 8) > G_LADDER[k].words) k++;
-      cls[i] = k;
+      c = k;
     }
-    est_cells_total += 3ll * (1 + P.nvar * (2 + P.nparm)) + 32;
+    return c;
+  };
+  if (in.uniform) {
+    const int c = plan_one(*in.uniform);
+    std::fill(cls.begin(), cls.end(), c);
+    est_cells_total = (long long)n * (3ll * (1 + in.uniform->nvar * (2 + in.uniform->nparm)) + 32);
+  } else {
+    for (size_t i = 0; i < n; i++) {
+      const PipProblem &P = in.h_prob[i];
+      cls[i] = plan_one(P);
+      est_cells_total += 3ll * (1 + P.nvar * (2 + P.nparm)) + 32;
+    }
   }
   s_words = (s_words + 1) & ~1ll;
   s32_words = (s32_words + 1) & ~1ll;
@@ -286,12 +367,24 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
    * fewer problems have to be re-run in a global-memory class */
   const bool s32_wide = try32 && s32_wide_words <= S32_WIDE_MAX_WORDS && getenv("PIPLIB_B200_NO_WIDE_SLACK") == nullptr;
   if (s32_wide) s32_words = (s32_wide_words + 1) & ~1ll;
+  /* host descriptors for the rare paths that look at single problems (the whole-grid class) */
+  std::vector<PipProblem> fetched_prob;
+  auto host_prob = [&]() -> const PipProblem * {
+    if (in.h_prob) return in.h_prob;
+    if (fetched_prob.empty()) {
+      fetched_prob.resize(n);
+      CK(cudaMemcpyAsync(fetched_prob.data(), d_prob, n * sizeof(PipProblem), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+    }
+    return fetched_prob.data();
+  };
 
   CK(cudaEventRecord(E.ev0, s));
   std::vector<int> order;
   order.reserve(n);
   int round = 0;
-  for (int k = -2; k < N_G; k++) {
+  size_t open_total = n;                /* problems not final yet, all classes */
+  for (int k = -2; k < N_G && open_total; k++) {
     int last_open = -1;                 /* problems of this class still open after the previous attempt */
     for (int attempt = 0;; attempt++) {
       order.clear();
@@ -303,6 +396,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       if (last_open >= 0 && m >= last_open)
         throw std::runtime_error("piplib-b200: size class made no progress (" + std::to_string(m) + " problems open)");
       last_open = m;
+      const bool identity = (size_t)m == n;           /* every problem of the batch: no permutation needed */
       /* geometry of this round */
       ClassSpec cs;
       int ctas;
@@ -337,14 +431,17 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       E.d_cells.reserve((size_t)per_warp * cs.warps * sizeof(PipCell));
       E.d_stack.reserve((size_t)cs.stack_words * cs.warps * sizeof(pip_i64));
       if (!cs.shared) E.d_gwork.reserve((size_t)cs.words * cs.warps * sizeof(pip_i64));
-      E.d_order.reserve((size_t)m * sizeof(int));
-      E.d_off.reserve((size_t)m * sizeof(long long));
-      CK(cudaMemcpyAsync(E.d_order.p, order.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, s));
+      if (!identity) {
+        E.d_order.reserve((size_t)m * sizeof(int));
+        CK(cudaMemcpyAsync(E.d_order.p, order.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, s));
+      }
+      const int *d_order = identity ? nullptr : (const int *)E.d_order.p;
+      if (!stream_out) E.d_off.reserve((size_t)m * sizeof(long long));
       CK(cudaMemsetAsync(E.d_queue.p, 0, 16, s));
 
       PipLaunch L;
       memset(&L, 0, sizeof L);
-      L.prob = d_prob; L.pool = d_pool; L.pool_elem_log2 = in.elem_log2; L.order = (const int *)E.d_order.p; L.nprob = m;
+      L.prob = d_prob; L.pool = d_pool; L.pool_elem_log2 = elem_log2; L.order = d_order; L.nprob = m;
       L.res = (PipResult *)E.d_res.p;
       L.cells = (PipCell *)E.d_cells.p; L.cells_per_warp = per_warp;
       L.stack = (pip_i64 *)E.d_stack.p; L.stack_words_per_warp = cs.stack_words;
@@ -358,104 +455,164 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       /* PIPLIB_B200_LARGE_FROM=<class index> moves the hand-over (tests), a negative value disables it */
       const char *lf = getenv("PIPLIB_B200_LARGE_FROM");
       const int large_from = lf && *lf ? atoi(lf) : PIP_LARGE_FROM_DEFAULT;
-      bool use_large = large_from >= 0 && k >= large_from && m <= 4 && in.elem_log2 <= 3;
-      for (int q = 0; q < m && use_large; q++) use_large = large_eligible(in.h_prob[order[q]]);
+      bool use_large = large_from >= 0 && k >= large_from && m <= 4 && elem_log2 <= 3;
+      if (use_large) { const PipProblem *hp = host_prob(); for (int q = 0; q < m && use_large; q++) use_large = large_eligible(hp[order[q]]); }
       if (use_large) {
-        run_large_round(in, d_pool, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
+        run_large_round(in, host_prob(), d_pool, elem_log2, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
         out.times.launches += m;
       } else {
         CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? 3 : cs.shared, ctas, cs.warps_per_cta, s));
         out.times.launches++;
       }
-      /* compact this round's output: packed cells, or (device-decode mode) serialised quasts */
+      /* this round's output: packed cells, or (device-decode mode) serialised quasts */
       if (ser_mode && (!all_sized || use_large)) {      /* sizing pass, unless the solver sized every stream itself */
-        CK(pip_launch_serialize((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
-                                (const PipDecodeParm *)E.d_parm.p, nullptr, nullptr, nullptr, m, 0, s));
+        CK(pip_launch_serialize((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p, d_parm, in.uniform_decode,
+                                nullptr, nullptr, nullptr, m, 0, nullptr, s));
         out.times.launches++;
       }
-      CK(pip_launch_gather((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
-                           (long long *)E.d_off.p, nullptr, m, (long long *)E.d_total.p, ser_mode ? 2 : 0, s));
-      out.times.launches++;
-      CK(cudaMemcpyAsync(E.h_total.p, E.d_total.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      const long long total = *(long long *)E.h_total.p;
-      E.d_compact.reserve((size_t)std::max<long long>(total, 1) * sizeof(pip_u64));
-      if (ser_mode)
-        CK(pip_launch_serialize((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
-                                (const PipDecodeParm *)E.d_parm.p, (const long long *)E.d_off.p,
-                                (pip_i64 *)E.d_compact.p, (pip_u64 *)E.d_hash.p, m, 1, s));
-      else
-        CK(pip_launch_gather((PipResult *)E.d_res.p, (const int *)E.d_order.p, (const PipCell *)E.d_cells.p,
-                             (long long *)E.d_off.p, (pip_u64 *)E.d_compact.p, m, (long long *)E.d_total.p, 1, s));
-      out.times.launches++;
-      CK(cudaEventRecord(E.ev1, s));
-      CK(cudaStreamSynchronize(s));
+      long long total = 0;
+      int finals = -1;                   /* stream_out: problems of this round with a final status */
+      if (stream_out) {
+        /* decode with span reservation: no scan, no host round trip before the decode; if the compact
+         * buffer turns out too small, grow it and decode the round again (the cells are still there) */
+        for (;;) {
+          CK(cudaMemsetAsync(so.ctl + PIP_SO_FINALS, 0, 2 * sizeof(unsigned long long), s));   /* finals, overflow */
+          CK(pip_launch_serialize((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p, d_parm, in.uniform_decode,
+                                  nullptr, (pip_i64 *)E.d_compact.p, nullptr, m, 1, &so, s));
+          out.times.launches++;
+          CK(cudaEventRecord(E.ev1, s));
+          CK(cudaMemcpyAsync(h_ctl, so.ctl, (PIP_SO_NCTL + 8) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+          CK(cudaStreamSynchronize(s));
+          if (!h_ctl[PIP_SO_OVERFLOW]) break;
+          /* h_ctl[SLOTS] = what the rounds so far need in total.  Grow, keep the spans of the earlier rounds,
+           * rewind the control block (slot cursor, counters) to the end of the previous round, decode again */
+          const long long need = (long long)h_ctl[PIP_SO_SLOTS];
+          DevBuf bigger;
+          bigger.reserve((size_t)(need + need / 4 + 1024) * sizeof(pip_u64));
+          if (slots_done) CK(cudaMemcpyAsync(bigger.p, E.d_compact.p, (size_t)slots_done * sizeof(pip_u64), cudaMemcpyDeviceToDevice, s));
+          h_ctl[PIP_SO_SLOTS] = (unsigned long long)slots_done;
+          h_ctl[PIP_SO_FINALS] = h_ctl[PIP_SO_OVERFLOW] = h_ctl[3] = 0;
+          for (int c = 0; c < 8; c++) h_ctl[PIP_SO_NCTL + c] = stats_prev[c];
+          CK(cudaMemcpyAsync(so.ctl, h_ctl, (PIP_SO_NCTL + 8) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+          CK(cudaStreamSynchronize(s));
+          E.d_compact.release();
+          E.d_compact = bigger;
+          so.cap = (long long)(E.d_compact.cap / sizeof(pip_u64));
+        }
+        for (int c = 0; c < 8; c++) stats_prev[c] = h_ctl[PIP_SO_NCTL + c];
+        finals = (int)h_ctl[PIP_SO_FINALS];
+        total = (long long)h_ctl[PIP_SO_SLOTS] - slots_done;
+      } else {
+        CK(pip_launch_gather((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p,
+                             (long long *)E.d_off.p, nullptr, m, (long long *)E.d_total.p, ser_mode ? 2 : 0, s));
+        out.times.launches++;
+        CK(cudaMemcpyAsync(E.h_total.p, E.d_total.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        total = *(long long *)E.h_total.p;
+        E.d_compact.reserve((size_t)std::max<long long>(total, 1) * sizeof(pip_u64));
+        if (ser_mode)
+          CK(pip_launch_serialize((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p, d_parm, in.uniform_decode,
+                                  (const long long *)E.d_off.p, (pip_i64 *)E.d_compact.p, (pip_u64 *)E.d_hash.p, m, 1,
+                                  nullptr, s));
+        else
+          CK(pip_launch_gather((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p,
+                               (long long *)E.d_off.p, (pip_u64 *)E.d_compact.p, m, (long long *)E.d_total.p, 1, s));
+        out.times.launches++;
+        CK(cudaEventRecord(E.ev1, s));
+        CK(cudaStreamSynchronize(s));
+      }
       out.times.kernel += now_s() - tk;
       if (round < 8) { out.times.round_s[round] = (float)(now_s() - tk); out.times.round_n[round] = m; }
-      /* fetch records (+ cells) */
-      double td = now_s();
-      CK(cudaMemcpyAsync(h_res, E.d_res.p, n * sizeof(PipResult), cudaMemcpyDeviceToHost, s));
-      out.times.d2h_bytes += n * sizeof(PipResult);
-      if ((size_t)round >= E.h_chunks.size()) E.h_chunks.resize(round + 1);
-      PinBuf &chunk = E.h_chunks[round];
-      if (in.fetch_cells && total > 0) {
-        chunk.reserve((size_t)total * sizeof(pip_u64));
-        CK(cudaMemcpyAsync(chunk.p, E.d_compact.p, (size_t)total * sizeof(pip_u64), cudaMemcpyDeviceToHost, s));
-        out.times.d2h_bytes += (size_t)total * sizeof(pip_u64);
-      }
-      CK(cudaStreamSynchronize(s));
-      out.times.d2h += now_s() - td;
-      round++;
-      out.times.rounds++;
-      /* classify */
-      int pending = 0;
       const double t_round = now_s() - tk;
-      for (int q = 0; q < m; q++) {
-        const int i = order[q];
-        const PipResult &r = h_res[i];
-        if (r.status == PIP_ST_PENDING) { pending++; continue; }
-        if (r.status == PIP_ST_WIDEN) { cls[i] = -1; h_res[i].status = PIP_ST_PENDING; continue; }
-        if (r.status == PIP_ST_CAPACITY && k + 1 < N_G && !use_large) {   /* class L has no larger class above it */
-          /* the wide int32 class already has half of G3's cut rows and all of its context rows: what
-           * outgrew it goes straight to the first team class (4x the rows) instead of failing G3 too */
-          cls[i] = k < 0 ? ((k == -2 && s32_wide) ? 1 : 0) : k + 1;
-          h_res[i].status = PIP_ST_PENDING;
-          continue;
+      int pending = 0, escalated = 0;
+      if (stream_out && finals == m) {
+        /* the common case: every problem of the round is final -- nothing per problem crosses PCIe */
+        for (int q = 0; q < m; q++) cls[order[q]] = 1000;
+        slots_done += total;
+        open_total -= (size_t)m;
+        round++;
+        out.times.rounds++;
+      } else {
+        /* fetch records (+ cells) */
+        double td = now_s();
+        need_h_res();
+        CK(cudaMemcpyAsync(h_res, E.d_res.p, n * sizeof(PipResult), cudaMemcpyDeviceToHost, s));
+        out.times.d2h_bytes += n * sizeof(PipResult);
+        PinBuf *chunk = nullptr;
+        if (!stream_out) {
+          if ((size_t)round >= E.h_chunks.size()) E.h_chunks.resize(round + 1);
+          chunk = &E.h_chunks[round];
+          if (in.fetch_cells && total > 0) {
+            chunk->reserve((size_t)total * sizeof(pip_u64));
+            CK(cudaMemcpyAsync(chunk->p, E.d_compact.p, (size_t)total * sizeof(pip_u64), cudaMemcpyDeviceToHost, s));
+            out.times.d2h_bytes += (size_t)total * sizeof(pip_u64);
+          }
         }
-        cls[i] = 1000;                       /* final */
-        out.res[i] = r;
-        out.base[i] = (const pip_u64 *)chunk.p;
-      }
-      if (getenv("PIPLIB_B200_TIMING")) {
-        int esc = 0;
-        for (int q = 0; q < m; q++) if (cls[order[q]] != 1000) esc++;
-        fprintf(stderr, "[piplib-b200] round %d: class %d attempt %d, %d problems on %d warps (%d words/warp): %.3f s, %d not final (%d pending)%s\n",
-                round - 1, k, attempt, m, cs.warps, (int)cs.words, t_round, esc, pending, use_large ? " [whole-grid kernel]" : "");
-      }
-      if (pending == 0) {
-        /* re-arm the escalated problems on the device */
-        bool any_escalated = false;
-        for (int q = 0; q < m; q++) if (cls[order[q]] != 1000 && cls[order[q]] != k) { any_escalated = true; break; }
-        if (any_escalated) {
+        CK(cudaStreamSynchronize(s));
+        out.times.d2h += now_s() - td;
+        slots_done += total;
+        round++;
+        out.times.rounds++;
+        /* classify */
+        bool widened_input = false;
+        for (int q = 0; q < m; q++) {
+          const int i = order[q];
+          const PipResult &r = h_res[i];
+          if (r.status == PIP_ST_PENDING) { pending++; continue; }
+          if (r.status == PIP_ST_WIDEN) { cls[i] = -1; h_res[i].status = PIP_ST_PENDING; escalated++; widened_input = true; continue; }
+          if (r.status == PIP_ST_CAPACITY && k + 1 < N_G && !use_large) {   /* class L has no larger class above it */
+            /* the wide int32 class already has half of G3's cut rows and all of its context rows: what
+             * outgrew it goes straight to the first team class (4x the rows) instead of failing G3 too */
+            cls[i] = k < 0 ? ((k == -2 && s32_wide) ? 1 : 0) : k + 1;
+            h_res[i].status = PIP_ST_PENDING;
+            escalated++;
+            continue;
+          }
+          cls[i] = 1000;                       /* final */
+          open_total--;
+          if (!stream_out) {
+            out.res[i] = r;
+            out.base[i] = (const pip_u64 *)chunk->p;
+          }
+        }
+        /* a problem whose input did not fit the int32 pool: from now on every round reads the int64 pool */
+        if (widened_input && elem_log2 < 3 && in.widen_pool) {
+          d_pool = in.widen_pool(in.widen_ctx, s);
+          elem_log2 = 3;
+        }
+        if (pending || escalated) {
+          /* re-arm the open problems on the device */
           CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
           CK(cudaStreamSynchronize(s));
         }
-        break;
       }
-      CK(cudaMemcpyAsync(E.d_res.p, h_res, n * sizeof(PipResult), cudaMemcpyHostToDevice, s));
-      CK(cudaStreamSynchronize(s));
+      if (getenv("PIPLIB_B200_TIMING"))
+        fprintf(stderr, "[piplib-b200] round %d: class %d attempt %d, %d problems on %d warps (%d words/warp): %.3f s, %d not final (%d pending)%s\n",
+                round - 1, k, attempt, m, cs.warps, (int)cs.words, t_round, escalated + pending, pending, use_large ? " [whole-grid kernel]" : "");
+      if (pending == 0) break;
     }
   }
   CK(cudaEventElapsedTime(&out.times.device_ms, E.ev0, E.ev1));
-  if (ser_mode) {
-    E.h_hash.reserve(n * sizeof(pip_u64));
-    CK(cudaMemcpy(E.h_hash.p, E.d_hash.p, n * sizeof(pip_u64), cudaMemcpyDeviceToHost));
-    out.hashes.assign((const pip_u64 *)E.h_hash.p, (const pip_u64 *)E.h_hash.p + n);
-    out.times.d2h_bytes += n * sizeof(pip_u64);
+  if (stream_out) {
+    out.dev.words = (const pip_i64 *)E.d_compact.p;
+    out.dev.slots = slots_done;
+    out.dev.status = so.status; out.dev.hash = so.hash; out.dev.off = so.off; out.dev.len = so.len;
+    for (int k = 0; k < 8; k++) out.dev.stats[k] = h_ctl[PIP_SO_NCTL + k];
+    /* anything still unsolved is too large for the ladder: its status array entry says CAPACITY already
+     * (the last decode pass wrote the record's status) */
+  } else {
+    if (ser_mode) {
+      E.h_hash.reserve(n * sizeof(pip_u64));
+      CK(cudaMemcpy(E.h_hash.p, E.d_hash.p, n * sizeof(pip_u64), cudaMemcpyDeviceToHost));
+      out.hashes.assign((const pip_u64 *)E.h_hash.p, (const pip_u64 *)E.h_hash.p + n);
+      out.times.d2h_bytes += n * sizeof(pip_u64);
+    }
+    /* anything still unsolved is too large for the ladder */
+    for (size_t i = 0; i < n; i++)
+      if (cls[i] != 1000) { out.res[i] = PipResult(); out.res[i].status = PIP_ST_CAPACITY; }
   }
+#ifdef PIP_PROFILE
   CK(cudaMemcpy(out.times.phase_cycles, E.d_prof.p, sizeof(unsigned long long) * PIP_NPHASE, cudaMemcpyDeviceToHost));
-  /* anything still unsolved is too large for the ladder */
-  for (size_t i = 0; i < n; i++)
-    if (cls[i] != 1000) { out.res[i] = PipResult(); out.res[i].status = PIP_ST_CAPACITY; }
+#endif
   out.times.total = now_s() - t_begin;
 }

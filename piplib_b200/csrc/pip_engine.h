@@ -22,6 +22,28 @@ struct PipBatchIn {
   const PipDecodeParm *h_decode = nullptr; /* if set: decode on the device, ship serialised quast words
                                               (+ hashes) instead of cells */
   int sol_size = PIP_SOL_SIZE, maxcol = PIP_MAXCOL;
+  /* ---- dense path (pip_solve_dense_dp) ---- */
+  const PipProblem *uniform = nullptr;  /* every problem has this shape (ni / nc = the maxima over the batch): the
+                                           plan is made once, h_prob may be NULL when d_prob is given */
+  const PipDecodeParm *uniform_decode = nullptr;   /* device decode, one parameter set for every problem */
+  bool stream_out = false;              /* decode with span reservation; the serialised words and the per-problem
+                                           arrays stay on the device (PipBatchOut::dev), nothing per problem
+                                           crosses PCIe inside run() unless a problem has to change class */
+  bool words64 = false;                 /* stream_out: every word as int64 (else int32 where it fits) */
+  long long words_hint = 0;             /* stream_out: expected 64-bit slots for the whole batch (0 = default) */
+  /* called when a problem's input does not fit the int32 pool (PIP_F_WIDE_INPUT): returns the int64 pool */
+  const void *(*widen_pool)(void *ctx, cudaStream_t s) = nullptr;
+  void *widen_ctx = nullptr;
+};
+
+/* device-resident results of a stream_out run: valid until the next run() on the same engine */
+struct PipDeviceOut {
+  const pip_i64 *words = nullptr;       /* compact buffer, 64-bit slots */
+  long long slots = 0;                  /* slots used */
+  const int *status = nullptr;
+  const pip_u64 *hash = nullptr;
+  const long long *off = nullptr, *len = nullptr;   /* per problem: slot offset, words | PIP_LEN_NARROW */
+  unsigned long long stats[8] = {0};    /* pivots, cuts, subsolves, splits, elem_updates, cells, max_rows, max_cols */
 };
 
 struct PipBatchTimes {
@@ -49,6 +71,7 @@ struct PipBatchOut {
   std::vector<const pip_u64 *> base;    /* per problem: base pointer of its round's host chunk */
   std::vector<pip_u64> hashes;          /* device-decode mode: hash of each serialised quast */
   PipBatchTimes times;
+  PipDeviceOut dev;                     /* stream_out mode */
   PipCellView cells_of(size_t i) const
   {
     PipCellView v;
@@ -63,9 +86,14 @@ class PipEngine {
  public:
   static PipEngine &get() { return lane(0); }
   /* independent engines (own stream + buffers) so that batches can be pipelined: while one lane
-   * waits for its kernels, another converts inputs or decodes results */
-  enum { MAX_LANES = 8 };
-  static PipEngine &lane(int i);
+   * waits for its kernels, another converts inputs or decodes results; one set of lanes per device */
+  enum { MAX_LANES = 8, MAX_DEVICES = 16 };
+  static PipEngine &lane(int i);                 /* on the default device (pip_set_device_dp) */
+  static PipEngine &at(int device, int lane);
+  /* engine-owned device scratch for the caller's raw input rows and converted pool (dense path) */
+  void *device_scratch(int which, size_t bytes);
+  void *pinned_scratch(int which, size_t bytes);
+  int device_id();
   /* engine-owned pinned staging for the input pool (valid until the next call on this lane) */
   void *pinned_input(size_t bytes);
   /* Runs the whole ladder.  Host cell storage referenced by `out` is engine-owned pinned memory,

@@ -11,12 +11,15 @@
  *   printers / alloc / free source/piplib.c:176-619
  */
 #include <ctype.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -27,8 +30,10 @@
 #endif
 
 #include "../../include/piplib_b200.h"
+#include "pip_convert.h"
 #include "pip_decode.h"
 #include "pip_engine.h"
+#include "pip_kernels.h"
 
 typedef long long I;
 
@@ -61,23 +66,20 @@ struct Shape {
 struct MatView { int rows, cols; const I *const *row; const I *dense; };
 inline I MV(const MatView &m, int i, int j) { return m.row ? m.row[i][j] : m.dense[(size_t)i * m.cols + j]; }
 
-Shape derive_shape(const MatView &dom, const MatView *ctx, int Bg, const PipOptions_dp &o)
+/* the part that depends on the dimensions and the options only (Nl / Nm are left 0) */
+Shape derive_shape_dims(int dom_cols, const MatView *ctx, int Bg, const PipOptions_dp &o)
 {
   Shape s;
   memset(&s, 0, sizeof s);
   s.has_ctx = ctx != nullptr;
   s.Np = ctx ? ctx->cols - 2 : 0;
-  s.Nn = dom.cols - s.Np - 2;
-  s.Nl = dom.rows;
-  for (int i = 0; i < dom.rows; i++) if (MV(dom, i, 0) == 0) s.Nl++;
+  s.Nn = dom_cols - s.Np - 2;
   if (o.Maximize) { s.sol_flags |= S_SHIFT | S_NEGATE; s.Shift = 1; }
   else if (o.Urs_unknowns) { s.sol_flags |= S_SHIFT; s.Shift = -1; }
   if (o.Urs_parms) { s.Urs = s.Np - (Bg >= 0); s.Np += s.Urs; }
   if (o.Maximize || o.Urs_unknowns)
-    if (Bg < 0) { Bg = dom.cols - 1; s.Np++; s.sol_flags |= S_REMOVE; }
+    if (Bg < 0) { Bg = dom_cols - 1; s.Np++; s.sol_flags |= S_REMOVE; }
   s.Bg = Bg;
-  s.Nm = 0;
-  if (ctx) { s.Nm = ctx->rows; for (int i = 0; i < ctx->rows; i++) if (MV(*ctx, i, 0) == 0) s.Nm++; }
   s.nq = o.Nq;
   s.flags = 0;
   if (o.Nq) s.flags |= PIP_F_INT;
@@ -86,56 +88,32 @@ Shape derive_shape(const MatView &dom, const MatView *ctx, int Bg, const PipOpti
   return s;
 }
 
-/* tab_Matrix2Tableau_xx (source/tab.c:292-393) writing `width`-wide rows to out.
+Shape derive_shape(const MatView &dom, const MatView *ctx, int Bg, const PipOptions_dp &o)
+{
+  Shape s = derive_shape_dims(dom.cols, ctx, Bg, o);
+  s.Nl = dom.rows;                      /* an equality becomes two tableau rows, source/tab.c:327-337 */
+  for (int i = 0; i < dom.rows; i++) if (MV(dom, i, 0) == 0) s.Nl++;
+  s.Nm = 0;
+  if (ctx) { s.Nm = ctx->rows; for (int i = 0; i < ctx->rows; i++) if (MV(*ctx, i, 0) == 0) s.Nm++; }
+  return s;
+}
+
+/* tab_Matrix2Tableau_xx (source/tab.c:292-393) writing `width`-wide rows to out: the per-row body is
+ * pip_convert_row (pip_convert.h), shared with the device-side conversion kernel.
  * ctx_mode: the matrix is the context (n == -1 in the reference). */
 /* returns false when some value does not fit the element type T */
 template <class T>
 bool matrix_to_rows(const MatView &mx, T *out, int width, int Nv, bool ctx_mode, int Shift, int Bg, int Urs)
 {
   I lost = 0;
-#define PIP_ST(dst, val) do { const I v_ = (val); const T t_ = (T)v_; (dst) = t_; lost |= ((I)t_ ^ v_); } while (0)
-  const int ctx = ctx_mode ? 1 : 0;
-  int ncolm = mx.cols - 1;
-  const bool isnew = Shift && (Bg + ctx > 0) && ((unsigned)(Bg + ctx) > (unsigned)(mx.cols - 2));
-  if (isnew) ncolm++;
-  int cst;
-  if (ctx) { Shift = 0; cst = Nv + Urs; } else cst = Nv;
   int cur = 0;
   for (int i = 0; i < mx.rows; i++) {
+    const I *in = mx.row ? mx.row[i] : mx.dense + (size_t)i * mx.cols;
     T *r = out + (size_t)cur * width;
-    for (int j = 0; j < width; j++) r[j] = 0;
-    I big = 0;
-    const bool ineq = MV(mx, i, 0) != 0;
-    int j;
-    for (j = 0; j < Nv; j++) {
-      if (isnew && j == Bg) continue;
-      if (Shift) big += MV(mx, i, 1 + j);
-      PIP_ST(r[j], Shift > 0 ? -MV(mx, i, 1 + j) : MV(mx, i, 1 + j));
-    }
-    int k = Nv + 1;
-    for (j = Nv + 1; j < ncolm; j++) {
-      if (isnew && j == Bg) continue;
-      PIP_ST(r[j], MV(mx, i, k));
-      k++;
-    }
-    for (j = 0; j < Urs; j++) {
-      int pos_n = ncolm - ctx + j, pos = pos_n - Urs;
-      if (pos <= Bg) --pos;
-      PIP_ST(r[pos_n], -(I)r[pos]);
-    }
-    PIP_ST(r[cst], MV(mx, i, mx.cols - 1));
-    if (Shift) {
-      if (Shift < 0) big = -big;
-      if (isnew) PIP_ST(r[Bg], big); else PIP_ST(r[Bg], (I)r[Bg] + big);
-    }
+    const bool ineq = pip_convert_row<T>(in, mx.cols, r, width, Nv, ctx_mode ? 1 : 0, Shift, Bg, Urs, lost);
     cur++;
-    if (!ineq) {
-      T *r2 = out + (size_t)cur * width;
-      for (j = 0; j < width; j++) PIP_ST(r2[j], -(I)r[j]);
-      cur++;
-    }
+    if (!ineq) { pip_convert_negate<T>(r, r + width, width, lost); cur++; }
   }
-#undef PIP_ST
   return lost == 0;
 }
 
@@ -360,20 +338,106 @@ void account(const PipBatchOut &out, double host_seconds)
   publish_stats(s);
 }
 
+/* ---- host threads: one persistent pool per process -----------------------------------------------
+ * Size = the cores this process may use (sched_getaffinity) divided by the ranks that share the node
+ * (LOCAL_WORLD_SIZE, set by torchrun / mpirun wrappers; PIPLIB_B200_THREADS overrides): 8 ranks on a
+ * 32-core box get 4 workers each instead of 8 x 64 threads fighting for 32 cores.  Workers are created
+ * once and parked on a condition variable; a parallel region hands out index ranges through an atomic
+ * counter and the caller works too. */
+class HostPool {
+ public:
+  /* never destroyed: the workers are detached and parked on the condition variable for the life of the
+   * process (destroying a condition variable with waiters blocks in glibc -- the process would hang at exit) */
+  static HostPool &get() { static HostPool *p = new HostPool; return *p; }
+  size_t size() const { return nworkers_ + 1; }
+  /* f(range index, begin, end) over `parts` nearly equal ranges of [0, n) */
+  template <class F>
+  void ranges(size_t n, size_t parts, F f)
+  {
+    parts = std::max<size_t>(1, std::min(parts, (n + 63) / 64));
+    const size_t per = (n + parts - 1) / parts;
+    if (parts == 1 || nworkers_ == 0) {
+      for (size_t t = 0; t < parts; t++) { const size_t a = t * per, b = std::min(n, a + per); if (a < b) f(t, a, b); }
+      return;
+    }
+    Job job;
+    job.parts = parts;
+    job.run = [&](size_t t) { const size_t a = t * per, b = std::min(n, a + per); if (a < b) f(t, a, b); };
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      jobs_.push_back(&job);
+      job.active = 1;                   /* the caller takes ranges too */
+    }
+    cv_.notify_all();
+    work_on(job);
+    std::unique_lock<std::mutex> lk(mu_);
+    /* the job lives on this stack: wait until every range is done AND no worker still holds the pointer */
+    job.done_cv.wait(lk, [&] { return job.finished == job.parts && job.active == 0; });
+    jobs_.erase(std::find(jobs_.begin(), jobs_.end(), &job));
+  }
+
+ private:
+  struct Job {
+    size_t parts = 0;
+    std::atomic<size_t> next{0};
+    size_t finished = 0;                /* under mu_ */
+    int active = 0;                     /* threads inside work_on for this job, under mu_ */
+    std::function<void(size_t)> run;
+    std::condition_variable done_cv;
+  };
+  HostPool()
+  {
+    size_t cores = 1;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0) cores = std::max(1, CPU_COUNT(&set));
+    else cores = std::max(1u, std::thread::hardware_concurrency());
+    size_t share = 1;
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) share = std::max(1, atoi(lw));
+    size_t want = std::max<size_t>(1, cores / share);
+    if (const char *t = getenv("PIPLIB_B200_THREADS")) if (atoi(t) > 0) want = (size_t)atoi(t);
+    nworkers_ = want > 1 ? want - 1 : 0;
+    for (size_t i = 0; i < nworkers_; i++) std::thread([this] { worker(); }).detach();
+  }
+  void work_on(Job &job)
+  {
+    size_t mine = 0;
+    for (;;) {
+      const size_t t = job.next.fetch_add(1);
+      if (t >= job.parts) break;
+      job.run(t);
+      mine++;
+    }
+    std::lock_guard<std::mutex> g(mu_);
+    job.finished += mine;
+    job.active--;
+    if (job.finished == job.parts && job.active == 0) job.done_cv.notify_all();
+  }
+  void worker()
+  {
+    for (;;) {
+      Job *job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] {
+          for (Job *j : jobs_) if (j->next.load() < j->parts) { job = j; return true; }
+          return false;
+        });
+        job->active++;
+      }
+      work_on(*job);
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::vector<Job *> jobs_;
+  size_t nworkers_ = 0;
+};
+
 template <class F>
 void parallel_for(size_t n, F f)
 {
-  unsigned hw = std::thread::hardware_concurrency();
-  size_t nt = std::min<size_t>(hw ? hw : 1, (n + 255) / 256);
-  if (nt <= 1) { f(0, n); return; }
-  std::vector<std::thread> th;
-  size_t chunk = (n + nt - 1) / nt;
-  for (size_t t = 0; t < nt; t++) {
-    size_t a = t * chunk, b = std::min(n, a + chunk);
-    if (a >= b) break;
-    th.emplace_back([=] { f(a, b); });
-  }
-  for (auto &t : th) t.join();
+  HostPool::get().ranges(n, HostPool::get().size(), [&](size_t, size_t a, size_t b) { f(a, b); });
 }
 
 const PipOptions_dp DEFAULT_OPTIONS = {1, 0, 0, 0, 0, 0, 0, 0};
@@ -824,25 +888,12 @@ struct DenseChunk {
   size_t per = 0;                       /* problems per worker range */
 };
 
-unsigned host_threads()
-{
-  unsigned hw = std::thread::hardware_concurrency();
-  return hw ? hw : 1;
-}
+unsigned host_threads() { return (unsigned)HostPool::get().size(); }
 
 template <class F>
 void parallel_ranges(size_t n, size_t nt, F f)
 {
-  nt = std::max<size_t>(1, std::min(nt, (n + 63) / 64));
-  const size_t per = (n + nt - 1) / nt;
-  if (nt == 1) { f(0, 0, n); return; }
-  std::vector<std::thread> th;
-  for (size_t t = 0; t < nt; t++) {
-    size_t a = t * per, b = std::min(n, a + per);
-    if (a >= b) break;
-    th.emplace_back([=] { f(t, a, b); });
-  }
-  for (auto &x : th) x.join();
+  HostPool::get().ranges(n, nt, f);
 }
 
 /* shapes + offsets of a chunk */
@@ -1038,46 +1089,59 @@ void emit_chunk(const DenseArgs &A, DenseChunk &C, int *status, unsigned long lo
   (void)per;
 }
 
-/* device-decode mode: the engine returned serialised quasts; reserve the chunk's span of the
- * caller's stream and copy every problem's words into it */
-void emit_chunk_ser(DenseChunk &C, int *status, unsigned long long *hashes, long long *ser, long long ser_cap,
-                    long long *ser_off, long long *ser_len, std::atomic<long long> *cursor, size_t nthreads)
+/* device-decode mode, results staged through pinned scratch (the caller's stream is pageable memory):
+ * `words` = the chunk's compact buffer (int32 words where they fit), per-problem arrays in SoA form.
+ * Reserve the chunk's span of the caller's stream and widen every problem's words into it. */
+void emit_chunk_staged(size_t first, size_t n, const pip_i64 *words, const int *st, const pip_u64 *hs,
+                       const long long *off, const long long *len, int *status, unsigned long long *hashes,
+                       long long *ser, long long ser_cap, long long *ser_off, long long *ser_len,
+                       std::atomic<long long> *cursor, size_t nthreads, std::vector<long long> &at)
 {
-  const size_t n = C.n;
   const bool keep = ser != nullptr && ser_off != nullptr;
   long long total = 0;
-  C.words.assign(n, 0);
-  for (size_t i = 0; i < n; i++) { C.words[i] = total; total += C.out.res[i].ser_words; }
+  at.resize(n);
+  for (size_t i = 0; i < n; i++) { at[i] = total; total += len[i] & ~PIP_LEN_NARROW; }
   const long long base = keep ? cursor->fetch_add(total) : 0;
   const bool fits = keep && base + total <= ser_cap;
   parallel_ranges(n, nthreads, [&](size_t, size_t a, size_t b) {
     for (size_t i = a; i < b; i++) {
-      const PipResult &r = C.out.res[i];
-      status[C.first + i] = r.status;
-      if (hashes) hashes[C.first + i] = C.out.hashes[i];
-      if (keep) {
-        ser_off[C.first + i] = base + C.words[i];
-        if (ser_len) ser_len[C.first + i] = r.ser_words;
-        if (fits && r.ser_words) {
-          I *dst = ser + base + C.words[i];
-          if (r.rflags & PIP_RES_SER32) {
-            /* the caller's stream is write-only here and far larger than the caches: streaming stores,
-             * so that widening 1.6 GB of int32 words does not first read 3.2 GB of destination lines */
-            const int *src = (const int *)(C.out.base[i] + r.cell_off);
+      const int s0 = st[i];
+      status[first + i] = PIP_STATUS_IS_FINAL(s0) ? s0 : PIP_ST_CAPACITY;
+      if (hashes) hashes[first + i] = hs[i];
+      if (!keep) continue;
+      const long long w = len[i] & ~PIP_LEN_NARROW;
+      ser_off[first + i] = base + at[i];
+      if (ser_len) ser_len[first + i] = w;
+      if (!fits || !w) continue;
+      I *dst = ser + base + at[i];
+      if (len[i] & PIP_LEN_NARROW) {
+        /* the caller's stream is write-only here and far larger than the caches: streaming stores,
+         * so that widening the int32 words does not first read the destination lines */
+        const int *src = (const int *)(words + off[i]);
 #if defined(__x86_64__)
-            for (unsigned k = 0; k < r.ser_words; k++) _mm_stream_si64((long long *)dst + k, (long long)src[k]);
+        for (long long k = 0; k < w; k++) _mm_stream_si64((long long *)dst + k, (long long)src[k]);
 #else
-            for (unsigned k = 0; k < r.ser_words; k++) dst[k] = src[k];
+        for (long long k = 0; k < w; k++) dst[k] = src[k];
 #endif
-          } else memcpy(dst, C.out.base[i] + r.cell_off, sizeof(I) * r.ser_words);
-        }
-      }
+      } else memcpy(dst, words + off[i], sizeof(I) * (size_t)w);
     }
 #if defined(__x86_64__)
     _mm_sfence();
 #endif
   });
 }
+
+bool is_pinned(const void *p)
+{
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+std::mutex g_dense_mu;                  /* one dense call at a time per process (it is parallel inside) */
+std::vector<int> g_devices;             /* devices a dense call spreads its chunks over (pip_set_devices_dp) */
+std::mutex g_devices_mu;
 
 }  // namespace
 
@@ -1092,6 +1156,35 @@ static size_t env_size(const char *name, size_t dflt)
   return x > 0 ? (size_t)x : dflt;
 }
 
+int pip_pin_buffer_dp(void *p, size_t bytes)
+{
+  if (!p || !bytes) return -1;
+  if (is_pinned(p)) return 0;
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+  return 0;
+}
+int pip_unpin_buffer_dp(void *p)
+{
+  if (!p) return -1;
+  const cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+  return 0;
+}
+int pip_set_devices_dp(int n, const int *devices)
+{
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return -1; }
+  std::vector<int> v;
+  for (int i = 0; i < n; i++) {
+    if (devices[i] < 0 || devices[i] >= count || devices[i] >= PipEngine::MAX_DEVICES) return -1;
+    v.push_back(devices[i]);
+  }
+  std::lock_guard<std::mutex> g(g_devices_mu);
+  g_devices = v;                        /* empty: back to the single default device */
+  return 0;
+}
+
 int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long *dom,
                        int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
                        int bignum, const PipOptions_dp *options,
@@ -1099,114 +1192,246 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
                        long long *ser, long long ser_cap, long long *ser_off, long long *ser_len)
 {
   if (n <= 0) return 0;
+  std::lock_guard<std::mutex> dense_guard(g_dense_mu);
   try {
     const double t0 = wall();
     DenseArgs A = {n, dom_rows, dom_cols, dom, has_ctx, ctx_rows, ctx_cols, ctx, bignum,
                    options ? *options : DEFAULT_OPTIONS};
-    const size_t CH = env_size("PIPLIB_B200_CHUNK", 1u << 17);
+    std::vector<int> devices;
+    {
+      std::lock_guard<std::mutex> g(g_devices_mu);
+      devices = g_devices;
+    }
+    if (devices.empty()) devices.push_back(pip_engine_device());
+    const bool keep = ser != nullptr && ser_off != nullptr;
+    /* decode on the GPU unless the host-only Simplify post-pass is wanted (PIPLIB_B200_HOST_DECODE=1
+     * forces the host decoder, for A/B tests) */
+    const bool device_decode = !A.opt.Simplify && !(A.opt.Compute_dual && !A.opt.Nq) &&
+                               getenv("PIPLIB_B200_HOST_DECODE") == nullptr;
+    /* Caller buffers in pinned (page-locked) memory are moved by DMA alone: the raw PolyLib rows go up as
+     * they are and tab_Matrix2Tableau runs on the device (pip_convert_kernel); the serialised quasts come
+     * down straight into the caller's stream.  Pageable buffers are converted (narrowed to int8 / int32)
+     * by the host pool into pinned staging, and widened out of it. */
+    const bool in_pinned = device_decode && is_pinned(dom) && (!has_ctx || !ctx_rows || is_pinned(ctx)) &&
+                           getenv("PIPLIB_B200_HOST_CONVERT") == nullptr;
+    const bool out_pinned = device_decode && keep && is_pinned(ser) && getenv("PIPLIB_B200_STAGED_OUT") == nullptr;
+
     /* chunk schedule: full chunks of CH problems, with a geometric ramp at both ends (CH/8, CH/4,
-     * CH/2) so that the GPU starts after one small conversion and the last copy-out is short */
+     * CH/2) so that the GPU starts after one small transfer and the last copy-out is short */
+    const size_t CH = env_size("PIPLIB_B200_CHUNK", 1u << 17);
     std::vector<size_t> sizes;
     {
       const size_t ramp = env_size("PIPLIB_B200_RAMP", 3);
       size_t left = (size_t)n;
       std::vector<size_t> head, tail;
-      for (size_t k = ramp; k >= 1 && left > 4 * CH; k--) {
+      for (size_t k = ramp; k >= 1 && left > 4 * CH * devices.size(); k--) {
         const size_t sz = std::max<size_t>(CH >> k, 1024);
-        head.push_back(sz); left -= sz;
-        tail.push_back(sz); left -= sz;
+        for (size_t d = 0; d < devices.size(); d++) {
+          head.push_back(sz); left -= sz;
+          tail.push_back(sz); left -= sz;
+        }
       }
       sizes = head;
       while (left > 0) { const size_t sz = std::min(CH, left); sizes.push_back(sz); left -= sz; }
       for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
     }
     const size_t nchunks = sizes.size();
-    const size_t lanes = std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 4), PipEngine::MAX_LANES), nchunks);
+    const size_t lanes = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", in_pinned ? 3 : 4), PipEngine::MAX_LANES),
+                                                              (nchunks + devices.size() - 1) / devices.size()));
+    const size_t nworkers = lanes * devices.size();
     /* host threads per lane: the lanes' conversion / copy-out phases overlap, so each gets a share */
-    const size_t nthreads = std::max<size_t>(1, env_size("PIPLIB_B200_THREADS", std::max<size_t>(2, (2 * host_threads() + lanes - 1) / lanes)));
-    const bool keep = ser != nullptr && ser_off != nullptr;
-    std::vector<DenseChunk> chunks(lanes);          /* per-lane scratch, reused from chunk to chunk */
+    const size_t nthreads = std::max<size_t>(1, (host_threads() + nworkers - 1) / nworkers);
     std::vector<size_t> firsts(nchunks + 1, 0);
     for (size_t c = 0; c < nchunks; c++) firsts[c + 1] = firsts[c] + sizes[c];
-    std::vector<std::string> errors(lanes);
+    std::vector<std::string> errors(nworkers);
     std::atomic<long long> cursor(0);
+    std::atomic<size_t> next_chunk(0);
     std::atomic<int> width_hint(0);
     std::atomic<int> uniform_hint(getenv("PIPLIB_B200_EXACT_PLAN") ? 0 : 1);
     const bool timing = getenv("PIPLIB_B200_TIMING") != nullptr;
-    /* decode on the GPU unless the host-only Simplify post-pass is wanted (PIPLIB_B200_HOST_DECODE=1
-     * forces the host decoder, for A/B tests) */
-    const bool device_decode = !A.opt.Simplify && !(A.opt.Compute_dual && !A.opt.Nq) &&
-                               getenv("PIPLIB_B200_HOST_DECODE") == nullptr;
-    std::vector<double> tstage(lanes * 4, 0.0);
-    std::vector<PipBatchStats_dp> lane_stats(lanes);
+    std::vector<double> tstage(nworkers * 4, 0.0);
+    std::vector<PipBatchStats_dp> lane_stats(nworkers);
     for (auto &ls : lane_stats) memset(&ls, 0, sizeof ls);
-    auto lane_main = [&](size_t lane) {
+
+    /* everything pip_solve derives from the dimensions and the options alone */
+    PipConvertShape CS;
+    PipDecodeParm uparm;
+    int sol_flags0 = 0;
+    {
+      MatView d0 = {A.dr, A.dc, nullptr, A.dom};
+      MatView c0 = {A.cr, A.cc, nullptr, A.ctx};
+      const Shape s0 = derive_shape_dims(d0.cols, A.has_ctx ? &c0 : nullptr, A.bignum, A.opt);
+      CS.dr = A.dr; CS.dc = A.dc; CS.cr = A.has_ctx ? A.cr : 0; CS.cc = A.cc; CS.has_ctx = A.has_ctx && A.cr > 0;
+      CS.Nn = s0.Nn; CS.Np = s0.Np; CS.Bg = s0.Bg; CS.Shift = s0.Shift; CS.Urs = s0.Urs;
+      CS.pflags = s0.flags | ((s0.sol_flags == 0 && s0.Urs == 0) ? PIP_F_SIMPLE_SER : 0);
+      CS.width = s0.Nn + s0.Np + 1; CS.cwidth = s0.Np + 1;
+      uparm.bg = s0.Bg - s0.Nn - 1; uparm.urs = s0.Urs; uparm.flags = s0.sol_flags;
+      sol_flags0 = s0.sol_flags;
+    }
+    (void)sol_flags0;
+
+    auto worker_main = [&](size_t w) {
       try {
-        PipEngine &E = PipEngine::lane((int)lane);
-        for (size_t c = lane; c < nchunks; c += lanes) {
-          DenseChunk &C = chunks[lane];
+        const int device = devices[w / lanes];
+        PipEngine &E = PipEngine::at(device, (int)(w % lanes));
+        cudaStream_t s = E.stream();
+        pip_cuda_check(cudaSetDevice(device), "cudaSetDevice");
+        DenseChunk C;                       /* per-worker scratch, reused from chunk to chunk */
+        std::vector<long long> at;
+        for (;;) {
+          const size_t c = next_chunk.fetch_add(1);          /* chunks go to whichever device / lane is free */
+          if (c >= nchunks) break;
           C.first = firsts[c]; C.n = sizes[c];
-          double ta = wall();
-          const bool optimistic = uniform_hint.load() != 0;
-          if (optimistic) plan_chunk_uniform(A, C); else plan_chunk(A, C, nthreads);
-          double tb = wall();
-          std::atomic<int> mismatch(0);
-          void *pool = convert_chunk(A, C, E, nthreads, &width_hint, optimistic ? &mismatch : nullptr);
-          if (mismatch.load()) {            /* the number of equality rows varies: exact plan, convert again */
-            uniform_hint.store(0);
-            plan_chunk(A, C, nthreads);
-            pool = convert_chunk(A, C, E, nthreads, &width_hint);
-          }
-          double tc = wall();
-          tstage[lane * 4 + 0] += tb - ta; tstage[lane * 4 + 1] += tc - tb;
+          const size_t cn = C.n;
+          double ta = wall(), tb = ta, tc = ta;
           PipBatchIn in;
-          in.n = C.n; in.h_prob = C.prob.data(); in.h_pool = pool; in.pool_words = C.pool_elems;
-          in.elem_log2 = C.elem_log2;
-          std::vector<PipDecodeParm> parm;
-          if (device_decode) {
-            parm.resize(C.n);
-            for (size_t i = 0; i < C.n; i++) {
-              const Shape &sh = C.shapes[i];
-              parm[i].bg = sh.Bg - sh.Nn - 1; parm[i].urs = sh.Urs; parm[i].flags = sh.sol_flags;
+          in.n = cn;
+          PipProblem uniform;
+          struct WidenCtx { PipConvertArgs a; void *pool64; } wc;
+          wc.pool64 = nullptr;
+          if (in_pinned) {
+            /* ---- DMA the raw rows up, convert on the device ---- */
+            const size_t dwords = (size_t)A.dr * A.dc, cwords = CS.has_ctx ? (size_t)A.cr * A.cc : 0;
+            pip_i64 *d_dom = (pip_i64 *)E.device_scratch(0, std::max<size_t>(cn * dwords * 8, 8));
+            pip_i64 *d_ctx = (pip_i64 *)E.device_scratch(1, std::max<size_t>(cn * cwords * 8, 8));
+            const long long stride = 2ll * A.dr * CS.width + 2ll * CS.cr * CS.cwidth;
+            void *d_pool = E.device_scratch(2, std::max<size_t>((size_t)cn * stride * 4, 8));
+            unsigned char *d_pd = (unsigned char *)E.device_scratch(3, cn * sizeof(PipProblem) + 64);
+            int *d_dims = (int *)(d_pd + cn * sizeof(PipProblem));
+            int *h_dims = (int *)E.pinned_scratch(0, 64);
+            if (dwords) pip_cuda_check(cudaMemcpyAsync(d_dom, A.dom + C.first * dwords, cn * dwords * 8, cudaMemcpyHostToDevice, s), "H2D domain rows");
+            if (cwords) pip_cuda_check(cudaMemcpyAsync(d_ctx, A.ctx + C.first * cwords, cn * cwords * 8, cudaMemcpyHostToDevice, s), "H2D context rows");
+            pip_cuda_check(cudaMemsetAsync(d_dims, 0, 16, s), "memset dims");
+            PipConvertArgs &ca = wc.a;
+            ca.s = CS; ca.dom = d_dom; ca.ctx = d_ctx; ca.n = (long long)cn; ca.stride = stride;
+            ca.pool = d_pool; ca.prob = (PipProblem *)d_pd; ca.dims = d_dims;
+            pip_cuda_check(pip_launch_convert(&ca, 2, s), "convert kernel");
+            pip_cuda_check(cudaMemcpyAsync(h_dims, d_dims, 16, cudaMemcpyDeviceToHost, s), "D2H dims");
+            pip_cuda_check(cudaStreamSynchronize(s), "sync after conversion");
+            tb = tc = wall();
+            uniform.nvar = CS.Nn; uniform.nparm = CS.Np; uniform.ni = h_dims[0]; uniform.nc = h_dims[1];
+            uniform.bigparm = CS.Bg; uniform.flags = CS.pflags; uniform.off = 0;
+            in.d_prob = (const PipProblem *)d_pd; in.d_pool = d_pool; in.elem_log2 = 2;
+            in.uniform = &uniform;
+            in.widen_ctx = &wc;
+            in.widen_pool = [](void *ctx, cudaStream_t st) -> const void * {
+              WidenCtx *w = (WidenCtx *)ctx;
+              if (!w->pool64) {
+                pip_cuda_check(cudaMalloc(&w->pool64, std::max<size_t>((size_t)w->a.n * w->a.stride * 8, 8)), "cudaMalloc(int64 pool)");
+                PipConvertArgs a64 = w->a;
+                a64.pool = w->pool64; a64.dims = nullptr;
+                pip_cuda_check(pip_launch_convert(&a64, 3, st), "convert kernel (int64)");
+              }
+              return w->pool64;
+            };
+            lane_stats[w].h2d_bytes += cn * (dwords + cwords) * 8;
+          } else {
+            /* ---- convert on the host (narrowing) into pinned staging ---- */
+            const bool optimistic = uniform_hint.load() != 0;
+            if (optimistic) plan_chunk_uniform(A, C); else plan_chunk(A, C, nthreads);
+            tb = wall();
+            std::atomic<int> mismatch(0);
+            void *pool = convert_chunk(A, C, E, nthreads, &width_hint, optimistic ? &mismatch : nullptr);
+            bool is_uniform = optimistic;
+            if (mismatch.load()) {            /* the number of equality rows varies: exact plan, convert again */
+              uniform_hint.store(0);
+              plan_chunk(A, C, nthreads);
+              pool = convert_chunk(A, C, E, nthreads, &width_hint);
+              is_uniform = false;
             }
-            in.h_decode = parm.data();
+            tc = wall();
+            in.h_prob = C.prob.data(); in.h_pool = pool; in.pool_words = C.pool_elems;
+            in.elem_log2 = C.elem_log2;
+            if (is_uniform && cn) { uniform = C.prob[0]; uniform.off = 0; in.uniform = &uniform; }
+          }
+          tstage[w * 4 + 0] += tb - ta; tstage[w * 4 + 1] += tc - tb;
+          if (device_decode) {
+            in.uniform_decode = &uparm;
+            in.stream_out = true;
+            in.words64 = out_pinned;
           }
           double td = wall();
           E.run(in, C.out);
           double te = wall();
-          if (device_decode) emit_chunk_ser(C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
-          else emit_chunk(A, C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
-          tstage[lane * 4 + 2] += te - td; tstage[lane * 4 + 3] += wall() - te;
-          accumulate(lane_stats[lane], C.out);
+          if (wc.pool64) { cudaFree(wc.pool64); wc.pool64 = nullptr; }
+          if (device_decode) {
+            /* per-problem arrays: SoA on the device -> pinned scratch -> the caller's arrays */
+            const PipDeviceOut &D = C.out.dev;
+            const size_t soa = cn * (sizeof(int) + sizeof(pip_u64) + 2 * sizeof(long long));
+            unsigned char *hp = (unsigned char *)E.pinned_scratch(1, soa + 64);
+            long long *h_off = (long long *)hp, *h_len = h_off + cn;
+            pip_u64 *h_hash = (pip_u64 *)(h_len + cn);
+            int *h_st = (int *)(h_hash + cn);
+            pip_cuda_check(cudaMemcpyAsync(h_off, D.off, cn * 8, cudaMemcpyDeviceToHost, s), "D2H offsets");
+            pip_cuda_check(cudaMemcpyAsync(h_len, D.len, cn * 8, cudaMemcpyDeviceToHost, s), "D2H lengths");
+            pip_cuda_check(cudaMemcpyAsync(h_hash, D.hash, cn * 8, cudaMemcpyDeviceToHost, s), "D2H hashes");
+            pip_cuda_check(cudaMemcpyAsync(h_st, D.status, cn * 4, cudaMemcpyDeviceToHost, s), "D2H statuses");
+            lane_stats[w].d2h_bytes += soa;
+            if (out_pinned) {
+              /* the chunk's words are one contiguous span of int64: one DMA into the caller's stream */
+              const long long total = D.slots;
+              const long long base = cursor.fetch_add(total);
+              const bool fits = base + total <= ser_cap;
+              if (fits && total) {
+                pip_cuda_check(cudaMemcpyAsync(ser + base, D.words, (size_t)total * 8, cudaMemcpyDeviceToHost, s), "D2H quasts");
+                lane_stats[w].d2h_bytes += (size_t)total * 8;
+              }
+              pip_cuda_check(cudaStreamSynchronize(s), "sync after D2H");
+              for (size_t i = 0; i < cn; i++) {
+                const int s0 = h_st[i];
+                status[C.first + i] = PIP_STATUS_IS_FINAL(s0) ? s0 : PIP_ST_CAPACITY;
+                ser_off[C.first + i] = base + h_off[i];
+                if (ser_len) ser_len[C.first + i] = h_len[i] & ~PIP_LEN_NARROW;
+              }
+              if (hashes) memcpy(hashes + C.first, h_hash, cn * 8);
+            } else {
+              pip_i64 *h_words = nullptr;
+              if (keep && D.slots) {
+                h_words = (pip_i64 *)E.pinned_scratch(2, (size_t)D.slots * 8);
+                pip_cuda_check(cudaMemcpyAsync(h_words, D.words, (size_t)D.slots * 8, cudaMemcpyDeviceToHost, s), "D2H quasts");
+                lane_stats[w].d2h_bytes += (size_t)D.slots * 8;
+              }
+              pip_cuda_check(cudaStreamSynchronize(s), "sync after D2H");
+              emit_chunk_staged(C.first, cn, h_words, h_st, h_hash, h_off, h_len, status, hashes, ser, ser_cap, ser_off,
+                                ser_len, &cursor, nthreads, at);
+            }
+            PipBatchStats_dp &ls = lane_stats[w];
+            ls.pivots += D.stats[0]; ls.cuts += D.stats[1]; ls.subsolves += D.stats[2]; ls.splits += D.stats[3];
+            ls.elem_updates += D.stats[4]; ls.cells += D.stats[5];
+            ls.max_rows = std::max(ls.max_rows, (unsigned)D.stats[6]); ls.max_cols = std::max(ls.max_cols, (unsigned)D.stats[7]);
+          } else emit_chunk(A, C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
+          tstage[w * 4 + 2] += te - td; tstage[w * 4 + 3] += wall() - te;
+          accumulate(lane_stats[w], C.out);
           if (timing)
-            fprintf(stderr, "[piplib-b200] chunk %zu lane %zu: rounds %d: %d problems %.3f s | %d problems %.3f s | %d problems %.3f s; d2h %.3f s\n", c, lane,
+            fprintf(stderr, "[piplib-b200] chunk %zu device %d lane %zu: rounds %d: %d problems %.3f s | %d problems %.3f s | %d problems %.3f s; d2h %.3f s\n", c, device, w % lanes,
                     C.out.times.rounds, C.out.times.round_n[0], C.out.times.round_s[0], C.out.times.round_n[1], C.out.times.round_s[1],
                     C.out.times.round_n[2], C.out.times.round_s[2], C.out.times.d2h);
           /* the cell chunks are engine-owned and reused by the next run on this lane: drop the views */
           C.out.base.clear();
         }
-      } catch (const std::exception &e) { errors[lane] = e.what(); }
+      } catch (const std::exception &e) { errors[w] = e.what(); }
     };
-    if (lanes <= 1) lane_main(0);
+    if (nworkers <= 1) worker_main(0);
     else {
       std::vector<std::thread> th;
-      for (size_t l = 0; l < lanes; l++) th.emplace_back(lane_main, l);
+      for (size_t l = 0; l < nworkers; l++) th.emplace_back(worker_main, l);
       for (auto &x : th) x.join();
     }
     for (const std::string &e : errors) if (!e.empty()) throw std::runtime_error(e);
-    const double tasm0 = wall();
     const long long total = cursor.load();
     if (ser_off) ser_off[n] = total;
     if (timing) {
-      for (size_t l = 0; l < lanes; l++)
-        fprintf(stderr, "[piplib-b200] lane %zu: plan %.3f convert %.3f run %.3f emit %.3f s\n", l,
+      for (size_t l = 0; l < nworkers; l++)
+        fprintf(stderr, "[piplib-b200] device %d lane %zu: plan %.3f convert %.3f run %.3f emit %.3f s\n", devices[l / lanes], l % lanes,
                 tstage[l * 4], tstage[l * 4 + 1], tstage[l * 4 + 2], tstage[l * 4 + 3]);
-      fprintf(stderr, "[piplib-b200] assemble %.3f s, total %.3f s, %zu chunks, %zu lanes, %zu threads\n",
-              wall() - tasm0, wall() - t0, nchunks, lanes, nthreads);
+      fprintf(stderr, "[piplib-b200] total %.3f s, %zu chunks, %zu devices x %zu lanes, %zu host threads per lane (pool %u), input %s, output %s\n",
+              wall() - t0, nchunks, devices.size(), lanes, nthreads, host_threads(),
+              in_pinned ? "pinned: DMA + device conversion" : "pageable: host conversion",
+              out_pinned ? "pinned: DMA" : "pageable: staged");
     }
     PipBatchStats_dp acc;
     memset(&acc, 0, sizeof acc);
-    for (size_t l = 0; l < lanes; l++) merge_stats(acc, lane_stats[l]);
+    for (size_t l = 0; l < nworkers; l++) merge_stats(acc, lane_stats[l]);
     acc.seconds_host = (wall() - t0) - acc.seconds_h2d - acc.seconds_kernel - acc.seconds_d2h;
     publish_stats(acc);
     if (keep && total > ser_cap) return -2;
@@ -1223,6 +1448,11 @@ struct pip_device_batch {
   PipProblem *d_prob = nullptr;
   void *d_pool = nullptr;
   bool fetched = false;
+  bool device_decode = false;           /* run() = solve + decode on the device (serialised quasts stay in HBM) */
+  bool uniform = false;
+  PipProblem shape;
+  std::vector<PipDecodeParm> parm;
+  int device = 0;
 };
 
 pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_cols, const long long *dom,
@@ -1236,11 +1466,23 @@ pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_col
     const size_t nthreads = host_threads();
     plan_chunk(b->A, b->C, nthreads);
     PipEngine &E = PipEngine::get();
+    b->device = E.device_id();
     void *pool = convert_chunk(b->A, b->C, E, nthreads, nullptr);
     pip_cuda_check(cudaMalloc((void **)&b->d_prob, sizeof(PipProblem) * (size_t)n), "cudaMalloc(problems)");
     pip_cuda_check(cudaMalloc(&b->d_pool, (b->C.pool_elems + 8) << b->C.elem_log2), "cudaMalloc(pool)");
     pip_cuda_check(cudaMemcpy(b->d_prob, b->C.prob.data(), sizeof(PipProblem) * (size_t)n, cudaMemcpyHostToDevice), "H2D problems");
     pip_cuda_check(cudaMemcpy(b->d_pool, pool, b->C.pool_elems << b->C.elem_log2, cudaMemcpyHostToDevice), "H2D pool");
+    /* the device job = solve + decode unless the decode needs the host (Simplify, dual with equalities) */
+    b->device_decode = !b->A.opt.Simplify && !(b->A.opt.Compute_dual && !b->A.opt.Nq) &&
+                       getenv("PIPLIB_B200_HOST_DECODE") == nullptr;
+    b->uniform = n > 0;
+    b->parm.resize((size_t)n);
+    for (size_t i = 0; i < (size_t)n; i++) {
+      const Shape &sh = b->C.shapes[i];
+      b->parm[i].bg = sh.Bg - sh.Nn - 1; b->parm[i].urs = sh.Urs; b->parm[i].flags = sh.sol_flags;
+      if (sh.Nl != b->C.shapes[0].Nl || sh.Nm != b->C.shapes[0].Nm) b->uniform = false;
+    }
+    if (b->uniform) { b->shape = b->C.prob[0]; b->shape.off = 0; }
     b->A.dom = nullptr; b->A.ctx = nullptr;          /* the caller's arrays are not kept */
     return b;
   } catch (const std::exception &e) {
@@ -1249,17 +1491,34 @@ pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_col
   }
 }
 
+/* fetch_cells = 0: the whole device job with the results left in HBM -- solve, then decode to serialised
+ * quasts (the same kernels the host-buffer path runs); fetch_cells = 1: solve + cell gather, cells copied
+ * to the host (host decoder) */
 int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
 {
   try {
     PipBatchIn in;
     in.n = b->C.n; in.h_prob = b->C.prob.data();
     in.d_prob = b->d_prob; in.d_pool = b->d_pool; in.elem_log2 = b->C.elem_log2;
-    in.fetch_cells = fetch_cells != 0;
-    PipEngine::get().run(in, b->C.out);
+    if (b->uniform) in.uniform = &b->shape;
+    const bool stream = !fetch_cells && b->device_decode;
+    if (stream) {
+      if (b->uniform) in.uniform_decode = &b->parm[0]; else in.h_decode = b->parm.data();
+      in.stream_out = true;
+    } else in.fetch_cells = fetch_cells != 0;
+    PipEngine &E = PipEngine::at(b->device, 0);
+    E.run(in, b->C.out);
     b->fetched = fetch_cells != 0;
     if (device_ms) *device_ms = b->C.out.times.device_ms;
-    account(b->C.out, 0);
+    if (stream) {
+      PipBatchStats_dp st;
+      memset(&st, 0, sizeof st);
+      const PipDeviceOut &D = b->C.out.dev;
+      st.pivots = D.stats[0]; st.cuts = D.stats[1]; st.subsolves = D.stats[2]; st.splits = D.stats[3];
+      st.elem_updates = D.stats[4]; st.cells = D.stats[5]; st.max_rows = (unsigned)D.stats[6]; st.max_cols = (unsigned)D.stats[7];
+      accumulate(st, b->C.out);
+      publish_stats(st);
+    } else account(b->C.out, 0);
   } catch (const std::exception &e) {
     fprintf(stderr, "%s\n", e.what());
     return -1;
@@ -1269,6 +1528,19 @@ int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
 
 int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long long *hashes)
 {
+  const PipDeviceOut &D = b->C.out.dev;
+  if (D.status) {                        /* last run decoded on the device: statuses and hashes are in HBM */
+    try {
+      pip_cuda_check(cudaSetDevice(b->device), "cudaSetDevice");
+      pip_cuda_check(cudaMemcpy(status, D.status, b->C.n * sizeof(int), cudaMemcpyDeviceToHost), "D2H statuses");
+      for (size_t i = 0; i < b->C.n; i++) if (!PIP_STATUS_IS_FINAL(status[i])) status[i] = PIP_ST_CAPACITY;
+      if (hashes) pip_cuda_check(cudaMemcpy(hashes, D.hash, b->C.n * sizeof(pip_u64), cudaMemcpyDeviceToHost), "D2H hashes");
+    } catch (const std::exception &e) {
+      fprintf(stderr, "%s\n", e.what());
+      return -1;
+    }
+    return 0;
+  }
   if (b->C.out.res.size() != b->C.n) return -1;
   if (hashes && !b->fetched) return -3;
   if (hashes) emit_chunk(b->A, b->C, status, hashes, nullptr, 0, nullptr, nullptr, nullptr, host_threads());

@@ -11,9 +11,11 @@
 #include <stdint.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
+#include "pip_convert.h"
 #include "pip_decode.h"
 #include "pip_decode_warp.h"
 #include "pip_kernels.h"
@@ -140,57 +142,65 @@ __global__ void pip_gather_kernel(PipResult *res, const int *order, const PipCel
 }
 
 /* ---- device-side decode: cells -> serialised quast words (pip_decode.h) --------------------- */
-/* one thread per problem; pass 0 sizes the stream, pass 1 writes it (and its hash) */
+/* sizing pass, one thread per problem, for streams the solver did not size itself (column surgery:
+ * Maximize / Urs_* / a big parameter): words of the stream, and whether they fit int32 */
 __global__ void pip_serialize_kernel(PipResult *res, const int *order, const PipCell *cells,
-                                     const PipDecodeParm *parm, const long long *dst_off, pip_i64 *out,
-                                     pip_u64 *hashes, int nprob, int pass)
+                                     const PipDecodeParm *parm, const PipDecodeParm uparm, int nprob)
 {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nprob) return;
   const int p = order ? order[q] : q;
   const PipResult r = res[p];
   PipSer s;
-  const bool narrow = pass && (r.rflags & PIP_RES_SER32);
-  s.out = pass ? out + dst_off[q] : nullptr;
-  s.cap = pass ? (long long)r.ser_words : 0;
-  s.len = 0; s.h = PIP_HASH_INIT; s.hashing = pass; s.narrow_out = narrow ? 1 : 0; s.wide = 0;
+  s.out = nullptr; s.cap = 0;
+  s.len = 0; s.h = PIP_HASH_INIT; s.hashing = 0; s.narrow_out = 0; s.wide = 0;
   if (r.status == PIP_ST_VOID) pip_sput(s, -1);
   else if (r.status == PIP_ST_OK) {
     PipRawCells c = {cells + r.cell_off};
-    const PipDecodeParm d = parm[p];
+    const PipDecodeParm d = parm ? parm[p] : uparm;
     pip_ser_cells(s, c, r.ncells, d.bg, d.urs, d.flags);
   }
-  if (pass == 0) {
-    res[p].ser_words = (unsigned)s.len;
-    if (!s.wide) res[p].rflags = r.rflags | PIP_RES_SER32;
-  } else {
-    res[p].cell_off = dst_off[q];
-    if (hashes) hashes[p] = (r.status == PIP_ST_OK || r.status == PIP_ST_VOID) ? s.h : 0ull;
-    /* a stream sized by the solver (PIP_RES_SIZED) must come out exactly that long and, when it was
-     * promised narrow, fit 32-bit words: anything else is a bug, never a silent truncation */
-    if ((r.rflags & PIP_RES_SIZED) && (s.len != (long long)r.ser_words || (narrow && s.wide)))
-      res[p].status = PIP_ST_FAULT + 1;
-  }
+  res[p].ser_words = (unsigned)s.len;
+  if (!s.wide) res[p].rflags = r.rflags | PIP_RES_SER32;
 }
 
 /* pass 1 with one warp per problem (pip_decode_warp.h): cells staged in shared memory by a coalesced
- * copy, warp-uniform parse, lane-parallel vectors, words out through a hashed shared-memory tile */
+ * copy, warp-uniform parse, lane-parallel vectors, words out through a hashed shared-memory tile.
+ * Two ways to place the output: `dst_off` (an exclusive scan computed beforehand, cell-gather path) or
+ * `so.ctl` (dense path): the warp reserves the span with one atomic add, writes the per-problem results
+ * in structure-of-arrays form and sums the counters of finished problems. */
 #define PIP_WS_WARPS 8
 #define PIP_WS_WORDS_PER_WARP (PIP_WS_TILE + 3 * PIP_WS_CELLS)
 __global__ void __launch_bounds__(32 * PIP_WS_WARPS)
 pip_serialize_warp_kernel(PipResult *res, const int *order, const PipCell *cells, const PipDecodeParm *parm,
-                          const long long *dst_off, pip_i64 *out, pip_u64 *hashes, int nprob)
+                          const PipDecodeParm uparm, const long long *dst_off, pip_i64 *out, pip_u64 *hashes, int nprob,
+                          const PipStreamOut so)
 {
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pip_i64 *tile = (pip_i64 *)pip_smem + (size_t)wid * PIP_WS_WORDS_PER_WARP;
   pip_i64 *stage = tile + PIP_WS_TILE;
+  const bool stream = so.ctl != nullptr;
+  unsigned long long acc[6] = {0, 0, 0, 0, 0, 0};
+  unsigned mrows = 0, mcols = 0, finals = 0;
   for (int q = blockIdx.x * PIP_WS_WARPS + wid; q < nprob; q += gridDim.x * PIP_WS_WARPS) {
     const int p = order ? order[q] : q;
     const PipResult r = res[p];
-    const bool narrow = (r.rflags & PIP_RES_SER32) != 0;
+    const bool narrow = (r.rflags & PIP_RES_SER32) != 0 && !(stream && so.words64);
     PipWarpSer s;
-    s.tile = tile; s.out = out + dst_off[q]; s.cap = (long long)r.ser_words; s.len = 0; s.fill = 0;
+    s.tile = tile; s.cap = (long long)r.ser_words; s.len = 0; s.fill = 0;
     s.h = PIP_HASH_INIT; s.narrow_out = narrow ? 1 : 0; s.wide = 0;
+    long long base = 0;
+    const bool has_words = r.status == PIP_ST_OK || r.status == PIP_ST_VOID;
+    if (stream) {
+      const long long slots = !has_words ? 0 : narrow ? ((long long)r.ser_words + 1) / 2 : (long long)r.ser_words;
+      if (lane == 0 && slots) base = (long long)atomicAdd(so.ctl + PIP_SO_SLOTS, (unsigned long long)slots);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      s.out = out + base;
+      if (base + slots > so.cap) {                     /* does not fit: count only, the host grows the buffer */
+        s.out = nullptr;
+        if (lane == 0) so.ctl[PIP_SO_OVERFLOW] = 1;
+      }
+    } else { base = dst_off[q]; s.out = out + base; }
     if (r.status == PIP_ST_VOID) pip_wput(s, -1);
     else if (r.status == PIP_ST_OK) {
       const PipCell *src = cells + r.cell_off;
@@ -201,37 +211,159 @@ pip_serialize_warp_kernel(PipResult *res, const int *order, const PipCell *cells
         src = (const PipCell *)stage;
       }
       PipRawCells c = {src};
-      const PipDecodeParm d = parm[p];
+      const PipDecodeParm d = parm ? parm[p] : uparm;
       pip_wser_cells(s, c, r.ncells, d.bg, d.urs, d.flags);
     }
     pip_wser_flush(s);
+    /* a stream sized by the solver (PIP_RES_SIZED) must come out exactly that long and, when it was
+     * promised narrow, fit 32-bit words: anything else is a bug, never a silent truncation */
+    const bool bad = (r.rflags & PIP_RES_SIZED) && has_words && (s.len != (long long)r.ser_words || (narrow && s.wide));
     if (lane == 0) {
-      res[p].cell_off = dst_off[q];
-      if (hashes) hashes[p] = (r.status == PIP_ST_OK || r.status == PIP_ST_VOID) ? s.h : 0ull;
-      if ((r.rflags & PIP_RES_SIZED) && (s.len != (long long)r.ser_words || (narrow && s.wide)))
-        res[p].status = PIP_ST_FAULT + 1;
+      const pip_u64 h = has_words ? s.h : 0ull;
+      if (stream) {
+        so.status[p] = bad ? PIP_ST_FAULT + 1 : r.status;
+        so.hash[p] = h;
+        so.off[p] = base;
+        so.len[p] = has_words ? ((long long)r.ser_words | (narrow ? PIP_LEN_NARROW : 0ll)) : 0ll;
+      } else {
+        res[p].cell_off = base;
+        if (hashes) hashes[p] = h;
+        if (bad) res[p].status = PIP_ST_FAULT + 1;
+      }
+    }
+    if (stream && PIP_STATUS_IS_FINAL(r.status)) {
+      finals++;
+      acc[0] += r.pivots; acc[1] += r.cuts; acc[2] += r.subsolves; acc[3] += r.splits;
+      acc[4] += ((unsigned long long)r.elem_updates_hi << 32) | r.elem_updates_lo;
+      acc[5] += (unsigned long long)r.ncells;
+      mrows = r.max_rows > mrows ? r.max_rows : mrows;
+      mcols = r.max_cols > mcols ? r.max_cols : mcols;
     }
     __syncwarp();
+  }
+  if (stream && lane == 0 && finals) {
+    atomicAdd(so.ctl + PIP_SO_FINALS, (unsigned long long)finals);
+    for (int k = 0; k < 6; k++) atomicAdd(so.stats + k, acc[k]);
+    atomicMax(so.stats + 6, (unsigned long long)mrows);
+    atomicMax(so.stats + 7, (unsigned long long)mcols);
   }
 }
 
 extern "C" cudaError_t pip_launch_serialize(PipResult *res, const int *order, const PipCell *cells,
-                                            const PipDecodeParm *parm, const long long *dst_off, pip_i64 *out,
-                                            pip_u64 *hashes, int nprob, int pass, cudaStream_t stream)
+                                            const PipDecodeParm *parm, const PipDecodeParm *uparm,
+                                            const long long *dst_off, pip_i64 *out,
+                                            pip_u64 *hashes, int nprob, int pass, const PipStreamOut *so,
+                                            cudaStream_t stream)
 {
-  const bool thread_decode = getenv("PIPLIB_B200_THREAD_DECODE") != nullptr;   /* A/B aid */
-  if (pass == 1 && !thread_decode) {
+  PipDecodeParm u = {0, 0, 0};
+  if (uparm) u = *uparm;
+  if (pass == 1) {
+    PipStreamOut o;
+    memset(&o, 0, sizeof o);
+    if (so) o = *so;
     const size_t smem = sizeof(pip_i64) * PIP_WS_WARPS * PIP_WS_WORDS_PER_WARP;
     cudaError_t e = pip_raise_dynamic_smem(pip_serialize_warp_kernel, smem, g_smem_ws);
     if (e != cudaSuccess) return e;
     int blocks = (nprob + PIP_WS_WARPS - 1) / PIP_WS_WARPS;
     if (blocks > 148 * 3) blocks = 148 * 3;
-    pip_serialize_warp_kernel<<<blocks, 32 * PIP_WS_WARPS, smem, stream>>>(res, order, cells, parm, dst_off, out, hashes, nprob);
+    pip_serialize_warp_kernel<<<blocks, 32 * PIP_WS_WARPS, smem, stream>>>(res, order, cells, parm, u, dst_off, out, hashes,
+                                                                          nprob, o);
     return cudaGetLastError();
   }
   const int threads = 128;
-  pip_serialize_kernel<<<(nprob + threads - 1) / threads, threads, 0, stream>>>(res, order, cells, parm, dst_off, out,
-                                                                               hashes, nprob, pass);
+  pip_serialize_kernel<<<(nprob + threads - 1) / threads, threads, 0, stream>>>(res, order, cells, parm, u, nprob);
+  return cudaGetLastError();
+}
+
+/* every record PENDING (the ladder re-arms escalated problems from the host) */
+__global__ void pip_init_results_kernel(PipResult *res, long long n)
+{
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  PipResult r;
+  memset(&r, 0, sizeof r);
+  r.status = PIP_ST_PENDING;
+  for (long long i = i0; i < n; i += step) res[i] = r;
+}
+extern "C" cudaError_t pip_launch_init_results(PipResult *res, long long n, cudaStream_t stream)
+{
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  pip_init_results_kernel<<<blocks, 256, 0, stream>>>(res, n);
+  return cudaGetLastError();
+}
+
+/* ---- device-side input conversion (pip_convert.h): tab_Matrix2Tableau_xx on the raw PolyLib rows ----
+ * One warp per problem, lane = input row (a row is converted by one lane exactly as the host does it);
+ * an equality row also writes its negated copy, so the output row of a lane is its index plus the
+ * equalities before it (ballot + popc).  lane 0 writes the descriptor. */
+template <class T>
+__global__ void __launch_bounds__(256) pip_convert_kernel(const PipConvertArgs A)
+{
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const PipConvertShape &S = A.s;
+  int max_nl = 0, max_nm = 0, nwide = 0;
+  for (long long p = warp; p < A.n; p += nwarps) {
+    T *tab = (T *)A.pool + p * A.stride;
+    pip_i64 lost = 0;
+    int nl = 0, nm = 0;
+    for (int b0 = 0; b0 < S.dr; b0 += 32) {
+      const int i = b0 + lane;
+      const bool in = i < S.dr;
+      const pip_i64 *row = A.dom + (p * S.dr + (in ? i : 0)) * (long long)S.dc;
+      const bool eq = in && row[0] == 0;
+      const unsigned eqm = __ballot_sync(0xffffffffu, eq), inm = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        T *r = tab + (size_t)(nl + lane + __popc(eqm & ((1u << lane) - 1u))) * S.width;
+        pip_convert_row<T>(row, S.dc, r, S.width, S.Nn, 0, S.Shift, S.Bg, S.Urs, lost);
+        if (eq) pip_convert_negate<T>(r, r + S.width, S.width, lost);
+      }
+      nl += __popc(inm) + __popc(eqm);
+    }
+    if (S.has_ctx) {
+      T *ctab = tab + (size_t)nl * S.width;
+      for (int b0 = 0; b0 < S.cr; b0 += 32) {
+        const int i = b0 + lane;
+        const bool in = i < S.cr;
+        const pip_i64 *row = A.ctx + (p * S.cr + (in ? i : 0)) * (long long)S.cc;
+        const bool eq = in && row[0] == 0;
+        const unsigned eqm = __ballot_sync(0xffffffffu, eq), inm = __ballot_sync(0xffffffffu, in);
+        if (in) {
+          T *r = ctab + (size_t)(nm + lane + __popc(eqm & ((1u << lane) - 1u))) * S.cwidth;
+          pip_convert_row<T>(row, S.cc, r, S.cwidth, S.Np - S.Urs, 1, S.Shift, S.Bg - S.Nn - 1, S.Urs, lost);
+          if (eq) pip_convert_negate<T>(r, r + S.cwidth, S.cwidth, lost);
+        }
+        nm += __popc(inm) + __popc(eqm);
+      }
+    }
+    const bool wide = __any_sync(0xffffffffu, lost != 0);
+    if (lane == 0) {
+      PipProblem P;
+      P.nvar = S.Nn; P.nparm = S.Np; P.ni = nl; P.nc = nm; P.bigparm = S.Bg;
+      P.flags = S.pflags | (wide ? PIP_F_WIDE_INPUT : 0);
+      P.off = p * A.stride;
+      A.prob[p] = P;
+    }
+    max_nl = nl > max_nl ? nl : max_nl;
+    max_nm = nm > max_nm ? nm : max_nm;
+    nwide += wide ? 1 : 0;
+  }
+  if (lane == 0 && A.dims) {
+    atomicMax(A.dims + 0, max_nl);
+    atomicMax(A.dims + 1, max_nm);
+    if (nwide) atomicAdd(A.dims + 2, nwide);
+  }
+}
+
+extern "C" cudaError_t pip_launch_convert(const PipConvertArgs *A, int elem_log2, cudaStream_t stream)
+{
+  long long blocks = (A->n + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  if (elem_log2 == 2) pip_convert_kernel<int><<<(int)blocks, 256, 0, stream>>>(*A);
+  else pip_convert_kernel<pip_i64><<<(int)blocks, 256, 0, stream>>>(*A);
   return cudaGetLastError();
 }
 

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include "pip_convert.h"
 #include "pip_types.h"
 
 #define PIP_WARPS_PER_CTA_MAX 4
@@ -19,9 +20,13 @@ cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, int ctas, int
 cudaError_t pip_solve_occupancy(int shared_class, int warps_per_cta, size_t smem_bytes, int *ctas_per_sm);
 cudaError_t pip_launch_gather(PipResult *res, const int *order, const PipCell *cells, long long *dst_off,
                               pip_u64 *out, int nprob, long long *total, int phase, cudaStream_t stream);
+/* pass 0: size the streams the solver did not size; pass 1: decode (parm per problem, or *uparm for all;
+ * placement by dst_off, or by span reservation when so != NULL) */
 cudaError_t pip_launch_serialize(PipResult *res, const int *order, const PipCell *cells, const PipDecodeParm *parm,
-                                 const long long *dst_off, pip_i64 *out, pip_u64 *hashes, int nprob, int pass,
-                                 cudaStream_t stream);
+                                 const PipDecodeParm *uparm, const long long *dst_off, pip_i64 *out, pip_u64 *hashes,
+                                 int nprob, int pass, const PipStreamOut *so, cudaStream_t stream);
+cudaError_t pip_launch_init_results(PipResult *res, long long n, cudaStream_t stream);
+cudaError_t pip_launch_convert(const PipConvertArgs *A, int elem_log2, cudaStream_t stream);
 long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level, int vbytes);
 #ifdef __cplusplus
 }

@@ -62,9 +62,15 @@ struct PipStats {
 #endif
 
 /* capacity slack per level: {new parameters, main cut rows, extra context rows, sub cut rows} */
+#ifndef PIP_WIDE_DP
+#define PIP_WIDE_DP 6
+#define PIP_WIDE_DR 32
+#define PIP_WIDE_DX 24
+#define PIP_WIDE_DS 24
+#endif
 PIP_HD void pip_slack(int level, int &dp, int &dr, int &dx, int &ds)
 {
-  if (level == PIP_LEVEL_S_WIDE) { dp = 6; dr = 32; dx = 24; ds = 24; }   /* int32 shared class: spare shared memory */
+  if (level == PIP_LEVEL_S_WIDE) { dp = PIP_WIDE_DP; dr = PIP_WIDE_DR; dx = PIP_WIDE_DX; ds = PIP_WIDE_DS; }   /* int32 shared class: spare shared memory */
   else if (level >= 3) {
     const int k = level - 3 > 5 ? 5 : level - 3;      /* classes G3..G8 grow geometrically */
     dp = 6 << k; dr = 64 << (2 * k); dx = 24 << (2 * k); ds = 24 << (2 * k);
@@ -1065,6 +1071,311 @@ PIP_SDEV int pip_find_parm(const V *ctx, int cstride, int nr, int nparm, V *cut)
   return -1;
 }
 
+/* ---- register-resident feasibility solve (compa_test_xx / the context check) ----------------------
+ * Nine out of ten traiter_xx activations of a parametric problem are the two integer feasibility solves
+ * compa_test_xx runs per tested row (source/traiter.c:191-220) on a tableau of nparm Unit positions plus
+ * the nc context rows plus the tested row, nparm + 1 columns wide: a handful of rows of a handful of
+ * words.  Solved through the general path every one of them pays a copy into the arena, full-warp scans
+ * and barriers for 8 busy lanes.  Here the whole sub-tableau lives in registers: lane = one record
+ * (a Unit position, or a stored row whose PIP_SUBREG_NC words sit in the lane's registers), labelled with
+ * its *position*; every order-dependent scan of the reference (chercher, exam_coef, the k loop of
+ * choisir_piv, the i loop of integrer) is a minimum over position labels, the sort and the slot swap of a
+ * pivot only permute labels, the pivot row reaches the other lanes by shuffles.  Nothing is read from or
+ * written to memory after the load, so there is no barrier in the loop.
+ *
+ * Same arithmetic, same decisions, same pivot sequence as the general path (and the reference): the
+ * emulator tests run both and compare cells, statuses and pivot counts.  Returns 1 feasible, 0 infeasible,
+ * -1 when the solve does not fit the register form (more than 32 positions, more than PIP_SUBREG_NC
+ * columns: the caller falls back to the general path, nothing has been counted), or a PIP_ST_* status. */
+enum { PIP_SUBREG_NC = 8 };
+
+PIP_SDEV V pip_bcast(V v, int src)
+{
+  if (sizeof(V) == 8) return (V)W::shfl64((pip_i64)v, src);
+  return (V)W::shfl((int)v, src);
+}
+
+PIP_SDEVNI int pip_subsolve_regs(const V *ctx, int cstride, int nc, int np, const V *trow, int mnvar, int mode, int critic,
+                                 PipStats &st)
+{
+  enum { NC = PIP_SUBREG_NC, INF = 0x7fffffff };
+  const int lane = W::lane();
+  const int ncol = np + 1;
+  const int extra = mode == 0 ? 0 : 1;
+  int nl = np + nc + extra;
+  if (ncol > NC || nl > 32) return -1;
+  unsigned ovf = 0;
+  /* ---- load: expanser_xx(context, nparm, nc, nparm+1, nparm, extra, 0), source/traiter.c:191-218 ---- */
+  V row[NC];
+  #pragma unroll
+  for (int j = 0; j < NC; j++) row[j] = 0;
+  V den = 1;
+  int pos = lane < nl ? lane : INF;
+  int flag = lane < np ? PIP_UNIT : lane < nl ? PIP_UNKNOWN : 0;
+  int unit = lane;
+  if (lane >= np && lane < np + nc) {
+    const V *r = ctx + (lane - np) * cstride;
+    #pragma unroll
+    for (int j = 0; j < NC; j++) if (j < ncol) row[j] = r[j];
+  } else if (extra && lane == np + nc) {
+    #pragma unroll
+    for (int j = 0; j < NC; j++) if (j < ncol) {
+      V v = (j < np) ? trow[mnvar + 1 + j] : trow[mnvar];
+      if (mode == 1) { if (j == np && !critic) v -= 1; }
+      else { v = -v; if (j == np) v -= 1; }
+      row[j] = v;
+    }
+  }
+  pip_i64 det[PIP_MAX_DET];
+  #pragma unroll
+  for (int k = 0; k < PIP_MAX_DET; k++) det[k] = 0;
+  det[0] = 1;
+  int ldet = 1;
+  unsigned pivots = 0, cuts = 0, max_rows = 0;
+  unsigned long long elem = 0;
+  /* counters are committed on every exit but the fall-back one (the general path then counts the solve) */
+#define PIP_SUBREG_COMMIT() do { st.pivots += pivots; st.cuts += cuts; st.elem_updates += elem; \
+    if (max_rows > st.max_rows) st.max_rows = max_rows; \
+    if (pivots && (unsigned)ncol > st.max_cols) st.max_cols = ncol; } while (0)
+
+  /* ---- tab_sort_rows_xx, source/traiter.c:556-623: at entry lane == position and no row position is Unit */
+  {
+    const bool isrow = lane >= np && lane < nl;
+    unsigned sz = 0;
+    if (isrow) {
+      #pragma unroll
+      for (int j = 0; j < NC - 1; j++) if (j < np) {
+        const pip_u64 u = pip_uabs((pip_i64)row[j]);
+        if (u < 2147483648ull && (unsigned)u > sz) sz = (unsigned)u;        /* den == 1 */
+      }
+    }
+    const unsigned sb = pip_f2u((float)(double)sz);          /* size is stored as float */
+    const unsigned smax_u = W::redmax(isrow ? sz : 0u);
+    const double smax = (double)smax_u;
+    /* nothing moves when the rows are already in non-decreasing order of size */
+    unsigned pm = isrow ? sb : 0u;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = (unsigned)W::shfl_up((int)pm, o);
+      if (lane >= o && y > pm) pm = y;
+    }
+    unsigned before = (unsigned)W::shfl_up((int)pm, 1);
+    if (lane == 0) before = 0u;
+    if (W::any(isrow && sb < before)) {
+      const bool movable = isrow && (double)pip_u2f(sb) < smax;
+      #pragma unroll 1
+      for (int i = np; i < nl; i++) {
+        /* first minimum strictly below smax among the positions >= i */
+        const unsigned key = (movable && pos >= i) ? sb : 0xffffffffu;
+        const unsigned m = W::redmin(key);
+        if (m == 0xffffffffu) break;
+        const int bestk = (int)W::redmin(key == m ? (unsigned)pos : 0xffffffffu);
+        if (bestk != i) {                                   /* the two records trade positions */
+          if (pos == i) pos = bestk;
+          else if (pos == bestk) pos = i;
+        }
+      }
+    }
+  }
+
+  #pragma unroll 1
+  for (;;) {
+    const bool isunit = (flag & PIP_UNIT) != 0;
+    /* ---- chercher(Minus), then exam_coef without parameters: the sign of the constant, rows in position
+     * order up to and including the first negative one (source/traiter.c:669-680, 118-157) ---- */
+    int pivi = (int)W::redmin((flag & PIP_MINUS) ? (unsigned)pos : (unsigned)INF);
+    if (pivi == INF) {
+      const bool unk = flag == PIP_UNKNOWN;
+      V cst = 0;
+      #pragma unroll
+      for (int j = 0; j < NC; j++) if (j == np) cst = row[j];
+      const int ff = cst < 0 ? PIP_MINUS : cst > 0 ? PIP_PLUS : PIP_ZERO;
+      const int first = (int)W::redmin((unk && ff == PIP_MINUS) ? (unsigned)pos : (unsigned)INF);
+      if (unk && pos <= first) flag = ff;
+      pivi = first;
+    }
+    if (pivi == INF) {
+      /* ---- integrer_xx without parameters, source/integrer.c:305-534: first position below nvar whose
+       * stored row needs a cut ---- */
+      int verdict = 0, from = 0;
+      #pragma unroll 1
+      for (;;) {
+        const bool cand = !isunit && pos < np && pos >= from && den != 1;
+        const int i = (int)W::redmin(cand ? (unsigned)pos : (unsigned)INF);
+        if (i == INF) break;
+        const int Lc = pip_ffs(W::ballot(pos == i)) - 1;
+        const V D = pip_bcast(den, Lc);
+        if (D == 0) { PIP_SUBREG_COMMIT(); return PIP_ST_FAULT; }
+        /* the residues, computed by the owner of the row, handed to every lane */
+        V cut[NC];
+        bool okv = false, okc = false;
+        #pragma unroll
+        for (int j = 0; j < NC; j++) {
+          V x = 0;
+          if (lane == Lc && j < ncol) {
+            if (j < np) { x = pip_mod(row[j], D); okv = okv || x > 0; }
+            else { x = -pip_mod(-row[j], D); okc = x != 0; }
+          }
+          cut[j] = pip_bcast(x, Lc);
+        }
+        const bool ok_var = W::any(okv), ok_const = W::any(okc);
+        if (!ok_const) { from = i + 1; continue; }           /* case (a): this row is integral */
+        if (!ok_var) { verdict = -1; break; }                /* case (b): no solution */
+        if (nl >= 32) return -1;                             /* no lane left for the cut: general path */
+        if (lane == nl) {
+          #pragma unroll
+          for (int j = 0; j < NC; j++) row[j] = cut[j];
+          den = D; flag = PIP_MINUS; pos = nl; unit = 0;
+        }
+        verdict = nl + 1;                                    /* > 0: the position of the cut, plus one */
+        nl++;
+        cuts++;
+        break;
+      }
+      if (verdict <= 0) {
+        PIP_SUBREG_COMMIT();
+        if (PipVal<V>::narrow && W::any(ovf != 0)) return PIP_ST_WIDEN;
+        return verdict == 0 ? 1 : 0;
+      }
+      pivi = verdict - 1;
+    }
+
+    /* ---- pivoter_xx, source/traiter.c:345-548 ---- */
+    const bool isu = (flag & PIP_UNIT) != 0;                /* (the cut lane changed its flag above) */
+    const int Lp = pip_ffs(W::ballot(pos == pivi)) - 1;
+    V prow[NC];
+    #pragma unroll
+    for (int j = 0; j < NC; j++) prow[j] = pip_bcast(row[j], Lp);
+    const V dpiv = pip_bcast(den, Lp);
+    /* choisir_piv_xx, source/traiter.c:297-341: candidates in increasing column order, the incumbent's
+     * column entry of every record kept in a register */
+    int pivj = -1;
+    V pivot = 0, bcol = 0;
+    #pragma unroll
+    for (int j = 0; j < NC - 1; j++) {
+      if (j < np && prow[j] > 0) {                           /* warp-uniform */
+        const V a = isu ? ((unit == j) ? den : (V)0) : row[j];
+        if (pivj < 0) { pivj = j; pivot = prow[j]; bcol = a; }
+        else {
+          const pip_i64 x = (pos < nl) ? PipVal<V>::cross(pivot, a, bcol, prow[j]) : 0;
+          const int k = (int)W::redmin(x != 0 ? (unsigned)pos : (unsigned)INF);
+          if (k != INF && W::any(x < 0 && pos == k)) { pivj = j; pivot = prow[j]; bcol = a; }
+        }
+      }
+    }
+    if (pivj < 0) {                                          /* no positive coefficient: infeasible */
+      PIP_SUBREG_COMMIT();
+      if (PipVal<V>::narrow && W::any(ovf != 0)) return PIP_ST_WIDEN;
+      return 0;
+    }
+    /* determinant bookkeeping = the overflow verdict, source/traiter.c:394-447 (uniform, every lane) */
+    {
+      const bool trivial = dpiv == 1 && pivot == 1 && det[0] > -(1ll << 61) && det[0] < (1ll << 61);
+      if (!trivial) {
+        const pip_i64 d = (dpiv == 1) ? 1 : pip_gcd((pip_i64)pivot, (pip_i64)dpiv);
+        if (d == 0) { PIP_SUBREG_COMMIT(); return PIP_ST_FAULT; }
+        pip_i64 ppivot = pivot, dppiv = dpiv;
+        if (d != 1) { ppivot = pip_div((pip_i64)pivot, d); dppiv = pip_div((pip_i64)dpiv, d); }
+        #pragma unroll
+        for (int i = 0; i < PIP_MAX_DET; i++) {
+          if (i < ldet && dppiv != 1) {
+            const pip_i64 g = pip_gcd(det[i], dppiv);
+            if (g == 0) { PIP_SUBREG_COMMIT(); return PIP_ST_FAULT; }
+            if (g != 1) { det[i] = pip_div(det[i], g); dppiv = pip_div(dppiv, g); }
+          }
+        }
+        if (dppiv != 1) { PIP_SUBREG_COMMIT(); return PIP_ST_FATAL + 1; }   /* "Integer overflow" */
+        const int bp = pip_bitlen(ppivot);
+        bool placed = false;
+        #pragma unroll
+        for (int i = 0; i < PIP_MAX_DET; i++) {
+          if (!placed && i < ldet && pip_bitlen(det[i]) + bp < 64) { det[i] = (pip_i64)((pip_u64)det[i] * (pip_u64)ppivot); placed = true; }
+        }
+        if (!placed) {
+          ldet++;
+          if (ldet >= PIP_MAX_DET) { PIP_SUBREG_COMMIT(); return PIP_ST_FATAL + 1; }   /* "Integer overflow : 4" */
+          #pragma unroll
+          for (int i = 0; i < PIP_MAX_DET; i++) if (i == ldet - 1) det[i] = ppivot;
+        }
+      }
+    }
+    pivots++;
+    if ((unsigned)nl > max_rows) max_rows = nl;
+    elem += (unsigned long long)(nl - np - 1) * ncol;
+    /* the Unit record that owns column pivj (source/traiter.c:503-516) */
+    const unsigned um = W::ballot(isu && unit == pivj && pos < nl);
+    if (um == 0) { PIP_SUBREG_COMMIT(); return PIP_ST_FAULT; }
+    const int Lu = pip_ffs(um) - 1;
+    const int ku = W::shfl(pos, Lu);
+    /* rank-1 update of every stored row but the pivot row + re-flag (source/traiter.c:467-502, 518-529) */
+    bool fault = false;
+    if (!isu && lane != Lp && pos < nl) {
+      V foo = bcol;
+      if (!(foo == 0 && den == 1)) {
+        V lpiv = pivot;
+        if (foo == 0) lpiv = 1;
+        else if (pivot != 1 && foo != 1 && foo != -1) {
+          const V d = pip_gcd(pivot, foo);
+          if (d != 1) { lpiv = pip_div(pivot, d); foo = pip_div(foo, d); }
+        }
+        const V newden = PipVal<V>::mul(lpiv, den, ovf);
+        V g = newden;
+        const V zp = PipVal<V>::mul(dpiv, foo, ovf);
+        pip_u64 orz = 0;
+        #pragma unroll
+        for (int j = 0; j < NC; j++) {
+          V z = PipVal<V>::mulsub(row[j], lpiv, prow[j], foo, ovf);
+          if (j == pivj) z = zp;
+          row[j] = z;
+          orz |= (pip_u64)(pip_i64)z;
+        }
+        if (g != 1) {
+          if ((g & (g - 1)) == 0 && g > 0) { orz |= (pip_u64)(pip_i64)g; g = (V)(pip_i64)(orz & (0ull - orz)); }
+          else {
+            #pragma unroll
+            for (int j = 0; j < NC; j++) if (j < ncol && g != 1) g = pip_gcd(g, row[j]);
+          }
+        }
+        if (g != 1) {
+          if (g == 0) fault = true;
+          else if ((g & (g - 1)) == 0) {
+            int sh = 0;
+            while (((pip_u64)(pip_i64)g >> sh) != 1ull) sh++;
+            #pragma unroll
+            for (int j = 0; j < NC; j++) row[j] = row[j] >> sh;
+            den = newden >> sh;
+          } else {
+            const PipExactDiv e = pip_exact_prepare((pip_i64)g);
+            #pragma unroll
+            for (int j = 0; j < NC; j++) row[j] = (V)pip_exact_apply((pip_i64)row[j], e);
+            den = (V)pip_exact_apply((pip_i64)newden, e);
+          }
+        } else den = newden;
+        if (!fault) {
+          int ff = PIP_FLAG(flag);
+          const int fff = zp < 0 ? PIP_MINUS : zp == 0 ? PIP_ZERO : PIP_PLUS;
+          if (fff != PIP_ZERO && fff != ff) {
+            if (ff == PIP_ZERO) ff = (fff == PIP_MINUS ? PIP_UNKNOWN : fff);
+            else ff = PIP_UNKNOWN;
+            flag = ff;
+          }
+        }
+      }
+    }
+    if (W::any(fault)) { PIP_SUBREG_COMMIT(); return PIP_ST_FAULT; }
+    if (PipVal<V>::narrow && W::any(ovf != 0)) return PIP_ST_WIDEN;
+    /* the pivot row's storage goes to position ku, position pivi becomes Unit for pivj */
+    if (lane == Lp) {
+      #pragma unroll
+      for (int j = 0; j < NC; j++) row[j] = (j == pivj) ? dpiv : (V)(-prow[j]);
+      den = pivot; flag = PIP_PLUS; pos = ku;
+    } else if (lane == Lu) {
+      flag = PIP_UNIT | PIP_ZERO; unit = pivj; den = 1; pos = pivi;
+    }
+  }
+#undef PIP_SUBREG_COMMIT
+}
+
 /* The solver for one problem.  `B` is the warp's working arena (`words` words), `out` the
  * warp's cell window (at least sol_size cells free), `stk` the warp's frame stack. */
 PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, int words, int slack_level,
@@ -1081,6 +1392,9 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
     level_try = level_try == PIP_LEVEL_S_WIDE ? 2 : level_try - 1;
     if (level_try < 0) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
   }
+  /* device-converted input that does not fit the int32 pool (pip_convert.h): only the int64 pool, built
+   * on demand by the host, holds this problem */
+  if ((P.flags & PIP_F_WIDE_INPUT) && elem_log2 < 3) { status_out = PIP_ST_WIDEN; ncell_out = 0; return; }
   /* Compute_dual with parameters: the reference re-sorts the copy made at a split with Unit rows in
    * the constraint range and reads ineq[] entries it never wrote (source/traiter.c:585 vs 616-617),
    * so its answer is undefined; only the split-free case is implemented */
@@ -1142,6 +1456,23 @@ BUILD_SUB:
     PipTab S = L.s;
     const int np = M.nparm;
     const int extra = ret_site == 0 ? 0 : 1;
+#ifndef PIP_NO_SUBREG
+    {
+      /* the register-resident form first (pip_subsolve_regs); -1 = does not fit, take the general path */
+      const V *trow = extra ? pip_row(B, M, PIP_LINK(pip_fl(B, M)[ci])) : (const V *)nullptr;
+      /* (Deepest_cut rewrites the constant cuts of the sub-solves too, source/integrer.c:417-438: general path) */
+      const int r = (P.flags & PIP_F_DEEPEST) ? -1 : pip_subsolve_regs(ctx, cstride, nc, np, trow, M.nvar, ret_site, critic, st);
+      if (r >= 0) {
+        st.subsolves++;
+        PIP_LAP(st, PIP_PH_BUILDSUB);
+        if (r > 1) { status = r; goto DONE; }
+        feasible = r == 1;
+        T = S; T.nvar = np; T.nparm = 0;           /* SUB_DONE sizes the transient cells from the sub tableau */
+        level = 1;
+        goto SUB_DONE;
+      }
+    }
+#endif
     S.nvar = np; S.nparm = 0; S.ni = nc + extra; S.ldet = 1;
     if (np + nc + extra > S.pcap || nc + extra > S.rcap || np + 1 > S.stride) { status = PIP_ST_CAPACITY; goto DONE; }
     int *sfl = pip_fl(B, S);

@@ -24,7 +24,9 @@ enum { PIP_C_FREE = 0, PIP_C_NIL = 1, PIP_C_IF = 2, PIP_C_LIST = 3, PIP_C_FORM =
        PIP_C_DIV = 6, PIP_C_VAL = 7, PIP_C_ERROR = 8 };
 /* problem flags (traiter flags, source/funcall.h:34-35, + our own) */
 enum { PIP_F_INT = 1, PIP_F_DUAL = 2, PIP_F_DEEPEST = 4,
-       PIP_F_SIMPLE_SER = 8 };    /* cells -> quast words without column surgery: the solver sizes the stream itself */
+       PIP_F_SIMPLE_SER = 8,      /* cells -> quast words without column surgery: the solver sizes the stream itself */
+       PIP_F_WIDE_INPUT = 16 };   /* device-side conversion: some input value left int32 (the int32 pool holds garbage
+                                     for this problem; it is solved from the int64 pool built on demand) */
 
 /* phases of the -DPIP_PROFILE cycle accounting */
 enum { PIP_PH_LOAD = 0, PIP_PH_SORT, PIP_PH_SCAN, PIP_PH_BUILDSUB, PIP_PH_CHOOSE, PIP_PH_UPDATE, PIP_PH_SWAP,
@@ -98,6 +100,26 @@ typedef struct {
 #define PIP_CELL_KIND(w) ((int)((w) & 15ull))
 #define PIP_CELL_P2(w) ((pip_i64)(((w) >> 4) & 0xffffull))
 #define PIP_CELL_P1(w) (((pip_i64)(w)) >> 20)
+
+/* Device-side decode with span reservation (dense path): the decoding warp reserves the problem's span of
+ * the compact word buffer with one atomic add, so neither a scan kernel nor a host round trip sits between
+ * the solve and the decode; per-problem results land in structure-of-arrays form (no 56-byte records cross
+ * PCIe), counters are summed on the device. */
+typedef struct {
+  unsigned long long *ctl;       /* [0] 64-bit slots reserved so far, [1] problems with a final status (this
+                                    launch), [2] set when a span did not fit `cap`, [3] spare */
+  long long cap;                 /* 64-bit slots in the compact buffer */
+  int words64;                   /* 1: every word is written as int64; 0: int32 words for PIP_RES_SER32 problems */
+  int *status;
+  pip_u64 *hash;
+  long long *off;                /* slot offset of the problem's span in the compact buffer */
+  long long *len;                /* words; bit 62 set when they were written as int32 */
+  unsigned long long *stats;     /* [8]: pivots, cuts, subsolves, splits, elem_updates, cells, max_rows, max_cols
+                                    (final statuses only) */
+} PipStreamOut;
+#define PIP_LEN_NARROW (1ll << 62)
+enum { PIP_SO_SLOTS = 0, PIP_SO_FINALS = 1, PIP_SO_OVERFLOW = 2, PIP_SO_NCTL = 4 };
+#define PIP_STATUS_IS_FINAL(st) ((st) != PIP_ST_PENDING && (st) != PIP_ST_CAPACITY && (st) != PIP_ST_WIDEN)
 
 /* launch parameters of the warp-per-problem kernels */
 typedef struct {

@@ -11,15 +11,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libpipemu.so")
 
 
-def build():
+def build(defines=(), so=None):
+    """defines + so: a variant of the emulated device source (e.g. PIP_NO_SUBREG: every feasibility
+    solve through the general path) next to the default build"""
     srcs = [os.path.join(HERE, f) for f in ("emu_runtime.cpp", "emu_driver.cpp")]
     subprocess.check_call(["g++", "-O2", "-g", "-fwrapv", "-DPIP_EMU", "-fPIC", "-shared", "-Wall",
-                           "-Wno-unused-function", "-Wno-unknown-pragmas"] + srcs + ["-o", SO])
+                           "-Wno-unused-function", "-Wno-unknown-pragmas"] + ["-D" + d for d in defines] + srcs +
+                          ["-o", so or SO])
+    return so or SO
 
 
 def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_level=2, order_mode=0,
-                        sol_size=0, maxcol=0, narrow=0):
-    lib = C.CDLL(SO)
+                        sol_size=0, maxcol=0, narrow=0, so=None):
+    lib = C.CDLL(so or SO)
     probs, pool = pack_tableau_problems(cases)
     n = len(probs)
     res = np.zeros(n, dtype=RESULT_DTYPE)

@@ -122,3 +122,18 @@ def test_no_cpu_solver_in_product():
                 if re.search(r"oracle/|piporacle|pipref|libpipemu", t) and f != "pip_host.cpp":
                     bad.append(f)
     assert not bad, bad
+
+
+def test_process_exits_after_the_host_pool_started(libpath):
+    """the dense entry point starts the persistent host thread pool before it touches the device; a process
+    that used it must still exit (a destroyed condition variable with parked workers blocks in glibc).
+    Without a GPU the call itself fails loudly (-1): there is no CPU path."""
+    import subprocess
+    import sys
+    code = ("import numpy as np\n"
+            "from piplib_b200 import api\n"
+            "dom = np.zeros((4, 3, 5), dtype=np.int64)\n"
+            "try:\n    api.solve_dense(dom, None, -1)\nexcept RuntimeError as e:\n    print('refused:', e)\n"
+            "print('bye')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "bye" in r.stdout

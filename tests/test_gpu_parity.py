@@ -298,11 +298,11 @@ def test_edge_cases(api, port):
     assert (st, ser) == port.solve([[1, 1, -1, 0]], np.zeros((0, 3), dtype=np.int64), -1, ctx_cols=3)
 
 
-@pytest.mark.parametrize("knob", ["PIPLIB_B200_THREAD_DECODE", "PIPLIB_B200_HOST_DECODE", "PIPLIB_B200_EXACT_PLAN",
+@pytest.mark.parametrize("knob", ["PIPLIB_B200_HOST_DECODE", "PIPLIB_B200_EXACT_PLAN",
                                   "PIPLIB_B200_NO_INT32", "PIPLIB_B200_NO_WIDE_SLACK", "PIPLIB_B200_NO_TMA"])
 def test_alternative_paths_give_the_same_answers(api, port, monkeypatch, knob):
     """every run-time knob of INTEGRATION.md section 7 selects another route to the same answer: the
-    thread-per-problem and the host decoder, the exact planning pass, the int64 shared-memory class,
+    host decoder, the exact planning pass, the int64 shared-memory class,
     the narrow capacity slack, the large kernel without shared-memory staging"""
     from workloads import synth
     monkeypatch.setenv(knob, "1")
@@ -394,3 +394,136 @@ def test_large_tableau_4096_vs_reference_golden(api):
     p.close()
     assert st == g["status"] and info["pivots"] == g["pivots"] and info["cuts"] == g["cuts"]
     assert cells == g["cells"]
+
+
+# ---- pinned caller buffers: DMA + device-side input conversion ----------------------
+
+def _words(r, i):
+    return [int(x) for x in r["ser"][r["ser_off"][i]:r["ser_off"][i] + r["ser_len"][i]]]
+
+
+def _dense_equal(a, b, n):
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["hashes"], b["hashes"])
+    assert np.array_equal(a["ser_len"], b["ser_len"])
+    for i in range(0, n, max(1, n // 200)):
+        assert _words(a, i) == _words(b, i)
+
+
+@pytest.mark.parametrize("workload,n", [("loopnest16x24p3", 40000), ("sor1d", 30000), ("fimmel", 2000)])
+def test_pinned_buffers_dma_path_vs_oracle(api, port, workload, n, monkeypatch):
+    """caller arrays in page-locked memory: raw PolyLib rows go up by DMA and tab_Matrix2Tableau runs as a
+    kernel, the quasts come down straight into the caller's stream.  Against the oracle, and word for
+    word against the pageable (host conversion, staged output) route and the two mixed routes."""
+    from workloads import synth
+    monkeypatch.setenv("PIPLIB_B200_CHUNK", "8192")          # several chunks, several lanes
+    dom, ctx = synth.generate(workload, n, seed=41)
+    bg, opts = synth.bignum(workload), synth.options(workload)
+    base = api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, **opts)        # pageable
+    api.pin(dom), api.pin(ctx)
+    try:
+        out = api.alloc_result(n, pinned=True)
+        r = api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, out=out, **opts)
+        assert int(api.last_stats().h2d_bytes) >= dom.nbytes              # the raw rows really went up
+        m = min(n, 6000)
+        _, st_o, h_o, _ = port.bench_dense(0, m, dom[:m], ctx[:m], bg, **opts)
+        st_g = np.where(r["status"][:m] == 1, 0, r["status"][:m])
+        assert np.array_equal(st_g, st_o) and np.array_equal(r["hashes"][:m][st_o == 0], h_o[st_o == 0])
+        for i in range(0, m, max(1, m // 10)):
+            st, ser = port.solve(dom[i], ctx[i], bg, ctx_cols=ctx.shape[2], **opts)
+            assert (st, ser) == (int(st_g[i]), _words(r, i)) or st != 0
+        _dense_equal(r, base, n)
+        monkeypatch.setenv("PIPLIB_B200_STAGED_OUT", "1")      # device conversion, staged output
+        _dense_equal(api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, **opts), base, n)
+        monkeypatch.delenv("PIPLIB_B200_STAGED_OUT")
+        monkeypatch.setenv("PIPLIB_B200_HOST_CONVERT", "1")    # host conversion, DMA output
+        out2 = api.alloc_result(n, pinned=True)
+        _dense_equal(api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, out=out2, **opts), base, n)
+        api.unpin(out["ser"]), api.unpin(out2["ser"])
+    finally:
+        api.unpin(dom), api.unpin(ctx)
+
+
+def test_device_conversion_column_surgery(api):
+    """the option variants of every example (Maximize / Urs_parms / Urs_unknowns / big parameter: Shift,
+    bignum and Urs column synthesis of tab_Matrix2Tableau, source/tab.c:292-393) through the device-side
+    conversion: one-problem dense batches in pinned memory against the reference's serialised quasts"""
+    checked = 0
+    for c in LIB:
+        if c["opts"].get("Simplify"):
+            continue                              # host-only post-pass: takes the staged route anyway
+        dom = np.ascontiguousarray(np.asarray(c["dom"], dtype=np.int64).reshape(1, *c["dom_shape"]))
+        ctx = None
+        if c["ctx_shape"] is not None:
+            ctx = np.ascontiguousarray(np.asarray(c["ctx"], dtype=np.int64).reshape(1, *c["ctx_shape"]))
+        if dom.size == 0:
+            continue
+        api.pin(dom)
+        if ctx is not None and ctx.size:
+            api.pin(ctx)
+        try:
+            r = api.solve_dense(dom, ctx, c["bignum"], want_hashes=True, want_ser=True, **c["opts"])
+        finally:
+            api.unpin(dom)
+            if ctx is not None and ctx.size:
+                api.unpin(ctx)
+        st = int(r["status"][0])
+        assert (0 if st == 1 else st) == c["ref_status"], c["name"]
+        if c["ref_status"] == 0:
+            assert _words(r, 0) == c["ref_ser"], c["name"]
+        checked += 1
+    assert checked > 60
+
+
+def test_device_conversion_equalities_and_wide_inputs(api, port):
+    """pinned route: a batch whose number of equality rows varies from problem to problem (the device
+    counts them; the pool reserves the worst case), and inputs that leave int32 (the int32 pool flags
+    them, the int64 pool is built on demand)"""
+    from workloads import synth
+    n = 3000
+    dom, ctx = synth.generate("loopnest8x12p2", n, seed=13)
+    dom = dom.copy()
+    rng = np.random.default_rng(9)
+    for i in range(n):
+        if i % 2:
+            for r in rng.choice(dom.shape[1], size=int(rng.integers(0, 3)), replace=False):
+                dom[i, r, 0] = 0
+        if i % 97 == 5:
+            dom[i, int(rng.integers(0, dom.shape[1])), -1] += (1 << 40)      # a constant beyond int32
+    dom = np.ascontiguousarray(dom)
+    _, st_o, h_o, _ = port.bench_dense(0, n, dom, ctx, -1)
+    api.pin(dom), api.pin(ctx)
+    try:
+        r = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+    finally:
+        api.unpin(dom), api.unpin(ctx)
+    st_g = np.where(r["status"] == 1, 0, r["status"])
+    assert np.array_equal(st_g, st_o)
+    ok = st_o == 0
+    assert ok.sum() > n // 8 and np.array_equal(r["hashes"][ok], h_o[ok])
+
+
+def test_one_call_over_several_gpus(api, port):
+    """pip_set_devices_dp: one pip_solve_dense_dp call spreads its chunks over every visible GPU through
+    a shared queue; the caller's arrays come back as from one device"""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs at least two GPUs")
+    from workloads import synth
+    n = 60000
+    dom, ctx = synth.generate("loopnest16x24p3", n, seed=19)
+    one = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
+    api.set_devices(list(range(ng)))
+    os.environ["PIPLIB_B200_CHUNK"] = "4096"
+    try:
+        for pinned in (False, True):
+            if pinned:
+                api.pin(dom), api.pin(ctx)
+            out = api.alloc_result(n, pinned=pinned)
+            r = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True, out=out)
+            _dense_equal(r, one, n)
+            if pinned:
+                api.unpin(dom), api.unpin(ctx), api.unpin(out["ser"])
+    finally:
+        api.set_devices([])
+        del os.environ["PIPLIB_B200_CHUNK"]
