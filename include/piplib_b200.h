@@ -71,6 +71,10 @@ typedef struct {
   unsigned long long h2d_bytes, d2h_bytes;
   unsigned long long cells;  /* solution cells produced by the batch */
   unsigned long long phase_cycles[16]; /* per-phase warp cycles, profile build only (else 0) */
+  unsigned long long wrapped; /* problems in which an exact 128-bit product of a pivot update left int64: the
+                                 reference wraps silently there (source/traiter.c:483-485) and so do we -- the answer is
+                                 bit-identical -- but from that point on its verdict is "Integer overflow" or garbage
+                                 (SURVEY.md section 8, P3).  Per problem: pip_last_batch_flags_dp. */
 } PipBatchStats_dp;
 
 /* n x pip_solve_dp.  options may be NULL (defaults) ; contexts[i] may be NULL (no parameters).
@@ -99,7 +103,7 @@ void pip_cells_bind_dp(const PipCell_dp *cells, int ncells);
 /* Dense batch through the pip_solve_dp path: dom is [n][dom_rows][dom_cols] (PolyLib rows),
  * ctx is [n][ctx_rows][ctx_cols] or NULL (has_ctx=0).  Host buffers in, host buffers out:
  *   status[i]  as above
- *   hashes[i]  (optional) FNV-1a over the serialised quast words (the function tests/ and
+ *   hashes[i]  (optional) hash of the serialised quast words (pip_hash_word: a sum of mixed (word, index) pairs; the function tests/ and
  *              oracle/ apply to the reference's trees); 0 when status[i] is fatal
  *   ser        (optional) the serialised quasts: problem i occupies
  *              ser[ser_off[i] .. ser_off[i] + ser_len[i]); spans are packed without gaps but, as
@@ -155,6 +159,10 @@ int pip_large_fetch_dp(pip_large_problem *p, int *status, PipCell_dp *cells, int
 void pip_large_destroy_dp(pip_large_problem *p);
 
 void pip_last_batch_stats_dp(PipBatchStats_dp *out);
+/* per-problem flags of the last pip_solve_batch_dp / pip_traiter_batch_dp call on this thread
+ * (bit 0 = PIP_FLAG_WRAPPED, see PipBatchStats_dp.wrapped); returns the number of problems of that call */
+#define PIP_FLAG_WRAPPED 1u
+long long pip_last_batch_flags_dp(unsigned *flags, long long cap);
 
 /* PipQuast -> int64 stream; returns the number of words (may exceed cap: nothing past cap is written) */
 long pip_quast_serialize_dp(const PipQuast_dp *q, long long *out, long cap);

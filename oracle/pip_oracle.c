@@ -970,15 +970,18 @@ int piporacle_solve_ser(int dom_rows, int dom_cols, const I *dom,
   return rc;
 }
 
-static unsigned long long fnv(unsigned long long h, long long v)
+/* hash of a serialised quast: start value + sum over the words of the splitmix64 finaliser of
+ * (word + (index + 1) * golden ratio): the function the library applies (pip_decode.h, pip_hash_word) */
+static unsigned long long hash_word(unsigned long long v, unsigned long long k)
 {
-  h ^= (unsigned long long)v;
-  h *= 0x9E3779B97F4A7C15ULL;
-  h ^= h >> 32;
-  return h;
+  unsigned long long x = v + (k + 1ULL) * 0x9E3779B97F4A7C15ULL;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+  x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+  x ^= x >> 31;
+  return x;
 }
 
-/* timed loop over a dense batch; hashes are FNV-1a over the serialised quast words, the same
+/* timed loop over a dense batch; hashes are hash_word sums over the serialised quast words, the same
  * function oracle/ref_harness.c applies to the reference's PipQuast */
 double piporacle_bench_dense(long first, long count, int dom_rows, int dom_cols, const I *dom,
                              int has_ctx, int ctx_rows, int ctx_cols, const I *ctx, int bg,
@@ -998,7 +1001,7 @@ double piporacle_bench_dense(long first, long count, int dom_rows, int dom_cols,
     if (status) status[i - first] = rc;
     if (hashes) {
       unsigned long long h = 0xcbf29ce484222325ULL;
-      if (rc == PIO_OK) { for (k = 0; k < n && k < cap; k++) h = fnv(h, buf[k]); } else h = 0;
+      if (rc == PIO_OK) { for (k = 0; k < n && k < cap; k++) h += hash_word((unsigned long long)buf[k], (unsigned long long)k); } else h = 0;
       hashes[i - first] = h;
     }
     if (tot) {

@@ -243,15 +243,18 @@ int pipref_solve_ser(int dom_rows, int dom_cols, const long long *dom,
   return 0;
 }
 
-static unsigned long long fnv(unsigned long long h, long long v)
+/* hash of a serialised quast: start value + sum over the words of the splitmix64 finaliser of
+ * (word + (index + 1) * golden ratio): the function the library applies (pip_decode.h, pip_hash_word) */
+static unsigned long long hash_word(unsigned long long v, unsigned long long k)
 {
-  h ^= (unsigned long long)v;
-  h *= 0x9E3779B97F4A7C15ULL;
-  h ^= h >> 32;
-  return h;
+  unsigned long long x = v + (k + 1ULL) * 0x9E3779B97F4A7C15ULL;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+  x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+  x ^= x >> 31;
+  return x;
 }
-static unsigned long long hash_h;
-static void hput(long long v) { hash_h = fnv(hash_h, v); }
+static unsigned long long hash_h, hash_k;
+static void hput(long long v) { hash_h += hash_word((unsigned long long)v, hash_k++); }
 static void hash_vec(PipVector_dp *v)
 { int i; hput(v->nb_elements); for (i = 0; i < v->nb_elements; i++) { hput(v->the_vector[i]); hput(v->the_deno[i]); } }
 static void hash_quast(PipQuast_dp *s)
@@ -270,7 +273,7 @@ static void hash_quast(PipQuast_dp *s)
 }
 
 /* Timed loop of pip_solve_dp over problems [first, first+count) of a dense batch (all problems
- * share one shape).  hashes[i] = FNV-1a of the serialised quast (0 for fatal), status[i] as
+ * share one shape).  hashes[i] = hash_word sum of the serialised quast (0 for fatal), status[i] as
  * above.  Returns seconds spent inside the solve loop (matrix setup included, as a real caller
  * pays it; hashing and freeing excluded by a second clock). */
 double pipref_bench_dense(long first, long count,
@@ -307,7 +310,7 @@ double pipref_bench_dense(long first, long count,
     pipref_armed = 0;
     total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     if (status) status[i - first] = 0;
-    if (hashes) { hash_h = 0xcbf29ce484222325ULL; hash_quast(q); hashes[i - first] = hash_h; }
+    if (hashes) { hash_h = 0xcbf29ce484222325ULL; hash_k = 0; hash_quast(q); hashes[i - first] = hash_h; }
     pip_quast_free_dp(q);
   }
   quiet_end();

@@ -44,7 +44,7 @@ class PipBatchStats(C.Structure):
                 ("seconds_d2h", C.c_double), ("seconds_host", C.c_double),
                 ("device_ms", C.c_float), ("launches", C.c_int), ("rounds", C.c_int),
                 ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
-                ("cells", C.c_ulonglong), ("phase_cycles", C.c_ulonglong * 16)]
+                ("cells", C.c_ulonglong), ("phase_cycles", C.c_ulonglong * 16), ("wrapped", C.c_ulonglong)]
 
 
 _lib = None
@@ -88,6 +88,8 @@ def lib():
         L.pip_large_destroy_dp.argtypes = [C.c_void_p]
         L.pip_last_batch_stats_dp.argtypes = [C.POINTER(PipBatchStats)]
         L.pip_set_device_dp.restype = C.c_int
+        L.pip_last_batch_flags_dp.restype = C.c_longlong
+        L.pip_last_batch_flags_dp.argtypes = [C.c_void_p, C.c_longlong]
         L.pip_set_devices_dp.restype = C.c_int
         L.pip_pin_buffer_dp.restype = C.c_int
         L.pip_pin_buffer_dp.argtypes = [C.c_void_p, C.c_size_t]
@@ -122,6 +124,14 @@ def pin(a):
 def unpin(a):
     if a is not None and a.nbytes:
         lib().pip_unpin_buffer_dp(a.ctypes.data)
+
+
+def last_flags():
+    """per-problem flags of the last batch / traiter call on this thread (bit 0: a 128-bit product wrapped)"""
+    n = lib().pip_last_batch_flags_dp(None, C.c_longlong(0))
+    out = np.zeros(max(int(n), 1), dtype=np.uint32)
+    lib().pip_last_batch_flags_dp(out.ctypes.data_as(C.c_void_p), C.c_longlong(int(n)))
+    return out[:int(n)]
 
 
 def last_stats():

@@ -28,13 +28,22 @@ struct PipSer {
 };
 #define PIP_HASH_INIT 0xcbf29ce484222325ULL
 
+/* hash of a serialised quast = PIP_HASH_INIT + sum over the words of a 64-bit mix of (word, index)
+ * (the splitmix64 finaliser).  A sum, so that the lanes of a warp hash their own words and add up: the
+ * chained form this replaces (h = (h ^ w) * K, word after word) was the longest dependency chain of the
+ * decode kernel.  The checker libraries apply the same function to the reference's trees. */
+PIP_HD pip_u64 pip_hash_word(pip_u64 v, pip_u64 k)
+{
+  pip_u64 x = v + (k + 1ull) * 0x9E3779B97F4A7C15ULL;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+  x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+  x ^= x >> 31;
+  return x;
+}
+
 PIP_HD void pip_sput(PipSer &s, pip_i64 v)
 {
-  if (s.hashing) {
-    s.h ^= (pip_u64)v;
-    s.h *= 0x9E3779B97F4A7C15ULL;
-    s.h ^= s.h >> 32;
-  }
+  if (s.hashing) s.h += pip_hash_word((pip_u64)v, (pip_u64)s.len);
   s.wide |= (unsigned)(v != (pip_i64)(int)v);
   if (s.out && s.len < s.cap) {
     if (s.narrow_out) ((int *)s.out)[s.len] = (int)v;

@@ -8,7 +8,7 @@
  * the control flow is warp-uniform: the cells of the problem are staged in shared memory with one
  * coalesced copy, all lanes parse the same stream, the entries of a vector (9 of 10 cells are
  * `Val`s) are reduced lane-parallel, and the words leave through a shared-memory tile that is
- * hashed and written out coalesced.
+ * hashed (every lane its own words, the hash is a sum) and written out coalesced.
  */
 #ifndef PIP_DECODE_WARP_H
 #define PIP_DECODE_WARP_H
@@ -24,7 +24,7 @@ struct PipWarpSer {
   pip_i64 *out;           /* destination (64-bit slots), may be NULL */
   long long cap, len;     /* words the destination holds / words emitted so far (warp-uniform) */
   int fill;               /* words waiting in the tile (warp-uniform) */
-  pip_u64 h;
+  pip_u64 h;              /* this LANE's share of the hash sum (pip_hash_word); pip_wser_hash adds the lanes up */
   int narrow_out;
   unsigned wide;
 };
@@ -38,14 +38,10 @@ PIP_DEVNI PipFlushOut pip_wser_flush_tile(const pip_i64 *tile, int n, pip_u64 h,
 {
   W::sync();
   const int lane = W::lane();
-  for (int k = 0; k < n; k++) {
-    h ^= (pip_u64)tile[k];
-    h *= 0x9E3779B97F4A7C15ULL;
-    h ^= h >> 32;
-  }
   bool w = false;
   for (int k = lane; k < n; k += 32) {
     const pip_i64 v = tile[k];
+    h += pip_hash_word((pip_u64)v, (pip_u64)(base + k));
     w = w || (v != (pip_i64)(int)v);
     if (out && base + k < cap) {
       if (narrow_out) ((int *)out)[base + k] = (int)v;
@@ -65,6 +61,14 @@ PIP_DEV void pip_wser_flush(PipWarpSer &s)
   s.h = r.h;
   s.wide |= r.wide;
   s.fill = 0;
+}
+
+/* the hash of the whole stream once everything is flushed: start value + the lanes' shares */
+PIP_DEV pip_u64 pip_wser_hash(const PipWarpSer &s)
+{
+  pip_u64 h = s.h;
+  for (int o = 16; o > 0; o >>= 1) h += (pip_u64)W::shfl_xor64((long long)h, o);
+  return h + PIP_HASH_INIT;
 }
 
 PIP_DEV void pip_wput(PipWarpSer &s, pip_i64 v)

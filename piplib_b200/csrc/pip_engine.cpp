@@ -298,16 +298,16 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
   PipStreamOut so;
   memset(&so, 0, sizeof so);
   long long slots_done = 0;              /* stream_out: slots reserved by the rounds completed so far */
-  unsigned long long stats_prev[8] = {0};   /* ... and the device counters at the end of the last good round */
+  unsigned long long stats_prev[PIP_SO_NSTAT] = {0};   /* ... and the device counters at the end of the last good round */
   unsigned long long *h_ctl = nullptr;
   if (stream_out) {
     E.d_so_status.reserve(n * sizeof(int));
     E.d_so_hash.reserve(n * sizeof(pip_u64));
     E.d_so_off.reserve(n * sizeof(long long));
     E.d_so_len.reserve(n * sizeof(long long));
-    E.d_so_ctl.reserve((PIP_SO_NCTL + 8) * sizeof(unsigned long long));
-    CK(cudaMemsetAsync(E.d_so_ctl.p, 0, (PIP_SO_NCTL + 8) * sizeof(unsigned long long), s));
-    E.h_ctl.reserve((PIP_SO_NCTL + 8) * sizeof(unsigned long long));
+    E.d_so_ctl.reserve((PIP_SO_NCTL + PIP_SO_NSTAT) * sizeof(unsigned long long));
+    CK(cudaMemsetAsync(E.d_so_ctl.p, 0, (PIP_SO_NCTL + PIP_SO_NSTAT) * sizeof(unsigned long long), s));
+    E.h_ctl.reserve((PIP_SO_NCTL + PIP_SO_NSTAT) * sizeof(unsigned long long));
     h_ctl = (unsigned long long *)E.h_ctl.p;
     const long long hint = in.words_hint > 0 ? in.words_hint : (long long)n * (in.words64 ? 640 : 384);
     E.d_compact.reserve((size_t)std::max<long long>(hint, 1024) * sizeof(pip_u64));
@@ -451,12 +451,17 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       L.sol_size = in.sol_size; L.maxcol = in.maxcol; L.maxparm = PIP_MAXPARM;
       L.slack_level = cs.level;
       L.prof = (unsigned long long *)E.d_prof.p;
+      L.hash_out = stream_out ? so.hash : nullptr;
       double tk = now_s();
       /* PIPLIB_B200_LARGE_FROM=<class index> moves the hand-over (tests), a negative value disables it */
       const char *lf = getenv("PIPLIB_B200_LARGE_FROM");
       const int large_from = lf && *lf ? atoi(lf) : PIP_LARGE_FROM_DEFAULT;
       bool use_large = large_from >= 0 && k >= large_from && m <= 4 && elem_log2 <= 3;
       if (use_large) { const PipProblem *hp = host_prob(); for (int q = 0; q < m && use_large; q++) use_large = large_eligible(hp[order[q]]); }
+      /* word mode: every stream can be written by the solver itself (no column surgery anywhere in the batch):
+       * no cells, no decode kernel -- a copy into the compact buffer is all that follows the solve */
+      const bool words_round = stream_out && all_sized && !use_large && getenv("PIPLIB_B200_CELL_DECODE") == nullptr;
+      L.emit_words = words_round ? 1 : 0;
       if (use_large) {
         run_large_round(in, host_prob(), d_pool, elem_log2, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
         out.times.launches += m;
@@ -477,11 +482,15 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
          * buffer turns out too small, grow it and decode the round again (the cells are still there) */
         for (;;) {
           CK(cudaMemsetAsync(so.ctl + PIP_SO_FINALS, 0, 2 * sizeof(unsigned long long), s));   /* finals, overflow */
-          CK(pip_launch_serialize((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p, d_parm, in.uniform_decode,
-                                  nullptr, (pip_i64 *)E.d_compact.p, nullptr, m, 1, &so, s));
+          if (words_round)
+            CK(pip_launch_gather_words((const PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p,
+                                       (pip_i64 *)E.d_compact.p, m, &so, s));
+          else
+            CK(pip_launch_serialize((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p, d_parm, in.uniform_decode,
+                                    nullptr, (pip_i64 *)E.d_compact.p, nullptr, m, 1, &so, s));
           out.times.launches++;
           CK(cudaEventRecord(E.ev1, s));
-          CK(cudaMemcpyAsync(h_ctl, so.ctl, (PIP_SO_NCTL + 8) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+          CK(cudaMemcpyAsync(h_ctl, so.ctl, (PIP_SO_NCTL + PIP_SO_NSTAT) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
           CK(cudaStreamSynchronize(s));
           if (!h_ctl[PIP_SO_OVERFLOW]) break;
           /* h_ctl[SLOTS] = what the rounds so far need in total.  Grow, keep the spans of the earlier rounds,
@@ -492,14 +501,14 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
           if (slots_done) CK(cudaMemcpyAsync(bigger.p, E.d_compact.p, (size_t)slots_done * sizeof(pip_u64), cudaMemcpyDeviceToDevice, s));
           h_ctl[PIP_SO_SLOTS] = (unsigned long long)slots_done;
           h_ctl[PIP_SO_FINALS] = h_ctl[PIP_SO_OVERFLOW] = h_ctl[3] = 0;
-          for (int c = 0; c < 8; c++) h_ctl[PIP_SO_NCTL + c] = stats_prev[c];
-          CK(cudaMemcpyAsync(so.ctl, h_ctl, (PIP_SO_NCTL + 8) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+          for (int c = 0; c < PIP_SO_NSTAT; c++) h_ctl[PIP_SO_NCTL + c] = stats_prev[c];
+          CK(cudaMemcpyAsync(so.ctl, h_ctl, (PIP_SO_NCTL + PIP_SO_NSTAT) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
           CK(cudaStreamSynchronize(s));
           E.d_compact.release();
           E.d_compact = bigger;
           so.cap = (long long)(E.d_compact.cap / sizeof(pip_u64));
         }
-        for (int c = 0; c < 8; c++) stats_prev[c] = h_ctl[PIP_SO_NCTL + c];
+        for (int c = 0; c < PIP_SO_NSTAT; c++) stats_prev[c] = h_ctl[PIP_SO_NCTL + c];
         finals = (int)h_ctl[PIP_SO_FINALS];
         total = (long long)h_ctl[PIP_SO_SLOTS] - slots_done;
       } else {
@@ -597,7 +606,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
     out.dev.words = (const pip_i64 *)E.d_compact.p;
     out.dev.slots = slots_done;
     out.dev.status = so.status; out.dev.hash = so.hash; out.dev.off = so.off; out.dev.len = so.len;
-    for (int k = 0; k < 8; k++) out.dev.stats[k] = h_ctl[PIP_SO_NCTL + k];
+    for (int k = 0; k < PIP_SO_NSTAT; k++) out.dev.stats[k] = h_ctl[PIP_SO_NCTL + k];
     /* anything still unsolved is too large for the ladder: its status array entry says CAPACITY already
      * (the last decode pass wrote the record's status) */
   } else {

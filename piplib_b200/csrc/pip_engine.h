@@ -43,7 +43,7 @@ struct PipDeviceOut {
   const int *status = nullptr;
   const pip_u64 *hash = nullptr;
   const long long *off = nullptr, *len = nullptr;   /* per problem: slot offset, words | PIP_LEN_NARROW */
-  unsigned long long stats[8] = {0};    /* pivots, cuts, subsolves, splits, elem_updates, cells, max_rows, max_cols */
+  unsigned long long stats[PIP_SO_NSTAT] = {0};   /* pivots, cuts, subsolves, splits, elem_updates, cells, max_rows, max_cols, wrapped */
 };
 
 struct PipBatchTimes {

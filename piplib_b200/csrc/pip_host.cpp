@@ -251,11 +251,7 @@ PipQuast_dp *decode_quast(const C &c, int *i, PipQuast_dp *father, int Bg, int U
 struct Ser { I *out; long cap, len; unsigned long long h; bool hashing; };
 inline void sput(Ser &s, I v)
 {
-  if (s.hashing) {
-    s.h ^= (unsigned long long)v;
-    s.h *= 0x9E3779B97F4A7C15ULL;
-    s.h ^= s.h >> 32;
-  }
+  if (s.hashing) s.h += pip_hash_word((unsigned long long)v, (unsigned long long)s.len);
   if (s.out && s.len < s.cap) s.out[s.len] = v;
   s.len++;
 }
@@ -311,6 +307,7 @@ void accumulate(PipBatchStats_dp &s, const PipBatchOut &out)
     s.elem_updates += ((unsigned long long)r.elem_updates_hi << 32) | r.elem_updates_lo;
     s.max_rows = std::max(s.max_rows, r.max_rows);
     s.max_cols = std::max(s.max_cols, r.max_cols);
+    if (r.rflags & PIP_RES_WRAPPED) s.wrapped++;
   }
   s.seconds_h2d += out.times.h2d; s.seconds_kernel += out.times.kernel; s.seconds_d2h += out.times.d2h;
   s.launches += out.times.launches; s.rounds += out.times.rounds;
@@ -322,6 +319,7 @@ void merge_stats(PipBatchStats_dp &s, const PipBatchStats_dp &o)
 {
   s.cells += o.cells; s.pivots += o.pivots; s.cuts += o.cuts; s.subsolves += o.subsolves; s.splits += o.splits;
   s.elem_updates += o.elem_updates;
+  s.wrapped += o.wrapped;
   s.max_rows = std::max(s.max_rows, o.max_rows); s.max_cols = std::max(s.max_cols, o.max_cols);
   s.seconds_h2d += o.seconds_h2d; s.seconds_kernel += o.seconds_kernel; s.seconds_d2h += o.seconds_d2h;
   s.launches += o.launches; s.rounds += o.rounds; s.device_ms += o.device_ms;
@@ -329,8 +327,12 @@ void merge_stats(PipBatchStats_dp &s, const PipBatchStats_dp &o)
   for (int k = 0; k < 16; k++) s.phase_cycles[k] += o.phase_cycles[k];
 }
 
+thread_local std::vector<unsigned> t_last_flags;     /* pip_last_batch_flags_dp */
+
 void account(const PipBatchOut &out, double host_seconds)
 {
+  t_last_flags.resize(out.res.size());
+  for (size_t i = 0; i < out.res.size(); i++) t_last_flags[i] = (out.res[i].rflags & PIP_RES_WRAPPED) ? PIP_FLAG_WRAPPED : 0u;
   PipBatchStats_dp s;
   memset(&s, 0, sizeof s);
   accumulate(s, out);
@@ -610,6 +612,12 @@ long pip_quast_serialize_dp(const PipQuast_dp *q, long long *out, long cap)
 
 int pip_set_device_dp(int device) { return PipEngine::get().set_device(device); }
 const char *pip_b200_version(void) { return "piplib-b200 0.1 (sm_100a)"; }
+long long pip_last_batch_flags_dp(unsigned *flags, long long cap)
+{
+  const long long n = (long long)t_last_flags.size();
+  for (long long i = 0; i < n && i < cap && flags; i++) flags[i] = t_last_flags[i];
+  return n;
+}
 void pip_last_batch_stats_dp(PipBatchStats_dp *out)
 {
   if (!out) return;
@@ -1397,7 +1405,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
             }
             PipBatchStats_dp &ls = lane_stats[w];
             ls.pivots += D.stats[0]; ls.cuts += D.stats[1]; ls.subsolves += D.stats[2]; ls.splits += D.stats[3];
-            ls.elem_updates += D.stats[4]; ls.cells += D.stats[5];
+            ls.elem_updates += D.stats[4]; ls.cells += D.stats[5]; ls.wrapped += D.stats[8];
             ls.max_rows = std::max(ls.max_rows, (unsigned)D.stats[6]); ls.max_cols = std::max(ls.max_cols, (unsigned)D.stats[7]);
           } else emit_chunk(A, C, status, hashes, ser, ser_cap, ser_off, ser_len, &cursor, nthreads);
           tstage[w * 4 + 2] += te - td; tstage[w * 4 + 3] += wall() - te;
@@ -1516,6 +1524,7 @@ int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
       const PipDeviceOut &D = b->C.out.dev;
       st.pivots = D.stats[0]; st.cuts = D.stats[1]; st.subsolves = D.stats[2]; st.splits = D.stats[3];
       st.elem_updates = D.stats[4]; st.cells = D.stats[5]; st.max_rows = (unsigned)D.stats[6]; st.max_cols = (unsigned)D.stats[7];
+      st.wrapped = D.stats[8];
       accumulate(st, b->C.out);
       publish_stats(st);
     } else account(b->C.out, 0);

@@ -180,7 +180,7 @@ pip_serialize_warp_kernel(PipResult *res, const int *order, const PipCell *cells
   pip_i64 *tile = (pip_i64 *)pip_smem + (size_t)wid * PIP_WS_WORDS_PER_WARP;
   pip_i64 *stage = tile + PIP_WS_TILE;
   const bool stream = so.ctl != nullptr;
-  unsigned long long acc[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long acc[7] = {0, 0, 0, 0, 0, 0, 0};
   unsigned mrows = 0, mcols = 0, finals = 0;
   for (int q = blockIdx.x * PIP_WS_WARPS + wid; q < nprob; q += gridDim.x * PIP_WS_WARPS) {
     const int p = order ? order[q] : q;
@@ -188,7 +188,7 @@ pip_serialize_warp_kernel(PipResult *res, const int *order, const PipCell *cells
     const bool narrow = (r.rflags & PIP_RES_SER32) != 0 && !(stream && so.words64);
     PipWarpSer s;
     s.tile = tile; s.cap = (long long)r.ser_words; s.len = 0; s.fill = 0;
-    s.h = PIP_HASH_INIT; s.narrow_out = narrow ? 1 : 0; s.wide = 0;
+    s.h = 0; s.narrow_out = narrow ? 1 : 0; s.wide = 0;
     long long base = 0;
     const bool has_words = r.status == PIP_ST_OK || r.status == PIP_ST_VOID;
     if (stream) {
@@ -215,11 +215,12 @@ pip_serialize_warp_kernel(PipResult *res, const int *order, const PipCell *cells
       pip_wser_cells(s, c, r.ncells, d.bg, d.urs, d.flags);
     }
     pip_wser_flush(s);
+    const pip_u64 hsum = pip_wser_hash(s);
     /* a stream sized by the solver (PIP_RES_SIZED) must come out exactly that long and, when it was
      * promised narrow, fit 32-bit words: anything else is a bug, never a silent truncation */
     const bool bad = (r.rflags & PIP_RES_SIZED) && has_words && (s.len != (long long)r.ser_words || (narrow && s.wide));
     if (lane == 0) {
-      const pip_u64 h = has_words ? s.h : 0ull;
+      const pip_u64 h = has_words ? hsum : 0ull;
       if (stream) {
         so.status[p] = bad ? PIP_ST_FAULT + 1 : r.status;
         so.hash[p] = h;
@@ -236,6 +237,7 @@ pip_serialize_warp_kernel(PipResult *res, const int *order, const PipCell *cells
       acc[0] += r.pivots; acc[1] += r.cuts; acc[2] += r.subsolves; acc[3] += r.splits;
       acc[4] += ((unsigned long long)r.elem_updates_hi << 32) | r.elem_updates_lo;
       acc[5] += (unsigned long long)r.ncells;
+      acc[6] += (r.rflags & PIP_RES_WRAPPED) ? 1ull : 0ull;
       mrows = r.max_rows > mrows ? r.max_rows : mrows;
       mcols = r.max_cols > mcols ? r.max_cols : mcols;
     }
@@ -246,6 +248,7 @@ pip_serialize_warp_kernel(PipResult *res, const int *order, const PipCell *cells
     for (int k = 0; k < 6; k++) atomicAdd(so.stats + k, acc[k]);
     atomicMax(so.stats + 6, (unsigned long long)mrows);
     atomicMax(so.stats + 7, (unsigned long long)mcols);
+    if (acc[6]) atomicAdd(so.stats + 8, acc[6]);
   }
 }
 
@@ -272,6 +275,77 @@ extern "C" cudaError_t pip_launch_serialize(PipResult *res, const int *order, co
   }
   const int threads = 128;
   pip_serialize_kernel<<<(nprob + threads - 1) / threads, threads, 0, stream>>>(res, order, cells, parm, u, nprob);
+  return cudaGetLastError();
+}
+
+/* word mode (the solver wrote the serialised quast itself): what is left of the decode is a copy -- reserve the
+ * problem's span of the compact buffer, move the words (int32 from class S32, int64 otherwise; written as
+ * int32 or int64 as the caller asked), fill the per-problem arrays, sum the counters.  One warp per problem. */
+__global__ void __launch_bounds__(256)
+pip_gather_words_kernel(const PipResult *res, const int *order, const PipCell *cells, pip_i64 *out, int nprob,
+                        const PipStreamOut so)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  unsigned mrows = 0, mcols = 0, finals = 0;
+  for (int q = warp; q < nprob; q += nwarps) {
+    const int p = order ? order[q] : q;
+    const PipResult r = res[p];
+    const bool has_words = r.status == PIP_ST_OK || r.status == PIP_ST_VOID;
+    const long long nw = has_words ? (long long)r.ser_words : 0;
+    const bool narrow = (r.rflags & PIP_RES_SER32) != 0 && !so.words64;
+    const long long slots = narrow ? (nw + 1) / 2 : nw;
+    long long base = 0;
+    if (lane == 0 && slots) base = (long long)atomicAdd(so.ctl + PIP_SO_SLOTS, (unsigned long long)slots);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + slots > so.cap) {                       /* does not fit: the host grows the buffer and repeats the pass */
+      if (lane == 0) so.ctl[PIP_SO_OVERFLOW] = 1;
+    } else if (nw) {
+      const void *src = (const void *)(cells + r.cell_off);
+      pip_i64 *dst = out + base;
+      if (r.rflags & PIP_RES_SRC32) {
+        const int *s32 = (const int *)src;
+        if (narrow) for (long long k = lane; k < nw; k += 32) ((int *)dst)[k] = s32[k];
+        else for (long long k = lane; k < nw; k += 32) dst[k] = (pip_i64)s32[k];
+      } else {
+        const pip_i64 *s64 = (const pip_i64 *)src;
+        if (narrow) for (long long k = lane; k < nw; k += 32) ((int *)dst)[k] = (int)s64[k];
+        else for (long long k = lane; k < nw; k += 32) dst[k] = s64[k];
+      }
+    }
+    if (lane == 0) {
+      so.status[p] = r.status;
+      if (!has_words) so.hash[p] = 0ull;              /* (the solver wrote the hash of a finished stream) */
+      so.off[p] = base;
+      so.len[p] = nw | (narrow && nw ? PIP_LEN_NARROW : 0ll);
+    }
+    if (PIP_STATUS_IS_FINAL(r.status)) {
+      finals++;
+      acc[0] += r.pivots; acc[1] += r.cuts; acc[2] += r.subsolves; acc[3] += r.splits;
+      acc[4] += ((unsigned long long)r.elem_updates_hi << 32) | r.elem_updates_lo;
+      acc[5] += (unsigned long long)r.ncells;
+      acc[6] += (r.rflags & PIP_RES_WRAPPED) ? 1ull : 0ull;
+      mrows = r.max_rows > mrows ? r.max_rows : mrows;
+      mcols = r.max_cols > mcols ? r.max_cols : mcols;
+    }
+  }
+  if (lane == 0 && finals) {
+    atomicAdd(so.ctl + PIP_SO_FINALS, (unsigned long long)finals);
+    for (int k = 0; k < 6; k++) atomicAdd(so.stats + k, acc[k]);
+    atomicMax(so.stats + 6, (unsigned long long)mrows);
+    atomicMax(so.stats + 7, (unsigned long long)mcols);
+    if (acc[6]) atomicAdd(so.stats + 8, acc[6]);
+  }
+}
+
+extern "C" cudaError_t pip_launch_gather_words(const PipResult *res, const int *order, const PipCell *cells, pip_i64 *out,
+                                               int nprob, const PipStreamOut *so, cudaStream_t stream)
+{
+  int blocks = (nprob + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  pip_gather_words_kernel<<<blocks, 256, 0, stream>>>(res, order, cells, out, nprob, *so);
   return cudaGetLastError();
 }
 

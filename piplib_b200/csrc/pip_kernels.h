@@ -25,6 +25,9 @@ cudaError_t pip_launch_gather(PipResult *res, const int *order, const PipCell *c
 cudaError_t pip_launch_serialize(PipResult *res, const int *order, const PipCell *cells, const PipDecodeParm *parm,
                                  const PipDecodeParm *uparm, const long long *dst_off, pip_i64 *out, pip_u64 *hashes,
                                  int nprob, int pass, const PipStreamOut *so, cudaStream_t stream);
+/* word mode: copy the streams the solver wrote itself into the compact buffer (span reservation) */
+cudaError_t pip_launch_gather_words(const PipResult *res, const int *order, const PipCell *cells, pip_i64 *out,
+                                    int nprob, const PipStreamOut *so, cudaStream_t stream);
 cudaError_t pip_launch_init_results(PipResult *res, long long n, cudaStream_t stream);
 cudaError_t pip_launch_convert(const PipConvertArgs *A, int elem_log2, cudaStream_t stream);
 long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level, int vbytes);

@@ -28,6 +28,7 @@
 #define PIP_SOLVER_H
 
 #include "pip_arith.h"
+#include "pip_decode.h"
 #include "pip_types.h"
 #include "simt.h"
 
@@ -41,6 +42,7 @@ struct PipTab {          /* warp-uniform, lives in registers */
 
 struct PipStats {
   unsigned pivots, cuts, subsolves, splits, max_rows, max_cols;
+  unsigned wrapped;              /* int64 classes: some exact product left 64 bits (per lane, OR-ed) */
   unsigned long long elem_updates;
 #ifdef PIP_PROFILE
   long long lap;                 /* clock64 of the last phase boundary */
@@ -134,9 +136,24 @@ PIP_HD bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level
 template <class V> struct PipVal;
 template <> struct PipVal<pip_i64> {
   enum { bytes = 8, narrow = 0 };
-  PIP_HDM static pip_i64 mulsub(pip_i64 a, pip_i64 l, pip_i64 b, pip_i64 f, unsigned &)
-  { return (pip_i64)((pip_u64)a * (pip_u64)l - (pip_u64)b * (pip_u64)f); }
-  PIP_HDM static pip_i64 mul(pip_i64 a, pip_i64 b, unsigned &) { return (pip_i64)((pip_u64)a * (pip_u64)b); }
+  /* The value is the reference's: the low 64 bits of the products (source/traiter.c:483-485 wraps silently;
+   * its verdict comes later from the determinant check).  `wrapped` additionally records whether the exact
+   * 128-bit result left int64 -- the immediate "true overflow" flag of SURVEY.md 8 P3, reported per problem
+   * (PIP_RES_WRAPPED) next to the reference's own verdict, never instead of it. */
+  PIP_DM static pip_i64 mulsub(pip_i64 a, pip_i64 l, pip_i64 b, pip_i64 f, unsigned &wrapped)
+  {
+    const pip_u64 lo1 = (pip_u64)a * (pip_u64)l, lo2 = (pip_u64)b * (pip_u64)f;
+    const pip_u64 dlo = lo1 - lo2;
+    const pip_i64 dhi = pip_mulhi(a, l) - pip_mulhi(b, f) - (pip_i64)(lo1 < lo2);
+    wrapped |= (unsigned)(dhi != ((pip_i64)dlo >> 63));
+    return (pip_i64)dlo;
+  }
+  PIP_DM static pip_i64 mul(pip_i64 a, pip_i64 b, unsigned &wrapped)
+  {
+    const pip_i64 lo = (pip_i64)((pip_u64)a * (pip_u64)b);
+    wrapped |= (unsigned)(pip_mulhi(a, b) != (lo >> 63));
+    return lo;
+  }
   PIP_HDM static pip_i64 cross(pip_i64 p, pip_i64 a, pip_i64 b, pip_i64 f)
   { return (pip_i64)((pip_u64)p * (pip_u64)a - (pip_u64)b * (pip_u64)f); }
   PIP_HDM static pip_i64 store(pip_i64 v, unsigned &) { return v; }
@@ -956,12 +973,13 @@ PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st, PipTeam *t
   if (TEAM && tm != nullptr && nl >= PIP_TEAM_MIN_ROWS) {
     if (lane == 0) {
       tm->cmd = PIP_TEAM_UPDATE; tm->pivi = pivi; tm->pivj = pivj; tm->pivot = (pip_i64)pivot; tm->dpiv = (pip_i64)dpiv;
-      tm->T = T; tm->B = B; tm->fault = 0;
+      tm->T = T; tm->B = B; tm->fault = 0; tm->ovf = 0;
     }
     W::sync();
     pip_team_barrier(tm->nthreads);
     pip_update_rows(B, T, pivi, pivj, pivot, dpiv, lane, tm->nthreads, ovf, fault, lane == 0 ? &st : nullptr);
     if (fault) tm->fault = 1;
+    if (ovf) tm->ovf = 1;
 #ifdef PIP_PROFILE
     const long long w0_ = clock64();
 #endif
@@ -970,8 +988,10 @@ PIP_SDEV int pip_pivot(pip_i64 *B, PipTab &T, int pivi, PipStats &st, PipTeam *t
     if (lane == 0) st.cyc[PIP_PH_U_WAIT] += (unsigned long long)(clock64() - w0_);
 #endif
     fault = tm->fault != 0;
+    ovf |= tm->ovf;
   } else pip_update_rows(B, T, pivi, pivj, pivot, dpiv, lane, 32, ovf, fault);
   if (PipVal<V>::narrow && W::any(ovf != 0)) return PIP_ST_WIDEN;
+  if (!PipVal<V>::narrow) st.wrapped |= ovf;
   if (W::any(fault)) return PIP_ST_FAULT;
   W::sync();
   PIP_LAP(st, PIP_PH_UPDATE);
@@ -1027,6 +1047,72 @@ PIP_SDEVNI bool pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int
     wide = pip_put(out, at + c, PIP_C_VAL, pip_entry(B, T, f, d, j), d) || wide;
   }
   return wide;
+}
+
+/* ---- word mode: the solver writes the SERIALISED quast itself (the word stream of pip_decode.h) instead
+ * of solution cells for a decode kernel to parse.  Only for problems whose decode needs no column surgery
+ * (PIP_F_SIMPLE_SER), i.e. every bulk workload: the cells were written (24 B each), read back and re-parsed
+ * by a second kernel that cost a fifth of the solve.  The grammar is pre-order like the cells; the only
+ * forward reference is the new-parameter count that opens a node, kept as a reserved slot (node_at) and
+ * patched when the node's kind is known.  Every lane hashes the words it writes (pip_hash_word is a sum). */
+struct PipWordOut {
+  V *w;                    /* the warp's window, as words of the stored type */
+  unsigned pos;            /* words emitted so far (warp-uniform) */
+  int node_at;             /* slot of the open node's new-parameter count, -1 = no node open */
+  unsigned nnew;
+  pip_u64 h;               /* this lane's share of the hash */
+  bool wide;               /* some word left int32 (int64 classes) */
+};
+PIP_SDEV void pip_wout(PipWordOut &o, unsigned idx, pip_i64 v)
+{
+  o.w[idx] = (V)v;
+  o.h += pip_hash_word((pip_u64)v, (pip_u64)idx);
+  if (!PipVal<V>::narrow) o.wide = o.wide || (v != (pip_i64)(int)v);
+}
+PIP_SDEV void pip_wnode_open(PipWordOut &o)
+{
+  if (o.node_at < 0) { o.node_at = (int)o.pos; o.pos++; o.nnew = 0; }
+}
+/* the node's kind is about to be written: patch the new-parameter count (lane 0) */
+PIP_SDEV void pip_wnode_kind(PipWordOut &o, int kind)
+{
+  pip_wnode_open(o);
+  if (W::lane() == 0) { pip_wout(o, (unsigned)o.node_at, (pip_i64)o.nnew); pip_wout(o, o.pos, kind); }
+  o.pos++;
+  o.node_at = -1;
+}
+/* solution_xx as words: `1 nvar { 1 VEC }* 0`, VEC = nparm+1 { num den }*, every value reduced by its gcd
+ * with the row denominator exactly as sol_vector_edit_xx does (source/sol.c:435-512) */
+PIP_SDEVNI void pip_emit_solution_words(pip_i64 *B, const PipTab &T, PipWordOut &o)
+{
+  const int lane = W::lane();
+  const int np1 = T.nparm + 1, per = 2 + 2 * np1;
+  pip_wnode_kind(o, 1);
+  const unsigned base = o.pos;
+  if (T.nvar == 0) {
+    if (lane == 0) { pip_wout(o, base, 1); pip_wout(o, base + 1, 0); pip_wout(o, base + 2, 0); }
+    o.pos += 3;
+    return;
+  }
+  const int *fl = pip_fl(B, T);
+  const V *den = pip_den(B, T);
+  if (lane == 0) { pip_wout(o, base, T.nvar); pip_wout(o, base + 1 + (unsigned)T.nvar * per, 0); }
+  #pragma unroll 1
+  for (int i = lane; i < T.nvar; i += 32) { pip_wout(o, base + 1 + i * per, 1); pip_wout(o, base + 2 + i * per, np1); }
+  const int pairs = T.nvar * np1;
+  #pragma unroll 1
+  for (int q = lane; q < pairs; q += 32) {
+    const int i = q / np1, r = q - i * np1;
+    const int j = (r == np1 - 1) ? T.nvar : T.nvar + 1 + r;
+    const pip_i64 D = (pip_i64)den[i];
+    const pip_i64 N = (pip_i64)pip_entry(B, T, fl[i], den[i], j);
+    const pip_i64 d = (D == 1) ? 1 : pip_gcd(N, D);
+    const pip_i64 num = d == 1 ? N : (d ? pip_div(N, d) : 0);
+    const pip_i64 dd = (d == D) ? 1 : (d ? pip_div(D, d) : 0);
+    pip_wout(o, base + 3 + i * per + 2 * r, num);
+    pip_wout(o, base + 4 + i * per + 2 * r, dd);
+  }
+  o.pos += 2 + (unsigned)T.nvar * per;
 }
 
 /* has_cut_xx, source/integrer.c:230-254 (serial, one lane) */
@@ -1087,7 +1173,9 @@ PIP_SDEV int pip_find_parm(const V *ctx, int cstride, int nr, int nparm, V *cut)
  * emulator tests run both and compare cells, statuses and pivot counts.  Returns 1 feasible, 0 infeasible,
  * -1 when the solve does not fit the register form (more than 32 positions, more than PIP_SUBREG_NC
  * columns: the caller falls back to the general path, nothing has been counted), or a PIP_ST_* status. */
-enum { PIP_SUBREG_NC = 8 };
+#ifndef PIP_SUBREG_NC
+#define PIP_SUBREG_NC 8
+#endif
 
 PIP_SDEV V pip_bcast(V v, int src)
 {
@@ -1382,10 +1470,12 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
                            int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st, PipTeam *tm = nullptr,
-                           unsigned *nwords_out = nullptr)
+                           unsigned *nwords_out = nullptr, bool wordmode = false, pip_u64 *hash_out = nullptr)
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
+  PipWordOut wo;
+  wo.w = (V *)out; wo.pos = 0; wo.node_at = -1; wo.nnew = 0; wo.h = 0; wo.wide = false;
   PipLayout L;
   int level_try = slack_level;
   while (!pip_layout(P.nvar, P.nparm, P.ni, P.nc, P.flags, level_try, words, (int)sizeof(V), L)) {
@@ -1456,7 +1546,7 @@ BUILD_SUB:
     PipTab S = L.s;
     const int np = M.nparm;
     const int extra = ret_site == 0 ? 0 : 1;
-#ifndef PIP_NO_SUBREG
+#ifdef PIP_USE_SUBREG
     {
       /* the register-resident form first (pip_subsolve_regs); -1 = does not fit, take the general path */
       const V *trow = extra ? pip_row(B, M, PIP_LINK(pip_fl(B, M)[ci])) : (const V *)nullptr;
@@ -1603,9 +1693,16 @@ AFTER_COMPA:
       if (j < np) v = pip_div(row[T.nvar + 1 + j], g);
       else v = integer ? pip_floor_q(row[T.nvar], g) : pip_div(row[T.nvar], g);
       crow[j] = v;
-      wide = pip_put(out, ncell + 2 + j, PIP_C_VAL, v, 1) || wide;
+      if (!wordmode) wide = pip_put(out, ncell + 2 + j, PIP_C_VAL, v, 1) || wide;
     }
-    if (lane == 0) {
+    if (wordmode) {
+      /* `nnew 2 VEC(condition)`: the vector is np + 1 values over the denominator 1 */
+      pip_wnode_kind(wo, 2);
+      if (lane == 0) pip_wout(wo, wo.pos, np + 1);
+      #pragma unroll 1
+      for (int j = lane; j <= np; j += 32) { pip_wout(wo, wo.pos + 1 + 2 * j, (pip_i64)crow[j]); pip_wout(wo, wo.pos + 2 + 2 * j, 1); }
+      wo.pos += 1 + 2 * (np + 1);
+    } else if (lane == 0) {
       pip_put(out, ncell, PIP_C_IF, 0, 0);
       pip_put(out, ncell + 1, PIP_C_FORM, np + 1, 0);
     }
@@ -1656,7 +1753,8 @@ NONNEG:
   if (level == 0 && !integer) {
     const int total = 1 + T.nvar * (T.nparm + 2);
     if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
-    wide = pip_emit_solution(B, T, out, ncell) || wide;
+    if (wordmode) pip_emit_solution_words(B, T, wo);
+    else wide = pip_emit_solution(B, T, out, ncell) || wide;
     ncell += total;
     nwords += T.nvar ? 4 + T.nvar * (2 * T.nparm + 4) : 5;
     if (dual) {
@@ -1710,7 +1808,21 @@ NONNEG:
           if (nc + 2 > L.crcap || np + 2 > cstride || ncol + 1 > T.stride) { status = PIP_ST_CAPACITY; goto DONE; }
           if (ncell + np + 5 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
           const V *c = cut + nvar;
+          if (wordmode) {
+            /* `rank deno VEC`: the new parameter's rank, its divisor, the np + 1 values of the form over 1 */
+            pip_wnode_open(wo);
+            if (lane == 0) {
+              const unsigned b0 = wo.pos;
+              pip_wout(wo, b0, np); pip_wout(wo, b0 + 1, (pip_i64)c[1 + np]); pip_wout(wo, b0 + 2, np + 1);
+              #pragma unroll 1
+              for (int j = 0; j < np; j++) { pip_wout(wo, b0 + 3 + 2 * j, -(pip_i64)c[1 + j]); pip_wout(wo, b0 + 4 + 2 * j, 1); }
+              pip_wout(wo, b0 + 3 + 2 * np, -(pip_i64)c[0]); pip_wout(wo, b0 + 4 + 2 * np, 1);
+            }
+            wo.pos += 2 * np + 5;
+            wo.nnew++;
+          }
           if (lane == 0) {
+            if (!wordmode) {
             pip_put(out, ncell, PIP_C_NEW, np, 0);
             pip_put(out, ncell + 1, PIP_C_DIV, 0, 0);
             pip_put(out, ncell + 2, PIP_C_FORM, np + 1, 0);
@@ -1718,6 +1830,7 @@ NONNEG:
             for (int j = 0; j < np; j++) wide = pip_put(out, ncell + 3 + j, PIP_C_VAL, -c[1 + j], 1) || wide;
             wide = pip_put(out, ncell + 3 + np, PIP_C_VAL, -c[0], 1) || wide;
             wide = pip_put(out, ncell + 4 + np, PIP_C_VAL, c[1 + np], 1) || wide;
+            }
             #pragma unroll 1
             for (int k = 0; k < nc; k++) { V *r = ctx + k * cstride; r[np + 1] = r[np]; r[np] = 0; }
             V *r0 = ctx + nc * cstride, *r1 = r0 + cstride;
@@ -1765,13 +1878,15 @@ NONNEG:
     if (verdict == 0) {
       const int total = 1 + T.nvar * (T.nparm + 2);
       if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
-      wide = pip_emit_solution(B, T, out, ncell) || wide;
+      if (wordmode) pip_emit_solution_words(B, T, wo);
+      else wide = pip_emit_solution(B, T, out, ncell) || wide;
       ncell += total;
       nwords += T.nvar ? 4 + T.nvar * (2 * T.nparm + 4) : 5;
       PIP_LAP(st, PIP_PH_EMIT);
     } else {
       if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
-      if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
+      if (wordmode) pip_wnode_kind(wo, 0);
+      else if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
       ncell += 1;
       nwords += 2;
     }
@@ -1786,7 +1901,8 @@ PIVOT:
     if (rc > 0) { status = rc; goto DONE; }
     if (level) { feasible = false; goto SUB_DONE; }
     if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
-    if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
+    if (wordmode) pip_wnode_kind(wo, 0);
+    else if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
     ncell += 1;
     nwords += 2;
   }
@@ -1838,7 +1954,18 @@ DONE:
   status_out = status;
   ncell_out = (status == PIP_ST_OK) ? ncell : 0;
   if (nwords_out) *nwords_out = status == PIP_ST_OK ? nwords : status == PIP_ST_VOID ? 1u : 0u;
-  rflags_out = W::any(wide) ? PIP_RES_WIDE : 0u;
+  if (wordmode) {
+    /* the stream is complete: its hash = start value + the lanes' shares; an empty context is the one word -1 */
+    if (status == PIP_ST_VOID) { wo.h = 0; wo.wide = false; if (lane == 0) pip_wout(wo, 0, -1); }
+    pip_u64 h = wo.h;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += (pip_u64)W::shfl_xor64((long long)h, o);
+    if (hash_out) *hash_out = (status == PIP_ST_OK || status == PIP_ST_VOID) ? h + PIP_HASH_INIT : 0ull;
+    /* the solver's own count (nwords) and the words written must agree: a mismatch is a bug, not a verdict */
+    if (status == PIP_ST_OK && wo.pos != nwords) status_out = PIP_ST_FAULT + 2;
+    wide = !PipVal<V>::narrow && wo.wide;
+  }
+  rflags_out = (W::any(wide) ? PIP_RES_WIDE : 0u) | ((!PipVal<V>::narrow && W::any(st.wrapped != 0)) ? PIP_RES_WRAPPED : 0u);
 }
 
 };

@@ -95,6 +95,10 @@ typedef struct {
 #define PIP_RES_WIDE 1u
 #define PIP_RES_SER32 2u          /* device-decode mode: the quast words were shipped as int32 */
 #define PIP_RES_SIZED 4u          /* ser_words was computed by the solver (PIP_F_SIMPLE_SER) */
+#define PIP_RES_WORDS 16u         /* word mode: the window holds the serialised quast words, not cells */
+#define PIP_RES_SRC32 32u         /* word mode: those words are int32 (class S32), else int64 */
+#define PIP_RES_WRAPPED 8u        /* int64 classes: an exact 128-bit product of a pivot update left 64 bits (the
+                                     reference wraps silently there; its own verdict is reported unchanged) */
 #define PIP_CELL_FITS(p1, p2) ((pip_u64)(p2) < 65536ull && (p1) >= -(1ll << 43) && (p1) < (1ll << 43))
 #define PIP_CELL_PACK(kind, p1, p2) ((pip_u64)(unsigned)(kind) | ((pip_u64)(p2) << 4) | ((pip_u64)(p1) << 20))
 #define PIP_CELL_KIND(w) ((int)((w) & 15ull))
@@ -114,10 +118,11 @@ typedef struct {
   pip_u64 *hash;
   long long *off;                /* slot offset of the problem's span in the compact buffer */
   long long *len;                /* words; bit 62 set when they were written as int32 */
-  unsigned long long *stats;     /* [8]: pivots, cuts, subsolves, splits, elem_updates, cells, max_rows, max_cols
-                                    (final statuses only) */
+  unsigned long long *stats;     /* [PIP_SO_NSTAT]: pivots, cuts, subsolves, splits, elem_updates, cells, max_rows,
+                                    max_cols, problems flagged PIP_RES_WRAPPED (final statuses only) */
 } PipStreamOut;
 #define PIP_LEN_NARROW (1ll << 62)
+#define PIP_SO_NSTAT 9
 enum { PIP_SO_SLOTS = 0, PIP_SO_FINALS = 1, PIP_SO_OVERFLOW = 2, PIP_SO_NCTL = 4 };
 #define PIP_STATUS_IS_FINAL(st) ((st) != PIP_ST_PENDING && (st) != PIP_ST_CAPACITY && (st) != PIP_ST_WIDEN)
 
@@ -139,6 +144,8 @@ typedef struct {
   int sol_size, maxcol, maxparm;
   int slack_level;
   unsigned long long *prof;      /* [PIP_NPHASE] cycle sums (profile build only) or NULL */
+  int emit_words;                /* word mode: PIP_F_SIMPLE_SER problems write their serialised quast (pip_solver.h) */
+  pip_u64 *hash_out;             /* word mode: hash of each problem's stream, indexed like res */
 } PipLaunch;
 
 #endif

@@ -25,14 +25,19 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
     PipStats st;
     st.pivots = st.cuts = st.subsolves = st.splits = st.max_rows = st.max_cols = 0;
     st.elem_updates = 0;
+    st.wrapped = 0;
 #ifdef PIP_PROFILE
     for (int k = 0; k < PIP_NPHASE; k++) st.cyc[k] = 0;
     st.lap = clock64();
 #endif
     int status = PIP_ST_OK, ncell = 0;
     unsigned rflags = 0, nwords = 0;
+    /* word mode (PipLaunch::emit_words): the solver writes the serialised quast itself into the window */
+    const bool wordmode = L.emit_words && (P.flags & PIP_F_SIMPLE_SER);
+    pip_u64 hash = 0;
     PipSolver<V, TEAM>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
-                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm, &nwords);
+                  L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm, &nwords,
+                  wordmode, &hash);
     if (lane == 0) {
       PipResult r;
       r.status = status; r.ncells = ncell;
@@ -44,6 +49,12 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
         r.ser_words = nwords;
         rflags |= PIP_RES_SIZED | (PipVal<V>::narrow ? PIP_RES_SER32 : 0u);
       }
+      if (wordmode) {
+        /* in word mode PIP_RES_WIDE means "some word left int32": the complement is PIP_RES_SER32 */
+        rflags = (rflags & ~(PIP_RES_WIDE | PIP_RES_SER32)) | PIP_RES_SIZED | PIP_RES_WORDS |
+                 ((rflags & PIP_RES_WIDE) ? 0u : PIP_RES_SER32) | (PipVal<V>::narrow ? PIP_RES_SRC32 : 0u);
+        if (L.hash_out) L.hash_out[p] = hash;
+      }
       r.elem_updates_lo = (unsigned)(st.elem_updates & 0xffffffffull);
       r.elem_updates_hi = (unsigned)(st.elem_updates >> 32);
       r.rflags = rflags;
@@ -52,7 +63,9 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
       if (L.prof) for (int k = 0; k < PIP_NPHASE; k++) atomicAdd(&L.prof[k], st.cyc[k]);
 #endif
     }
-    used += ncell;
+    /* window space consumed, in cells: the cells themselves, or the words written over them */
+    if (wordmode) used += ((pip_i64)((status == PIP_ST_OK || status == PIP_ST_VOID) ? nwords : 0u) * (pip_i64)sizeof(V) + (pip_i64)sizeof(PipCell) - 1) / (pip_i64)sizeof(PipCell);
+    else used += ncell;
     W::sync();
   }
 }
@@ -73,6 +86,7 @@ PIP_DEV void pip_team_helper(PipTeam *tm, int tid)
       PipSolver<V, true>::pip_update_rows(tm->B, tm->T, tm->pivi, tm->pivj, (V)tm->pivot, (V)tm->dpiv, tid, tm->nthreads,
                                           ovf, fault);
       if (fault) tm->fault = 1;
+      if (ovf) tm->ovf = 1;
     }
     pip_team_barrier(tm->nthreads);
   }

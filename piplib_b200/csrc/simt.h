@@ -17,6 +17,7 @@
 #define PIP_SDEVNI static __attribute__((noinline))
 #define PIP_HD static inline
 #define PIP_HDM inline
+#define PIP_DM inline
 #define PIP_HDNI static __attribute__((noinline))
 #define PIP_ASSUME_SHARED(p) ((void)0)
 
@@ -87,6 +88,7 @@ static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); 
 #define PIP_SDEVNI static __attribute__((noinline))
 #define PIP_HD static inline
 #define PIP_HDM inline
+#define PIP_DM inline
 #define PIP_HDNI static __attribute__((noinline, unused))
 
 #else  /* device */
@@ -97,6 +99,7 @@ static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); 
 #define PIP_SDEVNI static __device__ __noinline__
 #define PIP_HD __host__ __device__ __forceinline__
 #define PIP_HDM __host__ __device__ __forceinline__
+#define PIP_DM __device__ __forceinline__          /* device-only member function */
 #define PIP_HDNI static __host__ __device__ __noinline__
 #define PIP_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 

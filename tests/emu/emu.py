@@ -22,20 +22,36 @@ def build(defines=(), so=None):
 
 
 def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_level=2, order_mode=0,
-                        sol_size=0, maxcol=0, narrow=0, so=None):
+                        sol_size=0, maxcol=0, narrow=0, so=None, emit_words=False):
+    """emit_words: word mode -- the solver writes the serialised quast itself (problems flagged SIMPLE_SER);
+    the second element of every result is then the word list and a fourth one, the stream's hash, is added"""
     lib = C.CDLL(so or SO)
     probs, pool = pack_tableau_problems(cases)
+    if emit_words:
+        probs["flags"] |= 8                      # PIP_F_SIMPLE_SER
     n = len(probs)
     res = np.zeros(n, dtype=RESULT_DTYPE)
     cap = 4096 * (n + 1)
     cells = np.zeros(cap, dtype=CELL_DTYPE)
+    hashes = np.zeros(max(n, 1), dtype=np.uint64)
     lib.pipemu_solve_batch(probs.ctypes.data_as(C.c_void_p), n, pool.ctypes.data_as(C.c_void_p),
                            res.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p),
                            C.c_longlong(cap), work_words, C.c_longlong(stack_words), slack_level,
-                           order_mode, sol_size, maxcol, narrow)
+                           order_mode, sol_size, maxcol, narrow, 1 if emit_words else 0,
+                           hashes.ctypes.data_as(C.c_void_p))
     out = []
+    raw = cells.view(np.uint8)
     for i in range(n):
         r = res[i]
+        if emit_words:
+            nw = int(r["ser_words"]) if int(r["status"]) in (0, 1) else 0
+            at = int(r["cell_off"]) * CELL_DTYPE.itemsize
+            if narrow == 1:
+                w = raw[at:at + 4 * nw].view(np.int32).astype(np.int64)
+            else:
+                w = raw[at:at + 8 * nw].view(np.int64)
+            out.append((int(r["status"]), [int(x) for x in w], r, int(hashes[i])))
+            continue
         c = cells[r["cell_off"]:r["cell_off"] + r["ncells"]]
         out.append((int(r["status"]), [[int(x["kind"]), int(x["p1"]), int(x["p2"])] for x in c], r))
     return out

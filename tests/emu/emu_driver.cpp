@@ -23,7 +23,7 @@ static void warp_entry(void *a, int)
 extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i64 *pool, PipResult *res,
                                   PipCell *cells, long long cells_cap, int work_words,
                                   long long stack_words, int slack_level, int order_mode,
-                                  int sol_size, int maxcol, int narrow)
+                                  int sol_size, int maxcol, int narrow, int emit_words, unsigned long long *hash_out)
 {
   EmuArgs e;
   unsigned queue[2] = {0, 0};
@@ -37,6 +37,8 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
   e.L.maxcol = maxcol > 0 ? maxcol : PIP_MAXCOL;
   e.L.maxparm = PIP_MAXPARM;
   e.L.slack_level = slack_level;
+  e.L.emit_words = emit_words;
+  e.L.hash_out = hash_out;
   e.narrow = narrow;
   e.arena = (pip_i64 *)malloc(sizeof(pip_i64) * (size_t)work_words);
   memset(e.arena, 0x5a, sizeof(pip_i64) * (size_t)work_words);   // poison: nothing may rely on zeros
@@ -113,12 +115,13 @@ static void decode_entry(void *a, int)
 {
   EmuDecode *e = (EmuDecode *)a;
   PipWarpSer s;
-  s.tile = e->tile; s.out = e->out; s.cap = e->cap; s.len = 0; s.fill = 0; s.h = PIP_HASH_INIT;
+  s.tile = e->tile; s.out = e->out; s.cap = e->cap; s.len = 0; s.fill = 0; s.h = 0;
   s.narrow_out = e->narrow; s.wide = 0;
   PipRawCells c = {e->cells};
   const bool ok = pip_wser_cells(s, c, e->n, e->bg, e->urs, e->flags);
   pip_wser_flush(s);
-  if (W::lane() == 0) { e->len = s.len; e->h = s.h; e->wide = s.wide; e->ok = ok ? 1 : 0; }
+  const pip_u64 h = pip_wser_hash(s);
+  if (W::lane() == 0) { e->len = s.len; e->h = h; e->wide = s.wide; e->ok = ok ? 1 : 0; }
 }
 
 // which = 0: pip_ser_cells (one thread, the host/device reference decoder), 1: the warp decoder

@@ -3,6 +3,7 @@ fiber emulator in tests/emu (32 cooperative fibers = one warp), against the refe
 vectors.  This keeps the kernel logic under test in the no-GPU CI run; it is a debugging aid,
 not a product path (the shared library has no CPU solver).  Lane scheduling order is permuted
 to expose missing warp synchronisation."""
+import numpy as np
 import pytest
 
 from conftest import load_golden
@@ -183,19 +184,21 @@ def _dense_to_cases(dom, ctx, nq=1):
 @pytest.mark.parametrize("narrow", [0, 1])
 def test_register_resident_feasibility_solves_equal_the_general_path(port, narrow):
     """pip_subsolve_regs (the compa_test / context feasibility solves with the sub-tableau in registers)
-    against the same device source built with -DPIP_NO_SUBREG (every sub-solve through the arena): same
+    (built with -DPIP_USE_SUBREG; an experiment that lost on the GPU to instruction supply, profiles/README.md,
+    kept compiled out) against the default device source (every sub-solve through the arena): same
     status, same cells, and the same counters problem by problem -- pivots, cuts, sub-solves, element
     updates, largest tableau -- on the parametric fixtures, the random tableaus and the bench workloads;
     pivot totals against the oracle port"""
     import os
     from workloads import synth
-    so2 = emu.build(defines=("PIP_NO_SUBREG",), so=os.path.join(os.path.dirname(emu.SO), "libpipemu_nosubreg.so"))
+    so2 = emu.SO                      # the default build: every sub-solve through the arena
+    so1 = emu.build(defines=("PIP_USE_SUBREG",), so=os.path.join(os.path.dirname(emu.SO), "libpipemu_subreg.so"))
     cases = [c for c in CLI + RCLI if c["nparm"] > 0 and c["name"] not in HEAVY]
     for wl, n in (("loopnest16x24p3", 160), ("loopnest8x12p2", 300), ("sor1d", 200), ("cg1", 100), ("fimmel", 40)):
         dom, ctx = synth.generate(wl, n, seed=5)
         cases += _dense_to_cases(dom, ctx)
     assert len(cases) > 800
-    a = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=2, narrow=narrow)
+    a = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=2, narrow=narrow, so=so1)
     b = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=0, narrow=narrow, so=so2)
     bad, piv, subs = [], 0, 0
     keys = ("status", "ncells", "pivots", "cuts", "subsolves", "splits", "max_rows", "max_cols",
@@ -216,3 +219,33 @@ def test_register_resident_feasibility_solves_equal_the_general_path(port, narro
             port.traiter(c["nvar"], c["nparm"], c["ni"], c["nc"], c["bigparm"], c["nq"], c["tab"], c["ctx"], stats=stt)
             total += int(stt.pivots)
         assert total == piv
+
+
+@pytest.mark.parametrize("narrow", [0, 1, 2])
+def test_word_mode_equals_cells_then_decode(narrow):
+    """word mode (the solver writes the serialised quast itself) against the cell stream of the same
+    problem run through the reference decoder pip_ser_cells: the same words, the same hash, the same
+    counters -- fixtures, random tableaus and the bench workloads, int64 / int32 / global-memory builds"""
+    from workloads import synth
+    cases = [c for c in CLI + RCLI if c["name"] not in HEAVY]
+    for wl, n in (("loopnest16x24p3", 120), ("loopnest8x12p2", 200), ("sor1d", 150), ("fimmel", 30)):
+        dom, ctx = synth.generate(wl, n, seed=17)
+        cases += _dense_to_cases(dom, ctx)
+    a = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=2, narrow=narrow, emit_words=True)
+    b = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=0, narrow=narrow)
+    keys = ("status", "ncells", "pivots", "cuts", "subsolves", "splits", "ser_words")
+    bad, checked = [], 0
+    for k, ((st, words, r, h), (st2, cells, r2)) in enumerate(zip(a, b)):
+        if st != st2 or (st != 4003 and any(int(r[x]) != int(r2[x]) for x in keys if x != "ser_words")):
+            bad.append((k, st, st2))
+            continue
+        if st not in (0, 1):
+            continue
+        ok, ln, h2, wide, w2 = emu.decode(0, cells, -1, 0, 0) if st == 0 else (1, 1, None, 0, np.asarray([-1]))
+        if st == 0 and (words != [int(x) for x in w2] or h != h2 or len(words) != ln):
+            bad.append((k, "words", len(words), ln))
+        if st == 1 and words != [-1]:
+            bad.append((k, "void", words))
+        checked += 1
+    assert not bad, bad[:6]
+    assert checked > 600
