@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=int(os.environ.get("PIP_BENCH_BATCH", 1000000)))
     ap.add_argument("--workload", default="loopnest16x24p3")
+    ap.add_argument("--total", type=int, default=0,
+                    help="strong scaling (BASELINE config 5): this many problems in all, sharded over the ranks")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample")
@@ -186,6 +188,8 @@ def main():
     W = max(a.warmup, 0)
     K = max(a.steps, 1)
     B = a.batch
+    if a.total:
+        B = (a.total + world - 1) // world
     # shape of the workload from one generated problem (PolyLib rows: flag, unknowns, parameters, constant)
     d1, c1 = synth.generate(a.workload, 1, seed=a.seed)
     nparm = max(c1.shape[2] - 2, 0)
@@ -348,7 +352,7 @@ def main():
         uniq, counts = np.unique(status, return_counts=True)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if a.total else "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
             "pivots_per_sec": pivots_all * K / (dev_ms / 1e3),
             "elem_updates_per_sec": elem_all * K / (dev_ms / 1e3),

@@ -35,7 +35,7 @@ def _stale(lib=None):
     return os.path.getmtime(os.path.abspath(__file__)) > t
 
 
-def build(force=False, verbose=False, profile=False, variant=None, defines=()):
+def build(force=False, verbose=False, profile=False, variant=None, defines=(), nvcc_extra=()):
     """profile=True builds libpiplib_dp_prof.so with per-phase clock64 accounting compiled in;
     variant="x" + defines builds an experimental libpiplib_dp_x.so (tuning only)."""
     global LIB
@@ -53,7 +53,7 @@ def build(force=False, verbose=False, profile=False, variant=None, defines=()):
     for f in SOURCES_CU:
         o = os.path.join(LIBDIR, f + ".o")
         o = os.path.join(LIBDIR, f + (".%s" % profile if profile else "") + ".o")
-        cmd = [NVCC] + NVCC_FLAGS + extra + inc + ["-c", os.path.join(CSRC, f), "-o", o]
+        cmd = [NVCC] + NVCC_FLAGS + list(nvcc_extra) + extra + inc + ["-c", os.path.join(CSRC, f), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
@@ -92,11 +92,13 @@ def build_cli():
 
 
 if __name__ == "__main__":
-    var, defs = None, []
+    var, defs, nx = None, [], []
     for a in sys.argv[1:]:
         if a.startswith("--variant="):
             var = a.split("=", 1)[1]
+        if a.startswith("--nvcc="):
+            nx += a.split("=", 1)[1].split(",")
         if a.startswith("-D"):
             defs.append(a[2:])
     print(build(force="--force" in sys.argv, verbose=True, profile="--profile" in sys.argv, variant=var,
-                defines=defs))
+                defines=defs, nvcc_extra=nx))

@@ -100,8 +100,10 @@ PIP_HDNI pip_i64 pip_bezout(pip_i64 x, pip_i64 y, pip_i64 delta)
   return pip_mod((pip_i64)((pip_u64)c * (pip_u64)x), delta);
 }
 
-/* 32-bit overloads for the int32 instantiation of the solver (no 64-bit division subroutine) */
-PIP_HD int pip_gcd(int a, int b)
+/* 32-bit overloads for the int32 instantiation of the solver (no 64-bit division subroutine).  Out of line:
+ * a 32-bit '/' or '%' is ~20 instructions on the SM and these helpers are reached from a dozen places of a
+ * kernel whose executed code has to fit the 32 KB instruction cache (profiles/README.md) */
+PIP_HDNI int pip_gcd(int a, int b)
 {
   unsigned x = a < 0 ? 0u - (unsigned)a : (unsigned)a, y = b < 0 ? 0u - (unsigned)b : (unsigned)b;
 #ifndef PIP_GCD32_NOSWAP
@@ -110,8 +112,8 @@ PIP_HD int pip_gcd(int a, int b)
   while (y) { unsigned r = x % y; x = y; y = r; }
   return (int)x;
 }
-PIP_HD int pip_div(int a, int b) { return a / b; }
-PIP_HD int pip_mod(int a, int b)
+PIP_HDNI int pip_div(int a, int b) { return a / b; }
+PIP_HDNI int pip_mod(int a, int b)
 {
   int m = a % b;
   if (m < 0) m += (b < 0 ? -b : b);
@@ -121,12 +123,8 @@ PIP_HD int pip_floor_q(int a, int b) { return (a - pip_mod(a, b)) / b; }
 
 PIP_HD int pip_bitlen(pip_i64 x)
 {
-  pip_u64 u = pip_uabs(x);
-  int n = 0;
-  while (u >> 32) { u >>= 32; n += 32; }
-  unsigned w = (unsigned)u;
-  while (w) { w >>= 1; n++; }
-  return n ? n : 1;
+  const pip_u64 u = pip_uabs(x);
+  return u ? 64 - pip_clzll(u) : 1;
 }
 
 /* multiplicative inverse of an odd d modulo 2^64 (Newton: each step doubles the valid bits) */

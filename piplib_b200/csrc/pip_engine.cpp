@@ -400,6 +400,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       /* geometry of this round */
       ClassSpec cs;
       int ctas;
+      bool team_smem = false;
       if (k < 0) {
         cs.level = (k == -2 && s32_wide) ? PIP_LEVEL_S_WIDE : 2; cs.shared = (k == -2) ? 2 : 1;
         cs.words = std::max<long long>(k == -2 ? s32_words : s_words, 64);
@@ -418,6 +419,28 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         cs = G_LADDER[k];
         if (getenv("PIPLIB_B200_NO_TEAM")) cs.team = 0;
         int need_warps = std::min(cs.warps, m);
+        /* class M in shared memory: when the working set of every problem of the round at this class's
+         * slack fits the SM (e.g. vivien32-shaped cut chains: 22 + 256 rows x 23 words = 56 KB), the CTA's
+         * arena is dynamic shared memory instead of global memory */
+        if (cs.team && getenv("PIPLIB_B200_NO_TEAM_SMEM") == nullptr) {
+          const PipProblem *hp = host_prob();
+          long long need = 0;
+          for (int q = 0; q < m; q++) {
+            const PipProblem &P = hp[order[q]];
+            need = std::max(need, pip_layout_words(P.nvar, P.nparm, P.ni, P.nc, P.flags, cs.level, 8));
+          }
+          need = (need + 1) & ~1ll;
+          const size_t bytes = (size_t)need * sizeof(pip_i64);
+          if (bytes + 2048 <= E.smem_optin) {
+            int per_sm = 0;
+            CK(pip_solve_occupancy(4, cs.team, bytes, &per_sm));
+            if (per_sm >= 1) {
+              team_smem = true;
+              cs.words = need;
+              need_warps = std::min(m, E.sm_count * per_sm);
+            }
+          }
+        }
         if (cs.team) { ctas = need_warps; cs.warps = ctas; cs.warps_per_cta = cs.team; }
         else {
           ctas = (need_warps + cs.warps_per_cta - 1) / cs.warps_per_cta;
@@ -430,7 +453,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       if (attempt > 0) per_warp = std::max<long long>(per_warp, 4ll * in.sol_size);
       E.d_cells.reserve((size_t)per_warp * cs.warps * sizeof(PipCell));
       E.d_stack.reserve((size_t)cs.stack_words * cs.warps * sizeof(pip_i64));
-      if (!cs.shared) E.d_gwork.reserve((size_t)cs.words * cs.warps * sizeof(pip_i64));
+      if (!cs.shared && !team_smem) E.d_gwork.reserve((size_t)cs.words * cs.warps * sizeof(pip_i64));
       if (!identity) {
         E.d_order.reserve((size_t)m * sizeof(int));
         CK(cudaMemcpyAsync(E.d_order.p, order.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -445,13 +468,16 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       L.res = (PipResult *)E.d_res.p;
       L.cells = (PipCell *)E.d_cells.p; L.cells_per_warp = per_warp;
       L.stack = (pip_i64 *)E.d_stack.p; L.stack_words_per_warp = cs.stack_words;
-      L.gwork = cs.shared ? nullptr : (pip_i64 *)E.d_gwork.p;
+      L.gwork = (cs.shared || team_smem) ? nullptr : (pip_i64 *)E.d_gwork.p;
       L.work_words = (int)cs.words;
       L.queue = (unsigned *)E.d_queue.p;
       L.sol_size = in.sol_size; L.maxcol = in.maxcol; L.maxparm = PIP_MAXPARM;
       L.slack_level = cs.level;
       L.prof = (unsigned long long *)E.d_prof.p;
-      L.hash_out = stream_out ? so.hash : nullptr;
+      /* one shape for the whole batch: carve the arena here, once, instead of once per problem on the device */
+      if (in.uniform && getenv("PIPLIB_B200_DEVICE_LAYOUT") == nullptr)
+        L.have_layout = pip_layout_compute(in.uniform->nvar, in.uniform->nparm, in.uniform->ni, in.uniform->nc,
+                                           in.uniform->flags, cs.level, (int)cs.words, cs.shared == 2 ? 4 : 8, &L.layout);
       double tk = now_s();
       /* PIPLIB_B200_LARGE_FROM=<class index> moves the hand-over (tests), a negative value disables it */
       const char *lf = getenv("PIPLIB_B200_LARGE_FROM");
@@ -466,7 +492,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         run_large_round(in, host_prob(), d_pool, elem_log2, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
         out.times.launches += m;
       } else {
-        CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? 3 : cs.shared, ctas, cs.warps_per_cta, s));
+        CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? (team_smem ? 4 : 3) : cs.shared, ctas, cs.warps_per_cta, s));
         out.times.launches++;
       }
       /* this round's output: packed cells, or (device-decode mode) serialised quasts */
@@ -596,8 +622,9 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         }
       }
       if (getenv("PIPLIB_B200_TIMING"))
-        fprintf(stderr, "[piplib-b200] round %d: class %d attempt %d, %d problems on %d warps (%d words/warp): %.3f s, %d not final (%d pending)%s\n",
-                round - 1, k, attempt, m, cs.warps, (int)cs.words, t_round, escalated + pending, pending, use_large ? " [whole-grid kernel]" : "");
+        fprintf(stderr, "[piplib-b200] round %d: class %d attempt %d, %d problems on %d warps (%d words/warp): %.3f s, %d not final (%d pending)%s%s\n",
+                round - 1, k, attempt, m, cs.warps, (int)cs.words, t_round, escalated + pending, pending, use_large ? " [whole-grid kernel]" : "",
+                team_smem ? " [team arena in shared memory]" : "");
       if (pending == 0) break;
     }
   }

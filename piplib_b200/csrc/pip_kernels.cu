@@ -36,7 +36,7 @@ static cudaError_t pip_raise_dynamic_smem(K kernel, size_t bytes, size_t &high_w
   if (e == cudaSuccess) high_water = bytes;
   return e;
 }
-static size_t g_smem_s32 = 0, g_smem_s64 = 0, g_smem_ws = 0;
+static size_t g_smem_s32 = 0, g_smem_s64 = 0, g_smem_ws = 0, g_smem_team = 0;
 
 template <bool SH, class V>
 __global__ void __launch_bounds__(PIP_CTA_THREADS, PIP_MIN_CTAS)
@@ -60,8 +60,12 @@ pip_team_kernel(const PipLaunch L)
   const int tid = threadIdx.x;
   if (tid == 0) { team.nthreads = blockDim.x; team.cmd = PIP_TEAM_UPDATE; team.fault = 0; team.ovf = 0; }
   __syncthreads();
+  /* the problem's arena: global memory, or -- when the class's working set fits (pip_engine.cpp) -- the
+   * CTA's dynamic shared memory: the tall tableaus of cut chains (vivien32: 303 rows x 23 words = 56 KB)
+   * then never leave the SM */
+  pip_i64 *arena = L.gwork ? L.gwork + (size_t)blockIdx.x * L.work_words : (pip_i64 *)pip_smem;
   if (tid < 32) {
-    pip_warp_main<pip_i64, true>(L, blockIdx.x, L.gwork + (size_t)blockIdx.x * L.work_words, &team);
+    pip_warp_main<pip_i64, true>(L, blockIdx.x, arena, &team);
     if (tid == 0) team.cmd = PIP_TEAM_EXIT;
     __syncwarp();
     pip_team_barrier(team.nthreads);
@@ -69,7 +73,8 @@ pip_team_kernel(const PipLaunch L)
 }
 
 /* shared_class: 0 = global-memory arena (int64), 1 = shared arena int64, 2 = shared arena int32,
- * 3 = team (class M): `warps_per_cta` warps work on one problem, `ctas` problems in flight */
+ * 3 = team (class M): `warps_per_cta` warps work on one problem, `ctas` problems in flight; 4 = team with the
+ * arena in shared memory (L->gwork == NULL, work_words * 8 bytes of dynamic shared memory per CTA) */
 extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, int ctas, int warps_per_cta,
                                         cudaStream_t stream)
 {
@@ -85,6 +90,11 @@ extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, in
       if (e != cudaSuccess) return e;
       pip_solve_kernel<true, pip_i64><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
     }
+  } else if (shared_class == 4) {
+    const size_t smem = (size_t)L->work_words * sizeof(pip_i64);
+    cudaError_t e = pip_raise_dynamic_smem(pip_team_kernel, smem, g_smem_team);
+    if (e != cudaSuccess) return e;
+    pip_team_kernel<<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
   } else if (shared_class == 3) {
     pip_team_kernel<<<ctas, warps_per_cta * 32, 0, stream>>>(*L);
   } else {
@@ -95,6 +105,11 @@ extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, in
 
 extern "C" cudaError_t pip_solve_occupancy(int shared_class, int warps_per_cta, size_t smem_bytes, int *ctas_per_sm)
 {
+  if (shared_class == 4) {
+    cudaError_t e = pip_raise_dynamic_smem(pip_team_kernel, smem_bytes, g_smem_team);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, pip_team_kernel, warps_per_cta * 32, smem_bytes);
+  }
   if (shared_class == 2) {
     cudaError_t e = pip_raise_dynamic_smem(pip_solve_kernel<true, int>, smem_bytes, g_smem_s32);
     if (e != cudaSuccess) return e;
@@ -114,6 +129,20 @@ extern "C" long long pip_layout_words(int nvar, int nparm, int ni, int nc, int f
   PipLayout L;
   pip_layout(nvar, nparm, ni, nc, flags, level, 0x7fffffff, vbytes, L);
   return L.total;
+}
+
+/* the arena layout of a shape at a slack level, degraded exactly as the solver degrades it when the arena is
+ * too small; out->s.ni carries nc + 1 (the largest context the layout was carved for).  0 = does not fit */
+extern "C" int pip_layout_compute(int nvar, int nparm, int ni, int nc, int flags, int level, int words, int vbytes,
+                                  PipLayout *out)
+{
+  int level_try = level;
+  while (!pip_layout(nvar, nparm, ni, nc, flags, level_try, words, vbytes, *out)) {
+    level_try = level_try == PIP_LEVEL_S_WIDE ? 2 : level_try - 1;
+    if (level_try < 0) return 0;
+  }
+  out->s.ni = nc + 1;
+  return 1;
 }
 
 /* ---- cell gather ------------------------------------------------------------------------ */
@@ -299,24 +328,24 @@ pip_gather_words_kernel(const PipResult *res, const int *order, const PipCell *c
     long long base = 0;
     if (lane == 0 && slots) base = (long long)atomicAdd(so.ctl + PIP_SO_SLOTS, (unsigned long long)slots);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + slots > so.cap) {                       /* does not fit: the host grows the buffer and repeats the pass */
-      if (lane == 0) so.ctl[PIP_SO_OVERFLOW] = 1;
-    } else if (nw) {
+    const bool fits = base + slots <= so.cap;          /* else: the host grows the buffer and repeats the pass */
+    if (!fits && lane == 0) so.ctl[PIP_SO_OVERFLOW] = 1;
+    /* copy and hash in one pass: every lane mixes its own words, the hash is the sum (pip_hash_word) */
+    pip_u64 h = 0;
+    if (nw) {
       const void *src = (const void *)(cells + r.cell_off);
       pip_i64 *dst = out + base;
-      if (r.rflags & PIP_RES_SRC32) {
-        const int *s32 = (const int *)src;
-        if (narrow) for (long long k = lane; k < nw; k += 32) ((int *)dst)[k] = s32[k];
-        else for (long long k = lane; k < nw; k += 32) dst[k] = (pip_i64)s32[k];
-      } else {
-        const pip_i64 *s64 = (const pip_i64 *)src;
-        if (narrow) for (long long k = lane; k < nw; k += 32) ((int *)dst)[k] = (int)s64[k];
-        else for (long long k = lane; k < nw; k += 32) dst[k] = s64[k];
+      const bool s32 = (r.rflags & PIP_RES_SRC32) != 0;
+      for (long long k = lane; k < nw; k += 32) {
+        const pip_i64 v = s32 ? (pip_i64)((const int *)src)[k] : ((const pip_i64 *)src)[k];
+        h += pip_hash_word((pip_u64)v, (pip_u64)k);
+        if (fits) { if (narrow) ((int *)dst)[k] = (int)v; else dst[k] = v; }
       }
     }
+    for (int o = 16; o > 0; o >>= 1) h += (pip_u64)__shfl_xor_sync(0xffffffffu, (long long)h, o);
     if (lane == 0) {
       so.status[p] = r.status;
-      if (!has_words) so.hash[p] = 0ull;              /* (the solver wrote the hash of a finished stream) */
+      so.hash[p] = has_words ? h + PIP_HASH_INIT : 0ull;
       so.off[p] = base;
       so.len[p] = nw | (narrow && nw ? PIP_LEN_NARROW : 0ll);
     }

@@ -30,6 +30,7 @@ cudaError_t pip_launch_gather_words(const PipResult *res, const int *order, cons
                                     int nprob, const PipStreamOut *so, cudaStream_t stream);
 cudaError_t pip_launch_init_results(PipResult *res, long long n, cudaStream_t stream);
 cudaError_t pip_launch_convert(const PipConvertArgs *A, int elem_log2, cudaStream_t stream);
+int pip_layout_compute(int nvar, int nparm, int ni, int nc, int flags, int level, int words, int vbytes, PipLayout *out);
 long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level, int vbytes);
 #ifdef __cplusplus
 }

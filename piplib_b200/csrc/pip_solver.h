@@ -33,13 +33,6 @@
 #include "simt.h"
 
 
-struct PipTab {          /* warp-uniform, lives in registers */
-  int den, fl, data, det;   /* word offsets into the arena */
-  int stride, pcap, rcap;   /* words per slot, position capacity, slot capacity */
-  int nvar, nparm, ni;
-  int ldet;
-};
-
 struct PipStats {
   unsigned pivots, cuts, subsolves, splits, max_rows, max_cols;
   unsigned wrapped;              /* int64 classes: some exact product left 64 bits (per lane, OR-ed) */
@@ -81,13 +74,6 @@ PIP_HD void pip_slack(int level, int &dp, int &dr, int &dx, int &ds)
   else if (level == 1) { dp = 2; dr = 6; dx = 6; ds = 6; }
   else { dp = 1; dr = 2; dx = 3; ds = 3; }
 }
-
-struct PipLayout {
-  PipTab m, s;
-  int ctx, cstride, crcap;
-  int cut, tmp;
-  int total;
-};
 
 /* Carve the arena for one problem.  Returns false when even this slack level does not fit. */
 PIP_HD bool pip_layout(int nvar, int nparm, int ni, int nc, int flags, int level, int words, int vbytes, PipLayout &L)
@@ -242,6 +228,13 @@ PIP_SDEVNI void pip_copy2d(V *dst, int dstride, const V *src, int sstride, int r
     r += dr; j += dj;
     if (j >= cols) { j -= cols; r++; }
   }
+}
+
+/* warp-cooperative copy of n 64-bit words (the frame stack) */
+PIP_SDEVNI void pip_copy_words(pip_i64 *dst, const pip_i64 *src, int n)
+{
+  #pragma unroll 1
+  for (int k = W::lane(); k < n; k += 32) dst[k] = src[k];
 }
 
 /* problem load: like pip_copy2d but the source elements are int8 / int32 / int64 (the host ships
@@ -859,7 +852,7 @@ PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V
     /* pass 1: pure arithmetic.  The generic formula gives 0 in column pivj (foo*lpiv == pivot*foo'),
      * the real value dpiv*foo' is patched in afterwards, so the loop body has no special case */
     pip_u64 orz = 0;
-    #pragma unroll 4
+    #pragma unroll 2
     for (int j = 0; j < ncol; j++) {
       const V z = PipVal<V>::mulsub(row[j], lpiv, prow[j], foo, ovf);
       row[j] = z;
@@ -885,6 +878,12 @@ PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V
         #pragma unroll 2
         for (int j = 0; j < ncol; j++) row[j] = row[j] >> sh;
         den[k] = newden >> sh;
+      } else if (PipVal<V>::narrow) {
+        /* int32 storage: the shared 32-bit division (the modular-inverse route is 64-bit code the int32
+         * kernel otherwise never runs) */
+        #pragma unroll 1
+        for (int j = 0; j < ncol; j++) row[j] = pip_div(row[j], g);
+        den[k] = pip_div(newden, g);
       } else {
         PipExactDiv e = pip_exact_prepare((pip_i64)g);
         #pragma unroll 2
@@ -1054,19 +1053,19 @@ PIP_SDEVNI bool pip_emit_solution(pip_i64 *B, const PipTab &T, PipCell *out, int
  * (PIP_F_SIMPLE_SER), i.e. every bulk workload: the cells were written (24 B each), read back and re-parsed
  * by a second kernel that cost a fifth of the solve.  The grammar is pre-order like the cells; the only
  * forward reference is the new-parameter count that opens a node, kept as a reserved slot (node_at) and
- * patched when the node's kind is known.  Every lane hashes the words it writes (pip_hash_word is a sum). */
+ * patched when the node's kind is known.  (The stream's hash is taken by the copy kernel that follows:
+ * hashing here, 20 instructions at every one of two dozen emission sites, cost the instruction-supply-bound
+ * solve kernel more than the whole decode kernel it replaced.) */
 struct PipWordOut {
   V *w;                    /* the warp's window, as words of the stored type */
   unsigned pos;            /* words emitted so far (warp-uniform) */
   int node_at;             /* slot of the open node's new-parameter count, -1 = no node open */
   unsigned nnew;
-  pip_u64 h;               /* this lane's share of the hash */
   bool wide;               /* some word left int32 (int64 classes) */
 };
 PIP_SDEV void pip_wout(PipWordOut &o, unsigned idx, pip_i64 v)
 {
   o.w[idx] = (V)v;
-  o.h += pip_hash_word((pip_u64)v, (pip_u64)idx);
   if (!PipVal<V>::narrow) o.wide = o.wide || (v != (pip_i64)(int)v);
 }
 PIP_SDEV void pip_wnode_open(PipWordOut &o)
@@ -1104,13 +1103,16 @@ PIP_SDEVNI void pip_emit_solution_words(pip_i64 *B, const PipTab &T, PipWordOut 
   for (int q = lane; q < pairs; q += 32) {
     const int i = q / np1, r = q - i * np1;
     const int j = (r == np1 - 1) ? T.nvar : T.nvar + 1 + r;
-    const pip_i64 D = (pip_i64)den[i];
-    const pip_i64 N = (pip_i64)pip_entry(B, T, fl[i], den[i], j);
-    const pip_i64 d = (D == 1) ? 1 : pip_gcd(N, D);
-    const pip_i64 num = d == 1 ? N : (d ? pip_div(N, d) : 0);
-    const pip_i64 dd = (d == D) ? 1 : (d ? pip_div(D, d) : 0);
-    pip_wout(o, base + 3 + i * per + 2 * r, num);
-    pip_wout(o, base + 4 + i * per + 2 * r, dd);
+    const V D = den[i];
+    const V N = pip_entry(B, T, fl[i], D, j);
+    V num = N, dd = 1;
+    if (D != 1) {
+      const V d = pip_gcd(N, D);
+      if (d != 1) num = d ? pip_div(N, d) : (V)0;
+      if (d != D) dd = d ? pip_div(D, d) : (V)0;
+    }
+    pip_wout(o, base + 3 + i * per + 2 * r, (pip_i64)num);
+    pip_wout(o, base + 4 + i * per + 2 * r, (pip_i64)dd);
   }
   o.pos += 2 + (unsigned)T.nvar * per;
 }
@@ -1470,17 +1472,25 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
                            int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st, PipTeam *tm = nullptr,
-                           unsigned *nwords_out = nullptr, bool wordmode = false, pip_u64 *hash_out = nullptr)
+                           unsigned *nwords_out = nullptr, bool wordmode = false, const PipLayout *pre = nullptr)
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
   PipWordOut wo;
-  wo.w = (V *)out; wo.pos = 0; wo.node_at = -1; wo.nnew = 0; wo.h = 0; wo.wide = false;
+  wo.w = (V *)out; wo.pos = 0; wo.node_at = -1; wo.nnew = 0; wo.wide = false;
   PipLayout L;
-  int level_try = slack_level;
-  while (!pip_layout(P.nvar, P.nparm, P.ni, P.nc, P.flags, level_try, words, (int)sizeof(V), L)) {
-    level_try = level_try == PIP_LEVEL_S_WIDE ? 2 : level_try - 1;
-    if (level_try < 0) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
+  /* dense batches: one shape for the whole launch, the arena was carved once on the host (`pre`, for the
+   * largest row counts of the batch; capacities only ever decide CAPACITY, never an answer) */
+  if (pre && pre->m.nvar == P.nvar && pre->m.nparm == P.nparm && P.ni <= pre->m.ni && P.nc + 1 <= pre->s.ni) {
+    L = *pre;
+    L.m.ni = P.ni;
+    L.s.ni = 0;
+  } else {
+    int level_try = slack_level;
+    while (!pip_layout(P.nvar, P.nparm, P.ni, P.nc, P.flags, level_try, words, (int)sizeof(V), L)) {
+      level_try = level_try == PIP_LEVEL_S_WIDE ? 2 : level_try - 1;
+      if (level_try < 0) { status_out = PIP_ST_CAPACITY; ncell_out = 0; return; }
+    }
   }
   /* device-converted input that does not fit the int32 pool (pip_convert.h): only the int64 pool, built
    * on demand by the host, holds this problem */
@@ -1709,13 +1719,16 @@ AFTER_COMPA:
     ncell += np + 3;
     nwords += 2 * np + 5;
     W::sync();
-    /* push the ELSE continuation: 12 header words, den[nl], fl[nl], the ni stored rows, the
-     * nc+1 context rows (sections padded to whole 8-byte words), the frame size */
+    /* push the ELSE continuation: 12 header words, then two block copies of arena words -- the main tableau
+     * as it lies in the arena (den | fl | scratch | the ni stored rows with their stride: one contiguous
+     * region, pip_layout) and the nc+1 context rows -- then the frame size.  (A compact frame was four index
+     * loops here and four in the pop: 300 instructions of a kernel whose executed code has to fit the 32 KB
+     * instruction cache; two word-copy loops cost twice the frame bytes and a fifth of the code.) */
     {
 #define PIP_VW(n) (((pip_i64)(n) * (pip_i64)sizeof(V) + 7) / 8)
-      const pip_i64 wden = PIP_VW(nl), wfl = (nl + 1) / 2, wrows = PIP_VW((pip_i64)T.ni * ncol),
-                    wctx = PIP_VW((pip_i64)(nc + 1) * (np + 1));
-      const pip_i64 fsize = 12 + wden + wfl + wrows + wctx + 1;
+      const int w1 = (T.data - T.den) + (int)PIP_VW((pip_i64)T.ni * T.stride);
+      const int w2 = (int)PIP_VW((pip_i64)(nc + 1) * cstride);
+      const pip_i64 fsize = 12 + (pip_i64)w1 + w2 + 1;
       if (top + fsize > stk_cap) { status = PIP_ST_CAPACITY; goto DONE; }
       pip_i64 *F = stk + top;
       if (lane == 0) {
@@ -1724,19 +1737,8 @@ AFTER_COMPA:
         for (int k = 0; k < PIP_MAX_DET; k++) F[8 + k] = B[T.det + k];
         F[fsize - 1] = fsize;
       }
-      pip_i64 *q = F + 12;
-      const V *den = pip_den(B, T);
-      V *qv = (V *)q;
-      #pragma unroll 1
-      for (int k = lane; k < nl; k += 32) qv[k] = den[k];
-      q += wden;
-      int *qi = (int *)q;
-      #pragma unroll 1
-      for (int k = lane; k < nl; k += 32) qi[k] = fl[k];
-      q += wfl;
-      pip_copy2d((V *)q, ncol, (const V *)(B + T.data), T.stride, T.ni, ncol);
-      q += wrows;
-      pip_copy2d((V *)q, np + 1, ctx, cstride, nc + 1, np + 1);
+      pip_copy_words(F + 12, B + T.den, w1);
+      pip_copy_words(F + 12 + w1, B + L.ctx, w2);
       top += fsize;
     }
     W::sync();
@@ -1916,22 +1918,12 @@ LEAF:
     const pip_i64 fsize = stk[top - 1];
     const pip_i64 *F = stk + (top - fsize);
     T.nvar = (int)F[0]; T.nparm = (int)F[1]; T.ni = (int)F[2]; nc = (int)F[3]; pivi = (int)F[4]; T.ldet = (int)F[5];
-    const int np = T.nparm, ncol = T.nvar + np + 1, nl = T.nvar + T.ni;
+    const int np = T.nparm;
     int *fl = pip_fl(B, T);
-    V *den = pip_den(B, T);
     if (lane == 0) for (int k = 0; k < PIP_MAX_DET; k++) B[T.det + k] = F[8 + k];
-    const pip_i64 *q = F + 12;
-    const V *qv = (const V *)q;
-    #pragma unroll 1
-    for (int k = lane; k < nl; k += 32) den[k] = qv[k];
-    q += PIP_VW(nl);
-    const int *qi = (const int *)q;
-    #pragma unroll 1
-    for (int k = lane; k < nl; k += 32) fl[k] = qi[k];
-    q += (nl + 1) / 2;
-    pip_copy2d((V *)(B + T.data), T.stride, (const V *)q, ncol, T.ni, ncol);
-    q += PIP_VW((pip_i64)T.ni * ncol);
-    pip_copy2d(ctx, cstride, (const V *)q, np + 1, nc + 1, np + 1);
+    const int w1 = (T.data - T.den) + (int)PIP_VW((pip_i64)T.ni * T.stride);
+    pip_copy_words(B + T.den, F + 12, w1);
+    pip_copy_words(B + L.ctx, F + 12 + w1, (int)PIP_VW((pip_i64)(nc + 1) * cstride));
     W::sync();
     #pragma unroll 1
     for (int j = lane; j <= np; j += 32) {                 /* the negated condition */
@@ -1955,12 +1947,8 @@ DONE:
   ncell_out = (status == PIP_ST_OK) ? ncell : 0;
   if (nwords_out) *nwords_out = status == PIP_ST_OK ? nwords : status == PIP_ST_VOID ? 1u : 0u;
   if (wordmode) {
-    /* the stream is complete: its hash = start value + the lanes' shares; an empty context is the one word -1 */
-    if (status == PIP_ST_VOID) { wo.h = 0; wo.wide = false; if (lane == 0) pip_wout(wo, 0, -1); }
-    pip_u64 h = wo.h;
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) h += (pip_u64)W::shfl_xor64((long long)h, o);
-    if (hash_out) *hash_out = (status == PIP_ST_OK || status == PIP_ST_VOID) ? h + PIP_HASH_INIT : 0ull;
+    /* an empty context is the one word -1 */
+    if (status == PIP_ST_VOID) { wo.wide = false; if (lane == 0) pip_wout(wo, 0, -1); }
     /* the solver's own count (nwords) and the words written must agree: a mismatch is a bug, not a verdict */
     if (status == PIP_ST_OK && wo.pos != nwords) status_out = PIP_ST_FAULT + 2;
     wide = !PipVal<V>::narrow && wo.wide;

@@ -126,6 +126,21 @@ typedef struct {
 enum { PIP_SO_SLOTS = 0, PIP_SO_FINALS = 1, PIP_SO_OVERFLOW = 2, PIP_SO_NCTL = 4 };
 #define PIP_STATUS_IS_FINAL(st) ((st) != PIP_ST_PENDING && (st) != PIP_ST_CAPACITY && (st) != PIP_ST_WIDEN)
 
+/* the working arena of one problem, carved by pip_layout (pip_solver.h); word offsets into the arena */
+typedef struct PipTab {          /* warp-uniform, lives in registers */
+  int den, fl, data, det;   /* word offsets into the arena */
+  int stride, pcap, rcap;   /* words per slot, position capacity, slot capacity */
+  int nvar, nparm, ni;
+  int ldet;
+} PipTab;
+
+typedef struct PipLayout {
+  PipTab m, s;
+  int ctx, cstride, crcap;
+  int cut, tmp;
+  int total;
+} PipLayout;
+
 /* launch parameters of the warp-per-problem kernels */
 typedef struct {
   const PipProblem *prob;
@@ -144,8 +159,10 @@ typedef struct {
   int sol_size, maxcol, maxparm;
   int slack_level;
   unsigned long long *prof;      /* [PIP_NPHASE] cycle sums (profile build only) or NULL */
+  int have_layout;               /* every problem of the launch has the shape `layout` was carved for (dense batches):
+                                    the arena layout comes from the host, pip_layout does not run per problem */
+  PipLayout layout;
   int emit_words;                /* word mode: PIP_F_SIMPLE_SER problems write their serialised quast (pip_solver.h) */
-  pip_u64 *hash_out;             /* word mode: hash of each problem's stream, indexed like res */
 } PipLaunch;
 
 #endif

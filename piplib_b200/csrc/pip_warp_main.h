@@ -34,10 +34,9 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
     unsigned rflags = 0, nwords = 0;
     /* word mode (PipLaunch::emit_words): the solver writes the serialised quast itself into the window */
     const bool wordmode = L.emit_words && (P.flags & PIP_F_SIMPLE_SER);
-    pip_u64 hash = 0;
     PipSolver<V, TEAM>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
                   L.stack_words_per_warp, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm, &nwords,
-                  wordmode, &hash);
+                  wordmode, L.have_layout ? &L.layout : nullptr);
     if (lane == 0) {
       PipResult r;
       r.status = status; r.ncells = ncell;
@@ -53,7 +52,6 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
         /* in word mode PIP_RES_WIDE means "some word left int32": the complement is PIP_RES_SER32 */
         rflags = (rflags & ~(PIP_RES_WIDE | PIP_RES_SER32)) | PIP_RES_SIZED | PIP_RES_WORDS |
                  ((rflags & PIP_RES_WIDE) ? 0u : PIP_RES_SER32) | (PipVal<V>::narrow ? PIP_RES_SRC32 : 0u);
-        if (L.hash_out) L.hash_out[p] = hash;
       }
       r.elem_updates_lo = (unsigned)(st.elem_updates & 0xffffffffull);
       r.elem_updates_hi = (unsigned)(st.elem_updates >> 32);

@@ -90,6 +90,7 @@ static inline float pip_u2f(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); 
 #define PIP_HDM inline
 #define PIP_DM inline
 #define PIP_HDNI static __attribute__((noinline, unused))
+static inline int pip_clzll(unsigned long long v) { return v ? __builtin_clzll(v) : 64; }
 
 #else  /* device */
 
@@ -159,7 +160,14 @@ struct __align__(16) pip_i64x2 { long long x, y; };
 
 static __device__ __forceinline__ int pip_ffs(unsigned m) { return __ffs((int)m); }
 static __device__ __forceinline__ int pip_popc(unsigned m) { return __popc(m); }
-static __device__ __forceinline__ int pip_clzll(unsigned long long v) { return __clzll((long long)v); }
+static __host__ __device__ __forceinline__ int pip_clzll(unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)v);
+#else
+  return v ? __builtin_clzll(v) : 64;
+#endif
+}
 static __device__ __forceinline__ int pip_ctzll(unsigned long long v) { return v ? __ffsll((long long)v) - 1 : 64; }
 static __device__ __forceinline__ long long pip_mulhi(long long a, long long b) { return __mul64hi(a, b); }
 static __device__ __forceinline__ double pip_ll2d(long long v) { return __ll2double_rn(v); }

@@ -38,7 +38,7 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
   e.L.maxparm = PIP_MAXPARM;
   e.L.slack_level = slack_level;
   e.L.emit_words = emit_words;
-  e.L.hash_out = hash_out;
+  (void)hash_out;
   e.narrow = narrow;
   e.arena = (pip_i64 *)malloc(sizeof(pip_i64) * (size_t)work_words);
   memset(e.arena, 0x5a, sizeof(pip_i64) * (size_t)work_words);   // poison: nothing may rely on zeros

@@ -34,7 +34,7 @@ def main():
     a = ap.parse_args()
     build.build()
     from oracle import pyoracle as po
-    from bench import cpu_arm
+    from oracle.cpu_arm import cpu_arm
     po.build(ref=False, port=True)
     port = po.Port()
     cores = os.cpu_count() or 1

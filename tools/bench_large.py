@@ -16,7 +16,8 @@ from workloads import synth  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 check = "--no-check" not in sys.argv
-tab = synth.consecutive_ones(n, n, seed=2026)
+dense = "--dense" in sys.argv          # long intervals: nearly every row is touched by every pivot
+tab = synth.consecutive_ones(n, n, seed=2026, dense=dense)
 p = api.LargeProblem(n, n, 1, tab, cut_rows=1024, sol_size=1 << 20, maxcol=1 << 16)
 print("warm %.3f ms" % p.run(), flush=True)
 ms = []
@@ -35,8 +36,9 @@ src = "fallback"
 if os.path.exists(pk):
     peak = json.load(open(pk))["hbm_gbs"]
     src = "measured"
-line = {"workload": "consecutive-ones %d x %d int64, Nq=1" % (n, n + 1), "status": st, "pivots": piv,
-        "cuts": info["cuts"], "skipped_identity_rows": info["skipped_rows"], "kernel_ms": best,
+line = {"workload": "consecutive-ones %s%d x %d int64, Nq=1" % ("(long intervals) " if dense else "", n, n + 1), "status": st, "pivots": piv,
+        "cuts": info["cuts"], "skipped_identity_rows": info["skipped_rows"],
+        "identity_rows_skipped_frac": info["skipped_rows"] / max(1.0, float(R) * max(piv, 1)), "kernel_ms": best,
         "us_per_pivot": 1e3 * best / max(piv, 1),
         "phase_share": {"choice": info["cycles_choice"] / max(1, info["cycles_choice"] + info["cycles_update"]),
                         "update": info["cycles_update"] / max(1, info["cycles_choice"] + info["cycles_update"]),

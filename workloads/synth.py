@@ -84,7 +84,7 @@ def loopnest(n, seed=2026, nvar=16, nrows=24, nparm=3, first=0, p2=0.05, p3=0.05
     return np.ascontiguousarray(np.concatenate(doms)), np.ascontiguousarray(np.concatenate(ctxs))
 
 
-def consecutive_ones(nvar, nrows, seed=2026, cmax=50):
+def consecutive_ones(nvar, nrows, seed=2026, cmax=50, dense=False):
     """BASELINE config 4: one large tableau whose rows have the consecutive-ones property
     (sum_{j=a..b} x_j >= c): totally unimodular, so entries stay small through hundreds of pivots
     (dense random data overflows int64 within a few).  Returns the .dat-order tableau
@@ -93,6 +93,12 @@ def consecutive_ones(nvar, nrows, seed=2026, cmax=50):
     a = rng.integers(0, nvar, size=nrows)
     b = rng.integers(0, nvar, size=nrows)
     lo, hi = np.minimum(a, b), np.maximum(a, b)
+    if dense:
+        # long intervals: every row starts in the first eighth and ends in the last eighth of the columns, so
+        # nearly every row holds the pivot column and a pivot's update touches nearly the whole tableau
+        # (the default draw leaves 86 % of the row updates the identity, which the kernel skips)
+        lo = rng.integers(0, max(1, nvar // 8), size=nrows)
+        hi = nvar - 1 - rng.integers(0, max(1, nvar // 8), size=nrows)
     c = rng.integers(1, cmax + 1, size=nrows)
     j = np.arange(nvar)[None, :]
     tab = np.zeros((nrows, nvar + 1), dtype=np.int64)
