@@ -1244,7 +1244,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
       for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
     }
     const size_t nchunks = sizes.size();
-    const size_t lanes = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", in_pinned ? 3 : 4), PipEngine::MAX_LANES),
+    const size_t lanes = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 4), PipEngine::MAX_LANES),
                                                               (nchunks + devices.size() - 1) / devices.size()));
     const size_t nworkers = lanes * devices.size();
     /* host threads per lane: the lanes' conversion / copy-out phases overlap, so each gets a share */
