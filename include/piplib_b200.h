@@ -124,6 +124,10 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
  * The answers are identical either way.  Returns 0 or -1. */
 int pip_pin_buffer_dp(void *p, size_t bytes);
 int pip_unpin_buffer_dp(void *p);
+/* page-locked memory allocated by the driver (cudaHostAlloc, portable): the fastest DMA source / target;
+ * registering existing memory (above) pins 4 KB pages in place and transfers a little slower */
+void *pip_alloc_pinned_dp(size_t bytes);
+void pip_free_pinned_dp(void *p);
 
 /* Devices pip_solve_dense_dp spreads a batch over (one process, several GPUs): the chunks of a batch go
  * to whichever device has a free lane (a shared queue: dynamic balance across the GPUs), results land in

@@ -121,6 +121,38 @@ def pin(a):
     return a
 
 
+_pinned_allocs = {}
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked memory from the driver (pip_alloc_pinned_dp); free with pinned_free"""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    L = lib()
+    L.pip_alloc_pinned_dp.restype = C.c_void_p
+    L.pip_alloc_pinned_dp.argtypes = [C.c_size_t]
+    L.pip_free_pinned_dp.argtypes = [C.c_void_p]
+    p = L.pip_alloc_pinned_dp(max(n, 1))
+    if not p:
+        raise RuntimeError("pip_alloc_pinned_dp failed")
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    _pinned_allocs[a.ctypes.data] = p
+    return a
+
+
+def pinned_copy(a):
+    b = pinned_empty(a.shape, a.dtype)
+    b[...] = a
+    return b
+
+
+def pinned_free(a):
+    p = _pinned_allocs.pop(a.ctypes.data, None)
+    if p:
+        lib().pip_free_pinned_dp(p)
+
+
 def unpin(a):
     if a is not None and a.nbytes:
         lib().pip_unpin_buffer_dp(a.ctypes.data)
@@ -304,10 +336,11 @@ def solve_dense(dom, ctx, bignum=-1, want_hashes=True, want_ser=False, ser_cap_h
 def alloc_result(n, words_per_problem=448, pinned=False):
     """caller-owned result buffers for solve_dense(out=...); pinned=True page-locks the quast stream so
     that the device writes it by DMA"""
+    cap = words_per_problem * n + 1024
     out = dict(status=np.zeros(n, dtype=np.int32), hashes=np.zeros(n, dtype=np.uint64),
-               ser=np.empty(words_per_problem * n + 1024, dtype=np.int64),
+               ser=pinned_empty((cap,), np.int64) if pinned == "alloc" else np.empty(cap, dtype=np.int64),
                ser_off=np.zeros(n + 1, dtype=np.int64), ser_len=np.zeros(n, dtype=np.int64))
-    if pinned:
+    if pinned and pinned != "alloc":
         pin(out["ser"])
     return out
 

@@ -1148,6 +1148,11 @@ bool is_pinned(const void *p)
 }
 
 std::mutex g_dense_mu;                  /* one dense call at a time per process (it is parallel inside) */
+/* One lane at a time per device and direction on the PCIe link: lanes that all upload, then all solve, then
+ * all download move in lockstep and overlap nothing (measured at 8 GPUs: every lane's upload, solve and
+ * download each took four times its share and the call took their sum).  With the link handed from lane to
+ * lane a chunk goes up at full speed while the previous one is being solved and the one before comes down. */
+std::mutex g_h2d_mu[PipEngine::MAX_DEVICES], g_d2h_mu[PipEngine::MAX_DEVICES];
 std::vector<int> g_devices;             /* devices a dense call spreads its chunks over (pip_set_devices_dp) */
 std::mutex g_devices_mu;
 
@@ -1172,6 +1177,14 @@ int pip_pin_buffer_dp(void *p, size_t bytes)
   if (e != cudaSuccess) { cudaGetLastError(); return -1; }
   return 0;
 }
+void *pip_alloc_pinned_dp(size_t bytes)
+{
+  void *p = nullptr;
+  const cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pip_free_pinned_dp(void *p) { if (p) cudaFreeHost(p); }
 int pip_unpin_buffer_dp(void *p)
 {
   if (!p) return -1;
@@ -1244,7 +1257,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
       for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
     }
     const size_t nchunks = sizes.size();
-    const size_t lanes = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 4), PipEngine::MAX_LANES),
+    const size_t lanes = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 6), PipEngine::MAX_LANES),
                                                               (nchunks + devices.size() - 1) / devices.size()));
     const size_t nworkers = lanes * devices.size();
     /* host threads per lane: the lanes' conversion / copy-out phases overlap, so each gets a share */
@@ -1286,6 +1299,8 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
         pip_cuda_check(cudaSetDevice(device), "cudaSetDevice");
         DenseChunk C;                       /* per-worker scratch, reused from chunk to chunk */
         std::vector<long long> at;
+        cudaEvent_t copied = nullptr;
+        pip_cuda_check(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming), "cudaEventCreate");
         for (;;) {
           const size_t c = next_chunk.fetch_add(1);          /* chunks go to whichever device / lane is free */
           if (c >= nchunks) break;
@@ -1307,8 +1322,13 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
             unsigned char *d_pd = (unsigned char *)E.device_scratch(3, cn * sizeof(PipProblem) + 64);
             int *d_dims = (int *)(d_pd + cn * sizeof(PipProblem));
             int *h_dims = (int *)E.pinned_scratch(0, 64);
-            if (dwords) pip_cuda_check(cudaMemcpyAsync(d_dom, A.dom + C.first * dwords, cn * dwords * 8, cudaMemcpyHostToDevice, s), "H2D domain rows");
-            if (cwords) pip_cuda_check(cudaMemcpyAsync(d_ctx, A.ctx + C.first * cwords, cn * cwords * 8, cudaMemcpyHostToDevice, s), "H2D context rows");
+            {
+              std::lock_guard<std::mutex> link(g_h2d_mu[device]);
+              if (dwords) pip_cuda_check(cudaMemcpyAsync(d_dom, A.dom + C.first * dwords, cn * dwords * 8, cudaMemcpyHostToDevice, s), "H2D domain rows");
+              if (cwords) pip_cuda_check(cudaMemcpyAsync(d_ctx, A.ctx + C.first * cwords, cn * cwords * 8, cudaMemcpyHostToDevice, s), "H2D context rows");
+              pip_cuda_check(cudaEventRecord(copied, s), "cudaEventRecord");
+              pip_cuda_check(cudaEventSynchronize(copied), "wait for the upload");      /* (not for the kernels behind it) */
+            }
             pip_cuda_check(cudaMemsetAsync(d_dims, 0, 16, s), "memset dims");
             PipConvertArgs &ca = wc.a;
             ca.s = CS; ca.dom = d_dom; ca.ctx = d_ctx; ca.n = (long long)cn; ca.stride = stride;
@@ -1370,6 +1390,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
             long long *h_off = (long long *)hp, *h_len = h_off + cn;
             pip_u64 *h_hash = (pip_u64 *)(h_len + cn);
             int *h_st = (int *)(h_hash + cn);
+            std::unique_lock<std::mutex> link(g_d2h_mu[device]);
             pip_cuda_check(cudaMemcpyAsync(h_off, D.off, cn * 8, cudaMemcpyDeviceToHost, s), "D2H offsets");
             pip_cuda_check(cudaMemcpyAsync(h_len, D.len, cn * 8, cudaMemcpyDeviceToHost, s), "D2H lengths");
             pip_cuda_check(cudaMemcpyAsync(h_hash, D.hash, cn * 8, cudaMemcpyDeviceToHost, s), "D2H hashes");
@@ -1385,6 +1406,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
                 lane_stats[w].d2h_bytes += (size_t)total * 8;
               }
               pip_cuda_check(cudaStreamSynchronize(s), "sync after D2H");
+              link.unlock();
               for (size_t i = 0; i < cn; i++) {
                 const int s0 = h_st[i];
                 status[C.first + i] = PIP_STATUS_IS_FINAL(s0) ? s0 : PIP_ST_CAPACITY;
@@ -1400,6 +1422,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
                 lane_stats[w].d2h_bytes += (size_t)D.slots * 8;
               }
               pip_cuda_check(cudaStreamSynchronize(s), "sync after D2H");
+              link.unlock();
               emit_chunk_staged(C.first, cn, h_words, h_st, h_hash, h_off, h_len, status, hashes, ser, ser_cap, ser_off,
                                 ser_len, &cursor, nthreads, at);
             }
@@ -1417,6 +1440,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
           /* the cell chunks are engine-owned and reused by the next run on this lane: drop the views */
           C.out.base.clear();
         }
+        cudaEventDestroy(copied);
       } catch (const std::exception &e) { errors[w] = e.what(); }
     };
     if (nworkers <= 1) worker_main(0);
