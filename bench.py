@@ -392,6 +392,15 @@ def main():
                                                    "out of pinned staging"}
         if world == 1 and not a.no_large:
             line["config4_large_tableau"] = large_tableau_line(pk, pk_src)
+        if world == 1 and not a.no_e2e:
+            # the entry point north_star names: pip_solve_batch_dp (PipMatrix objects in, malloc'd PipQuast trees
+            # out), on a bounded slice (building the matrices through ctypes is the slow part, outside the timing)
+            nb = min(B, 50000)
+            sec, st_b = api.time_solve_batch(dom[:nb], ctx[:nb], bg, **opts)
+            if res is not None and not np.array_equal(np.where(st_b == 1, 0, st_b), np.where(res["status"][:nb] == 1, 0, res["status"][:nb])):
+                raise SystemExit("bench.py: pip_solve_batch_dp and pip_solve_dense_dp disagree")
+            line["batch_api"] = {"value": nb / sec, "unit": UNIT, "problems": nb,
+                                 "api": "pip_solve_batch_dp: PipMatrix objects in, PipQuast trees out (host decode, malloc per node)"}
         if world == 1:
             # the reference's CPU path on the same inputs, >= 1 s of work per core; its statuses and
             # hashes are compared with what the timed e2e call returned for the same problems

@@ -232,6 +232,39 @@ def solve_batch(problems, **opts):
     return res
 
 
+def time_solve_batch(dom, ctx, bignum=-1, reps=2, **opts):
+    """pip_solve_batch_dp (PipMatrix objects in, malloc'd PipQuast trees out) on a dense numpy batch: the
+    matrices are built before and the trees freed after the timed call.  Returns (best seconds, statuses)."""
+    import time
+    L = lib()
+    n = dom.shape[0]
+    doms = (C.POINTER(PipMatrix) * n)()
+    ctxs = (C.POINTER(PipMatrix) * n)()
+    bgs = (C.c_int * n)(*([int(bignum)] * n))
+    for i in range(n):
+        doms[i] = _matrix(dom.shape[1], dom.shape[2], dom[i])
+        if ctx is not None:
+            ctxs[i] = _matrix(ctx.shape[1], ctx.shape[2], ctx[i])
+    out = (C.c_void_p * n)()
+    status = (C.c_int * n)()
+    o = make_options(**opts)
+    best = 1e30
+    for _ in range(reps):
+        t = time.perf_counter()
+        rc = L.pip_solve_batch_dp(n, doms, ctxs, bgs, C.byref(o), out, status)
+        best = min(best, time.perf_counter() - t)
+        if rc != 0:
+            raise RuntimeError("pip_solve_batch_dp failed: %d" % rc)
+        for i in range(n):
+            if out[i]:
+                L.pip_quast_free_dp(out[i])
+    for i in range(n):
+        L.pip_matrix_free_dp(doms[i])
+        if ctxs[i]:
+            L.pip_matrix_free_dp(ctxs[i])
+    return best, np.asarray(list(status), dtype=np.int32)
+
+
 def solve(dom, ctx, bg, ctx_cols=None, **opts):
     """one problem through the batch entry point (pip_solve_dp itself exits on fatal verdicts)."""
     return solve_batch([dict(dom=dom, ctx=ctx, ctx_cols=ctx_cols, bignum=bg)], **opts)[0]

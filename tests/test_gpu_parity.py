@@ -527,3 +527,31 @@ def test_one_call_over_several_gpus(api, port):
     finally:
         api.set_devices([])
         del os.environ["PIPLIB_B200_CHUNK"]
+
+
+def test_reference_example_program_runs_on_our_library(api):
+    """the reference's own caller (example/example.c, compiled UNCHANGED against include/ and linked with
+    libpiplib_dp.so: oracle/_ref/example_dp, oracle/Makefile `example`) replays every example/*.pip and its
+    option variants: stdout must be the reference's .ll text (prompts, echoed matrices, pip_quast_print)"""
+    import subprocess
+    if not os.path.exists(po.EXAMPLE_DP):
+        pytest.skip("oracle/_ref/example_dp not built")
+    flags = {"Maximize": "Maximize", "Urs_parms": "Urs_parms", "Urs_unknowns": "Urs_unknowns", "Compute_dual": "Dual"}
+
+    def mat(shape, rows):
+        return "%d %d\n" % tuple(shape) + "".join(" ".join(str(v) for v in r) + "\n" for r in rows)
+    checked, bad = 0, []
+    for c in LIB:
+        if c["golden_ll"] is None or c["opts"].get("Simplify") or c["ref_status"] != 0:
+            continue
+        text = mat(c["ctx_shape"], c["ctx"]) + "%d\n" % c["bignum_raw"] + mat(c["dom_shape"], c["dom"]) + "\n"
+        for k, word in flags.items():
+            if c["opts"].get(k):
+                text += word + "\n"
+        if not c["opts"].get("Nq", 1):
+            text += "Rational\n"
+        r = subprocess.run([po.EXAMPLE_DP], input=text, capture_output=True, text=True, timeout=120)
+        if r.returncode != 0 or po.strip_ws_lines(r.stdout) != po.strip_ws_lines(c["golden_ll"]):
+            bad.append((c["name"], r.returncode, r.stderr[-200:]))
+        checked += 1
+    assert checked >= 15 and not bad, bad[:4]
