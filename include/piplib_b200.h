@@ -172,6 +172,11 @@ long long pip_last_batch_flags_dp(unsigned *flags, long long cap);
 long pip_quast_serialize_dp(const PipQuast_dp *q, long long *out, long cap);
 
 int pip_set_device_dp(int device);                     /* select the CUDA device (default 0) */
+/* Subtree donation inside one problem's parametric tree (dense path, bulk batches): idle warps take over the
+ * ELSE branches other warps offer (source/traiter.c:717,741-758: the THEN branch runs on a copy, the ELSE branch
+ * is a self-contained continuation) and the segments are spliced in pre-order -- same quasts, same verdicts.
+ * mode < 0: automatic (small batches of parametric problems, where most warps would idle), 0: off, > 0: on. */
+void pip_set_donation_dp(int mode);
 const char *pip_b200_version(void);
 
 #if defined(__cplusplus)

@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 SOURCES_CU = ["pip_kernels.cu", "pip_large.cu"]
 SOURCES_CPP = ["pip_engine.cpp", "pip_host.cpp"]
 SOURCES_CLI = ["pip_cli.cpp"]
-HEADERS = ["pip_types.h", "simt.h", "pip_arith.h", "pip_decode.h", "pip_decode_warp.h", "pip_solver.h", "pip_warp_main.h", "pip_kernels.h",
+HEADERS = ["pip_types.h", "pip_segments.h", "pip_convert.h", "simt.h", "pip_arith.h", "pip_decode.h", "pip_decode_warp.h", "pip_solver.h", "pip_warp_main.h", "pip_kernels.h",
            "pip_engine.h", "pip_large.h", os.path.join("..", "..", "include", "piplib_b200.h"),
            os.path.join("..", "..", "include", "piplib", "piplib.h")]
 

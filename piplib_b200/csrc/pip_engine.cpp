@@ -78,6 +78,8 @@ const int N_G = sizeof(G_LADDER) / sizeof(G_LADDER[0]);
 }  // namespace
 
 static std::atomic<int> g_device(0);
+static std::atomic<int> g_donation(-1);      /* subtree donation: -1 automatic, 0 off, 1 on (pip_set_donation_dp) */
+void pip_engine_set_donation(int mode) { g_donation = mode; }
 /* the device the calling thread works on: the engine's own device while one of its runs is in progress
  * (the whole-grid class is entered from inside PipEngine::run), else the default of pip_set_device_dp */
 static thread_local int t_run_device = -1;
@@ -92,6 +94,7 @@ struct PipEngine::Impl {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total, d_prof, d_parm, d_hash;
   DevBuf d_so_status, d_so_hash, d_so_off, d_so_len, d_so_ctl;     /* stream_out: per-problem arrays, control + stats */
+  DevBuf d_stl_offers, d_stl_segs, d_stl_next, d_stl_hwm, d_stl_head_next, d_stl_head_hwm, d_stl_ctl;   /* subtree donation */
   DevBuf d_scratch[4];
   PinBuf h_scratch[4];
   PinBuf h_hash;
@@ -488,6 +491,31 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
        * no cells, no decode kernel -- a copy into the compact buffer is all that follows the solve */
       const bool words_round = stream_out && all_sized && !use_large && getenv("PIPLIB_B200_CELL_DECODE") == nullptr;
       L.emit_words = words_round ? 1 : 0;
+      /* subtree donation (PipSteal): worth it when the batch is small against the machine -- then the tail of
+       * the launch is a few heavy parametric trees and most warps are idle; a big batch balances by problems.
+       * PIPLIB_B200_STEAL=0/1 overrides */
+      const int dmode = g_donation.load();
+      bool steal = words_round && k < 0 &&
+                   (dmode > 0 || (dmode < 0 && (long long)m <= 2ll * cs.warps && (!in.uniform || in.uniform->nparm > 0)));
+      if (const char *sv = getenv("PIPLIB_B200_STEAL")) steal = words_round && k < 0 && atoi(sv) != 0;
+      if (steal) {
+        PipSteal &S = L.steal;
+        S.mode = 1; S.cap = 1 << 16;
+        E.d_stl_offers.reserve((size_t)S.cap * sizeof(PipOffer));
+        E.d_stl_segs.reserve((size_t)S.cap * sizeof(PipResult));
+        E.d_stl_next.reserve((size_t)S.cap * sizeof(int));
+        E.d_stl_hwm.reserve((size_t)S.cap * sizeof(int));
+        E.d_stl_head_next.reserve(n * sizeof(int));
+        E.d_stl_head_hwm.reserve(n * sizeof(int));
+        E.d_stl_ctl.reserve(PIP_STL_NCTL * sizeof(unsigned));
+        CK(cudaMemsetAsync(E.d_stl_offers.p, 0, (size_t)S.cap * sizeof(PipOffer), s));
+        CK(cudaMemsetAsync(E.d_stl_head_next.p, 0xff, n * sizeof(int), s));
+        CK(cudaMemsetAsync(E.d_stl_head_hwm.p, 0, n * sizeof(int), s));
+        CK(cudaMemsetAsync(E.d_stl_ctl.p, 0, PIP_STL_NCTL * sizeof(unsigned), s));
+        S.offers = (PipOffer *)E.d_stl_offers.p; S.ctl = (unsigned *)E.d_stl_ctl.p;
+        S.segs = (PipResult *)E.d_stl_segs.p; S.seg_next = (int *)E.d_stl_next.p; S.seg_hwm = (int *)E.d_stl_hwm.p;
+        S.head_next = (int *)E.d_stl_head_next.p; S.head_hwm = (int *)E.d_stl_head_hwm.p;
+      }
       if (use_large) {
         run_large_round(in, host_prob(), d_pool, elem_log2, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
         out.times.launches += m;
@@ -509,8 +537,8 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         for (;;) {
           CK(cudaMemsetAsync(so.ctl + PIP_SO_FINALS, 0, 2 * sizeof(unsigned long long), s));   /* finals, overflow */
           if (words_round)
-            CK(pip_launch_gather_words((const PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p,
-                                       (pip_i64 *)E.d_compact.p, m, &so, s));
+            CK(pip_launch_gather_words((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p,
+                                       (pip_i64 *)E.d_compact.p, m, &so, L.steal.mode ? &L.steal : nullptr, in.sol_size, s));
           else
             CK(pip_launch_serialize((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p, d_parm, in.uniform_decode,
                                     nullptr, (pip_i64 *)E.d_compact.p, nullptr, m, 1, &so, s));

@@ -111,5 +111,6 @@ class PipEngine {
 
 void pip_cuda_check(cudaError_t e, const char *what);
 int pip_engine_device();
+void pip_engine_set_donation(int mode);
 
 #endif

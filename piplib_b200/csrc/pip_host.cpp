@@ -611,6 +611,7 @@ long pip_quast_serialize_dp(const PipQuast_dp *q, long long *out, long cap)
 }
 
 int pip_set_device_dp(int device) { return PipEngine::get().set_device(device); }
+void pip_set_donation_dp(int mode) { pip_engine_set_donation(mode < 0 ? -1 : mode > 0 ? 1 : 0); }
 const char *pip_b200_version(void) { return "piplib-b200 0.1 (sm_100a)"; }
 long long pip_last_batch_flags_dp(unsigned *flags, long long cap)
 {

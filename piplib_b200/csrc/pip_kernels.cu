@@ -19,6 +19,7 @@
 #include "pip_decode.h"
 #include "pip_decode_warp.h"
 #include "pip_kernels.h"
+#include "pip_segments.h"
 #include "pip_warp_main.h"
 
 extern __shared__ __align__(16) unsigned char pip_smem[];
@@ -36,9 +37,9 @@ static cudaError_t pip_raise_dynamic_smem(K kernel, size_t bytes, size_t &high_w
   if (e == cudaSuccess) high_water = bytes;
   return e;
 }
-static size_t g_smem_s32 = 0, g_smem_s64 = 0, g_smem_ws = 0, g_smem_team = 0;
+static size_t g_smem_s32 = 0, g_smem_s64 = 0, g_smem_ws = 0, g_smem_team = 0, g_smem_s32_steal = 0, g_smem_s64_steal = 0;
 
-template <bool SH, class V>
+template <bool SH, class V, bool STEAL = false>
 __global__ void __launch_bounds__(PIP_CTA_THREADS, PIP_MIN_CTAS)
 pip_solve_kernel(const PipLaunch L)
 {
@@ -48,7 +49,7 @@ pip_solve_kernel(const PipLaunch L)
   pip_i64 *arena;
   if (SH) arena = (pip_i64 *)pip_smem + (size_t)warp_in_cta * L.work_words;
   else arena = L.gwork + (size_t)warp_id * L.work_words;
-  pip_warp_main<V, !SH>(L, warp_id, arena, nullptr);   /* !SH: the global-memory code path */
+  pip_warp_main<V, !SH, STEAL>(L, warp_id, arena, nullptr);   /* !SH: the global-memory code path */
 }
 
 /* size class M: one problem per CTA, arena in global memory.  Warp 0 runs the solver, the other
@@ -81,10 +82,19 @@ extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, in
   if (shared_class == 1 || shared_class == 2) {
     size_t smem = (size_t)warps_per_cta * L->work_words * sizeof(pip_i64);
     cudaError_t e;
-    if (shared_class == 2) {
+    /* subtree donation (PipLaunch::steal) runs the instantiation that has it compiled in */
+    if (shared_class == 2 && L->steal.mode) {
+      e = pip_raise_dynamic_smem(pip_solve_kernel<true, int, true>, smem, g_smem_s32_steal);
+      if (e != cudaSuccess) return e;
+      pip_solve_kernel<true, int, true><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
+    } else if (shared_class == 2) {
       e = pip_raise_dynamic_smem(pip_solve_kernel<true, int>, smem, g_smem_s32);
       if (e != cudaSuccess) return e;
       pip_solve_kernel<true, int><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
+    } else if (L->steal.mode) {
+      e = pip_raise_dynamic_smem(pip_solve_kernel<true, pip_i64, true>, smem, g_smem_s64_steal);
+      if (e != cudaSuccess) return e;
+      pip_solve_kernel<true, pip_i64, true><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
     } else {
       e = pip_raise_dynamic_smem(pip_solve_kernel<true, pip_i64>, smem, g_smem_s64);
       if (e != cudaSuccess) return e;
@@ -311,8 +321,8 @@ extern "C" cudaError_t pip_launch_serialize(PipResult *res, const int *order, co
  * problem's span of the compact buffer, move the words (int32 from class S32, int64 otherwise; written as
  * int32 or int64 as the caller asked), fill the per-problem arrays, sum the counters.  One warp per problem. */
 __global__ void __launch_bounds__(256)
-pip_gather_words_kernel(const PipResult *res, const int *order, const PipCell *cells, pip_i64 *out, int nprob,
-                        const PipStreamOut so)
+pip_gather_words_kernel(PipResult *res, const int *order, const PipCell *cells, pip_i64 *out, int nprob,
+                        const PipStreamOut so, const PipSteal stl, int sol_size)
 {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -320,7 +330,20 @@ pip_gather_words_kernel(const PipResult *res, const int *order, const PipCell *c
   unsigned mrows = 0, mcols = 0, finals = 0;
   for (int q = warp; q < nprob; q += nwarps) {
     const int p = order ? order[q] : q;
-    const PipResult r = res[p];
+    PipResult r = res[p];
+    /* subtrees of this problem solved by other warps (PipSteal): resolve the verdict over the segment list */
+    const int chain = stl.mode ? stl.head_next[p] : -1;
+    PipResolved R;
+    if (chain >= 0) {
+      pip_resolve_segments(r, chain, stl, sol_size, R);
+      r.status = R.status;
+      r.ser_words = (unsigned)R.words; r.ncells = (int)R.cells;
+      r.pivots = (unsigned)R.pivots; r.cuts = (unsigned)R.cuts; r.subsolves = (unsigned)R.subsolves; r.splits = (unsigned)R.splits;
+      r.elem_updates_lo = (unsigned)(R.elem_updates & 0xffffffffull); r.elem_updates_hi = (unsigned)(R.elem_updates >> 32);
+      r.max_rows = R.max_rows; r.max_cols = R.max_cols;
+      r.rflags = (R.any_flags_or & ~PIP_RES_SER32) | (R.all_flags_and & PIP_RES_SER32);
+      if (lane == 0) res[p].status = r.status;         /* the ladder reads the resolved verdict */
+    }
     const bool has_words = r.status == PIP_ST_OK || r.status == PIP_ST_VOID;
     const long long nw = has_words ? (long long)r.ser_words : 0;
     const bool narrow = (r.rflags & PIP_RES_SER32) != 0 && !so.words64;
@@ -330,16 +353,27 @@ pip_gather_words_kernel(const PipResult *res, const int *order, const PipCell *c
     base = __shfl_sync(0xffffffffu, base, 0);
     const bool fits = base + slots <= so.cap;          /* else: the host grows the buffer and repeats the pass */
     if (!fits && lane == 0) so.ctl[PIP_SO_OVERFLOW] = 1;
-    /* copy and hash in one pass: every lane mixes its own words, the hash is the sum (pip_hash_word) */
+    /* copy and hash in one pass: every lane mixes its own words, the hash is the sum (pip_hash_word); the
+     * segments of a problem follow each other in pre-order */
     pip_u64 h = 0;
     if (nw) {
-      const void *src = (const void *)(cells + r.cell_off);
       pip_i64 *dst = out + base;
+      long long at = 0;
+      int seg = -1;                                       /* -1 = the head segment */
       const bool s32 = (r.rflags & PIP_RES_SRC32) != 0;
-      for (long long k = lane; k < nw; k += 32) {
-        const pip_i64 v = s32 ? (pip_i64)((const int *)src)[k] : ((const pip_i64 *)src)[k];
-        h += pip_hash_word((pip_u64)v, (pip_u64)k);
-        if (fits) { if (narrow) ((int *)dst)[k] = (int)v; else dst[k] = v; }
+      for (;;) {
+        const PipResult sr = seg < 0 ? res[p] : stl.segs[seg];
+        const void *src = (const void *)(cells + sr.cell_off);
+        const long long n = (long long)sr.ser_words;
+        for (long long k = lane; k < n; k += 32) {
+          const pip_i64 v = s32 ? (pip_i64)((const int *)src)[k] : ((const pip_i64 *)src)[k];
+          h += pip_hash_word((pip_u64)v, (pip_u64)(at + k));
+          if (fits) { if (narrow) ((int *)dst)[at + k] = (int)v; else dst[at + k] = v; }
+        }
+        at += n;
+        if (chain < 0) break;
+        seg = seg < 0 ? chain : stl.seg_next[seg];
+        if (seg < 0) break;
       }
     }
     for (int o = 16; o > 0; o >>= 1) h += (pip_u64)__shfl_xor_sync(0xffffffffu, (long long)h, o);
@@ -368,13 +402,16 @@ pip_gather_words_kernel(const PipResult *res, const int *order, const PipCell *c
   }
 }
 
-extern "C" cudaError_t pip_launch_gather_words(const PipResult *res, const int *order, const PipCell *cells, pip_i64 *out,
-                                               int nprob, const PipStreamOut *so, cudaStream_t stream)
+extern "C" cudaError_t pip_launch_gather_words(PipResult *res, const int *order, const PipCell *cells, pip_i64 *out,
+                                               int nprob, const PipStreamOut *so, const PipSteal *stl, int sol_size,
+                                               cudaStream_t stream)
 {
   int blocks = (nprob + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  pip_gather_words_kernel<<<blocks, 256, 0, stream>>>(res, order, cells, out, nprob, *so);
+  PipSteal none;
+  memset(&none, 0, sizeof none);
+  pip_gather_words_kernel<<<blocks, 256, 0, stream>>>(res, order, cells, out, nprob, *so, stl ? *stl : none, sol_size);
   return cudaGetLastError();
 }
 

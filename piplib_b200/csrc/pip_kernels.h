@@ -26,8 +26,9 @@ cudaError_t pip_launch_serialize(PipResult *res, const int *order, const PipCell
                                  const PipDecodeParm *uparm, const long long *dst_off, pip_i64 *out, pip_u64 *hashes,
                                  int nprob, int pass, const PipStreamOut *so, cudaStream_t stream);
 /* word mode: copy the streams the solver wrote itself into the compact buffer (span reservation) */
-cudaError_t pip_launch_gather_words(const PipResult *res, const int *order, const PipCell *cells, pip_i64 *out,
-                                    int nprob, const PipStreamOut *so, cudaStream_t stream);
+cudaError_t pip_launch_gather_words(PipResult *res, const int *order, const PipCell *cells, pip_i64 *out,
+                                    int nprob, const PipStreamOut *so, const PipSteal *stl, int sol_size,
+                                    cudaStream_t stream);
 cudaError_t pip_launch_init_results(PipResult *res, long long n, cudaStream_t stream);
 cudaError_t pip_launch_convert(const PipConvertArgs *A, int elem_log2, cudaStream_t stream);
 int pip_layout_compute(int nvar, int nparm, int ni, int nc, int flags, int level, int words, int vbytes, PipLayout *out);

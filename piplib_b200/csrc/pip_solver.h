@@ -185,7 +185,9 @@ PIP_DEV void pip_team_min(int *p, int v) { if (v < *p) *p = v; }
 
 /* TEAM = the global-memory code path (classes G and M): blocked row walks, and -- when a PipTeam
  * block is passed -- CTA-wide update and scans.  false = shared-memory classes (and the emulator). */
-template <class V, bool TEAM = false>
+/* STEAL = the instantiation with subtree donation compiled in (PipSteal): a separate kernel, because every
+ * instruction added to the bulk kernel costs it throughput (instruction cache, section 4 of DESIGN.md) */
+template <class V, bool TEAM = false, bool STEAL = false>
 struct PipSolver {
 /* ---- small accessors ------------------------------------------------------------------- */
 PIP_SDEV int *pip_fl(pip_i64 *B, const PipTab &T) { return (int *)(B + T.fl); }
@@ -235,6 +237,66 @@ PIP_SDEVNI void pip_copy_words(pip_i64 *dst, const pip_i64 *src, int n)
 {
   #pragma unroll 1
   for (int k = W::lane(); k < n; k += 32) dst[k] = src[k];
+}
+/* ... out of a frame in global memory, past the L1: the frame may have been written by another SM (donation) */
+PIP_SDEVNI void pip_copy_frame_in(pip_i64 *dst, const pip_i64 *src, int n)
+{
+  #pragma unroll 1
+  for (int k = W::lane(); k < n; k += 32) dst[k] = W::load_cg(src + k);
+}
+
+/* a claimed frame is read by the thief straight out of this warp's stack: before the donor leaves the frame
+ * behind for good (next problem, next stolen subtree on the same stack) the thief must have copied it */
+PIP_SDEVNI void pip_offer_wait_copied(const PipSteal &S, int idx)
+{
+  if (S.mode != 1) return;
+  for (;;) {
+    int stt = 0;
+    if (W::lane() == 0) stt = W::load_volatile(&S.offers[idx].state);
+    if (W::shfl(stt, 0) != PIP_OFFER_CLAIMED) return;
+    W::nap();
+  }
+}
+
+/* subtree donation, donor side (PipSteal, pip_types.h): publish the bottom frame of the stack -- the ELSE
+ * branch of the outermost open split -- when some warp is idle; one outstanding offer per segment */
+PIP_SDEVNI void pip_offer_bottom(const PipSteal &S, int problem, int seg, pip_i64 *stk, pip_i64 top, pip_i64 &top_base,
+                                 int &my_offer)
+{
+  if (!S.mode) return;
+  const int lane = W::lane();
+  if (my_offer >= 0) {
+    /* an offer that was claimed: its frame left this stack for good, the next one up is the new bottom */
+    int stt = 0;
+    if (lane == 0) stt = W::load_volatile(&S.offers[my_offer].state);
+    stt = W::shfl(stt, 0);
+    if (stt == PIP_OFFER_OPEN) return;
+    pip_offer_wait_copied(S, my_offer);
+    top_base += stk[top_base + 6];
+    my_offer = -1;
+  }
+  if (top <= top_base) return;
+  if (S.mode == 1) {
+    unsigned idle = 0;
+    if (lane == 0) idle = W::load_volatile(&S.ctl[PIP_STL_IDLE]);
+    if (!W::shfl((int)idle, 0)) return;
+  }
+  unsigned idx = 0;
+  if (lane == 0) idx = W::atomic_add(&S.ctl[PIP_STL_OFFERS], 1u);
+  idx = (unsigned)W::shfl((int)idx, 0);
+  if (idx >= (unsigned)S.cap) return;
+  W::fence();                       /* every lane's share of the frame is visible before the offer is */
+  W::sync();
+  if (lane == 0) {
+    PipOffer &o = S.offers[idx];
+    o.problem = problem; o.parent_seg = seg; o.frame = stk + top_base; o.pad = 0;
+    S.seg_next[idx] = -1;
+    W::fence();
+    W::atomic_exch(&o.state, S.mode == 2 ? PIP_OFFER_CLAIMED : PIP_OFFER_OPEN);
+  }
+  W::sync();
+  my_offer = (int)idx;
+  if (S.mode == 2) { top_base += stk[top_base + 6]; my_offer = -1; }     /* test mode: given away at once */
 }
 
 /* problem load: like pip_copy2d but the source elements are int8 / int32 / int64 (the host ships
@@ -1472,7 +1534,9 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
                            int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st, PipTeam *tm = nullptr,
-                           unsigned *nwords_out = nullptr, bool wordmode = false, const PipLayout *pre = nullptr)
+                           unsigned *nwords_out = nullptr, bool wordmode = false, const PipLayout *pre = nullptr,
+                           const PipSteal *stl = nullptr, int stl_problem = 0, int stl_seg = -1,
+                           const pip_i64 *resume = nullptr, int *hwm_out = nullptr)
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
@@ -1517,9 +1581,21 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
   rflags_out = 0;
   pip_i64 top = 0;
   unsigned ovf = 0;                /* int32 instantiation: some value left the 31-bit range */
+  /* subtree donation (PipSteal, pip_types.h) */
+  int hwm = 0;                     /* largest cell count this segment checked against SOL_SIZE */
+  pip_i64 top_base = 0;            /* frames below this stack offset were given away */
+  int my_offer = -1;               /* the one outstanding offer of this segment */
+  const pip_i64 *Fr = nullptr;     /* the frame being restored */
+/* the SOL_SIZE check of sol_alloc (source/sol.c:96-100); a segment of a donated subtree does not know how many
+ * cells precede it in pre-order, so it also records the largest count it checked (resolved by the copy kernel) */
+#define PIP_NEED(x) do { const int need_ = ncell + (x); if (STEAL) hwm = need_ > hwm ? need_ : hwm; \
+                         if (need_ >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; } } while (0)
   V *ctx = (V *)(B + L.ctx);
   V *cut = (V *)(B + L.cut);
   const int cstride = L.cstride;
+
+  /* a donated subtree: no load, the state comes out of the donor's frame */
+  if (STEAL && resume) { Fr = resume; goto RESTORE; }
 
   /* ---- load: source/tab.c:222-248 (tab_get) + tab_simplify when an integer solution is wanted */
   {
@@ -1649,7 +1725,7 @@ SUB_DONE:
   {
     /* the sub-solve's transient cells count against SOL_SIZE (source/sol.c:96-100) */
     const int need = feasible ? 1 + 2 * T.nvar : 1;
-    if (ncell + need >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+    PIP_NEED(need);
     T = M;
     level = 0;
     if (ret_site == 0) {
@@ -1685,10 +1761,10 @@ AFTER_COMPA:
   }
   /* split, source/traiter.c:695-759 */
   {
-    const int np = T.nparm, ncol = T.nvar + np + 1, nl = T.nvar + T.ni;
+    const int np = T.nparm;
     if (nc >= L.crcap) { status = PIP_ST_CAPACITY; goto DONE; }
     if (np >= maxparm) { status = PIP_ST_FATAL + 2; goto DONE; }
-    if (ncell + np + 3 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+    PIP_NEED(np + 3);
     int *fl = pip_fl(B, T);
     const V *row = pip_row(B, T, PIP_LINK(fl[pivi]));
     V g = 0;
@@ -1732,7 +1808,7 @@ AFTER_COMPA:
       if (top + fsize > stk_cap) { status = PIP_ST_CAPACITY; goto DONE; }
       pip_i64 *F = stk + top;
       if (lane == 0) {
-        F[0] = T.nvar; F[1] = np; F[2] = T.ni; F[3] = nc; F[4] = pivi; F[5] = T.ldet;
+        F[0] = T.nvar; F[1] = np; F[2] = T.ni; F[3] = nc; F[4] = pivi; F[5] = T.ldet; F[6] = fsize;
         #pragma unroll 1
         for (int k = 0; k < PIP_MAX_DET; k++) F[8 + k] = B[T.det + k];
         F[fsize - 1] = fsize;
@@ -1741,6 +1817,7 @@ AFTER_COMPA:
       pip_copy_words(F + 12 + w1, B + L.ctx, w2);
       top += fsize;
     }
+    if (STEAL && stl) pip_offer_bottom(*stl, stl_problem, stl_seg, stk, top, top_base, my_offer);
     W::sync();
     if (lane == 0) fl[pivi] = PIP_MKFL(PIP_PLUS, PIP_LINK(fl[pivi]));
     W::sync();
@@ -1754,14 +1831,14 @@ AFTER_COMPA:
 NONNEG:
   if (level == 0 && !integer) {
     const int total = 1 + T.nvar * (T.nparm + 2);
-    if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+    PIP_NEED(total);
     if (wordmode) pip_emit_solution_words(B, T, wo);
     else wide = pip_emit_solution(B, T, out, ncell) || wide;
     ncell += total;
     nwords += T.nvar ? 4 + T.nvar * (2 * T.nparm + 4) : 5;
     if (dual) {
       const int dtotal = 1 + 2 * T.ni;
-      if (ncell + dtotal >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+      PIP_NEED(dtotal);
       wide = pip_emit_dual(B, T, (const int *)(B + L.total - (L.m.rcap + 1) / 2), out, ncell) || wide;
       ncell += dtotal;
     }
@@ -1808,7 +1885,7 @@ NONNEG:
         if (parm == -1) {
           /* add_parm_xx, source/integrer.c:156-227 */
           if (nc + 2 > L.crcap || np + 2 > cstride || ncol + 1 > T.stride) { status = PIP_ST_CAPACITY; goto DONE; }
-          if (ncell + np + 5 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+          PIP_NEED(np + 5);
           const V *c = cut + nvar;
           if (wordmode) {
             /* `rank deno VEC`: the new parameter's rank, its divisor, the np + 1 values of the form over 1 */
@@ -1879,14 +1956,14 @@ NONNEG:
     if (level) { feasible = (verdict == 0); goto SUB_DONE; }
     if (verdict == 0) {
       const int total = 1 + T.nvar * (T.nparm + 2);
-      if (ncell + total >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+      PIP_NEED(total);
       if (wordmode) pip_emit_solution_words(B, T, wo);
       else wide = pip_emit_solution(B, T, out, ncell) || wide;
       ncell += total;
       nwords += T.nvar ? 4 + T.nvar * (2 * T.nparm + 4) : 5;
       PIP_LAP(st, PIP_PH_EMIT);
     } else {
-      if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+      PIP_NEED(1);
       if (wordmode) pip_wnode_kind(wo, 0);
       else if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
       ncell += 1;
@@ -1902,7 +1979,7 @@ PIVOT:
     if (rc == 0) goto LOOP;
     if (rc > 0) { status = rc; goto DONE; }
     if (level) { feasible = false; goto SUB_DONE; }
-    if (ncell + 1 >= sol_size) { status = PIP_ST_FATAL + 26; goto DONE; }
+    PIP_NEED(1);
     if (wordmode) pip_wnode_kind(wo, 0);
     else if (lane == 0) pip_put(out, ncell, PIP_C_NIL, 0, 0);
     ncell += 1;
@@ -1912,35 +1989,67 @@ PIVOT:
 LEAF:
   /* a branch of the main problem is finished: resume the innermost pending ELSE branch
    * (source/traiter.c:747-758) or stop */
-  if (depth == 0) goto DONE;
+  if (STEAL ? top == top_base : depth == 0) goto DONE;
   {
     W::sync();
     const pip_i64 fsize = stk[top - 1];
-    const pip_i64 *F = stk + (top - fsize);
-    T.nvar = (int)F[0]; T.nparm = (int)F[1]; T.ni = (int)F[2]; nc = (int)F[3]; pivi = (int)F[4]; T.ldet = (int)F[5];
+    if (STEAL && my_offer >= 0 && top - fsize == top_base) {
+      /* the frame on offer: take it back, unless an idle warp took it -- then that subtree is its segment */
+      int old = PIP_OFFER_OPEN;
+      if (lane == 0) old = W::atomic_cas(&stl->offers[my_offer].state, PIP_OFFER_OPEN, PIP_OFFER_RECLAIMED);
+      old = W::shfl(old, 0);
+      const int idx_ = my_offer;
+      my_offer = -1;
+      if (old != PIP_OFFER_OPEN) { pip_offer_wait_copied(*stl, idx_); goto DONE; }
+    }
+    Fr = stk + (top - fsize);
+    top -= fsize;
+    depth--;
+  }
+
+RESTORE:
+  {
+    const pip_i64 *F = Fr;
+#define PIP_FW(i) (STEAL ? W::load_cg(F + (i)) : F[i])      /* a donated frame was written by another SM */
+    T.nvar = (int)PIP_FW(0); T.nparm = (int)PIP_FW(1); T.ni = (int)PIP_FW(2); nc = (int)PIP_FW(3); pivi = (int)PIP_FW(4);
+    T.ldet = (int)PIP_FW(5);
     const int np = T.nparm;
     int *fl = pip_fl(B, T);
-    if (lane == 0) for (int k = 0; k < PIP_MAX_DET; k++) B[T.det + k] = F[8 + k];
+    if (lane == 0) for (int k = 0; k < PIP_MAX_DET; k++) B[T.det + k] = PIP_FW(8 + k);
+#undef PIP_FW
     const int w1 = (T.data - T.den) + (int)PIP_VW((pip_i64)T.ni * T.stride);
-    pip_copy_words(B + T.den, F + 12, w1);
-    pip_copy_words(B + L.ctx, F + 12 + w1, (int)PIP_VW((pip_i64)(nc + 1) * cstride));
+    if (STEAL) {
+      pip_copy_frame_in(B + T.den, F + 12, w1);
+      pip_copy_frame_in(B + L.ctx, F + 12 + w1, (int)PIP_VW((pip_i64)(nc + 1) * cstride));
+    } else {
+      pip_copy_words(B + T.den, F + 12, w1);
+      pip_copy_words(B + L.ctx, F + 12 + w1, (int)PIP_VW((pip_i64)(nc + 1) * cstride));
+    }
     W::sync();
     #pragma unroll 1
     for (int j = lane; j <= np; j += 32) {                 /* the negated condition */
       V v = ctx[nc * cstride + j];
       ctx[nc * cstride + j] = (j < np) ? -v : -(v + 1);
     }
-    top -= fsize;
-    depth--;
     W::sync();
     if (lane == 0) fl[pivi] = PIP_MKFL(PIP_MINUS, PIP_LINK(fl[pivi]));
     W::sync();
+    if (STEAL && resume && Fr == resume && stl && lane == 0) {     /* a donated frame: the donor may have its stack back */
+      W::fence();
+      W::atomic_exch(&stl->offers[stl_seg].state, PIP_OFFER_COPIED);
+    }
     nc++;
     PIP_LAP(st, PIP_PH_FRAME);
     goto PIVOT;
   }
 
 DONE:
+  if (STEAL && my_offer >= 0) {
+    int old = PIP_OFFER_OPEN;
+    if (lane == 0) old = W::atomic_cas(&stl->offers[my_offer].state, PIP_OFFER_OPEN, PIP_OFFER_RECLAIMED);
+    if (W::shfl(old, 0) != PIP_OFFER_OPEN) pip_offer_wait_copied(*stl, my_offer);
+  }
+  if (hwm_out) *hwm_out = hwm;
   W::sync();
   PIP_LAP(st, PIP_PH_OTHER);
   status_out = status;

@@ -141,6 +141,40 @@ typedef struct PipLayout {
   int total;
 } PipLayout;
 
+/* ---- subtree donation (independent subtrees of one problem's parametric tree) ----------------
+ * At a split the ELSE continuation is a self-contained work item: a snapshot of the tableau and the context
+ * in the warp's frame stack (source/traiter.c:717,741-758: THEN runs on a copy, ELSE continues in the frame).
+ * A warp that sees idle warps OFFERS the bottom frame of its stack -- the ELSE branch of its outermost open
+ * split; everything the donor still does precedes that subtree in pre-order.  An idle warp CLAIMS the offer
+ * (compare-and-swap on its state), restores the frame from the donor's stack, solves the subtree into its own
+ * window as a new SEGMENT of the problem's stream and links the segment right after the donor's (so later,
+ * inner donations of the same donor come before earlier, outer ones: pre-order).  An offer nobody claimed is
+ * reclaimed by its owner when it gets there.  The copy kernel walks the segment list: first fatal verdict in
+ * pre-order wins, the exit(26) cell limit is resolved from per-segment high-water marks, CAPACITY / WIDEN in
+ * any segment re-runs the whole problem one class up. */
+typedef struct {
+  int problem;                   /* index into prob / res */
+  int parent_seg;                /* the donor's segment: -1 = the problem's own (head) segment, else an offer index */
+  int state;                     /* PIP_OFFER_* */
+  int pad;
+  const pip_i64 *frame;          /* the ELSE continuation in the donor's frame stack */
+} PipOffer;
+enum { PIP_OFFER_NONE = 0, PIP_OFFER_OPEN = 1, PIP_OFFER_CLAIMED = 2, PIP_OFFER_RECLAIMED = 3,
+       PIP_OFFER_COPIED = 4 };      /* the thief has the frame in its own arena: the donor may reuse its stack */
+enum { PIP_STL_OFFERS = 0, PIP_STL_IDLE = 1, PIP_STL_TOTAL = 2, PIP_STL_CURSOR = 3, PIP_STL_CLAIMS = 4, PIP_STL_NCTL = 8 };
+typedef struct {
+  int mode;                      /* 0 off; 1 on; 2 test: every offer is taken by its owner once it finished
+                                    its own problem (exercises the whole splice on one warp, emulator) */
+  int cap;                       /* offers = segments (a claimed offer becomes the segment of the same index) */
+  PipOffer *offers;
+  unsigned *ctl;                 /* [PIP_STL_*]: offers published, idle warps, warps of the launch, test cursor */
+  PipResult *segs;               /* record of segment i (as PipResult: status, ncells, cell_off, counters, ser_words) */
+  int *seg_next;                 /* segment after segment i in pre-order, -1 = none */
+  int *seg_hwm;                  /* largest cell count segment i checked against SOL_SIZE (source/sol.c:96-100) */
+  int *head_next;                /* per problem: first donated segment after the head segment, -1 = none */
+  int *head_hwm;                 /* per problem: the head segment's high-water mark */
+} PipSteal;
+
 /* launch parameters of the warp-per-problem kernels */
 typedef struct {
   const PipProblem *prob;
@@ -162,6 +196,7 @@ typedef struct {
   int have_layout;               /* every problem of the launch has the shape `layout` was carved for (dense batches):
                                     the arena layout comes from the host, pip_layout does not run per problem */
   PipLayout layout;
+  PipSteal steal;                /* subtree donation (word mode only) */
   int emit_words;                /* word mode: PIP_F_SIMPLE_SER problems write their serialised quast (pip_solver.h) */
 } PipLaunch;
 

@@ -46,6 +46,14 @@ struct W {
   static inline long long shfl_xor64(long long v, int m) { return pipemu::shfl64(v, pipemu::lane() ^ m); }
   static inline int shfl_xor(int v, int m) { return (int)pipemu::shfl64(v, pipemu::lane() ^ m); }
   static inline unsigned atomic_add(unsigned *p, unsigned v) { return pipemu::atomic_add(p, v); }
+  /* (called by one lane at a time: the emulated warp is cooperative fibers, nothing runs in between) */
+  static inline int atomic_cas(int *p, int expect, int v) { const int o = *p; if (o == expect) *p = v; return o; }
+  static inline int atomic_exch(int *p, int v) { const int o = *p; *p = v; return o; }
+  static inline int load_volatile(const int *p) { return *p; }
+  static inline unsigned load_volatile(const unsigned *p) { return *p; }
+  static inline long long load_cg(const long long *p) { return *p; }
+  static inline void fence() {}
+  static inline void nap() {}
 };
 
 /* CTA / grid abstraction of the large-tableau kernel: in emulation one CTA of one warp */
@@ -119,6 +127,13 @@ struct W {
   static __device__ __forceinline__ long long shfl_xor64(long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
   static __device__ __forceinline__ int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
   static __device__ __forceinline__ unsigned atomic_add(unsigned *p, unsigned v) { return atomicAdd(p, v); }
+  static __device__ __forceinline__ int atomic_cas(int *p, int expect, int v) { return atomicCAS(p, expect, v); }
+  static __device__ __forceinline__ int atomic_exch(int *p, int v) { return atomicExch(p, v); }
+  static __device__ __forceinline__ int load_volatile(const int *p) { return *(const volatile int *)p; }
+  static __device__ __forceinline__ unsigned load_volatile(const unsigned *p) { return *(const volatile unsigned *)p; }
+  static __device__ __forceinline__ long long load_cg(const long long *p) { return __ldcg(p); }   /* past the L1: written by another SM */
+  static __device__ __forceinline__ void fence() { __threadfence(); }
+  static __device__ __forceinline__ void nap() { __nanosleep(200); }
 };
 
 struct G {

@@ -57,6 +57,29 @@ def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_le
     return out
 
 
+def solve_tableau_cases_steal(cases, work_words=1 << 16, stack_words=1 << 20, slack_level=2, order_mode=0, narrow=0,
+                              sol_size=0):
+    """word mode with subtree donation in test mode (PipSteal mode 2): every outermost ELSE branch becomes a
+    separate segment solved after the donor finished; returns [(status, words, record, segments)]"""
+    lib = C.CDLL(SO)
+    probs, pool = pack_tableau_problems(cases)
+    probs["flags"] |= 8
+    n = len(probs)
+    res = np.zeros(n, dtype=RESULT_DTYPE)
+    cap = 4096 * 64
+    cells = np.zeros(cap, dtype=CELL_DTYPE)
+    wcap = 1 << 22
+    words = np.zeros(wcap, dtype=np.int64)
+    woff = np.zeros(n + 1, dtype=np.int64)
+    nsegs = np.zeros(n, dtype=np.int32)
+    lib.pipemu_solve_batch_steal(probs.ctypes.data_as(C.c_void_p), n, pool.ctypes.data_as(C.c_void_p),
+                                 res.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p), C.c_longlong(cap),
+                                 work_words, C.c_longlong(stack_words), slack_level, order_mode, sol_size, narrow,
+                                 words.ctypes.data_as(C.c_void_p), C.c_longlong(wcap), woff.ctypes.data_as(C.c_void_p),
+                                 nsegs.ctypes.data_as(C.c_void_p))
+    return [(int(res[i]["status"]), [int(x) for x in words[woff[i]:woff[i + 1]]], res[i], int(nsegs[i])) for i in range(n)]
+
+
 def solve_large(case, cut_rows=64, sol_size=0, maxcol=0, order_mode=0, staged=0):
     """one non-parametric problem through the grid-per-problem code path (one emulated CTA)"""
     assert case["nparm"] == 0

@@ -10,12 +10,14 @@ void run_warp(void (*fn)(void *, int), void *arg);
 void set_order(int mode);
 }
 
-struct EmuArgs { PipLaunch L; pip_i64 *arena; int narrow; };
+struct EmuArgs { PipLaunch L; pip_i64 *arena; int narrow; int steal; };
 
 static void warp_entry(void *a, int)
 {
   EmuArgs *e = (EmuArgs *)a;
-  if (e->narrow == 2) pip_warp_main<pip_i64, true>(e->L, 0, e->arena, nullptr);   // the global-memory code path (classes G / M)
+  if (e->steal && e->narrow) pip_warp_main<int, false, true>(e->L, 0, e->arena);
+  else if (e->steal) pip_warp_main<pip_i64, false, true>(e->L, 0, e->arena);
+  else if (e->narrow == 2) pip_warp_main<pip_i64, true>(e->L, 0, e->arena, nullptr);   // the global-memory code path (classes G / M)
   else if (e->narrow) pip_warp_main<int>(e->L, 0, e->arena);
   else pip_warp_main<pip_i64>(e->L, 0, e->arena);
 }
@@ -47,6 +49,78 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
   pipemu::run_warp(warp_entry, &e);
   free(e.arena);
   free(e.L.stack);
+  return 0;
+}
+
+// ---- subtree donation in emulation (PipSteal mode 2): one warp offers the ELSE branch of every outermost open
+// split, finishes its own part, then solves the offered subtrees itself as separate segments; the segment walk
+// of the copy kernel (pip_segments.h) resolves the verdict and the words are concatenated in pre-order
+#include "../../piplib_b200/csrc/pip_segments.h"
+extern "C" int pipemu_solve_batch_steal(const PipProblem *prob, int nprob, const pip_i64 *pool, PipResult *res,
+                                        PipCell *cells, long long cells_cap, int work_words, long long stack_words,
+                                        int slack_level, int order_mode, int sol_size, int narrow,
+                                        long long *words_out, long long words_cap, long long *words_off, int *nsegs)
+{
+  EmuArgs e;
+  unsigned queue[2] = {0, 0};
+  memset(&e, 0, sizeof e);
+  e.L.prob = prob; e.L.pool = pool; e.L.pool_elem_log2 = 3; e.L.order = 0; e.L.nprob = nprob; e.L.res = res;
+  e.L.cells = cells; e.L.cells_per_warp = cells_cap;
+  e.L.stack = (pip_i64 *)malloc(sizeof(pip_i64) * stack_words);
+  e.L.stack_words_per_warp = stack_words;
+  e.L.gwork = 0; e.L.work_words = work_words; e.L.queue = queue;
+  e.L.sol_size = sol_size > 0 ? sol_size : PIP_SOL_SIZE;
+  e.L.maxcol = PIP_MAXCOL; e.L.maxparm = PIP_MAXPARM;
+  e.L.slack_level = slack_level;
+  e.L.emit_words = 1;
+  PipSteal &S = e.L.steal;
+  e.steal = 1;
+  S.mode = 2; S.cap = 1 << 16;
+  S.offers = (PipOffer *)calloc(S.cap, sizeof(PipOffer));
+  unsigned ctl[PIP_STL_NCTL] = {0};
+  ctl[PIP_STL_TOTAL] = 1;
+  S.ctl = ctl;
+  S.segs = (PipResult *)calloc(S.cap, sizeof(PipResult));
+  S.seg_next = (int *)malloc(sizeof(int) * S.cap);
+  S.seg_hwm = (int *)calloc(S.cap, sizeof(int));
+  S.head_next = (int *)malloc(sizeof(int) * (nprob + 1));
+  S.head_hwm = (int *)calloc(nprob + 1, sizeof(int));
+  for (int i = 0; i < S.cap; i++) S.seg_next[i] = -1;
+  for (int i = 0; i < nprob; i++) S.head_next[i] = -1;
+  e.narrow = narrow;
+  e.arena = (pip_i64 *)malloc(sizeof(pip_i64) * (size_t)work_words);
+  memset(e.arena, 0x5a, sizeof(pip_i64) * (size_t)work_words);
+  for (int i = 0; i < nprob; i++) res[i].status = PIP_ST_PENDING;
+  pipemu::set_order(order_mode);
+  /* a frame stack per problem would be the GPU's (one per warp, reused): here the single warp's stack is reused
+   * by the next problem while offers still point into it, so every problem is run with its offers drained:
+   * the queue hands out one problem at a time */
+  long long at = 0;
+  for (int i = 0; i < nprob; i++) {
+    queue[0] = (unsigned)i;
+    e.L.nprob = i + 1;
+    pipemu::run_warp(warp_entry, &e);
+    PipResolved R;
+    pip_resolve_segments(res[i], S.head_next[i], S, e.L.sol_size, R);
+    words_off[i] = at;
+    nsegs[i] = R.nseg;
+    res[i].status = R.status;
+    res[i].pivots = (unsigned)R.pivots; res[i].cuts = (unsigned)R.cuts; res[i].subsolves = (unsigned)R.subsolves;
+    res[i].splits = (unsigned)R.splits; res[i].ncells = (int)R.cells;
+    if (R.status == PIP_ST_OK || R.status == PIP_ST_VOID) {
+      int seg = -1;
+      for (;;) {
+        const PipResult sr = seg < 0 ? res[i] : S.segs[seg];
+        const long long n = seg < 0 && S.head_next[i] >= 0 ? (long long)sr.ser_words : (long long)sr.ser_words;
+        const void *src = (const void *)(cells + sr.cell_off);
+        for (long long k = 0; k < n && at < words_cap; k++) words_out[at++] = narrow == 1 ? (long long)((const int *)src)[k] : ((const long long *)src)[k];
+        seg = seg < 0 ? S.head_next[i] : S.seg_next[seg];
+        if (seg < 0) break;
+      }
+    }
+  }
+  words_off[nprob] = at;
+  free(e.arena); free(e.L.stack); free(S.offers); free(S.segs); free(S.seg_next); free(S.seg_hwm); free(S.head_next); free(S.head_hwm);
   return 0;
 }
 

@@ -249,3 +249,39 @@ def test_word_mode_equals_cells_then_decode(narrow):
         checked += 1
     assert not bad, bad[:6]
     assert checked > 600
+
+
+@pytest.mark.parametrize("narrow", [0, 1])
+def test_subtree_donation_splices_to_the_same_stream(narrow):
+    """subtree donation in test mode (PipSteal mode 2, pip_types.h): the ELSE branch of every outermost open
+    split is published as an offer, the donor finishes its own part, the offered subtrees are then solved as
+    separate segments (which donate in turn) and the segment walk of the copy kernel (pip_segments.h)
+    splices them in pre-order.  The resulting stream, status and counters must be those of the undonated
+    solve -- parametric fixtures, random tableaus, bench workloads, and a tight SOL_SIZE that makes the
+    cell limit fall into donated segments."""
+    from workloads import synth
+    cases = [c for c in CLI + RCLI if c["nparm"] > 0 and c["name"] not in HEAVY]
+    for wl, n in (("loopnest16x24p3", 120), ("loopnest8x12p2", 200), ("sor1d", 100), ("fimmel", 30)):
+        dom, ctx = synth.generate(wl, n, seed=29)
+        cases += _dense_to_cases(dom, ctx)
+    for sol_size in (0, 160):
+        a = emu.solve_tableau_cases_steal(cases, slack_level=3, work_words=1 << 18, order_mode=2, narrow=narrow,
+                                          sol_size=sol_size)
+        b = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=0, narrow=narrow,
+                                    emit_words=True, sol_size=sol_size)
+        bad, multi, fatal26 = [], 0, 0
+        for k, ((st, words, r, nseg), (st2, words2, r2, _)) in enumerate(zip(a, b)):
+            if st == 4003 or st2 == 4003:
+                if st != st2:
+                    bad.append((k, st, st2))
+                continue
+            if st != st2 or (st in (0, 1) and words != words2):
+                bad.append((k, st, st2, nseg, len(words), len(words2)))
+            elif st == 0 and any(int(r[x]) != int(r2[x]) for x in ("pivots", "cuts", "subsolves", "splits", "ncells")):
+                bad.append((k, "counters", nseg))
+            multi += nseg > 1
+            fatal26 += st == 1026
+        assert not bad, bad[:6]
+        assert multi > 150, multi
+        if sol_size:
+            assert fatal26 > 20, fatal26
