@@ -1563,6 +1563,9 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
    * the constraint range and reads ineq[] entries it never wrote (source/traiter.c:585 vs 616-617),
    * so its answer is undefined; only the split-free case is implemented */
   if ((P.flags & PIP_F_DUAL) && (P.nparm > 0 || P.nc > 0)) { status_out = PIP_ST_UNSUPPORTED; ncell_out = 0; return; }
+  /* a big-parameter column outside the tableau (test/challenges/pipFile_1: column 12 of 12): the reference reads
+   * past the row (source/traiter.c:111) and its answer depends on the heap; refused instead of answered at random */
+  if (P.bigparm >= P.nvar + P.nparm + 1) { status_out = PIP_ST_UNSUPPORTED; ncell_out = 0; return; }
   /* the rarely-set options live in the global-memory instantiations only (TEAM), so that the code of
    * the instruction-supply-bound shared-memory kernels is not touched by them; a problem that asks
    * for one here is handed to the next class like any other that does not fit */

@@ -578,3 +578,14 @@ def test_subtree_donation_on_the_device(api, port, workload, n, monkeypatch):
     assert np.array_equal(st_g, st_o)
     ok = st_o == 0
     assert np.array_equal(r["hashes"][ok], h_o[ok])
+
+
+def test_big_parameter_column_outside_the_tableau_is_refused(api):
+    """test/challenges/pipFile_1 names big-parameter column 12 in a 12-column tableau: the reference reads past
+    the row end (source/traiter.c:111), so its answer depends on the heap layout.  The library refuses the
+    problem with status 4002 (PIP_STATUS_UNSUPPORTED) -- every time -- instead of answering at random."""
+    c = [x for x in load_golden("cli_suite.json") if "pipFile_1" in x["name"]]
+    assert len(c) == 1 and c[0]["bigparm"] >= c[0]["nvar"] + c[0]["nparm"] + 1
+    for _ in range(3):
+        (st, cells), = api.traiter_batch(c)
+        assert st == 4002 and cells == []
