@@ -94,6 +94,7 @@ struct PipEngine::Impl {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf d_prob, d_pool, d_res, d_cells, d_stack, d_gwork, d_queue, d_order, d_off, d_compact, d_total, d_prof, d_parm, d_hash;
   DevBuf d_so_status, d_so_hash, d_so_off, d_so_len, d_so_ctl;     /* stream_out: per-problem arrays, control + stats */
+  DevBuf d_image;                  /* arena images of a uniform batch (pip_image_kernel) */
   DevBuf d_stl_offers, d_stl_segs, d_stl_next, d_stl_hwm, d_stl_head_next, d_stl_head_hwm, d_stl_ctl;   /* subtree donation */
   DevBuf d_scratch[4];
   PinBuf h_scratch[4];
@@ -386,6 +387,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
   std::vector<int> order;
   order.reserve(n);
   int round = 0;
+  int image_vb = 0, image_elem = -1;     /* arena images built for this value width / pool */
   size_t open_total = n;                /* problems not final yet, all classes */
   for (int k = -2; k < N_G && open_total; k++) {
     int last_open = -1;                 /* problems of this class still open after the previous attempt */
@@ -481,6 +483,19 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       if (in.uniform && getenv("PIPLIB_B200_DEVICE_LAYOUT") == nullptr)
         L.have_layout = pip_layout_compute(in.uniform->nvar, in.uniform->nparm, in.uniform->ni, in.uniform->nc,
                                            in.uniform->flags, cs.level, (int)cs.words, cs.shared == 2 ? 4 : 8, &L.layout);
+      /* ... and run the problem load ahead of the solver: arena images, two block copies per problem in the kernel */
+      if (L.have_layout && k < 0 && getenv("PIPLIB_B200_NO_IMAGE") == nullptr) {
+        const int vb = cs.shared == 2 ? 4 : 8;
+        const long long w1 = (L.layout.m.data - L.layout.m.den) + ((long long)in.uniform->ni * L.layout.m.stride * vb + 7) / 8;
+        const long long w2 = ((long long)in.uniform->nc * L.layout.cstride * vb + 7) / 8;
+        if (image_vb != vb || image_elem != elem_log2) {
+          E.d_image.reserve((size_t)n * (size_t)(w1 + w2) * sizeof(pip_i64) + 64);
+          CK(pip_launch_image(d_prob, d_pool, elem_log2, (long long)n, &L.layout, (pip_i64 *)E.d_image.p, (int)(w1 + w2), (int)w1, vb, s));
+          out.times.launches++;
+          image_vb = vb; image_elem = elem_log2;
+        }
+        L.images = (const pip_i64 *)E.d_image.p; L.image_words = (int)(w1 + w2); L.image_w1 = (int)w1;
+      }
       double tk = now_s();
       /* PIPLIB_B200_LARGE_FROM=<class index> moves the hand-over (tests), a negative value disables it */
       const char *lf = getenv("PIPLIB_B200_LARGE_FROM");

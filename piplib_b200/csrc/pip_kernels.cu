@@ -141,6 +141,39 @@ extern "C" long long pip_layout_words(int nvar, int nparm, int ni, int nc, int f
   return L.total;
 }
 
+/* ---- arena images (dense batches): the problem load of the solver, run ahead of it ----------------------
+ * One warp per problem runs the solver's own loader (pip_load_problem: element widening, den / fl, tab_simplify)
+ * into the problem's image in global memory, laid out like the arena regions it stands for (offsets rebased to
+ * the image).  The solve kernel then starts every problem with two block copies, and the loader -- 270
+ * instructions that ran once per problem -- is out of its instruction stream. */
+template <class V>
+__global__ void __launch_bounds__(256) pip_image_kernel(const PipProblem *prob, const void *pool, int elem_log2, long long n,
+                                                        const PipLayout lay, pip_i64 *images, int image_words, int image_w1)
+{
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  PipLayout L = lay;
+  L.m.fl -= L.m.den; L.tmp -= L.m.den; L.m.data -= L.m.den; L.m.den = 0;
+  L.ctx = image_w1;
+  for (long long p = warp; p < n; p += nwarps) {
+    const PipProblem P = prob[p];
+    if (P.flags & PIP_F_WIDE_INPUT) continue;            /* solved from the int64 pool by the general loader */
+    L.m.ni = P.ni;
+    PipSolver<V>::pip_load_problem(P, pool, elem_log2, images + p * image_words, L);
+  }
+}
+
+extern "C" cudaError_t pip_launch_image(const PipProblem *prob, const void *pool, int elem_log2, long long n, const PipLayout *lay,
+                                        pip_i64 *images, int image_words, int image_w1, int vbytes, cudaStream_t stream)
+{
+  long long blocks = (n + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  if (vbytes == 4) pip_image_kernel<int><<<(int)blocks, 256, 0, stream>>>(prob, pool, elem_log2, n, *lay, images, image_words, image_w1);
+  else pip_image_kernel<pip_i64><<<(int)blocks, 256, 0, stream>>>(prob, pool, elem_log2, n, *lay, images, image_words, image_w1);
+  return cudaGetLastError();
+}
+
 /* the arena layout of a shape at a slack level, degraded exactly as the solver degrades it when the arena is
  * too small; out->s.ni carries nc + 1 (the largest context the layout was carved for).  0 = does not fit */
 extern "C" int pip_layout_compute(int nvar, int nparm, int ni, int nc, int flags, int level, int words, int vbytes,

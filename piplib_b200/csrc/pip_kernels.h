@@ -31,6 +31,8 @@ cudaError_t pip_launch_gather_words(PipResult *res, const int *order, const PipC
                                     cudaStream_t stream);
 cudaError_t pip_launch_init_results(PipResult *res, long long n, cudaStream_t stream);
 cudaError_t pip_launch_convert(const PipConvertArgs *A, int elem_log2, cudaStream_t stream);
+cudaError_t pip_launch_image(const PipProblem *prob, const void *pool, int elem_log2, long long n, const PipLayout *lay,
+                             pip_i64 *images, int image_words, int image_w1, int vbytes, cudaStream_t stream);
 int pip_layout_compute(int nvar, int nparm, int ni, int nc, int flags, int level, int words, int vbytes, PipLayout *out);
 long long pip_layout_words(int nvar, int nparm, int ni, int nc, int flags, int level, int vbytes);
 #ifdef __cplusplus

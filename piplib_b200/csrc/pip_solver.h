@@ -1528,6 +1528,37 @@ PIP_SDEVNI int pip_subsolve_regs(const V *ctx, int cstride, int nc, int np, cons
 #undef PIP_SUBREG_COMMIT
 }
 
+/* ---- problem load: source/tab.c:222-248 (tab_get) + tab_simplify when an integer solution is wanted ----
+ * Fills the arena regions a fresh problem consists of: den | fl of the nvar + ni positions, the ni stored rows,
+ * the nc context rows.  Runs inside the solver (general path) or, for dense batches, ahead of it in
+ * pip_image_kernel with B = the problem's ARENA IMAGE in global memory: the solver then starts from two block
+ * copies and none of this code is in its instruction stream.  Returns the int32 range flag of the loads. */
+PIP_SDEVNI unsigned pip_load_problem(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, const PipLayout &L)
+{
+  const int lane = W::lane();
+  const int ncol = P.nvar + P.nparm + 1;
+  const PipTab &T = L.m;
+  int *fl = pip_fl(B, T);
+  V *den = pip_den(B, T);
+  V *ctx = (V *)(B + L.ctx);
+  unsigned ovf = 0;
+  #pragma unroll 1
+  for (int k = lane; k < P.nvar + P.ni; k += 32) {
+    if (k < P.nvar) { fl[k] = PIP_MKFL(PIP_UNIT, k); den[k] = 1; }
+    else { fl[k] = PIP_MKFL(PIP_UNKNOWN, k - P.nvar); den[k] = 1; }
+  }
+  ovf |= pip_load2d((V *)(B + T.data), T.stride, pool, elem_log2, P.off, P.ni, ncol);
+  ovf |= pip_load2d(ctx, L.cstride, pool, elem_log2, P.off + (pip_i64)P.ni * ncol, P.nc, P.nparm + 1);
+  W::sync();
+  if (PipVal<V>::narrow && W::any(ovf != 0)) return 1u;
+  if (P.flags & PIP_F_INT) {
+    pip_simplify_rows((V *)(B + T.data), P.ni, T.stride, ncol, P.nvar);
+    pip_simplify_rows(ctx, P.nc, L.cstride, P.nparm + 1, P.nparm);
+    W::sync();
+  }
+  return 0u;
+}
+
 /* The solver for one problem.  `B` is the warp's working arena (`words` words), `out` the
  * warp's cell window (at least sol_size cells free), `stk` the warp's frame stack. */
 PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, int words, int slack_level,
@@ -1536,7 +1567,8 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
                            int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st, PipTeam *tm = nullptr,
                            unsigned *nwords_out = nullptr, bool wordmode = false, const PipLayout *pre = nullptr,
                            const PipSteal *stl = nullptr, int stl_problem = 0, int stl_seg = -1,
-                           const pip_i64 *resume = nullptr, int *hwm_out = nullptr)
+                           const pip_i64 *resume = nullptr, int *hwm_out = nullptr,
+                           const pip_i64 *image = nullptr, int image_w1 = 0)
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
@@ -1600,26 +1632,16 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
   /* a donated subtree: no load, the state comes out of the donor's frame */
   if (STEAL && resume) { Fr = resume; goto RESTORE; }
 
-  /* ---- load: source/tab.c:222-248 (tab_get) + tab_simplify when an integer solution is wanted */
-  {
-    const int ncol = P.nvar + P.nparm + 1;
-    int *fl = pip_fl(B, T);
-    V *den = pip_den(B, T);
-    #pragma unroll 1
-    for (int k = lane; k < P.nvar + P.ni; k += 32) {
-      if (k < P.nvar) { fl[k] = PIP_MKFL(PIP_UNIT, k); den[k] = 1; }
-      else { fl[k] = PIP_MKFL(PIP_UNKNOWN, k - P.nvar); den[k] = 1; }
-    }
-    ovf |= pip_load2d((V *)(B + T.data), T.stride, pool, elem_log2, P.off, P.ni, ncol);
-    ovf |= pip_load2d(ctx, cstride, pool, elem_log2, P.off + (pip_i64)P.ni * ncol, P.nc, P.nparm + 1);
+  /* ---- load: the arena image prepared by pip_image_kernel (two block copies), or the general loader */
+  if (image) {
+    pip_copy_words(B + T.den, image, (T.data - T.den) + (int)(((pip_i64)P.ni * T.stride * (pip_i64)sizeof(V) + 7) / 8));
+    pip_copy_words(B + L.ctx, image + image_w1, (int)(((pip_i64)P.nc * cstride * (pip_i64)sizeof(V) + 7) / 8));
     if (lane == 0) { B[L.m.det] = 1; B[L.s.det] = 1; }
     W::sync();
-    if (PipVal<V>::narrow && W::any(ovf != 0)) { status = PIP_ST_WIDEN; goto DONE; }
-    if (integer) {
-      pip_simplify_rows((V *)(B + T.data), P.ni, T.stride, ncol, P.nvar);
-      pip_simplify_rows(ctx, P.nc, cstride, P.nparm + 1, P.nparm);
-      W::sync();
-    }
+  } else {
+    if (pip_load_problem(P, pool, elem_log2, B, L)) { status = PIP_ST_WIDEN; goto DONE; }
+    if (lane == 0) { B[L.m.det] = 1; B[L.s.det] = 1; }
+    W::sync();
   }
 
   PIP_LAP(st, PIP_PH_LOAD);

@@ -196,6 +196,8 @@ typedef struct {
   int have_layout;               /* every problem of the launch has the shape `layout` was carved for (dense batches):
                                     the arena layout comes from the host, pip_layout does not run per problem */
   PipLayout layout;
+  const pip_i64 *images;         /* arena images of the problems (pip_image_kernel), indexed like prob, or NULL */
+  int image_words, image_w1;     /* words per image; words of its first region (tableau), the context follows */
   PipSteal steal;                /* subtree donation (word mode only) */
   int emit_words;                /* word mode: PIP_F_SIMPLE_SER problems write their serialised quast (pip_solver.h) */
 } PipLaunch;

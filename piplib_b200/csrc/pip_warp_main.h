@@ -33,7 +33,8 @@ PIP_DEV pip_i64 pip_warp_unit(const PipLaunch &L, int warp_id, pip_i64 *arena, P
   PipSolver<V, TEAM, STEAL>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
                 stk_cap, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm, &nwords,
                 wordmode, L.have_layout ? &L.layout : nullptr, stl, p, offer,
-                (STEAL && offer >= 0) ? L.steal.offers[offer].frame : nullptr, STEAL ? &hwm : nullptr);
+                (STEAL && offer >= 0) ? L.steal.offers[offer].frame : nullptr, STEAL ? &hwm : nullptr,
+                (L.images && L.have_layout) ? L.images + (pip_i64)p * L.image_words : nullptr, L.image_w1);
   if (lane == 0) {
     PipResult r;
     r.status = status; r.ncells = ncell;

@@ -57,6 +57,31 @@ def solve_tableau_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_le
     return out
 
 
+def solve_uniform_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_level=2, order_mode=0, narrow=0):
+    """a batch of ONE shape as the engine runs dense batches: arena layout carved once (PipLaunch::layout),
+    arena images built ahead of the solve by the solver's own loader, word mode.  [(status, words, record)]"""
+    lib = C.CDLL(SO)
+    probs, pool = pack_tableau_problems(cases)
+    probs["flags"] |= 8
+    n = len(probs)
+    res = np.zeros(n, dtype=RESULT_DTYPE)
+    cap = 4096 * (n + 1)
+    cells = np.zeros(cap, dtype=CELL_DTYPE)
+    lib.pipemu_solve_uniform(probs.ctypes.data_as(C.c_void_p), n, pool.ctypes.data_as(C.c_void_p),
+                             res.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p), C.c_longlong(cap),
+                             work_words, C.c_longlong(stack_words), slack_level, order_mode, narrow,
+                             int(max(c["ni"] for c in cases)), int(max(c["nc"] for c in cases)))
+    out = []
+    raw = cells.view(np.uint8)
+    for i in range(n):
+        r = res[i]
+        nw = int(r["ser_words"]) if int(r["status"]) in (0, 1) else 0
+        at = int(r["cell_off"]) * CELL_DTYPE.itemsize
+        w = raw[at:at + 4 * nw].view(np.int32).astype(np.int64) if narrow == 1 else raw[at:at + 8 * nw].view(np.int64)
+        out.append((int(r["status"]), [int(x) for x in w], r))
+    return out
+
+
 def solve_tableau_cases_steal(cases, work_words=1 << 16, stack_words=1 << 20, slack_level=2, order_mode=0, narrow=0,
                               sol_size=0):
     """word mode with subtree donation in test mode (PipSteal mode 2): every outermost ELSE branch becomes a

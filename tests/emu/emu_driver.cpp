@@ -52,6 +52,58 @@ extern "C" int pipemu_solve_batch(const PipProblem *prob, int nprob, const pip_i
   return 0;
 }
 
+// ---- a uniform (dense) batch as the engine runs it: arena layout carved once, arena images built ahead of the
+// solve by the solver's own loader, word mode
+template <class V> struct EmuImage { const PipProblem *prob; const pip_i64 *pool; int n; PipLayout L; pip_i64 *images; int words; };
+template <class V> static void image_entry(void *a, int)
+{
+  EmuImage<V> *e = (EmuImage<V> *)a;
+  for (int p = 0; p < e->n; p++) {
+    PipLayout L = e->L;
+    L.m.ni = e->prob[p].ni;
+    PipSolver<V>::pip_load_problem(e->prob[p], e->pool, 3, e->images + (size_t)p * e->words, L);
+  }
+}
+extern "C" int pipemu_solve_uniform(const PipProblem *prob, int nprob, const pip_i64 *pool, PipResult *res,
+                                    PipCell *cells, long long cells_cap, int work_words, long long stack_words,
+                                    int slack_level, int order_mode, int narrow, int max_ni, int max_nc)
+{
+  EmuArgs e;
+  unsigned queue[2] = {0, 0};
+  memset(&e, 0, sizeof e);
+  e.L.prob = prob; e.L.pool = pool; e.L.pool_elem_log2 = 3; e.L.order = 0; e.L.nprob = nprob; e.L.res = res;
+  e.L.cells = cells; e.L.cells_per_warp = cells_cap;
+  e.L.stack = (pip_i64 *)malloc(sizeof(pip_i64) * stack_words);
+  e.L.stack_words_per_warp = stack_words;
+  e.L.gwork = 0; e.L.work_words = work_words; e.L.queue = queue;
+  e.L.sol_size = PIP_SOL_SIZE; e.L.maxcol = PIP_MAXCOL; e.L.maxparm = PIP_MAXPARM;
+  e.L.slack_level = slack_level;
+  e.L.emit_words = 1;
+  const int vb = narrow ? 4 : 8;
+  int level = slack_level;
+  while (!pip_layout(prob[0].nvar, prob[0].nparm, max_ni, max_nc, prob[0].flags, level, work_words, vb, e.L.layout)) level--;
+  e.L.layout.s.ni = max_nc + 1;
+  e.L.have_layout = 1;
+  const PipLayout &Y = e.L.layout;
+  const int w1 = (Y.m.data - Y.m.den) + (int)(((long long)max_ni * Y.m.stride * vb + 7) / 8);
+  const int w2 = (int)(((long long)max_nc * Y.cstride * vb + 7) / 8);
+  pip_i64 *images = (pip_i64 *)malloc(sizeof(pip_i64) * (size_t)nprob * (w1 + w2) + 64);
+  memset(images, 0x6b, sizeof(pip_i64) * (size_t)nprob * (w1 + w2));
+  PipLayout R = Y;
+  R.m.fl -= R.m.den; R.tmp -= R.m.den; R.m.data -= R.m.den; R.m.den = 0; R.ctx = w1;
+  pipemu::set_order(order_mode);
+  if (narrow) { EmuImage<int> im = {prob, pool, nprob, R, images, w1 + w2}; pipemu::run_warp(image_entry<int>, &im); }
+  else { EmuImage<pip_i64> im = {prob, pool, nprob, R, images, w1 + w2}; pipemu::run_warp(image_entry<pip_i64>, &im); }
+  e.L.images = images; e.L.image_words = w1 + w2; e.L.image_w1 = w1;
+  e.narrow = narrow;
+  e.arena = (pip_i64 *)malloc(sizeof(pip_i64) * (size_t)work_words);
+  memset(e.arena, 0x5a, sizeof(pip_i64) * (size_t)work_words);
+  for (int i = 0; i < nprob; i++) res[i].status = PIP_ST_PENDING;
+  pipemu::run_warp(warp_entry, &e);
+  free(e.arena); free(e.L.stack); free(images);
+  return 0;
+}
+
 // ---- subtree donation in emulation (PipSteal mode 2): one warp offers the ELSE branch of every outermost open
 // split, finishes its own part, then solves the offered subtrees itself as separate segments; the segment walk
 // of the copy kernel (pip_segments.h) resolves the verdict and the words are concatenated in pre-order

@@ -285,3 +285,27 @@ def test_subtree_donation_splices_to_the_same_stream(narrow):
         assert multi > 150, multi
         if sol_size:
             assert fatal26 > 20, fatal26
+
+
+@pytest.mark.parametrize("narrow", [0, 1])
+def test_uniform_batch_layout_and_arena_images(narrow):
+    """a dense batch as the engine runs it -- arena layout carved once for the largest row counts, arena images
+    built ahead of the solve by the solver's own loader (pip_load_problem), two block copies per problem in the
+    solver -- against the general path (layout and load per problem): same words, statuses, counters.  The
+    batches mix problems with and without equality rows, so images are smaller than the layout's row count."""
+    from workloads import synth
+    for wl, n in (("loopnest16x24p3", 150), ("loopnest8x12p2", 250), ("sor1d", 150), ("fimmel", 40)):
+        dom, ctx = synth.generate(wl, n, seed=43)
+        if wl == "loopnest8x12p2":
+            dom = dom.copy()
+            dom[::3, 1, 0] = 0                      # every third problem: one equality (an extra tableau row)
+        cases = _dense_to_cases(dom, ctx)
+        a = emu.solve_uniform_cases(cases, slack_level=3, work_words=1 << 18, order_mode=2, narrow=narrow)
+        b = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=0, narrow=narrow, emit_words=True)
+        bad = []
+        for k, ((st, words, r), (st2, words2, r2, _)) in enumerate(zip(a, b)):
+            if st != st2 or (st in (0, 1) and words != words2):
+                bad.append((wl, k, st, st2))
+            elif st == 0 and any(int(r[x]) != int(r2[x]) for x in ("pivots", "cuts", "subsolves", "splits", "ncells")):
+                bad.append((wl, k, "counters"))
+        assert not bad, bad[:6]
