@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) pip_image_kernel(const PipProblem *prob, 
     const PipProblem P = prob[p];
     if (P.flags & PIP_F_WIDE_INPUT) continue;            /* solved from the int64 pool by the general loader */
     L.m.ni = P.ni;
-    PipSolver<V>::pip_load_problem(P, pool, elem_log2, images + p * image_words, L);
+    PipSolver<V>::pip_load_problem(P, pool, elem_log2, images + p * image_words, L.m, L.ctx, L.cstride);
   }
 }
 

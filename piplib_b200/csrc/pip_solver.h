@@ -1533,14 +1533,14 @@ PIP_SDEVNI int pip_subsolve_regs(const V *ctx, int cstride, int nc, int np, cons
  * the nc context rows.  Runs inside the solver (general path) or, for dense batches, ahead of it in
  * pip_image_kernel with B = the problem's ARENA IMAGE in global memory: the solver then starts from two block
  * copies and none of this code is in its instruction stream.  Returns the int32 range flag of the loads. */
-PIP_SDEVNI unsigned pip_load_problem(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, const PipLayout &L)
+PIP_SDEVNI unsigned pip_load_problem(const PipProblem &P, const void *pool, int elem_log2, pip_i64 *B, const PipTab T,
+                                     int ctx_off, int cstride)
 {
   const int lane = W::lane();
   const int ncol = P.nvar + P.nparm + 1;
-  const PipTab &T = L.m;
   int *fl = pip_fl(B, T);
   V *den = pip_den(B, T);
-  V *ctx = (V *)(B + L.ctx);
+  V *ctx = (V *)(B + ctx_off);
   unsigned ovf = 0;
   #pragma unroll 1
   for (int k = lane; k < P.nvar + P.ni; k += 32) {
@@ -1548,12 +1548,12 @@ PIP_SDEVNI unsigned pip_load_problem(const PipProblem &P, const void *pool, int 
     else { fl[k] = PIP_MKFL(PIP_UNKNOWN, k - P.nvar); den[k] = 1; }
   }
   ovf |= pip_load2d((V *)(B + T.data), T.stride, pool, elem_log2, P.off, P.ni, ncol);
-  ovf |= pip_load2d(ctx, L.cstride, pool, elem_log2, P.off + (pip_i64)P.ni * ncol, P.nc, P.nparm + 1);
+  ovf |= pip_load2d(ctx, cstride, pool, elem_log2, P.off + (pip_i64)P.ni * ncol, P.nc, P.nparm + 1);
   W::sync();
   if (PipVal<V>::narrow && W::any(ovf != 0)) return 1u;
   if (P.flags & PIP_F_INT) {
     pip_simplify_rows((V *)(B + T.data), P.ni, T.stride, ncol, P.nvar);
-    pip_simplify_rows(ctx, P.nc, L.cstride, P.nparm + 1, P.nparm);
+    pip_simplify_rows(ctx, P.nc, cstride, P.nparm + 1, P.nparm);
     W::sync();
   }
   return 0u;
@@ -1576,7 +1576,8 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
   wo.w = (V *)out; wo.pos = 0; wo.node_at = -1; wo.nnew = 0; wo.wide = false;
   PipLayout L;
   /* dense batches: one shape for the whole launch, the arena was carved once on the host (`pre`, for the
-   * largest row counts of the batch; capacities only ever decide CAPACITY, never an answer) */
+   * largest row counts of the batch; capacities only ever decide CAPACITY, never an answer).  (Copied into
+   * registers: reading it in place through a pointer put every access into local memory -- 130 -> 153 ms.) */
   if (pre && pre->m.nvar == P.nvar && pre->m.nparm == P.nparm && P.ni <= pre->m.ni && P.nc + 1 <= pre->s.ni) {
     L = *pre;
     L.m.ni = P.ni;
@@ -1639,7 +1640,7 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
     if (lane == 0) { B[L.m.det] = 1; B[L.s.det] = 1; }
     W::sync();
   } else {
-    if (pip_load_problem(P, pool, elem_log2, B, L)) { status = PIP_ST_WIDEN; goto DONE; }
+    if (pip_load_problem(P, pool, elem_log2, B, T, L.ctx, cstride)) { status = PIP_ST_WIDEN; goto DONE; }
     if (lane == 0) { B[L.m.det] = 1; B[L.s.det] = 1; }
     W::sync();
   }
@@ -1683,7 +1684,11 @@ BUILD_SUB:
       sfl[k] = k < np ? PIP_MKFL(PIP_UNIT, k) : PIP_MKFL(PIP_UNKNOWN, k - np);
       sden[k] = 1;
     }
-    pip_copy2d((V *)(B + S.data), S.stride, ctx, cstride, nc, np + 1);
+    /* the sub tableau's rows have the context's stride (pip_layout: both XC), so the nc context rows are one
+     * block of arena words (an odd count of int32 values spills one value into the slot of row nc, which is
+     * written next or never read) */
+    pip_copy_words(B + S.data, B + L.ctx, (int)(((pip_i64)nc * cstride * (pip_i64)sizeof(V) + 7) / 8));
+    if (sizeof(V) < 8) W::sync();             /* (the spilled value and the tested row's first entry share a word) */
     if (extra) {
       const int f = pip_fl(B, M)[ci];
       const V *row = pip_row(B, M, PIP_LINK(f));

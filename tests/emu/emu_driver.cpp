@@ -61,7 +61,7 @@ template <class V> static void image_entry(void *a, int)
   for (int p = 0; p < e->n; p++) {
     PipLayout L = e->L;
     L.m.ni = e->prob[p].ni;
-    PipSolver<V>::pip_load_problem(e->prob[p], e->pool, 3, e->images + (size_t)p * e->words, L);
+    PipSolver<V>::pip_load_problem(e->prob[p], e->pool, 3, e->images + (size_t)p * e->words, L.m, L.ctx, L.cstride);
   }
 }
 extern "C" int pipemu_solve_uniform(const PipProblem *prob, int nprob, const pip_i64 *pool, PipResult *res,
