@@ -1262,7 +1262,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
                                                               (nchunks + devices.size() - 1) / devices.size()));
     const size_t nworkers = lanes * devices.size();
     /* host threads per lane: the lanes' conversion / copy-out phases overlap, so each gets a share */
-    const size_t nthreads = std::max<size_t>(1, (host_threads() + nworkers - 1) / nworkers);
+    const size_t nthreads_default = std::max<size_t>(1, (host_threads() + nworkers - 1) / nworkers);
     std::vector<size_t> firsts(nchunks + 1, 0);
     for (size_t c = 0; c < nchunks; c++) firsts[c + 1] = firsts[c] + sizes[c];
     std::vector<std::string> errors(nworkers);
@@ -1292,9 +1292,21 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     }
     (void)sol_flags0;
 
+    /* Mixed input routes (PIPLIB_B200_HOST_LANES=k, default 0): with pinned input, k of the lanes narrow their
+     * chunks on the host instead (0.5 KB per problem over the link instead of 4.2 KB) and pull from the same
+     * chunk queue.  Measured on a box whose link does 55 GB/s each way: no gain (the upload is not what bounds
+     * the call), so it is off; a box with a slower link may want it. */
+    size_t host_lanes = 0;
+    if (in_pinned) {
+      if (const char *hv = getenv("PIPLIB_B200_HOST_LANES")) host_lanes = (size_t)std::max(0, atoi(hv));
+      host_lanes = std::min<size_t>(host_lanes, lanes > 1 ? lanes - 1 : 0);
+    }
     auto worker_main = [&](size_t w) {
       try {
         const int device = devices[w / lanes];
+        const bool lane_dma = in_pinned && (w % lanes) >= host_lanes;
+        const size_t nthreads = (in_pinned && !lane_dma) ? std::max<size_t>(1, host_threads() / std::max<size_t>(1, host_lanes * devices.size()))
+                                                          : nthreads_default;
         PipEngine &E = PipEngine::at(device, (int)(w % lanes));
         cudaStream_t s = E.stream();
         pip_cuda_check(cudaSetDevice(device), "cudaSetDevice");
@@ -1313,7 +1325,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
           PipProblem uniform;
           struct WidenCtx { PipConvertArgs a; void *pool64; } wc;
           wc.pool64 = nullptr;
-          if (in_pinned) {
+          if (lane_dma) {
             /* ---- DMA the raw rows up, convert on the device ---- */
             const size_t dwords = (size_t)A.dr * A.dc, cwords = CS.has_ctx ? (size_t)A.cr * A.cc : 0;
             pip_i64 *d_dom = (pip_i64 *)E.device_scratch(0, std::max<size_t>(cn * dwords * 8, 8));
@@ -1457,8 +1469,8 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
       for (size_t l = 0; l < nworkers; l++)
         fprintf(stderr, "[piplib-b200] device %d lane %zu: plan %.3f convert %.3f run %.3f emit %.3f s\n", devices[l / lanes], l % lanes,
                 tstage[l * 4], tstage[l * 4 + 1], tstage[l * 4 + 2], tstage[l * 4 + 3]);
-      fprintf(stderr, "[piplib-b200] total %.3f s, %zu chunks, %zu devices x %zu lanes, %zu host threads per lane (pool %u), input %s, output %s\n",
-              wall() - t0, nchunks, devices.size(), lanes, nthreads, host_threads(),
+      fprintf(stderr, "[piplib-b200] total %.3f s, %zu chunks, %zu devices x %zu lanes (%zu of them convert on the host), pool %u, input %s, output %s\n",
+              wall() - t0, nchunks, devices.size(), lanes, in_pinned ? host_lanes : lanes, host_threads(),
               in_pinned ? "pinned: DMA + device conversion" : "pageable: host conversion",
               out_pinned ? "pinned: DMA" : "pageable: staged");
     }
