@@ -714,6 +714,10 @@ int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const 
 {
   if (n <= 0) return 0;
   const PipOptions_dp &o = options ? *options : DEFAULT_OPTIONS;
+  /* one batch call at a time: it stages in the engine's pinned buffers and decodes from them
+   * (the reference is not re-entrant either: sol_space and the cross counters are globals) */
+  static std::mutex batch_mu;
+  std::lock_guard<std::mutex> batch_guard(batch_mu);
   try {
     std::vector<Shape> shapes(n);
     std::vector<PipProblem> prob(n);
@@ -729,19 +733,38 @@ int pip_solve_batch_dp(int n, PipMatrix_dp *const *domains, PipMatrix_dp *const 
       off[i + 1] = off[i] + problem_words(shapes[i]);
       live.push_back(i);
     }
-    std::vector<I> pool(off[n] + 1);
+    /* the tableaux go straight into the engine's pinned staging area, as int32 when every value fits (the
+     * shared-memory int32 class is the fast one), else as int64 */
+    PipEngine &E = PipEngine::get();
+    void *pool = E.pinned_input((off[n] + 8) << 3);
     std::vector<PipProblem> lp(live.size());
-    parallel_for(live.size(), [&](size_t a, size_t b) {
-      for (size_t q = a; q < b; q++) {
-        int i = live[q];
-        MatView d = {(int)domains[i]->NbRows, (int)domains[i]->NbColumns, domains[i]->p, nullptr};
-        MatView c, *cp = nullptr;
-        if (contexts && contexts[i]) { c = {(int)contexts[i]->NbRows, (int)contexts[i]->NbColumns, contexts[i]->p, nullptr}; cp = &c; }
-        fill_problem(d, cp, shapes[i], lp[q], pool.data(), off[i]);
-      }
-    });
+    auto fill_all = [&](auto *typed) -> bool {
+      std::atomic<int> lost(0);
+      parallel_for(live.size(), [&](size_t a, size_t b) {
+        bool good = true;
+        for (size_t q = a; q < b; q++) {
+          int i = live[q];
+          MatView d = {(int)domains[i]->NbRows, (int)domains[i]->NbColumns, domains[i]->p, nullptr};
+          MatView c, *cp = nullptr;
+          if (contexts && contexts[i]) { c = {(int)contexts[i]->NbRows, (int)contexts[i]->NbColumns, contexts[i]->p, nullptr}; cp = &c; }
+          good = fill_problem(d, cp, shapes[i], lp[q], typed, off[i]) && good;
+        }
+        if (!good) lost.store(1);
+      });
+      return lost.load() == 0;
+    };
+    int elem_log2 = 2;
+    if (getenv("PIPLIB_B200_NO_INT32") || !fill_all((int *)pool)) { elem_log2 = 3; fill_all((I *)pool); }
+    /* same shape everywhere (the usual batch: one loop nest, many parameter samples): planned once */
+    bool same = !live.empty();
+    for (size_t q = 1; q < live.size() && same; q++) {
+      const PipProblem &A = lp[0], &B = lp[q];
+      same = A.nvar == B.nvar && A.nparm == B.nparm && A.ni == B.ni && A.nc == B.nc && A.bigparm == B.bigparm && A.flags == B.flags;
+    }
+    PipProblem shape0;
     PipBatchIn in;
-    in.n = live.size(); in.h_prob = lp.data(); in.h_pool = pool.data(); in.pool_words = off[n];
+    in.n = live.size(); in.h_prob = lp.data(); in.h_pool = pool; in.pool_words = off[n]; in.elem_log2 = elem_log2;
+    if (same) { shape0 = lp[0]; shape0.off = 0; in.uniform = &shape0; }
     PipBatchOut bo;
     PipEngine::get().run(in, bo);
     double t0 = 0;
