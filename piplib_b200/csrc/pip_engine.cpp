@@ -96,6 +96,7 @@ struct PipEngine::Impl {
   DevBuf d_so_status, d_so_hash, d_so_off, d_so_len, d_so_ctl;     /* stream_out: per-problem arrays, control + stats */
   DevBuf d_image;                  /* arena images of a uniform batch (pip_image_kernel) */
   DevBuf d_stl_offers, d_stl_segs, d_stl_next, d_stl_hwm, d_stl_head_next, d_stl_head_hwm, d_stl_ctl;   /* subtree donation */
+  DevBuf d_heavy;                /* problems handed over to the donation launch */
   DevBuf d_scratch[4];
   PinBuf h_scratch[4];
   PinBuf h_hash;
@@ -456,7 +457,9 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       long long est = est_cells_total * (long long)m / (long long)n;
       long long per_warp = (est + est / 4) / cs.warps + 1 + in.sol_size;
       if (attempt > 0) per_warp = std::max<long long>(per_warp, 4ll * in.sol_size);
-      E.d_cells.reserve((size_t)per_warp * cs.warps * sizeof(PipCell));
+      /* (+ the windows of the hand-over launch, below) */
+      const long long per_warp2 = k < 0 ? 3ll * in.sol_size : 0;
+      E.d_cells.reserve((size_t)(per_warp + per_warp2) * cs.warps * sizeof(PipCell));
       E.d_stack.reserve((size_t)cs.stack_words * cs.warps * sizeof(pip_i64));
       if (!cs.shared && !team_smem) E.d_gwork.reserve((size_t)cs.words * cs.warps * sizeof(pip_i64));
       if (!identity) {
@@ -513,9 +516,9 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       bool steal = words_round && k < 0 &&
                    (dmode > 0 || (dmode < 0 && (long long)m <= 2ll * cs.warps && (!in.uniform || in.uniform->nparm > 0)));
       if (const char *sv = getenv("PIPLIB_B200_STEAL")) steal = words_round && k < 0 && atoi(sv) != 0;
-      if (steal) {
-        PipSteal &S = L.steal;
+      auto arm_donation = [&](PipSteal &S) {
         S.mode = 1; S.cap = 1 << 16;
+        if (const char *cv = getenv("PIPLIB_B200_STEAL_CAP")) S.cap = std::max(1024, atoi(cv));
         E.d_stl_offers.reserve((size_t)S.cap * sizeof(PipOffer));
         E.d_stl_segs.reserve((size_t)S.cap * sizeof(PipResult));
         E.d_stl_next.reserve((size_t)S.cap * sizeof(int));
@@ -530,6 +533,34 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
         S.offers = (PipOffer *)E.d_stl_offers.p; S.ctl = (unsigned *)E.d_stl_ctl.p;
         S.segs = (PipResult *)E.d_stl_segs.p; S.seg_next = (int *)E.d_stl_next.p; S.seg_hwm = (int *)E.d_stl_hwm.p;
         S.head_next = (int *)E.d_stl_head_next.p; S.head_hwm = (int *)E.d_stl_head_hwm.p;
+      };
+      if (steal) arm_donation(L.steal);
+      /* heavy-problem hand-over (PipLaunch::budget): a batch balances by problems until its tail, which is a
+       * handful of very large trees on one warp each while the machine idles (loop nests: 16 ms of a 41 ms launch
+       * at 200 000 problems).  Those stop at `budget` pivots and a second launch, with donation, solves them with
+       * many warps.  Not for a batch so big that the tail is noise, nor when other lanes fill the machine anyway.
+       * PIPLIB_B200_HEAVY_PIVOTS=<n> sets the budget and forces the hand-over, 0 disables it */
+      unsigned heavy_budget = 1536;
+      bool handover = words_round && k < 0 && !steal && !in.overlapped && m <= (1 << 19) && (!in.uniform || in.uniform->nparm > 0);
+      if (const char *hv = getenv("PIPLIB_B200_HEAVY_PIVOTS")) {
+        heavy_budget = (unsigned)atoi(hv);
+        handover = words_round && k < 0 && !steal && heavy_budget > 0;
+      }
+      PipLaunch L2;
+      const PipSteal *gather_stl = steal ? &L.steal : nullptr;
+      if (handover) {
+        E.d_heavy.reserve((size_t)m * sizeof(int));
+        L.budget = heavy_budget;
+        L.heavy_max = (unsigned)std::max(64, m / 64);
+        L.heavy = (int *)E.d_heavy.p;
+        L2 = L;
+        L2.budget = 0; L2.from_heavy = 1;
+        L2.heavy_warps = 8;
+        if (const char *hw = getenv("PIPLIB_B200_HEAVY_WARPS")) L2.heavy_warps = std::max(1, atoi(hw));
+        L2.cell_base = per_warp * (long long)cs.warps; L2.cells_per_warp = per_warp2;
+        L2.heavy_region = per_warp2 * (long long)cs.warps;
+        arm_donation(L2.steal);
+        gather_stl = &L2.steal;
       }
       if (use_large) {
         run_large_round(in, host_prob(), d_pool, elem_log2, order, (PipCell *)E.d_cells.p, per_warp, (PipResult *)E.d_res.p, s);
@@ -537,6 +568,10 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
       } else {
         CK(pip_launch_solve(&L, (k >= 0 && cs.team) ? (team_smem ? 4 : 3) : cs.shared, ctas, cs.warps_per_cta, s));
         out.times.launches++;
+        if (handover) {
+          CK(pip_launch_solve(&L2, cs.shared, ctas, cs.warps_per_cta, s));
+          out.times.launches++;
+        }
       }
       /* this round's output: packed cells, or (device-decode mode) serialised quasts */
       if (ser_mode && (!all_sized || use_large)) {      /* sizing pass, unless the solver sized every stream itself */
@@ -553,7 +588,7 @@ void PipEngine::run(const PipBatchIn &in, PipBatchOut &out)
           CK(cudaMemsetAsync(so.ctl + PIP_SO_FINALS, 0, 2 * sizeof(unsigned long long), s));   /* finals, overflow */
           if (words_round)
             CK(pip_launch_gather_words((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p,
-                                       (pip_i64 *)E.d_compact.p, m, &so, L.steal.mode ? &L.steal : nullptr, in.sol_size, s));
+                                       (pip_i64 *)E.d_compact.p, m, &so, gather_stl, in.sol_size, s));
           else
             CK(pip_launch_serialize((PipResult *)E.d_res.p, d_order, (const PipCell *)E.d_cells.p, d_parm, in.uniform_decode,
                                     nullptr, (pip_i64 *)E.d_compact.p, nullptr, m, 1, &so, s));

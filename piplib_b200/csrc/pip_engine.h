@@ -30,6 +30,7 @@ struct PipBatchIn {
                                            arrays stay on the device (PipBatchOut::dev), nothing per problem
                                            crosses PCIe inside run() unless a problem has to change class */
   bool words64 = false;                 /* stream_out: every word as int64 (else int32 where it fits) */
+  bool overlapped = false;              /* other engine lanes run beside this batch: its tail is not idle time (no hand-over) */
   long long words_hint = 0;             /* stream_out: expected 64-bit slots for the whole batch (0 = default) */
   /* called when a problem's input does not fit the int32 pool (PIP_F_WIDE_INPUT): returns the int64 pool */
   const void *(*widen_pool)(void *ctx, cudaStream_t s) = nullptr;

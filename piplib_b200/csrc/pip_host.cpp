@@ -1284,6 +1284,7 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
     const size_t lanes = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(env_size("PIPLIB_B200_LANES", 6), PipEngine::MAX_LANES),
                                                               (nchunks + devices.size() - 1) / devices.size()));
     const size_t nworkers = lanes * devices.size();
+    const size_t tail_chunks = env_size("PIPLIB_B200_TAIL_CHUNKS", 0) * devices.size();   /* chunks at the end of the call that run with the hand-over (measured: no effect on the call) */
     /* host threads per lane: the lanes' conversion / copy-out phases overlap, so each gets a share */
     const size_t nthreads_default = std::max<size_t>(1, (host_threads() + nworkers - 1) / nworkers);
     std::vector<size_t> firsts(nchunks + 1, 0);
@@ -1412,6 +1413,8 @@ int pip_solve_dense_dp(long long n, int dom_rows, int dom_cols, const long long 
           if (device_decode) {
             in.uniform_decode = &uparm;
             in.stream_out = true;
+            /* other lanes keep the machine busy during this chunk's tail -- except at the end of the call */
+            in.overlapped = nworkers > 1 && c + tail_chunks < nchunks;
             in.words64 = out_pinned;
           }
           double td = wall();

@@ -1568,7 +1568,8 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
                            unsigned *nwords_out = nullptr, bool wordmode = false, const PipLayout *pre = nullptr,
                            const PipSteal *stl = nullptr, int stl_problem = 0, int stl_seg = -1,
                            const pip_i64 *resume = nullptr, int *hwm_out = nullptr,
-                           const pip_i64 *image = nullptr, int image_w1 = 0)
+                           const pip_i64 *image = nullptr, int image_w1 = 0, unsigned budget = 0,
+                           const unsigned *handed = nullptr, unsigned handed_max = 0)
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
@@ -1794,6 +1795,14 @@ AFTER_COMPA:
     const int np = T.nparm;
     if (nc >= L.crcap) { status = PIP_ST_CAPACITY; goto DONE; }
     if (np >= maxparm) { status = PIP_ST_FATAL + 2; goto DONE; }
+    /* heavy-problem hand-over (PipLaunch::budget): a big tree is better solved by many warps */
+    if (!STEAL && budget && st.pivots > budget) {
+      /* ... unless the whole batch is like that (handed_max): then the plain launch is the right one */
+      unsigned h = 0;
+      if (lane == 0) h = W::load_volatile(handed);
+      if ((unsigned)W::shfl((int)h, 0) < handed_max) { status = PIP_ST_PENDING; goto DONE; }
+      budget = 0;
+    }
     PIP_NEED(np + 3);
     int *fl = pip_fl(B, T);
     const V *row = pip_row(B, T, PIP_LINK(fl[pivi]));

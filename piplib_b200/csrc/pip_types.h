@@ -189,7 +189,7 @@ typedef struct {
   pip_i64 stack_words_per_warp;
   pip_i64 *gwork;                /* working arenas in global memory (class G) or NULL (class S) */
   int work_words;                /* words of working arena per warp */
-  unsigned *queue;               /* [0] next problem, [1] retired warps */
+  unsigned *queue;               /* [0] next problem, [2] problems handed over (budget), [3] next entry of heavy[] */
   int sol_size, maxcol, maxparm;
   int slack_level;
   unsigned long long *prof;      /* [PIP_NPHASE] cycle sums (profile build only) or NULL */
@@ -200,6 +200,19 @@ typedef struct {
   int image_words, image_w1;     /* words per image; words of its first region (tableau), the context follows */
   PipSteal steal;                /* subtree donation (word mode only) */
   int emit_words;                /* word mode: PIP_F_SIMPLE_SER problems write their serialised quast (pip_solver.h) */
+  /* ---- heavy-problem hand-over: the tail of a big launch is a few problems with very large parametric trees
+   * (loop nests: mean 66 pivots, 1 in 10^4 above 2000), each on one warp while the machine idles.  A problem
+   * that reaches a split with more than `budget` pivots behind it stops, is listed in heavy[] and keeps its
+   * PENDING record; a second launch (from_heavy) of the instantiation with subtree donation solves the list
+   * from scratch with every warp cooperating. */
+  unsigned budget;               /* 0 = no hand-over */
+  unsigned heavy_max;            /* no more hand-overs once this many are listed (a batch of heavy problems only is
+                                    balanced by problems; a few more may slip in: the count is read, not reserved) */
+  int *heavy;                    /* [nprob] problems handed over, queue[2] of them */
+  int from_heavy;                /* this launch solves heavy[0 .. queue[2]) (cursor queue[3]) instead of order[0 .. nprob) */
+  int heavy_warps;               /* ... with at most this many warps per listed problem (the others leave at once) */
+  pip_i64 heavy_region;          /* ... and the cells of the launch's whole region (shared out among the warps that stay) */
+  pip_i64 cell_base;             /* first cell of this launch's windows in `cells` (the second launch writes behind the first) */
 } PipLaunch;
 
 #endif

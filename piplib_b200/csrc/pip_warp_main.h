@@ -11,7 +11,7 @@
  * returns the window space consumed, in cells */
 template <class V, bool TEAM, bool STEAL>
 PIP_DEV pip_i64 pip_warp_unit(const PipLaunch &L, int warp_id, pip_i64 *arena, PipTeam *tm, PipCell *window, pip_i64 used,
-                              pip_i64 *stk, int p, int offer)
+                              pip_i64 *stk, int p, int offer, pip_i64 cpw)
 {
   /* (test mode 2 slices the warp's frame stack per unit, see pip_warp_main) */
   const pip_i64 stk_cap = (STEAL && L.steal.mode == 2) ? L.stack_words_per_warp / 64 : L.stack_words_per_warp;
@@ -34,11 +34,18 @@ PIP_DEV pip_i64 pip_warp_unit(const PipLaunch &L, int warp_id, pip_i64 *arena, P
                 stk_cap, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm, &nwords,
                 wordmode, L.have_layout ? &L.layout : nullptr, stl, p, offer,
                 (STEAL && offer >= 0) ? L.steal.offers[offer].frame : nullptr, STEAL ? &hwm : nullptr,
-                (L.images && L.have_layout) ? L.images + (pip_i64)p * L.image_words : nullptr, L.image_w1);
+                (L.images && L.have_layout) ? L.images + (pip_i64)p * L.image_words : nullptr, L.image_w1,
+                (STEAL || offer >= 0) ? 0u : L.budget, &L.queue[2], L.heavy_max);
+  if (!STEAL && status == PIP_ST_PENDING) {
+    /* handed over: listed for the launch that follows, the record stays PENDING, the window is not consumed */
+    if (lane == 0) L.heavy[W::atomic_add(&L.queue[2], 1u)] = p;      /* (heavy[] holds nprob entries) */
+    W::sync();
+    return 0;
+  }
   if (lane == 0) {
     PipResult r;
     r.status = status; r.ncells = ncell;
-    r.cell_off = (pip_i64)warp_id * L.cells_per_warp + used;
+    r.cell_off = L.cell_base + (pip_i64)warp_id * cpw + used;
     r.pivots = st.pivots; r.cuts = st.cuts; r.subsolves = st.subsolves; r.splits = st.splits;
     r.max_rows = st.max_rows; r.max_cols = st.max_cols; r.ser_words = 0;
     if (P.flags & PIP_F_SIMPLE_SER) {
@@ -72,7 +79,8 @@ PIP_DEV pip_i64 pip_warp_unit(const PipLaunch &L, int warp_id, pip_i64 *arena, P
 /* a claimed offer becomes segment `idx` of its problem: link it right after the donor's segment (later, inner
  * donations of the same donor thus come before earlier, outer ones: pre-order), then solve the subtree */
 template <class V>
-PIP_DEV pip_i64 pip_warp_steal(const PipLaunch &L, int warp_id, pip_i64 *arena, PipCell *window, pip_i64 used, pip_i64 *stk, int idx)
+PIP_DEV pip_i64 pip_warp_steal(const PipLaunch &L, int warp_id, pip_i64 *arena, PipCell *window, pip_i64 used, pip_i64 *stk, int idx,
+                               pip_i64 cpw)
 {
   const PipSteal &S = L.steal;
   int p = 0;
@@ -86,26 +94,43 @@ PIP_DEV pip_i64 pip_warp_steal(const PipLaunch &L, int warp_id, pip_i64 *arena, 
   }
   p = W::shfl(p, 0);
   W::sync();
-  return pip_warp_unit<V, false, true>(L, warp_id, arena, nullptr, window, used, stk, p, idx);
+  return pip_warp_unit<V, false, true>(L, warp_id, arena, nullptr, window, used, stk, p, idx, cpw);
 }
 
 template <class V, bool TEAM = false, bool STEAL = false>
 PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipTeam *tm = nullptr)
 {
   const int lane = W::lane();
-  PipCell *window = L.cells + (pip_i64)warp_id * L.cells_per_warp;
+  pip_i64 cpw = L.cells_per_warp;       /* cells of this warp's window */
   pip_i64 *stk = L.stack + (pip_i64)warp_id * L.stack_words_per_warp;
   pip_i64 used = 0;
+  /* the hand-over list of the previous launch (PipLaunch::from_heavy): its length is known on the device only;
+   * a short list keeps most warps out of the way (other launches may share the machine) */
+  unsigned nprob = (unsigned)L.nprob;
+  unsigned *cursor = &L.queue[0];
+  const int *order = L.order;
+  if (STEAL && L.from_heavy) {
+    nprob = W::load_volatile(&L.queue[2]);
+    cursor = &L.queue[3];
+    order = L.heavy;
+    unsigned act = nprob * (unsigned)L.heavy_warps;
+    if (act < 128u) act = 128u;
+    if (nprob == 0 || (unsigned)warp_id >= act) return;
+    /* the launch's cell region is shared out among the warps that stay: few listed problems, large windows
+     * (a listed problem's stream is long, and a warp whose window is full cannot take subtrees either) */
+    if ((pip_i64)act * cpw < L.heavy_region) cpw = L.heavy_region / (pip_i64)act;
+  }
+  PipCell *window = L.cells + L.cell_base + (pip_i64)warp_id * cpw;
   /* subtree donation: warps that have started (a CTA the hardware has not scheduled yet must not be waited for) */
   if (STEAL && L.steal.mode == 1 && L.emit_words && lane == 0) W::atomic_add(&L.steal.ctl[PIP_STL_TOTAL], 1u);
   for (;;) {
-    if (L.cells_per_warp - used < (pip_i64)L.sol_size) break;
+    if (cpw - used < (pip_i64)L.sol_size) break;
     unsigned q = 0;
-    if (lane == 0) q = W::atomic_add(&L.queue[0], 1u);
+    if (lane == 0) q = W::atomic_add(cursor, 1u);
     q = (unsigned)W::shfl((int)q, 0);
-    if (q >= (unsigned)L.nprob) break;
-    const int p = L.order ? L.order[q] : (int)q;
-    used += pip_warp_unit<V, TEAM, STEAL>(L, warp_id, arena, tm, window, used, stk, p, -1);
+    if (q >= nprob) break;
+    const int p = order ? order[q] : (int)q;
+    used += pip_warp_unit<V, TEAM, STEAL>(L, warp_id, arena, tm, window, used, stk, p, -1, cpw);
   }
   if (!STEAL || !L.steal.mode || !L.emit_words) return;
   const PipSteal &S = L.steal;
@@ -117,12 +142,12 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
       if (lane == 0) { c = W::load_volatile(&S.ctl[PIP_STL_CURSOR]); n = W::load_volatile(&S.ctl[PIP_STL_OFFERS]); }
       c = (unsigned)W::shfl((int)c, 0); n = (unsigned)W::shfl((int)n, 0);
       if (c >= n || c >= (unsigned)S.cap) break;
-      if (L.cells_per_warp - used < (pip_i64)L.sol_size) break;
+      if (cpw - used < (pip_i64)L.sol_size) break;
       if (lane == 0) W::atomic_add(&S.ctl[PIP_STL_CURSOR], 1u);
       /* (one warp plays donor and thief: every unit gets its own slice of the frame stack, so that the frames
        * still on offer are not overwritten by the subtree being solved) */
       const pip_i64 slice = L.stack_words_per_warp / 64;
-      used += pip_warp_steal<V>(L, warp_id, arena, window, used, stk + (1 + (c % 63)) * slice, (int)c);
+      used += pip_warp_steal<V>(L, warp_id, arena, window, used, stk + (1 + (c % 63)) * slice, (int)c, cpw);
     }
     return;
   }
@@ -133,7 +158,7 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
   unsigned scan = 0;                    /* every offer below was seen closed (states only move away from OPEN) */
   for (;;) {
     int got = -1;
-    const bool room = L.cells_per_warp - used >= (pip_i64)L.sol_size;
+    const bool room = cpw - used >= (pip_i64)L.sol_size;
     if (lane == 0 && room) {
       unsigned n = W::load_volatile(&S.ctl[PIP_STL_OFFERS]);
       if (n > (unsigned)S.cap) n = (unsigned)S.cap;
@@ -150,7 +175,7 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
     got = W::shfl(got, 0);
     if (got >= 0) {
       if (lane == 0) W::atomic_add(&S.ctl[PIP_STL_IDLE], 0xffffffffu);      /* idle-- */
-      used += pip_warp_steal<V>(L, warp_id, arena, window, used, stk, got);
+      used += pip_warp_steal<V>(L, warp_id, arena, window, used, stk, got, cpw);
       if (lane == 0) W::atomic_add(&S.ctl[PIP_STL_IDLE], 1u);
       continue;
     }

@@ -83,9 +83,11 @@ def solve_uniform_cases(cases, work_words=1 << 16, stack_words=1 << 20, slack_le
 
 
 def solve_tableau_cases_steal(cases, work_words=1 << 16, stack_words=1 << 20, slack_level=2, order_mode=0, narrow=0,
-                              sol_size=0):
+                              sol_size=0, budget=0, handed_max=1 << 30):
     """word mode with subtree donation in test mode (PipSteal mode 2): every outermost ELSE branch becomes a
-    separate segment solved after the donor finished; returns [(status, words, record, segments)]"""
+    separate segment solved after the donor finished; returns [(status, words, record, segments)].
+    budget > 0: the engine's heavy-problem hand-over -- a plain launch with a pivot budget, then the donation
+    launch over the problems that stopped; solve_tableau_cases_steal.handed = how many did"""
     lib = C.CDLL(SO)
     probs, pool = pack_tableau_problems(cases)
     probs["flags"] |= 8
@@ -97,11 +99,13 @@ def solve_tableau_cases_steal(cases, work_words=1 << 16, stack_words=1 << 20, sl
     words = np.zeros(wcap, dtype=np.int64)
     woff = np.zeros(n + 1, dtype=np.int64)
     nsegs = np.zeros(n, dtype=np.int32)
+    handed = C.c_int(0)
     lib.pipemu_solve_batch_steal(probs.ctypes.data_as(C.c_void_p), n, pool.ctypes.data_as(C.c_void_p),
                                  res.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p), C.c_longlong(cap),
                                  work_words, C.c_longlong(stack_words), slack_level, order_mode, sol_size, narrow,
                                  words.ctypes.data_as(C.c_void_p), C.c_longlong(wcap), woff.ctypes.data_as(C.c_void_p),
-                                 nsegs.ctypes.data_as(C.c_void_p))
+                                 nsegs.ctypes.data_as(C.c_void_p), C.c_uint(budget), C.byref(handed), C.c_uint(handed_max))
+    solve_tableau_cases_steal.handed = handed.value
     return [(int(res[i]["status"]), [int(x) for x in words[woff[i]:woff[i + 1]]], res[i], int(nsegs[i])) for i in range(n)]
 
 

@@ -111,10 +111,11 @@ extern "C" int pipemu_solve_uniform(const PipProblem *prob, int nprob, const pip
 extern "C" int pipemu_solve_batch_steal(const PipProblem *prob, int nprob, const pip_i64 *pool, PipResult *res,
                                         PipCell *cells, long long cells_cap, int work_words, long long stack_words,
                                         int slack_level, int order_mode, int sol_size, int narrow,
-                                        long long *words_out, long long words_cap, long long *words_off, int *nsegs)
+                                        long long *words_out, long long words_cap, long long *words_off, int *nsegs,
+                                        unsigned budget, int *handed, unsigned handed_max)
 {
   EmuArgs e;
-  unsigned queue[2] = {0, 0};
+  unsigned queue[4] = {0, 0, 0, 0};
   memset(&e, 0, sizeof e);
   e.L.prob = prob; e.L.pool = pool; e.L.pool_elem_log2 = 3; e.L.order = 0; e.L.nprob = nprob; e.L.res = res;
   e.L.cells = cells; e.L.cells_per_warp = cells_cap;
@@ -148,10 +149,31 @@ extern "C" int pipemu_solve_batch_steal(const PipProblem *prob, int nprob, const
    * by the next problem while offers still point into it, so every problem is run with its offers drained:
    * the queue hands out one problem at a time */
   long long at = 0;
-  for (int i = 0; i < nprob; i++) {
-    queue[0] = (unsigned)i;
-    e.L.nprob = i + 1;
+  int *heavy = (int *)malloc(sizeof(int) * (nprob + 1));
+  if (budget) {
+    /* heavy-problem hand-over as the engine runs it: a first launch without donation in which a problem past
+     * `budget` pivots stops at its next split and is listed, then the donation launch over the list, writing
+     * behind the first launch's windows */
+    PipLaunch first = e.L;
+    e.L.steal.mode = 0; e.steal = 0;
+    e.L.budget = budget; e.L.heavy = heavy; e.L.heavy_max = handed_max; e.L.cells_per_warp = cells_cap / 2;
     pipemu::run_warp(warp_entry, &e);
+    *handed = (int)queue[2];
+    e.L = first; e.steal = 1;
+    e.L.heavy = heavy; e.L.from_heavy = 1; e.L.heavy_warps = 8; e.L.cell_base = cells_cap / 2; e.L.cells_per_warp = cells_cap / 2;
+  }
+  const unsigned nheavy = queue[2];
+  for (int i = 0; i < nprob; i++) {
+    if (!budget) {
+      queue[0] = (unsigned)i;
+      e.L.nprob = i + 1;
+      pipemu::run_warp(warp_entry, &e);
+    } else {
+      /* (every run of the emulated warp starts its window afresh: a listed problem is solved right before
+       * its words are collected) */
+      for (unsigned j = 0; j < nheavy; j++)
+        if (heavy[j] == i) { queue[2] = j + 1; queue[3] = j; pipemu::run_warp(warp_entry, &e); }
+    }
     PipResolved R;
     pip_resolve_segments(res[i], S.head_next[i], S, e.L.sol_size, R);
     words_off[i] = at;
@@ -172,6 +194,7 @@ extern "C" int pipemu_solve_batch_steal(const PipProblem *prob, int nprob, const
     }
   }
   words_off[nprob] = at;
+  free(heavy);
   free(e.arena); free(e.L.stack); free(S.offers); free(S.segs); free(S.seg_next); free(S.seg_hwm); free(S.head_next); free(S.head_hwm);
   return 0;
 }

@@ -288,6 +288,37 @@ def test_subtree_donation_splices_to_the_same_stream(narrow):
 
 
 @pytest.mark.parametrize("narrow", [0, 1])
+def test_heavy_problem_handover_gives_the_same_stream(narrow):
+    """the engine's heavy-problem hand-over (PipLaunch::budget, pip_types.h): in a first launch without donation
+    a problem that reaches a split with more than `budget` pivots behind it stops and is listed; the donation
+    launch then solves the list from scratch behind the first launch's windows.  Streams, statuses and counters
+    must be those of the plain solve whatever the budget (nothing of the abandoned attempt may survive)."""
+    from workloads import synth
+    cases = [c for c in CLI + RCLI if c["nparm"] > 0 and c["name"] not in HEAVY]
+    for wl, n in (("loopnest16x24p3", 150), ("loopnest8x12p2", 200), ("fimmel", 30)):
+        dom, ctx = synth.generate(wl, n, seed=31)
+        cases += _dense_to_cases(dom, ctx)
+    b = emu.solve_tableau_cases(cases, slack_level=3, work_words=1 << 18, order_mode=0, narrow=narrow, emit_words=True)
+    for budget, cap, lo, hi in ((1, 1 << 30, 200, 10 ** 9), (40, 1 << 30, 20, len(cases) - 20), (1, 25, 25, 25),
+                                (100000, 1 << 30, 0, 0)):
+        a = emu.solve_tableau_cases_steal(cases, slack_level=3, work_words=1 << 18, order_mode=2, narrow=narrow,
+                                          budget=budget, handed_max=cap)
+        handed = emu.solve_tableau_cases_steal.handed
+        assert lo <= handed <= hi, (budget, handed)
+        bad = []
+        for k, ((st, words, r, nseg), (st2, words2, r2, _)) in enumerate(zip(a, b)):
+            if st == 4003 or st2 == 4003:
+                if st != st2:
+                    bad.append((k, st, st2))
+                continue
+            if st != st2 or (st in (0, 1) and words != words2):
+                bad.append((k, st, st2, nseg, len(words), len(words2)))
+            elif st == 0 and any(int(r[x]) != int(r2[x]) for x in ("pivots", "cuts", "subsolves", "splits", "ncells")):
+                bad.append((k, "counters", nseg))
+        assert not bad, (budget, bad[:6])
+
+
+@pytest.mark.parametrize("narrow", [0, 1])
 def test_uniform_batch_layout_and_arena_images(narrow):
     """a dense batch as the engine runs it -- arena layout carved once for the largest row counts, arena images
     built ahead of the solve by the solver's own loader (pip_load_problem), two block copies per problem in the

@@ -583,6 +583,32 @@ def test_subtree_donation_on_the_device(api, port, workload, n, monkeypatch):
     assert np.array_equal(r["hashes"][ok], h_o[ok])
 
 
+@pytest.mark.parametrize("budget", ["8", "64", "1024"])
+def test_heavy_problem_handover_on_the_device(api, port, budget, monkeypatch):
+    """heavy-problem hand-over (PipLaunch::budget): problems past the pivot budget stop at their next split in
+    the bulk launch and are solved from scratch by the donation launch that follows on the same stream.  With a
+    tiny budget the list fills to its cap; streams word for word against the run without hand-over, statuses
+    and hashes against the oracle.  (Pivot totals are not compared: for an exit(26) problem they count what ran
+    before the verdict, which depends on who solved which subtree.)"""
+    from workloads import synth
+    n = 40000
+    dom, ctx = synth.generate("loopnest16x24p3", n, seed=41)
+    bg, opts = synth.bignum("loopnest16x24p3"), synth.options("loopnest16x24p3")
+    monkeypatch.setenv("PIPLIB_B200_STEAL", "0")
+    monkeypatch.setenv("PIPLIB_B200_HEAVY_PIVOTS", "0")
+    base = api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, **opts)
+    monkeypatch.delenv("PIPLIB_B200_STEAL")
+    monkeypatch.setenv("PIPLIB_B200_HEAVY_PIVOTS", budget)
+    for rep in range(2):
+        r = api.solve_dense(dom, ctx, bg, want_hashes=True, want_ser=True, **opts)
+        _dense_equal(r, base, n)
+    _, st_o, h_o, _ = port.bench_dense(0, n, dom, ctx, bg, **opts)
+    st_g = np.where(r["status"] == 1, 0, r["status"])
+    assert np.array_equal(st_g, st_o)
+    ok = st_o == 0
+    assert np.array_equal(r["hashes"][ok], h_o[ok])
+
+
 def test_big_parameter_column_outside_the_tableau_is_refused(api):
     """test/challenges/pipFile_1 names big-parameter column 12 in a 12-column tableau: the reference reads past
     the row end (source/traiter.c:111), so its answer depends on the heap layout.  The library refuses the
