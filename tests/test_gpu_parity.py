@@ -163,7 +163,8 @@ def test_dense_batch_vs_oracle(api, port, workload, n):
     ok = st_o == 0
     assert np.array_equal(r["hashes"][ok], h_o[ok])
     s = api.last_stats()
-    assert int(s.pivots) == int(stats.pivots)            # same pivots, sub-solves included
+    if not (st_o >= 1000).any():                          # (a fatal verdict under donation leaves partial counters)
+        assert int(s.pivots) == int(stats.pivots)        # same pivots, sub-solves included
     for i in range(0, n, max(1, n // 20)):
         st, ser = port.solve(dom[i], ctx[i], -1)
         mine = [int(x) for x in r["ser"][r["ser_off"][i]:r["ser_off"][i] + r["ser_len"][i]]]
@@ -180,6 +181,7 @@ def test_config3_and_5_families_vs_oracle(api, port, workload, n, monkeypatch):
     # (pivot totals are compared: subtree donation -- tested on its own below -- leaves the counters of problems
     # that end in a fatal verdict partial, because the segments after the fatal point ran anyway or not at all)
     monkeypatch.setenv("PIPLIB_B200_STEAL", "0")
+    monkeypatch.setenv("PIPLIB_B200_HEAVY_PIVOTS", "0")        # (the hand-over ends in a donation launch)
     dom, ctx = synth.generate(workload, n, seed=31)
     bg, opts = synth.bignum(workload), synth.options(workload)
     _, st_o, h_o, stats = port.bench_dense(0, n, dom, ctx, bg, **opts)
@@ -269,6 +271,7 @@ def test_int32_and_int64_instantiations_agree_at_scale(api, port, monkeypatch):
     from workloads import synth
     n = 200000
     dom, ctx = synth.generate("loopnest16x24p3", n, seed=2026)
+    monkeypatch.setenv("PIPLIB_B200_HEAVY_PIVOTS", "0")     # pivot totals are compared: no donation launch
     a = api.solve_dense(dom, ctx, -1, want_hashes=True, want_ser=True)
     piv_a = int(api.last_stats().pivots)
     monkeypatch.setenv("PIPLIB_B200_NO_INT32", "1")
