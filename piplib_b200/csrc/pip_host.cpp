@@ -1524,6 +1524,11 @@ struct pip_device_batch {
   PipProblem shape;
   std::vector<PipDecodeParm> parm;
   int device = 0;
+  /* a big device job runs as a few parts of falling size on engine lanes of their own (pip_device_batch_run) */
+  struct Part { size_t first = 0, n = 0; PipBatchOut out; std::string error; };
+  std::vector<Part> parts;
+  cudaStream_t clock_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_cols, const long long *dom,
@@ -1577,6 +1582,87 @@ int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
       if (b->uniform) in.uniform_decode = &b->parm[0]; else in.h_decode = b->parm.data();
       in.stream_out = true;
     } else in.fetch_cells = fetch_cells != 0;
+    b->parts.clear();
+    /* A launch ends with its heaviest problems, one warp each, on an idle machine (loop nests: the last ~12 ms
+     * of 128 at 10^6 problems).  So a big job runs as parts of falling size on engine lanes
+     * of their own, launched in that order: the tail of a part is filled by the CTAs of the next one, and the
+     * last part is small enough for the heavy-problem hand-over.  The results of every part stay in its lane's
+     * buffers in HBM.  Measured at 10^6 problems (profiles/r2_device_job_parts.log): 129 -> 124.4 ms with 3 or 4
+     * parts, 127.5 with 6 or 8; which part holds the largest trees moves it by a few ms.
+     * PIPLIB_B200_DEVICE_PARTS=1 runs the job as one launch */
+    size_t nparts = 1;
+    if (stream && b->C.n > ((size_t)1 << 19)) nparts = std::min<size_t>(env_size("PIPLIB_B200_DEVICE_PARTS", 3), PipEngine::MAX_LANES);
+    if (nparts > 1) {
+      double share[8] = {0.55, 0.30, 0.15, 0.08, 0.04, 0.02, 0.01, 0.005};
+      if (const char *sv = getenv("PIPLIB_B200_DEVICE_SHARES")) {       /* "0.6,0.3,0.1": tuning */
+        nparts = 0;
+        for (const char *c = sv; *c && nparts < 8;) {
+          char *end = nullptr;
+          share[nparts++] = strtod(c, &end);
+          c = (*end == ',') ? end + 1 : end;
+          if (end == c && *end != ',') break;
+        }
+        if (nparts < 1) nparts = 1;
+      }
+      double sum = 0;
+      for (size_t q = 0; q < nparts; q++) sum += share[q];
+      b->parts.resize(nparts);
+      size_t at = 0;
+      for (size_t q = 0; q < nparts; q++) {
+        size_t cnt = q + 1 == nparts ? b->C.n - at : (size_t)((double)b->C.n * share[q] / sum) & ~(size_t)1023;
+        b->parts[q].first = at; b->parts[q].n = cnt;
+        at += cnt;
+      }
+      pip_cuda_check(cudaSetDevice(b->device), "cudaSetDevice");
+      if (!b->clock_stream) {
+        pip_cuda_check(cudaStreamCreateWithFlags(&b->clock_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        pip_cuda_check(cudaEventCreate(&b->ev0), "cudaEventCreate");
+        pip_cuda_check(cudaEventCreate(&b->ev1), "cudaEventCreate");
+      }
+      pip_cuda_check(cudaEventRecord(b->ev0, b->clock_stream), "cudaEventRecord");
+      std::atomic<int> turn(0);            /* parts enter their engines in order of size */
+      auto part_main = [&](size_t q) {
+        pip_device_batch::Part &P = b->parts[q];
+        try {
+          PipBatchIn pin = in;
+          pin.n = P.n; pin.h_prob = b->C.prob.data() + P.first; pin.d_prob = b->d_prob + P.first;
+          if (pin.h_decode) pin.h_decode = b->parm.data() + P.first;
+          pin.overlapped = q + 1 < b->parts.size();
+          while (turn.load() != (int)q) std::this_thread::yield();
+          PipEngine &E = PipEngine::at(b->device, (int)q);
+          std::thread next([&] { std::this_thread::sleep_for(std::chrono::microseconds(400)); turn.store((int)q + 1); });
+          E.run(pin, P.out);
+          next.join();
+        } catch (const std::exception &e) {
+          P.error = e.what();
+          turn.store((int)q + 1);
+        }
+      };
+      std::vector<std::thread> th;
+      for (size_t q = 1; q < nparts; q++) th.emplace_back(part_main, q);
+      part_main(0);
+      for (auto &t : th) t.join();
+      pip_cuda_check(cudaEventRecord(b->ev1, b->clock_stream), "cudaEventRecord");
+      pip_cuda_check(cudaEventSynchronize(b->ev1), "cudaEventSynchronize");
+      for (auto &P : b->parts) if (!P.error.empty()) throw std::runtime_error(P.error);
+      float ms = 0;
+      pip_cuda_check(cudaEventElapsedTime(&ms, b->ev0, b->ev1), "cudaEventElapsedTime");
+      b->fetched = false;
+      if (device_ms) *device_ms = ms;
+      PipBatchStats_dp st;
+      memset(&st, 0, sizeof st);
+      for (auto &P : b->parts) {
+        const PipDeviceOut &D = P.out.dev;
+        st.pivots += D.stats[0]; st.cuts += D.stats[1]; st.subsolves += D.stats[2]; st.splits += D.stats[3];
+        st.elem_updates += D.stats[4]; st.cells += D.stats[5];
+        st.max_rows = std::max(st.max_rows, (unsigned)D.stats[6]); st.max_cols = std::max(st.max_cols, (unsigned)D.stats[7]);
+        st.wrapped += D.stats[8];
+        accumulate(st, P.out);
+      }
+      st.device_ms = ms;
+      publish_stats(st);
+      return 0;
+    }
     PipEngine &E = PipEngine::at(b->device, 0);
     E.run(in, b->C.out);
     b->fetched = fetch_cells != 0;
@@ -1600,6 +1686,21 @@ int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
 
 int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long long *hashes)
 {
+  if (!b->parts.empty()) {               /* last run went in parts: every lane holds its part's arrays */
+    try {
+      pip_cuda_check(cudaSetDevice(b->device), "cudaSetDevice");
+      for (auto &P : b->parts) {
+        const PipDeviceOut &D = P.out.dev;
+        pip_cuda_check(cudaMemcpy(status + P.first, D.status, P.n * sizeof(int), cudaMemcpyDeviceToHost), "D2H statuses");
+        if (hashes) pip_cuda_check(cudaMemcpy(hashes + P.first, D.hash, P.n * sizeof(pip_u64), cudaMemcpyDeviceToHost), "D2H hashes");
+      }
+      for (size_t i = 0; i < b->C.n; i++) if (!PIP_STATUS_IS_FINAL(status[i])) status[i] = PIP_ST_CAPACITY;
+    } catch (const std::exception &e) {
+      fprintf(stderr, "%s\n", e.what());
+      return -1;
+    }
+    return 0;
+  }
   const PipDeviceOut &D = b->C.out.dev;
   if (D.status) {                        /* last run decoded on the device: statuses and hashes are in HBM */
     try {
@@ -1624,6 +1725,9 @@ void pip_device_batch_destroy(pip_device_batch *b)
 {
   if (!b) return;
   cudaFree(b->d_prob); cudaFree(b->d_pool);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->clock_stream) cudaStreamDestroy(b->clock_stream);
   delete b;
 }
 

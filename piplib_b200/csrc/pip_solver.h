@@ -232,7 +232,9 @@ PIP_SDEVNI void pip_copy2d(V *dst, int dstride, const V *src, int sstride, int r
   }
 }
 
-/* warp-cooperative copy of n 64-bit words (the frame stack) */
+/* warp-cooperative copy of n 64-bit words (the frame stack, arena images, the sub-tableau).  (Telling the
+ * compiler which side is shared memory -- __builtin_assume(__isShared(..)) -- shortens the loop from 15 to 7-12
+ * instructions per word but needs one copy of the function per direction: measured neutral, not kept.) */
 PIP_SDEVNI void pip_copy_words(pip_i64 *dst, const pip_i64 *src, int n)
 {
   #pragma unroll 1
@@ -914,11 +916,33 @@ PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V
     /* pass 1: pure arithmetic.  The generic formula gives 0 in column pivj (foo*lpiv == pivot*foo'),
      * the real value dpiv*foo' is patched in afterwards, so the loop body has no special case */
     pip_u64 orz = 0;
+#ifndef PIP_NO_UPD2
+    if (PipVal<V>::narrow) {
+      /* int32 storage: the range check is made once per row on the OR of the magnitudes instead of per entry
+       * (3 instructions per entry instead of 5.5).  The OR only proves |z| < 2^30 for all entries, so a row
+       * with an entry in [2^30, 2^31) now sends the problem to the int64 class although it would have fitted */
+      unsigned acc_hi = 0, acc_lo = 0, orl = 0;
+      const V *pr = prow;
+      V *r = row;
+      V *const rend = row + ncol;
+      #pragma unroll 2
+      for (; r != rend; r++, pr++) {
+        const pip_i64 z = PipVal<V>::cross(*r, lpiv, *pr, foo);
+        const int lo = (int)z, hi = (int)(z >> 32), sg = lo >> 31;
+        *r = (V)lo;
+        orl |= (unsigned)lo; acc_hi |= (unsigned)(hi ^ sg); acc_lo |= (unsigned)(lo ^ sg);
+      }
+      ovf |= acc_hi | (acc_lo >> 30);
+      orz = orl;
+    } else
+#endif
+    {
     #pragma unroll 2
     for (int j = 0; j < ncol; j++) {
       const V z = PipVal<V>::mulsub(row[j], lpiv, prow[j], foo, ovf);
       row[j] = z;
       orz |= (pip_u64)(pip_i64)z;
+    }
     }
     zp = PipVal<V>::mul(dpiv, foo, ovf);
     row[pivj] = zp;

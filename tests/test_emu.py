@@ -204,8 +204,10 @@ def test_register_resident_feasibility_solves_equal_the_general_path(port, narro
     keys = ("status", "ncells", "pivots", "cuts", "subsolves", "splits", "max_rows", "max_cols",
             "elem_updates_lo", "elem_updates_hi")
     for k, (c, (st, cells, r), (st2, cells2, r2)) in enumerate(zip(cases, a, b)):
-        if st == st2 == 4003:
-            continue                      # WIDEN: the problem is re-run by the int64 class, its counters are dropped
+        if st == 4003 or st2 == 4003:
+            # WIDEN: the problem is re-run by the int64 class, its counters are dropped.  (The two builds need not
+            # agree on it: the row update asks for |z| < 2^30, the register sub-solver for the int32 range.)
+            continue
         if st != st2 or cells != cells2 or any(int(r[x]) != int(r2[x]) for x in keys):
             bad.append((k, st, st2, [(x, int(r[x]), int(r2[x])) for x in keys if int(r[x]) != int(r2[x])]))
         piv += int(r["pivots"])

@@ -231,6 +231,30 @@ def test_device_resident_batch(api, port):
     db.close()
 
 
+def test_device_job_in_parts(api, monkeypatch):
+    """a device-resident job above 2^19 problems runs as parts of falling size on engine lanes of their own (the
+    tail of a part is filled by the next one): statuses, hashes and counters equal to the one-launch job"""
+    from workloads import synth
+    n = 600000
+    dom, ctx = synth.generate("loopnest16x24p3", n, seed=2026)
+    db = api.DeviceBatch(dom, ctx, -1)
+    monkeypatch.setenv("PIPLIB_B200_DEVICE_PARTS", "1")
+    db.run(False)
+    one = api.last_stats()
+    st1, h1 = db.results(True)
+    for parts in ("6", "3"):
+        monkeypatch.setenv("PIPLIB_B200_DEVICE_PARTS", parts)
+        for rep in range(2):
+            ms = db.run(False)
+            s = api.last_stats()
+            st, h = db.results(True)
+            assert ms > 0 and np.array_equal(st, st1) and np.array_equal(h, h1)
+            assert s.launches >= 3 * int(parts) and abs(int(s.pivots) - int(one.pivots)) < int(one.pivots) // 1000
+    db.close()
+    r = api.solve_dense(dom[:50000], ctx[:50000], -1)
+    assert np.array_equal(st1[:50000], r["status"]) and np.array_equal(h1[:50000], r["hashes"])
+
+
 def test_large_tableau_kernel_fixtures(api):
     """grid-per-problem cooperative kernel on every non-parametric fixture (incl. 260 cuts)"""
     cases = [c for c in load_golden("cli_suite.json")
