@@ -20,7 +20,10 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 200 python tools/e2e_timing.py 262144 pinned > /dev/null 2>&1 && \
 PIPLIB_B200_LANES=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $o/launches_e2e_$tag.csv \
     python tools/e2e_timing.py 262144 pinned > $o/ncu_e2e_$tag.log 2>&1
-# one full capture of the solve kernel
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:pip_solve_kernel -c 1 -o $o/prof_solve_$tag -f \
+# the 10^6 device job as bench.py runs it (three parts on lanes of their own): launch list of one step
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $o/launches_1m_$tag.csv \
+    python tools/ncu_run.py loopnest16x24p3 1000000 1 > $o/ncu_l1m_$tag.log 2>&1
+# one full capture of the solve kernel (one launch, no hand-over: the kernel as the 10^6 job runs it)
+PIPLIB_B200_HEAVY_PIVOTS=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pip_solve_kernel -c 1 -o $o/prof_solve_$tag -f \
     python tools/ncu_run.py loopnest16x24p3 200000 1 > $o/ncu_solve_$tag.log 2>&1
 ls -la $o/prof_solve_$tag.ncu-rep $o/launches_$tag.csv $o/launches_e2e_$tag.csv
