@@ -135,14 +135,18 @@ void pip_free_pinned_dp(void *p);
 int pip_set_devices_dp(int n, const int *devices);
 
 /* Device-resident variant of the dense batch: converted and uploaded once by create(); run()
- * executes only kernels (plus the 56-byte-per-problem status records the size-class ladder
- * needs); the solution cells stay in HBM unless fetch_cells is set. */
+ * executes only kernels: with fetch_cells = 0 the whole device job (solve + decode to serialised quasts,
+ * statuses and hashes, all left in HBM; nothing per problem crosses PCIe unless a problem has to change
+ * size class), with fetch_cells = 1 solve + cell gather and the cells copied to the host.  A job of more
+ * than 2^19 problems is run in three parts on engine lanes of their own (the tail of a part -- its few
+ * largest trees -- is filled by the next part); device_ms is then the time from the first launch to the
+ * end of the last part. */
 typedef struct pip_device_batch pip_device_batch;
 pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_cols, const long long *dom,
                                           int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
                                           int bignum, const PipOptions_dp *options);
 int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms);
-/* results of the last run: status always; hashes only if that run fetched the cells */
+/* results of the last run: status always; hashes if that run decoded on the device (fetch_cells = 0) or fetched the cells */
 int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long long *hashes);
 void pip_device_batch_destroy(pip_device_batch *b);
 
