@@ -39,7 +39,7 @@ static cudaError_t pip_raise_dynamic_smem(K kernel, size_t bytes, size_t &high_w
 }
 static size_t g_smem_s32 = 0, g_smem_s64 = 0, g_smem_ws = 0, g_smem_team = 0, g_smem_s32_steal = 0, g_smem_s64_steal = 0;
 
-template <bool SH, class V, bool STEAL = false>
+template <bool SH, class V, bool STEAL = false, bool WORDS = false>
 __global__ void __launch_bounds__(PIP_CTA_THREADS, PIP_MIN_CTAS)
 pip_solve_kernel(const PipLaunch L)
 {
@@ -49,7 +49,7 @@ pip_solve_kernel(const PipLaunch L)
   pip_i64 *arena;
   if (SH) arena = (pip_i64 *)pip_smem + (size_t)warp_in_cta * L.work_words;
   else arena = L.gwork + (size_t)warp_id * L.work_words;
-  pip_warp_main<V, !SH, STEAL>(L, warp_id, arena, nullptr);   /* !SH: the global-memory code path */
+  pip_warp_main<V, !SH, STEAL, WORDS>(L, warp_id, arena, nullptr);   /* !SH: the global-memory code path */
 }
 
 /* size class M: one problem per CTA, arena in global memory.  Warp 0 runs the solver, the other
@@ -82,24 +82,22 @@ extern "C" cudaError_t pip_launch_solve(const PipLaunch *L, int shared_class, in
   if (shared_class == 1 || shared_class == 2) {
     size_t smem = (size_t)warps_per_cta * L->work_words * sizeof(pip_i64);
     cudaError_t e;
-    /* subtree donation (PipLaunch::steal) runs the instantiation that has it compiled in */
-    if (shared_class == 2 && L->steal.mode) {
-      e = pip_raise_dynamic_smem(pip_solve_kernel<true, int, true>, smem, g_smem_s32_steal);
-      if (e != cudaSuccess) return e;
-      pip_solve_kernel<true, int, true><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
-    } else if (shared_class == 2) {
-      e = pip_raise_dynamic_smem(pip_solve_kernel<true, int>, smem, g_smem_s32);
-      if (e != cudaSuccess) return e;
-      pip_solve_kernel<true, int><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
-    } else if (L->steal.mode) {
-      e = pip_raise_dynamic_smem(pip_solve_kernel<true, pip_i64, true>, smem, g_smem_s64_steal);
-      if (e != cudaSuccess) return e;
-      pip_solve_kernel<true, pip_i64, true><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
-    } else {
-      e = pip_raise_dynamic_smem(pip_solve_kernel<true, pip_i64>, smem, g_smem_s64);
-      if (e != cudaSuccess) return e;
-      pip_solve_kernel<true, pip_i64><<<ctas, warps_per_cta * 32, smem, stream>>>(*L);
-    }
+    /* subtree donation (PipLaunch::steal) runs the instantiation that has it compiled in (word mode only);
+     * word-mode launches the one without the cell emitters */
+#define PIP_LAUNCH_S(V_, ST_, WD_, hw_) do { \
+      e = pip_raise_dynamic_smem(pip_solve_kernel<true, V_, ST_, WD_>, smem, hw_); \
+      if (e != cudaSuccess) return e; \
+      pip_solve_kernel<true, V_, ST_, WD_><<<ctas, warps_per_cta * 32, smem, stream>>>(*L); } while (0)
+    static size_t hw_words32 = 0, hw_words64 = 0;
+    const bool words = L->emit_words != 0;
+    if (L->steal.mode && !words) return cudaErrorInvalidValue;
+    if (shared_class == 2 && L->steal.mode) PIP_LAUNCH_S(int, true, true, g_smem_s32_steal);
+    else if (shared_class == 2 && words) PIP_LAUNCH_S(int, false, true, hw_words32);
+    else if (shared_class == 2) PIP_LAUNCH_S(int, false, false, g_smem_s32);
+    else if (L->steal.mode) PIP_LAUNCH_S(pip_i64, true, true, g_smem_s64_steal);
+    else if (words) PIP_LAUNCH_S(pip_i64, false, true, hw_words64);
+    else PIP_LAUNCH_S(pip_i64, false, false, g_smem_s64);
+#undef PIP_LAUNCH_S
   } else if (shared_class == 4) {
     const size_t smem = (size_t)L->work_words * sizeof(pip_i64);
     cudaError_t e = pip_raise_dynamic_smem(pip_team_kernel, smem, g_smem_team);

@@ -187,7 +187,9 @@ PIP_DEV void pip_team_min(int *p, int v) { if (v < *p) *p = v; }
  * block is passed -- CTA-wide update and scans.  false = shared-memory classes (and the emulator). */
 /* STEAL = the instantiation with subtree donation compiled in (PipSteal): a separate kernel, because every
  * instruction added to the bulk kernel costs it throughput (instruction cache, section 4 of DESIGN.md) */
-template <class V, bool TEAM = false, bool STEAL = false>
+/* WORDS = every problem of the launch writes its serialised quast itself (PipLaunch::emit_words, word mode): the
+ * cell emitters are not compiled in, which makes the executed code denser (section 4 of DESIGN.md) */
+template <class V, bool TEAM = false, bool STEAL = false, bool WORDS = false>
 struct PipSolver {
 /* ---- small accessors ------------------------------------------------------------------- */
 PIP_SDEV int *pip_fl(pip_i64 *B, const PipTab &T) { return (int *)(B + T.fl); }
@@ -723,7 +725,9 @@ PIP_SDEV int pip_team_scan(PipTeam *tm, pip_i64 *B, const PipTab &T, int cmd, in
 }
 
 /* chercher(Minus) + exam_coef for a tableau of at most 32 positions: one register-resident pass
- * (source/traiter.c:669-680); returns the pivot row or nl */
+ * (source/traiter.c:669-680); returns the pivot row or nl.  (-DPIP_NO_SCAN32 builds without it: 160
+ * instructions less of executed code, but measured no faster once the layout luck of a build is averaged
+ * out -- profiles/r2_build_variants.log.) */
 PIP_SDEV int pip_scan32(pip_i64 *B, const PipTab &T, int bigparm)
 {
   const int lane = W::lane();
@@ -925,7 +929,14 @@ PIP_SDEV void pip_update_rows(pip_i64 *B, const PipTab &T, int pivi, int pivj, V
       const V *pr = prow;
       V *r = row;
       V *const rend = row + ncol;
+      /* (not unrolled: with unroll 2 / 4 the same build ran the 10^6 job in 124.3 / 128.8 ms instead of 119.9) */
+#if defined(PIP_UPD_UNROLL2)
       #pragma unroll 2
+#elif defined(PIP_UPD_UNROLL4)
+      #pragma unroll 4
+#else
+      #pragma unroll 1
+#endif
       for (; r != rend; r++, pr++) {
         const pip_i64 z = PipVal<V>::cross(*r, lpiv, *pr, foo);
         const int lo = (int)z, hi = (int)(z >> 32), sg = lo >> 31;
@@ -1589,7 +1600,7 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
                            PipCell *out, pip_i64 *stk, pip_i64 stk_cap,
                            int sol_size, int maxcol, int maxparm,
                            int &status_out, int &ncell_out, unsigned &rflags_out, PipStats &st, PipTeam *tm = nullptr,
-                           unsigned *nwords_out = nullptr, bool wordmode = false, const PipLayout *pre = nullptr,
+                           unsigned *nwords_out = nullptr, bool wordmode_arg = false, const PipLayout *pre = nullptr,
                            const PipSteal *stl = nullptr, int stl_problem = 0, int stl_seg = -1,
                            const pip_i64 *resume = nullptr, int *hwm_out = nullptr,
                            const pip_i64 *image = nullptr, int image_w1 = 0, unsigned budget = 0,
@@ -1597,6 +1608,7 @@ PIP_SDEV void pip_solve_one(const PipProblem &P, const void *pool, int elem_log2
 {
   const int lane = W::lane();
   const bool integer = (P.flags & PIP_F_INT) != 0;
+  const bool wordmode = WORDS || wordmode_arg;
   PipWordOut wo;
   wo.w = (V *)out; wo.pos = 0; wo.node_at = -1; wo.nnew = 0; wo.wide = false;
   PipLayout L;
@@ -1743,8 +1755,11 @@ ENTRY:
 LOOP:
   {
     const int nl = T.nvar + T.ni;
+#ifndef PIP_NO_SCAN32
     if (nl <= 32) pivi = pip_scan32(B, T, level ? -1 : P.bigparm);
-    else {
+    else
+#endif
+    {
       const int bg = level ? -1 : P.bigparm;
       if (TEAM && tm != nullptr && nl >= PIP_TEAM_MIN_SCAN) {
         pivi = pip_team_scan(tm, B, T, PIP_TEAM_FIRST, 0, PIP_MINUS, 0, nl);

@@ -9,7 +9,7 @@
 
 /* one unit of work: a problem (offer < 0) or a donated subtree of one (offer = index of the claimed PipOffer);
  * returns the window space consumed, in cells */
-template <class V, bool TEAM, bool STEAL>
+template <class V, bool TEAM, bool STEAL, bool WORDS = false>
 PIP_DEV pip_i64 pip_warp_unit(const PipLaunch &L, int warp_id, pip_i64 *arena, PipTeam *tm, PipCell *window, pip_i64 used,
                               pip_i64 *stk, int p, int offer, pip_i64 cpw)
 {
@@ -28,9 +28,9 @@ PIP_DEV pip_i64 pip_warp_unit(const PipLaunch &L, int warp_id, pip_i64 *arena, P
   int status = PIP_ST_OK, ncell = 0, hwm = 0;
   unsigned rflags = 0, nwords = 0;
   /* word mode (PipLaunch::emit_words): the solver writes the serialised quast itself into the window */
-  const bool wordmode = L.emit_words && (P.flags & PIP_F_SIMPLE_SER);
+  const bool wordmode = WORDS || (L.emit_words && (P.flags & PIP_F_SIMPLE_SER));   /* (WORDS: the host checked every problem) */
   const PipSteal *stl = (STEAL && wordmode && L.steal.mode) ? &L.steal : nullptr;
-  PipSolver<V, TEAM, STEAL>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
+  PipSolver<V, TEAM, STEAL, WORDS>::pip_solve_one(P, L.pool, L.pool_elem_log2, arena, L.work_words, L.slack_level, window + used, stk,
                 stk_cap, L.sol_size, L.maxcol, L.maxparm, status, ncell, rflags, st, tm, &nwords,
                 wordmode, L.have_layout ? &L.layout : nullptr, stl, p, offer,
                 (STEAL && offer >= 0) ? L.steal.offers[offer].frame : nullptr, STEAL ? &hwm : nullptr,
@@ -76,9 +76,19 @@ PIP_DEV pip_i64 pip_warp_unit(const PipLaunch &L, int warp_id, pip_i64 *arena, P
   return ncell;
 }
 
+/* one out-of-line copy of the unit for the donation instantiation: it is entered from three places (the problem
+ * loop, the test-mode drain, the idle loop), and inlining the solver three times made that kernel 15 000
+ * instructions long -- in a kernel bound by the instruction cache */
+template <class V, bool TEAM, bool STEAL, bool WORDS>
+PIP_DEVNI pip_i64 pip_warp_unit_shared(const PipLaunch &L, int warp_id, pip_i64 *arena, PipTeam *tm, PipCell *window, pip_i64 used,
+                                       pip_i64 *stk, int p, int offer, pip_i64 cpw)
+{
+  return pip_warp_unit<V, TEAM, STEAL, WORDS>(L, warp_id, arena, tm, window, used, stk, p, offer, cpw);
+}
+
 /* a claimed offer becomes segment `idx` of its problem: link it right after the donor's segment (later, inner
  * donations of the same donor thus come before earlier, outer ones: pre-order), then solve the subtree */
-template <class V>
+template <class V, bool WORDS = false>
 PIP_DEV pip_i64 pip_warp_steal(const PipLaunch &L, int warp_id, pip_i64 *arena, PipCell *window, pip_i64 used, pip_i64 *stk, int idx,
                                pip_i64 cpw)
 {
@@ -94,10 +104,10 @@ PIP_DEV pip_i64 pip_warp_steal(const PipLaunch &L, int warp_id, pip_i64 *arena, 
   }
   p = W::shfl(p, 0);
   W::sync();
-  return pip_warp_unit<V, false, true>(L, warp_id, arena, nullptr, window, used, stk, p, idx, cpw);
+  return pip_warp_unit_shared<V, false, true, WORDS>(L, warp_id, arena, nullptr, window, used, stk, p, idx, cpw);
 }
 
-template <class V, bool TEAM = false, bool STEAL = false>
+template <class V, bool TEAM = false, bool STEAL = false, bool WORDS = false>
 PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipTeam *tm = nullptr)
 {
   const int lane = W::lane();
@@ -130,7 +140,8 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
     q = (unsigned)W::shfl((int)q, 0);
     if (q >= nprob) break;
     const int p = order ? order[q] : (int)q;
-    used += pip_warp_unit<V, TEAM, STEAL>(L, warp_id, arena, tm, window, used, stk, p, -1, cpw);
+    if (STEAL) used += pip_warp_unit_shared<V, TEAM, STEAL, WORDS>(L, warp_id, arena, tm, window, used, stk, p, -1, cpw);
+    else used += pip_warp_unit<V, TEAM, STEAL, WORDS>(L, warp_id, arena, tm, window, used, stk, p, -1, cpw);
   }
   if (!STEAL || !L.steal.mode || !L.emit_words) return;
   const PipSteal &S = L.steal;
@@ -147,7 +158,7 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
       /* (one warp plays donor and thief: every unit gets its own slice of the frame stack, so that the frames
        * still on offer are not overwritten by the subtree being solved) */
       const pip_i64 slice = L.stack_words_per_warp / 64;
-      used += pip_warp_steal<V>(L, warp_id, arena, window, used, stk + (1 + (c % 63)) * slice, (int)c, cpw);
+      used += pip_warp_steal<V, WORDS>(L, warp_id, arena, window, used, stk + (1 + (c % 63)) * slice, (int)c, cpw);
     }
     return;
   }
@@ -175,7 +186,7 @@ PIP_DEV void pip_warp_main(const PipLaunch &L, int warp_id, pip_i64 *arena, PipT
     got = W::shfl(got, 0);
     if (got >= 0) {
       if (lane == 0) W::atomic_add(&S.ctl[PIP_STL_IDLE], 0xffffffffu);      /* idle-- */
-      used += pip_warp_steal<V>(L, warp_id, arena, window, used, stk, got, cpw);
+      used += pip_warp_steal<V, WORDS>(L, warp_id, arena, window, used, stk, got, cpw);
       if (lane == 0) W::atomic_add(&S.ctl[PIP_STL_IDLE], 1u);
       continue;
     }
