@@ -1628,14 +1628,14 @@ int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms)
           pin.n = P.n; pin.h_prob = b->C.prob.data() + P.first; pin.d_prob = b->d_prob + P.first;
           if (pin.h_decode) pin.h_decode = b->parm.data() + P.first;
           pin.overlapped = q + 1 < b->parts.size();
-          while (turn.load() != (int)q) std::this_thread::yield();
-          PipEngine &E = PipEngine::at(b->device, (int)q);
-          std::thread next([&] { std::this_thread::sleep_for(std::chrono::microseconds(400)); turn.store((int)q + 1); });
-          E.run(pin, P.out);
-          next.join();
+          /* part q enters its engine 400 us after part q - 1 did (its launches are queued behind) */
+          while (turn.load() < (int)q) std::this_thread::yield();
+          if (q) std::this_thread::sleep_for(std::chrono::microseconds(400));
+          turn.store((int)q + 1);
+          PipEngine::at(b->device, (int)q).run(pin, P.out);
         } catch (const std::exception &e) {
           P.error = e.what();
-          turn.store((int)q + 1);
+          if (turn.load() <= (int)q) turn.store((int)q + 1);
         }
       };
       std::vector<std::thread> th;
