@@ -146,7 +146,8 @@ pip_device_batch *pip_device_batch_create(long long n, int dom_rows, int dom_col
                                           int has_ctx, int ctx_rows, int ctx_cols, const long long *ctx,
                                           int bignum, const PipOptions_dp *options);
 int pip_device_batch_run(pip_device_batch *b, int fetch_cells, float *device_ms);
-/* results of the last run: status always; hashes if that run decoded on the device (fetch_cells = 0) or fetched the cells */
+/* results of the last run: status always; hashes if that run decoded on the device (fetch_cells = 0) or fetched the cells.
+ * They are read out of the engines' buffers in HBM: call it before the next solve on the same device. */
 int pip_device_batch_results(pip_device_batch *b, int *status, unsigned long long *hashes);
 void pip_device_batch_destroy(pip_device_batch *b);
 
